@@ -1,0 +1,135 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by running the UNMODIFIED
+reference (/root/reference, imported through oracle/ref_harness.py) on seeded
+synthetic inputs.  Run in the build container only:
+
+    python -m oracle.make_golden
+
+Inputs and weights are drawn from numpy RandomState (bit-stable across boxes) by
+the same helpers the tests use, so the fixtures hold only seeds + reference
+OUTPUTS.  Reference classes exercised (file:line):
+  MelGanGenerator        featuresynth/generator/full.py:16-50
+  ResidualStack          featuresynth/util/modules.py:391-405
+  Audio2Mel              featuresynth/feature/feature.py:11-59
+  MelGanDiscriminator    featuresynth/discriminator/melgan.py:7-27
+  fft_frequency_*        featuresynth/audio/transform.py:50-115
+  loss functions         featuresynth/loss/loss.py:5-79
+  Generator/Discriminator trainers   featuresynth/train/train.py:26-74
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness, restate, bases, synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def main():
+    ref_harness.load()
+    from featuresynth.generator.full import MelGanGenerator
+    from featuresynth.util.modules import ResidualStack
+    from featuresynth.feature.feature import Audio2Mel
+    from featuresynth.discriminator.melgan import MelGanDiscriminator
+    from featuresynth.audio.transform import (
+        fft_frequency_decompose, fft_frequency_recompose)
+    from featuresynth.loss import loss as ref_loss
+
+    torch.set_grad_enabled(False)
+
+    # ---- MelGanGenerator: small (B2,T8), biased variant, and cfg1 (B1,T64)
+    for name, seed, B, T, biased in (("gen_b2_t8", 11, 2, 8, False),
+                                     ("gen_b2_t8_bias", 12, 2, 8, True),
+                                     ("gen_b3_t20_bias", 14, 3, 20, True),
+                                     ("gen_cfg1_b1_t64", 0, 1, 64, False)):
+        sd = restate.melgan_generator_state(seed)
+        if biased:
+            sd = restate.randomize_biases(sd, seed + 1000)
+        g = MelGanGenerator(T, 128).eval()
+        g.load_state_dict(sd)
+        x = synth.mel_features(seed, B, T)
+        y = g(x)
+        save(name, seed=seed, B=B, T=T, biased=int(biased), y=y.numpy())
+
+    # ---- ResidualStack alone
+    for C, L, seed in ((32, 96, 21), (128, 64, 22)):
+        rs = ResidualStack(C, [1, 3, 9]).eval()
+        sd = synth.residual_stack_state(seed, C)
+        rs.load_state_dict({k[len("s."):]: v for k, v in sd.items()})
+        x = synth.randn(seed + 1, 2, C, L)
+        save(f"resstack_c{C}", seed=seed, C=C, L=L, y=rs(x).numpy())
+
+    # ---- Audio2Mel
+    a2m = Audio2Mel(1024, 256, 1024, 22050, 128)
+    save("mel_basis_22050_1024_128", mel_basis=a2m.mel_basis.numpy(),
+         window=a2m.window.numpy())
+    for name, seed, B, N in (("a2m_b2_n16384", 31, 2, 16384),
+                             ("a2m_b3_n4000", 32, 3, 4000)):
+        a = synth.uniform_audio(seed, B, N)
+        save(name, seed=seed, B=B, N=N, y=a2m(a).numpy())
+
+    # ---- MelGanDiscriminator (shared-weight, 3 scales)
+    d = MelGanDiscriminator().eval()
+    sd = restate.randomize_biases(restate.melgan_discriminator_state(41), 1041)
+    d.load_state_dict(sd)
+    x = synth.randn(42, 2, 1, 4096) * 0.1
+    feats, judg = d(x)
+    arrays = {"seed": 41, "N": 4096}
+    for s, (fl, j) in enumerate(zip(feats, judg)):
+        arrays[f"j{s}"] = j.numpy()
+        for i, f in enumerate(fl):
+            arrays[f"f{s}_{i}_shape"] = np.array(f.shape)
+            arrays[f"f{s}_{i}_sub"] = f.numpy().reshape(-1)[::37]
+            arrays[f"f{s}_{i}_abs_mean"] = f.abs().mean().item()
+    save("disc_melgan_n4096", **arrays)
+
+    # ---- losses (loss.py) on the discriminator outputs above vs a second input
+    x2 = synth.randn(43, 2, 1, 4096) * 0.1
+    feats2, judg2 = d(x2)
+    save("losses_melgan",
+         disc_hinge=ref_loss.mel_gan_disc_loss(judg, judg2).item(),
+         disc_lsq=ref_loss.mel_gan_disc_loss(
+             judg, judg2, gan_loss=ref_loss.least_squares_disc_loss).item(),
+         feature=ref_loss.mel_gan_feature_loss(feats, feats2).item(),
+         gen_hinge=ref_loss.mel_gan_gen_loss(feats, feats2, judg, judg2).item(),
+         gen_lsq=ref_loss.mel_gan_gen_loss(
+             feats, feats2, judg, judg2,
+             gan_loss=ref_loss.least_squares_generator_loss).item())
+
+    # ---- FFT band split / merge
+    x = synth.randn(51, 2, 1, 8192) * 0.1
+    bands = fft_frequency_decompose(x, 512)
+    rec = fft_frequency_recompose(bands, 8192)
+    arrays = {"seed": 51, "N": 8192, "min_size": 512, "recomposed": rec.numpy()}
+    for k, v in bands.items():
+        arrays[f"band_{k}"] = v.numpy()
+    save("fft_bands_n8192", **arrays)
+
+    # ---- Morlet filter bank analysis / synthesis (zounds restatement; the bank
+    #      tensor itself is part of the fixture because its construction is unpinned)
+    import zounds
+    from featuresynth.generator.multiscale import FilterBankMultiScaleGenerator
+    fbg = FilterBankMultiScaleGenerator(zounds.SR22050(), 128, 32, 8192,
+                                        recompose=False)
+    fb = fbg.channel_generators[8192].filter_bank
+    x = synth.randn(61, 2, 1, 1024) * 0.1
+    conv = fb.convolve(x)
+    back = fb.transposed_convolve(conv)
+    save("filterbank_n1024", seed=61, bank=fb.filter_bank.numpy(),
+         conv_sub=conv.numpy().reshape(-1)[::29], conv_shape=np.array(conv.shape),
+         back=back.numpy())
+
+
+if __name__ == "__main__":
+    main()

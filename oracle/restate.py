@@ -1,0 +1,276 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product path.
+
+CPU restatement (torch fp32 on host cores) of the reference's stage-two hot path.
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / reference
+arm may import this file, and only as the checker / reported CPU baseline.
+
+Each function states the reference file:line it follows.  The restatement is
+functional (explicit state dicts, no nn.Module) so that it shares no code with
+either the reference or the product's module mirrors.
+
+Pinning: `tests/test_oracle_golden.py` checks every function here against the
+fixtures in `tests/golden/` which were produced by running the UNMODIFIED
+reference through `oracle/ref_harness.py` (`oracle/make_golden.py`, committed).
+The reference itself holds no golden vectors for this path.
+"""
+import math
+
+import torch
+from torch.nn import functional as F
+
+
+def leaky(x):
+    return F.leaky_relu(x, 0.2)
+
+
+# ------------------------------------------------------------------ Audio2Mel
+def audio2mel(audio, mel_basis, window, n_fft=1024, hop_length=256):
+    """featuresynth/feature/feature.py:39-59 (Audio2Mel.forward).
+
+    audio (B,1,N) -> right zero-pad (n_fft-hop)//2 -> STFT(center=False, one-sided)
+    -> magnitude -> mel_basis @ mag -> log10(clamp(., 1e-5)).  (B, n_mels, F),
+    F = (N + p - n_fft)//hop + 1.
+    """
+    p = (n_fft - hop_length) // 2
+    a = F.pad(audio, (0, p)).squeeze(1)
+    frames = a.unfold(-1, n_fft, hop_length)                     # (B, F, n_fft)
+    spec = torch.fft.rfft(frames * window, dim=-1)               # (B, F, bins)
+    mag = torch.sqrt(spec.real ** 2 + spec.imag ** 2).transpose(1, 2)
+    mel = torch.matmul(mel_basis, mag)
+    return torch.log10(torch.clamp(mel, min=1e-5))
+
+
+# ------------------------------------------------------------- residual blocks
+def residual_atom(x, w1, b1, w2, b2, dilation):
+    """featuresynth/util/modules.py:350-388 (ResidualAtom.forward):
+    x + leaky(conv_k3_pad1(leaky(conv_k3_dil_d_pad_d(x))))."""
+    y = leaky(F.conv1d(x, w1, b1, dilation=dilation, padding=dilation))
+    y = leaky(F.conv1d(y, w2, b2, padding=1))
+    return x + y
+
+
+def residual_stack(x, sd, prefix, dilations=(1, 3, 9)):
+    """featuresynth/util/modules.py:391-405 (ResidualStack)."""
+    for a, d in enumerate(dilations):
+        x = residual_atom(
+            x,
+            sd[f"{prefix}.main.{a}.main.0.weight"], sd[f"{prefix}.main.{a}.main.0.bias"],
+            sd[f"{prefix}.main.{a}.main.1.weight"], sd[f"{prefix}.main.{a}.main.1.bias"],
+            d)
+    return x
+
+
+# ------------------------------------------------------------- MelGanGenerator
+MELGAN_UPSAMPLERS = ((3, 5, 8, 4), (6, 8, 8, 4), (9, 11, 2, 1), (12, 14, 2, 1))
+
+
+def melgan_generator(x, sd):
+    """featuresynth/generator/full.py:16-50 (MelGanGenerator; weight_norm is the
+    identity there, full.py:12-13).  x (B,128,T) -> (B,1,256T)."""
+    x = F.pad(x, (3, 3), mode="reflect")
+    x = leaky(F.conv1d(x, sd["main.1.weight"], sd["main.1.bias"]))
+    for ct, st, s, p in MELGAN_UPSAMPLERS:
+        x = leaky(F.conv_transpose1d(
+            x, sd[f"main.{ct}.weight"], sd[f"main.{ct}.bias"], stride=s, padding=p))
+        x = residual_stack(x, sd, f"main.{st}")
+    x = F.conv1d(x, sd["main.15.weight"], sd["main.15.bias"], padding=3)
+    return torch.tanh(x)
+
+
+def melgan_generator_state(seed, in_channels=128):
+    """Random-init weights of MelGanGenerator as experiment/init.py:3-9 leaves
+    them (weight ~ N(0, 0.02), bias = 0), drawn from a *numpy* RandomState so
+    that the fixture generator, the oracle tests and the GPU tests regenerate
+    bit-identical tensors on any box."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+
+    def w(*shape):
+        return torch.from_numpy((rs.standard_normal(shape) * 0.02).astype(np.float32))
+
+    sd = {}
+    sd["main.1.weight"] = w(512, in_channels, 7)
+    sd["main.1.bias"] = torch.zeros(512)
+    chans = {3: (512, 256, 16), 6: (256, 128, 16), 9: (128, 64, 4), 12: (64, 32, 4)}
+    for ct, st, s, p in MELGAN_UPSAMPLERS:
+        cin, cout, k = chans[ct]
+        sd[f"main.{ct}.weight"] = w(cin, cout, k)
+        sd[f"main.{ct}.bias"] = torch.zeros(cout)
+        for a in range(3):
+            for c in range(2):
+                sd[f"main.{st}.main.{a}.main.{c}.weight"] = w(cout, cout, 3)
+                sd[f"main.{st}.main.{a}.main.{c}.bias"] = torch.zeros(cout)
+    sd["main.15.weight"] = w(1, 32, 7)
+    sd["main.15.bias"] = torch.zeros(1)
+    return sd
+
+
+def randomize_biases(sd, seed, std=0.01):
+    """Non-zero biases so parity tests exercise the bias path (the reference
+    init zeroes them; trained checkpoints do not)."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    out = dict(sd)
+    for k in sorted(sd):
+        if k.endswith("bias"):
+            out[k] = torch.from_numpy(
+                (rs.standard_normal(tuple(sd[k].shape)) * std).astype(np.float32))
+    return out
+
+
+# -------------------------------------------------------------- discriminators
+FULL_DISC_LAYERS = (
+    # (index, stride, padding, groups)   featuresynth/discriminator/full.py:13-20
+    (0, 1, 7, 1), (1, 4, 20, 4), (2, 4, 20, 16), (3, 4, 20, 64), (4, 4, 20, 256),
+    (5, 1, 2, 1),
+)
+
+
+def full_discriminator(x, sd, prefix="disc"):
+    """featuresynth/discriminator/full.py:34-40 (FullDiscriminator.forward)."""
+    feats = []
+    for i, s, p, g in FULL_DISC_LAYERS:
+        x = leaky(F.conv1d(x, sd[f"{prefix}.main.{i}.weight"],
+                           sd[f"{prefix}.main.{i}.bias"], stride=s, padding=p, groups=g))
+        feats.append(x)
+    j = F.conv1d(x, sd[f"{prefix}.judge.weight"], sd[f"{prefix}.judge.bias"], padding=1)
+    return feats, j
+
+
+def melgan_discriminator(x, sd, scales=2):
+    """featuresynth/discriminator/melgan.py:13-27: ONE shared FullDiscriminator
+    at 3 scales, avg_pool1d(k4, s2, p2) (count_include_pad=True) between."""
+    features, judgements = [], []
+    f, j = full_discriminator(x, sd)
+    features.append(f)
+    judgements.append(j)
+    for _ in range(scales):
+        x = F.avg_pool1d(x, kernel_size=4, stride=2, padding=2)
+        f, j = full_discriminator(x, sd)
+        features.append(f)
+        judgements.append(j)
+    return features, judgements
+
+
+def melgan_discriminator_state(seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+
+    def w(*shape):
+        return torch.from_numpy((rs.standard_normal(shape) * 0.02).astype(np.float32))
+
+    shapes = {0: (16, 1, 15), 1: (64, 4, 41), 2: (256, 4, 41), 3: (1024, 4, 41),
+              4: (1024, 4, 41), 5: (1024, 1024, 5)}
+    sd = {}
+    for i, shp in shapes.items():
+        sd[f"disc.main.{i}.weight"] = w(*shp)
+        sd[f"disc.main.{i}.bias"] = torch.zeros(shp[0])
+    sd["disc.judge.weight"] = w(1, 1024, 3)
+    sd["disc.judge.bias"] = torch.zeros(1)
+    return sd
+
+
+# ---------------------------------------------------------------------- losses
+def hinge_generator_loss(j):
+    """featuresynth/loss/loss.py:9-10."""
+    return (-j).mean()
+
+
+def hinge_discriminator_loss(r_j, f_j):
+    """featuresynth/loss/loss.py:17-18."""
+    return (F.relu(1 - r_j) + F.relu(1 + f_j)).mean()
+
+
+def least_squares_generator_loss(j):
+    """featuresynth/loss/loss.py:5-6."""
+    return 0.5 * ((j - 1) ** 2).mean()
+
+
+def least_squares_disc_loss(r_j, f_j):
+    """featuresynth/loss/loss.py:13-14."""
+    return 0.5 * (((r_j - 1) ** 2).mean() + (f_j ** 2).mean())
+
+
+def mel_gan_disc_loss(real_judgements, fake_judgements,
+                      gan_loss=hinge_discriminator_loss):
+    """featuresynth/loss/loss.py:21-25."""
+    return sum(gan_loss(r, f) for r, f in zip(real_judgements, fake_judgements))
+
+
+def mel_gan_feature_loss(real_features, fake_features):
+    """featuresynth/loss/loss.py:28-65: sum over discriminators and layers of
+    (1/n_disc)(1/n_layers) * mean |r - f|."""
+    loss = 0
+    nd = 1 / len(real_features)
+    for r_group, f_group in zip(real_features, fake_features):
+        nl = 1 / len(r_group)
+        for r_f, f_f in zip(r_group, f_group):
+            loss = loss + (nl * nd) * F.l1_loss(r_f, f_f)
+    return loss
+
+
+def mel_gan_gen_loss(real_features, fake_features, real_judgements,
+                     fake_judgements, gan_loss=hinge_generator_loss,
+                     feature_loss_weight=10):
+    """featuresynth/loss/loss.py:68-79."""
+    j_loss = sum(gan_loss(f) for _, f in zip(real_judgements, fake_judgements))
+    return j_loss + feature_loss_weight * mel_gan_feature_loss(
+        real_features, fake_features)
+
+
+# ------------------------------------------------- FFT multiscale band split/merge
+def fft_frequency_decompose(x, min_size):
+    """featuresynth/audio/transform.py:50-82: ortho rFFT; band of size S keeps
+    bins [S/4, S/2] (the lowest keeps [0, S/2]); ortho irFFT at length S."""
+    coeffs = torch.fft.rfft(x, norm="ortho")
+    out = {}
+    size = min_size
+    while size <= x.shape[-1]:
+        sl = coeffs[..., :size // 2 + 1].clone()
+        if size > min_size:
+            sl[..., :size // 4] = 0
+        out[size] = torch.fft.irfft(sl, n=size, norm="ortho")
+        size *= 2
+    return out
+
+
+def fft_resample(x, desired_size, is_lowest_band):
+    """featuresynth/audio/transform.py:85-104."""
+    coeffs = torch.fft.rfft(x, norm="ortho")
+    n = coeffs.shape[-1]
+    new = torch.zeros(x.shape[0], x.shape[1], desired_size // 2 + 1,
+                      dtype=coeffs.dtype)
+    if is_lowest_band:
+        new[..., :n] = coeffs
+    else:
+        new[..., n // 2:n] = coeffs[..., n // 2:]
+    return torch.fft.irfft(new, n=desired_size, norm="ortho")
+
+
+def fft_frequency_recompose(d, desired_size):
+    """featuresynth/audio/transform.py:107-115."""
+    first = min(d.keys())
+    return sum(fft_resample(b, desired_size, s == first) for s, b in d.items())
+
+
+# -------------------------------------------------------- Morlet filter bank ops
+def filterbank_convolve(x, bank):
+    """zounds FilterBank.convolve as used at discriminator/multiscale.py:112:
+    conv1d(x(B,1,L), bank(n,1,k), padding=k//2) -> (B,n,L+1) for even k."""
+    k = bank.shape[-1]
+    return F.conv1d(x.view(-1, 1, x.shape[-1]), bank, padding=k // 2)
+
+
+def filterbank_transposed_convolve(x, bank):
+    """zounds FilterBank.transposed_convolve as used at generator/multiscale.py:91:
+    conv_transpose1d(x(B,n,L+1), bank(n,1,k), padding=k//2) -> (B,1,L)."""
+    k = bank.shape[-1]
+    return F.conv_transpose1d(x, bank, padding=k // 2)
+
+
+# ---------------------------------------------------------------- FLOP counting
+MELGAN_FLOP_PER_SAMPLE = 409536  # SURVEY.md App. A.1 (2 x MAC, conv/convT only)
+
+
+def melgan_generator_flops(batch, frames):
+    return MELGAN_FLOP_PER_SAMPLE * batch * frames * 256
