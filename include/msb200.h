@@ -1,0 +1,159 @@
+/* msb200 -- C ABI of the B200-native stage-two waveform-synthesis hot path.
+ *
+ * The reference (JohnVinyard/music-synthesis) is pure Python/PyTorch: it has NO FFI
+ * layer for this path; its "plugin boundary" is torch.nn.Module.forward.  The entry
+ * points below are therefore what a binding for each hot-path module would call;
+ * every function names the reference interface (file:line under /root/reference)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures: device pointers are `void*` /
+ *     `float*`, the CUDA stream is passed as `void*` (a cudaStream_t / CUstream).
+ *   - the caller owns all memory and the stream; the library never allocates device
+ *     memory, never synchronises, and keeps no global state (thread-safe).
+ *   - every function returns MS_OK (0) or a negative ms_status; ms_strerror()
+ *     describes it.  There is NO CPU fallback: without a sm_100 device every compute
+ *     entry point returns MS_ERR_CUDA.
+ *
+ * Device tensor layouts
+ *   NCL f32   : (B, C, L) contiguous fp32 -- the reference's tensor layout.
+ *   BLK f16   : (B, C/8, L, 8) fp16  -- "channel-blocked": 16-byte vectors of 8
+ *               consecutive channels, time-major inside a block.  Operand layout of
+ *               the tcgen05 implicit GEMM (any row shift = +16 bytes, no swizzle).
+ *   BLK f32   : (B, C/8, L, 8) fp32  -- the fp32 residual stream, same blocking.
+ */
+#ifndef MSB200_H
+#define MSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int ms_status;
+enum {
+  MS_OK = 0,
+  MS_ERR_INVALID = -1,   /* bad descriptor / unsupported shape */
+  MS_ERR_CUDA = -2,      /* CUDA runtime error (see ms_last_cuda_error) */
+  MS_ERR_WORKSPACE = -3  /* workspace too small */
+};
+
+int ms_version(void);
+const char* ms_strerror(ms_status s);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char* ms_last_cuda_error(void);
+/* number of kernels this library has launched in this process (all threads);
+ * used by bench.py for its gpu_launches claim */
+uint64_t ms_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Dense 1-D convolution / transposed convolution as a tcgen05 implicit GEMM.
+ *   replaces F.conv1d / F.conv_transpose1d as dispatched from
+ *     featuresynth/generator/full.py:24,27,31,35,39        (MelGanGenerator trunk)
+ *     featuresynth/util/modules.py:358-365,384-388         (ResidualAtom)
+ *     featuresynth/util/modules.py:178-184                 (LearnedUpSample)
+ *     featuresynth/discriminator/full.py:19 (1024->1024 k5)
+ *   kind MS_CONV     : stride-1 conv, `ksize` taps, `dilation`, zero padding `pad`
+ *                      (pad may be 0 for a pre-padded input): Lout = Lin + 2*pad
+ *                      - dilation*(ksize-1).
+ *   kind MS_CONVT    : ConvTranspose1d with ksize == 2*stride, padding `pad`
+ *                      (1 <= pad <= stride): Lout = stride*Lin + ksize - stride
+ *                      - 2*pad ... for the reference's (16,8,4),(4,2,1),(8,4,2)
+ *                      this is stride*Lin.  Computed in polyphase form (2 taps at the
+ *                      input rate, N = stride*Cout) so there is no overlap-add.
+ *   epilogue         : y = act(alpha * acc + bias) [+ res32]; act = LeakyReLU(0.2)
+ *                      when `leaky` != 0.  Writes BLK f16 (y16) and/or BLK f32 (y32).
+ *   operands         : fp16 (default) or bf16, fp32 accumulate in tensor memory.
+ * ------------------------------------------------------------------------- */
+enum { MS_CONV = 0, MS_CONVT = 1 };
+enum { MS_F16 = 0, MS_BF16 = 1 };
+
+typedef struct {
+  int kind;      /* MS_CONV | MS_CONVT */
+  int batch;     /* B */
+  int cin;       /* multiple of 16 */
+  int cout;      /* multiple of 8 (MS_CONV: multiple of 16) */
+  int lin;       /* input length */
+  int ksize;     /* taps (MS_CONVT: == 2*stride) */
+  int dilation;  /* MS_CONV only */
+  int pad;       /* zero padding (both sides) */
+  int stride;    /* MS_CONVT only (MS_CONV: must be 1) */
+  int leaky;     /* 1: LeakyReLU(0.2) in the epilogue */
+  int operand;   /* MS_F16 | MS_BF16 */
+  float alpha;   /* accumulator scale (1.0f normally) */
+} ms_conv_desc;
+
+/* output length for a descriptor (or <0 on invalid) */
+int ms_conv_out_len(const ms_conv_desc* d);
+/* bytes of the packed (tile-ordered, 16-bit) weight image for this descriptor */
+size_t ms_conv_packed_weight_bytes(const ms_conv_desc* d);
+/* pack fp32 weights in the reference layout -- (Cout,Cin,K) for MS_CONV,
+ * (Cin,Cout,K) for MS_CONVT, i.e. nn.Conv1d.weight / nn.ConvTranspose1d.weight --
+ * into the packed 16-bit image (device to device). */
+ms_status ms_conv_pack_weight(const ms_conv_desc* d, const float* w_f32, void* w_packed,
+                              void* stream);
+/* x16: BLK f16 (B,cin/8,lin,8); bias: fp32 [cout] or NULL; res32: BLK f32
+ * (B,cout/8,Lout,8) or NULL; y16 / y32: outputs, either may be NULL. */
+ms_status ms_conv_fwd(const ms_conv_desc* d, const void* x16, const void* w_packed,
+                      const float* bias, const float* res32, void* y16, float* y32,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Layout conversion at the path boundary.
+ *   ms_pack_ncl_to_blk16: NCL f32 (B,C,L) -> BLK 16-bit (B,C/8,L+2*pad,8) with
+ *     reflection (pad_mode 1: nn.ReflectionPad1d, generator/full.py:23) or zero
+ *     (pad_mode 0) padding baked in.  C multiple of 8.
+ *   ms_unpack_blk32_to_ncl: BLK f32 -> NCL f32 (feature maps handed back to torch).
+ * ------------------------------------------------------------------------- */
+ms_status ms_pack_ncl_to_blk16(const float* x, void* y16, int batch, int channels,
+                               int len, int pad, int pad_mode, int operand, void* stream);
+ms_status ms_unpack_blk32_to_ncl(const float* x32, float* y, int batch, int channels,
+                                 int len, void* stream);
+ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int channels,
+                                 int len, int operand, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Single-output-channel conv + optional tanh, fp32 CUDA-core path.
+ *   replaces Conv1d(32,1,7,1,3) + Tanh at generator/full.py:43-44 and the judge
+ *   convs (1024->1 k3) at discriminator/full.py:22.
+ *   x32: BLK f32 (B,cin/8,L,8); w: fp32 (1,cin,ksize) reference layout; y: (B,1,L).
+ * ------------------------------------------------------------------------- */
+ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, float* y,
+                          int batch, int cin, int len, int ksize, int pad, int tanh_out,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Whole MelGanGenerator forward (inference), features -> waveform.
+ *   replaces MelGanGenerator.forward, featuresynth/generator/full.py:47-50
+ *   (layer list 22-45; ResidualStack util/modules.py:391-405).
+ *   `weights` is the packed parameter blob produced by ms_melgan_pack_weights from
+ *   the 60 state-dict tensors in state-dict order.
+ *   x: NCL f32 (B,128,T) ; y: NCL f32 (B,1,256*T).
+ * ------------------------------------------------------------------------- */
+#define MS_MELGAN_NUM_PARAMS 60
+size_t ms_melgan_packed_weight_bytes(int in_channels, int operand);
+ms_status ms_melgan_pack_weights(const float* const* params /* 60 device ptrs */,
+                                 int in_channels, int operand, void* packed, void* stream);
+size_t ms_melgan_workspace_bytes(int batch, int frames, int in_channels);
+ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, int operand,
+                                  const float* x, float* y, int batch, int frames,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Audio2Mel: right zero-pad (n_fft-hop)/2, frame (n_fft=1024, hop), Hann window,
+ * real FFT, magnitude, mel projection, log10(clamp(.,1e-5)) -- one fused kernel.
+ *   replaces Audio2Mel.forward, featuresynth/feature/feature.py:39-59.
+ *   audio: (B,1,N) f32; window: (1024) f32; mel_basis: (n_mels,513) f32;
+ *   out: (B,n_mels,F) f32 with F = (N + 384 - 1024)/hop + 1.
+ * ------------------------------------------------------------------------- */
+int ms_audio2mel_frames(int samples, int n_fft, int hop);
+ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float* mel_basis,
+                           float* out, int batch, int samples, int n_fft, int hop,
+                           int n_mels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSB200_H */

@@ -1,0 +1,185 @@
+// Audio2Mel in one fused kernel: right zero-pad -> framing -> window -> real FFT ->
+// magnitude -> mel projection -> log10(clamp(., 1e-5)).
+//   replaces Audio2Mel.forward, featuresynth/feature/feature.py:39-59.
+//
+// fp32 throughout (the 1e-3 log-mel bar is a max-abs bar: bins with little energy make
+// 16-bit DFT operands unsafe).  One CTA handles 8 consecutive frames of
+// one clip: the 8 real frames are packed pairwise into 4 complex radix-2 FFTs in shared
+// memory (two real transforms for the price of one), magnitudes stay in shared memory,
+// and the mel basis is streamed once per CTA in coalesced 128x32 tiles and reused for
+// all 8 frames.  HBM traffic = audio in + log-mel out (+ the L2-resident basis).
+#include <math_constants.h>
+
+#include "runtime.cuh"
+
+namespace msb {
+
+constexpr int kFramesPerCta = 8;
+constexpr int kA2MThreads = 256;
+
+struct A2MParams {
+  const float* audio;   // (B, 1, N)
+  const float* window;  // (n_fft)
+  const float* basis;   // (n_mels, bins)
+  float* out;           // (B, n_mels, F)
+  int N, n_fft, log2n, hop, n_mels, bins, F, groups;
+};
+
+__global__ void __launch_bounds__(kA2MThreads)
+audio2mel_kernel(const A2MParams p) {
+  extern __shared__ float sm[];
+  const int n = p.n_fft;
+  const int bins = p.bins;
+  const int magld = bins + 3;           // row stride of the magnitude array
+  float* tw_c = sm;                     // [n/2]
+  float* tw_s = tw_c + n / 2;           // [n/2]
+  float* mag = tw_s + n / 2;            // [8][magld]
+  float* zr = mag + kFramesPerCta * magld;   // [4][n]   (re)  -- reused as basis tile
+  float* zi = zr + 4 * n;                    // [4][n]   (im)
+  float* tile = zr;                          // [128][33]
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x / p.groups;
+  const int f0 = (blockIdx.x % p.groups) * kFramesPerCta;
+  const float* a = p.audio + static_cast<size_t>(b) * p.N;
+
+  for (int i = tid; i < n / 2; i += kA2MThreads) {
+    float s, c;
+    sincospif(-2.0f * static_cast<float>(i) / static_cast<float>(n), &s, &c);
+    tw_c[i] = c;
+    tw_s[i] = s;
+  }
+  // load 8 windowed frames, bit-reversed, frame 2j -> real part, 2j+1 -> imaginary part
+  for (int i = tid; i < 4 * n; i += kA2MThreads) {
+    const int j = i / n;
+    const int t = i - j * n;
+    const int rev = static_cast<int>(__brev(static_cast<unsigned>(t)) >> (32 - p.log2n));
+    const float w = __ldg(p.window + t);
+    const int fa = f0 + 2 * j, fb = fa + 1;
+    const long long sa = static_cast<long long>(fa) * p.hop + t;
+    const long long sb = static_cast<long long>(fb) * p.hop + t;
+    const float va = (fa < p.F && sa < p.N) ? __ldg(a + sa) : 0.f;
+    const float vb = (fb < p.F && sb < p.N) ? __ldg(a + sb) : 0.f;
+    zr[j * n + rev] = va * w;
+    zi[j * n + rev] = vb * w;
+  }
+  __syncthreads();
+  // 4 in-place radix-2 DIT FFTs side by side
+  for (int s = 0; s < p.log2n; ++s) {
+    const int half = 1 << s;
+    const int tws = n >> (s + 1);
+    for (int i = tid; i < 2 * n; i += kA2MThreads) {   // 4 * n/2 butterflies
+      const int j = i / (n / 2);
+      const int bf = i - j * (n / 2);
+      const int pos = bf & (half - 1);
+      const int i0 = ((bf >> s) << (s + 1)) + pos + j * n;
+      const int i1 = i0 + half;
+      const float c = tw_c[pos * tws], sn = tw_s[pos * tws];
+      const float xr = zr[i1], xi = zi[i1];
+      const float tr = xr * c - xi * sn;
+      const float ti = xr * sn + xi * c;
+      const float ur = zr[i0], ui = zi[i0];
+      zr[i0] = ur + tr; zi[i0] = ui + ti;
+      zr[i1] = ur - tr; zi[i1] = ui - ti;
+    }
+    __syncthreads();
+  }
+  // untangle the two real spectra of each complex transform, take magnitudes
+  for (int i = tid; i < 4 * bins; i += kA2MThreads) {
+    const int j = i / bins;
+    const int k = i - j * bins;
+    const int kn = (n - k) & (n - 1);
+    const float ar = zr[j * n + k], ai = zi[j * n + k];
+    const float br = zr[j * n + kn], bi = zi[j * n + kn];
+    const float xar = 0.5f * (ar + br), xai = 0.5f * (ai - bi);
+    const float xbr = 0.5f * (ai + bi), xbi = -0.5f * (ar - br);
+    mag[(2 * j) * magld + k] = sqrtf(xar * xar + xai * xai);
+    mag[(2 * j + 1) * magld + k] = sqrtf(xbr * xbr + xbi * xbi);
+  }
+  __syncthreads();
+  // mel projection: thread (m, gh) accumulates frames gh*4 .. gh*4+3 of mel row m
+  const int ml = tid & 127;
+  const int gh = tid >> 7;
+  for (int mb = 0; mb < p.n_mels; mb += 128) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < bins; k0 += 32) {
+      // stage basis[mb .. mb+128)[k0 .. k0+32) : coalesced 128-byte row segments
+      for (int i = tid; i < 128 * 32; i += kA2MThreads) {
+        const int r = i >> 5, kk = i & 31;
+        const int m = mb + r, k = k0 + kk;
+        tile[r * 33 + kk] =
+            (m < p.n_mels && k < bins) ? __ldg(p.basis + static_cast<size_t>(m) * bins + k) : 0.f;
+      }
+      __syncthreads();
+      const int kmax = (bins - k0) < 32 ? (bins - k0) : 32;
+      const float* mg = mag + (gh * 4) * magld + k0;
+      for (int kk = 0; kk < kmax; ++kk) {
+        const float w = tile[ml * 33 + kk];
+        acc[0] = fmaf(w, mg[kk], acc[0]);
+        acc[1] = fmaf(w, mg[magld + kk], acc[1]);
+        acc[2] = fmaf(w, mg[2 * magld + kk], acc[2]);
+        acc[3] = fmaf(w, mg[3 * magld + kk], acc[3]);
+      }
+      __syncthreads();
+    }
+    const int m = mb + ml;
+    if (m < p.n_mels) {
+      float* o = p.out + (static_cast<size_t>(b) * p.n_mels + m) * p.F;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int f = f0 + gh * 4 + g;
+        if (f < p.F) o[f] = log10f(fmaxf(acc[g], 1e-5f));
+      }
+    }
+  }
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int ms_audio2mel_frames(int samples, int n_fft, int hop) {
+  if (samples <= 0 || n_fft <= 0 || hop <= 0 || hop > n_fft) return MS_ERR_INVALID;
+  const int padded = samples + (n_fft - hop) / 2;
+  if (padded < n_fft) return 0;
+  return (padded - n_fft) / hop + 1;
+}
+
+ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float* mel_basis,
+                           float* out, int batch, int samples, int n_fft, int hop, int n_mels,
+                           void* stream) {
+  if (audio == nullptr || window == nullptr || mel_basis == nullptr || out == nullptr ||
+      batch <= 0 || n_mels <= 0)
+    return MS_ERR_INVALID;
+  int log2n = 0;
+  while ((1 << log2n) < n_fft) ++log2n;
+  if ((1 << log2n) != n_fft || n_fft < 64 || n_fft > 2048) return MS_ERR_INVALID;
+  const int F = ms_audio2mel_frames(samples, n_fft, hop);
+  if (F < 0) return MS_ERR_INVALID;
+  if (F == 0) return MS_OK;
+  A2MParams p;
+  p.audio = audio; p.window = window; p.basis = mel_basis; p.out = out;
+  p.N = samples; p.n_fft = n_fft; p.log2n = log2n; p.hop = hop; p.n_mels = n_mels;
+  p.bins = n_fft / 2 + 1; p.F = F; p.groups = (F + kFramesPerCta - 1) / kFramesPerCta;
+  const size_t fft_floats = 8 * static_cast<size_t>(n_fft);
+  const size_t tile_floats = 128 * 33;
+  const size_t smem = sizeof(float) * (n_fft + kFramesPerCta * (p.bins + 3) +
+                                       (fft_floats > tile_floats ? fft_floats : tile_floats));
+  static thread_local size_t attr_set = 0;
+  if (smem > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(audio2mel_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(audio2mel_kernel)");
+    attr_set = smem;
+  }
+  const long long blocks = static_cast<long long>(batch) * p.groups;
+  if (blocks > 0x7fffffffLL) return MS_ERR_INVALID;
+  audio2mel_kernel<<<static_cast<unsigned>(blocks), kA2MThreads, smem,
+                     static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("audio2mel_kernel");
+}
+
+}  // extern "C"

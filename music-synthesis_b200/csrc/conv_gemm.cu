@@ -1,0 +1,469 @@
+// Dense 1-D (dilated / transposed) convolution as a tcgen05 implicit GEMM.
+//
+//   D[m, n] = sum_t sum_ci  X[m + off_t, ci] * W_t[n, ci]        (per clip)
+//
+// GEMM rows m are time steps (UMMA M = 128, TMEM lanes), columns n are output
+// channels (MS_CONV) or (phase, channel) pairs (MS_CONVT in polyphase form), K runs
+// over input channels, one pass per tap.  The A operand of tap t is the SAME staged
+// activation tile viewed with its start address advanced by (off_t - min_off) rows:
+// activations are kept channel-blocked (B, C/8, L, 8) so that a row is one 16-byte
+// vector, core matrices are 8 consecutive rows (128 contiguous bytes, SWIZZLE_NONE)
+// and any row shift is a +16-byte descriptor offset -- no im2col, no re-load per tap.
+//
+// Persistent CTAs (one per SM), warp-specialised:
+//   warp 0      producer: bulk async copies (TMA unit) global -> smem ring, zero-fills
+//               out-of-range rows (= the conv's zero padding) at clip edges
+//   warp 1      MMA issuer (one thread), owns the TMEM allocation
+//   warps 2-5   epilogue: tcgen05.ld -> alpha/bias/LeakyReLU/residual -> global
+// Accumulators are double-buffered in tensor memory so the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+//
+// Replaces F.conv1d / F.conv_transpose1d at featuresynth/generator/full.py:24-43 and
+// featuresynth/util/modules.py:358-388 (see include/msb200.h).
+#include "conv_gemm.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+// ---------------------------------------------------------------- configuration
+static int pick_nt(int ntot) {
+  for (int nt = 256; nt >= 16; nt -= 16)
+    if (ntot % nt == 0) return nt;
+  return 0;
+}
+
+bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
+  if (d.batch <= 0 || d.lin <= 0 || d.cin <= 0 || d.cout <= 0) return false;
+  if (d.cin % 16 != 0 || d.cout % 8 != 0) return false;
+  if (d.operand != MS_F16 && d.operand != MS_BF16) return false;
+  if (d.kind == MS_CONV) {
+    if (d.stride != 1 && d.stride != 0) return false;
+    if (d.ksize < 1 || d.ksize > kMaxTaps || d.dilation < 1 || d.pad < 0) return false;
+    if (d.cout % 16 != 0) return false;
+    c->taps = d.ksize;
+    for (int t = 0; t < d.ksize; ++t) c->off[t] = t * d.dilation - d.pad;
+    c->Ntot = d.cout;
+    c->Lout = d.lin + 2 * d.pad - d.dilation * (d.ksize - 1);
+    c->Lm = c->Lout;
+  } else if (d.kind == MS_CONVT) {
+    if (d.stride < 1 || d.ksize != 2 * d.stride) return false;
+    if (d.pad < 1 || d.pad > d.stride) return false;
+    c->taps = 2;
+    c->off[0] = -1;  // weight tap k = r + stride
+    c->off[1] = 0;   // weight tap k = r
+    c->Ntot = d.stride * d.cout;
+    if (c->Ntot % 16 != 0) return false;
+    c->Lout = (d.lin - 1) * d.stride - 2 * d.pad + d.ksize;
+    c->Lm = d.lin + 1;
+  } else {
+    return false;
+  }
+  if (c->Lout <= 0) return false;
+  int mn = c->off[0], mx = c->off[0];
+  for (int t = 1; t < c->taps; ++t) {
+    mn = c->off[t] < mn ? c->off[t] : mn;
+    mx = c->off[t] > mx ? c->off[t] : mx;
+  }
+  c->min_off = mn;
+  c->RA = 128 + mx - mn;
+  c->NT = pick_nt(c->Ntot);
+  if (c->NT == 0) return false;
+  c->KB = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
+  auto stage = [&](int kb, int nt) {
+    return (kb / 8) * c->RA * 16 + c->taps * (kb / 8) * nt * 16;
+  };
+  const int budget = kSmemBudget - kSmemHeader;
+  // want >= 3 stages when possible
+  while (stage(c->KB, c->NT) * 3 > budget && c->KB > 16) c->KB /= 2;
+  while (stage(c->KB, c->NT) * 2 > budget && c->NT > 16) {
+    int nt = c->NT - 16;
+    while (nt >= 16 && c->Ntot % nt != 0) nt -= 16;
+    if (nt < 16) return false;
+    c->NT = nt;
+  }
+  if (stage(c->KB, c->NT) * 2 > budget) return false;
+  c->nnt = c->Ntot / c->NT;
+  c->nkb = d.cin / c->KB;
+  c->mtiles = (c->Lm + 127) / 128;
+  c->a_stage_bytes = (c->KB / 8) * c->RA * 16;
+  c->w_stage_bytes = c->taps * (c->KB / 8) * c->NT * 16;
+  c->stage_bytes = (c->a_stage_bytes + c->w_stage_bytes + 127) / 128 * 128;
+  int s = budget / c->stage_bytes;
+  if (s > kMaxStages) s = kMaxStages;
+  int need = c->nkb * 2 > 2 ? c->nkb * 2 : 2;  // no point in more than 2 tiles in flight
+  if (s > need) s = need;
+  if (s < 2) return false;
+  c->stages = s;
+  int cols = 32;
+  while (cols < 2 * c->NT) cols *= 2;
+  c->tmem_cols = cols;
+  size_t smem = kSmemHeader + static_cast<size_t>(c->stages) * c->stage_bytes;
+  // always ask for more than half an SM's shared memory: one CTA per SM, so the
+  // 2*NT-column TMEM allocation can never contend with a co-resident CTA
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  c->smem_bytes = smem;
+  c->packed_weight_bytes = static_cast<size_t>(c->nnt) * c->nkb * c->w_stage_bytes;
+  return true;
+}
+
+// ------------------------------------------------------------------ the kernel
+__device__ __forceinline__ uint32_t pack2(float a, float b, int operand) {
+  if (operand == MS_BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_h2(a, b);
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // [0..7] full, [8..15] empty, [16..17] tmem_full, [18..19] tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  const uint32_t bar_base = smem_u32(bars);
+  const uint32_t data_base = smem_u32(smem + kSmemHeader);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (16 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (18 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks = p.KB >> 3;  // 16-byte channel chunks per k-block
+
+  if (warp == 0) {
+    // =============================== producer ===============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt_idx = tile % p.nnt;
+      const int rest = tile / p.nnt;
+      const int mt = rest % p.mtiles;
+      const int b = rest / p.mtiles;
+      const int r0 = mt * 128 + p.min_off;
+      const int lo = r0 < 0 ? 0 : r0;
+      const int hi = (r0 + p.RA) > p.lin ? p.lin : (r0 + p.RA);
+      const int nrows = hi > lo ? hi - lo : 0;
+      const bool ragged = (nrows != p.RA);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+        const uint32_t sW = sA + p.a_stage_bytes;
+        if (ragged) {
+          // rows outside [0, lin) are the convolution's zero padding
+          const int head = lo - r0;                    // rows [0, head)
+          const int tail0 = head + nrows;              // rows [tail0, RA)
+          const int nz = head + (p.RA - tail0);
+          for (int i = lane; i < nz * chunks; i += 32) {
+            const int c = i / nz;
+            int r = i - c * nz;
+            r = r < head ? r : tail0 + (r - head);
+            const uint32_t a = sA + static_cast<uint32_t>(c * p.RA + r) * 16u;
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+        }
+        if (lane == 0) {
+          const uint32_t bytes_a = static_cast<uint32_t>(nrows) * 16u * chunks;
+          mbar_arrive_expect_tx(full_bar(stage), bytes_a + p.w_stage_bytes);
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) +
+                                (static_cast<size_t>(nt_idx) * p.nkb + kb) * p.w_stage_bytes;
+          bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
+          if (nrows > 0) {
+            const size_t cbase = static_cast<size_t>(b) * (p.cin >> 3) + kb * chunks;
+            for (int c = 0; c < chunks; ++c) {
+              const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
+              bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,
+                       static_cast<uint32_t>(nrows) * 16u, full_bar(stage));
+            }
+          }
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(p.NT, p.operand);
+      const uint32_t lbo_a = static_cast<uint32_t>(p.RA) * 16u;
+      const uint32_t lbo_b = static_cast<uint32_t>(p.NT) * 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.NT);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint32_t sW = sA + p.a_stage_bytes;
+          for (int t = 0; t < p.taps; ++t) {
+            const uint32_t a_tap = sA + static_cast<uint32_t>(p.off[t] - p.min_off) * 16u;
+            const uint32_t w_tap = sW + static_cast<uint32_t>(t * chunks * p.NT) * 16u;
+            for (int k16 = 0; k16 < (p.KB >> 4); ++k16) {
+              const uint64_t ad =
+                  umma_desc_nosw(a_tap + static_cast<uint32_t>(2 * k16 * p.RA) * 16u, lbo_a, 128);
+              const uint64_t bd =
+                  umma_desc_nosw(w_tap + static_cast<uint32_t>(2 * k16 * p.NT) * 16u, lbo_b, 128);
+              umma_f16_ss(d_tmem, ad, bd, idesc, (kb | t | k16) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int cout8 = p.cout >> 3;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt_idx = tile % p.nnt;
+      const int rest = tile / p.nnt;
+      const int mt = rest % p.mtiles;
+      const int b = rest / p.mtiles;
+      const int m = mt * 128 + q * 32 + lane;
+      const int n0 = nt_idx * p.NT;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.NT);
+      for (int c0 = 0; c0 < p.NT; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.NT) {
+          // accumulator fully drained into registers: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n = n0 + c0 + h * 8;
+          int ch, orow;
+          bool valid = m < p.Lm;
+          if (p.kind == MS_CONVT) {
+            const int r = n / p.cout;
+            ch = n - r * p.cout;
+            orow = p.stride * m + r - p.pad;
+            valid = valid && orow >= 0 && orow < p.Lout;
+          } else {
+            ch = n;
+            orow = m;
+          }
+          if (!valid) continue;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[h * 8 + j]) * p.alpha;
+          if (p.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + 1);
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          if (p.leaky) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
+          }
+          const size_t idx = (static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + orow;
+          if (p.res32 != nullptr) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8));
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8) + 1);
+            f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+            f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+          }
+          if (p.y32 != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(p.y32 + idx * 8);
+            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+          if (p.y16 != nullptr) {
+            uint4 o;
+            o.x = pack2(f[0], f[1], p.operand);
+            o.y = pack2(f[2], f[3], p.operand);
+            o.z = pack2(f[4], f[5], p.operand);
+            o.w = pack2(f[6], f[7], p.operand);
+            *reinterpret_cast<uint4*>(p.y16 + idx * 8) = o;
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------ weight packing
+// packed[nt][kb][tap][chunk][nn][e]  <-  reference-layout fp32 weights
+__global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
+                                   int kind, int cin, int cout, int ksize, int stride,
+                                   int taps, int NT, int KB, int nnt, int nkb, int operand,
+                                   size_t total) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  size_t r = i;
+  const int e = r % 8; r /= 8;
+  const int nn = r % NT; r /= NT;
+  const int c = r % (KB / 8); r /= (KB / 8);
+  const int t = r % taps; r /= taps;
+  const int kb = r % nkb; r /= nkb;
+  const int nt = static_cast<int>(r);
+  const int n = nt * NT + nn;
+  const int ci = kb * KB + c * 8 + e;
+  float v;
+  if (kind == MS_CONV) {
+    v = w[(static_cast<size_t>(n) * cin + ci) * ksize + t];
+  } else {
+    const int ph = n / cout;
+    const int co = n - ph * cout;
+    const int kk = (t == 0) ? ph + stride : ph;
+    v = w[(static_cast<size_t>(ci) * cout + co) * ksize + kk];
+  }
+  if (operand == MS_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  } else {
+    __half h = __float2half_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+
+ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
+                      const void* w_packed, const float* bias, const float* res32, void* y16,
+                      float* y32, cudaStream_t stream) {
+  ConvGemmParams p;
+  p.x = static_cast<const uint16_t*>(x16);
+  p.w = static_cast<const uint16_t*>(w_packed);
+  p.bias = bias;
+  p.res32 = res32;
+  p.y16 = static_cast<uint16_t*>(y16);
+  p.y32 = y32;
+  p.B = d.batch; p.cin = d.cin; p.lin = d.lin; p.cout = d.cout;
+  p.Lout = c.Lout; p.Lm = c.Lm;
+  p.taps = c.taps;
+  for (int t = 0; t < kMaxTaps; ++t) p.off[t] = t < c.taps ? c.off[t] : 0;
+  p.min_off = c.min_off; p.RA = c.RA;
+  p.Ntot = c.Ntot; p.NT = c.NT; p.KB = c.KB; p.nnt = c.nnt; p.nkb = c.nkb;
+  p.mtiles = c.mtiles;
+  p.stages = c.stages; p.a_stage_bytes = c.a_stage_bytes; p.w_stage_bytes = c.w_stage_bytes;
+  p.stage_bytes = c.stage_bytes; p.tmem_cols = c.tmem_cols;
+  p.kind = d.kind; p.stride = d.stride; p.pad = d.pad; p.leaky = d.leaky;
+  p.operand = d.operand; p.alpha = d.alpha;
+  const long long tiles = static_cast<long long>(d.batch) * c.mtiles * c.nnt;
+  if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
+  p.total_tiles = static_cast<int>(tiles);
+
+  static thread_local size_t attr_set = 0;
+  if (c.smem_bytes > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBudget);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_gemm_kernel)");
+    attr_set = kSmemBudget;
+  }
+  int sms = sm_count();
+  if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
+  int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  conv_gemm_kernel<<<grid, 192, c.smem_bytes, stream>>>(p);
+  return after_launch("conv_gemm_kernel");
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int ms_conv_out_len(const ms_conv_desc* d) {
+  ConvCfg c;
+  if (d == nullptr || !make_conv_cfg(*d, &c)) return MS_ERR_INVALID;
+  return c.Lout;
+}
+
+size_t ms_conv_packed_weight_bytes(const ms_conv_desc* d) {
+  ConvCfg c;
+  if (d == nullptr || !make_conv_cfg(*d, &c)) return 0;
+  return c.packed_weight_bytes;
+}
+
+ms_status ms_conv_pack_weight(const ms_conv_desc* d, const float* w_f32, void* w_packed,
+                              void* stream) {
+  ConvCfg c;
+  if (d == nullptr || w_f32 == nullptr || w_packed == nullptr || !make_conv_cfg(*d, &c))
+    return MS_ERR_INVALID;
+  const size_t total = c.packed_weight_bytes / 2;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
+  pack_weight_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      w_f32, static_cast<uint16_t*>(w_packed), d->kind, d->cin, d->cout, d->ksize, d->stride,
+      c.taps, c.NT, c.KB, c.nnt, c.nkb, d->operand, total);
+  return after_launch("pack_weight_kernel");
+}
+
+ms_status ms_conv_fwd(const ms_conv_desc* d, const void* x16, const void* w_packed,
+                      const float* bias, const float* res32, void* y16, float* y32,
+                      void* stream) {
+  ConvCfg c;
+  if (d == nullptr || x16 == nullptr || w_packed == nullptr || !make_conv_cfg(*d, &c))
+    return MS_ERR_INVALID;
+  if (y16 == nullptr && y32 == nullptr) return MS_ERR_INVALID;
+  auto misaligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; };
+  if (misaligned(x16) || misaligned(w_packed) || misaligned(bias) || misaligned(res32) ||
+      misaligned(y16) || misaligned(y32))
+    return MS_ERR_INVALID;
+  return launch_conv(*d, c, x16, w_packed, bias, res32, y16, y32,
+                     static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

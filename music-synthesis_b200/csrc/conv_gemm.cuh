@@ -1,0 +1,55 @@
+// Host-visible description of one tcgen05 implicit-GEMM convolution launch.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/msb200.h"
+
+namespace msb {
+
+constexpr int kMaxTaps = 8;
+constexpr int kMaxStages = 8;
+constexpr int kSmemHeader = 1024;          // barriers + tmem slot
+constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100
+
+// Tile configuration + derived geometry, a pure function of the descriptor so that
+// weight packing and the forward launch always agree.
+struct ConvCfg {
+  int taps;            // GEMM taps (MS_CONV: ksize; MS_CONVT: 2)
+  int off[kMaxTaps];   // input row of tap t for GEMM row m is m + off[t]
+  int min_off, RA;     // RA = 128 + max_off - min_off rows of A staged per tile
+  int Ntot;            // GEMM N (MS_CONV: cout; MS_CONVT: stride*cout)
+  int NT, KB;          // n-tile (columns per CTA tile), k-block (input channels per stage)
+  int nnt, nkb;        // Ntot/NT, cin/KB
+  int Lm;              // GEMM rows per clip (MS_CONV: Lout; MS_CONVT: lin+1)
+  int Lout;
+  int mtiles;          // ceil(Lm/128)
+  int a_stage_bytes, w_stage_bytes, stage_bytes;
+  int stages;
+  int tmem_cols;       // power of two >= 2*NT
+  size_t smem_bytes;
+  size_t packed_weight_bytes;
+};
+
+// returns false when the descriptor is unsupported
+bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* cfg);
+
+struct ConvGemmParams {
+  const uint16_t* x;    // BLK 16-bit (B, cin/8, lin, 8)
+  const uint16_t* w;    // packed
+  const float* bias;    // [cout] or null
+  const float* res32;   // BLK f32 (B, cout/8, Lout, 8) or null
+  uint16_t* y16;        // or null
+  float* y32;           // or null
+  int B, cin, lin, cout, Lout, Lm;
+  int taps;
+  int off[kMaxTaps];
+  int min_off, RA;
+  int Ntot, NT, KB, nnt, nkb, mtiles;
+  int stages, a_stage_bytes, w_stage_bytes, stage_bytes, tmem_cols;
+  int kind, stride, pad, leaky, operand;
+  float alpha;
+  int total_tiles;
+};
+
+}  // namespace msb

@@ -1,0 +1,218 @@
+// MelGanGenerator forward (inference): layer schedule over the tcgen05 conv kernels.
+//   replaces featuresynth/generator/full.py:16-50 (+ util/modules.py:350-405).
+//
+// Numerics: 16-bit operands (fp16 default), fp32 accumulation in tensor memory, and an
+// fp32 residual stream: each ResidualAtom output is kept in fp32 (BLK f32) for the next
+// skip connection and, rounded once, in 16-bit as the next conv's operand.  The final
+// 32->1 conv + tanh runs in fp32 on the fp32 stream.
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
+                      const void* w_packed, const float* bias, const float* res32, void* y16,
+                      float* y32, cudaStream_t stream);
+ms_status conv_to_mono(const float* x32, const float* w, const float* bias, float* y, int batch,
+                       int cin, int len, int ksize, int pad, int tanh_out, cudaStream_t stream);
+ms_status pack_ncl_to_blk16(const float* x, void* y16, int batch, int channels, int len,
+                            int pad, int pad_mode, int operand, cudaStream_t stream);
+
+namespace {
+
+struct GenLayer {
+  ms_conv_desc d;   // batch / lin filled per call
+  int w_param, b_param;
+  size_t w_off, b_off;
+  int role;         // 0 first conv, 1 upsampler, 2 atom conv1, 3 atom conv2
+  int len_mult;     // lin = len_mult * T (+6 for the first conv)
+};
+
+struct GenPlan {
+  std::vector<GenLayer> layers;
+  size_t final_w_off, final_b_off;
+  size_t total_bytes;
+};
+
+// (cin, cout, ksize, stride, pad) of the four upsamplers, generator/full.py:27-39
+const int kUp[4][5] = {{512, 256, 16, 8, 4}, {256, 128, 16, 8, 4}, {128, 64, 4, 2, 1},
+                       {64, 32, 4, 2, 1}};
+const int kDil[3] = {1, 3, 9};
+
+bool build_plan(int in_channels, int operand, GenPlan* plan) {
+  plan->layers.clear();
+  size_t off = 0;
+  int param = 0;
+  auto add = [&](ms_conv_desc d, int role, int len_mult) -> bool {
+    d.batch = 1;
+    d.lin = 1024;  // nominal: the tile config does not depend on batch / length
+    d.operand = operand;
+    d.alpha = 1.0f;
+    ConvCfg c;
+    if (!make_conv_cfg(d, &c)) return false;
+    GenLayer L;
+    L.d = d; L.role = role; L.len_mult = len_mult;
+    L.w_param = param++; L.b_param = param++;
+    L.w_off = off; off = align_up(off + c.packed_weight_bytes, 256);
+    L.b_off = off; off = align_up(off + sizeof(float) * d.cout, 256);
+    plan->layers.push_back(L);
+    return true;
+  };
+  ms_conv_desc d{};
+  d.kind = MS_CONV; d.cin = in_channels; d.cout = 512; d.ksize = 7; d.dilation = 1;
+  d.pad = 0; d.stride = 1; d.leaky = 1;
+  if (!add(d, 0, 1)) return false;
+  int mult = 1;
+  for (int s = 0; s < 4; ++s) {
+    ms_conv_desc u{};
+    u.kind = MS_CONVT; u.cin = kUp[s][0]; u.cout = kUp[s][1]; u.ksize = kUp[s][2];
+    u.stride = kUp[s][3]; u.pad = kUp[s][4]; u.dilation = 1; u.leaky = 1;
+    if (!add(u, 1, mult)) return false;
+    mult *= kUp[s][3];
+    for (int a = 0; a < 3; ++a) {
+      ms_conv_desc c1{};
+      c1.kind = MS_CONV; c1.cin = c1.cout = kUp[s][1]; c1.ksize = 3; c1.dilation = kDil[a];
+      c1.pad = kDil[a]; c1.stride = 1; c1.leaky = 1;
+      if (!add(c1, 2, mult)) return false;
+      ms_conv_desc c2 = c1;
+      c2.dilation = 1; c2.pad = 1;
+      if (!add(c2, 3, mult)) return false;
+    }
+  }
+  plan->final_w_off = off; off = align_up(off + sizeof(float) * 32 * 7, 256);
+  plan->final_b_off = off; off = align_up(off + sizeof(float), 256);
+  plan->total_bytes = off;
+  return param == MS_MELGAN_NUM_PARAMS - 2;
+}
+
+size_t per_clip_workspace(int frames, int in_channels) {
+  const size_t T = frames;
+  const size_t E = 8192 * T;  // largest stage: C*L = 128*64T = 64*128T = 32*256T
+  size_t b = 0;
+  b += align_up(static_cast<size_t>(in_channels) * (T + 6) * 2, 256);
+  b += align_up(512 * T * 2, 256);
+  b += 3 * align_up(E * 2, 256);
+  b += 2 * align_up(E * 4, 256);
+  return b;
+}
+
+}  // namespace
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+size_t ms_melgan_packed_weight_bytes(int in_channels, int operand) {
+  GenPlan plan;
+  if (!build_plan(in_channels, operand, &plan)) return 0;
+  return plan.total_bytes;
+}
+
+ms_status ms_melgan_pack_weights(const float* const* params, int in_channels, int operand,
+                                 void* packed, void* stream) {
+  GenPlan plan;
+  if (params == nullptr || packed == nullptr || !build_plan(in_channels, operand, &plan))
+    return MS_ERR_INVALID;
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (const GenLayer& L : plan.layers) {
+    ms_status s = ms_conv_pack_weight(&L.d, params[L.w_param], base + L.w_off, stream);
+    if (s != MS_OK) return s;
+    s = check_cuda(cudaMemcpyAsync(base + L.b_off, params[L.b_param],
+                                   sizeof(float) * L.d.cout, cudaMemcpyDeviceToDevice, st),
+                   "cudaMemcpyAsync(bias)");
+    if (s != MS_OK) return s;
+  }
+  ms_status s = check_cuda(
+      cudaMemcpyAsync(base + plan.final_w_off, params[MS_MELGAN_NUM_PARAMS - 2],
+                      sizeof(float) * 32 * 7, cudaMemcpyDeviceToDevice, st),
+      "cudaMemcpyAsync(final w)");
+  if (s != MS_OK) return s;
+  return check_cuda(cudaMemcpyAsync(base + plan.final_b_off, params[MS_MELGAN_NUM_PARAMS - 1],
+                                    sizeof(float), cudaMemcpyDeviceToDevice, st),
+                    "cudaMemcpyAsync(final b)");
+}
+
+size_t ms_melgan_workspace_bytes(int batch, int frames, int in_channels) {
+  if (batch <= 0 || frames <= 0 || in_channels <= 0) return 0;
+  return static_cast<size_t>(batch) * per_clip_workspace(frames, in_channels);
+}
+
+ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, int operand,
+                                  const float* x, float* y, int batch, int frames,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  GenPlan plan;
+  if (packed_weights == nullptr || x == nullptr || y == nullptr || workspace == nullptr ||
+      batch <= 0 || frames < 4 || !build_plan(in_channels, operand, &plan))
+    return MS_ERR_INVALID;
+  const size_t per_clip = per_clip_workspace(frames, in_channels);
+  int bc = static_cast<int>(workspace_bytes / per_clip);
+  if (bc < 1) return MS_ERR_WORKSPACE;
+  if (bc > batch) bc = batch;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint8_t* wb = static_cast<const uint8_t*>(packed_weights);
+  const size_t T = frames;
+  const size_t E = 8192 * T;
+
+  // carve the workspace for `bc` clips
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  size_t o = 0;
+  auto carve = [&](size_t bytes_per_clip) {
+    uint8_t* p = ws + o;
+    o += static_cast<size_t>(bc) * align_up(bytes_per_clip, 256);
+    return p;
+  };
+  void* xin16 = carve(static_cast<size_t>(in_channels) * (T + 6) * 2);
+  void* h16 = carve(512 * T * 2);
+  void* x16[2] = {carve(E * 2), carve(E * 2)};
+  void* y16 = carve(E * 2);
+  float* x32[2] = {reinterpret_cast<float*>(carve(E * 4)), reinterpret_cast<float*>(carve(E * 4))};
+
+  for (int b0 = 0; b0 < batch; b0 += bc) {
+    const int nb = (batch - b0) < bc ? (batch - b0) : bc;
+    ms_status s = pack_ncl_to_blk16(x + static_cast<size_t>(b0) * in_channels * T, xin16, nb,
+                                    in_channels, frames, 3, 1, operand, st);
+    if (s != MS_OK) return s;
+    const void* cur16 = nullptr;  // 16-bit operand of the next layer
+    int cur = 0;                  // which x16/x32 buffer holds the residual stream
+    for (const GenLayer& L : plan.layers) {
+      ms_conv_desc d = L.d;
+      d.batch = nb;
+      d.lin = L.len_mult * frames + (L.role == 0 ? 6 : 0);
+      ConvCfg c;
+      if (!make_conv_cfg(d, &c)) return MS_ERR_INVALID;
+      const void* w = wb + L.w_off;
+      const float* bias = reinterpret_cast<const float*>(wb + L.b_off);
+      switch (L.role) {
+        case 0:
+          s = launch_conv(d, c, xin16, w, bias, nullptr, h16, nullptr, st);
+          cur16 = h16;
+          break;
+        case 1:  // upsampler: starts a new residual stream
+          cur = 0;
+          s = launch_conv(d, c, cur16, w, bias, nullptr, x16[0], x32[0], st);
+          cur16 = x16[0];
+          break;
+        case 2:  // y = leaky(conv_dil(x))
+          s = launch_conv(d, c, cur16, w, bias, nullptr, y16, nullptr, st);
+          break;
+        default:  // x' = x + leaky(conv(y))
+          s = launch_conv(d, c, y16, w, bias, x32[cur], x16[cur ^ 1], x32[cur ^ 1], st);
+          cur ^= 1;
+          cur16 = x16[cur];
+          break;
+      }
+      if (s != MS_OK) return s;
+    }
+    s = conv_to_mono(x32[cur], reinterpret_cast<const float*>(wb + plan.final_w_off),
+                     reinterpret_cast<const float*>(wb + plan.final_b_off),
+                     y + static_cast<size_t>(b0) * 256 * T, nb, 32, 256 * frames, 7, 3, 1, st);
+    if (s != MS_OK) return s;
+  }
+  return MS_OK;
+}
+
+}  // extern "C"

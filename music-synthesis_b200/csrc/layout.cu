@@ -1,0 +1,187 @@
+// Boundary kernels: NCL f32 <-> channel-blocked layouts, and the single-output-channel
+// convolution (+tanh) that ends the generator.  All HBM-bound, vectorised 16/32-byte
+// accesses, coalesced along time.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+__device__ __forceinline__ uint32_t pack2op(float a, float b, int operand) {
+  if (operand == MS_BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_h2(a, b);
+}
+
+// (B,C,L) f32 -> (B,C/8,L+2*pad,8) 16-bit; one thread per output 16-byte vector.
+__global__ void pack_ncl_to_blk16_kernel(const float* __restrict__ x, uint4* __restrict__ y,
+                                         int C, int L, int pad, int pad_mode, int operand,
+                                         size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int Lp = L + 2 * pad;
+  const int tp = static_cast<int>(i % Lp);
+  const size_t bc = i / Lp;  // b*(C/8) + chunk
+  int t = tp - pad;
+  bool zero = false;
+  if (t < 0) {
+    if (pad_mode == 1) t = -t; else zero = true;
+  } else if (t >= L) {
+    if (pad_mode == 1) t = 2 * (L - 1) - t; else zero = true;
+  }
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    f[j] = zero ? 0.f : __ldg(x + (bc * 8 + j) * L + t);
+  uint4 o;
+  o.x = pack2op(f[0], f[1], operand);
+  o.y = pack2op(f[2], f[3], operand);
+  o.z = pack2op(f[4], f[5], operand);
+  o.w = pack2op(f[6], f[7], operand);
+  y[i] = o;
+}
+
+__global__ void unpack_blk32_to_ncl_kernel(const float4* __restrict__ x, float* __restrict__ y,
+                                           int L, size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int t = static_cast<int>(i % L);
+  const size_t bc = i / L;
+  const float4 a = __ldg(x + 2 * i), b = __ldg(x + 2 * i + 1);
+  float* d = y + bc * 8 * L + t;
+  d[0 * (size_t)L] = a.x; d[1 * (size_t)L] = a.y; d[2 * (size_t)L] = a.z; d[3 * (size_t)L] = a.w;
+  d[4 * (size_t)L] = b.x; d[5 * (size_t)L] = b.y; d[6 * (size_t)L] = b.z; d[7 * (size_t)L] = b.w;
+}
+
+__global__ void unpack_blk16_to_ncl_kernel(const uint4* __restrict__ x, float* __restrict__ y,
+                                           int L, int operand, size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int t = static_cast<int>(i % L);
+  const size_t bc = i / L;
+  const uint4 v = __ldg(x + i);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float* d = y + bc * 8 * L + t;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f;
+    if (operand == MS_BF16)
+      f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    else
+      f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    d[(2 * j) * (size_t)L] = f.x;
+    d[(2 * j + 1) * (size_t)L] = f.y;
+  }
+}
+
+// y[b,0,t] = act(bias + sum_c sum_k w[c,k] * x[b,c,t+k-pad]); x is BLK f32.
+// One thread per output sample; weights staged in shared memory (broadcast reads).
+__global__ void conv_to_mono_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ y,
+                                    int cin, int L, int ksize, int pad, int tanh_out) {
+  extern __shared__ float sw[];  // [cin/8][ksize][8]
+  const int chunks = cin >> 3;
+  for (int i = threadIdx.x; i < cin * ksize; i += blockDim.x) {
+    const int e = i % 8;
+    const int k = (i / 8) % ksize;
+    const int c = i / (8 * ksize);
+    sw[i] = w[(c * 8 + e) * ksize + k];
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= L) return;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float4* xr = reinterpret_cast<const float4*>(
+        x + (static_cast<size_t>(b) * chunks + c) * static_cast<size_t>(L) * 8);
+    const float* wc = sw + c * ksize * 8;
+    for (int k = 0; k < ksize; ++k) {
+      const int ti = t + k - pad;
+      if (ti < 0 || ti >= L) continue;
+      const float4 a = __ldg(xr + 2 * static_cast<size_t>(ti));
+      const float4 bq = __ldg(xr + 2 * static_cast<size_t>(ti) + 1);
+      const float* wk = wc + k * 8;
+      acc0 = fmaf(a.x, wk[0], acc0); acc1 = fmaf(a.y, wk[1], acc1);
+      acc0 = fmaf(a.z, wk[2], acc0); acc1 = fmaf(a.w, wk[3], acc1);
+      acc0 = fmaf(bq.x, wk[4], acc0); acc1 = fmaf(bq.y, wk[5], acc1);
+      acc0 = fmaf(bq.z, wk[6], acc0); acc1 = fmaf(bq.w, wk[7], acc1);
+    }
+  }
+  float v = acc0 + acc1 + (bias != nullptr ? bias[0] : 0.f);
+  if (tanh_out) v = tanhf(v);
+  y[static_cast<size_t>(b) * L + t] = v;
+}
+
+ms_status conv_to_mono(const float* x32, const float* w, const float* bias, float* y, int batch,
+                       int cin, int len, int ksize, int pad, int tanh_out,
+                       cudaStream_t stream) {
+  if (batch <= 0 || cin <= 0 || cin % 8 != 0 || len <= 0 || ksize <= 0) return MS_ERR_INVALID;
+  const size_t smem = static_cast<size_t>(cin) * ksize * sizeof(float);
+  if (smem > 48 * 1024) return MS_ERR_INVALID;
+  dim3 grid(ceil_div(len, 256), batch);
+  conv_to_mono_kernel<<<grid, 256, smem, stream>>>(x32, w, bias, y, cin, len, ksize, pad,
+                                                   tanh_out);
+  return after_launch("conv_to_mono_kernel");
+}
+
+ms_status pack_ncl_to_blk16(const float* x, void* y16, int batch, int channels, int len,
+                            int pad, int pad_mode, int operand, cudaStream_t stream) {
+  if (batch <= 0 || channels <= 0 || channels % 8 != 0 || len <= 0 || pad < 0)
+    return MS_ERR_INVALID;
+  if (pad_mode == 1 && pad >= len) return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * (len + 2 * pad);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  pack_ncl_to_blk16_kernel<<<blocks, 256, 0, stream>>>(x, static_cast<uint4*>(y16), channels,
+                                                       len, pad, pad_mode, operand, total);
+  return after_launch("pack_ncl_to_blk16_kernel");
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+ms_status ms_pack_ncl_to_blk16(const float* x, void* y16, int batch, int channels, int len,
+                               int pad, int pad_mode, int operand, void* stream) {
+  if (x == nullptr || y16 == nullptr) return MS_ERR_INVALID;
+  return pack_ncl_to_blk16(x, y16, batch, channels, len, pad, pad_mode, operand,
+                           static_cast<cudaStream_t>(stream));
+}
+
+ms_status ms_unpack_blk32_to_ncl(const float* x32, float* y, int batch, int channels, int len,
+                                 void* stream) {
+  if (x32 == nullptr || y == nullptr || batch <= 0 || channels % 8 != 0 || len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * len;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  unpack_blk32_to_ncl_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x32), y, len, total);
+  return after_launch("unpack_blk32_to_ncl_kernel");
+}
+
+ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int channels, int len,
+                                 int operand, void* stream) {
+  if (x16 == nullptr || y == nullptr || batch <= 0 || channels % 8 != 0 || len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * len;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  unpack_blk16_to_ncl_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x16), y, len, operand, total);
+  return after_launch("unpack_blk16_to_ncl_kernel");
+}
+
+ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, float* y,
+                          int batch, int cin, int len, int ksize, int pad, int tanh_out,
+                          void* stream) {
+  if (x32 == nullptr || w == nullptr || y == nullptr) return MS_ERR_INVALID;
+  return conv_to_mono(x32, w, bias, y, batch, cin, len, ksize, pad, tanh_out,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

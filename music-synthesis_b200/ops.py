@@ -1,0 +1,143 @@
+"""Tensor-level wrappers over the C ABI (device pointers in, device pointers out).
+
+torch is used for device memory and streams only; all arithmetic happens in
+csrc/libmsb200.so.  16-bit channel-blocked tensors are carried as torch.int16 with
+shape (B, C/8, L, 8); the fp32 residual stream as float32 of the same shape.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, MS_CONV, MS_CONVT, MS_F16, MS_BF16, check, ptr, stream_ptr
+
+OPERANDS = {"f16": MS_F16, "fp16": MS_F16, "bf16": MS_BF16}
+
+
+def conv_desc(kind, batch, cin, cout, lin, ksize, dilation=1, pad=0, stride=1, leaky=False,
+              operand=MS_F16, alpha=1.0):
+    return ConvDesc(kind, batch, cin, cout, lin, ksize, dilation, pad, stride, int(leaky),
+                    operand, alpha)
+
+
+def conv_out_len(desc):
+    n = _lib.lib().ms_conv_out_len(ctypes.byref(desc))
+    if n < 0:
+        raise _lib.MsbError("unsupported convolution descriptor")
+    return n
+
+
+def pack_ncl(x, pad=0, pad_mode=0, operand=MS_F16):
+    """(B,C,L) f32 -> (B,C/8,L+2*pad,8) 16-bit, zero (0) or reflection (1) padded."""
+    _lib.require_cuda(x, "x")
+    x = x.contiguous()
+    B, C, L = x.shape
+    y = torch.empty((B, C // 8, L + 2 * pad, 8), dtype=torch.int16, device=x.device)
+    check(_lib.lib().ms_pack_ncl_to_blk16(ptr(x), ptr(y), B, C, L, pad, pad_mode, operand,
+                                          stream_ptr()), "ms_pack_ncl_to_blk16")
+    return y
+
+
+def unpack_blk32(x32):
+    B, C8, L, _ = x32.shape
+    y = torch.empty((B, C8 * 8, L), dtype=torch.float32, device=x32.device)
+    check(_lib.lib().ms_unpack_blk32_to_ncl(ptr(x32), ptr(y), B, C8 * 8, L, stream_ptr()),
+          "ms_unpack_blk32_to_ncl")
+    return y
+
+
+def unpack_blk16(x16, operand=MS_F16):
+    B, C8, L, _ = x16.shape
+    y = torch.empty((B, C8 * 8, L), dtype=torch.float32, device=x16.device)
+    check(_lib.lib().ms_unpack_blk16_to_ncl(ptr(x16), ptr(y), B, C8 * 8, L, operand,
+                                            stream_ptr()), "ms_unpack_blk16_to_ncl")
+    return y
+
+
+def pack_conv_weight(desc, w):
+    """fp32 reference-layout weight -> packed 16-bit tile image (uint8 tensor)."""
+    _lib.require_cuda(w, "weight")
+    n = _lib.lib().ms_conv_packed_weight_bytes(ctypes.byref(desc))
+    if n == 0:
+        raise _lib.MsbError("unsupported convolution descriptor")
+    out = torch.empty(n, dtype=torch.uint8, device=w.device)
+    check(_lib.lib().ms_conv_pack_weight(ctypes.byref(desc), ptr(w.contiguous()), ptr(out),
+                                         stream_ptr()), "ms_conv_pack_weight")
+    return out
+
+
+def conv_fwd(desc, x16, w_packed, bias=None, res32=None, want16=True, want32=False):
+    """One tcgen05 implicit-GEMM conv / transposed conv.  Returns (y16, y32)."""
+    lout = conv_out_len(desc)
+    shape = (desc.batch, desc.cout // 8, lout, 8)
+    y16 = torch.empty(shape, dtype=torch.int16, device=x16.device) if want16 else None
+    y32 = torch.empty(shape, dtype=torch.float32, device=x16.device) if want32 else None
+    check(_lib.lib().ms_conv_fwd(ctypes.byref(desc), ptr(x16), ptr(w_packed), ptr(bias),
+                                 ptr(res32), ptr(y16), ptr(y32), stream_ptr()), "ms_conv_fwd")
+    return y16, y32
+
+
+def conv_to_mono(x32, w, bias, ksize, pad, tanh_out):
+    B, C8, L, _ = x32.shape
+    y = torch.empty((B, 1, L), dtype=torch.float32, device=x32.device)
+    check(_lib.lib().ms_conv_to_mono(ptr(x32), ptr(w.contiguous()), ptr(bias), ptr(y), B,
+                                     C8 * 8, L, ksize, pad, int(tanh_out), stream_ptr()),
+          "ms_conv_to_mono")
+    return y
+
+
+def audio2mel(audio, window, mel_basis, n_fft, hop):
+    _lib.require_cuda(audio, "audio")
+    audio = audio.contiguous()
+    B, _, N = audio.shape
+    n_mels = mel_basis.shape[0]
+    F = _lib.lib().ms_audio2mel_frames(N, n_fft, hop)
+    if F < 0:
+        raise _lib.MsbError("invalid Audio2Mel geometry")
+    out = torch.empty((B, n_mels, F), dtype=torch.float32, device=audio.device)
+    check(_lib.lib().ms_audio2mel_fwd(ptr(audio), ptr(window.contiguous()),
+                                      ptr(mel_basis.contiguous()), ptr(out), B, N, n_fft, hop,
+                                      n_mels, stream_ptr()), "ms_audio2mel_fwd")
+    return out
+
+
+class MelGanWeights:
+    """Packed parameter blob of a MelGanGenerator (60 state-dict tensors, in order)."""
+
+    def __init__(self, params, in_channels, operand=MS_F16):
+        L = _lib.lib()
+        if len(params) != _lib.MELGAN_NUM_PARAMS:
+            raise _lib.MsbError("MelGanGenerator has 60 parameter tensors, got %d" % len(params))
+        n = L.ms_melgan_packed_weight_bytes(in_channels, operand)
+        if n == 0:
+            raise _lib.MsbError("unsupported MelGanGenerator configuration")
+        for p in params:
+            _lib.require_cuda(p, "parameter")
+        keep = [p.detach().contiguous() for p in params]
+        arr = (ctypes.c_void_p * len(keep))(*[p.data_ptr() for p in keep])
+        self.blob = torch.empty(n, dtype=torch.uint8, device=keep[0].device)
+        self.in_channels = in_channels
+        self.operand = operand
+        check(L.ms_melgan_pack_weights(arr, in_channels, operand, ptr(self.blob), stream_ptr()),
+              "ms_melgan_pack_weights")
+
+
+def melgan_workspace_bytes(batch, frames, in_channels):
+    return int(_lib.lib().ms_melgan_workspace_bytes(batch, frames, in_channels))
+
+
+def melgan_generator_fwd(weights, x, workspace, out=None):
+    """x (B,C,T) f32 cuda -> (B,1,256T) f32.  `workspace`: uint8 cuda tensor; the batch
+    is processed in passes of as many clips as the workspace holds."""
+    _lib.require_cuda(x, "x")
+    x = x.contiguous()
+    B, C, T = x.shape
+    if C != weights.in_channels:
+        raise _lib.MsbError("expected %d input channels, got %d" % (weights.in_channels, C))
+    if out is None:
+        out = torch.empty((B, 1, 256 * T), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ms_melgan_generator_fwd(ptr(weights.blob), C, weights.operand, ptr(x),
+                                             ptr(out), B, T, ptr(workspace),
+                                             workspace.numel(), stream_ptr()),
+          "ms_melgan_generator_fwd")
+    return out

@@ -1,0 +1,137 @@
+"""Drop-in mirrors of the shared blocks in featuresynth/util/modules.py.
+
+Same class names, constructor signatures, forward contracts and state-dict keys as
+the reference; parameters live in ordinary nn.Conv1d / nn.ConvTranspose1d containers
+(so `module.apply(weights_init)`, `.parameters()`, `.state_dict()` and checkpoints
+behave identically) but `forward` dispatches to the tcgen05 kernels through the C ABI.
+Inference only in this round (no autograd through the CUDA path yet).
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
+
+
+def zero_grad(*optims):
+    """featuresynth/util/modules.py:38-40."""
+    for o in optims:
+        o.zero_grad()
+
+
+class _PackedConv:
+    """Caches the packed 16-bit weight image of one conv layer; repacks when the
+    parameter is modified in place (optimizer step, load_state_dict, init) or moved."""
+
+    def __init__(self):
+        self.key = None
+        self.packed = None
+
+    def get(self, desc, weight):
+        key = (weight.data_ptr(), weight._version, desc.kind, desc.operand)
+        if key != self.key:
+            self.packed = ops.pack_conv_weight(desc, weight.detach())
+            self.key = key
+        return self.packed
+
+
+def _no_grad_check(*tensors):
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        raise MsbError(
+            "the sm_100a path is forward-only in this build: call under torch.no_grad()")
+
+
+class ResidualAtom(nn.Module):
+    """featuresynth/util/modules.py:350-388:
+    x + leaky(conv_k3_pad1(leaky(conv_k3_dil_d(x))))."""
+
+    def __init__(self, channels, dilation, add_weight_norm=False, operand=MS_F16):
+        super().__init__()
+        if add_weight_norm:
+            raise NotImplementedError("weight-normed ResidualAtom is not on this path yet")
+        self.add_weight_norm = add_weight_norm
+        self.dilation = dilation
+        self.channels = channels
+        self.operand = operand
+        first = nn.Conv1d(channels, channels, 3, 1, dilation=dilation, padding=dilation)
+        second = nn.Conv1d(channels, channels, 3, 1, 1)
+        self.main = nn.Sequential(first, second)
+        self._packed = (_PackedConv(), _PackedConv())
+
+    def forward_blocked(self, x16, x32):
+        """(x16, x32) channel-blocked in -> channel-blocked out (no layout conversion)."""
+        B, _, L, _ = x16.shape
+        C = self.channels
+        d1 = ops.conv_desc(MS_CONV, B, C, C, L, 3, self.dilation, self.dilation, leaky=True,
+                           operand=self.operand)
+        d2 = ops.conv_desc(MS_CONV, B, C, C, L, 3, 1, 1, leaky=True, operand=self.operand)
+        c1, c2 = self.main[0], self.main[1]
+        y16, _ = ops.conv_fwd(d1, x16, self._packed[0].get(d1, c1.weight), c1.bias)
+        return ops.conv_fwd(d2, y16, self._packed[1].get(d2, c2.weight), c2.bias, res32=x32,
+                            want16=True, want32=True)
+
+    def forward(self, x):
+        _no_grad_check(x, *self.parameters())
+        x16 = ops.pack_ncl(x, operand=self.operand)
+        x32 = _blk32_from_ncl(x)
+        _, y32 = self.forward_blocked(x16, x32)
+        return ops.unpack_blk32(y32)
+
+
+def _blk32_from_ncl(x):
+    # (B,C,L) -> (B,C/8,L,8) fp32: pure data movement (torch is plumbing here)
+    B, C, L = x.shape
+    return x.view(B, C // 8, 8, L).permute(0, 1, 3, 2).contiguous()
+
+
+class ResidualStack(nn.Module):
+    """featuresynth/util/modules.py:391-405."""
+
+    def __init__(self, channels, dilations, add_weight_norm=False, operand=MS_F16):
+        super().__init__()
+        self.dilations = dilations
+        self.channels = channels
+        self.operand = operand
+        self.main = nn.Sequential(
+            *[ResidualAtom(channels, d, add_weight_norm, operand) for d in dilations])
+
+    def forward(self, x):
+        _no_grad_check(x, *self.parameters())
+        x16 = ops.pack_ncl(x, operand=self.operand)
+        x32 = _blk32_from_ncl(x)
+        for atom in self.main:
+            x16, x32 = atom.forward_blocked(x16, x32)
+        return ops.unpack_blk32(x32)
+
+
+class LearnedUpSample(nn.Module):
+    """featuresynth/util/modules.py:168-188: ConvTranspose1d(k, stride=s,
+    padding=(k-s)//2, bias=False) followed by `activation`.  Only k == 2*s with
+    LeakyReLU(0.2) (the configuration every hot-path experiment uses) is fused."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, scale_factor, activation=None,
+                 operand=MS_F16):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self.scale_factor = scale_factor
+        self.activation = activation
+        self.operand = operand
+        if kernel_size != 2 * scale_factor:
+            raise NotImplementedError("LearnedUpSample: only kernel_size == 2*scale_factor")
+        self.conv = nn.ConvTranspose1d(in_channels, out_channels, kernel_size,
+                                       stride=scale_factor,
+                                       padding=(kernel_size - scale_factor) // 2, bias=False)
+        self._packed = _PackedConv()
+
+    def forward(self, x, leaky=True):
+        _no_grad_check(x, *self.parameters())
+        B, C, L = x.shape
+        d = ops.conv_desc(MS_CONVT, B, C, self.out_channels, L, self.kernel_size, 1,
+                          (self.kernel_size - self.scale_factor) // 2, self.scale_factor,
+                          leaky=leaky, operand=self.operand)
+        x16 = ops.pack_ncl(x, operand=self.operand)
+        _, y32 = ops.conv_fwd(d, x16, self._packed.get(d, self.conv.weight), None,
+                              want16=False, want32=True)
+        return ops.unpack_blk32(y32)

@@ -1,0 +1,94 @@
+"""-m "not gpu": the C-ABI library loads and exports every symbol include/msb200.h
+declares; host-side logic (descriptors, shapes, mel basis) without any compute call."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    from music_synthesis_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        ge.build()
+    return _lib.lib()
+
+
+def test_header_symbols_are_exported(lib):
+    from music_synthesis_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "msb200.h")).read()
+    declared = set(re.findall(r"\b(ms_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_status_strings_and_version(lib):
+    assert lib.ms_version() >= 100
+    assert lib.ms_strerror(0) == b"ok"
+    assert b"workspace" in lib.ms_strerror(-3)
+    assert lib.ms_launch_count() >= 0
+
+
+def test_conv_geometry_host_logic(lib):
+    from music_synthesis_b200 import ops
+    # ResidualAtom convs keep the length; first conv on reflect-padded input
+    assert ops.conv_out_len(ops.conv_desc(ops.MS_CONV, 1, 128, 128, 1000, 3, 9, 9)) == 1000
+    assert ops.conv_out_len(ops.conv_desc(ops.MS_CONV, 1, 128, 512, 70, 7, 1, 0)) == 64
+    # the reference's three upsampler geometries give exactly stride * L
+    for k, s, p in ((16, 8, 4), (4, 2, 1), (8, 4, 2)):
+        d = ops.conv_desc(ops.MS_CONVT, 1, 64, 32, 100, k, 1, p, s)
+        assert ops.conv_out_len(d) == s * 100
+    d = ops.conv_desc(ops.MS_CONV, 1, 256, 256, 64, 3, 1, 1)
+    assert lib.ms_conv_packed_weight_bytes(ctypes.byref(d)) == 256 * 256 * 3 * 2
+    assert lib.ms_audio2mel_frames(16384, 1024, 256) == 62
+    assert lib.ms_audio2mel_frames(8192, 1024, 256) == 30
+    assert lib.ms_audio2mel_frames(65536, 1024, 256) == 254
+    assert lib.ms_melgan_packed_weight_bytes(128, 0) > 4_691_969 * 2 - 512
+    assert lib.ms_melgan_workspace_bytes(2, 64, 128) == 2 * lib.ms_melgan_workspace_bytes(1, 64, 128)
+
+
+def test_module_mirrors_keep_reference_state_dict_layout():
+    from music_synthesis_b200.generator.full import MelGanGenerator
+    from music_synthesis_b200.feature.feature import Audio2Mel
+    from oracle import restate
+    g = MelGanGenerator(64, 128)
+    ref = restate.melgan_generator_state(0)
+    sd = g.state_dict()
+    assert list(sd) == list(ref)            # same keys, same ORDER (pack order)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    assert sum(v.numel() for v in sd.values()) == 4_691_969
+    a = Audio2Mel(1024, 256, 1024, 22050, 128)
+    assert set(a.state_dict()) == {"mel_basis", "window"}
+    assert tuple(a.mel_basis.shape) == (128, 513)
+
+
+def test_product_mel_basis_equals_reference_fixture(golden):
+    from music_synthesis_b200.feature.melbasis import mel_filterbank
+    g = golden("mel_basis_22050_1024_128")
+    assert np.array_equal(mel_filterbank(22050, 1024, 128, 0.0, None), g["mel_basis"])
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package may import it."""
+    pkg = os.path.join(ROOT, "music-synthesis_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from music_synthesis_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmsb200.so")
+    with pytest.raises(ImportError):
+        _lib.lib()

@@ -1,0 +1,132 @@
+"""-m gpu: MelGanGenerator / Audio2Mel parity through the module mirrors (which call
+the C ABI) against (a) the committed golden vectors produced by the unmodified
+reference and (b) the oracle restatement on larger seeded inputs.
+
+Tolerances (north star): waveform relative L2 <= 1e-3; log-mel max-abs <= 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+from tests.gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+WAVEFORM_TOL = 1e-3
+LOGMEL_TOL = 1e-3
+
+
+def _module(sd):
+    from music_synthesis_b200.generator.full import MelGanGenerator
+    g = MelGanGenerator(64, 128).eval()
+    g.load_state_dict(sd)
+    return g.cuda()
+
+
+@pytest.mark.parametrize("name", ["gen_b2_t8", "gen_b2_t8_bias", "gen_b3_t20_bias",
+                                  "gen_cfg1_b1_t64"])
+def test_generator_matches_golden(golden, name):
+    g = golden(name)
+    seed, B, T = int(g["seed"]), int(g["B"]), int(g["T"])
+    sd = restate.melgan_generator_state(seed)
+    if int(g["biased"]):
+        sd = restate.randomize_biases(sd, seed + 1000)
+    m = _module(sd)
+    with torch.no_grad():
+        y = m(synth.mel_features(seed, B, T).cuda())
+    torch.cuda.synchronize()
+    assert y.shape == (B, 1, 256 * T)
+    err = rel_l2(y, g["y"])
+    print(name, "rel_l2 =", err)
+    assert err < WAVEFORM_TOL
+
+
+def test_generator_matches_oracle_multi_pass():
+    """More clips than one workspace pass holds, odd T: exercises the pass loop and
+    the ragged last time tile of every layer."""
+    sd = restate.randomize_biases(restate.melgan_generator_state(77), 1077)
+    m = _module(sd)
+    m.clips_per_pass = 2
+    x = synth.mel_features(78, 5, 37)
+    with torch.no_grad():
+        y = m(x.cuda())
+        ref = restate.melgan_generator(x, sd)
+    err = rel_l2(y, ref)
+    print("multi-pass rel_l2 =", err)
+    assert err < WAVEFORM_TOL
+    # per-clip results must not depend on how the batch was split into passes
+    m.clips_per_pass = 16
+    with torch.no_grad():
+        y2 = m(x.cuda())
+    assert torch.equal(y, y2)
+
+
+def test_generator_reacts_to_weight_updates():
+    sd = restate.melgan_generator_state(5)
+    m = _module(sd)
+    x = synth.mel_features(6, 1, 8).cuda()
+    with torch.no_grad():
+        y0 = m(x).clone()
+        m.main[1].weight.mul_(0.5)          # in-place update must invalidate the pack
+        y1 = m(x)
+    assert not torch.equal(y0, y1)
+    sd2 = dict(sd)
+    sd2["main.1.weight"] = sd["main.1.weight"] * 0.5
+    assert rel_l2(y1, restate.melgan_generator(x.cpu(), sd2)) < WAVEFORM_TOL
+
+
+def test_generator_refuses_cpu_and_autograd():
+    from music_synthesis_b200._lib import MsbError
+    m = _module(restate.melgan_generator_state(5))
+    with pytest.raises(MsbError):
+        m(torch.zeros(1, 128, 8))                      # CPU input: no CPU path
+    with pytest.raises(MsbError):
+        m(torch.zeros(1, 128, 8, device="cuda"))       # grad enabled: forward-only
+
+
+@pytest.mark.parametrize("C,L", [(32, 96), (128, 64)])
+def test_residual_stack_module_matches_golden(golden, C, L):
+    from music_synthesis_b200.util.modules import ResidualStack
+    g = golden(f"resstack_c{C}")
+    seed = int(g["seed"])
+    sd = synth.residual_stack_state(seed, C)
+    rs = ResidualStack(C, [1, 3, 9]).eval()
+    rs.load_state_dict({k[len("s."):]: v for k, v in sd.items()})
+    rs = rs.cuda()
+    with torch.no_grad():
+        y = rs(synth.randn(seed + 1, 2, C, L).cuda())
+    assert rel_l2(y, g["y"]) < WAVEFORM_TOL
+
+
+@pytest.mark.parametrize("name", ["a2m_b2_n16384", "a2m_b3_n4000"])
+def test_audio2mel_matches_golden(golden, name):
+    from music_synthesis_b200.feature.feature import Audio2Mel
+    g = golden(name)
+    a2m = Audio2Mel(1024, 256, 1024, 22050, 128).cuda()
+    b = golden("mel_basis_22050_1024_128")
+    assert np.array_equal(a2m.mel_basis.cpu().numpy(), b["mel_basis"])
+    a = synth.uniform_audio(int(g["seed"]), int(g["B"]), int(g["N"]))
+    y = a2m(a.cuda()).cpu().numpy()
+    assert y.shape == g["y"].shape
+    err = np.abs(y - g["y"]).max()
+    print(name, "max |d log10 mel| =", err)
+    assert err < LOGMEL_TOL
+
+
+def test_audio2mel_cfg2_and_edge_cases():
+    from music_synthesis_b200.feature.feature import Audio2Mel
+    a2m = Audio2Mel(1024, 256, 1024, 22050, 128).cuda()
+    a = synth.uniform_audio(3, 64, 16384)                       # BASELINE config 2
+    y = a2m(a.cuda()).cpu()
+    ref = restate.audio2mel(a, a2m.mel_basis.cpu(), a2m.window.cpu())
+    assert y.shape == (64, 128, 62)
+    assert (y - ref).abs().max() < LOGMEL_TOL
+    # silence hits the 1e-5 clamp exactly; numpy input path; shortest legal clip
+    z = a2m(torch.zeros(1, 1, 2048, device="cuda")).cpu()
+    assert torch.all(z == -5.0)
+    n = a2m(a[0, 0].numpy()).cpu()
+    assert (n - ref[:1]).abs().max() < LOGMEL_TOL
+    s = a2m(a[:2, :, :640].contiguous().cuda())
+    assert s.shape == (2, 128, 1)
+    assert (s.cpu() - restate.audio2mel(a[:2, :, :640], a2m.mel_basis.cpu(),
+                                        a2m.window.cpu())).abs().max() < LOGMEL_TOL

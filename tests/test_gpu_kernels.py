@@ -1,0 +1,152 @@
+"""-m gpu: single-kernel parity of the C-ABI entry points against plain PyTorch fp32
+on the host, on the SAME 16-bit-rounded operands (so the only difference left is fp32
+accumulation order: tolerance 2e-5 relative L2), plus loose checks against the
+unrounded fp32 op (tolerance 2e-3: operand rounding)."""
+import pytest
+import torch
+from torch.nn import functional as F
+
+from tests.gpu_util import rel_l2, rnd16, randn
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = 2e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from music_synthesis_b200 import ops as _ops
+    return _ops
+
+
+def _blk32(x):
+    B, C, L = x.shape
+    return x.view(B, C // 8, 8, L).permute(0, 1, 3, 2).contiguous()
+
+
+def test_pack_unpack_roundtrip(ops):
+    x = randn(1, 3, 32, 77)
+    xd = x.cuda()
+    for pad, mode in ((0, 0), (3, 1), (5, 0)):
+        y16 = ops.pack_ncl(xd, pad, mode)
+        back = ops.unpack_blk16(y16).cpu()
+        if mode == 1:
+            ref = F.pad(x, (pad, pad), mode="reflect")
+        else:
+            ref = F.pad(x, (pad, pad))
+        assert back.shape == ref.shape
+        assert torch.equal(back, rnd16(ref))
+    x32 = _blk32(x).cuda()
+    assert torch.equal(ops.unpack_blk32(x32).cpu(), x)
+
+
+CONV_CASES = [
+    # (B, C_in, C_out, L, k, dilation, pad, bias, residual)
+    (1, 32, 32, 128, 3, 1, 1, False, False),
+    (2, 32, 32, 300, 3, 3, 3, True, True),
+    (2, 64, 64, 515, 3, 9, 9, True, True),
+    (1, 128, 128, 1000, 3, 1, 1, True, False),
+    (2, 128, 128, 260, 3, 9, 9, True, True),
+    (1, 256, 256, 384, 3, 3, 3, True, True),
+    (2, 128, 512, 70, 7, 1, 0, True, False),     # first conv (input pre-padded)
+    (1, 1024, 1024, 64, 5, 1, 2, True, False),   # discriminator dense layer
+    (3, 16, 48, 130, 5, 2, 4, True, False),      # odd tile shapes
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv1d(ops, case):
+    B, Ci, Co, L, k, dil, pad, has_bias, has_res = case
+    x = randn(10, B, Ci, L)
+    w = randn(11, Co, Ci, k, scale=0.05)
+    bias = randn(12, Co, scale=0.1) if has_bias else None
+    desc = ops.conv_desc(ops.MS_CONV, B, Ci, Co, L, k, dil, pad, leaky=True)
+    lout = ops.conv_out_len(desc)
+    res = randn(13, B, Co, lout) if has_res else None
+
+    ref = F.leaky_relu(F.conv1d(rnd16(x).double(), rnd16(w).double(),
+                                None if bias is None else bias.double(),
+                                dilation=dil, padding=pad), 0.2)
+    if has_res:
+        ref = ref + res.double()
+    assert ref.shape[-1] == lout
+
+    x16 = ops.pack_ncl(x.cuda())
+    wp = ops.pack_conv_weight(desc, w.cuda())
+    y16, y32 = ops.conv_fwd(desc, x16, wp, None if bias is None else bias.cuda(),
+                            None if res is None else _blk32(res).cuda(),
+                            want16=True, want32=True)
+    torch.cuda.synchronize()
+    got32 = ops.unpack_blk32(y32).cpu()
+    got16 = ops.unpack_blk16(y16).cpu()
+    assert rel_l2(got32, ref) < TIGHT
+    assert torch.equal(got16, rnd16(got32))
+    # against the unrounded fp32 op
+    full = F.leaky_relu(F.conv1d(x, w, bias, dilation=dil, padding=pad), 0.2)
+    if has_res:
+        full = full + res
+    assert rel_l2(got32, full) < 2e-3
+
+
+CONVT_CASES = [
+    # (B, C_in, C_out, L, k, stride, pad, bias)
+    (1, 64, 32, 128, 4, 2, 1, True),
+    (2, 128, 64, 300, 4, 2, 1, True),
+    (2, 256, 128, 100, 16, 8, 4, True),
+    (1, 512, 256, 64, 16, 8, 4, True),
+    (2, 128, 128, 37, 8, 4, 2, False),    # LearnedUpSample k8 s4
+]
+
+
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transpose1d(ops, case):
+    B, Ci, Co, L, k, s, pad, has_bias = case
+    x = randn(20, B, Ci, L)
+    w = randn(21, Ci, Co, k, scale=0.05)
+    bias = randn(22, Co, scale=0.1) if has_bias else None
+    desc = ops.conv_desc(ops.MS_CONVT, B, Ci, Co, L, k, 1, pad, s, leaky=True)
+    ref = F.leaky_relu(F.conv_transpose1d(rnd16(x).double(), rnd16(w).double(),
+                                          None if bias is None else bias.double(),
+                                          stride=s, padding=pad), 0.2)
+    assert ops.conv_out_len(desc) == ref.shape[-1] == s * L
+    x16 = ops.pack_ncl(x.cuda())
+    wp = ops.pack_conv_weight(desc, w.cuda())
+    _, y32 = ops.conv_fwd(desc, x16, wp, None if bias is None else bias.cuda(),
+                          want16=False, want32=True)
+    torch.cuda.synchronize()
+    assert rel_l2(ops.unpack_blk32(y32).cpu(), ref) < TIGHT
+
+
+def test_conv_bf16_operands(ops):
+    B, C, L = 2, 64, 200
+    x, w = randn(30, B, C, L), randn(31, C, C, 3, scale=0.05)
+    desc = ops.conv_desc(ops.MS_CONV, B, C, C, L, 3, 3, 3, leaky=False, operand=ops.MS_BF16)
+    ref = F.conv1d(rnd16(x, "bf16").double(), rnd16(w, "bf16").double(), dilation=3, padding=3)
+    x16 = ops.pack_ncl(x.cuda(), operand=ops.MS_BF16)
+    wp = ops.pack_conv_weight(desc, w.cuda())
+    _, y32 = ops.conv_fwd(desc, x16, wp, want16=False, want32=True)
+    assert rel_l2(ops.unpack_blk32(y32).cpu(), ref) < TIGHT
+
+
+@pytest.mark.parametrize("cin,k,pad,tanh", [(32, 7, 3, True), (1024, 3, 1, False)])
+def test_conv_to_mono(ops, cin, k, pad, tanh):
+    B, L = 2, 333
+    x = randn(40, B, cin, L, scale=0.5)
+    w = randn(41, 1, cin, k, scale=0.05)
+    b = randn(42, 1, scale=0.1)
+    ref = F.conv1d(x.double(), w.double(), b.double(), padding=pad)
+    if tanh:
+        ref = torch.tanh(ref)
+    got = ops.conv_to_mono(_blk32(x).cuda(), w.cuda(), b.cuda(), k, pad, tanh).cpu()
+    assert got.shape == (B, 1, L)
+    assert rel_l2(got, ref) < 5e-6
+
+
+def test_bad_descriptors_are_rejected(ops):
+    from music_synthesis_b200._lib import MsbError
+    with pytest.raises(MsbError):
+        ops.conv_out_len(ops.conv_desc(ops.MS_CONV, 1, 30, 32, 100, 3, 1, 1))  # cin % 16
+    with pytest.raises(MsbError):
+        ops.conv_out_len(ops.conv_desc(ops.MS_CONVT, 1, 32, 32, 100, 5, 1, 1, 2))  # k != 2s
+    with pytest.raises(MsbError):
+        ops.pack_ncl(torch.zeros(1, 8, 16))  # CPU tensor: no CPU path
