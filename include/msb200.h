@@ -125,6 +125,23 @@ ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, f
                           void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Fused ResidualStack: 3 ResidualAtoms = 6 k3 convolutions (dilations d0,1,d1,1,d2,1)
+ * in one kernel; activations stay in shared memory, the fp32 residual stream in
+ * tensor memory.  channels in {32, 64, 128}; d0+d1+d2+3 <= 16.
+ *   replaces ResidualStack.forward, featuresynth/util/modules.py:391-405
+ *   (atoms: 350-388) as used at generator/full.py:29,33,37,41.
+ *   params: 12 device pointers in state-dict order (w,b of main.{a}.main.{0,1}).
+ *   x32: BLK f32 (B,C/8,L,8) in; y16 (BLK 16-bit) and/or y32 (BLK f32) out.
+ * ------------------------------------------------------------------------- */
+int ms_resstack_supported(int channels);
+size_t ms_resstack_packed_weight_bytes(int channels);
+ms_status ms_resstack_pack_weights(const float* const* params /* 12 device ptrs */,
+                                   int channels, int operand, void* packed, void* stream);
+ms_status ms_resstack_fwd(int channels, int batch, int len, const int* dilations /* [3] */,
+                          int operand, const float* x32, const void* packed, void* y16,
+                          float* y32, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Whole MelGanGenerator forward (inference), features -> waveform.
  *   replaces MelGanGenerator.forward, featuresynth/generator/full.py:47-50
  *   (layer list 22-45; ResidualStack util/modules.py:391-405).

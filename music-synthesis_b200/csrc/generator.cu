@@ -19,6 +19,9 @@ ms_status conv_to_mono(const float* x32, const float* w, const float* bias, floa
                        int cin, int len, int ksize, int pad, int tanh_out, cudaStream_t stream);
 ms_status pack_ncl_to_blk16(const float* x, void* y16, int batch, int channels, int len,
                             int pad, int pad_mode, int operand, cudaStream_t stream);
+ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int operand,
+                       const float* x32, const void* packed, void* y16, float* y32,
+                       cudaStream_t stream);
 
 namespace {
 
@@ -26,7 +29,9 @@ struct GenLayer {
   ms_conv_desc d;   // batch / lin filled per call
   int w_param, b_param;
   size_t w_off, b_off;
-  int role;         // 0 first conv, 1 upsampler, 2 atom conv1, 3 atom conv2
+  int role;         // 0 first conv, 1 upsampler, 2 atom conv1, 3 atom conv2,
+                    // 4 fused ResidualStack (w_param = first of its 12 params), 5 = upsampler
+                    // feeding a fused stack (fp32 output only)
   int len_mult;     // lin = len_mult * T (+6 for the first conv)
 };
 
@@ -71,6 +76,17 @@ bool build_plan(int in_channels, int operand, GenPlan* plan) {
     u.stride = kUp[s][3]; u.pad = kUp[s][4]; u.dilation = 1; u.leaky = 1;
     if (!add(u, 1, mult)) return false;
     mult *= kUp[s][3];
+    if (ms_resstack_supported(kUp[s][1])) {
+      plan->layers.back().role = 5;
+      GenLayer L{};
+      L.d = u; L.d.cin = L.d.cout = kUp[s][1]; L.d.operand = operand;
+      L.role = 4; L.len_mult = mult;
+      L.w_param = param; param += 12; L.b_param = -1;
+      L.w_off = off; off = align_up(off + ms_resstack_packed_weight_bytes(kUp[s][1]), 256);
+      L.b_off = 0;
+      plan->layers.push_back(L);
+      continue;
+    }
     for (int a = 0; a < 3; ++a) {
       ms_conv_desc c1{};
       c1.kind = MS_CONV; c1.cin = c1.cout = kUp[s][1]; c1.ksize = 3; c1.dilation = kDil[a];
@@ -119,6 +135,12 @@ ms_status ms_melgan_pack_weights(const float* const* params, int in_channels, in
   uint8_t* base = static_cast<uint8_t*>(packed);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (const GenLayer& L : plan.layers) {
+    if (L.role == 4) {
+      ms_status s4 = ms_resstack_pack_weights(params + L.w_param, L.d.cout, operand,
+                                              base + L.w_off, stream);
+      if (s4 != MS_OK) return s4;
+      continue;
+    }
     ms_status s = ms_conv_pack_weight(&L.d, params[L.w_param], base + L.w_off, stream);
     if (s != MS_OK) return s;
     s = check_cuda(cudaMemcpyAsync(base + L.b_off, params[L.b_param],
@@ -179,6 +201,16 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
     const void* cur16 = nullptr;  // 16-bit operand of the next layer
     int cur = 0;                  // which x16/x32 buffer holds the residual stream
     for (const GenLayer& L : plan.layers) {
+      if (L.role == 4) {
+        // fused ResidualStack: fp32 stream in, 16-bit operand (+ fp32 for the last stage) out
+        const bool final_stage = (L.d.cout == 32);
+        s = resstack_fwd(L.d.cout, nb, L.len_mult * frames, kDil, operand, x32[0],
+                         wb + L.w_off, x16[1], final_stage ? x32[1] : nullptr, st);
+        if (s != MS_OK) return s;
+        cur = 1;
+        cur16 = x16[1];
+        continue;
+      }
       ms_conv_desc d = L.d;
       d.batch = nb;
       d.lin = L.len_mult * frames + (L.role == 0 ? 6 : 0);
@@ -195,6 +227,11 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
           cur = 0;
           s = launch_conv(d, c, cur16, w, bias, nullptr, x16[0], x32[0], st);
           cur16 = x16[0];
+          break;
+        case 5:  // upsampler in front of a fused stack: only the fp32 stream is needed
+          cur = 0;
+          s = launch_conv(d, c, cur16, w, bias, nullptr, nullptr, x32[0], st);
+          cur16 = nullptr;
           break;
         case 2:  // y = leaky(conv_dil(x))
           s = launch_conv(d, c, cur16, w, bias, nullptr, y16, nullptr, st);

@@ -1,0 +1,430 @@
+// Fused ResidualStack: three ResidualAtoms (six k=3 convolutions, dilations d0,d1,d2 /
+// 1,1,1) per time tile in ONE kernel, activations never leaving the SM.
+//   replaces ResidualStack.forward / ResidualAtom.forward,
+//   featuresynth/util/modules.py:350-405, as used at generator/full.py:29,33,37,41.
+//
+// Per CTA tile of R = MB*128 rows (MB = 256/C M-blocks; R*C = 32768 always):
+//   SMEM  X16 [C/8][R][8]   16-bit operand copy of the residual stream        (64 KB)
+//         Y16 [C/8][R][8]   16-bit inner activation of the current atom       (64 KB)
+//         W ring            one k-tap weight image (C x C, 16-bit) per slot   (<= 96 KB)
+//   TMEM  per M-block: C columns fp32 residual stream + C columns accumulator (512 cols)
+// The tile covers rows [t0-16, t0+R-16): 16 halo rows each side are recomputed (the
+// stack's receptive field is +-16), only the middle R-32 rows are stored.  Rows outside
+// the clip are forced to zero after every layer -- that IS each conv's zero padding.
+// A tap with dilation shift s is the same SMEM buffer addressed s rows further
+// (descriptor start address + 16*s bytes); reads that run off a tile edge only ever
+// contaminate halo rows.
+//
+// Warp roles: warp 0 streams weight taps (bulk async copies) through the ring, warp 1
+// issues tcgen05.mma, warps 2-9 are the prologue/epilogue: TMEM -> bias, LeakyReLU,
+// residual add (fp32, TMEM resident) -> 16-bit operand for the next conv in SMEM.
+// MMA and epilogue overlap at M-block granularity: conv l+1 starts on M-block 0 while
+// the epilogue of conv l is still draining M-block 1.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+constexpr int kStackHalo = 16;
+constexpr int kStackThreads = 320;       // 10 warps
+constexpr int kStackHeader = 1024;
+
+struct StackParams {
+  const float* x32;      // BLK f32 (B, C/8, L, 8): stack input (upsampler output)
+  const uint16_t* w;     // [6 convs][3 taps][C/8][C][8] 16-bit
+  const float* bias;     // [6][C]
+  uint16_t* y16;         // BLK 16-bit output or null
+  float* y32;            // BLK f32 output or null
+  int B, L;
+  int dil[3];
+  int tiles_per_clip, total_tiles;
+  int operand;
+};
+
+template <int C>
+struct StackGeom {
+  static constexpr int MB = 256 / C;             // M-blocks per tile
+  static constexpr int R = MB * 128;             // rows per tile
+  static constexpr int V = R - 2 * kStackHalo;   // rows stored per tile
+  static constexpr int NCH = C / 8;
+  static constexpr int ACT_BYTES = R * C * 2;    // 65536
+  static constexpr int TAP_BYTES = C * C * 2;
+  static constexpr int NSLOT = (96 * 1024 / TAP_BYTES) < 18 ? (96 * 1024 / TAP_BYTES) : 18;
+  static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES;
+};
+
+__device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
+  if (operand == MS_BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_h2(a, b);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kStackThreads, 1)
+resstack_kernel(const __grid_constant__ StackParams p) {
+  using G = StackGeom<C>;
+  constexpr int MB = G::MB, R = G::R, NSLOT = G::NSLOT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // [0,18) wfull  [18,36) wempty  [36,44) acc_full  [44,52) act_ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
+  const uint32_t bar_base = smem_u32(bars);
+  const uint32_t sX = smem_u32(smem + kStackHeader);
+  const uint32_t sY = sX + G::ACT_BYTES;
+  const uint32_t sW = sY + G::ACT_BYTES;
+  auto wfull = [&](int s) { return bar_base + 8u * s; };
+  auto wempty = [&](int s) { return bar_base + 8u * (18 + s); };
+  auto acc_full = [&](int m) { return bar_base + 8u * (36 + m); };
+  auto act_ready = [&](int m) { return bar_base + 8u * (44 + m); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 18; ++s) {
+      mbar_init(wfull(s), 1);
+      mbar_init(wempty(s), 1);
+    }
+    for (int m = 0; m < 8; ++m) {
+      mbar_init(acc_full(m), 1);
+      mbar_init(act_ready(m), 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= weight-tap producer =========================
+    if (lane == 0) {
+      uint32_t pos = 0;  // running tap counter (ring position)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tap = 0; tap < 18; ++tap, ++pos) {
+          const int slot = pos % NSLOT;
+          const uint32_t par = (pos / NSLOT) & 1u;
+          mbar_wait(wempty(slot), par ^ 1u);
+          mbar_arrive_expect_tx(wfull(slot), G::TAP_BYTES);
+          bulk_g2s(sW + slot * G::TAP_BYTES,
+                   reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(tap) * G::TAP_BYTES,
+                   G::TAP_BYTES, wfull(slot));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(C, p.operand);
+      uint32_t pos = 0;      // ring position of the current conv's first tap
+      uint32_t nconv = 0;    // convs issued so far (parity of act_ready waits)
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int l = 0; l < 6; ++l, pos += 3, ++nconv) {
+          const int d = (l & 1) ? 1 : p.dil[l >> 1];
+          const uint32_t src = (l & 1) ? sY : sX;
+          const uint32_t ready_par = nconv & 1u;
+          auto issue = [&](int mb, int t, bool first) {
+            const int slot = (pos + t) % NSLOT;
+            const int shift = (t - 1) * d;
+            const uint32_t a0 = src + static_cast<uint32_t>((mb * 128 + shift) * 16);
+            const uint32_t b0 = sW + slot * G::TAP_BYTES;
+            const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
+#pragma unroll
+            for (int k16 = 0; k16 < C / 16; ++k16) {
+              const uint64_t ad = umma_desc_nosw(a0 + static_cast<uint32_t>(2 * k16 * R * 16),
+                                                 R * 16, 128);
+              const uint64_t bd = umma_desc_nosw(b0 + static_cast<uint32_t>(2 * k16 * C * 16),
+                                                 C * 16, 128);
+              umma_f16_ss(dst, ad, bd, idesc, (first && k16 == 0) ? 0u : 1u);
+            }
+          };
+          auto wait_tap = [&](int t) {
+            const uint32_t q = pos + t;
+            mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u);
+          };
+          auto free_tap = [&](int t) { umma_commit(wempty((pos + t) % NSLOT)); };
+          for (int mb = 0; mb < MB; ++mb) {
+            mbar_wait(act_ready(mb), ready_par);
+            tc_fence_after();
+            if (mb == 0) wait_tap(0);
+            issue(mb, 0, true);
+            if (mb == MB - 1) free_tap(0);
+            if (mb == 0) wait_tap(1);
+            issue(mb, 1, false);
+            if (mb == MB - 1) free_tap(1);
+            if (mb >= 1) {
+              if (mb == 1) wait_tap(2);
+              issue(mb - 1, 2, false);
+              umma_commit(acc_full(mb - 1));
+            }
+          }
+          if (MB == 1) wait_tap(2);
+          issue(MB - 1, 2, false);
+          free_tap(2);
+          umma_commit(acc_full(MB - 1));
+        }
+      }
+    }
+  } else {
+    // ====================== prologue / epilogue warps ======================
+    const int e = warp - 2;            // 0..7
+    const int q = warp & 3;            // TMEM lane quarter accessible to this warp
+    const int hsel = e >> 2;           // which half of the channels
+    constexpr int HALF = C / 2;
+    uint32_t nconv = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_clip;
+      const int t0 = (tile % p.tiles_per_clip) * G::V - kStackHalo;  // clip row of tile row 0
+      // ---- prologue: x32 (global) -> TMEM residual stream + 16-bit operand in sX
+      for (int mb = 0; mb < MB; ++mb) {
+        const int row = mb * 128 + q * 32 + lane;
+        const int t = t0 + row;
+        const bool inside = (t >= 0) && (t < p.L);
+        const uint32_t tx = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                            static_cast<uint32_t>(mb * 2 * C + hsel * HALF);
+#pragma unroll
+        for (int g = 0; g < HALF / 16; ++g) {
+          uint32_t v[16];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int chunk = (hsel * HALF + g * 16) / 8 + h;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+            if (inside) {
+              const float4* src = reinterpret_cast<const float4*>(
+                  p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk) * p.L + t) * 8);
+              a = __ldg(src);
+              c = __ldg(src + 1);
+            }
+            v[h * 8 + 0] = __float_as_uint(a.x); v[h * 8 + 1] = __float_as_uint(a.y);
+            v[h * 8 + 2] = __float_as_uint(a.z); v[h * 8 + 3] = __float_as_uint(a.w);
+            v[h * 8 + 4] = __float_as_uint(c.x); v[h * 8 + 5] = __float_as_uint(c.y);
+            v[h * 8 + 6] = __float_as_uint(c.z); v[h * 8 + 7] = __float_as_uint(c.w);
+            const uint32_t dst = sX + static_cast<uint32_t>((chunk * R + row) * 16);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                         "r"(pack2s(a.x, a.y, p.operand)), "r"(pack2s(a.z, a.w, p.operand)),
+                         "r"(pack2s(c.x, c.y, p.operand)), "r"(pack2s(c.z, c.w, p.operand))
+                         : "memory");
+          }
+          tmem_st16(tx + g * 16, v);
+        }
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(act_ready(mb));
+      }
+      // ---- six convolutions
+      for (int l = 0; l < 6; ++l, ++nconv) {
+        const bool second = (l & 1) != 0;     // second conv of an atom: residual add
+        const bool last = (l == 5);
+        const uint32_t dstbuf = second ? sX : sY;
+        const float* bias = p.bias + l * C + hsel * HALF;
+        for (int mb = 0; mb < MB; ++mb) {
+          const int row = mb * 128 + q * 32 + lane;
+          const int t = t0 + row;
+          const bool inside = (t >= 0) && (t < p.L);
+          const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+          const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + hsel * HALF);
+          const uint32_t ta = tx + C;
+          mbar_wait(acc_full(mb), nconv & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int g = 0; g < HALF / 16; ++g) {
+            uint32_t v[16], xr[16];
+            tmem_ld16(ta + g * 16, v);
+            if (second) tmem_ld16(tx + g * 16, xr);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + g * 16) + j4);
+              f[j4 * 4 + 0] = leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
+              f[j4 * 4 + 1] = leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
+              f[j4 * 4 + 2] = leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
+              f[j4 * 4 + 3] = leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
+            }
+            if (second) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(xr[j]);
+            }
+            if (!inside) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = 0.f;
+            }
+            if (second && !last) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xr[j] = __float_as_uint(f[j]);
+              tmem_st16(tx + g * 16, xr);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int chunk = (hsel * HALF + g * 16) / 8 + h;
+              const uint32_t o0 = pack2s(f[h * 8 + 0], f[h * 8 + 1], p.operand);
+              const uint32_t o1 = pack2s(f[h * 8 + 2], f[h * 8 + 3], p.operand);
+              const uint32_t o2 = pack2s(f[h * 8 + 4], f[h * 8 + 5], p.operand);
+              const uint32_t o3 = pack2s(f[h * 8 + 6], f[h * 8 + 7], p.operand);
+              if (!last) {
+                const uint32_t dst = dstbuf + static_cast<uint32_t>((chunk * R + row) * 16);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0),
+                             "r"(o1), "r"(o2), "r"(o3)
+                             : "memory");
+              } else if (inside && row >= kStackHalo && row < R - kStackHalo) {
+                const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk) * p.L + t;
+                if (p.y16 != nullptr)
+                  *reinterpret_cast<uint4*>(p.y16 + idx * 8) = make_uint4(o0, o1, o2, o3);
+                if (p.y32 != nullptr) {
+                  float4* d32 = reinterpret_cast<float4*>(p.y32 + idx * 8);
+                  d32[0] = make_float4(f[h * 8 + 0], f[h * 8 + 1], f[h * 8 + 2], f[h * 8 + 3]);
+                  d32[1] = make_float4(f[h * 8 + 4], f[h * 8 + 5], f[h * 8 + 6], f[h * 8 + 7]);
+                }
+              }
+            }
+          }
+          if (!last) {
+            if (second) tmem_st_wait();
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(act_ready(mb));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int C>
+ms_status launch_stack(const StackParams& p, cudaStream_t stream) {
+  using G = StackGeom<C>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resstack_kernel<C>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(resstack_kernel)");
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  resstack_kernel<C><<<grid, kStackThreads, G::SMEM, stream>>>(p);
+  return after_launch("resstack_kernel");
+}
+
+ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int operand,
+                       const float* x32, const void* packed, void* y16, float* y32,
+                       cudaStream_t stream) {
+  if (batch <= 0 || len <= 0 || x32 == nullptr || packed == nullptr ||
+      (y16 == nullptr && y32 == nullptr))
+    return MS_ERR_INVALID;
+  for (int i = 0; i < 3; ++i)
+    if (dil[i] < 1 || dil[i] > 9) return MS_ERR_INVALID;
+  // receptive field of the stack must fit the 16-row halo
+  if (dil[0] + dil[1] + dil[2] + 3 > kStackHalo) return MS_ERR_INVALID;
+  StackParams p;
+  p.x32 = x32;
+  p.w = static_cast<const uint16_t*>(packed);
+  p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) +
+                                          static_cast<size_t>(18) * channels * channels * 2);
+  p.y16 = static_cast<uint16_t*>(y16);
+  p.y32 = y32;
+  p.B = batch; p.L = len;
+  p.dil[0] = dil[0]; p.dil[1] = dil[1]; p.dil[2] = dil[2];
+  p.operand = operand;
+  int V;
+  switch (channels) {
+    case 128: V = StackGeom<128>::V; break;
+    case 64: V = StackGeom<64>::V; break;
+    case 32: V = StackGeom<32>::V; break;
+    default: return MS_ERR_INVALID;
+  }
+  p.tiles_per_clip = (len + V - 1) / V;
+  const long long tiles = static_cast<long long>(batch) * p.tiles_per_clip;
+  if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
+  p.total_tiles = static_cast<int>(tiles);
+  switch (channels) {
+    case 128: return launch_stack<128>(p, stream);
+    case 64: return launch_stack<64>(p, stream);
+    default: return launch_stack<32>(p, stream);
+  }
+}
+
+// packed[conv][tap][chunk][n][e] <- w_l (C, C, 3) fp32, then 6 x C fp32 biases
+__global__ void pack_stack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
+                                         int C, int operand) {
+  const int total = 3 * C * C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int e = i % 8;
+  const int n = (i / 8) % C;
+  const int c = (i / (8 * C)) % (C / 8);
+  const int t = i / (C * C);
+  const float v = w[(static_cast<size_t>(n) * C + c * 8 + e) * 3 + t];
+  if (operand == MS_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  } else {
+    __half h = __float2half_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int ms_resstack_supported(int channels) {
+  return channels == 128 || channels == 64 || channels == 32;
+}
+
+size_t ms_resstack_packed_weight_bytes(int channels) {
+  if (!ms_resstack_supported(channels)) return 0;
+  return static_cast<size_t>(18) * channels * channels * 2 + sizeof(float) * 6 * channels;
+}
+
+ms_status ms_resstack_pack_weights(const float* const* params, int channels, int operand,
+                                   void* packed, void* stream) {
+  if (params == nullptr || packed == nullptr || !ms_resstack_supported(channels))
+    return MS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  const size_t conv_bytes = static_cast<size_t>(3) * channels * channels * 2;
+  float* bias = reinterpret_cast<float*>(base + 6 * conv_bytes);
+  const int total = 3 * channels * channels;
+  for (int l = 0; l < 6; ++l) {
+    pack_stack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(
+        params[2 * l], reinterpret_cast<uint16_t*>(base + l * conv_bytes), channels, operand);
+    ms_status s = after_launch("pack_stack_weight_kernel");
+    if (s != MS_OK) return s;
+    s = check_cuda(cudaMemcpyAsync(bias + l * channels, params[2 * l + 1],
+                                   sizeof(float) * channels, cudaMemcpyDeviceToDevice, st),
+                   "cudaMemcpyAsync(stack bias)");
+    if (s != MS_OK) return s;
+  }
+  return MS_OK;
+}
+
+ms_status ms_resstack_fwd(int channels, int batch, int len, const int* dilations, int operand,
+                          const float* x32, const void* packed, void* y16, float* y32,
+                          void* stream) {
+  if (dilations == nullptr || !ms_resstack_supported(channels)) return MS_ERR_INVALID;
+  return resstack_fwd(channels, batch, len, dilations, operand, x32, packed, y16, y32,
+                      static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

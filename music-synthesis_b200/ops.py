@@ -101,6 +101,37 @@ def audio2mel(audio, window, mel_basis, n_fft, hop):
     return out
 
 
+def resstack_supported(channels):
+    return bool(_lib.lib().ms_resstack_supported(channels))
+
+
+def resstack_pack_weights(params, channels, operand=MS_F16):
+    """12 tensors (w,b of main.{a}.main.{0,1}) -> packed blob for the fused stack."""
+    L = _lib.lib()
+    n = L.ms_resstack_packed_weight_bytes(channels)
+    if n == 0 or len(params) != 12:
+        raise _lib.MsbError("fused ResidualStack: unsupported configuration")
+    keep = [p.detach().contiguous() for p in params]
+    for p in keep:
+        _lib.require_cuda(p, "parameter")
+    arr = (ctypes.c_void_p * 12)(*[p.data_ptr() for p in keep])
+    blob = torch.empty(n, dtype=torch.uint8, device=keep[0].device)
+    check(L.ms_resstack_pack_weights(arr, channels, operand, ptr(blob), stream_ptr()),
+          "ms_resstack_pack_weights")
+    return blob
+
+
+def resstack_fwd(x32, blob, dilations, operand=MS_F16, want16=False, want32=True):
+    """Fused ResidualStack on a BLK f32 tensor (B,C/8,L,8).  Returns (y16, y32)."""
+    B, C8, L, _ = x32.shape
+    y16 = torch.empty((B, C8, L, 8), dtype=torch.int16, device=x32.device) if want16 else None
+    y32 = torch.empty_like(x32) if want32 else None
+    dil = (ctypes.c_int * 3)(*dilations)
+    check(_lib.lib().ms_resstack_fwd(C8 * 8, B, L, dil, operand, ptr(x32), ptr(blob), ptr(y16),
+                                     ptr(y32), stream_ptr()), "ms_resstack_fwd")
+    return y16, y32
+
+
 class MelGanWeights:
     """Packed parameter blob of a MelGanGenerator (60 state-dict tensors, in order)."""
 

@@ -94,9 +94,25 @@ class ResidualStack(nn.Module):
         self.operand = operand
         self.main = nn.Sequential(
             *[ResidualAtom(channels, d, add_weight_norm, operand) for d in dilations])
+        self._blob = None
+        self._blob_key = None
+
+    def _fused_blob(self):
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if key != self._blob_key:
+            self._blob = ops.resstack_pack_weights(params, self.channels, self.operand)
+            self._blob_key = key
+        return self._blob
 
     def forward(self, x):
         _no_grad_check(x, *self.parameters())
+        if (len(self.dilations) == 3 and ops.resstack_supported(self.channels)
+                and sum(self.dilations) + 3 <= 16):
+            # one fused kernel: activations in SMEM, fp32 residual stream in TMEM
+            _, y32 = ops.resstack_fwd(_blk32_from_ncl(x), self._fused_blob(),
+                                      list(self.dilations), self.operand)
+            return ops.unpack_blk32(y32)
         x16 = ops.pack_ncl(x, operand=self.operand)
         x32 = _blk32_from_ncl(x)
         for atom in self.main:

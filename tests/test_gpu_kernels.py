@@ -150,3 +150,37 @@ def test_bad_descriptors_are_rejected(ops):
         ops.conv_out_len(ops.conv_desc(ops.MS_CONVT, 1, 32, 32, 100, 5, 1, 1, 2))  # k != 2s
     with pytest.raises(MsbError):
         ops.pack_ncl(torch.zeros(1, 8, 16))  # CPU tensor: no CPU path
+
+
+def _stack_emulated(x, sd, operand="f16"):
+    """ResidualStack with exactly the kernel's rounding points: 16-bit operands
+    (activations and weights), fp64 accumulate, fp32-like residual stream."""
+    x = x.double()
+    for a, d in enumerate((1, 3, 9)):
+        w1, b1 = sd[f"s.main.{a}.main.0.weight"], sd[f"s.main.{a}.main.0.bias"]
+        w2, b2 = sd[f"s.main.{a}.main.1.weight"], sd[f"s.main.{a}.main.1.bias"]
+        y = F.leaky_relu(F.conv1d(rnd16(x.float(), operand).double(), rnd16(w1, operand).double(),
+                                  b1.double(), dilation=d, padding=d), 0.2)
+        y = F.leaky_relu(F.conv1d(rnd16(y.float(), operand).double(), rnd16(w2, operand).double(),
+                                  b2.double(), padding=1), 0.2)
+        x = x + y
+    return x
+
+
+@pytest.mark.parametrize("C,B,L", [(128, 1, 224), (128, 2, 1000), (64, 2, 480), (64, 1, 1500),
+                                   (32, 1, 992), (32, 3, 2500), (128, 3, 50)])
+def test_fused_residual_stack(ops, C, B, L):
+    from oracle import synth
+    sd = synth.residual_stack_state(50 + C, C)
+    x = randn(51, B, C, L, scale=0.5)
+    ref = _stack_emulated(x, sd)
+    params = []
+    for a in range(3):
+        for c in range(2):
+            params += [sd[f"s.main.{a}.main.{c}.weight"].cuda(), sd[f"s.main.{a}.main.{c}.bias"].cuda()]
+    blob = ops.resstack_pack_weights(params, C)
+    y16, y32 = ops.resstack_fwd(_blk32(x).cuda(), blob, [1, 3, 9], want16=True, want32=True)
+    torch.cuda.synchronize()
+    got = ops.unpack_blk32(y32).cpu()
+    assert rel_l2(got, ref) < TIGHT
+    assert torch.equal(ops.unpack_blk16(y16).cpu(), rnd16(got))
