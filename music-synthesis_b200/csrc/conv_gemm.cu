@@ -192,7 +192,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           fence_proxy_async_smem();
           __syncwarp();
         }
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t bytes_a = static_cast<uint32_t>(nrows) * 16u * chunks;
           mbar_arrive_expect_tx(full_bar(stage), bytes_a + p.w_stage_bytes);
           const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) +
@@ -216,10 +216,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    // Warp-uniform loop; only the tcgen05 instructions are predicated on one elected
+    // lane so the descriptors live in uniform registers.
+    {
       const uint32_t idesc = umma_idesc_f16(p.NT, p.operand);
-      const uint32_t lbo_a = static_cast<uint32_t>(p.RA) * 16u;
-      const uint32_t lbo_b = static_cast<uint32_t>(p.NT) * 16u;
+      const uint64_t adesc0 = umma_desc_base_nosw(static_cast<uint32_t>(p.RA) * 16u, 128);
+      const uint64_t bdesc0 = umma_desc_base_nosw(static_cast<uint32_t>(p.NT) * 16u, 128);
+      const uint32_t a_kstep = static_cast<uint32_t>(2 * p.RA);   // 16-byte units per k16
+      const uint32_t b_kstep = static_cast<uint32_t>(2 * p.NT);
+      const int nk16 = p.KB >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -233,24 +238,25 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           tc_fence_after();
           const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
           const uint32_t sW = sA + p.a_stage_bytes;
-          for (int t = 0; t < p.taps; ++t) {
-            const uint32_t a_tap = sA + static_cast<uint32_t>(p.off[t] - p.min_off) * 16u;
-            const uint32_t w_tap = sW + static_cast<uint32_t>(t * chunks * p.NT) * 16u;
-            for (int k16 = 0; k16 < (p.KB >> 4); ++k16) {
-              const uint64_t ad =
-                  umma_desc_nosw(a_tap + static_cast<uint32_t>(2 * k16 * p.RA) * 16u, lbo_a, 128);
-              const uint64_t bd =
-                  umma_desc_nosw(w_tap + static_cast<uint32_t>(2 * k16 * p.NT) * 16u, lbo_b, 128);
-              umma_f16_ss(d_tmem, ad, bd, idesc, (kb | t | k16) != 0 ? 1u : 0u);
+          if (elect_one()) {
+            for (int t = 0; t < p.taps; ++t) {
+              uint64_t ad = adesc0 + ((sA >> 4) + static_cast<uint32_t>(p.off[t] - p.min_off));
+              uint64_t bd = bdesc0 + ((sW >> 4) + static_cast<uint32_t>(t * chunks * p.NT));
+              for (int k16 = 0; k16 < nk16; ++k16) {
+                umma_f16_ss(d_tmem, ad, bd, idesc, (kb | t | k16) != 0 ? 1u : 0u);
+                ad += a_kstep;
+                bd += b_kstep;
+              }
             }
+            umma_commit(empty_bar(stage));
+            if (kb == p.nkb - 1) umma_commit(tfull_bar(acc));
           }
-          umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }

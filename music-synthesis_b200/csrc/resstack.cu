@@ -29,7 +29,6 @@
 namespace msb {
 
 constexpr int kStackHalo = 16;
-constexpr int kStackThreads = 320;       // 10 warps
 constexpr int kStackHeader = 1024;
 
 struct StackParams {
@@ -42,7 +41,18 @@ struct StackParams {
   int dil[3];
   int tiles_per_clip, total_tiles;
   int operand;
+  long long* dbg;        // optional clock trace of CTA 0 (null in production)
 };
+
+#ifdef MSB_STACK_TRACE
+#define MSB_TRACE(slot)                                                     \
+  do {                                                                      \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0)     \
+      p.dbg[(slot)] = clock64();                                            \
+  } while (0)
+#else
+#define MSB_TRACE(slot) do { } while (0)
+#endif
 
 template <int C>
 struct StackGeom {
@@ -64,8 +74,8 @@ __device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
   return pack_h2(a, b);
 }
 
-template <int C>
-__global__ void __launch_bounds__(kStackThreads, 1)
+template <int C, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 resstack_kernel(const __grid_constant__ StackParams p) {
   using G = StackGeom<C>;
   constexpr int MB = G::MB, R = G::R, NSLOT = G::NSLOT;
@@ -92,7 +102,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
     }
     for (int m = 0; m < 8; ++m) {
       mbar_init(acc_full(m), 1);
-      mbar_init(act_ready(m), 256);
+      mbar_init(act_ready(m), 32 * EW);
     }
     fence_mbar_init();
   }
@@ -107,24 +117,29 @@ resstack_kernel(const __grid_constant__ StackParams p) {
 
   if (warp == 0) {
     // ======================= weight-tap producer =========================
-    if (lane == 0) {
-      uint32_t pos = 0;  // running tap counter (ring position)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        for (int tap = 0; tap < 18; ++tap, ++pos) {
-          const int slot = pos % NSLOT;
-          const uint32_t par = (pos / NSLOT) & 1u;
-          mbar_wait(wempty(slot), par ^ 1u);
+    uint32_t pos = 0;  // running tap counter (ring position)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tap = 0; tap < 18; ++tap, ++pos) {
+        const int slot = pos % NSLOT;
+        const uint32_t par = (pos / NSLOT) & 1u;
+        mbar_wait(wempty(slot), par ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(wfull(slot), G::TAP_BYTES);
           bulk_g2s(sW + slot * G::TAP_BYTES,
                    reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(tap) * G::TAP_BYTES,
                    G::TAP_BYTES, wfull(slot));
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
+    // Warp-uniform control flow; only the tcgen05 instructions are predicated on one
+    // elected lane, so descriptors stay in uniform registers.
+    {
       const uint32_t idesc = umma_idesc_f16(C, p.operand);
+      const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);
+      const uint64_t bdesc0 = umma_desc_base_nosw(C * 16, 128);
       uint32_t pos = 0;      // ring position of the current conv's first tap
       uint32_t nconv = 0;    // convs issued so far (parity of act_ready waits)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -135,169 +150,216 @@ resstack_kernel(const __grid_constant__ StackParams p) {
           auto issue = [&](int mb, int t, bool first) {
             const int slot = (pos + t) % NSLOT;
             const int shift = (t - 1) * d;
-            const uint32_t a0 = src + static_cast<uint32_t>((mb * 128 + shift) * 16);
-            const uint32_t b0 = sW + slot * G::TAP_BYTES;
+            const uint64_t ad = adesc0 + ((src + static_cast<uint32_t>((mb * 128 + shift) * 16)) >> 4);
+            const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(slot * G::TAP_BYTES)) >> 4);
             const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
+            if (elect_one()) {
 #pragma unroll
-            for (int k16 = 0; k16 < C / 16; ++k16) {
-              const uint64_t ad = umma_desc_nosw(a0 + static_cast<uint32_t>(2 * k16 * R * 16),
-                                                 R * 16, 128);
-              const uint64_t bd = umma_desc_nosw(b0 + static_cast<uint32_t>(2 * k16 * C * 16),
-                                                 C * 16, 128);
-              umma_f16_ss(dst, ad, bd, idesc, (first && k16 == 0) ? 0u : 1u);
+              for (int k16 = 0; k16 < C / 16; ++k16)
+                umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * (2 * R * 16 / 16)),
+                            bd + static_cast<uint64_t>(k16 * (2 * C * 16 / 16)), idesc,
+                            (first && k16 == 0) ? 0u : 1u);
             }
+            __syncwarp();
           };
           auto wait_tap = [&](int t) {
             const uint32_t q = pos + t;
             mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u);
           };
-          auto free_tap = [&](int t) { umma_commit(wempty((pos + t) % NSLOT)); };
+          auto commit = [&](uint32_t bar) {
+            if (elect_one()) umma_commit(bar);
+            __syncwarp();
+          };
           for (int mb = 0; mb < MB; ++mb) {
+            if (nconv < 12) MSB_TRACE(nconv * 16 + mb * 4 + 0);
             mbar_wait(act_ready(mb), ready_par);
             tc_fence_after();
+            if (nconv < 12) MSB_TRACE(nconv * 16 + mb * 4 + 1);
             if (mb == 0) wait_tap(0);
+            if (nconv < 12) MSB_TRACE(nconv * 16 + mb * 4 + 2);
             issue(mb, 0, true);
-            if (mb == MB - 1) free_tap(0);
+            if (mb == MB - 1) commit(wempty((pos + 0) % NSLOT));
             if (mb == 0) wait_tap(1);
             issue(mb, 1, false);
-            if (mb == MB - 1) free_tap(1);
+            if (mb == MB - 1) commit(wempty((pos + 1) % NSLOT));
             if (mb >= 1) {
               if (mb == 1) wait_tap(2);
               issue(mb - 1, 2, false);
-              umma_commit(acc_full(mb - 1));
+              commit(acc_full(mb - 1));
             }
           }
           if (MB == 1) wait_tap(2);
           issue(MB - 1, 2, false);
-          free_tap(2);
-          umma_commit(acc_full(MB - 1));
+          commit(wempty((pos + 2) % NSLOT));
+          commit(acc_full(MB - 1));
+          if (nconv < 12) MSB_TRACE(nconv * 16 + 15);
         }
       }
     }
   } else {
     // ====================== prologue / epilogue warps ======================
-    const int e = warp - 2;            // 0..7
+    const int e = warp - 2;            // 0 .. EW-1
     const int q = warp & 3;            // TMEM lane quarter accessible to this warp
-    const int hsel = e >> 2;           // which half of the channels
-    constexpr int HALF = C / 2;
+    const int part = e >> 2;           // which slice of the channels
+    constexpr int COLS = C / (EW / 4); // channels per thread
+    constexpr int NG = COLS / 16;      // 16-column groups per thread
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     uint32_t nconv = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_clip;
       const int t0 = (tile % p.tiles_per_clip) * G::V - kStackHalo;  // clip row of tile row 0
+      const bool edge = (t0 < 0) || (t0 + R > p.L);                 // warp-uniform
       // ---- prologue: x32 (global) -> TMEM residual stream + 16-bit operand in sX
+      if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(480 + (nconv / 6) * 2);
       for (int mb = 0; mb < MB; ++mb) {
         const int row = mb * 128 + q * 32 + lane;
         const int t = t0 + row;
         const bool inside = (t >= 0) && (t < p.L);
-        const uint32_t tx = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                            static_cast<uint32_t>(mb * 2 * C + hsel * HALF);
+        const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
+        const int chunk0 = part * (COLS / 8);
+        const float4* src = reinterpret_cast<const float4*>(
+            p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8);
+        const size_t cstride = static_cast<size_t>(p.L) * 2;   // float4 per chunk
+        uint32_t v[COLS];
 #pragma unroll
-        for (int g = 0; g < HALF / 16; ++g) {
-          uint32_t v[16];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int chunk = (hsel * HALF + g * 16) / 8 + h;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-            if (inside) {
-              const float4* src = reinterpret_cast<const float4*>(
-                  p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk) * p.L + t) * 8);
-              a = __ldg(src);
-              c = __ldg(src + 1);
-            }
-            v[h * 8 + 0] = __float_as_uint(a.x); v[h * 8 + 1] = __float_as_uint(a.y);
-            v[h * 8 + 2] = __float_as_uint(a.z); v[h * 8 + 3] = __float_as_uint(a.w);
-            v[h * 8 + 4] = __float_as_uint(c.x); v[h * 8 + 5] = __float_as_uint(c.y);
-            v[h * 8 + 6] = __float_as_uint(c.z); v[h * 8 + 7] = __float_as_uint(c.w);
-            const uint32_t dst = sX + static_cast<uint32_t>((chunk * R + row) * 16);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                         "r"(pack2s(a.x, a.y, p.operand)), "r"(pack2s(a.z, a.w, p.operand)),
-                         "r"(pack2s(c.x, c.y, p.operand)), "r"(pack2s(c.z, c.w, p.operand))
-                         : "memory");
+        for (int c = 0; c < COLS / 8; ++c) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d4 = a;
+          if (inside) {
+            a = __ldg(src + c * cstride);
+            d4 = __ldg(src + c * cstride + 1);
           }
-          tmem_st16(tx + g * 16, v);
+          v[c * 8 + 0] = __float_as_uint(a.x); v[c * 8 + 1] = __float_as_uint(a.y);
+          v[c * 8 + 2] = __float_as_uint(a.z); v[c * 8 + 3] = __float_as_uint(a.w);
+          v[c * 8 + 4] = __float_as_uint(d4.x); v[c * 8 + 5] = __float_as_uint(d4.y);
+          v[c * 8 + 6] = __float_as_uint(d4.z); v[c * 8 + 7] = __float_as_uint(d4.w);
         }
+#pragma unroll
+        for (int c = 0; c < COLS / 8; ++c) {
+          const uint32_t dst = sX + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
+          st_shared_v4(dst,
+                       pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), p.operand),
+                       pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), p.operand),
+                       pack2s(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]), p.operand),
+                       pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), p.operand));
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(act_ready(mb));
       }
+      if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(480 + (nconv / 6) * 2 + 1);
       // ---- six convolutions
       for (int l = 0; l < 6; ++l, ++nconv) {
         const bool second = (l & 1) != 0;     // second conv of an atom: residual add
         const bool last = (l == 5);
         const uint32_t dstbuf = second ? sX : sY;
-        const float* bias = p.bias + l * C + hsel * HALF;
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * C + part * COLS);
+        if (l == 4) {
+          // warm L2 with the next tile's input while this tile finishes
+          const int ntile = tile + gridDim.x;
+          if (ntile < p.total_tiles) {
+            const int nb = ntile / p.tiles_per_clip;
+            const int nt0 = (ntile % p.tiles_per_clip) * G::V - kStackHalo;
+            for (int mb = 0; mb < MB; ++mb) {
+              const int t = nt0 + mb * 128 + q * 32 + lane;
+              if (t >= 0 && t < p.L && (lane & 3) == 0) {
+#pragma unroll
+                for (int c = 0; c < COLS / 8; ++c)
+                  prefetch_l2(p.x32 + ((static_cast<size_t>(nb) * G::NCH + part * (COLS / 8) + c) *
+                                           p.L + t) * 8);
+              }
+            }
+          }
+        }
         for (int mb = 0; mb < MB; ++mb) {
           const int row = mb * 128 + q * 32 + lane;
           const int t = t0 + row;
-          const bool inside = (t >= 0) && (t < p.L);
-          const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-          const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + hsel * HALF);
+          const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
           const uint32_t ta = tx + C;
+          if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(256 + nconv * 16 + mb * 4 + 0);
           mbar_wait(acc_full(mb), nconv & 1u);
           tc_fence_after();
+          if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(256 + nconv * 16 + mb * 4 + 1);
+          uint32_t v[COLS];
 #pragma unroll
-          for (int g = 0; g < HALF / 16; ++g) {
-            uint32_t v[16], xr[16];
-            tmem_ld16(ta + g * 16, v);
-            if (second) tmem_ld16(tx + g * 16, xr);
+          for (int g = 0; g < NG; ++g) tmem_ld16p(ta + g * 16, &v[g * 16]);
+          float f[COLS];
+          if (second) {
+            uint32_t xr[COLS];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) tmem_ld16p(tx + g * 16, &xr[g * 16]);
             tmem_ld_wait();
-            float f[16];
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + g * 16) + j4);
+            for (int j4 = 0; j4 < COLS / 4; ++j4) {
+              const float4 bv = __ldg(bias4 + j4);
+              f[j4 * 4 + 0] = __uint_as_float(xr[j4 * 4 + 0]) + leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
+              f[j4 * 4 + 1] = __uint_as_float(xr[j4 * 4 + 1]) + leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
+              f[j4 * 4 + 2] = __uint_as_float(xr[j4 * 4 + 2]) + leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
+              f[j4 * 4 + 3] = __uint_as_float(xr[j4 * 4 + 3]) + leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
+            }
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < COLS / 4; ++j4) {
+              const float4 bv = __ldg(bias4 + j4);
               f[j4 * 4 + 0] = leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
               f[j4 * 4 + 1] = leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
               f[j4 * 4 + 2] = leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
               f[j4 * 4 + 3] = leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
             }
-            if (second) {
+          }
+          if (edge) {
+            if (t < 0 || t >= p.L) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(xr[j]);
-            }
-            if (!inside) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = 0.f;
-            }
-            if (second && !last) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) xr[j] = __float_as_uint(f[j]);
-              tmem_st16(tx + g * 16, xr);
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int chunk = (hsel * HALF + g * 16) / 8 + h;
-              const uint32_t o0 = pack2s(f[h * 8 + 0], f[h * 8 + 1], p.operand);
-              const uint32_t o1 = pack2s(f[h * 8 + 2], f[h * 8 + 3], p.operand);
-              const uint32_t o2 = pack2s(f[h * 8 + 4], f[h * 8 + 5], p.operand);
-              const uint32_t o3 = pack2s(f[h * 8 + 6], f[h * 8 + 7], p.operand);
-              if (!last) {
-                const uint32_t dst = dstbuf + static_cast<uint32_t>((chunk * R + row) * 16);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0),
-                             "r"(o1), "r"(o2), "r"(o3)
-                             : "memory");
-              } else if (inside && row >= kStackHalo && row < R - kStackHalo) {
-                const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk) * p.L + t;
-                if (p.y16 != nullptr)
-                  *reinterpret_cast<uint4*>(p.y16 + idx * 8) = make_uint4(o0, o1, o2, o3);
-                if (p.y32 != nullptr) {
-                  float4* d32 = reinterpret_cast<float4*>(p.y32 + idx * 8);
-                  d32[0] = make_float4(f[h * 8 + 0], f[h * 8 + 1], f[h * 8 + 2], f[h * 8 + 3]);
-                  d32[1] = make_float4(f[h * 8 + 4], f[h * 8 + 5], f[h * 8 + 6], f[h * 8 + 7]);
-                }
-              }
+              for (int j = 0; j < COLS; ++j) f[j] = 0.f;
             }
           }
           if (!last) {
+            if (second) {
+#pragma unroll
+              for (int j = 0; j < COLS; ++j) v[j] = __float_as_uint(f[j]);
+#pragma unroll
+              for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+            }
+#pragma unroll
+            for (int c = 0; c < COLS / 8; ++c) {
+              const uint32_t dst =
+                  dstbuf + static_cast<uint32_t>(((part * (COLS / 8) + c) * R + row) * 16);
+              st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
+                           pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
+                           pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
+                           pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
+            }
             if (second) tmem_st_wait();
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(act_ready(mb));
+          } else if (t >= 0 && t < p.L && row >= kStackHalo && row < R - kStackHalo) {
+#pragma unroll
+            for (int c = 0; c < COLS / 8; ++c) {
+              const size_t idx =
+                  (static_cast<size_t>(b) * G::NCH + part * (COLS / 8) + c) * p.L + t;
+              if (p.y16 != nullptr)
+                *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
+                    make_uint4(pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
+                               pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
+                               pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
+                               pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
+              if (p.y32 != nullptr) {
+                float4* d32 = reinterpret_cast<float4*>(p.y32 + idx * 8);
+                d32[0] = make_float4(f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3]);
+                d32[1] = make_float4(f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]);
+              }
+            }
           }
+          if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(256 + nconv * 16 + mb * 4 + 2);
         }
       }
     }
   }
+
 
   tc_fence_before();
   __syncthreads();
@@ -307,12 +369,12 @@ resstack_kernel(const __grid_constant__ StackParams p) {
   }
 }
 
-template <int C>
+template <int C, int EW>
 ms_status launch_stack(const StackParams& p, cudaStream_t stream) {
   using G = StackGeom<C>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resstack_kernel<C>,
+    cudaError_t e = cudaFuncSetAttribute(resstack_kernel<C, EW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(resstack_kernel)");
     attr_set = true;
@@ -320,9 +382,11 @@ ms_status launch_stack(const StackParams& p, cudaStream_t stream) {
   const int sms = sm_count();
   if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  resstack_kernel<C><<<grid, kStackThreads, G::SMEM, stream>>>(p);
+  resstack_kernel<C, EW><<<grid, 64 + 32 * EW, G::SMEM, stream>>>(p);
   return after_launch("resstack_kernel");
 }
+
+static thread_local long long* g_stack_dbg = nullptr;
 
 ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int operand,
                        const float* x32, const void* packed, void* y16, float* y32,
@@ -344,6 +408,7 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   p.B = batch; p.L = len;
   p.dil[0] = dil[0]; p.dil[1] = dil[1]; p.dil[2] = dil[2];
   p.operand = operand;
+  p.dbg = g_stack_dbg;
   int V;
   switch (channels) {
     case 128: V = StackGeom<128>::V; break;
@@ -356,9 +421,9 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
   p.total_tiles = static_cast<int>(tiles);
   switch (channels) {
-    case 128: return launch_stack<128>(p, stream);
-    case 64: return launch_stack<64>(p, stream);
-    default: return launch_stack<32>(p, stream);
+    case 128: return launch_stack<128, 8>(p, stream);
+    case 64: return launch_stack<64, 8>(p, stream);
+    default: return launch_stack<32, 8>(p, stream);
   }
 }
 
@@ -387,6 +452,10 @@ __global__ void pack_stack_weight_kernel(const float* __restrict__ w, uint16_t* 
 using namespace msb;
 
 extern "C" {
+
+/* debugging aid (not in the public header): clock64 trace buffer (512 x int64, device)
+ * filled by CTA 0 of subsequent ms_resstack_fwd launches from this thread */
+void ms_debug_set_stack_trace(long long* dev_buf) { msb::g_stack_dbg = dev_buf; }
 
 int ms_resstack_supported(int channels) {
   return channels == 128 || channels == 64 || channels == 32;

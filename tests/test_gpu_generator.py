@@ -80,7 +80,7 @@ def test_generator_refuses_cpu_and_autograd():
     m = _module(restate.melgan_generator_state(5))
     with pytest.raises(MsbError):
         m(torch.zeros(1, 128, 8))                      # CPU input: no CPU path
-    with pytest.raises(MsbError):
+    with torch.enable_grad(), pytest.raises(MsbError):
         m(torch.zeros(1, 128, 8, device="cuda"))       # grad enabled: forward-only
 
 
