@@ -8,11 +8,16 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libmsb200.so")
 SOURCES = ["runtime.cu", "conv_gemm.cu", "layout.cu", "generator.cu", "audio2mel.cu",
-           "resstack.cu"]
+           "resstack.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
 ]
+
+
+def _extra_flags():
+    """MSB_NVCC_EXTRA="-DMSB_STACK_TRACE" enables the clock64 trace points."""
+    return os.environ.get("MSB_NVCC_EXTRA", "").split()
 
 
 def _nvcc():
@@ -39,7 +44,7 @@ def build_library(force=False, verbose=False):
         o = s[:-3] + ".o"
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o])
+            jobs.append([nvcc] + NVCC_FLAGS + _extra_flags() + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,0 +1,146 @@
+// Debug-only microbenchmarks of the synchronisation / issue primitives the kernels are
+// built from (not part of the public ABI; used by tools/microbench.py).
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+// out[i] = cycles for primitive i (single warp, CTA 0)
+__global__ void __launch_bounds__(128, 1) microbench_kernel(long long* out) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  const uint32_t bar0 = smem_u32(bars), bar1 = bar0 + 8, bar2 = bar0 + 16;
+  const uint32_t sA = smem_u32(smem + 1024);          // 64 KB of A
+  const uint32_t sB = sA + 65536;                     // 64 KB of B
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1); mbar_init(bar1, 1); mbar_init(bar2, 1);
+    fence_mbar_init();
+  }
+  // zero operands
+  for (int i = threadIdx.x; i < 131072 / 16; i += blockDim.x)
+    st_shared_v4(sA + i * 16, 0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    int slot = 0;
+    long long t0, t1;
+    // (0) clock overhead
+    t0 = clock64(); t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = t1 - t0; slot++;
+    // (1) mbarrier arrive + try_wait on completed phase
+    if (threadIdx.x == 0) mbar_arrive(bar0);
+    __syncwarp();
+    t0 = clock64();
+    mbar_wait(bar0, 0);
+    t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = t1 - t0; slot++;
+    // (2) elect_one + syncwarp x4
+    t0 = clock64();
+    int acc = 0;
+    for (int i = 0; i < 4; ++i) { if (elect_one()) acc++; __syncwarp(); }
+    t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = (t1 - t0) / 4 + (acc > 100); slot++;
+    // (3) tc_fence_after x4
+    t0 = clock64();
+    for (int i = 0; i < 4; ++i) tc_fence_after();
+    t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = (t1 - t0) / 4; slot++;
+    // (4) commit with nothing outstanding + wait
+    t0 = clock64();
+    if (elect_one()) umma_commit(bar1);
+    __syncwarp();
+    t1 = clock64();
+    mbar_wait(bar1, 0);
+    long long t2 = clock64();
+    if (threadIdx.x == 0) { out[slot] = t1 - t0; out[slot + 1] = t2 - t1; } slot += 2;
+    // (6..) MMA issue / completion for N in {32,64,128,256}, 16 MMAs each, same accumulator
+    uint32_t par1 = 1, par2 = 0;
+    const int Ns[4] = {32, 64, 128, 256};
+    for (int ni = 0; ni < 4; ++ni) {
+      const int N = Ns[ni];
+      const uint32_t idesc = umma_idesc_f16(N, 0);
+      const uint64_t ad = umma_desc_base_nosw(256 * 16, 128) + (sA >> 4);
+      const uint64_t bd = umma_desc_base_nosw(N * 16, 128) + (sB >> 4);
+      for (int variant = 0; variant < 2; ++variant) {   // 0: same accumulator, 1: alternate 2
+        __syncwarp();
+        t0 = clock64();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_f16_ss(tmem + (variant ? (k & 1) * 256 : 0), ad + (k & 7) * 512, bd + (k & 7) * 2 * N, idesc, 1u);
+        }
+        __syncwarp();
+        t1 = clock64();
+        if (elect_one()) umma_commit(bar1);
+        __syncwarp();
+        mbar_wait(bar1, par1); par1 ^= 1;
+        t2 = clock64();
+        if (threadIdx.x == 0) { out[slot] = (t1 - t0); out[slot + 1] = (t2 - t0); }
+        slot += 2;
+      }
+    }
+    // (22) 64 MMAs N=128 back-to-back, to see the steady state rate
+    {
+      const uint32_t idesc = umma_idesc_f16(128, 0);
+      const uint64_t ad = umma_desc_base_nosw(256 * 16, 128) + (sA >> 4);
+      const uint64_t bd = umma_desc_base_nosw(128 * 16, 128) + (sB >> 4);
+      __syncwarp();
+      t0 = clock64();
+      if (elect_one()) {
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k)
+          umma_f16_ss(tmem, ad + (k & 7) * 512, bd + (k & 7) * 256, idesc, 1u);
+      }
+      __syncwarp();
+      t1 = clock64();
+      if (elect_one()) umma_commit(bar1);
+      __syncwarp();
+      mbar_wait(bar1, par1); par1 ^= 1;
+      t2 = clock64();
+      if (threadIdx.x == 0) { out[slot] = (t1 - t0); out[slot + 1] = (t2 - t0); }
+      slot += 2;
+    }
+    // (24) 64 MMAs N=32
+    {
+      const uint32_t idesc = umma_idesc_f16(32, 0);
+      const uint64_t ad = umma_desc_base_nosw(256 * 16, 128) + (sA >> 4);
+      const uint64_t bd = umma_desc_base_nosw(32 * 16, 128) + (sB >> 4);
+      __syncwarp();
+      t0 = clock64();
+      if (elect_one()) {
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k)
+          umma_f16_ss(tmem + (k & 3) * 64, ad + (k & 7) * 512, bd + (k & 7) * 64, idesc, 1u);
+      }
+      __syncwarp();
+      t1 = clock64();
+      if (elect_one()) umma_commit(bar1);
+      __syncwarp();
+      mbar_wait(bar1, par1); par1 ^= 1;
+      t2 = clock64();
+      if (threadIdx.x == 0) { out[slot] = (t1 - t0); out[slot + 1] = (t2 - t0); }
+      slot += 2;
+    }
+    (void)par2; (void)bar2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+}  // namespace msb
+
+extern "C" int ms_debug_microbench(long long* dev_out, void* stream) {
+  const int smem = 1024 + 131072;
+  cudaFuncSetAttribute(msb::microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  msb::microbench_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(dev_out);
+  return msb::after_launch("microbench_kernel");
+}

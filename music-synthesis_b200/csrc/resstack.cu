@@ -47,7 +47,8 @@ struct StackParams {
 #ifdef MSB_STACK_TRACE
 #define MSB_TRACE(slot)                                                     \
   do {                                                                      \
-    if (p.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0)     \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 &&   \
+        nconv < 12)                                                         \
       p.dbg[(slot)] = clock64();                                            \
   } while (0)
 #else
@@ -57,6 +58,10 @@ struct StackParams {
 template <int C>
 struct StackGeom {
   static constexpr int MB = 256 / C;             // M-blocks per tile
+  static constexpr int HB = MB / 2 > 0 ? MB / 2 : 1;   // M-blocks per half tile
+  static constexpr int PARTS = C >= 128 ? 4 : 2;       // column split of the epilogue
+  static constexpr int MSPLIT = 4 / PARTS;             // M-block split of the epilogue
+  static constexpr int EW = 16;                        // epilogue warps = 4 * PARTS * MSPLIT
   static constexpr int R = MB * 128;             // rows per tile
   static constexpr int V = R - 2 * kStackHalo;   // rows stored per tile
   static constexpr int NCH = C / 8;
@@ -74,11 +79,12 @@ __device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
   return pack_h2(a, b);
 }
 
-template <int C, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+template <int C>
+__global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
 resstack_kernel(const __grid_constant__ StackParams p) {
   using G = StackGeom<C>;
-  constexpr int MB = G::MB, R = G::R, NSLOT = G::NSLOT;
+  constexpr int MB = G::MB, HB = G::HB, R = G::R, NSLOT = G::NSLOT, EW = G::EW;
+  static_assert(MB >= 2 && MB == 2 * HB, "tile must split into two halves");
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   // [0,18) wfull  [18,36) wempty  [36,44) acc_full  [44,52) act_ready
@@ -147,18 +153,22 @@ resstack_kernel(const __grid_constant__ StackParams p) {
           const int d = (l & 1) ? 1 : p.dil[l >> 1];
           const uint32_t src = (l & 1) ? sY : sX;
           const uint32_t ready_par = nconv & 1u;
-          auto issue = [&](int mb, int t, bool first) {
+          // one elected lane issues tap t for M-blocks [mb0, mb1)
+          auto issue = [&](int t, int mb0, int mb1) {
             const int slot = (pos + t) % NSLOT;
             const int shift = (t - 1) * d;
-            const uint64_t ad = adesc0 + ((src + static_cast<uint32_t>((mb * 128 + shift) * 16)) >> 4);
             const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(slot * G::TAP_BYTES)) >> 4);
-            const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
             if (elect_one()) {
+              for (int mb = mb0; mb < mb1; ++mb) {
+                const uint64_t ad =
+                    adesc0 + ((src + static_cast<uint32_t>((mb * 128 + shift) * 16)) >> 4);
+                const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
 #pragma unroll
-              for (int k16 = 0; k16 < C / 16; ++k16)
-                umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * (2 * R * 16 / 16)),
-                            bd + static_cast<uint64_t>(k16 * (2 * C * 16 / 16)), idesc,
-                            (first && k16 == 0) ? 0u : 1u);
+                for (int k16 = 0; k16 < C / 16; ++k16)
+                  umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * (2 * R * 16 / 16)),
+                              bd + static_cast<uint64_t>(k16 * (2 * C * 16 / 16)), idesc,
+                              (t == 0 && k16 == 0) ? 0u : 1u);
+              }
             }
             __syncwarp();
           };
@@ -170,29 +180,34 @@ resstack_kernel(const __grid_constant__ StackParams p) {
             if (elect_one()) umma_commit(bar);
             __syncwarp();
           };
-          for (int mb = 0; mb < MB; ++mb) {
-            if (nconv < 12) MSB_TRACE(nconv * 16 + mb * 4 + 0);
-            mbar_wait(act_ready(mb), ready_par);
-            tc_fence_after();
-            if (nconv < 12) MSB_TRACE(nconv * 16 + mb * 4 + 1);
-            if (mb == 0) wait_tap(0);
-            if (nconv < 12) MSB_TRACE(nconv * 16 + mb * 4 + 2);
-            issue(mb, 0, true);
-            if (mb == MB - 1) commit(wempty((pos + 0) % NSLOT));
-            if (mb == 0) wait_tap(1);
-            issue(mb, 1, false);
-            if (mb == MB - 1) commit(wempty((pos + 1) % NSLOT));
-            if (mb >= 1) {
-              if (mb == 1) wait_tap(2);
-              issue(mb - 1, 2, false);
-              commit(acc_full(mb - 1));
-            }
-          }
-          if (MB == 1) wait_tap(2);
-          issue(MB - 1, 2, false);
+          // ---- half A: everything except tap +d of its last M-block (which reads rows
+          //      of half B)
+          MSB_TRACE(nconv * 16 + 0);
+          mbar_wait(act_ready(0), ready_par);
+          tc_fence_after();
+          MSB_TRACE(nconv * 16 + 1);
+          wait_tap(0);
+          MSB_TRACE(nconv * 16 + 2);
+          issue(0, 0, HB);
+          wait_tap(1);
+          issue(1, 0, HB);
+          wait_tap(2);
+          if (HB > 1) issue(2, 0, HB - 1);
+          // ---- half B
+          MSB_TRACE(nconv * 16 + 4);
+          mbar_wait(act_ready(1), ready_par);
+          tc_fence_after();
+          MSB_TRACE(nconv * 16 + 5);
+          issue(2, HB - 1, HB);
+          commit(acc_full(0));
+          issue(0, HB, MB);
+          commit(wempty((pos + 0) % NSLOT));
+          issue(1, HB, MB);
+          commit(wempty((pos + 1) % NSLOT));
+          issue(2, HB, MB);
           commit(wempty((pos + 2) % NSLOT));
-          commit(acc_full(MB - 1));
-          if (nconv < 12) MSB_TRACE(nconv * 16 + 15);
+          commit(acc_full(1));
+          MSB_TRACE(nconv * 16 + 15);
         }
       }
     }
@@ -200,56 +215,59 @@ resstack_kernel(const __grid_constant__ StackParams p) {
     // ====================== prologue / epilogue warps ======================
     const int e = warp - 2;            // 0 .. EW-1
     const int q = warp & 3;            // TMEM lane quarter accessible to this warp
-    const int part = e >> 2;           // which slice of the channels
-    constexpr int COLS = C / (EW / 4); // channels per thread
+    const int part = (e >> 2) % G::PARTS;    // which slice of the channels
+    const int ms = (e >> 2) / G::PARTS;      // which M-blocks of a half
+    constexpr int COLS = C / G::PARTS; // channels per thread
     constexpr int NG = COLS / 16;      // 16-column groups per thread
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int chunk0 = part * (COLS / 8);
     uint32_t nconv = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_clip;
       const int t0 = (tile % p.tiles_per_clip) * G::V - kStackHalo;  // clip row of tile row 0
       const bool edge = (t0 < 0) || (t0 + R > p.L);                 // warp-uniform
       // ---- prologue: x32 (global) -> TMEM residual stream + 16-bit operand in sX
-      if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(480 + (nconv / 6) * 2);
-      for (int mb = 0; mb < MB; ++mb) {
-        const int row = mb * 128 + q * 32 + lane;
-        const int t = t0 + row;
-        const bool inside = (t >= 0) && (t < p.L);
-        const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
-        const int chunk0 = part * (COLS / 8);
-        const float4* src = reinterpret_cast<const float4*>(
-            p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8);
-        const size_t cstride = static_cast<size_t>(p.L) * 2;   // float4 per chunk
-        uint32_t v[COLS];
+      if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2);
+      for (int h = 0; h < 2; ++h) {
+        for (int mb = h * HB + ms; mb < (h + 1) * HB; mb += G::MSPLIT) {
+          const int row = mb * 128 + q * 32 + lane;
+          const int t = t0 + row;
+          const bool inside = (t >= 0) && (t < p.L);
+          const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
+          const float4* src = reinterpret_cast<const float4*>(
+              p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8);
+          const size_t cstride = static_cast<size_t>(p.L) * 2;   // float4 per chunk
+          uint32_t v[COLS];
 #pragma unroll
-        for (int c = 0; c < COLS / 8; ++c) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d4 = a;
-          if (inside) {
-            a = __ldg(src + c * cstride);
-            d4 = __ldg(src + c * cstride + 1);
+          for (int c = 0; c < COLS / 8; ++c) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d4 = a;
+            if (inside) {
+              a = __ldg(src + c * cstride);
+              d4 = __ldg(src + c * cstride + 1);
+            }
+            v[c * 8 + 0] = __float_as_uint(a.x); v[c * 8 + 1] = __float_as_uint(a.y);
+            v[c * 8 + 2] = __float_as_uint(a.z); v[c * 8 + 3] = __float_as_uint(a.w);
+            v[c * 8 + 4] = __float_as_uint(d4.x); v[c * 8 + 5] = __float_as_uint(d4.y);
+            v[c * 8 + 6] = __float_as_uint(d4.z); v[c * 8 + 7] = __float_as_uint(d4.w);
           }
-          v[c * 8 + 0] = __float_as_uint(a.x); v[c * 8 + 1] = __float_as_uint(a.y);
-          v[c * 8 + 2] = __float_as_uint(a.z); v[c * 8 + 3] = __float_as_uint(a.w);
-          v[c * 8 + 4] = __float_as_uint(d4.x); v[c * 8 + 5] = __float_as_uint(d4.y);
-          v[c * 8 + 6] = __float_as_uint(d4.z); v[c * 8 + 7] = __float_as_uint(d4.w);
-        }
 #pragma unroll
-        for (int c = 0; c < COLS / 8; ++c) {
-          const uint32_t dst = sX + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
-          st_shared_v4(dst,
-                       pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), p.operand),
-                       pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), p.operand),
-                       pack2s(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]), p.operand),
-                       pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), p.operand));
-        }
+          for (int c = 0; c < COLS / 8; ++c) {
+            const uint32_t dst = sX + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
+            st_shared_v4(dst,
+                         pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), p.operand),
+                         pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), p.operand),
+                         pack2s(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]), p.operand),
+                         pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), p.operand));
+          }
 #pragma unroll
-        for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+          for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+        }
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(act_ready(mb));
+        mbar_arrive(act_ready(h));
       }
-      if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(480 + (nconv / 6) * 2 + 1);
+      if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2 + 1);
       // ---- six convolutions
       for (int l = 0; l < 6; ++l, ++nconv) {
         const bool second = (l & 1) != 0;     // second conv of an atom: residual add
@@ -259,107 +277,107 @@ resstack_kernel(const __grid_constant__ StackParams p) {
         if (l == 4) {
           // warm L2 with the next tile's input while this tile finishes
           const int ntile = tile + gridDim.x;
-          if (ntile < p.total_tiles) {
+          if (ntile < p.total_tiles && (lane & 3) == 0) {
             const int nb = ntile / p.tiles_per_clip;
             const int nt0 = (ntile % p.tiles_per_clip) * G::V - kStackHalo;
-            for (int mb = 0; mb < MB; ++mb) {
+            for (int mb = ms; mb < MB; mb += G::MSPLIT) {
               const int t = nt0 + mb * 128 + q * 32 + lane;
-              if (t >= 0 && t < p.L && (lane & 3) == 0) {
+              if (t >= 0 && t < p.L) {
 #pragma unroll
                 for (int c = 0; c < COLS / 8; ++c)
-                  prefetch_l2(p.x32 + ((static_cast<size_t>(nb) * G::NCH + part * (COLS / 8) + c) *
-                                           p.L + t) * 8);
+                  prefetch_l2(p.x32 + ((static_cast<size_t>(nb) * G::NCH + chunk0 + c) * p.L + t) * 8);
               }
             }
           }
         }
-        for (int mb = 0; mb < MB; ++mb) {
-          const int row = mb * 128 + q * 32 + lane;
-          const int t = t0 + row;
-          const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
-          const uint32_t ta = tx + C;
-          if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(256 + nconv * 16 + mb * 4 + 0);
-          mbar_wait(acc_full(mb), nconv & 1u);
+        for (int h = 0; h < 2; ++h) {
+          if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 0);
+          mbar_wait(acc_full(h), nconv & 1u);
           tc_fence_after();
-          if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(256 + nconv * 16 + mb * 4 + 1);
-          uint32_t v[COLS];
+          if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 1);
+          for (int mb = h * HB + ms; mb < (h + 1) * HB; mb += G::MSPLIT) {
+            const int row = mb * 128 + q * 32 + lane;
+            const int t = t0 + row;
+            const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
+            const uint32_t ta = tx + C;
+            uint32_t v[COLS];
 #pragma unroll
-          for (int g = 0; g < NG; ++g) tmem_ld16p(ta + g * 16, &v[g * 16]);
-          float f[COLS];
-          if (second) {
-            uint32_t xr[COLS];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) tmem_ld16p(tx + g * 16, &xr[g * 16]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j4 = 0; j4 < COLS / 4; ++j4) {
-              const float4 bv = __ldg(bias4 + j4);
-              f[j4 * 4 + 0] = __uint_as_float(xr[j4 * 4 + 0]) + leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
-              f[j4 * 4 + 1] = __uint_as_float(xr[j4 * 4 + 1]) + leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
-              f[j4 * 4 + 2] = __uint_as_float(xr[j4 * 4 + 2]) + leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
-              f[j4 * 4 + 3] = __uint_as_float(xr[j4 * 4 + 3]) + leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
-            }
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int j4 = 0; j4 < COLS / 4; ++j4) {
-              const float4 bv = __ldg(bias4 + j4);
-              f[j4 * 4 + 0] = leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
-              f[j4 * 4 + 1] = leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
-              f[j4 * 4 + 2] = leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
-              f[j4 * 4 + 3] = leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
-            }
-          }
-          if (edge) {
-            if (t < 0 || t >= p.L) {
-#pragma unroll
-              for (int j = 0; j < COLS; ++j) f[j] = 0.f;
-            }
-          }
-          if (!last) {
+            for (int g = 0; g < NG; ++g) tmem_ld16p(ta + g * 16, &v[g * 16]);
+            float f[COLS];
             if (second) {
+              uint32_t xr[COLS];
 #pragma unroll
-              for (int j = 0; j < COLS; ++j) v[j] = __float_as_uint(f[j]);
+              for (int g = 0; g < NG; ++g) tmem_ld16p(tx + g * 16, &xr[g * 16]);
+              tmem_ld_wait();
 #pragma unroll
-              for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+              for (int j4 = 0; j4 < COLS / 4; ++j4) {
+                const float4 bv = __ldg(bias4 + j4);
+                f[j4 * 4 + 0] = __uint_as_float(xr[j4 * 4 + 0]) + leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
+                f[j4 * 4 + 1] = __uint_as_float(xr[j4 * 4 + 1]) + leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
+                f[j4 * 4 + 2] = __uint_as_float(xr[j4 * 4 + 2]) + leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
+                f[j4 * 4 + 3] = __uint_as_float(xr[j4 * 4 + 3]) + leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
+              }
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j4 = 0; j4 < COLS / 4; ++j4) {
+                const float4 bv = __ldg(bias4 + j4);
+                f[j4 * 4 + 0] = leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
+                f[j4 * 4 + 1] = leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
+                f[j4 * 4 + 2] = leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
+                f[j4 * 4 + 3] = leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
+              }
             }
+            if (edge) {
+              if (t < 0 || t >= p.L) {
 #pragma unroll
-            for (int c = 0; c < COLS / 8; ++c) {
-              const uint32_t dst =
-                  dstbuf + static_cast<uint32_t>(((part * (COLS / 8) + c) * R + row) * 16);
-              st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
-                           pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
-                           pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
-                           pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
+                for (int j = 0; j < COLS; ++j) f[j] = 0.f;
+              }
             }
-            if (second) tmem_st_wait();
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(act_ready(mb));
-          } else if (t >= 0 && t < p.L && row >= kStackHalo && row < R - kStackHalo) {
+            if (!last) {
+              if (second) {
 #pragma unroll
-            for (int c = 0; c < COLS / 8; ++c) {
-              const size_t idx =
-                  (static_cast<size_t>(b) * G::NCH + part * (COLS / 8) + c) * p.L + t;
-              if (p.y16 != nullptr)
-                *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
-                    make_uint4(pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
-                               pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
-                               pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
-                               pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
-              if (p.y32 != nullptr) {
-                float4* d32 = reinterpret_cast<float4*>(p.y32 + idx * 8);
-                d32[0] = make_float4(f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3]);
-                d32[1] = make_float4(f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]);
+                for (int j = 0; j < COLS; ++j) v[j] = __float_as_uint(f[j]);
+#pragma unroll
+                for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+              }
+#pragma unroll
+              for (int c = 0; c < COLS / 8; ++c) {
+                const uint32_t dst = dstbuf + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
+                st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
+                             pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
+                             pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
+                             pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
+              }
+            } else if (t >= 0 && t < p.L && row >= kStackHalo && row < R - kStackHalo) {
+#pragma unroll
+              for (int c = 0; c < COLS / 8; ++c) {
+                const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk0 + c) * p.L + t;
+                if (p.y16 != nullptr)
+                  *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
+                      make_uint4(pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
+                                 pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
+                                 pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
+                                 pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
+                if (p.y32 != nullptr) {
+                  float4* d32 = reinterpret_cast<float4*>(p.y32 + idx * 8);
+                  d32[0] = make_float4(f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3]);
+                  d32[1] = make_float4(f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]);
+                }
               }
             }
           }
-          if (warp == 2 && lane == 0 && nconv < 12) MSB_TRACE(256 + nconv * 16 + mb * 4 + 2);
+          if (!last) {
+            if (second) tmem_st_wait();
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(act_ready(h));
+          }
+          if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 2);
         }
       }
     }
   }
-
 
   tc_fence_before();
   __syncthreads();
@@ -369,12 +387,12 @@ resstack_kernel(const __grid_constant__ StackParams p) {
   }
 }
 
-template <int C, int EW>
+template <int C>
 ms_status launch_stack(const StackParams& p, cudaStream_t stream) {
   using G = StackGeom<C>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resstack_kernel<C, EW>,
+    cudaError_t e = cudaFuncSetAttribute(resstack_kernel<C>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(resstack_kernel)");
     attr_set = true;
@@ -382,7 +400,7 @@ ms_status launch_stack(const StackParams& p, cudaStream_t stream) {
   const int sms = sm_count();
   if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  resstack_kernel<C, EW><<<grid, 64 + 32 * EW, G::SMEM, stream>>>(p);
+  resstack_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
   return after_launch("resstack_kernel");
 }
 
@@ -421,9 +439,9 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
   p.total_tiles = static_cast<int>(tiles);
   switch (channels) {
-    case 128: return launch_stack<128, 8>(p, stream);
-    case 64: return launch_stack<64, 8>(p, stream);
-    default: return launch_stack<32, 8>(p, stream);
+    case 128: return launch_stack<128>(p, stream);
+    case 64: return launch_stack<64>(p, stream);
+    default: return launch_stack<32>(p, stream);
   }
 }
 

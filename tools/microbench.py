@@ -1,0 +1,21 @@
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from music_synthesis_b200 import _lib
+lib = _lib.lib()
+out = torch.zeros(64, dtype=torch.int64, device="cuda")
+lib.ms_debug_microbench.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+for _ in range(2):
+    lib.ms_debug_microbench(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(0))
+torch.cuda.synchronize()
+o = out.cpu().tolist()
+names = ["clock overhead", "mbar_wait (completed)", "elect+syncwarp", "tc_fence_after", "commit issue (idle)", "commit->wait (idle)"]
+for i, n in enumerate(names):
+    print("%-28s %6d" % (n, o[i]))
+s = 6
+for N in (32, 64, 128, 256):
+    for v in ("same acc", "2 accs"):
+        print("16 MMAs N=%-3d %-8s issue %6d  issue+complete %6d  (ideal exec %d)" % (N, v, o[s], o[s + 1], 16 * N // 2))
+        s += 2
+print("64 MMAs N=128 issue %d complete %d (ideal %d)" % (o[s], o[s + 1], 64 * 64)); s += 2
+print("64 MMAs N=32 (4 accs) issue %d complete %d (ideal %d)" % (o[s], o[s + 1], 64 * 16))

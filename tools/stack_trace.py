@@ -24,20 +24,13 @@ ops.resstack_fwd(x32, blob, [1, 3, 9], want16=True, want32=False)
 torch.cuda.synchronize()
 lib.ms_debug_set_stack_trace(ctypes.c_void_p(0))
 d = dbg.cpu().tolist()
-MB = 256 // C
 t0 = d[480]
-print("C=%d MB=%d ; all times in cycles relative to prologue start of tile 0" % (C, MB))
+print("C=%d ; cycles relative to prologue start of tile 0" % C)
 print("prologue tile0: %d -> %d ; tile1: %d -> %d" % (0, d[481] - t0, d[482] - t0, d[483] - t0))
 for n in range(12):
-    mma = []
-    for mb in range(MB if MB <= 4 else 4):
-        b = n * 16 + mb * 4
-        if mb * 4 + 2 < 15:
-            mma.append("mb%d[wait_act %d->%d, w_ready %d]" % (mb, d[b] - t0, d[b + 1] - t0, d[b + 2] - t0))
-    print("conv %2d MMA: %s issue_done %d" % (n, " ".join(mma), d[n * 16 + 15] - t0))
-    epi = []
-    for mb in range(MB if MB <= 4 else 4):
-        b = 256 + n * 16 + mb * 4
-        if mb * 4 + 2 < 16:
-            epi.append("mb%d[wait %d->%d done %d]" % (mb, d[b] - t0, d[b + 1] - t0, d[b + 2] - t0))
-    print("        EPI: %s" % " ".join(epi))
+    m = n * 16
+    print("conv %2d MMA: A[wait_act %d->%d tap0 %d] B[wait_act %d->%d] issue_done %d" % (
+        n, d[m] - t0, d[m + 1] - t0, d[m + 2] - t0, d[m + 4] - t0, d[m + 5] - t0, d[m + 15] - t0))
+    e = 256 + n * 16
+    print("        EPI: A[wait %d->%d done %d] B[wait %d->%d done %d]" % (
+        d[e] - t0, d[e + 1] - t0, d[e + 2] - t0, d[e + 4] - t0, d[e + 5] - t0, d[e + 6] - t0))
