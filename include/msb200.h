@@ -141,6 +141,13 @@ ms_status ms_resstack_fwd(int channels, int batch, int len, const int* dilations
                           int operand, const float* x32, const void* packed, void* y16,
                           float* y32, void* stream);
 
+/* Last generator stage in one kernel: ResidualStack(32) followed by the 32 -> 1 k7 conv
+ * (zero pad 3) + tanh of generator/full.py:43-44.  y: (B,1,L) fp32. */
+ms_status ms_resstack_tail_fwd(int batch, int len, const int* dilations /* [3] */,
+                               int operand, const float* x32, const void* packed,
+                               const float* tail_w /* (1,32,7) */, const float* tail_b,
+                               float* y, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Whole MelGanGenerator forward (inference), features -> waveform.
  *   replaces MelGanGenerator.forward, featuresynth/generator/full.py:47-50

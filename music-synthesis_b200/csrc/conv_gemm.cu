@@ -70,12 +70,16 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     mx = c->off[t] > mx ? c->off[t] : mx;
   }
   c->min_off = mn;
-  c->RA = 128 + mx - mn;
+  c->MBLK = c->Lm > 128 ? 2 : 1;
+  c->RA = 128 * c->MBLK + mx - mn;
   c->NT = pick_nt(c->Ntot);
   if (c->NT == 0) return false;
   c->KB = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
+  // NT / KB define the packed weight layout, so they must not depend on the input
+  // length: size the stages for the largest tile (two M-blocks) regardless of MBLK
+  const int ra_max = 256 + mx - mn;
   auto stage = [&](int kb, int nt) {
-    return (kb / 8) * c->RA * 16 + c->taps * (kb / 8) * nt * 16;
+    return (kb / 8) * ra_max * 16 + c->taps * (kb / 8) * nt * 16;
   };
   const int budget = kSmemBudget - kSmemHeader;
   // want >= 3 stages when possible
@@ -89,7 +93,7 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
   if (stage(c->KB, c->NT) * 2 > budget) return false;
   c->nnt = c->Ntot / c->NT;
   c->nkb = d.cin / c->KB;
-  c->mtiles = (c->Lm + 127) / 128;
+  c->mtiles = (c->Lm + 128 * c->MBLK - 1) / (128 * c->MBLK);
   c->a_stage_bytes = (c->KB / 8) * c->RA * 16;
   c->w_stage_bytes = c->taps * (c->KB / 8) * c->NT * 16;
   c->stage_bytes = (c->a_stage_bytes + c->w_stage_bytes + 127) / 128 * 128;
@@ -99,8 +103,9 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
   if (s > need) s = need;
   if (s < 2) return false;
   c->stages = s;
+  c->acc_stages = (2 * c->MBLK * c->NT <= 512) ? 2 : 1;
   int cols = 32;
-  while (cols < 2 * c->NT) cols *= 2;
+  while (cols < c->acc_stages * c->MBLK * c->NT) cols *= 2;
   c->tmem_cols = cols;
   size_t smem = kSmemHeader + static_cast<size_t>(c->stages) * c->stage_bytes;
   // always ask for more than half an SM's shared memory: one CTA per SM, so the
@@ -120,7 +125,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int operand) {
   return pack_h2(a, b);
 }
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int kConvEpiWarps = 8;
+constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -143,7 +151,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * kConvEpiWarps);
     }
     fence_mbar_init();
   }
@@ -157,6 +165,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   const int chunks = p.KB >> 3;  // 16-byte channel chunks per k-block
+  const int rows_per_tile = 128 * p.MBLK;
+  const int acc_cols = p.MBLK * p.NT;
 
   if (warp == 0) {
     // =============================== producer ===============================
@@ -167,7 +177,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int rest = tile / p.nnt;
       const int mt = rest % p.mtiles;
       const int b = rest / p.mtiles;
-      const int r0 = mt * 128 + p.min_off;
+      const int r0 = mt * rows_per_tile + p.min_off;
       const int lo = r0 < 0 ? 0 : r0;
       const int hi = (r0 + p.RA) > p.lin ? p.lin : (r0 + p.RA);
       const int nrows = hi > lo ? hi - lo : 0;
@@ -185,9 +195,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const int c = i / nz;
             int r = i - c * nz;
             r = r < head ? r : tail0 + (r - head);
-            const uint32_t a = sA + static_cast<uint32_t>(c * p.RA + r) * 16u;
-            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u)
-                         : "memory");
+            st_shared_v4(sA + static_cast<uint32_t>(c * p.RA + r) * 16u, 0u, 0u, 0u, 0u);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -218,127 +226,148 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // ============================== MMA issuer ==============================
     // Warp-uniform loop; only the tcgen05 instructions are predicated on one elected
     // lane so the descriptors live in uniform registers.
-    {
-      const uint32_t idesc = umma_idesc_f16(p.NT, p.operand);
-      const uint64_t adesc0 = umma_desc_base_nosw(static_cast<uint32_t>(p.RA) * 16u, 128);
-      const uint64_t bdesc0 = umma_desc_base_nosw(static_cast<uint32_t>(p.NT) * 16u, 128);
-      const uint32_t a_kstep = static_cast<uint32_t>(2 * p.RA);   // 16-byte units per k16
-      const uint32_t b_kstep = static_cast<uint32_t>(2 * p.NT);
-      const int nk16 = p.KB >> 4;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    const uint32_t idesc = umma_idesc_f16(p.NT, p.operand);
+    const uint64_t adesc0 = umma_desc_base_nosw(static_cast<uint32_t>(p.RA) * 16u, 128);
+    const uint64_t bdesc0 = umma_desc_base_nosw(static_cast<uint32_t>(p.NT) * 16u, 128);
+    const uint32_t a_kstep = static_cast<uint32_t>(2 * p.RA);   // 16-byte units per k16
+    const uint32_t b_kstep = static_cast<uint32_t>(2 * p.NT);
+    const int nk16 = p.KB >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * acc_cols);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.NT);
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
-          const uint32_t sW = sA + p.a_stage_bytes;
-          if (elect_one()) {
-            for (int t = 0; t < p.taps; ++t) {
-              uint64_t ad = adesc0 + ((sA >> 4) + static_cast<uint32_t>(p.off[t] - p.min_off));
-              uint64_t bd = bdesc0 + ((sW >> 4) + static_cast<uint32_t>(t * chunks * p.NT));
+        const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+        const uint32_t sW = sA + p.a_stage_bytes;
+        if (elect_one()) {
+          for (int t = 0; t < p.taps; ++t) {
+            const uint64_t bd0 = bdesc0 + ((sW >> 4) + static_cast<uint32_t>(t * chunks * p.NT));
+            for (int mb = 0; mb < p.MBLK; ++mb) {
+              uint64_t ad = adesc0 + ((sA >> 4) + static_cast<uint32_t>(p.off[t] - p.min_off + mb * 128));
+              uint64_t bd = bd0;
+              const uint32_t dst = d_tmem + static_cast<uint32_t>(mb * p.NT);
               for (int k16 = 0; k16 < nk16; ++k16) {
-                umma_f16_ss(d_tmem, ad, bd, idesc, (kb | t | k16) != 0 ? 1u : 0u);
+                umma_f16_ss(dst, ad, bd, idesc, (kb | t | k16) != 0 ? 1u : 0u);
                 ad += a_kstep;
                 bd += b_kstep;
               }
             }
-            umma_commit(empty_bar(stage));
-            if (kb == p.nkb - 1) umma_commit(tfull_bar(acc));
           }
-          __syncwarp();
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          umma_commit(empty_bar(stage));
+          if (kb == p.nkb - 1) umma_commit(tfull_bar(acc));
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1u;
       }
     }
   } else {
     // =============================== epilogue ===============================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // 8 warps: lane quarter q = warp % 4 (hardware rule), two warps per quarter take
+    // alternate 32-column groups.  TMEM loads are batched (32 columns per wait).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int cout8 = p.cout >> 3;
+    const int ngroups = p.NT >> 4;            // 16-column groups per M-block
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt_idx = tile % p.nnt;
       const int rest = tile / p.nnt;
       const int mt = rest % p.mtiles;
       const int b = rest / p.mtiles;
-      const int m = mt * 128 + q * 32 + lane;
       const int n0 = nt_idx * p.NT;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.NT);
-      for (int c0 = 0; c0 < p.NT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (c0 + 16 >= p.NT) {
-          // accumulator fully drained into registers: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
-        }
+      for (int mb = 0; mb < p.MBLK; ++mb) {
+        const int m = mt * rows_per_tile + mb * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>(acc * acc_cols + mb * p.NT);
+        // this warp handles group pairs (2 x 16 columns) g = 2*half, 2*half+4, ...
+        for (int g = 2 * half; g < ngroups; g += 4) {
+          const bool two = (g + 1) < ngroups;
+          uint32_t v[32];
+          tmem_ld16p(taddr + g * 16, &v[0]);
+          if (two) tmem_ld16p(taddr + (g + 1) * 16, &v[16]);
+          tmem_ld_wait();
+          if (mb == p.MBLK - 1 && g + 4 >= ngroups) {
+            // last TMEM read of this tile by this thread: hand the accumulator back
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+          }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int n = n0 + c0 + h * 8;
-          int ch, orow;
-          bool valid = m < p.Lm;
-          if (p.kind == MS_CONVT) {
-            const int r = n / p.cout;
-            ch = n - r * p.cout;
-            orow = p.stride * m + r - p.pad;
-            valid = valid && orow >= 0 && orow < p.Lout;
-          } else {
-            ch = n;
-            orow = m;
-          }
-          if (!valid) continue;
-          float f[8];
+          for (int h = 0; h < 4; ++h) {
+            if (h >= 2 && !two) break;
+            const int n = n0 + g * 16 + h * 8;
+            int ch, orow;
+            bool valid = m < p.Lm;
+            if (p.kind == MS_CONVT) {
+              const int r = n / p.cout;
+              ch = n - r * p.cout;
+              orow = p.stride * m + r - p.pad;
+              valid = valid && orow >= 0 && orow < p.Lout;
+            } else {
+              ch = n;
+              orow = m;
+            }
+            if (!valid) continue;
+            float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[h * 8 + j]) * p.alpha;
-          if (p.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + 1);
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-          }
-          if (p.leaky) {
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[h * 8 + j]) * p.alpha;
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + 1);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (p.leaky) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
-          }
-          const size_t idx = (static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + orow;
-          if (p.res32 != nullptr) {
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8));
-            const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8) + 1);
-            f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-            f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-          }
-          if (p.y32 != nullptr) {
-            float4* dst = reinterpret_cast<float4*>(p.y32 + idx * 8);
-            dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-            dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-          }
-          if (p.y16 != nullptr) {
-            uint4 o;
-            o.x = pack2(f[0], f[1], p.operand);
-            o.y = pack2(f[2], f[3], p.operand);
-            o.z = pack2(f[4], f[5], p.operand);
-            o.w = pack2(f[6], f[7], p.operand);
-            *reinterpret_cast<uint4*>(p.y16 + idx * 8) = o;
+              for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
+            }
+            const size_t idx = (static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + orow;
+            if (p.res32 != nullptr) {
+              const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8));
+              const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8) + 1);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+            }
+            if (p.y32 != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(p.y32 + idx * 8);
+              dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+              dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+            }
+            if (p.y16 != nullptr) {
+              uint4 o;
+              o.x = pack2(f[0], f[1], p.operand);
+              o.y = pack2(f[2], f[3], p.operand);
+              o.z = pack2(f[4], f[5], p.operand);
+              o.w = pack2(f[6], f[7], p.operand);
+              *reinterpret_cast<uint4*>(p.y16 + idx * 8) = o;
+            }
           }
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      // warps with no column group in this tile (tiny NT) still have to arrive
+      if (2 * half >= ngroups) {
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+      }
+      if (++acc == p.acc_stages) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
     }
   }
 
@@ -401,7 +430,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   for (int t = 0; t < kMaxTaps; ++t) p.off[t] = t < c.taps ? c.off[t] : 0;
   p.min_off = c.min_off; p.RA = c.RA;
   p.Ntot = c.Ntot; p.NT = c.NT; p.KB = c.KB; p.nnt = c.nnt; p.nkb = c.nkb;
-  p.mtiles = c.mtiles;
+  p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages;
   p.stages = c.stages; p.a_stage_bytes = c.a_stage_bytes; p.w_stage_bytes = c.w_stage_bytes;
   p.stage_bytes = c.stage_bytes; p.tmem_cols = c.tmem_cols;
   p.kind = d.kind; p.stride = d.stride; p.pad = d.pad; p.leaky = d.leaky;
@@ -421,7 +450,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   int sms = sm_count();
   if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
   int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  conv_gemm_kernel<<<grid, 192, c.smem_bytes, stream>>>(p);
+  conv_gemm_kernel<<<grid, kConvThreads, c.smem_bytes, stream>>>(p);
   return after_launch("conv_gemm_kernel");
 }
 

@@ -17,13 +17,15 @@ constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100
 struct ConvCfg {
   int taps;            // GEMM taps (MS_CONV: ksize; MS_CONVT: 2)
   int off[kMaxTaps];   // input row of tap t for GEMM row m is m + off[t]
-  int min_off, RA;     // RA = 128 + max_off - min_off rows of A staged per tile
+  int MBLK;            // 128-row M-blocks per CTA tile (1 or 2): they share each W stage
+  int min_off, RA;     // RA = 128*MBLK + max_off - min_off rows of A staged per tile
   int Ntot;            // GEMM N (MS_CONV: cout; MS_CONVT: stride*cout)
   int NT, KB;          // n-tile (columns per CTA tile), k-block (input channels per stage)
   int nnt, nkb;        // Ntot/NT, cin/KB
   int Lm;              // GEMM rows per clip (MS_CONV: Lout; MS_CONVT: lin+1)
   int Lout;
-  int mtiles;          // ceil(Lm/128)
+  int mtiles;          // ceil(Lm/(128*MBLK))
+  int acc_stages;      // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   int a_stage_bytes, w_stage_bytes, stage_bytes;
   int stages;
   int tmem_cols;       // power of two >= 2*NT
@@ -45,7 +47,7 @@ struct ConvGemmParams {
   int taps;
   int off[kMaxTaps];
   int min_off, RA;
-  int Ntot, NT, KB, nnt, nkb, mtiles;
+  int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages;
   int stages, a_stage_bytes, w_stage_bytes, stage_bytes, tmem_cols;
   int kind, stride, pad, leaky, operand;
   float alpha;

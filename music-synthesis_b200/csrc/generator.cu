@@ -21,7 +21,8 @@ ms_status pack_ncl_to_blk16(const float* x, void* y16, int batch, int channels, 
                             int pad, int pad_mode, int operand, cudaStream_t stream);
 ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int operand,
                        const float* x32, const void* packed, void* y16, float* y32,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const float* mono_w, const float* mono_b,
+                       float* mono_out);
 
 namespace {
 
@@ -198,14 +199,25 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
     ms_status s = pack_ncl_to_blk16(x + static_cast<size_t>(b0) * in_channels * T, xin16, nb,
                                     in_channels, frames, 3, 1, operand, st);
     if (s != MS_OK) return s;
+    bool fused_tail = false;
     const void* cur16 = nullptr;  // 16-bit operand of the next layer
     int cur = 0;                  // which x16/x32 buffer holds the residual stream
     for (const GenLayer& L : plan.layers) {
       if (L.role == 4) {
         // fused ResidualStack: fp32 stream in, 16-bit operand (+ fp32 for the last stage) out
-        const bool final_stage = (L.d.cout == 32);
+        if (L.d.cout == 32) {
+          // last stage: the 32->1 k7 conv + tanh is fused into the stack kernel's tail
+          s = resstack_fwd(32, nb, L.len_mult * frames, kDil, operand, x32[0], wb + L.w_off,
+                           nullptr, nullptr, st,
+                           reinterpret_cast<const float*>(wb + plan.final_w_off),
+                           reinterpret_cast<const float*>(wb + plan.final_b_off),
+                           y + static_cast<size_t>(b0) * 256 * T);
+          if (s != MS_OK) return s;
+          fused_tail = true;
+          continue;
+        }
         s = resstack_fwd(L.d.cout, nb, L.len_mult * frames, kDil, operand, x32[0],
-                         wb + L.w_off, x16[1], final_stage ? x32[1] : nullptr, st);
+                         wb + L.w_off, x16[1], nullptr, st, nullptr, nullptr, nullptr);
         if (s != MS_OK) return s;
         cur = 1;
         cur16 = x16[1];
@@ -244,6 +256,7 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
       }
       if (s != MS_OK) return s;
     }
+    if (fused_tail) continue;
     s = conv_to_mono(x32[cur], reinterpret_cast<const float*>(wb + plan.final_w_off),
                      reinterpret_cast<const float*>(wb + plan.final_b_off),
                      y + static_cast<size_t>(b0) * 256 * T, nb, 32, 256 * frames, 7, 3, 1, st);

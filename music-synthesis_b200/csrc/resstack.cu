@@ -40,7 +40,13 @@ struct StackParams {
   int B, L;
   int dil[3];
   int tiles_per_clip, total_tiles;
+  int halo, V;           // rows recomputed per tile side / rows stored per tile (R - 2*halo)
   int operand;
+  // optional fused tail (C == 32 only): y = tanh(conv_k7_pad3(x, mono_w) + mono_b),
+  // generator/full.py:43-44.  When mono_out != null, y16 / y32 are not written.
+  const float* mono_w;   // (1, 32, 7) fp32, reference layout
+  const float* mono_b;   // (1)
+  float* mono_out;       // (B, 1, L) fp32
   long long* dbg;        // optional clock trace of CTA 0 (null in production)
 };
 
@@ -63,12 +69,12 @@ struct StackGeom {
   static constexpr int MSPLIT = 4 / PARTS;             // M-block split of the epilogue
   static constexpr int EW = 16;                        // epilogue warps = 4 * PARTS * MSPLIT
   static constexpr int R = MB * 128;             // rows per tile
-  static constexpr int V = R - 2 * kStackHalo;   // rows stored per tile
   static constexpr int NCH = C / 8;
   static constexpr int ACT_BYTES = R * C * 2;    // 65536
   static constexpr int TAP_BYTES = C * C * 2;
   static constexpr int NSLOT = (96 * 1024 / TAP_BYTES) < 18 ? (96 * 1024 / TAP_BYTES) : 18;
-  static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES;
+  static constexpr int MONO_BYTES = 1024;        // [7][32] fp32 tail-conv weights
+  static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES;
 };
 
 __device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
@@ -93,6 +99,9 @@ resstack_kernel(const __grid_constant__ StackParams p) {
   const uint32_t sX = smem_u32(smem + kStackHeader);
   const uint32_t sY = sX + G::ACT_BYTES;
   const uint32_t sW = sY + G::ACT_BYTES;
+  float* sMono = reinterpret_cast<float*>(smem + kStackHeader + 2 * G::ACT_BYTES +
+                                          NSLOT * G::TAP_BYTES);
+  const bool mono = (C == 32) && (p.mono_out != nullptr);
   auto wfull = [&](int s) { return bar_base + 8u * s; };
   auto wempty = [&](int s) { return bar_base + 8u * (18 + s); };
   auto acc_full = [&](int m) { return bar_base + 8u * (36 + m); };
@@ -115,6 +124,11 @@ resstack_kernel(const __grid_constant__ StackParams p) {
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
+  }
+  if (mono) {
+    // tail-conv weights, transposed to [tap][channel] for vector broadcast loads
+    for (int i = threadIdx.x; i < 7 * 32; i += blockDim.x)
+      sMono[i] = p.mono_w[(i & 31) * 7 + (i >> 5)];
   }
   tc_fence_before();
   __syncthreads();
@@ -224,7 +238,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
     uint32_t nconv = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_clip;
-      const int t0 = (tile % p.tiles_per_clip) * G::V - kStackHalo;  // clip row of tile row 0
+      const int t0 = (tile % p.tiles_per_clip) * p.V - p.halo;  // clip row of tile row 0
       const bool edge = (t0 < 0) || (t0 + R > p.L);                 // warp-uniform
       // ---- prologue: x32 (global) -> TMEM residual stream + 16-bit operand in sX
       if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2);
@@ -279,7 +293,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
           const int ntile = tile + gridDim.x;
           if (ntile < p.total_tiles && (lane & 3) == 0) {
             const int nb = ntile / p.tiles_per_clip;
-            const int nt0 = (ntile % p.tiles_per_clip) * G::V - kStackHalo;
+            const int nt0 = (ntile % p.tiles_per_clip) * p.V - p.halo;
             for (int mb = ms; mb < MB; mb += G::MSPLIT) {
               const int t = nt0 + mb * 128 + q * 32 + lane;
               if (t >= 0 && t < p.L) {
@@ -349,7 +363,26 @@ resstack_kernel(const __grid_constant__ StackParams p) {
                              pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
                              pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
               }
-            } else if (t >= 0 && t < p.L && row >= kStackHalo && row < R - kStackHalo) {
+            } else if (mono) {
+              // fused tail, step 1: this thread's 16 channels of its row contribute
+              // 7 per-tap partial dot products; P[part][tap][row] lives in the X buffer
+              // (free during the last conv).
+              float pk[7];
+#pragma unroll
+              for (int k = 0; k < 7; ++k) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < COLS / 4; ++j4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(sMono + k * 32 + part * COLS + j4 * 4);
+                  a0 = fmaf(f[j4 * 4 + 0], w4.x, a0); a1 = fmaf(f[j4 * 4 + 1], w4.y, a1);
+                  a0 = fmaf(f[j4 * 4 + 2], w4.z, a0); a1 = fmaf(f[j4 * 4 + 3], w4.w, a1);
+                }
+                pk[k] = a0 + a1;
+              }
+              float* P = reinterpret_cast<float*>(smem + kStackHeader) + (part * 7) * R + row;
+#pragma unroll
+              for (int k = 0; k < 7; ++k) P[k * R] = pk[k];
+            } else if (t >= 0 && t < p.L && row >= p.halo && row < R - p.halo) {
 #pragma unroll
               for (int c = 0; c < COLS / 8; ++c) {
                 const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk0 + c) * p.L + t;
@@ -375,6 +408,24 @@ resstack_kernel(const __grid_constant__ StackParams p) {
           }
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 2);
         }
+      }
+      if (mono) {
+        // ---- fused tail, step 2: y[row] = tanh(b + sum_k sum_part P[part][k][row+k-3])
+        named_bar_sync(1, 32 * EW);            // partial sums complete (epilogue warps only)
+        const float bias0 = __ldg(p.mono_b);
+        const float* P = reinterpret_cast<const float*>(smem + kStackHeader);
+        for (int row = threadIdx.x - 64; row < R - p.halo; row += 32 * EW) {
+          const int t = t0 + row;
+          if (row < p.halo || t < 0 || t >= p.L) continue;
+          float a0 = bias0, a1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            a0 += P[k * R + row + k - 3];
+            a1 += P[(7 + k) * R + row + k - 3];
+          }
+          p.mono_out[static_cast<size_t>(b) * p.L + t] = tanhf(a0 + a1);
+        }
+        named_bar_sync(1, 32 * EW);            // staging consumed before the next prologue
       }
     }
   }
@@ -408,13 +459,17 @@ static thread_local long long* g_stack_dbg = nullptr;
 
 ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int operand,
                        const float* x32, const void* packed, void* y16, float* y32,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const float* mono_w, const float* mono_b,
+                       float* mono_out) {
   if (batch <= 0 || len <= 0 || x32 == nullptr || packed == nullptr ||
-      (y16 == nullptr && y32 == nullptr))
+      (y16 == nullptr && y32 == nullptr && mono_out == nullptr))
+    return MS_ERR_INVALID;
+  if (mono_out != nullptr && (channels != 32 || mono_w == nullptr || mono_b == nullptr))
     return MS_ERR_INVALID;
   for (int i = 0; i < 3; ++i)
     if (dil[i] < 1 || dil[i] > 9) return MS_ERR_INVALID;
-  // receptive field of the stack must fit the 16-row halo
+  // receptive field of the stack (+3 for the fused k7 tail) must fit the halo
+  const int halo = mono_out != nullptr ? kStackHalo + 4 : kStackHalo;
   if (dil[0] + dil[1] + dil[2] + 3 > kStackHalo) return MS_ERR_INVALID;
   StackParams p;
   p.x32 = x32;
@@ -426,14 +481,16 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   p.B = batch; p.L = len;
   p.dil[0] = dil[0]; p.dil[1] = dil[1]; p.dil[2] = dil[2];
   p.operand = operand;
+  p.mono_w = mono_w; p.mono_b = mono_b; p.mono_out = mono_out;
   p.dbg = g_stack_dbg;
   int V;
   switch (channels) {
-    case 128: V = StackGeom<128>::V; break;
-    case 64: V = StackGeom<64>::V; break;
-    case 32: V = StackGeom<32>::V; break;
+    case 128: V = StackGeom<128>::R - 2 * halo; break;
+    case 64: V = StackGeom<64>::R - 2 * halo; break;
+    case 32: V = StackGeom<32>::R - 2 * halo; break;
     default: return MS_ERR_INVALID;
   }
+  p.halo = halo; p.V = V;
   p.tiles_per_clip = (len + V - 1) / V;
   const long long tiles = static_cast<long long>(batch) * p.tiles_per_clip;
   if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
@@ -511,7 +568,16 @@ ms_status ms_resstack_fwd(int channels, int batch, int len, const int* dilations
                           void* stream) {
   if (dilations == nullptr || !ms_resstack_supported(channels)) return MS_ERR_INVALID;
   return resstack_fwd(channels, batch, len, dilations, operand, x32, packed, y16, y32,
-                      static_cast<cudaStream_t>(stream));
+                      static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr);
+}
+
+ms_status ms_resstack_tail_fwd(int batch, int len, const int* dilations, int operand,
+                               const float* x32, const void* packed, const float* tail_w,
+                               const float* tail_b, float* y, void* stream) {
+  if (dilations == nullptr || tail_w == nullptr || tail_b == nullptr || y == nullptr)
+    return MS_ERR_INVALID;
+  return resstack_fwd(32, batch, len, dilations, operand, x32, packed, nullptr, nullptr,
+                      static_cast<cudaStream_t>(stream), tail_w, tail_b, y);
 }
 
 }  // extern "C"

@@ -15,7 +15,7 @@ from ..util.modules import ResidualStack
 
 class MelGanGenerator(nn.Module):
     #: clips per pass through the layer schedule (bounds the activation workspace)
-    clips_per_pass = 16
+    clips_per_pass = 256
 
     def __init__(self, input_size, in_channels, operand=MS_F16):
         super().__init__()

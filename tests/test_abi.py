@@ -92,3 +92,15 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmsb200.so")
     with pytest.raises(ImportError):
         _lib.lib()
+
+
+def test_packed_weight_layout_is_length_independent(lib):
+    """NT/KB (the packed layout) must not change with the input length or batch."""
+    from music_synthesis_b200 import ops
+    for kind, cin, cout, k, s, p in ((ops.MS_CONV, 256, 256, 3, 1, 1), (ops.MS_CONVT, 512, 256, 16, 8, 4),
+                                     (ops.MS_CONV, 128, 512, 7, 1, 0)):
+        sizes = set()
+        for lin in (8, 70, 129, 1024, 5000):
+            d = ops.conv_desc(kind, 3, cin, cout, lin, k, 1, p, s)
+            sizes.add(lib.ms_conv_packed_weight_bytes(ctypes.byref(d)))
+        assert len(sizes) == 1 and 0 not in sizes
