@@ -134,6 +134,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   // [0..7] full, [8..15] empty, [16..17] tmem_full, [18..19] tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  // per-tile epilogue tables, double-buffered by accumulator stage:
+  //   s_bias[2][256] fp32 (bias of each tile column), s_tab[2][32] (phase r, channel of each
+  //   8-column chunk) -- so the epilogue has no dependent global loads / integer divisions
+  float* s_bias = reinterpret_cast<float*>(smem + 512);
+  int2* s_tab = reinterpret_cast<int2*>(smem + 512 + 2048 - 512);
   const uint32_t bar_base = smem_u32(bars);
   const uint32_t data_base = smem_u32(smem + kSmemHeader);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -289,6 +294,30 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int mt = rest % p.mtiles;
       const int b = rest / p.mtiles;
       const int n0 = nt_idx * p.NT;
+      {
+        // tables for this tile (the buffer of this acc stage was last read two tiles ago,
+        // and every epilogue thread passed the barrier below since then)
+        const int et = threadIdx.x - 64;              // 0 .. 255
+        float* tb = s_bias + (acc & 1) * 256;
+        int2* tt = s_tab + (acc & 1) * 32;
+        if (et < p.NT) {
+          const int n = n0 + et;
+          const int ch = (p.kind == MS_CONVT) ? n % p.cout : n;
+          tb[et] = p.bias != nullptr ? __ldg(p.bias + ch) : 0.f;
+        }
+        if (et < (p.NT >> 3)) {
+          const int n = n0 + et * 8;
+          if (p.kind == MS_CONVT) {
+            const int r = n / p.cout;
+            tt[et] = make_int2(r, n - r * p.cout);
+          } else {
+            tt[et] = make_int2(0, n);
+          }
+        }
+        named_bar_sync(1, 32 * kConvEpiWarps);
+      }
+      const float* tbias = s_bias + (acc & 1) * 256;
+      const int2* ttab = s_tab + (acc & 1) * 32;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int mb = 0; mb < p.MBLK; ++mb) {
@@ -310,27 +339,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             if (h >= 2 && !two) break;
-            const int n = n0 + g * 16 + h * 8;
-            int ch, orow;
-            bool valid = m < p.Lm;
-            if (p.kind == MS_CONVT) {
-              const int r = n / p.cout;
-              ch = n - r * p.cout;
-              orow = p.stride * m + r - p.pad;
-              valid = valid && orow >= 0 && orow < p.Lout;
-            } else {
-              ch = n;
-              orow = m;
-            }
+            const int cidx = g * 2 + h;               // 8-column chunk within the tile
+            const int2 rc = ttab[cidx];
+            const int ch = rc.y;
+            const int orow = (p.kind == MS_CONVT) ? p.stride * m + rc.x - p.pad : m;
+            const bool valid = (m < p.Lm) && orow >= 0 && orow < p.Lout;
             if (!valid) continue;
             float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[h * 8 + j]) * p.alpha;
-            if (p.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ch) + 1);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            {
+              const float4 b0 = *reinterpret_cast<const float4*>(tbias + cidx * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(tbias + cidx * 8 + 4);
+              f[0] = fmaf(__uint_as_float(v[h * 8 + 0]), p.alpha, b0.x);
+              f[1] = fmaf(__uint_as_float(v[h * 8 + 1]), p.alpha, b0.y);
+              f[2] = fmaf(__uint_as_float(v[h * 8 + 2]), p.alpha, b0.z);
+              f[3] = fmaf(__uint_as_float(v[h * 8 + 3]), p.alpha, b0.w);
+              f[4] = fmaf(__uint_as_float(v[h * 8 + 4]), p.alpha, b1.x);
+              f[5] = fmaf(__uint_as_float(v[h * 8 + 5]), p.alpha, b1.y);
+              f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), p.alpha, b1.z);
+              f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), p.alpha, b1.w);
             }
             if (p.leaky) {
 #pragma unroll
@@ -338,16 +364,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
             const size_t idx = (static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + orow;
             if (p.res32 != nullptr) {
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8));
-              const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.res32 + idx * 8) + 1);
-              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
-              f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+              float r8[8];
+              ld_global_nc_v8(p.res32 + idx * 8, r8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += r8[j];
             }
-            if (p.y32 != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(p.y32 + idx * 8);
-              dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-              dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-            }
+            if (p.y32 != nullptr) st_global_v8(p.y32 + idx * 8, f);
             if (p.y16 != nullptr) {
               uint4 o;
               o.x = pack2(f[0], f[1], p.operand);

@@ -130,6 +130,39 @@ __global__ void __launch_bounds__(128, 1) microbench_kernel(long long* out) {
       slot += 2;
     }
     (void)par2; (void)bar2;
+    // ---- epilogue primitives (slot 26..)
+    slot = 26;
+    uint32_t v[16];
+    const uint32_t taddr = tmem;   // warp 0 -> lanes 0..31
+    t0 = clock64();
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+    t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = t1 - t0 + (v[0] == 0x12345678u); slot++;     // 26: ld16+wait
+    t0 = clock64();
+    uint32_t v2[16], v3[16], v4[16];
+    tmem_ld16(taddr, v); tmem_ld16(taddr + 16, v2); tmem_ld16(taddr + 32, v3); tmem_ld16(taddr + 48, v4);
+    tmem_ld_wait();
+    v[0] ^= v2[0] ^ v3[0] ^ v4[0];
+    t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = t1 - t0 + (v[0] == 0x12345678u); slot++;     // 27: 4x ld16 + wait
+    t0 = clock64();
+    tmem_st16(taddr, v);
+    tmem_st_wait();
+    t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = t1 - t0; slot++;                              // 28: st16 + wait
+    t0 = clock64();
+    st_shared_v4(sA + threadIdx.x * 16, v[0], v[1], v[2], v[3]);
+    st_shared_v4(sA + 4096 + threadIdx.x * 16, v[0], v[1], v[2], v[3]);
+    t1 = clock64();
+    fence_proxy_async_smem();
+    t2 = clock64();
+    if (threadIdx.x == 0) { out[slot] = t1 - t0; out[slot + 1] = t2 - t1; } slot += 2;  // 29: 2 STS, 30: fence.proxy.async
+    slot += 3;
+    t0 = clock64();
+    named_bar_sync(2, 32);
+    t1 = clock64();
+    if (threadIdx.x == 0) out[slot] = t1 - t0; slot++;                              // 34: named barrier (1 warp)
   }
   tc_fence_before();
   __syncthreads();

@@ -255,6 +255,20 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global accesses (sm_100+): one full 32-byte sector per thread per instruction --
+// exactly one BLK f32 (row, channel-block) element group.  Address must be 32-byte aligned.
+__device__ __forceinline__ void ld_global_nc_v8(const float* p, float (&f)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]),
+                 "=f"(f[6]), "=f"(f[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_v8(float* p, const float (&f)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(f[0]),
+               "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7])
+               : "memory");
+}
+
 // ------------------------------------------------------------------- small math
 __device__ __forceinline__ float leaky02(float v) { return fmaxf(v, 0.2f * v); }
 

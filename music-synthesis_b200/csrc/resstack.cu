@@ -248,21 +248,16 @@ resstack_kernel(const __grid_constant__ StackParams p) {
           const int t = t0 + row;
           const bool inside = (t >= 0) && (t < p.L);
           const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
-          const float4* src = reinterpret_cast<const float4*>(
-              p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8);
-          const size_t cstride = static_cast<size_t>(p.L) * 2;   // float4 per chunk
+          const float* src =
+              p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8;
+          const size_t cstride = static_cast<size_t>(p.L) * 8;   // floats per chunk
           uint32_t v[COLS];
 #pragma unroll
           for (int c = 0; c < COLS / 8; ++c) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), d4 = a;
-            if (inside) {
-              a = __ldg(src + c * cstride);
-              d4 = __ldg(src + c * cstride + 1);
-            }
-            v[c * 8 + 0] = __float_as_uint(a.x); v[c * 8 + 1] = __float_as_uint(a.y);
-            v[c * 8 + 2] = __float_as_uint(a.z); v[c * 8 + 3] = __float_as_uint(a.w);
-            v[c * 8 + 4] = __float_as_uint(d4.x); v[c * 8 + 5] = __float_as_uint(d4.y);
-            v[c * 8 + 6] = __float_as_uint(d4.z); v[c * 8 + 7] = __float_as_uint(d4.w);
+            float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (inside) ld_global_nc_v8(src + c * cstride, a8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[c * 8 + j] = __float_as_uint(a8[j]);
           }
 #pragma unroll
           for (int c = 0; c < COLS / 8; ++c) {
@@ -393,9 +388,9 @@ resstack_kernel(const __grid_constant__ StackParams p) {
                                  pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
                                  pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
                 if (p.y32 != nullptr) {
-                  float4* d32 = reinterpret_cast<float4*>(p.y32 + idx * 8);
-                  d32[0] = make_float4(f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3]);
-                  d32[1] = make_float4(f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]);
+                  const float o8[8] = {f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3],
+                                       f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]};
+                  st_global_v8(p.y32 + idx * 8, o8);
                 }
               }
             }

@@ -19,3 +19,8 @@ for N in (32, 64, 128, 256):
         s += 2
 print("64 MMAs N=128 issue %d complete %d (ideal %d)" % (o[s], o[s + 1], 64 * 64)); s += 2
 print("64 MMAs N=32 (4 accs) issue %d complete %d (ideal %d)" % (o[s], o[s + 1], 64 * 16))
+
+names2 = ["tmem ld16+wait", "4x tmem ld16 + wait", "tmem st16 + wait", "2x st.shared.v4", "fence.proxy.async",
+          "tc_fence_before+mbar_arrive", "LDG.128 (L2/cold)", "LDG.128 (L1 hit)", "named bar (1 warp)"]
+for i, n in enumerate(names2):
+    print("%-30s %6d" % (n, o[26 + i]))
