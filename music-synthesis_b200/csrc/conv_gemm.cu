@@ -22,6 +22,8 @@
 // featuresynth/util/modules.py:358-388 (see include/msb200.h).
 #include "conv_gemm.cuh"
 
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -31,6 +33,16 @@
 namespace msb {
 
 // ---------------------------------------------------------------- configuration
+// MSB_CONV_PAIR=0 disables the CTA-pair kernel (process-wide, read once)
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MSB_CONV_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int pick_nt(int ntot) {
   for (int nt = 256; nt >= 16; nt -= 16)
     if (ntot % nt == 0) return nt;
@@ -70,10 +82,42 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     mx = c->off[t] > mx ? c->off[t] : mx;
   }
   c->min_off = mn;
-  c->MBLK = c->Lm > 128 ? 2 : 1;
-  c->RA = 128 * c->MBLK + mx - mn;
   c->NT = pick_nt(c->Ntot);
   if (c->NT == 0) return false;
+  // the pair kernel pays off when a tile carries enough K work to amortise the cross-CTA
+  // hand-offs (measured: wins for K*taps >= 512, loses for the small s=2 upsamplers)
+  c->pair = (pair_enabled() && c->NT % 32 == 0 && d.cin * c->taps >= 512) ? 1 : 0;
+  if (c->pair) {
+    // CTA pair: 256-row cluster tile, one M-block + half of every weight stage per CTA
+    c->MBLK = 1;
+    c->RA = 128 + mx - mn;
+    const int nth = c->NT / 2;
+    c->KB = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
+    auto pstage = [&](int kb) { return (kb / 8) * c->RA * 16 + c->taps * (kb / 8) * nth * 16; };
+    const int pbudget = kSmemBudget - kSmemHeader;
+    while (pstage(c->KB) * 3 > pbudget && c->KB > 16) c->KB /= 2;
+    if (pstage(c->KB) * 2 > pbudget) return false;
+    c->nnt = c->Ntot / c->NT;
+    c->nkb = d.cin / c->KB;
+    c->mtiles = (c->Lm + 255) / 256;
+    c->a_stage_bytes = (c->KB / 8) * c->RA * 16;
+    c->w_stage_bytes = c->taps * (c->KB / 8) * nth * 16;   // per CTA (half of the n-tile)
+    c->stage_bytes = (c->a_stage_bytes + c->w_stage_bytes + 127) / 128 * 128;
+    int ps = pbudget / c->stage_bytes;
+    if (ps > kMaxStages) ps = kMaxStages;
+    c->stages = ps;
+    c->acc_stages = 2;
+    int pcols = 32;
+    while (pcols < 2 * c->NT) pcols *= 2;
+    c->tmem_cols = pcols;
+    size_t psmem = kSmemHeader + static_cast<size_t>(c->stages) * c->stage_bytes;
+    if (psmem < 120 * 1024) psmem = 120 * 1024;
+    c->smem_bytes = psmem;
+    c->packed_weight_bytes = static_cast<size_t>(c->nnt) * 2 * c->nkb * c->w_stage_bytes;
+    return true;
+  }
+  c->MBLK = c->Lm > 128 ? 2 : 1;
+  c->RA = 128 * c->MBLK + mx - mn;
   c->KB = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
   // NT / KB define the packed weight layout, so they must not depend on the input
   // length: size the stages for the largest tile (two M-blocks) regardless of MBLK
@@ -436,6 +480,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
   }
 }
 
+ms_status launch_conv_pair(const ConvGemmParams& p, size_t smem_bytes, cudaStream_t stream);
+
 ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
                       const void* w_packed, const float* bias, const float* res32, void* y16,
                       float* y32, cudaStream_t stream) {
@@ -452,7 +498,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   for (int t = 0; t < kMaxTaps; ++t) p.off[t] = t < c.taps ? c.off[t] : 0;
   p.min_off = c.min_off; p.RA = c.RA;
   p.Ntot = c.Ntot; p.NT = c.NT; p.KB = c.KB; p.nnt = c.nnt; p.nkb = c.nkb;
-  p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages;
+  p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages; p.pair = c.pair;
   p.stages = c.stages; p.a_stage_bytes = c.a_stage_bytes; p.w_stage_bytes = c.w_stage_bytes;
   p.stage_bytes = c.stage_bytes; p.tmem_cols = c.tmem_cols;
   p.kind = d.kind; p.stride = d.stride; p.pad = d.pad; p.leaky = d.leaky;
@@ -461,6 +507,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
   p.total_tiles = static_cast<int>(tiles);
 
+  if (c.pair) return launch_conv_pair(p, c.smem_bytes, stream);
   static thread_local size_t attr_set = 0;
   if (c.smem_bytes > attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel,
@@ -504,7 +551,8 @@ ms_status ms_conv_pack_weight(const ms_conv_desc* d, const float* w_f32, void* w
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
   pack_weight_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
       w_f32, static_cast<uint16_t*>(w_packed), d->kind, d->cin, d->cout, d->ksize, d->stride,
-      c.taps, c.NT, c.KB, c.nnt, c.nkb, d->operand, total);
+      c.taps, c.pair ? c.NT / 2 : c.NT, c.KB, c.pair ? 2 * c.nnt : c.nnt, c.nkb, d->operand,
+      total);
   return after_launch("pack_weight_kernel");
 }
 

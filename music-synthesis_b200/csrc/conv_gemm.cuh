@@ -17,6 +17,7 @@ constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100
 struct ConvCfg {
   int taps;            // GEMM taps (MS_CONV: ksize; MS_CONVT: 2)
   int off[kMaxTaps];   // input row of tap t for GEMM row m is m + off[t]
+  int pair;            // 1: CTA-pair kernel (cta_group::2, 256-row cluster tile, W split)
   int MBLK;            // 128-row M-blocks per CTA tile (1 or 2): they share each W stage
   int min_off, RA;     // RA = 128*MBLK + max_off - min_off rows of A staged per tile
   int Ntot;            // GEMM N (MS_CONV: cout; MS_CONVT: stride*cout)
@@ -47,7 +48,7 @@ struct ConvGemmParams {
   int taps;
   int off[kMaxTaps];
   int min_off, RA;
-  int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages;
+  int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages, pair;
   int stages, a_stage_bytes, w_stage_bytes, stage_bytes, tmem_cols;
   int kind, stride, pad, leaky, operand;
   float alpha;

@@ -1,0 +1,334 @@
+// CTA-pair variant of the implicit-GEMM convolution (see conv_gemm.cu for the math).
+//
+// A cluster of two CTAs (one SM pair) computes a 256-row x NT-column tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256):
+//   - CTA rank r stages ITS OWN 128 rows of activations (A) and HALF of every weight
+//     stage (rows [r*NT/2, (r+1)*NT/2) of the B tile): weight bytes moved L2->SMEM per
+//     output row halve, and each tensor core reads only 4 KB (A) + NT/2*32 B (B) per MMA;
+//   - the leader (rank 0) issues the MMAs for both CTAs; D rows 0-127 land in rank 0's
+//     tensor memory, rows 128-255 in rank 1's; each CTA drains its own accumulator;
+//   - accumulators are double-buffered (2*NT <= 512 columns) so the epilogue of tile i
+//     overlaps the MMAs of tile i+1 even at NT = 256.
+// Synchronisation across the pair:
+//   full[s]      local: this CTA's bulk copies for stage s have landed
+//   peer_full[s] leader only: rank 1's stage s has landed (rank 1's warp 1 relays it with a
+//                remote mbarrier arrive)
+//   empty[s], tmem_full[a]   tcgen05.commit ... multicast::cluster to both CTAs
+//   tmem_empty[a] leader only: both epilogues drained accumulator a (rank 1 arrives remotely)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+constexpr int kPairEpiWarps = 8;
+constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
+
+__device__ __forceinline__ uint32_t pack2p(float a, float b, int operand) {
+  if (operand == MS_BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_h2(a, b);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // [0..7] full, [8..15] empty, [16..23] peer_full, [24..25] tmem_full, [26..27] tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  float* s_bias = reinterpret_cast<float*>(smem + 512);             // [2][256]
+  int2* s_tab = reinterpret_cast<int2*>(smem + 512 + 2048 - 512);   // [2][32]
+  const uint32_t bar_base = smem_u32(bars);
+  const uint32_t data_base = smem_u32(smem + kSmemHeader);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (24 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (26 + a); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int cluster_id = blockIdx.x >> 1;
+  const int nclusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+      mbar_init(pfull_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * 32 * kPairEpiWarps);   // both CTAs' epilogue threads
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(tmem_slot), p.tmem_cols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks = p.KB >> 3;
+  const int nth = p.NT >> 1;   // B rows staged by each CTA
+
+  if (warp == 0) {
+    // =============================== producer ===============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
+      const int nt_idx = tile % p.nnt;
+      const int rest = tile / p.nnt;
+      const int mt = rest % p.mtiles;
+      const int b = rest / p.mtiles;
+      const int r0 = mt * 256 + static_cast<int>(rank) * 128 + p.min_off;
+      const int lo = r0 < 0 ? 0 : r0;
+      const int hi = (r0 + p.RA) > p.lin ? p.lin : (r0 + p.RA);
+      const int nrows = hi > lo ? hi - lo : 0;
+      const bool ragged = (nrows != p.RA);
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+        const uint32_t sW = sA + p.a_stage_bytes;
+        if (ragged) {
+          const int head = lo - r0;
+          const int tail0 = head + nrows;
+          const int nz = head + (p.RA - tail0);
+          for (int i = lane; i < nz * chunks; i += 32) {
+            const int c = i / nz;
+            int r = i - c * nz;
+            r = r < head ? r : tail0 + (r - head);
+            st_shared_v4(sA + static_cast<uint32_t>(c * p.RA + r) * 16u, 0u, 0u, 0u, 0u);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+        }
+        if (elect_one()) {
+          const uint32_t bytes_a = static_cast<uint32_t>(nrows) * 16u * chunks;
+          mbar_arrive_expect_tx(full_bar(stage), bytes_a + p.w_stage_bytes);
+          const uint8_t* wsrc =
+              reinterpret_cast<const uint8_t*>(p.w) +
+              ((static_cast<size_t>(nt_idx) * 2 + rank) * p.nkb + kb) * p.w_stage_bytes;
+          bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
+          if (nrows > 0) {
+            const size_t cbase = static_cast<size_t>(b) * (p.cin >> 3) + kb * chunks;
+            for (int c = 0; c < chunks; ++c) {
+              const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
+              bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,
+                       static_cast<uint32_t>(nrows) * 16u, full_bar(stage));
+            }
+          }
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ============================ MMA issuer (rank 0) ============================
+      const uint32_t idesc = umma_idesc_f16_m256(p.NT, p.operand);
+      const uint64_t adesc0 = umma_desc_base_nosw(static_cast<uint32_t>(p.RA) * 16u, 128);
+      const uint64_t bdesc0 = umma_desc_base_nosw(static_cast<uint32_t>(nth) * 16u, 128);
+      const uint32_t a_kstep = static_cast<uint32_t>(2 * p.RA);
+      const uint32_t b_kstep = static_cast<uint32_t>(2 * nth);
+      const int nk16 = p.KB >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
+        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.NT);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          mbar_wait_cluster(pfull_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint32_t sW = sA + p.a_stage_bytes;
+          if (elect_one()) {
+            for (int t = 0; t < p.taps; ++t) {
+              uint64_t ad = adesc0 + ((sA >> 4) + static_cast<uint32_t>(p.off[t] - p.min_off));
+              uint64_t bd = bdesc0 + ((sW >> 4) + static_cast<uint32_t>(t * chunks * nth));
+              for (int k16 = 0; k16 < nk16; ++k16) {
+                umma2_f16_ss(d_tmem, ad, bd, idesc, (kb | t | k16) != 0 ? 1u : 0u);
+                ad += a_kstep;
+                bd += b_kstep;
+              }
+            }
+            umma2_commit_mc(empty_bar(stage));
+            if (kb == p.nkb - 1) umma2_commit_mc(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else {
+      // ====================== relay (rank 1): stage landed -> leader ======================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          if (elect_one()) mbar_arrive_remote(pfull_bar(stage), 0);
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int cout8 = p.cout >> 3;
+    const int ngroups = p.NT >> 4;
+    for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
+      const int nt_idx = tile % p.nnt;
+      const int rest = tile / p.nnt;
+      const int mt = rest % p.mtiles;
+      const int b = rest / p.mtiles;
+      const int n0 = nt_idx * p.NT;
+      {
+        const int et = threadIdx.x - 64;
+        float* tb = s_bias + (acc & 1) * 256;
+        int2* tt = s_tab + (acc & 1) * 32;
+        if (et < p.NT) {
+          const int n = n0 + et;
+          const int ch = (p.kind == MS_CONVT) ? n % p.cout : n;
+          tb[et] = p.bias != nullptr ? __ldg(p.bias + ch) : 0.f;
+        }
+        if (et < (p.NT >> 3)) {
+          const int n = n0 + et * 8;
+          if (p.kind == MS_CONVT) {
+            const int r = n / p.cout;
+            tt[et] = make_int2(r, n - r * p.cout);
+          } else {
+            tt[et] = make_int2(0, n);
+          }
+        }
+        named_bar_sync(1, 32 * kPairEpiWarps);
+      }
+      const float* tbias = s_bias + (acc & 1) * 256;
+      const int2* ttab = s_tab + (acc & 1) * 32;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = mt * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                             static_cast<uint32_t>(acc * p.NT);
+      bool arrived = false;
+      for (int g = 2 * half; g < ngroups; g += 4) {
+        const bool two = (g + 1) < ngroups;
+        uint32_t v[32];
+        tmem_ld16p(taddr + g * 16, &v[0]);
+        if (two) tmem_ld16p(taddr + (g + 1) * 16, &v[16]);
+        tmem_ld_wait();
+        if (g + 4 >= ngroups) {
+          tc_fence_before();
+          if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
+          arrived = true;
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (h >= 2 && !two) break;
+          const int cidx = g * 2 + h;
+          const int2 rc = ttab[cidx];
+          const int ch = rc.y;
+          const int orow = (p.kind == MS_CONVT) ? p.stride * m + rc.x - p.pad : m;
+          const bool valid = (m < p.Lm) && orow >= 0 && orow < p.Lout;
+          if (!valid) continue;
+          float f[8];
+          {
+            const float4 b0 = *reinterpret_cast<const float4*>(tbias + cidx * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(tbias + cidx * 8 + 4);
+            f[0] = fmaf(__uint_as_float(v[h * 8 + 0]), p.alpha, b0.x);
+            f[1] = fmaf(__uint_as_float(v[h * 8 + 1]), p.alpha, b0.y);
+            f[2] = fmaf(__uint_as_float(v[h * 8 + 2]), p.alpha, b0.z);
+            f[3] = fmaf(__uint_as_float(v[h * 8 + 3]), p.alpha, b0.w);
+            f[4] = fmaf(__uint_as_float(v[h * 8 + 4]), p.alpha, b1.x);
+            f[5] = fmaf(__uint_as_float(v[h * 8 + 5]), p.alpha, b1.y);
+            f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), p.alpha, b1.z);
+            f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), p.alpha, b1.w);
+          }
+          if (p.leaky) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
+          }
+          const size_t idx = (static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + orow;
+          if (p.res32 != nullptr) {
+            float r8[8];
+            ld_global_nc_v8(p.res32 + idx * 8, r8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r8[j];
+          }
+          if (p.y32 != nullptr) st_global_v8(p.y32 + idx * 8, f);
+          if (p.y16 != nullptr) {
+            uint4 o;
+            o.x = pack2p(f[0], f[1], p.operand);
+            o.y = pack2p(f[2], f[3], p.operand);
+            o.z = pack2p(f[4], f[5], p.operand);
+            o.w = pack2p(f[6], f[7], p.operand);
+            *reinterpret_cast<uint4*>(p.y16 + idx * 8) = o;
+          }
+        }
+      }
+      if (!arrived) {
+        tc_fence_before();
+        if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  // nobody leaves while the peer may still touch this CTA's SMEM / barriers / TMEM
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, p.tmem_cols);
+  }
+}
+
+ms_status launch_conv_pair(const ConvGemmParams& p, size_t smem_bytes, cudaStream_t stream) {
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBudget);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(conv_gemm_pair_kernel)");
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 1) return check_cuda(cudaGetLastError(), "sm_count");
+  int clusters = sms / 2;
+  if (p.total_tiles < clusters) clusters = p.total_tiles;
+  conv_gemm_pair_kernel<<<2 * clusters, kPairThreads, smem_bytes, stream>>>(p);
+  return after_launch("conv_gemm_pair_kernel");
+}
+
+}  // namespace msb
