@@ -71,7 +71,9 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     c->Ntot = d.stride * d.cout;
     if (c->Ntot % 16 != 0) return false;
     c->Lout = (d.lin - 1) * d.stride - 2 * d.pad + d.ksize;
-    c->Lm = d.lin + 1;
+    // GEMM rows q = 0 .. lin-1; the extra row q = lin (only tap x[lin-1], last `pad` output
+    // rows of each clip) is computed by convt_tail_kernel so that lin = 256 is ONE tile
+    c->Lm = d.lin;
   } else {
     return false;
   }
@@ -445,6 +447,53 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 }
 
+// ------------------------------------------------- ConvTranspose tail (GEMM row q = lin)
+// out[b, co, s*lin + r - pad] = act(bias[co] + sum_ci x[b, ci, lin-1] * W[ci, co, r + s]),
+// r < pad.  Reads the SAME packed 16-bit weights / 16-bit activations as the main GEMM
+// (tap 0 of the polyphase form), accumulates in fp32.  Tiny: pad*cout outputs per clip.
+__global__ void convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */,
+                                  int nnt_p /* packed n-tiles */) {
+  const int r = blockIdx.y;                 // phase < pad
+  const int b = blockIdx.z;
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= p.cout) return;
+  const int orow = p.stride * p.lin + r - p.pad;
+  if (orow < 0 || orow >= p.Lout) return;
+  const int n = r * p.cout + co;            // GEMM column
+  const int nt = n / ntp, nn = n - nt * ntp;
+  const int chunks = p.KB >> 3;
+  float acc = 0.f;
+  for (int ci = 0; ci < p.cin; ++ci) {
+    const int kb = ci / p.KB, c = (ci % p.KB) >> 3, e = ci & 7;
+    // packed[nt][kb][tap = 0][c][nn][e]
+    const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + 0) * chunks + c) * ntp + nn) * 8 + e;
+    const size_t xi = ((static_cast<size_t>(b) * (p.cin >> 3) + (ci >> 3)) * p.lin + (p.lin - 1)) * 8 + e;
+    float wv, xv;
+    if (p.operand == MS_BF16) {
+      wv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p.w + wi));
+      xv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p.x + xi));
+    } else {
+      wv = __half2float(*reinterpret_cast<const __half*>(p.w + wi));
+      xv = __half2float(*reinterpret_cast<const __half*>(p.x + xi));
+    }
+    acc = fmaf(xv, wv, acc);
+  }
+  float v = acc * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
+  if (p.leaky) v = leaky02(v);
+  const size_t idx = ((static_cast<size_t>(b) * (p.cout >> 3) + (co >> 3)) * p.Lout + orow) * 8 + (co & 7);
+  if (p.res32 != nullptr) v += p.res32[idx];
+  if (p.y32 != nullptr) p.y32[idx] = v;
+  if (p.y16 != nullptr) {
+    if (p.operand == MS_BF16) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      p.y16[idx] = *reinterpret_cast<uint16_t*>(&h);
+    } else {
+      __half h = __float2half_rn(v);
+      p.y16[idx] = *reinterpret_cast<uint16_t*>(&h);
+    }
+  }
+}
+
 // ------------------------------------------------------------ weight packing
 // packed[nt][kb][tap][chunk][nn][e]  <-  reference-layout fp32 weights
 __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
@@ -507,6 +556,14 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
   p.total_tiles = static_cast<int>(tiles);
 
+  if (d.kind == MS_CONVT) {
+    // the q = lin row first (independent outputs: last `pad` rows of each clip)
+    dim3 tgrid((d.cout + 127) / 128, d.pad, d.batch);
+    convt_tail_kernel<<<tgrid, 128, 0, stream>>>(p, c.pair ? c.NT / 2 : c.NT,
+                                                 c.pair ? 2 * c.nnt : c.nnt);
+    ms_status ts = after_launch("convt_tail_kernel");
+    if (ts != MS_OK) return ts;
+  }
   if (c.pair) return launch_conv_pair(p, c.smem_bytes, stream);
   static thread_local size_t attr_set = 0;
   if (c.smem_bytes > attr_set) {
