@@ -125,6 +125,21 @@ ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, f
                           void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Grouped / strided conv1d on CUDA cores (fp32, NCL in / NCL out, fused bias + LeakyReLU)
+ * and average pooling.
+ *   replaces F.conv1d(..., stride, padding, groups) at featuresynth/discriminator/full.py:
+ *   13-18 (Conv1d(1,16,15,1,7) and the k41 s4 grouped convs, 4 input channels per group)
+ *   and F.avg_pool1d(x, 4, 2, 2) (count_include_pad=True) at discriminator/melgan.py:22.
+ *   w: (cout, cin/groups, k) reference layout.  Lout = (lin + 2*pad - k)/stride + 1.
+ * ------------------------------------------------------------------------- */
+int ms_conv1d_out_len(int lin, int ksize, int stride, int pad);
+ms_status ms_conv1d_direct_fwd(const float* x, const float* w, const float* bias, float* y,
+                               int batch, int cin, int cout, int lin, int ksize, int stride,
+                               int pad, int groups, int leaky, void* stream);
+ms_status ms_avg_pool1d_fwd(const float* x, float* y, int batch_channels, int lin, int ksize,
+                            int stride, int pad, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Fused ResidualStack: 3 ResidualAtoms = 6 k3 convolutions (dilations d0,1,d1,1,d2,1)
  * in one kernel; activations stay in shared memory, the fp32 residual stream in
  * tensor memory.  channels in {32, 64, 128}; d0+d1+d2+3 <= 16.

@@ -42,6 +42,11 @@ SIGNATURES = {
                                        c_void_p]),
     "ms_conv_to_mono": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
+    "ms_conv1d_out_len": (c_int, [c_int, c_int, c_int, c_int]),
+    "ms_conv1d_direct_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ms_avg_pool1d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p]),
     "ms_resstack_supported": (c_int, [c_int]),
     "ms_resstack_packed_weight_bytes": (c_size_t, [c_int]),
     "ms_resstack_pack_weights": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),

@@ -1,0 +1,2 @@
+from .full import FullDiscriminator  # noqa: F401
+from .melgan import MelGanDiscriminator  # noqa: F401

@@ -101,6 +101,35 @@ def audio2mel(audio, window, mel_basis, n_fft, hop):
     return out
 
 
+def conv1d_direct(x, w, bias, stride=1, pad=0, groups=1, leaky=False):
+    """fp32 CUDA-core conv1d (grouped / strided), NCL in -> NCL out."""
+    _lib.require_cuda(x, "x")
+    x = x.contiguous()
+    B, cin, lin = x.shape
+    cout, cin_g, k = w.shape
+    if cin_g * groups != cin:
+        raise _lib.MsbError("conv1d_direct: weight / groups mismatch")
+    lout = _lib.lib().ms_conv1d_out_len(lin, k, stride, pad)
+    if lout < 0:
+        raise _lib.MsbError("conv1d_direct: invalid geometry")
+    y = torch.empty((B, cout, lout), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ms_conv1d_direct_fwd(ptr(x), ptr(w.contiguous()), ptr(bias), ptr(y), B, cin,
+                                          cout, lin, k, stride, pad, groups, int(leaky),
+                                          stream_ptr()), "ms_conv1d_direct_fwd")
+    return y
+
+
+def avg_pool1d(x, ksize, stride, pad):
+    _lib.require_cuda(x, "x")
+    x = x.contiguous()
+    B, C, lin = x.shape
+    lout = _lib.lib().ms_conv1d_out_len(lin, ksize, stride, pad)
+    y = torch.empty((B, C, lout), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ms_avg_pool1d_fwd(ptr(x), ptr(y), B * C, lin, ksize, stride, pad,
+                                       stream_ptr()), "ms_avg_pool1d_fwd")
+    return y
+
+
 def resstack_supported(channels):
     return bool(_lib.lib().ms_resstack_supported(channels))
 
