@@ -463,20 +463,28 @@ __global__ void convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-ti
   const int nt = n / ntp, nn = n - nt * ntp;
   const int chunks = p.KB >> 3;
   float acc = 0.f;
-  for (int ci = 0; ci < p.cin; ++ci) {
-    const int kb = ci / p.KB, c = (ci % p.KB) >> 3, e = ci & 7;
-    // packed[nt][kb][tap = 0][c][nn][e]
-    const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + 0) * chunks + c) * ntp + nn) * 8 + e;
-    const size_t xi = ((static_cast<size_t>(b) * (p.cin >> 3) + (ci >> 3)) * p.lin + (p.lin - 1)) * 8 + e;
-    float wv, xv;
-    if (p.operand == MS_BF16) {
-      wv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p.w + wi));
-      xv = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p.x + xi));
-    } else {
-      wv = __half2float(*reinterpret_cast<const __half*>(p.w + wi));
-      xv = __half2float(*reinterpret_cast<const __half*>(p.x + xi));
+  for (int c8 = 0; c8 < (p.cin >> 3); ++c8) {        // 8 input channels per step (16-byte loads)
+    const int ci = c8 * 8;
+    const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
+    // packed[nt][kb][tap = 0][c][nn][0..7]
+    const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + 0) * chunks + c) * ntp + nn) * 8;
+    const size_t xi = ((static_cast<size_t>(b) * (p.cin >> 3) + c8) * p.lin + (p.lin - 1)) * 8;
+    const uint4 wq = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
+    const uint4 xq = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
+    const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 wf, xf;
+      if (p.operand == MS_BF16) {
+        wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+        xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
+      } else {
+        wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+        xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+      }
+      acc = fmaf(xf.x, wf.x, acc);
+      acc = fmaf(xf.y, wf.y, acc);
     }
-    acc = fmaf(xv, wv, acc);
   }
   float v = acc * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
   if (p.leaky) v = leaky02(v);

@@ -64,9 +64,10 @@ struct StackParams {
 template <int C>
 struct StackGeom {
   static constexpr int MB = 256 / C;             // M-blocks per tile
-  static constexpr int HB = MB / 2 > 0 ? MB / 2 : 1;   // M-blocks per half tile
-  static constexpr int PARTS = C >= 128 ? 4 : 2;       // column split of the epilogue
-  static constexpr int MSPLIT = 4 / PARTS;             // M-block split of the epilogue
+  static constexpr int NP = 2;                         // pipeline parts per tile (4 measured slower)
+  static constexpr int HB = MB / NP;                   // M-blocks per part
+  static constexpr int MSPLIT = HB >= 2 ? 2 : 1;       // M-block split of the epilogue
+  static constexpr int PARTS = 4 / MSPLIT;             // column split of the epilogue
   static constexpr int EW = 16;                        // epilogue warps = 4 * PARTS * MSPLIT
   static constexpr int R = MB * 128;             // rows per tile
   static constexpr int NCH = C / 8;
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
 resstack_kernel(const __grid_constant__ StackParams p) {
   using G = StackGeom<C>;
   constexpr int MB = G::MB, HB = G::HB, R = G::R, NSLOT = G::NSLOT, EW = G::EW;
-  static_assert(MB >= 2 && MB == 2 * HB, "tile must split into two halves");
+  constexpr int NP = G::NP;
+  static_assert(MB >= 2 && MB == NP * HB && NP <= 8, "tile must split into NP parts");
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   // [0,18) wfull  [18,36) wempty  [36,44) acc_full  [44,52) act_ready
@@ -194,33 +196,30 @@ resstack_kernel(const __grid_constant__ StackParams p) {
             if (elect_one()) umma_commit(bar);
             __syncwarp();
           };
-          // ---- half A: everything except tap +d of its last M-block (which reads rows
-          //      of half B)
-          MSB_TRACE(nconv * 16 + 0);
-          mbar_wait(act_ready(0), ready_par);
-          tc_fence_after();
-          MSB_TRACE(nconv * 16 + 1);
-          wait_tap(0);
-          MSB_TRACE(nconv * 16 + 2);
-          issue(0, 0, HB);
-          wait_tap(1);
-          issue(1, 0, HB);
-          wait_tap(2);
-          if (HB > 1) issue(2, 0, HB - 1);
-          // ---- half B
-          MSB_TRACE(nconv * 16 + 4);
-          mbar_wait(act_ready(1), ready_par);
-          tc_fence_after();
-          MSB_TRACE(nconv * 16 + 5);
-          issue(2, HB - 1, HB);
-          commit(acc_full(0));
-          issue(0, HB, MB);
-          commit(wempty((pos + 0) % NSLOT));
-          issue(1, HB, MB);
-          commit(wempty((pos + 1) % NSLOT));
-          issue(2, HB, MB);
+          // Part i = M-blocks [i*HB, (i+1)*HB).  As soon as the epilogue has produced part i
+          // (act_ready(i)): tap +d of part i-1's last M-block (it reads into part i) completes
+          // part i-1; then every tap of part i except tap +d of ITS last M-block.
+          for (int part = 0; part < NP; ++part) {
+            mbar_wait(act_ready(part), ready_par);
+            tc_fence_after();
+            const int m0 = part * HB, m1 = m0 + HB;
+            if (part > 0) {
+              issue(2, m0 - 1, m0);
+              commit(acc_full(part - 1));
+            } else {
+              wait_tap(0);
+            }
+            issue(0, m0, m1);
+            if (part == NP - 1) commit(wempty((pos + 0) % NSLOT));
+            if (part == 0) wait_tap(1);
+            issue(1, m0, m1);
+            if (part == NP - 1) commit(wempty((pos + 1) % NSLOT));
+            if (part == 0) wait_tap(2);
+            // the tile's very last M-block has no successor: its tap +d runs off the tile edge
+            issue(2, m0, part == NP - 1 ? m1 : m1 - 1);
+          }
           commit(wempty((pos + 2) % NSLOT));
-          commit(acc_full(1));
+          commit(acc_full(NP - 1));
           MSB_TRACE(nconv * 16 + 15);
         }
       }
@@ -242,7 +241,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
       const bool edge = (t0 < 0) || (t0 + R > p.L);                 // warp-uniform
       // ---- prologue: x32 (global) -> TMEM residual stream + 16-bit operand in sX
       if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2);
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < NP; ++h) {
         for (int mb = h * HB + ms; mb < (h + 1) * HB; mb += G::MSPLIT) {
           const int row = mb * 128 + q * 32 + lane;
           const int t = t0 + row;
@@ -299,7 +298,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
             }
           }
         }
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NP; ++h) {
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 0);
           mbar_wait(acc_full(h), nconv & 1u);
           tc_fence_after();
