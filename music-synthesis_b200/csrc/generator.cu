@@ -5,6 +5,7 @@
 // fp32 residual stream: each ResidualAtom output is kept in fp32 (BLK f32) for the next
 // skip connection and, rounded once, in 16-bit as the next conv's operand.  The final
 // 32->1 conv + tanh runs in fp32 on the fp32 stream.
+#include <cstdlib>
 #include <vector>
 
 #include "conv_gemm.cuh"
@@ -25,6 +26,17 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
                        float* mono_out);
 
 namespace {
+
+// MSB_STAGE1_CHUNK: clips per sub-chunk of the leading low-rate layers (0 = whole pass)
+int stage1_chunk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MSB_STAGE1_CHUNK");
+    v = e != nullptr ? atoi(e) : 0;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
 
 struct GenLayer {
   ms_conv_desc d;   // batch / lin filled per call
@@ -202,7 +214,58 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
     bool fused_tail = false;
     const void* cur16 = nullptr;  // 16-bit operand of the next layer
     int cur = 0;                  // which x16/x32 buffer holds the residual stream
-    for (const GenLayer& L : plan.layers) {
+    // The leading low-rate layers (first conv, first upsampler, C=256 residual stack) are
+    // run in sub-chunks of `sc` clips so that their fp32 residual stream stays L2-resident
+    // between consecutive launches; everything after runs on the whole pass.
+    size_t nlead = 0;
+    while (nlead < plan.layers.size() && plan.layers[nlead].role <= 3) ++nlead;
+    int sc = stage1_chunk();
+    if (sc <= 0 || sc > nb) sc = nb;
+    for (int c0 = 0; c0 < nb; c0 += sc) {
+      const int ncb = (nb - c0) < sc ? (nb - c0) : sc;
+      const size_t o1 = static_cast<size_t>(c0) * 2048 * T;          // stage-1 elements / clip
+      uint8_t* lx16[2] = {static_cast<uint8_t*>(x16[0]) + o1 * 2, static_cast<uint8_t*>(x16[1]) + o1 * 2};
+      uint8_t* ly16 = static_cast<uint8_t*>(y16) + o1 * 2;
+      float* lx32[2] = {x32[0] + o1, x32[1] + o1};
+      const uint8_t* lxin = static_cast<const uint8_t*>(xin16) + static_cast<size_t>(c0) * in_channels * (T + 6) * 2;
+      uint8_t* lh16 = static_cast<uint8_t*>(h16) + static_cast<size_t>(c0) * 512 * T * 2;
+      const void* l16 = nullptr;
+      int lc = 0;
+      for (size_t li = 0; li < nlead; ++li) {
+        const GenLayer& L = plan.layers[li];
+        ms_conv_desc d = L.d;
+        d.batch = ncb;
+        d.lin = L.len_mult * frames + (L.role == 0 ? 6 : 0);
+        ConvCfg c;
+        if (!make_conv_cfg(d, &c)) return MS_ERR_INVALID;
+        const void* w = wb + L.w_off;
+        const float* bias = reinterpret_cast<const float*>(wb + L.b_off);
+        switch (L.role) {
+          case 0:
+            s = launch_conv(d, c, lxin, w, bias, nullptr, lh16, nullptr, st);
+            l16 = lh16;
+            break;
+          case 1:
+            lc = 0;
+            s = launch_conv(d, c, l16, w, bias, nullptr, lx16[0], lx32[0], st);
+            l16 = lx16[0];
+            break;
+          case 2:
+            s = launch_conv(d, c, l16, w, bias, nullptr, ly16, nullptr, st);
+            break;
+          default:
+            s = launch_conv(d, c, ly16, w, bias, lx32[lc], lx16[lc ^ 1], lx32[lc ^ 1], st);
+            lc ^= 1;
+            l16 = lx16[lc];
+            break;
+        }
+        if (s != MS_OK) return s;
+      }
+      cur = lc;
+    }
+    cur16 = x16[cur];
+    for (size_t li = nlead; li < plan.layers.size(); ++li) {
+      const GenLayer& L = plan.layers[li];
       if (L.role == 4) {
         // fused ResidualStack: fp32 stream in, 16-bit operand (+ fp32 for the last stage) out
         if (L.d.cout == 32) {

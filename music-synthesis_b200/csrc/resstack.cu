@@ -20,6 +20,8 @@
 // residual add (fp32, TMEM resident) -> 16-bit operand for the next conv in SMEM.
 // MMA and epilogue overlap at M-block granularity: conv l+1 starts on M-block 0 while
 // the epilogue of conv l is still draining M-block 1.
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -74,6 +76,9 @@ struct StackGeom {
   static constexpr int ACT_BYTES = R * C * 2;    // 65536
   static constexpr int TAP_BYTES = C * C * 2;
   static constexpr int NSLOT = (96 * 1024 / TAP_BYTES) < 18 ? (96 * 1024 / TAP_BYTES) : 18;
+  // CTA-pair mode: each CTA stages half of every tap (the other N-half lives in the peer)
+  static constexpr int TAP_BYTES_P = TAP_BYTES / 2;
+  static constexpr int NSLOT_P = (96 * 1024 / TAP_BYTES_P) < 18 ? (96 * 1024 / TAP_BYTES_P) : 18;
   static constexpr int MONO_BYTES = 1024;        // [7][32] fp32 tail-conv weights
   static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES;
 };
@@ -86,28 +91,39 @@ __device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
   return pack_h2(a, b);
 }
 
-template <int C>
-__global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
-resstack_kernel(const __grid_constant__ StackParams p) {
+template <int C, bool PAIR>
+__device__ __forceinline__ void resstack_body(const StackParams& p) {
   using G = StackGeom<C>;
-  constexpr int MB = G::MB, HB = G::HB, R = G::R, NSLOT = G::NSLOT, EW = G::EW;
+  constexpr int MB = G::MB, HB = G::HB, R = G::R, EW = G::EW;
+  constexpr int NSLOT = PAIR ? G::NSLOT_P : G::NSLOT;
+  constexpr int TAPB = PAIR ? G::TAP_BYTES_P : G::TAP_BYTES;   // bytes of a tap staged per CTA
+  constexpr int NB = PAIR ? C / 2 : C;                         // B rows staged per CTA
   constexpr int NP = G::NP;
   static_assert(MB >= 2 && MB == NP * HB && NP <= 8, "tile must split into NP parts");
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // [0,18) wfull  [18,36) wempty  [36,44) acc_full  [44,52) act_ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
+  // [0,18) wfull  [18,36) wempty  [36,44) acc_full  [44,52) act_ready  [52,70) peer wfull
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 640);
   const uint32_t bar_base = smem_u32(bars);
   const uint32_t sX = smem_u32(smem + kStackHeader);
   const uint32_t sY = sX + G::ACT_BYTES;
   const uint32_t sW = sY + G::ACT_BYTES;
   float* sMono = reinterpret_cast<float*>(smem + kStackHeader + 2 * G::ACT_BYTES +
-                                          NSLOT * G::TAP_BYTES);
-  const bool mono = (C == 32) && (p.mono_out != nullptr);
+                                          G::NSLOT * G::TAP_BYTES);
+  const bool mono = (C == 32) && !PAIR && (p.mono_out != nullptr);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0);
+  // tiles: CTA (or CTA pair) j takes tiles j, j + stride, ...; in pair mode the two CTAs of
+  // a cluster take adjacent tiles 2j + rank (rank 1's may be a masked dummy past the end)
+  const int tile_first = PAIR ? 2 * static_cast<int>(blockIdx.x >> 1) + static_cast<int>(rank)
+                              : static_cast<int>(blockIdx.x);
+  const int tile_stride = gridDim.x;
+  auto pair_has_work = [&](int tile) { return tile - static_cast<int>(rank) < p.total_tiles; };
   auto wfull = [&](int s) { return bar_base + 8u * s; };
   auto wempty = [&](int s) { return bar_base + 8u * (18 + s); };
   auto acc_full = [&](int m) { return bar_base + 8u * (36 + m); };
   auto act_ready = [&](int m) { return bar_base + 8u * (44 + m); };
+  auto pwfull = [&](int s) { return bar_base + 8u * (52 + s); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -116,16 +132,22 @@ resstack_kernel(const __grid_constant__ StackParams p) {
     for (int s = 0; s < 18; ++s) {
       mbar_init(wfull(s), 1);
       mbar_init(wempty(s), 1);
+      mbar_init(pwfull(s), 1);
     }
     for (int m = 0; m < 8; ++m) {
       mbar_init(acc_full(m), 1);
-      mbar_init(act_ready(m), 32 * EW);
+      mbar_init(act_ready(m), (PAIR ? 2 : 1) * EW);   // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 512);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(smem_u32(tmem_slot), 512);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(smem_u32(tmem_slot), 512);
+      tmem_relinquish();
+    }
   }
   if (mono) {
     // tail-conv weights, transposed to [tap][channel] for vector broadcast loads
@@ -134,23 +156,36 @@ resstack_kernel(const __grid_constant__ StackParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // peer barriers initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ======================= weight-tap producer =========================
     uint32_t pos = 0;  // running tap counter (ring position)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
       for (int tap = 0; tap < 18; ++tap, ++pos) {
         const int slot = pos % NSLOT;
         const uint32_t par = (pos / NSLOT) & 1u;
         mbar_wait(wempty(slot), par ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(wfull(slot), G::TAP_BYTES);
-          bulk_g2s(sW + slot * G::TAP_BYTES,
-                   reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(tap) * G::TAP_BYTES,
-                   G::TAP_BYTES, wfull(slot));
+          mbar_arrive_expect_tx(wfull(slot), TAPB);
+          // pair layout: [conv][tap][N-half][chunk][C/2][8]
+          bulk_g2s(sW + slot * TAPB,
+                   reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(tap) * G::TAP_BYTES +
+                       (PAIR ? rank * TAPB : 0u),
+                   TAPB, wfull(slot));
         }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1 && PAIR && !leader) {
+    // ============ relay (rank 1): "my half of tap landed" -> leader's pwfull ============
+    uint32_t pos = 0;
+    for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
+      for (int tap = 0; tap < 18; ++tap, ++pos) {
+        mbar_wait(wfull(pos % NSLOT), (pos / NSLOT) & 1u);
+        if (elect_one()) mbar_arrive_remote(pwfull(pos % NSLOT), 0);
         __syncwarp();
       }
     }
@@ -159,12 +194,12 @@ resstack_kernel(const __grid_constant__ StackParams p) {
     // Warp-uniform control flow; only the tcgen05 instructions are predicated on one
     // elected lane, so descriptors stay in uniform registers.
     {
-      const uint32_t idesc = umma_idesc_f16(C, p.operand);
+      const uint32_t idesc = PAIR ? umma_idesc_f16_m256(C, p.operand) : umma_idesc_f16(C, p.operand);
       const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);
-      const uint64_t bdesc0 = umma_desc_base_nosw(C * 16, 128);
+      const uint64_t bdesc0 = umma_desc_base_nosw(NB * 16, 128);
       uint32_t pos = 0;      // ring position of the current conv's first tap
       uint32_t nconv = 0;    // convs issued so far (parity of act_ready waits)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
         for (int l = 0; l < 6; ++l, pos += 3, ++nconv) {
           const int d = (l & 1) ? 1 : p.dil[l >> 1];
           const uint32_t src = (l & 1) ? sY : sX;
@@ -173,17 +208,20 @@ resstack_kernel(const __grid_constant__ StackParams p) {
           auto issue = [&](int t, int mb0, int mb1) {
             const int slot = (pos + t) % NSLOT;
             const int shift = (t - 1) * d;
-            const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(slot * G::TAP_BYTES)) >> 4);
+            const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(slot * TAPB)) >> 4);
             if (elect_one()) {
               for (int mb = mb0; mb < mb1; ++mb) {
                 const uint64_t ad =
                     adesc0 + ((src + static_cast<uint32_t>((mb * 128 + shift) * 16)) >> 4);
                 const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
 #pragma unroll
-                for (int k16 = 0; k16 < C / 16; ++k16)
-                  umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * (2 * R * 16 / 16)),
-                              bd + static_cast<uint64_t>(k16 * (2 * C * 16 / 16)), idesc,
-                              (t == 0 && k16 == 0) ? 0u : 1u);
+                for (int k16 = 0; k16 < C / 16; ++k16) {
+                  const uint64_t a_k = ad + static_cast<uint64_t>(k16 * (2 * R * 16 / 16));
+                  const uint64_t b_k = bd + static_cast<uint64_t>(k16 * (2 * NB * 16 / 16));
+                  const uint32_t accum = (t == 0 && k16 == 0) ? 0u : 1u;
+                  if (PAIR) umma2_f16_ss(dst, a_k, b_k, idesc, accum);
+                  else umma_f16_ss(dst, a_k, b_k, idesc, accum);
+                }
               }
             }
             __syncwarp();
@@ -191,16 +229,20 @@ resstack_kernel(const __grid_constant__ StackParams p) {
           auto wait_tap = [&](int t) {
             const uint32_t q = pos + t;
             mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u);
+            if (PAIR) mbar_wait_cluster(pwfull(q % NSLOT), (q / NSLOT) & 1u);
           };
           auto commit = [&](uint32_t bar) {
-            if (elect_one()) umma_commit(bar);
+            if (elect_one()) {
+              if (PAIR) umma2_commit_mc(bar); else umma_commit(bar);
+            }
             __syncwarp();
           };
           // Part i = M-blocks [i*HB, (i+1)*HB).  As soon as the epilogue has produced part i
           // (act_ready(i)): tap +d of part i-1's last M-block (it reads into part i) completes
           // part i-1; then every tap of part i except tap +d of ITS last M-block.
           for (int part = 0; part < NP; ++part) {
-            mbar_wait(act_ready(part), ready_par);
+            if (PAIR) mbar_wait_cluster(act_ready(part), ready_par);
+            else mbar_wait(act_ready(part), ready_par);
             tc_fence_after();
             const int m0 = part * HB, m1 = m0 + HB;
             if (part > 0) {
@@ -235,9 +277,19 @@ resstack_kernel(const __grid_constant__ StackParams p) {
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int chunk0 = part * (COLS / 8);
     uint32_t nconv = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_clip;
-      const int t0 = (tile % p.tiles_per_clip) * p.V - p.halo;  // clip row of tile row 0
+    // one arrival per warp on act_ready (local, or on the leader's barrier in pair mode)
+    auto arrive_act = [&](int h) {
+      __syncwarp();
+      if (lane == 0) {
+        if (!PAIR || leader) mbar_arrive(act_ready(h));
+        else mbar_arrive_remote(act_ready(h), 0);
+      }
+    };
+    for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
+      const bool live = tile < p.total_tiles;      // false: rank 1's dummy tile of an odd pair
+      const int b = live ? tile / p.tiles_per_clip : 0;
+      // a dummy tile sits entirely before the clip: every row is masked to zero
+      const int t0 = live ? (tile % p.tiles_per_clip) * p.V - p.halo : -2 * R;
       const bool edge = (t0 < 0) || (t0 + R > p.L);                 // warp-uniform
       // ---- prologue: x32 (global) -> TMEM residual stream + 16-bit operand in sX
       if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2);
@@ -273,7 +325,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(act_ready(h));
+        arrive_act(h);
       }
       if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2 + 1);
       // ---- six convolutions
@@ -284,7 +336,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * C + part * COLS);
         if (l == 4) {
           // warm L2 with the next tile's input while this tile finishes
-          const int ntile = tile + gridDim.x;
+          const int ntile = tile + tile_stride;
           if (ntile < p.total_tiles && (lane & 3) == 0) {
             const int nb = ntile / p.tiles_per_clip;
             const int nt0 = (ntile % p.tiles_per_clip) * p.V - p.halo;
@@ -376,7 +428,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
               float* P = reinterpret_cast<float*>(smem + kStackHeader) + (part * 7) * R + row;
 #pragma unroll
               for (int k = 0; k < 7; ++k) P[k * R] = pk[k];
-            } else if (t >= 0 && t < p.L && row >= p.halo && row < R - p.halo) {
+            } else if (live && t >= 0 && t < p.L && row >= p.halo && row < R - p.halo) {
 #pragma unroll
               for (int c = 0; c < COLS / 8; ++c) {
                 const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk0 + c) * p.L + t;
@@ -398,7 +450,7 @@ resstack_kernel(const __grid_constant__ StackParams p) {
             if (second) tmem_st_wait();
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(act_ready(h));
+            arrive_act(h);
           }
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 2);
         }
@@ -426,10 +478,57 @@ resstack_kernel(const __grid_constant__ StackParams p) {
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // nobody leaves while the peer may still signal / read us
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <int C>
+__global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
+resstack_kernel(const __grid_constant__ StackParams p) {
+  resstack_body<C, false>(p);
+}
+
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster work on adjacent tiles in
+// lock-step; the leader issues M = 256 MMAs covering one M-block of each tile, each CTA
+// stages half of every weight tap.  Used for C = 128, where a single CTA's N = 128 MMAs
+// saturate the shared-memory port (A 4 KB + B 4 KB per 64 cycles) and starve the epilogue.
+template <int C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
+resstack_pair_kernel(const __grid_constant__ StackParams p) {
+  resstack_body<C, true>(p);
+}
+
+// MSB_STACK_PAIR=1 enables the CTA-pair variant (process-wide, read once).  Off by default:
+// measured on B200 at B=256, L=16384 it is 8 % slower (2861 vs 2650 us) -- the cross-CTA
+// hand-offs cost more than the halved B-operand traffic buys.
+bool stack_pair_enabled(int channels) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MSB_STACK_PAIR");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1 && channels == 128;
+}
+
+template <int C>
+ms_status launch_stack_pair(const StackParams& p, cudaStream_t stream) {
+  using G = StackGeom<C>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resstack_pair_kernel<C>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(resstack_pair_kernel)");
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 1) return check_cuda(cudaGetLastError(), "sm_count");
+  const int pairs = (p.total_tiles + 1) / 2;
+  const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+  resstack_pair_kernel<C><<<2 * clusters, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+  return after_launch("resstack_pair_kernel");
 }
 
 template <int C>
@@ -490,7 +589,9 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
   p.total_tiles = static_cast<int>(tiles);
   switch (channels) {
-    case 128: return launch_stack<128>(p, stream);
+    case 128:
+      return stack_pair_enabled(128) ? launch_stack_pair<128>(p, stream)
+                                     : launch_stack<128>(p, stream);
     case 64: return launch_stack<64>(p, stream);
     default: return launch_stack<32>(p, stream);
   }
@@ -498,14 +599,22 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
 
 // packed[conv][tap][chunk][n][e] <- w_l (C, C, 3) fp32, then 6 x C fp32 biases
 __global__ void pack_stack_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out,
-                                         int C, int operand) {
+                                         int C, int operand, int pair) {
   const int total = 3 * C * C;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int e = i % 8;
-  const int n = (i / 8) % C;
-  const int c = (i / (8 * C)) % (C / 8);
+  int n, c;
   const int t = i / (C * C);
+  if (pair) {   // [tap][N-half][chunk][C/2][8]
+    const int nn = (i / 8) % (C / 2);
+    c = (i / (8 * (C / 2))) % (C / 8);
+    const int half = (i / (8 * (C / 2) * (C / 8))) % 2;
+    n = half * (C / 2) + nn;
+  } else {      // [tap][chunk][C][8]
+    n = (i / 8) % C;
+    c = (i / (8 * C)) % (C / 8);
+  }
   const float v = w[(static_cast<size_t>(n) * C + c * 8 + e) * 3 + t];
   if (operand == MS_BF16) {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -546,7 +655,8 @@ ms_status ms_resstack_pack_weights(const float* const* params, int channels, int
   const int total = 3 * channels * channels;
   for (int l = 0; l < 6; ++l) {
     pack_stack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(
-        params[2 * l], reinterpret_cast<uint16_t*>(base + l * conv_bytes), channels, operand);
+        params[2 * l], reinterpret_cast<uint16_t*>(base + l * conv_bytes), channels, operand,
+        stack_pair_enabled(channels) ? 1 : 0);
     ms_status s = after_launch("pack_stack_weight_kernel");
     if (s != MS_OK) return s;
     s = check_cuda(cudaMemcpyAsync(bias + l * channels, params[2 * l + 1],
