@@ -222,16 +222,15 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- end to end through the module with HOST buffers ---------------------
+        # the public host-to-host call: pinned features in, pinned waveform out, every step
+        # copies its 33.5 MB of inputs H2D and its 67 MB of audio D2H inside the timed region
         for _ in range(2):
-            y = gen(x_host.to(dev, non_blocking=True))
-            y_host.copy_(y, non_blocking=True)
+            gen.generate(x_host, out=y_host)
         sync_all()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(args.steps):
-            xd = x_host.to(dev, non_blocking=True)
-            y = gen(xd)
-            y_host.copy_(y, non_blocking=True)
+            gen.generate(x_host, out=y_host)
         f1.record()
         sync_all()
         ms_e2e = f0.elapsed_time(f1)

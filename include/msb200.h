@@ -164,6 +164,21 @@ ms_status ms_resstack_tail_fwd(int batch, int len, const int* dilations /* [3] *
                                float* y, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * GAN loss reductions (forward), deterministic (no atomics).
+ *   replaces featuresynth/loss/loss.py:5-79.  out[0] (+)= weight * L(a, b) with
+ *   MS_RED_L1      mean|a-b|                     F.l1_loss in mel_gan_feature_loss (28-65)
+ *   MS_RED_HINGE_D mean(relu(1-a)+relu(1+b))     hinge_discriminator_loss(real, fake) (17-18)
+ *   MS_RED_HINGE_G mean(-a)                      hinge_generator_loss(fake)           (9-10)
+ *   MS_RED_LSQ_D   0.5(mean((a-1)^2)+mean(b^2))  least_squares_disc_loss(real, fake)  (13-14)
+ *   MS_RED_LSQ_G   0.5 mean((a-1)^2)             least_squares_generator_loss(fake)   (5-6)
+ *   workspace: ms_reduce_workspace_bytes() bytes of device memory.
+ * ------------------------------------------------------------------------- */
+enum { MS_RED_L1 = 0, MS_RED_HINGE_D = 1, MS_RED_HINGE_G = 2, MS_RED_LSQ_D = 3, MS_RED_LSQ_G = 4 };
+size_t ms_reduce_workspace_bytes(void);
+ms_status ms_reduce_fwd(int mode, const float* a, const float* b, size_t n, float weight,
+                        float* out, int accumulate, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Whole MelGanGenerator forward (inference), features -> waveform.
  *   replaces MelGanGenerator.forward, featuresynth/generator/full.py:47-50
  *   (layer list 22-45; ResidualStack util/modules.py:391-405).

@@ -54,6 +54,9 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "ms_resstack_tail_fwd": (c_int, [c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ms_reduce_workspace_bytes": (c_size_t, []),
+    "ms_reduce_fwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_int,
+                              c_void_p, c_void_p]),
     "ms_melgan_packed_weight_bytes": (c_size_t, [c_int, c_int]),
     "ms_melgan_pack_weights": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
     "ms_melgan_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

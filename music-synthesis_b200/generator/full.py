@@ -67,6 +67,54 @@ class MelGanGenerator(nn.Module):
             ws = self._workspace = torch.empty(need, dtype=torch.uint8, device=device)
         return ws
 
+    @torch.no_grad()
+    def generate(self, features, out=None, chunk_clips=64):
+        """Host-to-host inference: `features` (B,C,T) CPU tensor (pinned for full speed) ->
+        waveform (B,1,256T) CPU tensor.  This is the reference's usage pattern
+        (`generator(torch.from_numpy(x).to(device)).data.cpu().numpy()`, evaluate.py:133)
+        with the three legs pipelined: clips are processed in chunks, the H2D copy of
+        chunk i+1 and the D2H copy of chunk i-1 overlap the kernels of chunk i."""
+        if features.is_cuda:
+            raise MsbError("generate() takes host tensors; call forward() for device tensors")
+        dev = next(self.parameters()).device
+        B, C, T = features.shape
+        if out is None:
+            out = torch.empty((B, 1, 256 * T), dtype=torch.float32).pin_memory()
+        comp = torch.cuda.current_stream(dev)
+        if getattr(self, "_io_streams", None) is None:
+            self._io_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._io_streams
+        s_in.wait_stream(comp)
+        s_out.wait_stream(comp)
+        nchunks = (B + chunk_clips - 1) // chunk_clips
+        xbuf = [torch.empty((chunk_clips, C, T), dtype=torch.float32, device=dev) for _ in range(2)]
+        ybuf = [torch.empty((chunk_clips, 1, 256 * T), dtype=torch.float32, device=dev) for _ in range(2)]
+        ws = self._get_workspace(chunk_clips, T, dev)
+        weights = self._packed_weights()
+        x_free = [None, None]     # compute finished reading xbuf[k]
+        y_free = [None, None]     # D2H finished reading ybuf[k]
+        for i in range(nchunks):
+            k = i & 1
+            lo, hi = i * chunk_clips, min(B, (i + 1) * chunk_clips)
+            n = hi - lo
+            with torch.cuda.stream(s_in):
+                if x_free[k] is not None:
+                    s_in.wait_event(x_free[k])
+                xbuf[k][:n].copy_(features[lo:hi], non_blocking=True)
+                x_ready = s_in.record_event()
+            comp.wait_event(x_ready)
+            if y_free[k] is not None:
+                comp.wait_event(y_free[k])
+            ops.melgan_generator_fwd(weights, xbuf[k][:n], ws, out=ybuf[k][:n])
+            y_ready = comp.record_event()
+            x_free[k] = y_ready
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(y_ready)
+                out[lo:hi].copy_(ybuf[k][:n], non_blocking=True)
+                y_free[k] = s_out.record_event()
+        comp.wait_stream(s_out)
+        return out
+
     def forward(self, x):
         if torch.is_grad_enabled() and (x.requires_grad or
                                         any(p.requires_grad for p in self.parameters())):

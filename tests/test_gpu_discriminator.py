@@ -94,3 +94,39 @@ def test_discriminator_state_dict_layout():
     assert list(sd) == list(ref)
     for k in sd:
         assert tuple(sd[k].shape) == tuple(ref[k].shape)
+
+
+def test_loss_functions_match_golden(golden):
+    """loss.py mirrors on the GPU discriminator outputs vs the reference's loss values."""
+    from music_synthesis_b200.loss import loss as L
+    g = golden("losses_melgan")
+    d, _ = _disc()
+    with torch.no_grad():
+        f1, j1 = d((synth.randn(42, 2, 1, 4096) * 0.1).cuda())
+        f2, j2 = d((synth.randn(43, 2, 1, 4096) * 0.1).cuda())
+    got = dict(
+        disc_hinge=L.mel_gan_disc_loss(j1, j2),
+        disc_lsq=L.mel_gan_disc_loss(j1, j2, gan_loss=L.least_squares_disc_loss),
+        feature=L.mel_gan_feature_loss(f1, f2),
+        gen_hinge=L.mel_gan_gen_loss(f1, f2, j1, j2),
+        gen_lsq=L.mel_gan_gen_loss(f1, f2, j1, j2, gan_loss=L.least_squares_generator_loss))
+    for k, v in got.items():
+        assert v.is_cuda and v.dim() == 0
+        assert abs(float(v) - float(g[k])) <= 1e-3 * max(1.0, abs(float(g[k]))), (k, float(v), float(g[k]))
+
+
+def test_loss_reductions_exact_on_same_inputs():
+    """Same tensors on both sides: only fp32-vs-double accumulation differs."""
+    from music_synthesis_b200.loss import loss as L
+    a, b = randn(7, 3, 5, 1001), randn(8, 3, 5, 1001)
+    ac, bc = a.cuda(), b.cuda()
+    ref = [restate.hinge_discriminator_loss(a, b), restate.hinge_generator_loss(a),
+           restate.least_squares_disc_loss(a, b), restate.least_squares_generator_loss(a),
+           F.l1_loss(a, b)]
+    got = [L.hinge_discriminator_loss(ac, bc), L.hinge_generator_loss(ac),
+           L.least_squares_disc_loss(ac, bc), L.least_squares_generator_loss(ac),
+           L.mel_gan_feature_loss([[ac]], [[bc]])]
+    for r, v in zip(ref, got):
+        assert abs(float(r) - float(v)) < 2e-6 * max(1.0, abs(float(r)))
+    # deterministic: bit-identical on repeat
+    assert float(L.mel_gan_feature_loss([[ac]], [[bc]])) == float(got[4])

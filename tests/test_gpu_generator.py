@@ -130,3 +130,18 @@ def test_audio2mel_cfg2_and_edge_cases():
     assert s.shape == (2, 128, 1)
     assert (s.cpu() - restate.audio2mel(a[:2, :, :640], a2m.mel_basis.cpu(),
                                         a2m.window.cpu())).abs().max() < LOGMEL_TOL
+
+
+def test_generate_host_pipeline_matches_forward():
+    """The chunked, copy-overlapped host-to-host path returns exactly forward()'s result."""
+    sd = restate.melgan_generator_state(9)
+    m = _module(sd)
+    x = synth.mel_features(10, 7, 12)
+    with torch.no_grad():
+        ref = m(x.cuda()).cpu()
+    got = m.generate(x.pin_memory(), chunk_clips=3)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and torch.equal(got, ref)
+    got2 = m.generate(x, chunk_clips=64)          # pageable input, single chunk
+    torch.cuda.synchronize()
+    assert torch.equal(got2, ref)
