@@ -164,6 +164,23 @@ ms_status ms_resstack_tail_fwd(int batch, int len, const int* dilations /* [3] *
                                float* y, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * FFT octave-band split / merge (the fixed multiscale FFT filterbank).
+ *   replaces fft_frequency_decompose / fft_resample / fft_frequency_recompose,
+ *   featuresynth/audio/transform.py:50-115 (MultiScale.from_audio / to_audio,
+ *   audio/representation.py:82-103).  x: (B,1,n) f32, n and min_size powers of two.
+ *   decompose: band i has size min_size << i (i = 0 .. nbands-1, last = n); bands_out[i] is
+ *   a device pointer to (B,1,size_i) f32.  recompose: any subset of bands -> (B,1,desired).
+ *   `bands_out` / `bands` / `sizes` are HOST arrays (of device pointers / ints).
+ * ------------------------------------------------------------------------- */
+size_t ms_fft_bands_workspace_bytes(int batch, int n);
+ms_status ms_fft_frequency_decompose(const float* x, int batch, int n, int min_size,
+                                     float* const* bands_out, int nbands, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes, int nbands,
+                                     int batch, int desired_size, float* out, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------
  * GAN loss reductions (forward), deterministic (no atomics).
  *   replaces featuresynth/loss/loss.py:5-79.  out[0] (+)= weight * L(a, b) with
  *   MS_RED_L1      mean|a-b|                     F.l1_loss in mel_gan_feature_loss (28-65)

@@ -54,6 +54,11 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "ms_resstack_tail_fwd": (c_int, [c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ms_fft_bands_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ms_fft_frequency_decompose": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p), c_int,
+                                           c_void_p, c_size_t, c_void_p]),
+    "ms_fft_frequency_recompose": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int,
+                                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "ms_reduce_workspace_bytes": (c_size_t, []),
     "ms_reduce_fwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_int,
                               c_void_p, c_void_p]),

@@ -1,0 +1,261 @@
+// FFT octave-band split / merge ("fixed multiscale filterbank").
+//   replaces fft_frequency_decompose / fft_resample / fft_frequency_recompose,
+//   featuresynth/audio/transform.py:50-115 (ortho-normalised rFFT of the whole clip, band of
+//   size S keeps bins [S/4, S/2] -- the lowest keeps [0, S/2] -- and is inverse-transformed
+//   at length S; recompose zero-stuffs each band's spectrum to the full length and sums,
+//   including the reference's double-counted boundary bins).
+// HBM-bound, fp32.  Transforms are power-of-two Stockham autosort FFTs, out of place between
+// two workspace buffers: radix-4 passes (+ one radix-2 pass when log2 n is odd), twiddles
+// from sincospif (no recurrences).  Because irFFT is linear, recompose sums the bands'
+// spectra first and runs ONE inverse transform.
+#include "runtime.cuh"
+
+namespace msb {
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 twiddle(float frac_pi, float sign) {  // exp(sign*i*pi*frac)
+  float s, c;
+  sincospif(frac_pi, &s, &c);
+  return make_float2(c, sign * s);
+}
+
+// One Stockham radix-2 pass: p = 1, 2, 4, ... n/2.  sign = -1 forward, +1 inverse.
+__global__ void fft_pass2_kernel(const float2* __restrict__ x, float2* __restrict__ y, int n, int p,
+                                 float sign, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = n >> 1;
+  const int i = static_cast<int>(gid % t);
+  const size_t base = (gid / t) * n;
+  const int k = i & (p - 1);
+  const int j = ((i - k) << 1) + k;
+  const float2 u0 = x[base + i];
+  const float2 u1 = cmul(x[base + i + t], twiddle(static_cast<float>(k) / static_cast<float>(p), sign));
+  y[base + j] = make_float2(u0.x + u1.x, u0.y + u1.y);
+  y[base + j + p] = make_float2(u0.x - u1.x, u0.y - u1.y);
+}
+
+// One Stockham radix-4 pass: p = 1, 4, 16, ...
+__global__ void fft_pass4_kernel(const float2* __restrict__ x, float2* __restrict__ y, int n, int p,
+                                 float sign, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = n >> 2;
+  const int i = static_cast<int>(gid % t);
+  const size_t base = (gid / t) * n;
+  const int k = i & (p - 1);
+  const int j = ((i - k) << 2) + k;
+  const float a = static_cast<float>(k) / static_cast<float>(2 * p);   // alpha / pi
+  float2 v0 = x[base + i];
+  float2 v1 = cmul(x[base + i + t], twiddle(a, sign));
+  float2 v2 = cmul(x[base + i + 2 * t], twiddle(2.f * a, sign));
+  float2 v3 = cmul(x[base + i + 3 * t], twiddle(3.f * a, sign));
+  // radix-4 butterfly
+  const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+  const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+  // multiply d13 by (sign * i):  forward (sign=-1): -i*d13 = (d13.y, -d13.x)
+  const float2 r13 = make_float2(-sign * d13.y, sign * d13.x);
+  y[base + j] = make_float2(s02.x + s13.x, s02.y + s13.y);
+  y[base + j + p] = make_float2(d02.x + r13.x, d02.y + r13.y);
+  y[base + j + 2 * p] = make_float2(s02.x - s13.x, s02.y - s13.y);
+  y[base + j + 3 * p] = make_float2(d02.x - r13.x, d02.y - r13.y);
+}
+
+// complex FFT of `batch` rows of length n (power of two); data starts in `a`; returns the
+// buffer holding the result (a or b)
+static float2* fft_c2c(float2* a, float2* b, int batch, int n, float sign, cudaStream_t st,
+                       ms_status* status) {
+  int log2n = 0;
+  while ((1 << log2n) < n) ++log2n;
+  float2* src = a;
+  float2* dst = b;
+  int p = 1;
+  int stages = log2n;
+  const int threads = 256;
+  if (stages & 1) {
+    const size_t total = static_cast<size_t>(batch) * (n >> 1);
+    fft_pass2_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
+        src, dst, n, p, sign, total);
+    *status = after_launch("fft_pass2_kernel");
+    if (*status != MS_OK) return nullptr;
+    p <<= 1;
+    float2* t = src; src = dst; dst = t;
+    --stages;
+  }
+  for (; stages > 0; stages -= 2) {
+    const size_t total = static_cast<size_t>(batch) * (n >> 2);
+    fft_pass4_kernel<<<static_cast<unsigned>((total + threads - 1) / threads), threads, 0, st>>>(
+        src, dst, n, p, sign, total);
+    *status = after_launch("fft_pass4_kernel");
+    if (*status != MS_OK) return nullptr;
+    p <<= 2;
+    float2* t = src; src = dst; dst = t;
+  }
+  return src;
+}
+
+__global__ void real_to_complex_kernel(const float* __restrict__ x, float2* __restrict__ z,
+                                       size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < total) z[i] = make_float2(__ldg(x + i), 0.f);
+}
+
+// Hermitian spectrum of one band: Z[k] = scale * C[k] for lo <= k <= S/2 (imag of k = 0 and
+// k = S/2 dropped, as a c2r transform ignores them), Z[S-k] = conj(Z[k]), 0 elsewhere.
+__global__ void band_spectrum_kernel(const float2* __restrict__ coeffs, float2* __restrict__ z,
+                                     int n, int S, int lo, float scale, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int k = static_cast<int>(gid % S);
+  const size_t b = gid / S;
+  const int kk = k <= S / 2 ? k : S - k;
+  float2 v = make_float2(0.f, 0.f);
+  if (kk >= lo) {
+    v = coeffs[b * n + kk];
+    v.x *= scale;
+    v.y *= (kk == 0 || kk == S / 2) ? 0.f : (k <= S / 2 ? scale : -scale);
+  }
+  z[gid] = v;
+}
+
+__global__ void complex_real_part_kernel(const float2* __restrict__ z, float* __restrict__ y,
+                                         size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < total) y[i] = z[i].x;
+}
+
+// accumulate a band's spectrum (size S transform in `zs`) into the full-size Hermitian
+// spectrum `acc` (length D): bins [lo, S/2] of the band land on the same bin indices.
+__global__ void accumulate_band_kernel(const float2* __restrict__ zs, float2* __restrict__ acc,
+                                       int S, int D, int lo, float scale, int first, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int k = static_cast<int>(gid % (D / 2 + 1));
+  const size_t b = gid / (D / 2 + 1);
+  float2 v = first ? make_float2(0.f, 0.f) : acc[b * (D / 2 + 1) + k];
+  if (k >= lo && k <= S / 2) {
+    const float2 c = zs[b * S + k];
+    v.x += c.x * scale;
+    v.y += c.y * scale;
+  }
+  acc[b * (D / 2 + 1) + k] = v;
+}
+
+// full Hermitian spectrum of length D from its D/2+1 half (imag of DC / Nyquist dropped)
+__global__ void hermitian_expand_kernel(const float2* __restrict__ half, float2* __restrict__ z,
+                                        int D, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int k = static_cast<int>(gid % D);
+  const size_t b = gid / D;
+  const int kk = k <= D / 2 ? k : D - k;
+  float2 v = half[b * (D / 2 + 1) + kk];
+  if (kk == 0 || kk == D / 2) v.y = 0.f;
+  else if (k > D / 2) v.y = -v.y;
+  z[gid] = v;
+}
+
+inline unsigned nblk(size_t total) { return static_cast<unsigned>((total + 255) / 256); }
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+size_t ms_fft_bands_workspace_bytes(int batch, int n) {
+  if (batch <= 0 || n <= 0) return 0;
+  // coefficient buffer + two ping-pong transform buffers (complex, full length)
+  return 3 * static_cast<size_t>(batch) * n * sizeof(float2) + 1024;
+}
+
+ms_status ms_fft_frequency_decompose(const float* x, int batch, int n, int min_size,
+                                     float* const* bands_out, int nbands, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (x == nullptr || bands_out == nullptr || workspace == nullptr || batch <= 0 ||
+      !is_pow2(n) || !is_pow2(min_size) || min_size < 4 || min_size > n)
+    return MS_ERR_INVALID;
+  int expect = 0;
+  for (int s = min_size; s <= n; s <<= 1) ++expect;
+  if (nbands != expect) return MS_ERR_INVALID;
+  if (workspace_bytes < ms_fft_bands_workspace_bytes(batch, n)) return MS_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bn = static_cast<size_t>(batch) * n;
+  float2* coef = static_cast<float2*>(workspace);
+  float2* w0 = coef + bn;
+  float2* w1 = w0 + bn;
+  real_to_complex_kernel<<<nblk(bn), 256, 0, st>>>(x, w0, bn);
+  ms_status s = after_launch("real_to_complex_kernel");
+  if (s != MS_OK) return s;
+  float2* f = fft_c2c(w0, w1, batch, n, -1.f, st, &s);
+  if (f == nullptr) return s;
+  s = check_cuda(cudaMemcpyAsync(coef, f, bn * sizeof(float2), cudaMemcpyDeviceToDevice, st),
+                 "cudaMemcpyAsync(coeffs)");
+  if (s != MS_OK) return s;
+  int bi = 0;
+  for (int S = min_size; S <= n; S <<= 1, ++bi) {
+    const size_t bs = static_cast<size_t>(batch) * S;
+    const int lo = (S > min_size) ? S / 4 : 0;
+    // ortho forward (1/sqrt(n)) and ortho inverse at length S (1/sqrt(S))
+    const float scale = 1.0f / (sqrtf(static_cast<float>(n)) * sqrtf(static_cast<float>(S)));
+    band_spectrum_kernel<<<nblk(bs), 256, 0, st>>>(coef, w0, n, S, lo, scale, bs);
+    s = after_launch("band_spectrum_kernel");
+    if (s != MS_OK) return s;
+    float2* r = fft_c2c(w0, w1, batch, S, +1.f, st, &s);
+    if (r == nullptr) return s;
+    complex_real_part_kernel<<<nblk(bs), 256, 0, st>>>(r, bands_out[bi], bs);
+    s = after_launch("complex_real_part_kernel");
+    if (s != MS_OK) return s;
+  }
+  return MS_OK;
+}
+
+ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes, int nbands,
+                                     int batch, int desired_size, float* out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (bands == nullptr || sizes == nullptr || out == nullptr || workspace == nullptr ||
+      nbands <= 0 || batch <= 0 || !is_pow2(desired_size))
+    return MS_ERR_INVALID;
+  int smin = sizes[0];
+  for (int i = 0; i < nbands; ++i) {
+    if (!is_pow2(sizes[i]) || sizes[i] > desired_size || sizes[i] < 4) return MS_ERR_INVALID;
+    if (sizes[i] < smin) smin = sizes[i];
+  }
+  if (workspace_bytes < ms_fft_bands_workspace_bytes(batch, desired_size)) return MS_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = desired_size;
+  const size_t bd = static_cast<size_t>(batch) * D;
+  float2* acc = static_cast<float2*>(workspace);      // (batch, D/2+1)
+  float2* w0 = acc + bd;
+  float2* w1 = w0 + bd;
+  const size_t bh = static_cast<size_t>(batch) * (D / 2 + 1);
+  ms_status s = MS_OK;
+  for (int i = 0; i < nbands; ++i) {
+    const int S = sizes[i];
+    const size_t bs = static_cast<size_t>(batch) * S;
+    real_to_complex_kernel<<<nblk(bs), 256, 0, st>>>(bands[i], w0, bs);
+    s = after_launch("real_to_complex_kernel");
+    if (s != MS_OK) return s;
+    float2* f = fft_c2c(w0, w1, batch, S, -1.f, st, &s);
+    if (f == nullptr) return s;
+    // fft_resample: the lowest band keeps bins [0, S/2], the others [S/4, S/2]
+    // (n_coeffs // 2 with n_coeffs = S/2 + 1), audio/transform.py:93-96
+    const int lo = (S == smin) ? 0 : (S / 2 + 1) / 2;
+    const float scale = 1.0f / (sqrtf(static_cast<float>(S)) * sqrtf(static_cast<float>(D)));
+    accumulate_band_kernel<<<nblk(bh), 256, 0, st>>>(f, acc, S, D, lo, scale, i == 0 ? 1 : 0, bh);
+    s = after_launch("accumulate_band_kernel");
+    if (s != MS_OK) return s;
+  }
+  hermitian_expand_kernel<<<nblk(bd), 256, 0, st>>>(acc, w0, D, bd);
+  s = after_launch("hermitian_expand_kernel");
+  if (s != MS_OK) return s;
+  float2* r = fft_c2c(w0, w1, batch, D, +1.f, st, &s);
+  if (r == nullptr) return s;
+  complex_real_part_kernel<<<nblk(bd), 256, 0, st>>>(r, out, bd);
+  return after_launch("complex_real_part_kernel");
+}
+
+}  // extern "C"
