@@ -115,6 +115,22 @@ ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int chann
                                  int len, int operand, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Building blocks of the fixed Morlet filter bank (zounds.learn.FilterBank as used at
+ * featuresynth/discriminator/multiscale.py:112 and generator/multiscale.py:91).  Both bank
+ * operations are re-shaped so that their 2*n*k FLOP/sample run on the tcgen05 conv kernel:
+ *   analysis  conv1d(x(B,1,L), bank(n,1,k), padding=k/2):
+ *       ms_expand_mono_to_blk16 (Y[u,i] = x[u+i-shift], 16 channels) then ms_conv_fwd as a
+ *       16 -> n channel conv with k/16 taps of dilation 16;
+ *   synthesis conv_transpose1d(x(B,n,L+1), bank, padding=k/2) -> (B,1,L):
+ *       ms_conv_fwd as an n -> 16 channel conv (8 phase channels used) with k/8 taps of
+ *       dilation 8, then ms_diag_sum (y[t] = sum_i z[t+i+skew, i]).
+ * ------------------------------------------------------------------------- */
+ms_status ms_expand_mono_to_blk16(const float* x, void* y16, int batch, int len, int out_len,
+                                  int shift, int operand, void* stream);
+ms_status ms_diag_sum(const float* z32, float* y, int batch, int channels, int z_len,
+                      int out_len, int nphase, int skew, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Single-output-channel conv + optional tanh, fp32 CUDA-core path.
  *   replaces Conv1d(32,1,7,1,3) + Tanh at generator/full.py:43-44 and the judge
  *   convs (1024->1 k3) at discriminator/full.py:22.

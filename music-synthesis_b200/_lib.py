@@ -40,6 +40,10 @@ SIGNATURES = {
     "ms_unpack_blk32_to_ncl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ms_unpack_blk16_to_ncl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_void_p]),
+    "ms_expand_mono_to_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p]),
+    "ms_diag_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p]),
     "ms_conv_to_mono": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
     "ms_conv1d_out_len": (c_int, [c_int, c_int, c_int, c_int]),

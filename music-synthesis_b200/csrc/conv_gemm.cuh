@@ -7,7 +7,7 @@
 
 namespace msb {
 
-constexpr int kMaxTaps = 8;
+constexpr int kMaxTaps = 16;
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 2560;          // barriers + tmem slot + per-tile bias / index tables
 constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100

@@ -117,6 +117,49 @@ __global__ void conv_to_mono_kernel(const float* __restrict__ x, const float* __
   y[static_cast<size_t>(b) * L + t] = v;
 }
 
+// Filter-bank analysis, step 1: sliding-window expansion of a mono signal into 16 channels,
+//   Y[b, u, i] = x[b, u + i - shift]   (0 outside the clip),  i = 0..15,  BLK 16-bit out.
+// A 1 -> n-channel k-tap convolution then becomes a 16 -> n-channel conv with k/16 taps of
+// dilation 16 -- tensor-core shaped (see ms_filterbank_* in include/msb200.h).
+__global__ void expand_mono_kernel(const float* __restrict__ x, uint4* __restrict__ y, int L,
+                                   int Lx, int shift, int operand, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int u = static_cast<int>(gid % Lx);
+  const size_t bc = gid / Lx;          // b * 2 + chunk
+  const int chunk = static_cast<int>(bc & 1);
+  const size_t b = bc >> 1;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int t = u + chunk * 8 + j - shift;
+    f[j] = (t >= 0 && t < L) ? __ldg(x + b * L + t) : 0.f;
+  }
+  uint4 o;
+  o.x = pack2op(f[0], f[1], operand);
+  o.y = pack2op(f[2], f[3], operand);
+  o.z = pack2op(f[4], f[5], operand);
+  o.w = pack2op(f[6], f[7], operand);
+  y[gid] = o;
+}
+
+// Filter-bank synthesis, last step: y[b, t] = sum_{i < nphase} z[b, t + i + skew, channel i]
+// over a BLK f32 tensor z (B, C/8, Lz, 8) (anti-diagonal sum of the phase channels).
+__global__ void diag_sum_kernel(const float* __restrict__ z, float* __restrict__ y, int C8,
+                                int Lz, int L, int nphase, int skew, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = static_cast<int>(gid % L);
+  const size_t b = gid / L;
+  float acc = 0.f;
+  for (int i = 0; i < nphase; ++i) {
+    const int u = t + i + skew;
+    if (u >= 0 && u < Lz)
+      acc += __ldg(z + ((b * C8 + (i >> 3)) * Lz + u) * 8 + (i & 7));
+  }
+  y[gid] = acc;
+}
+
 ms_status conv_to_mono(const float* x32, const float* w, const float* bias, float* y, int batch,
                        int cin, int len, int ksize, int pad, int tanh_out,
                        cudaStream_t stream) {
@@ -174,6 +217,29 @@ ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int chann
   unpack_blk16_to_ncl_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x16), y, len, operand, total);
   return after_launch("unpack_blk16_to_ncl_kernel");
+}
+
+ms_status ms_expand_mono_to_blk16(const float* x, void* y16, int batch, int len, int out_len,
+                                  int shift, int operand, void* stream) {
+  if (x == nullptr || y16 == nullptr || batch <= 0 || len <= 0 || out_len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * 2 * out_len;
+  expand_mono_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(y16), len,
+                                                            out_len, shift, operand, total);
+  return after_launch("expand_mono_kernel");
+}
+
+ms_status ms_diag_sum(const float* z32, float* y, int batch, int channels, int z_len, int out_len,
+                      int nphase, int skew, void* stream) {
+  if (z32 == nullptr || y == nullptr || batch <= 0 || channels % 8 != 0 || z_len <= 0 ||
+      out_len <= 0 || nphase <= 0 || nphase > channels)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * out_len;
+  diag_sum_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                    static_cast<cudaStream_t>(stream)>>>(z32, y, channels / 8, z_len, out_len,
+                                                         nphase, skew, total);
+  return after_launch("diag_sum_kernel");
 }
 
 ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, float* y,

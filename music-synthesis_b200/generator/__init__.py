@@ -1,1 +1,2 @@
 from .full import MelGanGenerator  # noqa: F401
+from .multiscale import FilterBankChannelGenerator, FilterBankMultiScaleGenerator  # noqa: F401

@@ -131,5 +131,31 @@ def main():
          back=back.numpy())
 
 
+def fb_generator():
+    """FilterBankMultiScaleGenerator, featuresynth/generator/multiscale.py:95-178."""
+    ref_harness.load()
+    import zounds
+    from featuresynth.generator.multiscale import FilterBankMultiScaleGenerator
+    torch.set_grad_enabled(False)
+    for recompose in (False, True):
+        g = FilterBankMultiScaleGenerator(zounds.SR22050(), 128, 8, 2048, recompose=recompose).eval()
+        sd = restate.fb_generator_state(71, 2048)
+        g.load_state_dict(sd)
+        x = synth.mel_features(72, 2, 8)
+        y = g(x)
+        if recompose:
+            save("fb_generator_recomposed_t8", seed=71, y=y.numpy())
+        else:
+            arrays = {"seed": 71, "sizes": np.array(list(y.keys()))}
+            for k, v in y.items():
+                arrays[f"band_{k}"] = v.numpy()
+            for i, (size, cg) in enumerate(g.channel_generators.items()):
+                arrays[f"bank_checksum_{size}"] = float(cg.filter_bank.filter_bank.double().abs().sum())
+            save("fb_generator_t8", **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fb_generator":
+        fb_generator()
+        sys.exit(0)
     main()

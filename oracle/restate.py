@@ -268,6 +268,65 @@ def filterbank_transposed_convolve(x, bank):
     return F.conv_transpose1d(x, bank, padding=k // 2)
 
 
+# ------------------------------------------------ FilterBankMultiScaleGenerator
+# per band (largest first): LearnedUpSample strides, generator/multiscale.py:113-140
+FB_STRIDES = ((4, 4, 4, 4), (4, 4, 4, 2), (4, 4, 2, 2), (4, 2, 2, 2), (2, 2, 2, 2))
+
+
+def fb_band_sizes(output_size):
+    """generator/multiscale.py:110"""
+    import numpy as np
+    return [int(2 ** (np.log2(output_size) - i)) for i in range(5)]
+
+
+def fb_banks(samplerate=22050, kernel_size=128, n_bands=128):
+    """The five fixed Morlet banks of generator/multiscale.py:113-164 (rates sr, sr/2 ... sr/16,
+    each spanning [nyquist/2, nyquist] of its own rate, the lowest [0, nyquist])."""
+    from oracle import bases
+    out = []
+    for i in range(5):
+        sr = bases.SampleRate(samplerate) * (2 ** i)
+        start = 0 if i == 4 else sr.nyquist / 2
+        scale = bases.LinearScale(bases.FrequencyBand(start, sr.nyquist), n_bands)
+        out.append(torch.from_numpy(bases.morlet_filter_bank(sr, kernel_size, scale, 0.05))
+                   .view(n_bands, 1, kernel_size))
+    return out
+
+
+def fb_generator_state(seed, output_size):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    sd = {}
+    for size, strides in zip(fb_band_sizes(output_size), FB_STRIDES):
+        sd[f"channel_{size}.main.0.0.weight"] = torch.from_numpy(
+            (rs.standard_normal((128, 128, 7)) * 0.02).astype(np.float32))
+        sd[f"channel_{size}.main.0.0.bias"] = torch.from_numpy(
+            (rs.standard_normal((128,)) * 0.01).astype(np.float32))
+        for li, s_ in enumerate(strides):
+            sd[f"channel_{size}.main.{li + 1}.conv.weight"] = torch.from_numpy(
+                (rs.standard_normal((128, 128, 2 * s_)) * 0.02).astype(np.float32))
+    return sd
+
+
+def filterbank_multiscale_generator(x, sd, banks, output_size, recompose=False):
+    """generator/multiscale.py:86-92 (channel generator) and 166-178 (multi-scale forward);
+    LearnedUpSample = ConvTranspose1d(k=2s, stride s, padding s//2, bias=False) + leaky,
+    util/modules.py:168-188."""
+    results = {}
+    for size, strides, bank in zip(fb_band_sizes(output_size), FB_STRIDES, banks):
+        h = leaky(F.conv1d(x, sd[f"channel_{size}.main.0.0.weight"],
+                           sd[f"channel_{size}.main.0.0.bias"], padding=3))
+        for li, s_ in enumerate(strides):
+            h = leaky(F.conv_transpose1d(h, sd[f"channel_{size}.main.{li + 1}.conv.weight"],
+                                         stride=s_, padding=s_ // 2))
+        h = F.pad(h, (0, 1))
+        results[size] = filterbank_transposed_convolve(h, bank)
+    if recompose:
+        up = output_size // x.shape[-1]
+        return fft_frequency_recompose(results, x.shape[-1] * up)
+    return results
+
+
 # ---------------------------------------------------------------- FLOP counting
 MELGAN_FLOP_PER_SAMPLE = 409536  # SURVEY.md App. A.1 (2 x MAC, conv/convT only)
 

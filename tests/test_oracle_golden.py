@@ -136,3 +136,18 @@ def test_reference_still_agrees_when_present():
     g.load_state_dict(sd)
     x = synth.mel_features(6, 1, 4)
     assert rel_l2(restate.melgan_generator(x, sd), g(x)) < 2e-6
+
+
+def test_fb_generator_matches_reference(golden):
+    g = golden("fb_generator_t8")
+    sd = restate.fb_generator_state(71, 2048)
+    banks = restate.fb_banks()
+    for size, bank in zip(restate.fb_band_sizes(2048), banks):
+        assert abs(float(bank.double().abs().sum()) - float(g[f"bank_checksum_{size}"])) < 1e-6
+    x = synth.mel_features(72, 2, 8)
+    y = restate.filterbank_multiscale_generator(x, sd, banks, 2048)
+    assert list(y) == list(g["sizes"]) == [2048, 1024, 512, 256, 128]
+    for k, v in y.items():
+        assert rel_l2(v, g[f"band_{k}"]) < 2e-6
+    r = restate.filterbank_multiscale_generator(x, sd, banks, 2048, recompose=True)
+    assert rel_l2(r, golden("fb_generator_recomposed_t8")["y"]) < 2e-6
