@@ -83,6 +83,7 @@ typedef struct {
   int leaky;     /* 1: LeakyReLU(0.2) in the epilogue */
   int operand;   /* MS_F16 | MS_BF16 */
   float alpha;   /* accumulator scale (1.0f normally) */
+  int crop;      /* MS_CONV: output rows dropped at the end (asymmetric padding) */
 } ms_conv_desc;
 
 /* output length for a descriptor (or <0 on invalid) */
@@ -111,6 +112,11 @@ ms_status ms_pack_ncl_to_blk16(const float* x, void* y16, int batch, int channel
                                int len, int pad, int pad_mode, int operand, void* stream);
 ms_status ms_unpack_blk32_to_ncl(const float* x32, float* y, int batch, int channels,
                                  int len, void* stream);
+/* space-to-depth along time: BLK 16-bit (B,C/8,src_rows,8) -> (B, s*C/8, ceil(len/s), 8) with
+ * Y[u, i*C + c] = X[s*u + i, c] for s*u + i < len (0 beyond).  Turns the stride-s k7 convs of
+ * featuresynth/discriminator/multiscale.py:83-88 into stride-1 convs over s*C channels. */
+ms_status ms_space_to_depth_blk16(const void* x16, void* y16, int batch, int channels,
+                                  int src_rows, int len, int stride, void* stream);
 ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int channels,
                                  int len, int operand, void* stream);
 

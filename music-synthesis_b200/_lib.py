@@ -21,7 +21,7 @@ class ConvDesc(Structure):
     _fields_ = [("kind", c_int), ("batch", c_int), ("cin", c_int), ("cout", c_int),
                 ("lin", c_int), ("ksize", c_int), ("dilation", c_int), ("pad", c_int),
                 ("stride", c_int), ("leaky", c_int), ("operand", c_int),
-                ("alpha", c_float)]
+                ("alpha", c_float), ("crop", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/msb200.h declares
@@ -44,6 +44,8 @@ SIGNATURES = {
                                         c_void_p]),
     "ms_diag_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_void_p]),
+    "ms_space_to_depth_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p]),
     "ms_conv_to_mono": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
     "ms_conv1d_out_len": (c_int, [c_int, c_int, c_int, c_int]),

@@ -80,7 +80,7 @@ class FilterBank:
         return self
 
     # -- analysis: conv1d(x, bank, padding=k/2) -> (B, n, L+1) ------------------------------
-    def convolve(self, x):
+    def _analysis(self, x, want16, want32):
         _lib.require_cuda(x, "x")
         L = x.shape[-1]
         x = x.reshape(-1, 1, L).contiguous()
@@ -96,13 +96,15 @@ class FilterBank:
             # W[f, i, j] = bank[f, 16 j + i]
             w = self.filter_bank.to(x.device).reshape(n, taps, 16).permute(0, 2, 1).contiguous()
             self._packed[key] = ops.pack_conv_weight(d, w)
-        _, y32 = ops.conv_fwd(d, x16, self._packed[key], None, want16=False, want32=True)
-        return ops.unpack_blk32(y32)
+        return ops.conv_fwd(d, x16, self._packed[key], None, want16=want16, want32=want32)
 
-    def convolve_blocked(self, x, out_len=None):
+    def convolve(self, x):
+        return ops.unpack_blk32(self._analysis(x, False, True)[1])
+
+    def convolve_blocked(self, x):
         """Same as `convolve` but returns the channel-blocked 16-bit tensor (B, n/8, L+1, 8)
         the next tcgen05 conv consumes directly."""
-        raise NotImplementedError
+        return self._analysis(x, True, False)[0]
 
     # -- synthesis: conv_transpose1d(x(B,n,L+1), bank, padding=k/2) -> (B,1,L) --------------
     def _synth_weights(self, d, device):

@@ -60,7 +60,8 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     c->taps = d.ksize;
     for (int t = 0; t < d.ksize; ++t) c->off[t] = t * d.dilation - d.pad;
     c->Ntot = d.cout;
-    c->Lout = d.lin + 2 * d.pad - d.dilation * (d.ksize - 1);
+    if (d.crop < 0) return false;
+    c->Lout = d.lin + 2 * d.pad - d.dilation * (d.ksize - 1) - d.crop;
     c->Lm = c->Lout;
   } else if (d.kind == MS_CONVT) {
     if (d.stride < 1 || d.ksize != 2 * d.stride) return false;

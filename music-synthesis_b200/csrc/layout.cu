@@ -160,6 +160,22 @@ __global__ void diag_sum_kernel(const float* __restrict__ z, float* __restrict__
   y[gid] = acc;
 }
 
+// space-to-depth along time, 16-byte vectors: Y[b, i*C8 + c, u] = X[b, c, s*u + i]
+__global__ void space_to_depth_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int C8,
+                                      int src_rows, int len, int stride, int lx, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int u = static_cast<int>(gid % lx);
+  size_t r = gid / lx;
+  const int cp = static_cast<int>(r % (stride * C8));
+  const size_t b = r / (stride * C8);
+  const int i = cp / C8, c = cp - i * C8;
+  const int t = stride * u + i;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (t < len) v = __ldg(x + (b * C8 + c) * static_cast<size_t>(src_rows) + t);
+  y[gid] = v;
+}
+
 ms_status conv_to_mono(const float* x32, const float* w, const float* bias, float* y, int batch,
                        int cin, int len, int ksize, int pad, int tanh_out,
                        cudaStream_t stream) {
@@ -217,6 +233,20 @@ ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int chann
   unpack_blk16_to_ncl_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x16), y, len, operand, total);
   return after_launch("unpack_blk16_to_ncl_kernel");
+}
+
+ms_status ms_space_to_depth_blk16(const void* x16, void* y16, int batch, int channels,
+                                  int src_rows, int len, int stride, void* stream) {
+  if (x16 == nullptr || y16 == nullptr || batch <= 0 || channels % 8 != 0 || stride < 1 ||
+      len <= 0 || len > src_rows)
+    return MS_ERR_INVALID;
+  const int lx = (len + stride - 1) / stride;
+  const size_t total = static_cast<size_t>(batch) * stride * (channels / 8) * lx;
+  space_to_depth_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x16), static_cast<uint4*>(y16), channels / 8, src_rows, len,
+      stride, lx, total);
+  return after_launch("space_to_depth_kernel");
 }
 
 ms_status ms_expand_mono_to_blk16(const float* x, void* y16, int batch, int len, int out_len,

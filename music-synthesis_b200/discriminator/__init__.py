@@ -1,2 +1,3 @@
 from .full import FullDiscriminator  # noqa: F401
 from .melgan import MelGanDiscriminator  # noqa: F401
+from .multiscale import FilterBankChannelDiscriminator, FilterBankMultiScaleDiscriminator  # noqa: F401

@@ -1,0 +1,189 @@
+"""Drop-in mirrors of featuresynth/discriminator/multiscale.py:70-252:
+`FilterBankChannelDiscriminator` and `FilterBankMultiScaleDiscriminator`.
+
+Same constructors, state-dict keys (`channel_{size}.main.{0..3}`, `.mj.{0..2}`, `.judge`,
+`final.{0..2}`, `judge`) and forward contract: (x: {size: (B,1,size)} | (B,1,N), feat (B,C,T))
+-> (features: 5 x [7 maps] + [3 maps], judgements: 6 x (B,1,T)).
+
+Everything runs channel-blocked on the tcgen05 kernel: the Morlet analysis bank (sliding-
+window expansion -> 16->128 ch, 8 taps, dilation 16), the stride-s k7 convs as stride-1 convs
+over the space-to-depth input (s*128 channels, 2 or 4 taps), the k3 convs directly; the 1-ch
+judges use the fp32 CUDA-core conv.  Every layer also emits its fp32 feature map, converted
+to the reference's NCL layout because the feature-matching loss consumes them.
+Forward (inference) only in this round.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import MS_CONV, MS_F16, MsbError
+from ..audio.filterbank import FilterBank, linear_center_frequencies
+from ..audio.transform import fft_frequency_decompose
+from ..generator.multiscale import _as_samplerate
+from ..util.modules import _PackedConv
+
+
+class _PackedStrided:
+    """packed weights of a stride-s conv rewritten as a stride-1 conv over space-to-depth"""
+
+    def __init__(self):
+        self.key = None
+        self.val = None
+
+    def get(self, weight, stride, make_desc):
+        key = (weight.data_ptr(), weight._version, stride)
+        if key != self.key:
+            w1, taps, pad = ops.strided_conv_weight(weight.detach(), stride)
+            self.val = (w1, taps, pad, None)
+            self.key = key
+        w1, taps, pad, packed = self.val
+        d = make_desc(taps, pad)
+        if packed is None:
+            packed = ops.pack_conv_weight(d, w1)
+            self.val = (w1, taps, pad, packed)
+        return d, packed
+
+
+def _k3(conv, packed, x16, leaky=True, operand=MS_F16):
+    B, _, L, _ = x16.shape
+    d = ops.conv_desc(MS_CONV, B, conv.in_channels, conv.out_channels, L, 3, 1, 1, leaky=leaky,
+                      operand=operand)
+    return ops.conv_fwd(d, x16, packed.get(d, conv.weight), conv.bias, want16=True, want32=True)
+
+
+class FilterBankChannelDiscriminator(nn.Module):
+    def __init__(self, scale_factors, channels, filter_bank, conditioning_channels=0,
+                 operand=MS_F16):
+        super().__init__()
+        self.conditioning_channels = conditioning_channels
+        self.filter_bank = filter_bank
+        self.channels = channels
+        self.scale_factors = scale_factors
+        self.kernel_size = 7
+        self.operand = operand
+        self.main = nn.Sequential(*[
+            nn.Conv1d(channels[i], channels[i + 1], self.kernel_size, scale_factors[i],
+                      padding=self.kernel_size // 2) for i in range(len(scale_factors))])
+        start = channels[-1] + (conditioning_channels if conditioning_channels > 0 else 0)
+        self.mj = nn.Sequential(
+            nn.Conv1d(start, channels[-1], 3, 1, 1),
+            nn.Conv1d(channels[-1], channels[-1], 3, 1, 1),
+            nn.Conv1d(channels[-1], channels[-1], 3, 1, 1))
+        self.judge = nn.Conv1d(channels[-1], 1, 3, 1, 1)
+        self._pm = [_PackedStrided() for _ in self.main]
+        self._pj = [_PackedConv() for _ in self.mj]
+
+    def forward_blocked(self, x, feat16):
+        """x (B,1,L) f32; feat16 BLK 16-bit conditioning or None.
+        Returns ([7 NCL f32 maps], x16, x32 of the last map, judgement)."""
+        B, _, L = x.shape
+        features = []
+        # analysis bank: (B,128,L+1), sliced to L by reading only L rows below
+        a16 = self.filter_bank.convolve_blocked(x)
+        h16, length = a16, L
+        for conv, pm in zip(self.main, self._pm):
+            s = conv.stride[0]
+            xs = ops.space_to_depth(h16, s, length)
+            lx = xs.shape[2]
+
+            def make(taps, pad, B=B, conv=conv, s=s, lx=lx):
+                # stride-1 conv over s*C channels; drop the one extra row of symmetric padding
+                lout_full = lx + 2 * pad - (taps - 1)
+                return ops.conv_desc(MS_CONV, B, s * conv.in_channels, conv.out_channels, lx, taps,
+                                     1, pad, leaky=True, operand=self.operand,
+                                     crop=lout_full - lx)
+            d, packed = pm.get(conv.weight, s, make)
+            h16, h32 = ops.conv_fwd(d, xs, packed, conv.bias, want16=True, want32=True)
+            features.append(ops.unpack_blk32(h32))
+            length = lx
+        if self.conditioning_channels > 0:
+            h16 = torch.cat([h16, feat16], dim=1)
+        h32 = None
+        for conv, pj in zip(self.mj, self._pj):
+            h16, h32 = _k3(conv, pj, h16, operand=self.operand)
+            features.append(ops.unpack_blk32(h32))
+        j = ops.conv_to_mono(h32, self.judge.weight, self.judge.bias, 3, 1, False)
+        return features, h16, j
+
+    def forward(self, x, feat):
+        _fwd_only(self, x)
+        feat16 = ops.pack_ncl(feat, operand=self.operand) if self.conditioning_channels > 0 else None
+        f, h16, j = self.forward_blocked(x, feat16)
+        return f, f[-1], j
+
+
+def _fwd_only(module, x):
+    probe = x if isinstance(x, torch.Tensor) else next(iter(x.values()))
+    if torch.is_grad_enabled() and (probe.requires_grad or
+                                    any(p.requires_grad for p in module.parameters())):
+        raise MsbError("sm_100a path is forward-only in this build: use torch.no_grad()")
+
+
+class FilterBankMultiScaleDiscriminator(nn.Module):
+    def __init__(self, input_size, samplerate, decompose=True, conditioning_channels=0):
+        super().__init__()
+        self.samplerate = samplerate
+        self.conditioning_channels = conditioning_channels
+        self.decompose = decompose
+        self.input_size = input_size
+        band_sizes = [int(2 ** (np.log2(self.input_size) - i)) for i in range(5)]
+        sr = _as_samplerate(samplerate)
+        strides = ([4, 4, 4, 4], [4, 4, 4, 2], [4, 4, 2, 2], [4, 2, 2, 2], [2, 2, 2, 2])
+        self.spec = {}
+        self.channel_discs = {}
+        for i, (size, sf) in enumerate(zip(band_sizes, strides)):
+            srb = sr * (2 ** i)
+            start = 0 if i == 4 else srb.nyquist / 2
+            self.spec[size] = {
+                "scale_factors": sf, "channels": [128] * 5,
+                "filter_bank": FilterBank(srb, 128,
+                                          linear_center_frequencies(start, srb.nyquist, 128),
+                                          scaling_factors=0.05),
+                "conditioning_channels": conditioning_channels}
+            disc = FilterBankChannelDiscriminator(**self.spec[size])
+            self.add_module(f"channel_{size}", disc)
+            self.channel_discs[size] = disc
+        self.smallest_band = min(self.spec.keys())
+        final_channels = sum(v["channels"][-1] for v in self.spec.values())
+        channels = 512
+        self.final = nn.Sequential(
+            nn.Conv1d(final_channels + self.conditioning_channels, channels, 3, 1, 1),
+            nn.Conv1d(channels, channels, 3, 1, 1),
+            nn.Conv1d(channels, channels, 3, 1, 1))
+        self.judge = nn.Conv1d(channels, 1, 3, 1, 1)
+        self._pf = [_PackedConv() for _ in self.final]
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        probe = fn(torch.zeros(1))
+        for d in self.channel_discs.values():
+            d.filter_bank.to(probe.device)
+        return out
+
+    def forward(self, x, feat):
+        _fwd_only(self, x)
+        bands = fft_frequency_decompose(x, self.smallest_band) if self.decompose else x
+        cond = self.conditioning_channels > 0
+        feat16 = ops.pack_ncl(feat) if cond else None
+        features, channels, judgements = [], [], []
+        for size, layer in self.channel_discs.items():
+            f, h16, j = layer.forward_blocked(bands[size], feat16)
+            features.append(f)
+            channels.append(h16)
+            judgements.append(j)
+        x16 = torch.cat(channels, dim=1)
+        if cond:
+            T = x16.shape[2]
+            if feat.shape[-1] != T:      # F.upsample(feat, size=T): nearest neighbour
+                idx = (torch.arange(T, device=feat.device) * feat.shape[-1]) // T
+                feat16 = ops.pack_ncl(feat[..., idx].contiguous())
+            x16 = torch.cat([x16, feat16], dim=1)
+        final_features = []
+        h32 = None
+        for conv, pf in zip(self.final, self._pf):
+            x16, h32 = _k3(conv, pf, x16)
+            final_features.append(ops.unpack_blk32(h32))
+        features.append(final_features)
+        judgements.append(ops.conv_to_mono(h32, self.judge.weight, self.judge.bias, 3, 1, False))
+        return features, judgements

@@ -15,9 +15,9 @@ OPERANDS = {"f16": MS_F16, "fp16": MS_F16, "bf16": MS_BF16}
 
 
 def conv_desc(kind, batch, cin, cout, lin, ksize, dilation=1, pad=0, stride=1, leaky=False,
-              operand=MS_F16, alpha=1.0):
+              operand=MS_F16, alpha=1.0, crop=0):
     return ConvDesc(kind, batch, cin, cout, lin, ksize, dilation, pad, stride, int(leaky),
-                    operand, alpha)
+                    operand, alpha, crop)
 
 
 def conv_out_len(desc):
@@ -75,6 +75,33 @@ def conv_fwd(desc, x16, w_packed, bias=None, res32=None, want16=True, want32=Fal
     check(_lib.lib().ms_conv_fwd(ctypes.byref(desc), ptr(x16), ptr(w_packed), ptr(bias),
                                  ptr(res32), ptr(y16), ptr(y32), stream_ptr()), "ms_conv_fwd")
     return y16, y32
+
+
+def space_to_depth(x16, stride, length=None):
+    """BLK 16-bit (B,C/8,L,8) -> (B, stride*C/8, ceil(length/stride), 8)."""
+    B, C8, rows, _ = x16.shape
+    length = rows if length is None else length
+    lx = (length + stride - 1) // stride
+    y = torch.empty((B, stride * C8, lx, 8), dtype=torch.int16, device=x16.device)
+    check(_lib.lib().ms_space_to_depth_blk16(ptr(x16), ptr(y), B, C8 * 8, rows, length, stride,
+                                             stream_ptr()), "ms_space_to_depth_blk16")
+    return y
+
+
+def strided_conv_weight(w, stride):
+    """(Cout, C, k) weight of a stride-s conv with padding k//2 -> the equivalent stride-1
+    weight (Cout, s*C, taps) over the space-to-depth input, and (taps, pad)."""
+    cout, c, k = w.shape
+    half = k // 2
+    j_min = -((half + stride - 1) // stride)
+    j_max = half // stride
+    taps = j_max - j_min + 1
+    out = torch.zeros((cout, stride * c, taps), dtype=w.dtype, device=w.device)
+    for kk in range(k):
+        m = kk - half
+        j, i = m // stride, m % stride
+        out[:, i * c:(i + 1) * c, j - j_min] = w[:, :, kk]
+    return out.contiguous(), taps, -j_min
 
 
 def conv_to_mono(x32, w, bias, ksize, pad, tanh_out):

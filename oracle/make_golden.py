@@ -154,7 +154,33 @@ def fb_generator():
             save("fb_generator_t8", **arrays)
 
 
+def fb_discriminator():
+    """FilterBankMultiScaleDiscriminator, featuresynth/discriminator/multiscale.py:130-252."""
+    ref_harness.load()
+    import zounds
+    from featuresynth.discriminator.multiscale import FilterBankMultiScaleDiscriminator
+    torch.set_grad_enabled(False)
+    d = FilterBankMultiScaleDiscriminator(2048, zounds.SR22050(), decompose=False,
+                                          conditioning_channels=128).eval()
+    sd = restate.fb_discriminator_state(81, 2048)
+    d.load_state_dict(sd)
+    bands = {s: synth.randn(82 + i, 2, 1, s) * 0.1 for i, s in enumerate(restate.fb_band_sizes(2048))}
+    feat = synth.mel_features(90, 2, 8)
+    feats, judg = d(bands, feat)
+    arrays = {"seed": 81}
+    for i, j in enumerate(judg):
+        arrays[f"j{i}"] = j.numpy()
+    for g, fl in enumerate(feats):
+        for i, f in enumerate(fl):
+            arrays[f"f{g}_{i}_shape"] = np.array(f.shape)
+            arrays[f"f{g}_{i}_sub"] = f.numpy().reshape(-1)[::13]
+    save("fb_discriminator_n2048", **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fb_discriminator":
+        fb_discriminator()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fb_generator":
         fb_generator()
         sys.exit(0)

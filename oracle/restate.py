@@ -327,6 +327,78 @@ def filterbank_multiscale_generator(x, sd, banks, output_size, recompose=False):
     return results
 
 
+# -------------------------------------------- FilterBankMultiScaleDiscriminator
+# per band (largest first): strides of the four k7 convs, discriminator/multiscale.py:141-175
+FB_DISC_STRIDES = ((4, 4, 4, 4), (4, 4, 4, 2), (4, 4, 2, 2), (4, 2, 2, 2), (2, 2, 2, 2))
+
+
+def fb_discriminator_state(seed, input_size, conditioning_channels=128):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+
+    def w(*shape):
+        return torch.from_numpy((rs.standard_normal(shape) * 0.02).astype(np.float32))
+
+    def b(n):
+        return torch.from_numpy((rs.standard_normal((n,)) * 0.01).astype(np.float32))
+
+    sd = {}
+    for size in fb_band_sizes(input_size):
+        for i in range(4):
+            sd[f"channel_{size}.main.{i}.weight"] = w(128, 128, 7)
+            sd[f"channel_{size}.main.{i}.bias"] = b(128)
+        for i in range(3):
+            cin = 128 + conditioning_channels if i == 0 else 128
+            sd[f"channel_{size}.mj.{i}.weight"] = w(128, cin, 3)
+            sd[f"channel_{size}.mj.{i}.bias"] = b(128)
+        sd[f"channel_{size}.judge.weight"] = w(1, 128, 3)
+        sd[f"channel_{size}.judge.bias"] = b(1)
+    for i in range(3):
+        cin = 5 * 128 + conditioning_channels if i == 0 else 512
+        sd[f"final.{i}.weight"] = w(512, cin, 3)
+        sd[f"final.{i}.bias"] = b(512)
+    sd["judge.weight"] = w(1, 512, 3)
+    sd["judge.bias"] = b(1)
+    return sd
+
+
+def filterbank_multiscale_discriminator(bands, feat, sd, banks, input_size,
+                                        conditioning_channels=128):
+    """discriminator/multiscale.py:109-126 (per-band) and 212-252 (head), decompose=False:
+    `bands` is {size: (B,1,size)}.  Returns (features: 5 x [7] + [3], judgements: 6)."""
+    features, channels, judgements = [], [], []
+    for size, strides, bank in zip(fb_band_sizes(input_size), FB_DISC_STRIDES, banks):
+        x = bands[size]
+        f = []
+        x = filterbank_convolve(x, bank)[:, :, :x.shape[-1]]
+        for i, s_ in enumerate(strides):
+            x = leaky(F.conv1d(x, sd[f"channel_{size}.main.{i}.weight"],
+                               sd[f"channel_{size}.main.{i}.bias"], stride=s_, padding=3))
+            f.append(x)
+        if conditioning_channels > 0:
+            x = torch.cat([x, feat], dim=1)
+        for i in range(3):
+            x = leaky(F.conv1d(x, sd[f"channel_{size}.mj.{i}.weight"],
+                               sd[f"channel_{size}.mj.{i}.bias"], padding=1))
+            f.append(x)
+        j = F.conv1d(x, sd[f"channel_{size}.judge.weight"], sd[f"channel_{size}.judge.bias"],
+                     padding=1)
+        features.append(f)
+        channels.append(x)
+        judgements.append(j)
+    x = torch.cat(channels, dim=1)
+    if conditioning_channels > 0:
+        up = F.interpolate(feat, size=x.shape[-1])      # F.upsample default: nearest
+        x = torch.cat([x, up], dim=1)
+    final = []
+    for i in range(3):
+        x = leaky(F.conv1d(x, sd[f"final.{i}.weight"], sd[f"final.{i}.bias"], padding=1))
+        final.append(x)
+    features.append(final)
+    judgements.append(F.conv1d(x, sd["judge.weight"], sd["judge.bias"], padding=1))
+    return features, judgements
+
+
 # ---------------------------------------------------------------- FLOP counting
 MELGAN_FLOP_PER_SAMPLE = 409536  # SURVEY.md App. A.1 (2 x MAC, conv/convT only)
 

@@ -96,3 +96,58 @@ def test_fb_multiscale_generator_cfg5_size_vs_oracle():
     assert list(y) == list(ref) == [65536, 32768, 16384, 8192, 4096]
     for k in ref:
         assert rel_l2(y[k], ref[k]) < 2e-3
+
+
+def test_space_to_depth_strided_conv_equals_strided_conv():
+    """stride-s k7 conv == stride-1 conv over the space-to-depth input (exact re-indexing)."""
+    from music_synthesis_b200 import ops
+    from torch.nn import functional as F
+    from tests.gpu_util import rnd16, randn
+    for s, L in ((4, 1000), (2, 333), (4, 17)):
+        x, w, b = randn(1, 2, 128, L), randn(2, 128, 128, 7, scale=0.05), randn(3, 128, scale=0.1)
+        ref = F.leaky_relu(F.conv1d(rnd16(x).double(), rnd16(w).double(), b.double(), stride=s, padding=3), 0.2)
+        x16 = ops.pack_ncl(x.cuda())
+        xs = ops.space_to_depth(x16, s)
+        w1, taps, pad = ops.strided_conv_weight(w.cuda(), s)
+        lx = xs.shape[2]
+        d = ops.conv_desc(ops.MS_CONV, 2, s * 128, 128, lx, taps, 1, pad, leaky=True,
+                          crop=lx + 2 * pad - (taps - 1) - lx)
+        _, y32 = ops.conv_fwd(d, xs, ops.pack_conv_weight(d, w1), b.cuda(), want16=False, want32=True)
+        got = ops.unpack_blk32(y32).cpu()
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        assert rel_l2(got, ref) < 2e-5
+
+
+def test_fb_multiscale_discriminator_matches_golden(golden):
+    """SURVEY section 8 row a11 vs the unmodified reference's outputs."""
+    from music_synthesis_b200.discriminator.multiscale import FilterBankMultiScaleDiscriminator
+    g = golden("fb_discriminator_n2048")
+    sd = restate.fb_discriminator_state(81, 2048)
+    d = FilterBankMultiScaleDiscriminator(2048, 22050, decompose=False, conditioning_channels=128).eval()
+    assert list(d.state_dict()) == list(sd)
+    d.load_state_dict(sd)
+    d = d.cuda()
+    bands = {s: (synth.randn(82 + i, 2, 1, s) * 0.1).cuda()
+             for i, s in enumerate(restate.fb_band_sizes(2048))}
+    feat = synth.mel_features(90, 2, 8).cuda()
+    with torch.no_grad():
+        feats, judg = d(bands, feat)
+    assert len(judg) == 6 and [len(f) for f in feats] == [7, 7, 7, 7, 7, 3]
+    for i, j in enumerate(judg):
+        assert j.shape == (2, 1, 8)
+        assert rel_l2(j, g[f"j{i}"]) < 5e-3, i
+    for gi, fl in enumerate(feats):
+        for i, f in enumerate(fl):
+            assert tuple(f.shape) == tuple(g[f"f{gi}_{i}_shape"])
+            assert rel_l2(f.reshape(-1)[::13], g[f"f{gi}_{i}_sub"]) < 3e-3, (gi, i)
+    # decompose=True path: full-band audio in, FFT octave split on the device
+    d2 = FilterBankMultiScaleDiscriminator(2048, 22050, decompose=True, conditioning_channels=128).eval()
+    d2.load_state_dict(sd)
+    d2 = d2.cuda()
+    audio = synth.randn(95, 2, 1, 2048) * 0.1
+    with torch.no_grad():
+        f2, j2 = d2(audio.cuda(), feat)
+    rb = restate.fft_frequency_decompose(audio, 128)
+    rf, rj = restate.filterbank_multiscale_discriminator(rb, feat.cpu(), sd, restate.fb_banks(), 2048)
+    for a, b in zip(j2, rj):
+        assert rel_l2(a, b) < 5e-3

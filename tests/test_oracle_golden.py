@@ -151,3 +151,23 @@ def test_fb_generator_matches_reference(golden):
         assert rel_l2(v, g[f"band_{k}"]) < 2e-6
     r = restate.filterbank_multiscale_generator(x, sd, banks, 2048, recompose=True)
     assert rel_l2(r, golden("fb_generator_recomposed_t8")["y"]) < 2e-6
+
+
+def _fb_disc_inputs():
+    bands = {s: synth.randn(82 + i, 2, 1, s) * 0.1
+             for i, s in enumerate(restate.fb_band_sizes(2048))}
+    return bands, synth.mel_features(90, 2, 8)
+
+
+def test_fb_discriminator_matches_reference(golden):
+    g = golden("fb_discriminator_n2048")
+    sd = restate.fb_discriminator_state(81, 2048)
+    bands, feat = _fb_disc_inputs()
+    feats, judg = restate.filterbank_multiscale_discriminator(bands, feat, sd, restate.fb_banks(), 2048)
+    assert len(judg) == 6 and [len(f) for f in feats] == [7, 7, 7, 7, 7, 3]
+    for i, j in enumerate(judg):
+        assert j.shape == (2, 1, 8) and rel_l2(j, g[f"j{i}"]) < 5e-6
+    for gi, fl in enumerate(feats):
+        for i, f in enumerate(fl):
+            assert tuple(f.shape) == tuple(g[f"f{gi}_{i}_shape"])
+            assert rel_l2(f.reshape(-1)[::13], g[f"f{gi}_{i}_sub"]) < 5e-6
