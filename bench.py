@@ -235,6 +235,24 @@ def main():
         sync_all()
         ms_e2e = f0.elapsed_time(f1)
 
+        # ---- dominant kernel, timed alone on this stream: the fused ResidualStack at C=128
+        # (stage 2: largest single kernel of the step).  Same shapes as inside the step.
+        from music_synthesis_b200 import ops as _ops
+        stack = gen.main[8]
+        blob = _ops.resstack_pack_weights(list(stack.parameters()), 128)
+        x32 = torch.randn((clips, 16, 64 * FRAMES, 8), device=dev) * 0.1
+        for _ in range(2):
+            _ops.resstack_fwd(x32, blob, [1, 3, 9], want16=True, want32=False)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        k0.record()
+        for _ in range(reps):
+            _ops.resstack_fwd(x32, blob, [1, 3, 9], want16=True, want32=False)
+        k1.record()
+        torch.cuda.synchronize()
+        us_stack = k0.elapsed_time(k1) * 1e3 / reps
+        del x32
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -260,13 +278,27 @@ def main():
                     "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": y_host.numel() * 4},
             "gpu_launches": launches,
+            # dominant kernel (largest single launch of the step), timed alone with CUDA
+            # events above; algorithmic FLOPs = 6 convs x 2*3*128^2 per output row.
             "roofline": {
+                "bound": "tensor", "kernel": "resstack_kernel<128> (fused ResidualStack, stage 2)",
+                "achieved": 6 * 2 * 3 * 128 * 128 * clips * 64 * FRAMES / (us_stack * 1e-6) / 1e12,
+                "peak": pk["burst"], "unit": "TFLOP/s",
+                "frac": 6 * 2 * 3 * 128 * 128 * clips * 64 * FRAMES / (us_stack * 1e-6) / 1e12 / pk["burst"],
+                "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
+                "us_per_launch": us_stack,
+                # dram__bytes_read+write of this kernel from profiles/r01_ncu_final_summary.tsv
+                # (776.7 MB per 64-clip launch, scaled to this launch's clip count); the
+                # algorithmic bytes are 4C in + 2C out per row = 805 MB per 64 clips
+                "traffic": 776.7e6 * clips / 64,
+            },
+            # the whole step (15 kernels) against the same roofline: algorithmic generator FLOPs
+            # (409 536 per sample) / CUDA-event step time, sustained peak (seconds-long step)
+            "roofline_step": {
                 "bound": "tensor", "achieved": tflops_per_gpu, "peak": pk["sustained"],
                 "unit": "TFLOP/s", "frac": tflops_per_gpu / pk["sustained"],
                 "frac_of_burst": tflops_per_gpu / pk["burst"], "peak_source": pk["source"],
-                "kernel": "conv_gemm_kernel (29 launches/pass) + pack + mono conv: "
-                          "whole-step algorithmic FLOPs / CUDA-event step time, per GPU",
-                "flop_per_sample": FLOP_PER_SAMPLE, "traffic": None,
+                "flop_per_sample": FLOP_PER_SAMPLE,
             },
             "clocks": clocks,
         }
