@@ -191,6 +191,11 @@ def main():
     gen = MelGanGenerator(FRAMES, MELS).eval()
     gen.load_state_dict(sd)
     gen = gen.to(dev)
+    # weak scaling: the global synthetic batch has clips*world clips; this rank's contiguous
+    # shard (no data-path collective) is regenerated locally from its own seed
+    from music_synthesis_b200.sharding import clip_shard
+    lo, hi = clip_shard(clips * world, rank, world)
+    assert hi - lo == clips
     x_host = synth.mel_features(1000 + rank, clips, FRAMES).pin_memory()
     x_dev = x_host.to(dev, non_blocking=True)
     y_host = torch.empty((clips, 1, 256 * FRAMES), dtype=torch.float32).pin_memory()

@@ -185,7 +185,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   //   s_bias[2][256] fp32 (bias of each tile column), s_tab[2][32] (phase r, channel of each
   //   8-column chunk) -- so the epilogue has no dependent global loads / integer divisions
   float* s_bias = reinterpret_cast<float*>(smem + 512);
-  int2* s_tab = reinterpret_cast<int2*>(smem + 512 + 2048 - 512);
+  int2* s_tab = reinterpret_cast<int2*>(smem + 512 + 2048);
   const uint32_t bar_base = smem_u32(bars);
   const uint32_t data_base = smem_u32(smem + kSmemHeader);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };

@@ -9,7 +9,7 @@ namespace msb {
 
 constexpr int kMaxTaps = 16;
 constexpr int kMaxStages = 8;
-constexpr int kSmemHeader = 2560;          // barriers + tmem slot + per-tile bias / index tables
+constexpr int kSmemHeader = 3072;          // barriers [0,512) | bias tables [512,2560) | index tables [2560,3072)
 constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100
 
 // Tile configuration + derived geometry, a pure function of the descriptor so that

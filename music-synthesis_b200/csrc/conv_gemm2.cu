@@ -42,7 +42,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   // [0..7] full, [8..15] empty, [16..23] peer_full, [24..25] tmem_full, [26..27] tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
   float* s_bias = reinterpret_cast<float*>(smem + 512);             // [2][256]
-  int2* s_tab = reinterpret_cast<int2*>(smem + 512 + 2048 - 512);   // [2][32]
+  int2* s_tab = reinterpret_cast<int2*>(smem + 512 + 2048);   // [2][32]
   const uint32_t bar_base = smem_u32(bars);
   const uint32_t data_base = smem_u32(smem + kSmemHeader);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };

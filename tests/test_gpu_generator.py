@@ -145,3 +145,39 @@ def test_generate_host_pipeline_matches_forward():
     got2 = m.generate(x, chunk_clips=64)          # pageable input, single chunk
     torch.cuda.synchronize()
     assert torch.equal(got2, ref)
+
+
+def test_generator_full_size_config3_properties():
+    """BASELINE config 3 size (256 clips x 256 frames): oracle parity on sampled clips and the
+    size-independent property that a clip's waveform does not depend on its batch-mates."""
+    sd = restate.melgan_generator_state(0)
+    m = _module(sd)
+    x = synth.mel_features(1000, 256, 256)
+    with torch.no_grad():
+        y = m(x.cuda())
+        alone = m(x[[0, 137, 255]].cuda())
+    assert y.shape == (256, 1, 65536)
+    assert torch.isfinite(y).all()
+    assert torch.equal(y[[0, 137, 255]], alone)          # bit-identical per clip
+    ref = restate.melgan_generator(x[[0, 255]], sd)
+    err = rel_l2(y[[0, 255]], ref)
+    print("config-3 sampled clips rel_l2 =", err)
+    assert err < WAVEFORM_TOL
+
+
+@pytest.mark.parametrize("B,T", [(1, 4), (1, 5), (2, 512), (7, 3)])
+def test_generator_edge_shapes(B, T):
+    """shortest legal input (reflection pad 3 needs T >= 4), odd T, the stage-one caller's
+    T = 512 (featureexperiment.py:310-312); T < 4 is rejected like nn.ReflectionPad1d does."""
+    from music_synthesis_b200._lib import MsbError
+    sd = restate.randomize_biases(restate.melgan_generator_state(3), 1003)
+    m = _module(sd)
+    x = synth.mel_features(5, B, T)
+    if T < 4:
+        with pytest.raises(MsbError), torch.no_grad():
+            m(x.cuda())
+        return
+    with torch.no_grad():
+        y = m(x.cuda())
+    assert y.shape == (B, 1, 256 * T)
+    assert rel_l2(y, restate.melgan_generator(x, sd)) < WAVEFORM_TOL

@@ -184,3 +184,30 @@ def test_fused_residual_stack(ops, C, B, L):
     got = ops.unpack_blk32(y32).cpu()
     assert rel_l2(got, ref) < TIGHT
     assert torch.equal(ops.unpack_blk16(y16).cpu(), rnd16(got))
+
+
+@pytest.mark.parametrize("pairs", ["many_tiles"])
+def test_conv_many_tiles_per_cta(ops, pairs):
+    """More tiles than CTAs / clusters: every persistent-loop path (ring wrap, accumulator
+    double-buffering, per-tile epilogue tables) is exercised beyond its first iteration."""
+    for (B, Ci, Co, L, k, dil, pad) in ((24, 256, 256, 4096, 3, 1, 1), (40, 64, 32, 8192, 3, 3, 3)):
+        x = randn(70, B, Ci, L)
+        w = randn(71, Co, Ci, k, scale=0.05)
+        bias = randn(72, Co, scale=0.1)
+        desc = ops.conv_desc(ops.MS_CONV, B, Ci, Co, L, k, dil, pad, leaky=True)
+        ref = F.leaky_relu(F.conv1d(rnd16(x), rnd16(w), bias, dilation=dil, padding=pad), 0.2)
+        _, y32 = ops.conv_fwd(desc, ops.pack_ncl(x.cuda()), ops.pack_conv_weight(desc, w.cuda()),
+                              bias.cuda(), want16=False, want32=True)
+        got = ops.unpack_blk32(y32).cpu()
+        per_clip = (got - ref).double().norm(dim=(1, 2)) / ref.double().norm(dim=(1, 2))
+        assert per_clip.max().item() < 1e-5, per_clip.tolist()
+    # transposed conv, 8 phases, > 74 cluster tiles
+    B, Ci, Co, L = 6, 256, 128, 2048
+    x, w, bias = randn(73, B, Ci, L), randn(74, Ci, Co, 16, scale=0.05), randn(75, Co, scale=0.1)
+    desc = ops.conv_desc(ops.MS_CONVT, B, Ci, Co, L, 16, 1, 4, 8, leaky=True)
+    ref = F.leaky_relu(F.conv_transpose1d(rnd16(x), rnd16(w), bias, stride=8, padding=4), 0.2)
+    _, y32 = ops.conv_fwd(desc, ops.pack_ncl(x.cuda()), ops.pack_conv_weight(desc, w.cuda()),
+                          bias.cuda(), want16=False, want32=True)
+    got = ops.unpack_blk32(y32).cpu()
+    per_clip = (got - ref).double().norm(dim=(1, 2)) / ref.double().norm(dim=(1, 2))
+    assert per_clip.max().item() < 1e-5, per_clip.tolist()
