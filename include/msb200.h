@@ -239,12 +239,14 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
  * real FFT, magnitude, mel projection, log10(clamp(.,1e-5)) -- one fused kernel.
  *   replaces Audio2Mel.forward, featuresynth/feature/feature.py:39-59.
  *   audio: (B,1,N) f32; window: (1024) f32; mel_basis: (n_mels,513) f32;
+ *   row_ranges: optional device int[n_mels][2] = [first, last+1) non-zero bin of each mel row
+ *   (the Slaney filters are banded; NULL = treat the basis as dense -- same result);
  *   out: (B,n_mels,F) f32 with F = (N + 384 - 1024)/hop + 1.
  * ------------------------------------------------------------------------- */
 int ms_audio2mel_frames(int samples, int n_fft, int hop);
 ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float* mel_basis,
-                           float* out, int batch, int samples, int n_fft, int hop,
-                           int n_mels, void* stream);
+                           const int* row_ranges, float* out, int batch, int samples, int n_fft,
+                           int hop, int n_mels, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,8 +74,8 @@ SIGNATURES = {
     "ms_melgan_generator_fwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
                                         c_int, c_void_p, c_size_t, c_void_p]),
     "ms_audio2mel_frames": (c_int, [c_int, c_int, c_int]),
-    "ms_audio2mel_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                 c_int, c_int, c_void_p]),
+    "ms_audio2mel_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -22,18 +22,25 @@ struct A2MParams {
   const float* window;  // (n_fft)
   const float* basis;   // (n_mels, bins)
   float* out;           // (B, n_mels, F)
+  const int2* ranges;   // per mel row [first, last+1) non-zero bin, or null (dense basis)
   int N, n_fft, log2n, hop, n_mels, bins, F, groups;
 };
 
+// LOG2N > 0: compile-time FFT size (index arithmetic becomes shifts / masks); 0: runtime size
+template <int LOG2N>
 __global__ void __launch_bounds__(kA2MThreads)
 audio2mel_kernel(const A2MParams p) {
   extern __shared__ float sm[];
-  const int n = p.n_fft;
+  const int n = LOG2N > 0 ? (1 << LOG2N) : p.n_fft;
+  const int log2n = LOG2N > 0 ? LOG2N : p.log2n;
   const int bins = p.bins;
   const int magld = bins + 3;           // row stride of the magnitude array
-  float* tw_c = sm;                     // [n/2]
-  float* tw_s = tw_c + n / 2;           // [n/2]
-  float* mag = tw_s + n / 2;            // [8][magld]
+  // per-stage CONTIGUOUS twiddle tables: stage with butterfly span `half` uses entries
+  // [half-1, 2*half-1) = exp(-2*pi*i*pos/(2*half)) -- conflict-free (a single strided table
+  // would be read with a power-of-two stride: up to 32-way bank conflicts)
+  float* tw_c = sm;                     // [n]
+  float* tw_s = tw_c + n;               // [n]
+  float* mag = tw_s + n;                // [8][magld]
   float* zr = mag + kFramesPerCta * magld;   // [4][n]   (re)  -- reused as basis tile
   float* zi = zr + 4 * n;                    // [4][n]   (im)
   float* tile = zr;                          // [128][33]
@@ -43,9 +50,11 @@ audio2mel_kernel(const A2MParams p) {
   const int f0 = (blockIdx.x % p.groups) * kFramesPerCta;
   const float* a = p.audio + static_cast<size_t>(b) * p.N;
 
-  for (int i = tid; i < n / 2; i += kA2MThreads) {
+  for (int i = tid; i < n - 1; i += kA2MThreads) {
+    const int half = 1 << (31 - __clz(i + 1));      // largest power of two <= i+1
+    const int pos = i + 1 - half;
     float s, c;
-    sincospif(-2.0f * static_cast<float>(i) / static_cast<float>(n), &s, &c);
+    sincospif(-static_cast<float>(pos) / static_cast<float>(half), &s, &c);
     tw_c[i] = c;
     tw_s[i] = s;
   }
@@ -53,7 +62,7 @@ audio2mel_kernel(const A2MParams p) {
   for (int i = tid; i < 4 * n; i += kA2MThreads) {
     const int j = i / n;
     const int t = i - j * n;
-    const int rev = static_cast<int>(__brev(static_cast<unsigned>(t)) >> (32 - p.log2n));
+    const int rev = static_cast<int>(__brev(static_cast<unsigned>(t)) >> (32 - log2n));
     const float w = __ldg(p.window + t);
     const int fa = f0 + 2 * j, fb = fa + 1;
     const long long sa = static_cast<long long>(fa) * p.hop + t;
@@ -65,16 +74,17 @@ audio2mel_kernel(const A2MParams p) {
   }
   __syncthreads();
   // 4 in-place radix-2 DIT FFTs side by side
-  for (int s = 0; s < p.log2n; ++s) {
+  for (int s = 0; s < log2n; ++s) {
     const int half = 1 << s;
-    const int tws = n >> (s + 1);
+    const float* twc = tw_c + half - 1;
+    const float* tws_ = tw_s + half - 1;
     for (int i = tid; i < 2 * n; i += kA2MThreads) {   // 4 * n/2 butterflies
       const int j = i / (n / 2);
       const int bf = i - j * (n / 2);
       const int pos = bf & (half - 1);
       const int i0 = ((bf >> s) << (s + 1)) + pos + j * n;
       const int i1 = i0 + half;
-      const float c = tw_c[pos * tws], sn = tw_s[pos * tws];
+      const float c = twc[pos], sn = tws_[pos];
       const float xr = zr[i1], xi = zi[i1];
       const float tr = xr * c - xi * sn;
       const float ti = xr * sn + xi * c;
@@ -100,6 +110,32 @@ audio2mel_kernel(const A2MParams p) {
   // mel projection: thread (m, gh) accumulates frames gh*4 .. gh*4+3 of mel row m
   const int ml = tid & 127;
   const int gh = tid >> 7;
+  if (p.ranges != nullptr) {
+    // banded basis (triangular mel filters): walk only the row's non-zero bins, in the same
+    // ascending order as the dense product -> bit-identical sums
+    for (int mb = 0; mb < p.n_mels; mb += 128) {
+      const int m = mb + ml;
+      if (m >= p.n_mels) continue;
+      const int2 r = __ldg(p.ranges + m);
+      const float* brow = p.basis + static_cast<size_t>(m) * bins;
+      const float* mg = mag + (gh * 4) * magld;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = r.x; k < r.y; ++k) {
+        const float w = __ldg(brow + k);
+        acc[0] = fmaf(w, mg[k], acc[0]);
+        acc[1] = fmaf(w, mg[magld + k], acc[1]);
+        acc[2] = fmaf(w, mg[2 * magld + k], acc[2]);
+        acc[3] = fmaf(w, mg[3 * magld + k], acc[3]);
+      }
+      float* o = p.out + (static_cast<size_t>(b) * p.n_mels + m) * p.F;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int f = f0 + gh * 4 + g;
+        if (f < p.F) o[f] = log10f(fmaxf(acc[g], 1e-5f));
+      }
+    }
+    return;
+  }
   for (int mb = 0; mb < p.n_mels; mb += 128) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = 0; k0 < bins; k0 += 32) {
@@ -148,8 +184,8 @@ int ms_audio2mel_frames(int samples, int n_fft, int hop) {
 }
 
 ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float* mel_basis,
-                           float* out, int batch, int samples, int n_fft, int hop, int n_mels,
-                           void* stream) {
+                           const int* row_ranges, float* out, int batch, int samples, int n_fft,
+                           int hop, int n_mels, void* stream) {
   if (audio == nullptr || window == nullptr || mel_basis == nullptr || out == nullptr ||
       batch <= 0 || n_mels <= 0)
     return MS_ERR_INVALID;
@@ -161,24 +197,32 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
   if (F == 0) return MS_OK;
   A2MParams p;
   p.audio = audio; p.window = window; p.basis = mel_basis; p.out = out;
+  p.ranges = reinterpret_cast<const int2*>(row_ranges);
   p.N = samples; p.n_fft = n_fft; p.log2n = log2n; p.hop = hop; p.n_mels = n_mels;
   p.bins = n_fft / 2 + 1; p.F = F; p.groups = (F + kFramesPerCta - 1) / kFramesPerCta;
   const size_t fft_floats = 8 * static_cast<size_t>(n_fft);
   const size_t tile_floats = 128 * 33;
-  const size_t smem = sizeof(float) * (n_fft + kFramesPerCta * (p.bins + 3) +
+  const size_t smem = sizeof(float) * (2 * n_fft + kFramesPerCta * (p.bins + 3) +
                                        (fft_floats > tile_floats ? fft_floats : tile_floats));
   static thread_local size_t attr_set = 0;
   if (smem > attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(audio2mel_kernel,
+    cudaError_t e = cudaFuncSetAttribute(audio2mel_kernel<10>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(audio2mel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(audio2mel_kernel)");
     attr_set = smem;
   }
   const long long blocks = static_cast<long long>(batch) * p.groups;
   if (blocks > 0x7fffffffLL) return MS_ERR_INVALID;
-  audio2mel_kernel<<<static_cast<unsigned>(blocks), kA2MThreads, smem,
-                     static_cast<cudaStream_t>(stream)>>>(p);
+  if (n_fft == 1024)
+    audio2mel_kernel<10><<<static_cast<unsigned>(blocks), kA2MThreads, smem,
+                           static_cast<cudaStream_t>(stream)>>>(p);
+  else
+    audio2mel_kernel<0><<<static_cast<unsigned>(blocks), kA2MThreads, smem,
+                          static_cast<cudaStream_t>(stream)>>>(p);
   return after_launch("audio2mel_kernel");
 }
 

@@ -30,11 +30,15 @@ class Audio2Mel(nn.Module):
         self.win_length = win_length
         self.sampling_rate = sampling_rate
         self.n_mel_channels = n_mel_channels
+        self._ranges = None          # (key, device tensor): banded structure of mel_basis
 
     def forward(self, audio):
         if isinstance(audio, np.ndarray):
             audio = torch.from_numpy(audio).view(1, 1, -1).to(self.window.device)
         if audio.dim() != 3 or audio.shape[1] != 1:
             raise MsbError("Audio2Mel expects (B, 1, N) audio")
+        key = (self.mel_basis.data_ptr(), self.mel_basis._version)
+        if self._ranges is None or self._ranges[0] != key:
+            self._ranges = (key, ops.mel_row_ranges(self.mel_basis).to(self.mel_basis.device))
         return ops.audio2mel(audio.float(), self.window, self.mel_basis, self.n_fft,
-                             self.hop_length)
+                             self.hop_length, self._ranges[1])

@@ -113,7 +113,17 @@ def conv_to_mono(x32, w, bias, ksize, pad, tanh_out):
     return y
 
 
-def audio2mel(audio, window, mel_basis, n_fft, hop):
+def mel_row_ranges(mel_basis):
+    """int32 (n_mels, 2): [first, last+1) non-zero column of each basis row (host-side scan)."""
+    nz = (mel_basis != 0).cpu()
+    n_mels, bins = nz.shape
+    any_ = nz.any(dim=1)
+    first = torch.where(any_, nz.float().argmax(dim=1), torch.zeros(n_mels, dtype=torch.long))
+    last = torch.where(any_, bins - nz.flip(1).float().argmax(dim=1), torch.zeros(n_mels, dtype=torch.long))
+    return torch.stack([first, last], dim=1).to(torch.int32).contiguous()
+
+
+def audio2mel(audio, window, mel_basis, n_fft, hop, row_ranges=None):
     _lib.require_cuda(audio, "audio")
     audio = audio.contiguous()
     B, _, N = audio.shape
@@ -123,8 +133,8 @@ def audio2mel(audio, window, mel_basis, n_fft, hop):
         raise _lib.MsbError("invalid Audio2Mel geometry")
     out = torch.empty((B, n_mels, F), dtype=torch.float32, device=audio.device)
     check(_lib.lib().ms_audio2mel_fwd(ptr(audio), ptr(window.contiguous()),
-                                      ptr(mel_basis.contiguous()), ptr(out), B, N, n_fft, hop,
-                                      n_mels, stream_ptr()), "ms_audio2mel_fwd")
+                                      ptr(mel_basis.contiguous()), ptr(row_ranges), ptr(out), B, N,
+                                      n_fft, hop, n_mels, stream_ptr()), "ms_audio2mel_fwd")
     return out
 
 

@@ -181,3 +181,17 @@ def test_generator_edge_shapes(B, T):
         y = m(x.cuda())
     assert y.shape == (B, 1, 256 * T)
     assert rel_l2(y, restate.melgan_generator(x, sd)) < WAVEFORM_TOL
+
+
+def test_audio2mel_banded_projection_is_bit_identical_to_dense():
+    from music_synthesis_b200 import ops
+    from music_synthesis_b200.feature.feature import Audio2Mel
+    a2m = Audio2Mel(1024, 256, 1024, 22050, 128).cuda()
+    a = synth.uniform_audio(8, 5, 12000).cuda()
+    banded = a2m(a)
+    dense = ops.audio2mel(a, a2m.window, a2m.mel_basis, 1024, 256, None)
+    assert torch.equal(banded, dense)
+    # a basis with arbitrary (non-banded) rows still works through the ranges path
+    a2m.mel_basis[3, 500] = 0.01
+    a2m.mel_basis[3, 2] = 0.02
+    assert torch.equal(a2m(a), ops.audio2mel(a, a2m.window, a2m.mel_basis, 1024, 256, None))
