@@ -117,6 +117,15 @@ ms_status ms_unpack_blk32_to_ncl(const float* x32, float* y, int batch, int chan
  * featuresynth/discriminator/multiscale.py:83-88 into stride-1 convs over s*C channels. */
 ms_status ms_space_to_depth_blk16(const void* x16, void* y16, int batch, int channels,
                                   int src_rows, int len, int stride, void* stream);
+/* y[t'] = act(x[map(t'-pad)]) on a channel-blocked tensor (elem_bits 16 or 32): zero / reflection
+ * padding (+ LeakyReLU 0.2) -- the pre-activation + ReflectionPad1d in front of the convs of the
+ * official MelGAN blocks (experiment/realmelgan.py:35-37,80-81). */
+ms_status ms_blk_act_pad(const void* x, void* y, int elem_bits, int batch, int channels, int len,
+                         int pad, int pad_mode, int leaky, int operand, void* stream);
+/* weight-norm fold out[r,:] = g[r] * v[r,:] / ||v[r,:]|| (torch weight_norm, dim=0;
+ * experiment/realmelgan.py:24-29). */
+ms_status ms_weight_norm_fold(const float* v, const float* g, float* out, int rows, int cols,
+                              void* stream);
 ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int channels,
                                  int len, int operand, void* stream);
 
@@ -155,11 +164,15 @@ ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, f
  *   w: (cout, cin/groups, k) reference layout.  Lout = (lin + 2*pad - k)/stride + 1.
  * ------------------------------------------------------------------------- */
 int ms_conv1d_out_len(int lin, int ksize, int stride, int pad);
+/* pad_mode: 0 zero padding, 1 reflection (nn.ReflectionPad1d(7) in front of the first conv of
+ * NLayerDiscriminator, experiment/realmelgan.py:98-102).  count_include_pad: 1 = F.avg_pool1d
+ * default (discriminator/melgan.py:22), 0 = nn.AvgPool1d(4,2,1,count_include_pad=False)
+ * (experiment/realmelgan.py:166-167). */
 ms_status ms_conv1d_direct_fwd(const float* x, const float* w, const float* bias, float* y,
                                int batch, int cin, int cout, int lin, int ksize, int stride,
-                               int pad, int groups, int leaky, void* stream);
+                               int pad, int groups, int leaky, int pad_mode, void* stream);
 ms_status ms_avg_pool1d_fwd(const float* x, float* y, int batch_channels, int lin, int ksize,
-                            int stride, int pad, void* stream);
+                            int stride, int pad, int count_include_pad, void* stream);
 
 /* ---------------------------------------------------------------------------
  * Fused ResidualStack: 3 ResidualAtoms = 6 k3 convolutions (dilations d0,1,d1,1,d2,1)

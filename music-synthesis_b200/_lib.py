@@ -50,9 +50,12 @@ SIGNATURES = {
                                 c_int, c_int, c_int, c_void_p]),
     "ms_conv1d_out_len": (c_int, [c_int, c_int, c_int, c_int]),
     "ms_conv1d_direct_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "ms_avg_pool1d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ms_avg_pool1d_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p]),
+    "ms_blk_act_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_void_p]),
+    "ms_weight_norm_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ms_resstack_supported": (c_int, [c_int]),
     "ms_resstack_packed_weight_bytes": (c_size_t, [c_int]),
     "ms_resstack_pack_weights": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),

@@ -18,7 +18,7 @@ struct DirectConvParams {
   const float* w;      // (cout, cin/groups, k)
   const float* bias;   // (cout) or null
   float* y;            // (B, cout, lout)
-  int B, cin, cout, lin, lout, k, stride, pad, groups, leaky;
+  int B, cin, cout, lin, lout, k, stride, pad, groups, leaky, pad_mode;
 };
 
 __global__ void __launch_bounds__(kDcTile)
@@ -31,7 +31,11 @@ direct_conv_kernel(const DirectConvParams p) {
   const int in0 = t0 * p.stride - p.pad;
   for (int i = threadIdx.x; i < cin_g * win; i += kDcTile) {
     const int c = i / win, j = i - c * win;
-    const int ti = in0 + j;
+    int ti = in0 + j;
+    if (p.pad_mode == 1) {            // reflection padding (nn.ReflectionPad1d)
+      if (ti < 0) ti = -ti;
+      else if (ti >= p.lin) ti = 2 * (p.lin - 1) - ti;
+    }
     sx[i] = (ti >= 0 && ti < p.lin)
                 ? __ldg(p.x + (static_cast<size_t>(b) * p.cin + g * cin_g + c) * p.lin + ti)
                 : 0.f;
@@ -63,18 +67,20 @@ direct_conv_kernel(const DirectConvParams p) {
 // y[b,c,t] = (1/k) * sum_j x[b,c,t*stride - pad + j]   (zero padding counted: the
 // reference's count_include_pad=True default)
 __global__ void avg_pool_kernel(const float* __restrict__ x, float* __restrict__ y, int lin,
-                                int lout, int k, int stride, int pad, size_t total) {
+                                int lout, int k, int stride, int pad, int include_pad,
+                                size_t total) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   const int t = static_cast<int>(i % lout);
   const size_t bc = i / lout;
   const float* xr = x + bc * lin;
   float acc = 0.f;
+  int cnt = 0;
   for (int j = 0; j < k; ++j) {
     const int ti = t * stride - pad + j;
-    if (ti >= 0 && ti < lin) acc += __ldg(xr + ti);
+    if (ti >= 0 && ti < lin) { acc += __ldg(xr + ti); ++cnt; }
   }
-  y[i] = acc / static_cast<float>(k);
+  y[i] = acc / static_cast<float>(include_pad ? k : (cnt > 0 ? cnt : 1));
 }
 
 }  // namespace msb
@@ -91,14 +97,16 @@ int ms_conv1d_out_len(int lin, int ksize, int stride, int pad) {
 
 ms_status ms_conv1d_direct_fwd(const float* x, const float* w, const float* bias, float* y,
                                int batch, int cin, int cout, int lin, int ksize, int stride,
-                               int pad, int groups, int leaky, void* stream) {
+                               int pad, int groups, int leaky, int pad_mode, void* stream) {
   if (x == nullptr || w == nullptr || y == nullptr || batch <= 0 || cin <= 0 || cout <= 0 ||
       groups <= 0 || cin % groups != 0 || cout % groups != 0)
     return MS_ERR_INVALID;
   const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
   if (lout < 0) return MS_ERR_INVALID;
   if (lout == 0) return MS_OK;
-  DirectConvParams p{x, w, bias, y, batch, cin, cout, lin, lout, ksize, stride, pad, groups, leaky};
+  if (pad_mode == 1 && pad >= lin) return MS_ERR_INVALID;
+  DirectConvParams p{x, w, bias, y, batch, cin, cout, lin, lout, ksize, stride, pad, groups, leaky,
+                     pad_mode};
   const int cin_g = cin / groups;
   const size_t smem = sizeof(float) * cin_g * ((kDcTile - 1) * stride + ksize);
   if (smem > 200 * 1024 || groups > 65535 || batch > 65535) return MS_ERR_INVALID;
@@ -118,15 +126,15 @@ ms_status ms_conv1d_direct_fwd(const float* x, const float* w, const float* bias
 }
 
 ms_status ms_avg_pool1d_fwd(const float* x, float* y, int batch_channels, int lin, int ksize,
-                            int stride, int pad, void* stream) {
+                            int stride, int pad, int count_include_pad, void* stream) {
   if (x == nullptr || y == nullptr || batch_channels <= 0) return MS_ERR_INVALID;
   const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
   if (lout < 0) return MS_ERR_INVALID;
   if (lout == 0) return MS_OK;
   const size_t total = static_cast<size_t>(batch_channels) * lout;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  avg_pool_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, lin, lout, ksize,
-                                                                          stride, pad, total);
+  avg_pool_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, y, lin, lout, ksize, stride, pad, count_include_pad, total);
   return after_launch("avg_pool_kernel");
 }
 

@@ -160,6 +160,72 @@ __global__ void diag_sum_kernel(const float* __restrict__ z, float* __restrict__
   y[gid] = acc;
 }
 
+// y[b, c, t'] = act(x[b, c, map(t' - pad)]) on channel-blocked tensors: zero (mode 0) or
+// reflection (mode 1) padding with an optional LeakyReLU(0.2) -- the pre-activation +
+// ReflectionPad1d that precede the convs of the official MelGAN blocks
+// (experiment/realmelgan.py:35-37, 80-81).  ELEM = 16 (16-bit operand) or 32 (fp32 stream).
+template <int ELEM>
+__global__ void act_pad_kernel(const void* __restrict__ xin, void* __restrict__ yout, int L, int pad,
+                               int mode, int leaky, int operand, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int Lp = L + 2 * pad;
+  const int tp = static_cast<int>(gid % Lp);
+  const size_t bc = gid / Lp;
+  int t = tp - pad;
+  bool zero = false;
+  if (t < 0) { if (mode == 1) t = -t; else zero = true; }
+  else if (t >= L) { if (mode == 1) t = 2 * (L - 1) - t; else zero = true; }
+  float f[8];
+  if (zero) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  } else if (ELEM == 32) {
+    ld_global_nc_v8(static_cast<const float*>(xin) + (bc * L + t) * 8, f);
+  } else {
+    const uint4 v = __ldg(static_cast<const uint4*>(xin) + bc * L + t);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 q;
+      if (operand == MS_BF16) q = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      else q = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      f[2 * j] = q.x; f[2 * j + 1] = q.y;
+    }
+  }
+  if (leaky) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
+  }
+  if (ELEM == 32) {
+    st_global_v8(static_cast<float*>(yout) + gid * 8, f);
+  } else {
+    uint4 o;
+    o.x = pack2op(f[0], f[1], operand); o.y = pack2op(f[2], f[3], operand);
+    o.z = pack2op(f[4], f[5], operand); o.w = pack2op(f[6], f[7], operand);
+    static_cast<uint4*>(yout)[gid] = o;
+  }
+}
+
+// weight normalisation fold: out[r, :] = g[r] * v[r, :] / ||v[r, :]||_2 (norm over all dims but 0,
+// torch.nn.utils.weight_norm with dim=0); one block per row
+__global__ void weight_norm_fold_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                        float* __restrict__ out, int cols) {
+  __shared__ float sh[256];
+  const float* vr = v + static_cast<size_t>(blockIdx.x) * cols;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) acc += vr[i] * vr[i];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float scale = g[blockIdx.x] / sqrtf(sh[0]);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x)
+    out[static_cast<size_t>(blockIdx.x) * cols + i] = vr[i] * scale;
+}
+
 // space-to-depth along time, 16-byte vectors: Y[b, i*C8 + c, u] = X[b, c, s*u + i]
 __global__ void space_to_depth_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int C8,
                                       int src_rows, int len, int stride, int lx, size_t total) {
@@ -233,6 +299,28 @@ ms_status ms_unpack_blk16_to_ncl(const void* x16, float* y, int batch, int chann
   unpack_blk16_to_ncl_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x16), y, len, operand, total);
   return after_launch("unpack_blk16_to_ncl_kernel");
+}
+
+ms_status ms_blk_act_pad(const void* x, void* y, int elem_bits, int batch, int channels, int len,
+                         int pad, int pad_mode, int leaky, int operand, void* stream) {
+  if (x == nullptr || y == nullptr || batch <= 0 || channels % 8 != 0 || len <= 0 || pad < 0 ||
+      (elem_bits != 16 && elem_bits != 32) || (pad_mode == 1 && pad >= len))
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * (len + 2 * pad);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (elem_bits == 16)
+    act_pad_kernel<16><<<blocks, 256, 0, st>>>(x, y, len, pad, pad_mode, leaky, operand, total);
+  else
+    act_pad_kernel<32><<<blocks, 256, 0, st>>>(x, y, len, pad, pad_mode, leaky, operand, total);
+  return after_launch("act_pad_kernel");
+}
+
+ms_status ms_weight_norm_fold(const float* v, const float* g, float* out, int rows, int cols,
+                              void* stream) {
+  if (v == nullptr || g == nullptr || out == nullptr || rows <= 0 || cols <= 0) return MS_ERR_INVALID;
+  weight_norm_fold_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, out, cols);
+  return after_launch("weight_norm_fold_kernel");
 }
 
 ms_status ms_space_to_depth_blk16(const void* x16, void* y16, int batch, int channels,

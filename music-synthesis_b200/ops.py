@@ -138,7 +138,29 @@ def audio2mel(audio, window, mel_basis, n_fft, hop, row_ranges=None):
     return out
 
 
-def conv1d_direct(x, w, bias, stride=1, pad=0, groups=1, leaky=False):
+def act_pad(x, pad=0, pad_mode=0, leaky=False, operand=MS_F16):
+    """Channel-blocked tensor (int16 = 16-bit operand, float32 = fp32 stream) ->
+    act(pad(x)): zero (0) / reflection (1) padding and optional LeakyReLU(0.2)."""
+    B, C8, L, _ = x.shape
+    bits = 32 if x.dtype == torch.float32 else 16
+    y = torch.empty((B, C8, L + 2 * pad, 8), dtype=x.dtype, device=x.device)
+    check(_lib.lib().ms_blk_act_pad(ptr(x), ptr(y), bits, B, C8 * 8, L, pad, pad_mode, int(leaky),
+                                    operand, stream_ptr()), "ms_blk_act_pad")
+    return y
+
+
+def weight_norm_fold(v, g):
+    """weight_g * weight_v / ||weight_v|| (norm over all dims but 0), on the device."""
+    _lib.require_cuda(v, "weight_v")
+    v = v.contiguous()
+    rows = v.shape[0]
+    out = torch.empty_like(v)
+    check(_lib.lib().ms_weight_norm_fold(ptr(v), ptr(g.contiguous()), ptr(out), rows,
+                                         v.numel() // rows, stream_ptr()), "ms_weight_norm_fold")
+    return out
+
+
+def conv1d_direct(x, w, bias, stride=1, pad=0, groups=1, leaky=False, pad_mode=0):
     """fp32 CUDA-core conv1d (grouped / strided), NCL in -> NCL out."""
     _lib.require_cuda(x, "x")
     x = x.contiguous()
@@ -151,19 +173,19 @@ def conv1d_direct(x, w, bias, stride=1, pad=0, groups=1, leaky=False):
         raise _lib.MsbError("conv1d_direct: invalid geometry")
     y = torch.empty((B, cout, lout), dtype=torch.float32, device=x.device)
     check(_lib.lib().ms_conv1d_direct_fwd(ptr(x), ptr(w.contiguous()), ptr(bias), ptr(y), B, cin,
-                                          cout, lin, k, stride, pad, groups, int(leaky),
+                                          cout, lin, k, stride, pad, groups, int(leaky), pad_mode,
                                           stream_ptr()), "ms_conv1d_direct_fwd")
     return y
 
 
-def avg_pool1d(x, ksize, stride, pad):
+def avg_pool1d(x, ksize, stride, pad, count_include_pad=True):
     _lib.require_cuda(x, "x")
     x = x.contiguous()
     B, C, lin = x.shape
     lout = _lib.lib().ms_conv1d_out_len(lin, ksize, stride, pad)
     y = torch.empty((B, C, lout), dtype=torch.float32, device=x.device)
     check(_lib.lib().ms_avg_pool1d_fwd(ptr(x), ptr(y), B * C, lin, ksize, stride, pad,
-                                       stream_ptr()), "ms_avg_pool1d_fwd")
+                                       int(count_include_pad), stream_ptr()), "ms_avg_pool1d_fwd")
     return y
 
 

@@ -177,7 +177,37 @@ def fb_discriminator():
     save("fb_discriminator_n2048", **arrays)
 
 
+def realmelgan():
+    """experiment/realmelgan.py Generator (48-89) and Discriminator (158-181)."""
+    ref_harness.load()
+    import featuresynth.experiment.realmelgan as rm
+    torch.set_grad_enabled(False)
+    g = rm.Generator(128, 32, n_residual_layers=3).eval()
+    sd = restate.realmelgan_generator_state(101)
+    assert list(g.state_dict()) == list(sd), "state-dict key order differs from the reference"
+    g.load_state_dict(sd)
+    x = synth.mel_features(102, 2, 8)
+    y = g(x)
+    save("realmelgan_gen_t8", seed=101, y=y.numpy(), n_keys=len(sd))
+    d = rm.Discriminator(3, 16, 4, 4).eval()
+    dsd = restate.realmelgan_discriminator_state(103)
+    assert list(d.state_dict()) == list(dsd), "discriminator key order differs"
+    d.load_state_dict(dsd)
+    a = synth.randn(104, 2, 1, 4096) * 0.1
+    feats, judg = d(a, None)
+    arrays = {"seed": 103}
+    for i, j in enumerate(judg):
+        arrays[f"j{i}"] = j.numpy()
+        for k, f in enumerate(feats[i]):
+            arrays[f"f{i}_{k}_shape"] = np.array(f.shape)
+            arrays[f"f{i}_{k}_sub"] = f.numpy().reshape(-1)[::41]
+    save("realmelgan_disc_n4096", **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "realmelgan":
+        realmelgan()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fb_discriminator":
         fb_discriminator()
         sys.exit(0)

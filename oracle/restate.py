@@ -399,6 +399,141 @@ def filterbank_multiscale_discriminator(bands, feat, sd, banks, input_size,
     return features, judgements
 
 
+# ------------------------------------------- official MelGAN pair (realmelgan.py)
+def _wn(sd, name):
+    """legacy torch weight_norm (dim 0): w = g * v / ||v||, norm over all dims but 0."""
+    v, g = sd[name + ".weight_v"], sd[name + ".weight_g"]
+    return g * v / v.reshape(v.shape[0], -1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+
+
+REAL_RATIOS = (8, 8, 2, 2)
+
+
+def realmelgan_generator_layout(n_residual_layers=3):
+    """model indices of experiment/realmelgan.py:48-89: [(kind, index, arg)]"""
+    layout, idx = [("first", 1, None)], 2
+    for r in REAL_RATIOS:
+        layout.append(("up", idx + 1, r))
+        idx += 2
+        for j in range(n_residual_layers):
+            layout.append(("res", idx, 3 ** j))
+            idx += 1
+    layout.append(("last", idx + 2, None))
+    return layout
+
+
+def realmelgan_generator_state(seed, input_size=128, ngf=32, n_residual_layers=3):
+    """weight_g / weight_v / bias tensors in the reference's state-dict naming; v ~ N(0, 0.02),
+    g perturbed around ||v|| (weight_norm initialises g = ||v||), small biases."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    sd = {}
+
+    def wn(name, shape):
+        v = torch.from_numpy((rs.standard_normal(shape) * 0.02).astype(np.float32))
+        nrm = v.reshape(shape[0], -1).norm(dim=1)
+        g = nrm * torch.from_numpy((1.0 + 0.1 * rs.standard_normal((shape[0],))).astype(np.float32))
+        sd[name + ".bias"] = None      # placeholder to keep reference key order: bias, g, v
+        sd[name + ".weight_g"] = g.view(-1, *([1] * (len(shape) - 1)))
+        sd[name + ".weight_v"] = v
+
+    mult = 16
+    for kind, idx, arg in realmelgan_generator_layout(n_residual_layers):
+        if kind == "first":
+            wn(f"model.{idx}", (mult * ngf, input_size, 7))
+            sd[f"model.{idx}.bias"] = torch.from_numpy((rs.standard_normal((mult * ngf,)) * 0.01).astype(np.float32))
+        elif kind == "up":
+            cin, cout = mult * ngf, mult * ngf // 2
+            wn(f"model.{idx}", (cin, cout, 2 * arg))
+            sd[f"model.{idx}.bias"] = torch.from_numpy((rs.standard_normal((cout,)) * 0.01).astype(np.float32))
+            mult //= 2
+        elif kind == "res":
+            dim = mult * ngf
+            for sub, k in (("block.2", 3), ("block.4", 1), ("shortcut", 1)):
+                wn(f"model.{idx}.{sub}", (dim, dim, k))
+                sd[f"model.{idx}.{sub}.bias"] = torch.from_numpy((rs.standard_normal((dim,)) * 0.01).astype(np.float32))
+        else:
+            wn(f"model.{idx}", (1, ngf, 7))
+            sd[f"model.{idx}.bias"] = torch.from_numpy((rs.standard_normal((1,)) * 0.01).astype(np.float32))
+    return sd
+
+
+def realmelgan_generator(x, sd, n_residual_layers=3):
+    """experiment/realmelgan.py:32-89: official MelGAN generator (weight norm, reflection pads,
+    pre-activation ResnetBlocks with 1x1 conv shortcuts)."""
+    for kind, idx, arg in realmelgan_generator_layout(n_residual_layers):
+        n = f"model.{idx}"
+        if kind == "first":
+            x = F.conv1d(F.pad(x, (3, 3), mode="reflect"), _wn(sd, n), sd[n + ".bias"])
+        elif kind == "up":
+            r = arg
+            x = F.conv_transpose1d(leaky(x), _wn(sd, n), sd[n + ".bias"], stride=r,
+                                   padding=r // 2 + r % 2, output_padding=r % 2)
+        elif kind == "res":
+            d = arg
+            h = F.conv1d(F.pad(leaky(x), (d, d), mode="reflect"), _wn(sd, n + ".block.2"),
+                         sd[n + ".block.2.bias"], dilation=d)
+            h = F.conv1d(leaky(h), _wn(sd, n + ".block.4"), sd[n + ".block.4.bias"])
+            x = F.conv1d(x, _wn(sd, n + ".shortcut"), sd[n + ".shortcut.bias"]) + h
+        else:
+            x = torch.tanh(F.conv1d(F.pad(leaky(x), (3, 3), mode="reflect"), _wn(sd, n), sd[n + ".bias"]))
+    return x
+
+
+# (name, cin, cout, k, stride, pad, groups) of NLayerDiscriminator(ndf=16, n_layers=4, factor=4)
+REAL_DISC_LAYERS = (("layer_0.1", 1, 16, 15, 1, 0, 1), ("layer_1.0", 16, 64, 41, 4, 20, 4),
+                    ("layer_2.0", 64, 256, 41, 4, 20, 16), ("layer_3.0", 256, 1024, 41, 4, 20, 64),
+                    ("layer_4.0", 1024, 1024, 41, 4, 20, 256), ("layer_5.0", 1024, 1024, 5, 1, 2, 1),
+                    ("layer_6", 1024, 1, 3, 1, 1, 1))
+
+
+def realmelgan_discriminator_state(seed, num_D=3):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    sd = {}
+    for i in range(num_D):
+        for name, cin, cout, k, s_, p_, g_ in REAL_DISC_LAYERS:
+            shape = (cout, cin // g_, k)
+            v = torch.from_numpy((rs.standard_normal(shape) * 0.02).astype(np.float32))
+            nrm = v.reshape(cout, -1).norm(dim=1)
+            pre = f"model.disc_{i}.model.{name}"
+            sd[pre + ".bias"] = torch.from_numpy((rs.standard_normal((cout,)) * 0.01).astype(np.float32))
+            sd[pre + ".weight_g"] = (nrm * torch.from_numpy(
+                (1.0 + 0.1 * rs.standard_normal((cout,))).astype(np.float32))).view(-1, 1, 1)
+            sd[pre + ".weight_v"] = v
+    return sd
+
+
+def realmelgan_discriminator(x, sd, num_D=3):
+    """experiment/realmelgan.py:92-181: three INDEPENDENT NLayerDiscriminators on x, pooled x
+    (AvgPool1d(4, 2, 1, count_include_pad=False)); features = all but the last map."""
+    features, judgements = [], []
+    for i in range(num_D):
+        h, res = x, []
+        for name, cin, cout, k, s_, p_, g_ in REAL_DISC_LAYERS:
+            pre = f"model.disc_{i}.model.{name}"
+            if name == "layer_0.1":
+                h = F.pad(h, (7, 7), mode="reflect")
+            h = F.conv1d(h, _wn(sd, pre), sd[pre + ".bias"], stride=s_, padding=p_, groups=g_)
+            if name != "layer_6":
+                h = leaky(h)
+            res.append(h)
+        features.append(res[:-1])
+        judgements.append(res[-1])
+        x = F.avg_pool1d(x, 4, stride=2, padding=1, count_include_pad=False)
+    return features, judgements
+
+
+def real_mel_gan_feature_loss(real_features, fake_features):
+    """experiment/realmelgan.py:185-202: fixed weight (1/3)(4/5) per feature map."""
+    wt = (1 / 3) * (4.0 / 5)
+    loss = 0
+    for r_group, f_group in zip(real_features, fake_features):
+        for r_f, f_f in zip(r_group, f_group):
+            loss = loss + wt * F.l1_loss(r_f, f_f)
+    return loss
+
+
 # ---------------------------------------------------------------- FLOP counting
 MELGAN_FLOP_PER_SAMPLE = 409536  # SURVEY.md App. A.1 (2 x MAC, conv/convT only)
 

@@ -171,3 +171,22 @@ def test_fb_discriminator_matches_reference(golden):
         for i, f in enumerate(fl):
             assert tuple(f.shape) == tuple(g[f"f{gi}_{i}_shape"])
             assert rel_l2(f.reshape(-1)[::13], g[f"f{gi}_{i}_sub"]) < 5e-6
+
+
+def test_realmelgan_pair_matches_reference(golden):
+    g = golden("realmelgan_gen_t8")
+    sd = restate.realmelgan_generator_state(101)
+    assert len(sd) == int(g["n_keys"]) == 126
+    y = restate.realmelgan_generator(synth.mel_features(102, 2, 8), sd)
+    assert y.shape == (2, 1, 2048) and rel_l2(y, g["y"]) < 3e-6
+    gd = golden("realmelgan_disc_n4096")
+    dsd = restate.realmelgan_discriminator_state(103)
+    assert len(dsd) == 63
+    feats, judg = restate.realmelgan_discriminator(synth.randn(104, 2, 1, 4096) * 0.1, dsd)
+    assert [j.shape[-1] for j in judg] == [16, 8, 4]
+    for i, j in enumerate(judg):
+        assert rel_l2(j, gd[f"j{i}"]) < 2e-5
+        assert len(feats[i]) == 6
+        for k, f in enumerate(feats[i]):
+            assert tuple(f.shape) == tuple(gd[f"f{i}_{k}_shape"])
+            assert rel_l2(f.reshape(-1)[::41], gd[f"f{i}_{k}_sub"]) < 2e-5
