@@ -261,6 +261,78 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
                            const int* row_ranges, float* out, int batch, int samples, int n_fft,
                            int hop, int n_mels, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Training step (backward pass + optimiser).  The reference gets these from autograd
+ * (featuresynth/train/train.py:36,70: loss.backward()) and torch.optim.Adam
+ * (experiment/experiment.py:111-117); here they are explicit kernels called from
+ * torch.autograd.Function.backward through this ABI.
+ *   Gradients travel as BLK f32 between layers and are converted to a 16-bit GEMM operand
+ *   (bf16: the range of fp32, so no loss scaling) by ms_blk_act_bwd, which also applies LeakyReLU' and
+ *   accumulates the bias gradient.
+ * ------------------------------------------------------------------------- */
+/* dz16 = to16(dy32 * LeakyReLU'(.)), dbias[c] += sum_{b,l} dz.  Sign source: `sign16` (BLK
+ * 16-bit saved activation) or the fp32 pair (ya32 - yb32 > 0; the branch of a ResidualAtom,
+ * util/modules.py:384-388); none = no activation.  s2d_stride > 1 writes dz16 in the
+ * space-to-depth layout of ms_space_to_depth_blk16 (input of the ConvTranspose1d dgrad).
+ * dbias may be NULL; otherwise it must be zero-initialised (atomic accumulation). */
+ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya32,
+                         const float* yb32, void* dz16, float* dbias, int batch, int channels,
+                         int len, int fmt, int s2d_stride, void* stream);
+/* reference-layout fp32 weights of the convolution that computes the INPUT gradient, to be
+ * packed with ms_conv_pack_weight and run with ms_conv_fwd:
+ *   MS_CONV  w (cout,cin,k)  -> out (cin,cout,k) tap-reversed; run as MS_CONV cin'=cout,
+ *            cout'=cin, same k / dilation, pad' = dilation*(k-1) - pad;
+ *   MS_CONVT w (cin,cout,2s) -> out (cin, s*cout, 3); run as MS_CONV over the space-to-depth
+ *            gradient (s*cout channels), k 3, pad 1. */
+ms_status ms_weight_dgrad_view(const float* w, float* out, int kind, int cout, int cin, int ksize,
+                               int stride, int pad, void* stream);
+/* Weight gradient as a tcgen05 GEMM reduced over time (MN-major operands straight from the
+ * channel-blocked layout):  G[t][m][n] = sum_b sum_l a16[b,m,l] * x16[b,n,l+shifts[t]]
+ * (rows outside [0,lx) are zero), scattered into dw:
+ *   mode MS_CONV : Conv1d weight (cout=cm, cin=cn, k=taps); a16 = dz, x16 = layer input,
+ *                  shifts[t] = t*dilation - pad;
+ *   mode MS_CONVT: ConvTranspose1d weight (cin=cm, cout, 2*stride); a16 = layer input,
+ *                  x16 = space-to-depth dz (cn = stride*cout), shifts = {-1,0,1}.
+ * fmt: MS_F16 | MS_BF16 of BOTH operands (tcgen05 kind::f16 does not mix them: a mixed
+ * instruction descriptor raises an illegal-instruction fault on sm_100a).  dw = beta*dw + G. */
+size_t ms_wgrad_workspace_bytes(int batch, int cm, int cn, int la, int lx, int taps,
+                                const int* shifts);
+ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int cn, int la,
+                       int lx, int taps, const int* shifts, int fmt, int mode, int stride,
+                       int pad, int cout, float beta, float* dw, void* workspace,
+                       size_t workspace_bytes, void* stream);
+/* 16-bit operand format conversion (fp16 forward activations -> bf16 for the weight-gradient
+ * GEMM, whose other operand is a bf16 gradient) */
+ms_status ms_blk16_convert(const void* src, void* dst, size_t elems, int src_fmt, int dst_fmt,
+                           void* stream);
+/* NCL f32 -> BLK f32 (gradient of ms_unpack_blk32_to_ncl) */
+ms_status ms_pack_ncl_to_blk32(const float* x, float* y32, int batch, int channels, int len,
+                               void* stream);
+/* backward of ms_conv1d_direct_fwd (zero padding).  `y` = forward output (LeakyReLU mask) when
+ * leaky.  dw / dbias must be zero-initialised (atomic accumulation); dbias may be NULL. */
+ms_status ms_conv1d_direct_dgrad(const float* dy, const float* y, const float* w, float* dx,
+                                 int batch, int cin, int cout, int lin, int ksize, int stride,
+                                 int pad, int groups, int leaky, void* stream);
+ms_status ms_conv1d_direct_wgrad(const float* dy, const float* y, const float* x, float* dw,
+                                 float* dbias, int batch, int cin, int cout, int lin, int ksize,
+                                 int stride, int pad, int groups, int leaky, void* stream);
+/* backward of ms_conv_to_mono: dzm (B,1,L) scratch/out = dy * (1 - y_tanh^2) (y_tanh NULL: no
+ * tanh); dx32 BLK f32 (may be NULL); dw (cin,k) / dbias (1) zero-initialised, may be NULL. */
+ms_status ms_conv_to_mono_bwd(const float* dy, const float* y_tanh, const float* x32,
+                              const float* w, float* dzm, float* dx32, float* dw, float* dbias,
+                              int batch, int cin, int len, int ksize, int pad, void* stream);
+ms_status ms_avg_pool1d_bwd(const float* dy, float* dx, int batch_channels, int lin, int ksize,
+                            int stride, int pad, int count_include_pad, void* stream);
+/* gradients of the ms_reduce_fwd terms wrt a (da) and b (db), either may be NULL;
+ * grad_out: device scalar = upstream gradient of the loss (NULL = 1). */
+ms_status ms_reduce_bwd(int mode, const float* a, const float* b, size_t n, float weight,
+                        const float* grad_out, float* da, float* db, void* stream);
+/* torch.optim.Adam step (no amsgrad / weight decay) on a flat fp32 buffer; `step` counts from
+ * 1; grad_scale multiplies the gradient first (1/world_size after a summing all-reduce). */
+ms_status ms_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       size_t n, float lr, float beta1, float beta2, float eps, int step,
+                       float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

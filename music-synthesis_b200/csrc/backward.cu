@@ -1,0 +1,659 @@
+// Backward-pass kernels of the GAN training step that are not GEMM-shaped: activation
+// gradients + operand conversion, bias gradients, the grouped / strided direct convolutions
+// of the discriminator, the single-channel convs, pooling, loss gradients and Adam.
+// The reference gets all of these from autograd (featuresynth/train/train.py:36,70 ->
+// loss.backward()) and torch.optim.Adam (experiment/experiment.py:111-117).
+// All HBM/latency-bound CUDA-core work: coalesced along time, 16/32-byte vectors on the
+// channel-blocked tensors.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+__device__ __forceinline__ uint32_t bw_pack2(float a, float b, int fmt) {
+  if (fmt == MS_BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_h2(a, b);
+}
+
+// dz = dy * LeakyReLU'(.) on BLK tensors -> 16-bit GEMM operand (optionally written in the
+// space-to-depth layout the transposed-conv backward consumes) + per-channel bias gradient.
+//   sign source: s16 (sign bit of the saved 16-bit activation) or the fp32 pair (ya - yb > 0,
+//   the residual branch y - x of a ResidualAtom); neither -> no activation.
+struct ActBwdParams {
+  const float* dy;      // BLK f32 (B, C/8, L, 8)
+  const uint16_t* s16;  // BLK 16-bit or null
+  const float* ya;      // BLK f32 or null
+  const float* yb;      // BLK f32 or null
+  uint16_t* dz;         // BLK 16-bit (B, C/8, L, 8) or s2d (B, s*C/8, L/s, 8)
+  float* dbias;         // [C] accumulated with atomics, or null
+  int C8, L, fmt, s2d;
+};
+
+constexpr int kActBwdRows = 1024;   // rows per block (256 threads x 4)
+
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const ActBwdParams p) {
+  const size_t bc = blockIdx.y;                 // b * C8 + c8
+  const int c8 = static_cast<int>(bc % p.C8);
+  const size_t b = bc / p.C8;
+  float bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  const int t_end = min(p.L, (static_cast<int>(blockIdx.x) + 1) * kActBwdRows);
+  for (int t = blockIdx.x * kActBwdRows + threadIdx.x; t < t_end; t += 256) {
+    const size_t idx = bc * p.L + t;
+    float g[8];
+    ld_global_nc_v8(p.dy + idx * 8, g);
+    if (p.s16 != nullptr) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.s16) + idx);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (w[j] & 0x8000u) g[2 * j] *= 0.2f;
+        if (w[j] & 0x80000000u) g[2 * j + 1] *= 0.2f;
+      }
+    } else if (p.ya != nullptr) {
+      float a[8], x[8];
+      ld_global_nc_v8(p.ya + idx * 8, a);
+      ld_global_nc_v8(p.yb + idx * 8, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!(a[j] - x[j] > 0.f)) g[j] *= 0.2f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bsum[j] += g[j];
+    uint4 o;
+    o.x = bw_pack2(g[0], g[1], p.fmt); o.y = bw_pack2(g[2], g[3], p.fmt);
+    o.z = bw_pack2(g[4], g[5], p.fmt); o.w = bw_pack2(g[6], g[7], p.fmt);
+    size_t oidx = idx;
+    if (p.s2d > 1) {
+      const int u = t / p.s2d, i = t - u * p.s2d;
+      oidx = ((b * p.s2d + i) * p.C8 + c8) * static_cast<size_t>(p.L / p.s2d) + u;
+    }
+    reinterpret_cast<uint4*>(p.dz)[oidx] = o;
+  }
+  if (p.dbias == nullptr) return;
+  __shared__ float sh[8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = bsum[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
+    atomicAdd(p.dbias + c8 * 8 + threadIdx.x, v);
+  }
+}
+
+// reference-layout weights of the convolution that computes the INPUT gradient:
+//   MS_CONV : w (Co,Ci,K) -> out (Ci,Co,K), out[ci][co][k] = w[co][ci][K-1-k]
+//   MS_CONVT: w (Ci,Co,2s), padding p -> out (Ci, s*Co, 3) over the space-to-depth gradient,
+//             out[ci][r*Co+co][t] = w[ci][co][s*(t-1) + r + p]  (0 where that tap does not exist)
+__global__ void weight_dgrad_view_kernel(const float* __restrict__ w, float* __restrict__ out,
+                                         int kind, int co_n, int ci_n, int K, int stride, int pad,
+                                         size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  if (kind == MS_CONV) {
+    const int k = static_cast<int>(i % K);
+    const int co = static_cast<int>((i / K) % co_n);
+    const int ci = static_cast<int>(i / (static_cast<size_t>(K) * co_n));
+    out[i] = w[(static_cast<size_t>(co) * ci_n + ci) * K + (K - 1 - k)];
+  } else {
+    const int t = static_cast<int>(i % 3);
+    const int n = static_cast<int>((i / 3) % (stride * co_n));
+    const int ci = static_cast<int>(i / (static_cast<size_t>(3) * stride * co_n));
+    const int r = n / co_n, co = n - r * co_n;
+    const int k = stride * (t - 1) + r + pad;
+    out[i] = (k >= 0 && k < K) ? w[(static_cast<size_t>(ci) * co_n + co) * K + k] : 0.f;
+  }
+}
+
+// fp16 <-> bf16 on 16-byte vectors
+__global__ void blk16_convert_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                     size_t nvec, int src_fmt, int dst_fmt) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= nvec) return;
+  const uint4 v = __ldg(src + i);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 f;
+    if (src_fmt == MS_BF16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    else f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    o[j] = bw_pack2(f.x, f.y, dst_fmt);
+  }
+  dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// NCL f32 -> BLK f32 (gradient of ms_unpack_blk32_to_ncl)
+__global__ void pack_ncl_to_blk32_kernel(const float* __restrict__ x, float* __restrict__ y, int L,
+                                         size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int t = static_cast<int>(i % L);
+  const size_t bc = i / L;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = __ldg(x + (bc * 8 + j) * L + t);
+  st_global_v8(y + i * 8, f);
+}
+
+// ------------------------------------------------------------ direct conv backward (NCL f32)
+struct DirectBwdParams {
+  const float* dy;   // (B, cout, lout)
+  const float* y;    // forward output (LeakyReLU mask source) or null
+  const float* x;    // (B, cin, lin)          [wgrad]
+  const float* w;    // (cout, cin/groups, k)  [dgrad]
+  float* dx;         // (B, cin, lin)          [dgrad]
+  float* dw;         // (cout, cin/groups, k)  [wgrad, atomics]
+  float* dbias;      // (cout)                 [wgrad, atomics] or null
+  int B, cin, cout, lin, lout, k, stride, pad, groups, leaky;
+};
+
+__device__ __forceinline__ float masked(float g, float y, int leaky) {
+  return (leaky && !(y > 0.f)) ? 0.2f * g : g;
+}
+
+constexpr int kDgTile = 128;
+
+// dx[b, ci, i] = sum_{co in group} sum_k w[co, cil, k] * dz[b, co, (i + pad - k)/stride]
+__global__ void __launch_bounds__(kDgTile)
+direct_dgrad_kernel(const DirectBwdParams p) {
+  extern __shared__ float sm[];
+  const int cin_g = p.cin / p.groups, cout_g = p.cout / p.groups;
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int i0 = blockIdx.x * kDgTile;
+  // dz rows l in [l0, l0 + nl): l = (i + pad - k)/stride for i in the tile
+  int l0 = (i0 + p.pad - (p.k - 1));
+  l0 = l0 < 0 ? -((-l0 + p.stride - 1) / p.stride) : l0 / p.stride;
+  const int l1 = (i0 + kDgTile - 1 + p.pad) / p.stride;
+  const int nl = l1 - l0 + 1;
+  float* sw = sm;                               // [cout_g][cin_g][k]
+  float* sz = sm + cout_g * cin_g * p.k;        // [cout_g][nl]
+  for (int i = threadIdx.x; i < cout_g * cin_g * p.k; i += kDgTile)
+    sw[i] = __ldg(p.w + static_cast<size_t>(g) * cout_g * cin_g * p.k + i);
+  for (int i = threadIdx.x; i < cout_g * nl; i += kDgTile) {
+    const int oc = i / nl, l = l0 + (i - oc * nl);
+    float v = 0.f;
+    if (l >= 0 && l < p.lout) {
+      const size_t idx = (static_cast<size_t>(b) * p.cout + g * cout_g + oc) * p.lout + l;
+      v = __ldg(p.dy + idx);
+      if (p.y != nullptr) v = masked(v, __ldg(p.y + idx), p.leaky);
+    }
+    sz[i] = v;
+  }
+  __syncthreads();
+  const int i = i0 + threadIdx.x;
+  if (i >= p.lin) return;
+  const int ip = i + p.pad;
+  const int kfirst = ip % p.stride;            // taps with (ip - k) % stride == 0
+  for (int c = 0; c < cin_g; ++c) {
+    float acc = 0.f;
+    for (int oc = 0; oc < cout_g; ++oc) {
+      const float* wr = sw + (oc * cin_g + c) * p.k;
+      const float* zr = sz + oc * nl - l0;
+      for (int k = kfirst; k < p.k; k += p.stride) {
+        const int l = (ip - k) / p.stride;
+        if (ip - k >= 0) acc = fmaf(wr[k], zr[l], acc);
+      }
+    }
+    p.dx[(static_cast<size_t>(b) * p.cin + g * cin_g + c) * p.lin + i] = acc;
+  }
+}
+
+constexpr int kWgTileL = 256;
+constexpr int kWgDirectThreads = 256;
+
+// dw[co, cil, k] += sum_b sum_l dz[b, co, l] * x[b, g*cin_g + cil, l*stride + k - pad]
+// one CTA = one output channel x one tile of l x a set of clips; thread = (output o, lane group)
+__global__ void __launch_bounds__(kWgDirectThreads)
+direct_wgrad_kernel(const DirectBwdParams p) {
+  extern __shared__ float sm[];
+  const int cin_g = p.cin / p.groups, cout_g = p.cout / p.groups;
+  const int co = blockIdx.x;
+  const int g = co / cout_g;
+  const int l0 = blockIdx.y * kWgTileL;
+  const int nl = min(kWgTileL, p.lout - l0);
+  const int win = (kWgTileL - 1) * p.stride + p.k;
+  float* sz = sm;                 // [kWgTileL]
+  float* sx = sm + kWgTileL;      // [cin_g][win]
+  const int nout = cin_g * p.k;
+  const int ngroups = max(1, kWgDirectThreads / nout);
+  const int o = threadIdx.x % nout, lg = threadIdx.x / nout;
+  const bool active = lg < ngroups;
+  const int cil = o / p.k, k = o - cil * p.k;
+  float acc = 0.f, bacc = 0.f;
+  for (int b = blockIdx.z; b < p.B; b += gridDim.z) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nl; i += kWgDirectThreads) {
+      const size_t idx = (static_cast<size_t>(b) * p.cout + co) * p.lout + l0 + i;
+      float v = __ldg(p.dy + idx);
+      if (p.y != nullptr) v = masked(v, __ldg(p.y + idx), p.leaky);
+      sz[i] = v;
+    }
+    const int in0 = l0 * p.stride - p.pad;
+    const int nwin = (nl - 1) * p.stride + p.k;
+    for (int i = threadIdx.x; i < cin_g * nwin; i += kWgDirectThreads) {
+      const int c = i / nwin, j = i - c * nwin;
+      const int ti = in0 + j;
+      sx[c * win + j] = (ti >= 0 && ti < p.lin)
+          ? __ldg(p.x + (static_cast<size_t>(b) * p.cin + g * cin_g + c) * p.lin + ti) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      const float* xr = sx + cil * win + k;
+      for (int l = lg; l < nl; l += ngroups) acc = fmaf(sz[l], xr[l * p.stride], acc);
+      if (o == 0 && p.dbias != nullptr)
+        for (int l = lg; l < nl; l += ngroups) bacc += sz[l];
+    }
+  }
+  // combine the lane groups
+  __syncthreads();
+  float* red = sm;                // [ngroups][nout] <= 256 floats
+  if (active) red[lg * nout + o] = acc;
+  __syncthreads();
+  if (threadIdx.x < nout) {
+    float v = 0.f;
+    for (int q = 0; q < ngroups; ++q) v += red[q * nout + threadIdx.x];
+    atomicAdd(p.dw + static_cast<size_t>(co) * nout + threadIdx.x, v);
+  }
+  if (p.dbias != nullptr) {
+    __syncthreads();
+    if (active && o == 0) red[lg] = bacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = 0.f;
+      for (int q = 0; q < ngroups; ++q) v += red[q];
+      atomicAdd(p.dbias + co, v);
+    }
+  }
+}
+
+// --------------------------------------------------------- single-output-channel conv backward
+// forward: y[b,l] = act(bias + sum_c sum_k w[c,k] x[b,c,l+k-pad]),  x BLK f32.
+// dzm[b,l] = dy[b,l] * (tanh ? 1 - y^2 : 1)
+__global__ void mono_dz_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                               float* __restrict__ dzm, size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  float g = __ldg(dy + i);
+  if (y != nullptr) {
+    const float v = __ldg(y + i);
+    g *= (1.f - v * v);
+  }
+  dzm[i] = g;
+}
+
+// dx[b,c,i] = sum_k w[c,k] * dzm[b, i - k + pad]   -> BLK f32
+__global__ void mono_dgrad_kernel(const float* __restrict__ dzm, const float* __restrict__ w,
+                                  float* __restrict__ dx, int C8, int L, int ksize, int pad) {
+  extern __shared__ float sw[];    // [ksize][8] of this channel group
+  const int c8 = blockIdx.y, b = blockIdx.z;
+  for (int i = threadIdx.x; i < 8 * ksize; i += blockDim.x) {
+    const int k = i / 8, e = i - k * 8;
+    sw[i] = __ldg(w + (c8 * 8 + e) * ksize + k);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  const float* z = dzm + static_cast<size_t>(b) * L;
+  for (int k = 0; k < ksize; ++k) {
+    const int l = i - k + pad;
+    if (l < 0 || l >= L) continue;
+    const float g = __ldg(z + l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(sw[k * 8 + j], g, f[j]);
+  }
+  st_global_v8(dx + ((static_cast<size_t>(b) * C8 + c8) * L + i) * 8, f);
+}
+
+constexpr int kMonoMaxK = 8;
+// dw[c,k] += sum_b sum_l dzm[b,l] * x[b,c,l+k-pad];  dbias += sum dzm
+__global__ void __launch_bounds__(256)
+mono_wgrad_kernel(const float* __restrict__ dzm, const float* __restrict__ x,
+                  float* __restrict__ dw, float* __restrict__ dbias, int B, int C8, int L,
+                  int ksize, int pad) {
+  const int c8 = blockIdx.y;
+  float acc[kMonoMaxK][8];
+#pragma unroll
+  for (int k = 0; k < kMonoMaxK; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  float bacc = 0.f;
+  for (int b = blockIdx.z; b < B; b += gridDim.z) {
+    const float* z = dzm + static_cast<size_t>(b) * L;
+    const float* xr = x + (static_cast<size_t>(b) * C8 + c8) * static_cast<size_t>(L) * 8;
+    // thread owns input row i; it contributes to tap k with dzm[i - k + pad]
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < L; i += gridDim.x * 256) {
+      float f[8];
+      ld_global_nc_v8(xr + static_cast<size_t>(i) * 8, f);
+#pragma unroll
+      for (int k = 0; k < kMonoMaxK; ++k) {
+        if (k >= ksize) break;
+        const int l = i - k + pad;
+        if (l < 0 || l >= L) continue;
+        const float g = __ldg(z + l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(g, f[j], acc[k][j]);
+      }
+      if (c8 == 0) bacc += __ldg(z + i);
+    }
+  }
+  __shared__ float sh[8][kMonoMaxK * 8 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kMonoMaxK; ++k) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[k][j];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sh[warp][k * 8 + j] = v;
+    }
+  }
+  {
+    float v = bacc;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][kMonoMaxK * 8] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < ksize * 8) {
+    const int k = threadIdx.x / 8, j = threadIdx.x - k * 8;
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += sh[w][k * 8 + j];
+    atomicAdd(dw + (c8 * 8 + j) * ksize + k, v);
+  }
+  if (c8 == 0 && dbias != nullptr && threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += sh[w][kMonoMaxK * 8];
+    atomicAdd(dbias, v);
+  }
+}
+
+// ---------------------------------------------------------------- pooling / losses / Adam
+__global__ void avg_pool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int lin,
+                                    int lout, int k, int stride, int pad, int include_pad,
+                                    size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int ti = static_cast<int>(i % lin);
+  const size_t bc = i / lin;
+  float acc = 0.f;
+  // windows t with t*stride - pad <= ti < t*stride - pad + k
+  int t_hi = (ti + pad) / stride;
+  if (t_hi > lout - 1) t_hi = lout - 1;
+  for (int t = t_hi; t >= 0 && t * stride - pad + k > ti; --t) {
+    float div = static_cast<float>(k);
+    if (!include_pad) {
+      const int a = max(t * stride - pad, 0), e = min(t * stride - pad + k, lin);
+      div = static_cast<float>(max(e - a, 1));
+    }
+    acc += __ldg(dy + bc * lout + t) / div;
+  }
+  dx[i] = acc;
+}
+
+// gradients of the ms_reduce_fwd terms; *gscale (device scalar, may be null = 1) is the
+// upstream gradient of the scalar loss
+__global__ void reduce_bwd_kernel(int mode, const float* __restrict__ a,
+                                  const float* __restrict__ b, size_t n, float scale,
+                                  const float* __restrict__ gscale, float* __restrict__ da,
+                                  float* __restrict__ db) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float s = scale * (gscale != nullptr ? __ldg(gscale) : 1.f);
+  const float av = __ldg(a + i);
+  const float bv = b != nullptr ? __ldg(b + i) : 0.f;
+  float ga = 0.f, gb = 0.f;
+  switch (mode) {
+    case MS_RED_L1: {
+      const float d = av - bv;
+      ga = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      gb = -ga;
+      break;
+    }
+    case MS_RED_HINGE_D:
+      ga = (1.f - av > 0.f) ? -1.f : 0.f;
+      gb = (1.f + bv > 0.f) ? 1.f : 0.f;
+      break;
+    case MS_RED_HINGE_G: ga = -1.f; break;
+    case MS_RED_LSQ_D: ga = av - 1.f; gb = bv; break;
+    default: ga = av - 1.f; break;
+  }
+  if (da != nullptr) da[i] = ga * s;
+  if (db != nullptr) db[i] = gb * s;
+}
+
+// torch.optim.Adam (no amsgrad, no weight decay) on a flat parameter buffer
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                            float* __restrict__ m, float* __restrict__ v, size_t n, float lr,
+                            float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya32,
+                         const float* yb32, void* dz16, float* dbias, int batch, int channels,
+                         int len, int fmt, int s2d_stride, void* stream) {
+  if (dy32 == nullptr || dz16 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
+      len <= 0)
+    return MS_ERR_INVALID;
+  if ((ya32 == nullptr) != (yb32 == nullptr)) return MS_ERR_INVALID;
+  if (s2d_stride < 1 || len % s2d_stride != 0) return MS_ERR_INVALID;
+  if (fmt != MS_F16 && fmt != MS_BF16) return MS_ERR_INVALID;
+  const long long rows = static_cast<long long>(batch) * (channels / 8);
+  if (rows > 65535) return MS_ERR_INVALID;
+  ActBwdParams p{dy32, static_cast<const uint16_t*>(sign16), ya32, yb32,
+                 static_cast<uint16_t*>(dz16), dbias, channels / 8, len, fmt, s2d_stride};
+  dim3 grid(ceil_div(len, kActBwdRows), static_cast<unsigned>(rows));
+  act_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("act_bwd_kernel");
+}
+
+ms_status ms_weight_dgrad_view(const float* w, float* out, int kind, int cout, int cin, int ksize,
+                               int stride, int pad, void* stream) {
+  if (w == nullptr || out == nullptr || cout <= 0 || cin <= 0 || ksize <= 0) return MS_ERR_INVALID;
+  size_t total;
+  if (kind == MS_CONV) {
+    total = static_cast<size_t>(cin) * cout * ksize;
+  } else if (kind == MS_CONVT) {
+    if (stride < 1 || ksize != 2 * stride) return MS_ERR_INVALID;
+    total = static_cast<size_t>(cin) * stride * cout * 3;
+  } else {
+    return MS_ERR_INVALID;
+  }
+  weight_dgrad_view_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(w, out, kind, cout, cin, ksize,
+                                                                  stride, pad, total);
+  return after_launch("weight_dgrad_view_kernel");
+}
+
+ms_status ms_blk16_convert(const void* src, void* dst, size_t elems, int src_fmt, int dst_fmt,
+                           void* stream) {
+  if (src == nullptr || dst == nullptr || elems % 8 != 0) return MS_ERR_INVALID;
+  if (elems == 0) return MS_OK;
+  const size_t nvec = elems / 8;
+  blk16_convert_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), nvec, src_fmt, dst_fmt);
+  return after_launch("blk16_convert_kernel");
+}
+
+ms_status ms_pack_ncl_to_blk32(const float* x, float* y32, int batch, int channels, int len,
+                               void* stream) {
+  if (x == nullptr || y32 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
+      len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * len;
+  pack_ncl_to_blk32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(x, y32, len, total);
+  return after_launch("pack_ncl_to_blk32_kernel");
+}
+
+ms_status ms_conv1d_direct_dgrad(const float* dy, const float* y, const float* w, float* dx,
+                                 int batch, int cin, int cout, int lin, int ksize, int stride,
+                                 int pad, int groups, int leaky, void* stream) {
+  if (dy == nullptr || w == nullptr || dx == nullptr || batch <= 0 || cin <= 0 || cout <= 0 ||
+      groups <= 0 || cin % groups != 0 || cout % groups != 0 || (leaky && y == nullptr))
+    return MS_ERR_INVALID;
+  const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
+  if (lout <= 0) return MS_ERR_INVALID;
+  DirectBwdParams p{dy, y, nullptr, w, dx, nullptr, nullptr, batch, cin, cout, lin, lout,
+                    ksize, stride, pad, groups, leaky};
+  const int cin_g = cin / groups, cout_g = cout / groups;
+  const int nl = (kDgTile + ksize) / stride + 3;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(cout_g) * cin_g * ksize +
+                                       static_cast<size_t>(cout_g) * nl);
+  if (smem > 200 * 1024 || groups > 65535 || batch > 65535) return MS_ERR_INVALID;
+  if (smem > 48 * 1024) {
+    static thread_local size_t attr_set = 0;
+    if (smem > attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(direct_dgrad_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(direct_dgrad_kernel)");
+      attr_set = smem;
+    }
+  }
+  dim3 grid(ceil_div(lin, kDgTile), groups, batch);
+  direct_dgrad_kernel<<<grid, kDgTile, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("direct_dgrad_kernel");
+}
+
+ms_status ms_conv1d_direct_wgrad(const float* dy, const float* y, const float* x, float* dw,
+                                 float* dbias, int batch, int cin, int cout, int lin, int ksize,
+                                 int stride, int pad, int groups, int leaky, void* stream) {
+  if (dy == nullptr || x == nullptr || dw == nullptr || batch <= 0 || cin <= 0 || cout <= 0 ||
+      groups <= 0 || cin % groups != 0 || cout % groups != 0 || (leaky && y == nullptr))
+    return MS_ERR_INVALID;
+  const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
+  if (lout <= 0) return MS_ERR_INVALID;
+  const int cin_g = cin / groups;
+  if (cin_g * ksize > kWgDirectThreads) return MS_ERR_INVALID;
+  DirectBwdParams p{dy, y, x, nullptr, nullptr, dw, dbias, batch, cin, cout, lin, lout,
+                    ksize, stride, pad, groups, leaky};
+  const int win = (kWgTileL - 1) * stride + ksize;
+  const size_t smem = sizeof(float) * (kWgTileL + static_cast<size_t>(cin_g) * win);
+  if (smem > 200 * 1024 || cout > 0x7fffffff) return MS_ERR_INVALID;
+  if (smem > 48 * 1024) {
+    static thread_local size_t attr_set = 0;
+    if (smem > attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(direct_wgrad_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(direct_wgrad_kernel)");
+      attr_set = smem;
+    }
+  }
+  const int ltiles = ceil_div(lout, kWgTileL);
+  if (ltiles > 65535) return MS_ERR_INVALID;
+  long long z = 4096LL / (static_cast<long long>(cout) * ltiles);
+  if (z < 1) z = 1;
+  if (z > batch) z = batch;
+  dim3 grid(cout, ltiles, static_cast<unsigned>(z));
+  direct_wgrad_kernel<<<grid, kWgDirectThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  return after_launch("direct_wgrad_kernel");
+}
+
+ms_status ms_conv_to_mono_bwd(const float* dy, const float* y_tanh, const float* x32,
+                              const float* w, float* dzm, float* dx32, float* dw, float* dbias,
+                              int batch, int cin, int len, int ksize, int pad, void* stream) {
+  if (dy == nullptr || dzm == nullptr || w == nullptr || batch <= 0 || cin <= 0 ||
+      cin % 8 != 0 || len <= 0 || ksize <= 0 || ksize > kMonoMaxK || batch > 65535)
+    return MS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t total = static_cast<size_t>(batch) * len;
+  mono_dz_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(dy, y_tanh, dzm, total);
+  ms_status s = after_launch("mono_dz_kernel");
+  if (s != MS_OK) return s;
+  if (dx32 != nullptr) {
+    dim3 grid(ceil_div(len, 256), cin / 8, batch);
+    mono_dgrad_kernel<<<grid, 256, sizeof(float) * 8 * ksize, st>>>(dzm, w, dx32, cin / 8, len,
+                                                                   ksize, pad);
+    s = after_launch("mono_dgrad_kernel");
+    if (s != MS_OK) return s;
+  }
+  if (dw != nullptr) {
+    if (x32 == nullptr) return MS_ERR_INVALID;
+    int xb = ceil_div(len, 256 * 8);
+    if (xb > 64) xb = 64;
+    int zb = 2048 / (xb * (cin / 8));
+    if (zb < 1) zb = 1;
+    if (zb > batch) zb = batch;
+    dim3 grid(xb, cin / 8, zb);
+    mono_wgrad_kernel<<<grid, 256, 0, st>>>(dzm, x32, dw, dbias, batch, cin / 8, len, ksize, pad);
+    s = after_launch("mono_wgrad_kernel");
+  }
+  return s;
+}
+
+ms_status ms_avg_pool1d_bwd(const float* dy, float* dx, int batch_channels, int lin, int ksize,
+                            int stride, int pad, int count_include_pad, void* stream) {
+  if (dy == nullptr || dx == nullptr || batch_channels <= 0) return MS_ERR_INVALID;
+  const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
+  if (lout <= 0) return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch_channels) * lin;
+  avg_pool_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(dy, dx, lin, lout, ksize, stride, pad,
+                                                             count_include_pad, total);
+  return after_launch("avg_pool_bwd_kernel");
+}
+
+ms_status ms_reduce_bwd(int mode, const float* a, const float* b, size_t n, float weight,
+                        const float* grad_out, float* da, float* db, void* stream) {
+  if (a == nullptr || n == 0 || mode < 0 || mode > 4 || (da == nullptr && db == nullptr))
+    return MS_ERR_INVALID;
+  if ((mode == MS_RED_L1 || mode == MS_RED_HINGE_D || mode == MS_RED_LSQ_D) && b == nullptr)
+    return MS_ERR_INVALID;
+  float scale = weight / static_cast<float>(n);
+  if (mode == MS_RED_LSQ_D || mode == MS_RED_LSQ_G) scale = weight / static_cast<float>(n);
+  reduce_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
+                      static_cast<cudaStream_t>(stream)>>>(mode, a, b, n, scale, grad_out, da, db);
+  return after_launch("reduce_bwd_kernel");
+}
+
+ms_status ms_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       size_t n, float lr, float beta1, float beta2, float eps, int step,
+                       float grad_scale, void* stream) {
+  if (param == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr ||
+      step < 1)
+    return MS_ERR_INVALID;
+  if (n == 0) return MS_OK;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
+                static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                     beta2, eps, static_cast<float>(bc1),
+                                                     static_cast<float>(sqrt(bc2)), grad_scale);
+  return after_launch("adam_kernel");
+}
+
+}  // extern "C"

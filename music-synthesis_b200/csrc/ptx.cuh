@@ -135,7 +135,8 @@ __device__ __forceinline__ uint64_t umma_desc_base_nosw(uint32_t lbo_bytes, uint
   return umma_desc_nosw(0, lbo_bytes, sbo_bytes);
 }
 
-// Instruction descriptor for kind::f16: A,B = fp16 (format 0) or bf16 (format 1),
+// Instruction descriptor for kind::f16: A,B = fp16 (format 0) or bf16 (format 1) -- the SAME
+// format for both: a descriptor that mixes them faults (illegal instruction) on sm_100a,
 // D = fp32, both operands K-major, dense, M = 128.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int n, int ab_format /*0 f16, 1 bf16*/) {
   return (1u << 4)                                   // D format: F32

@@ -1,0 +1,181 @@
+"""Tensor-level wrappers over the backward-pass / optimiser entry points of the C ABI
+(include/msb200.h, "Training step").  torch supplies device memory and the stream only."""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+from ._lib import MS_CONV, MS_CONVT, MS_F16, MS_BF16, check, ptr, stream_ptr
+
+# 16-bit format of the backward GEMMs: bf16 has the range of fp32, so the small GAN gradients need
+# no loss scaling.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, so the weights (dgrad)
+# and the saved forward activations (wgrad) are converted to bf16 for the backward pass.
+GRAD_FMT = MS_BF16
+
+
+def convert16(x16, src_fmt, dst_fmt):
+    if src_fmt == dst_fmt:
+        return x16
+    out = torch.empty_like(x16)
+    check(_lib.lib().ms_blk16_convert(ptr(x16), ptr(out), x16.numel(), src_fmt, dst_fmt,
+                                      stream_ptr()), "ms_blk16_convert")
+    return out
+
+
+def act_bwd(dy32, sign16=None, ya32=None, yb32=None, want_bias=True, fmt=GRAD_FMT, s2d=1):
+    """dz16 = to16(dy32 * LeakyReLU'(.)) (+ bias gradient).  Returns (dz16, dbias|None)."""
+    dy32 = dy32.contiguous()
+    B, C8, L, _ = dy32.shape
+    if s2d > 1:
+        dz = torch.empty((B, s2d * C8, L // s2d, 8), dtype=torch.int16, device=dy32.device)
+    else:
+        dz = torch.empty((B, C8, L, 8), dtype=torch.int16, device=dy32.device)
+    db = torch.zeros(C8 * 8, dtype=torch.float32, device=dy32.device) if want_bias else None
+    check(_lib.lib().ms_blk_act_bwd(ptr(dy32), ptr(sign16), ptr(ya32), ptr(yb32), ptr(dz), ptr(db),
+                                    B, C8 * 8, L, fmt, s2d, stream_ptr()), "ms_blk_act_bwd")
+    return dz, db
+
+
+def weight_dgrad_view(w, kind, stride=1, pad=0):
+    """reference-layout weight of the conv that computes the input gradient (see msb200.h)"""
+    w = w.contiguous()
+    if kind == MS_CONV:
+        cout, cin, k = w.shape
+        out = torch.empty((cin, cout, k), dtype=torch.float32, device=w.device)
+    else:
+        cin, cout, k = w.shape
+        out = torch.empty((cin, stride * cout, 3), dtype=torch.float32, device=w.device)
+    check(_lib.lib().ms_weight_dgrad_view(ptr(w), ptr(out), kind, cout, cin, k, stride, pad,
+                                          stream_ptr()), "ms_weight_dgrad_view")
+    return out
+
+
+def conv_dgrad(w, dz16, kind, dilation=1, pad=0, stride=1, res32=None, operand=GRAD_FMT):
+    """Input gradient (BLK f32) of a dense conv / transposed conv from its 16-bit output
+    gradient `dz16` (space-to-depth layout for MS_CONVT).  res32 is added in the epilogue."""
+    B, C8, L, _ = dz16.shape
+    wv = weight_dgrad_view(w, kind, stride, pad)
+    if kind == MS_CONV:
+        cout, cin, k = w.shape
+        d = ops.conv_desc(MS_CONV, B, cout, cin, L, k, dilation, dilation * (k - 1) - pad,
+                          operand=operand)
+    else:
+        cin, cout, k = w.shape
+        d = ops.conv_desc(MS_CONV, B, stride * cout, cin, L, 3, 1, 1, operand=operand)
+    _, dx32 = ops.conv_fwd(d, dz16, ops.pack_conv_weight(d, wv), None, res32=res32,
+                           want16=False, want32=True)
+    return dx32
+
+
+_ws = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0):
+    """Weight gradient (reference layout `w_shape`) on the tcgen05 time-reduction GEMM."""
+    B, Cm8, La, _ = a16.shape
+    _, Cn8, Lx, _ = x16.shape
+    taps = len(shifts)
+    sh = (ctypes.c_int * taps)(*shifts)
+    L = _lib.lib()
+    n = L.ms_wgrad_workspace_bytes(B, Cm8 * 8, Cn8 * 8, La, Lx, taps, sh)
+    if n == 0:
+        raise _lib.MsbError("unsupported weight-gradient geometry")
+    ws = _workspace(n, a16.device)
+    dw = torch.empty(w_shape, dtype=torch.float32, device=a16.device)
+    cout = w_shape[1] if mode == MS_CONVT else 0
+    check(L.ms_wgrad_fwd(ptr(a16), ptr(x16), B, Cm8 * 8, Cn8 * 8, La, Lx, taps, sh, fmt,
+                         mode, stride, pad, cout, 0.0, ptr(dw), ptr(ws), ws.numel(), stream_ptr()),
+          "ms_wgrad_fwd")
+    return dw
+
+
+def conv_wgrad(dz16, x16, w_shape, dilation=1, pad=0, fmt_dz=GRAD_FMT, fmt_x=MS_F16):
+    """dW of a stride-1 Conv1d: dz16 (B,Cout/8,Lout,8), x16 (B,Cin/8,Lin,8)."""
+    k = w_shape[2]
+    return wgrad(dz16, convert16(x16, fmt_x, fmt_dz), [t * dilation - pad for t in range(k)],
+                 MS_CONV, w_shape, fmt_dz)
+
+
+def convt_wgrad(x16, dzs16, w_shape, stride, pad, fmt_dz=GRAD_FMT, fmt_x=MS_F16):
+    """dW of a ConvTranspose1d (k = 2*stride): x16 layer input, dzs16 space-to-depth dz."""
+    return wgrad(convert16(x16, fmt_x, fmt_dz), dzs16, [-1, 0, 1], MS_CONVT, w_shape, fmt_dz,
+                 stride, pad)
+
+
+def pack_ncl32(x):
+    x = x.contiguous()
+    B, C, L = x.shape
+    y = torch.empty((B, C // 8, L, 8), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ms_pack_ncl_to_blk32(ptr(x), ptr(y), B, C, L, stream_ptr()),
+          "ms_pack_ncl_to_blk32")
+    return y
+
+
+def conv1d_direct_bwd(dy, y, x, w, stride, pad, groups, leaky, need_dx=True, need_dw=True,
+                      has_bias=True):
+    """backward of ops.conv1d_direct (zero padding) -> (dx, dw, dbias)"""
+    dy = dy.contiguous()
+    B, cin, lin = x.shape
+    cout, _, k = w.shape
+    L = _lib.lib()
+    dx = dw = db = None
+    if need_dx:
+        dx = torch.empty_like(x)
+        check(L.ms_conv1d_direct_dgrad(ptr(dy), ptr(y), ptr(w.contiguous()), ptr(dx), B, cin, cout,
+                                       lin, k, stride, pad, groups, int(leaky), stream_ptr()),
+              "ms_conv1d_direct_dgrad")
+    if need_dw:
+        dw = torch.zeros_like(w)
+        db = torch.zeros(cout, dtype=torch.float32, device=x.device) if has_bias else None
+        check(L.ms_conv1d_direct_wgrad(ptr(dy), ptr(y), ptr(x.contiguous()), ptr(dw), ptr(db), B,
+                                       cin, cout, lin, k, stride, pad, groups, int(leaky),
+                                       stream_ptr()), "ms_conv1d_direct_wgrad")
+    return dx, dw, db
+
+
+def conv_to_mono_bwd(dy, y_tanh, x32, w, ksize, pad, need_dx=True, need_dw=True, has_bias=True):
+    """backward of ops.conv_to_mono -> (dx32, dw, dbias)"""
+    dy = dy.contiguous()
+    B, C8, L, _ = x32.shape
+    dzm = torch.empty((B, 1, L), dtype=torch.float32, device=x32.device)
+    dx = torch.empty_like(x32) if need_dx else None
+    dw = torch.zeros_like(w) if need_dw else None
+    db = torch.zeros(1, dtype=torch.float32, device=x32.device) if (need_dw and has_bias) else None
+    check(_lib.lib().ms_conv_to_mono_bwd(ptr(dy), ptr(y_tanh), ptr(x32), ptr(w.contiguous()),
+                                         ptr(dzm), ptr(dx), ptr(dw), ptr(db), B, C8 * 8, L, ksize,
+                                         pad, stream_ptr()), "ms_conv_to_mono_bwd")
+    return dx, dw, db
+
+
+def avg_pool1d_bwd(dy, lin, ksize, stride, pad, count_include_pad=True):
+    dy = dy.contiguous()
+    B, C, _ = dy.shape
+    dx = torch.empty((B, C, lin), dtype=torch.float32, device=dy.device)
+    check(_lib.lib().ms_avg_pool1d_bwd(ptr(dy), ptr(dx), B * C, lin, ksize, stride, pad,
+                                       int(count_include_pad), stream_ptr()), "ms_avg_pool1d_bwd")
+    return dx
+
+
+def reduce_bwd(mode, a, b, weight, grad_out=None, need_a=True, need_b=False):
+    a = a.contiguous()
+    b = b.contiguous() if b is not None else None
+    da = torch.empty_like(a) if need_a else None
+    db = torch.empty_like(b) if (need_b and b is not None) else None
+    check(_lib.lib().ms_reduce_bwd(mode, ptr(a), ptr(b), a.numel(), float(weight), ptr(grad_out),
+                                   ptr(da), ptr(db), stream_ptr()), "ms_reduce_bwd")
+    return da, db
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    check(_lib.lib().ms_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq),
+                                  param.numel(), lr, beta1, beta2, eps, step, grad_scale,
+                                  stream_ptr()), "ms_adam_step")
