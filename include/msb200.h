@@ -112,6 +112,18 @@ ms_status ms_pack_ncl_to_blk16(const float* x, void* y16, int batch, int channel
                                int len, int pad, int pad_mode, int operand, void* stream);
 ms_status ms_unpack_blk32_to_ncl(const float* x32, float* y, int batch, int channels,
                                  int len, void* stream);
+/* split-precision operands.  ms_pack_ncl_split_blk16: NCL f32 (B,C,L) -> BLK 16-bit
+ * (B, terms*C/8, L, 8): channels [0,C) = hi = to16(s*x), [C,2C) = lo = to16(s*x - hi) and, for
+ * terms = 3, [2C,3C) = hi again.  ms_weight_split: w (cout,cin,k) -> (cout,3cin,k) = [s*w, s*w,
+ * s*w - to16(s*w)].  The 3C-channel conv [x_hi,x_lo,x_hi]*[W_hi,W_hi,W_lo] (alpha = 1/(s_x*s_w))
+ * equals x*W to ~2^-22; the power-of-two scales keep the lo terms out of the fp16 subnormals.
+ * Used for the dense 1024 -> 1024 layer of the discriminator (discriminator/full.py:19): its
+ * activations are bias-dominated and the real/fake gradients of a GAN step cancel to first
+ * order, so LeakyReLU masks and weight gradients hinge on differences of ~1e-4 relative. */
+ms_status ms_pack_ncl_split_blk16(const float* x, void* y16, int batch, int channels, int len,
+                                  int operand, int terms, float scale, void* stream);
+ms_status ms_weight_split(const float* w, float* out, int cout, int cin, int ksize, int operand,
+                          float scale, void* stream);
 /* space-to-depth along time: BLK 16-bit (B,C/8,src_rows,8) -> (B, s*C/8, ceil(len/s), 8) with
  * Y[u, i*C + c] = X[s*u + i, c] for s*u + i < len (0 beyond).  Turns the stride-s k7 convs of
  * featuresynth/discriminator/multiscale.py:83-88 into stride-1 convs over s*C channels. */
@@ -294,12 +306,14 @@ ms_status ms_weight_dgrad_view(const float* w, float* out, int kind, int cout, i
  *   mode MS_CONVT: ConvTranspose1d weight (cin=cm, cout, 2*stride); a16 = layer input,
  *                  x16 = space-to-depth dz (cn = stride*cout), shifts = {-1,0,1}.
  * fmt: MS_F16 | MS_BF16 of BOTH operands (tcgen05 kind::f16 does not mix them: a mixed
- * instruction descriptor raises an illegal-instruction fault on sm_100a).  dw = beta*dw + G. */
+ * instruction descriptor raises an illegal-instruction fault on sm_100a).  dw = beta*dw + G.
+ * fold = 2 (MS_CONV): x16 holds a two-term split (ms_pack_ncl_split_blk16) of the layer input in
+ * its two channel halves; the halves of G are summed into the cn/2-channel weight gradient. */
 size_t ms_wgrad_workspace_bytes(int batch, int cm, int cn, int la, int lx, int taps,
                                 const int* shifts);
 ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int cn, int la,
                        int lx, int taps, const int* shifts, int fmt, int mode, int stride,
-                       int pad, int cout, float beta, float* dw, void* workspace,
+                       int pad, int cout, int fold, float beta, float* dw, void* workspace,
                        size_t workspace_bytes, void* stream);
 /* 16-bit operand format conversion (fp16 forward activations -> bf16 for the weight-gradient
  * GEMM, whose other operand is a bf16 gradient) */

@@ -86,8 +86,12 @@ SIGNATURES = {
     "ms_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int,
                                             POINTER(c_int)]),
     "ms_wgrad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                             POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_float,
+                             POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                              c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ms_pack_ncl_split_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_float, c_void_p]),
+    "ms_weight_split": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                c_void_p]),
     "ms_blk16_convert": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "ms_pack_ncl_to_blk32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ms_conv1d_direct_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -1,0 +1,325 @@
+"""torch.autograd.Function wrappers that put the sm_100a kernels on the TRAINING path.
+
+The reference trains through plain autograd (featuresynth/train/train.py:26-74:
+`loss.backward()` then `optim.step()`); here every differentiable block of the hot path is a
+Function whose forward AND backward are calls into the C ABI (include/msb200.h):
+
+  * activations travel between blocks as a pair (x32, x16): the BLK f32 tensor is the
+    autograd-visible value (its gradient is BLK f32), the BLK f16 tensor is the tensor-core
+    operand image written by the producing kernel's epilogue (marked non-differentiable);
+  * backward of a dense conv = `ms_blk_act_bwd` (LeakyReLU' + bias gradient + bf16 operand)
+    -> `ms_wgrad_fwd` (tcgen05 time-reduction GEMM) and `ms_conv_fwd` on the transposed /
+    tap-reversed weights (input gradient, residual gradient added in its epilogue);
+  * the discriminator's grouped convs, the single-channel convs, pooling and the losses use
+    the direct fp32 kernels.
+
+torch is the tape and the allocator; no torch arithmetic runs on the path except autograd's
+own accumulation of gradients that fan in from several consumers.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, grad_ops, ops
+from ._lib import MS_CONV, MS_CONVT, MS_F16, check, ptr, stream_ptr
+
+GRAD_FMT = grad_ops.GRAD_FMT
+
+
+class WeightCache:
+    """Packed 16-bit images of one layer's weight: the forward image (fp16) and the
+    input-gradient image (bf16, transposed / tap-reversed); rebuilt when the parameter changes
+    in place (optimizer step, init, load_state_dict) or is moved."""
+
+    def __init__(self):
+        self._fwd = (None, None)
+        self._bwd = (None, None)
+
+    @staticmethod
+    def _key(w, desc):
+        return (w.data_ptr(), w._version, desc.kind, desc.cin, desc.cout, desc.ksize, desc.stride,
+                desc.operand)
+
+    def fwd(self, desc, w):
+        key = self._key(w, desc)
+        if self._fwd[0] != key:
+            self._fwd = (key, ops.pack_conv_weight(desc, w.detach()))
+        return self._fwd[1]
+
+    def fwd_dup(self, desc, w):
+        """forward image of [W_hi, W_hi, W_lo] along the input-channel axis (split precision)"""
+        key = self._key(w, desc)
+        if self._fwd[0] != key:
+            self._fwd = (key, ops.pack_conv_weight(desc, ops.weight_split(w.detach(), scale=SPLIT_SW)))
+        return self._fwd[1]
+
+    def dgrad(self, desc, w, kind, stride, pad):
+        key = self._key(w, desc)
+        if self._bwd[0] != key:
+            wv = grad_ops.weight_dgrad_view(w.detach(), kind, stride, pad)
+            self._bwd = (key, ops.pack_conv_weight(desc, wv))
+        return self._bwd[1]
+
+
+def _dgrad_conv(cache, w, dz16, kind, dilation, pad, stride, res32=None):
+    """input gradient (BLK f32) of a dense conv / transposed conv; `res32` added in the epilogue"""
+    B, _, L, _ = dz16.shape
+    if kind == MS_CONV:
+        cout, cin, k = w.shape
+        d = ops.conv_desc(MS_CONV, B, cout, cin, L, k, dilation, dilation * (k - 1) - pad,
+                          operand=GRAD_FMT)
+    else:
+        cin, cout, k = w.shape
+        d = ops.conv_desc(MS_CONV, B, stride * cout, cin, L, 3, 1, 1, operand=GRAD_FMT)
+    _, dx32 = ops.conv_fwd(d, dz16, cache.dgrad(d, w, kind, stride, pad), None, res32=res32,
+                           want16=False, want32=True)
+    return dx32
+
+
+class ConvBlk(Function):
+    """y = act(conv(x) + b) on channel-blocked tensors (stride-1 dilated Conv1d or k = 2*stride
+    ConvTranspose1d).  Returns (y32, y16)."""
+
+    @staticmethod
+    def forward(ctx, x32, x16, w, b, cache, kind, dilation, pad, stride, leaky):
+        B, _, L, _ = x16.shape
+        if kind == MS_CONV:
+            cout, cin, k = w.shape
+        else:
+            cin, cout, k = w.shape
+        d = ops.conv_desc(kind, B, cin, cout, L, k, dilation, pad, stride, leaky=leaky)
+        y16, y32 = ops.conv_fwd(d, x16, cache.fwd(d, w), b, want16=True, want32=True)
+        ctx.save_for_backward(x16, w, y16)
+        ctx.cfg = (cache, kind, dilation, pad, stride, leaky, b is not None)
+        ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, _unused):
+        x16, w, y16 = ctx.saved_tensors
+        cache, kind, dilation, pad, stride, leaky, has_bias = ctx.cfg
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        s2d = stride if kind == MS_CONVT else 1
+        dz16, db = grad_ops.act_bwd(dy32, sign16=y16 if leaky else None,
+                                    want_bias=has_bias and ctx.needs_input_grad[3], s2d=s2d)
+        dw = dx32 = None
+        if need_w:
+            if kind == MS_CONV:
+                dw = grad_ops.conv_wgrad(dz16, x16, tuple(w.shape), dilation, pad)
+            else:
+                dw = grad_ops.convt_wgrad(x16, dz16, tuple(w.shape), stride, pad)
+        if need_x:
+            dx32 = _dgrad_conv(cache, w, dz16, kind, dilation, pad, stride)
+        return dx32, None, dw, db, None, None, None, None, None, None
+
+
+class ResidualAtomBlk(Function):
+    """x + leaky(conv_k3_pad1(leaky(conv_k3_dil_d(x)))), featuresynth/util/modules.py:384-388.
+    Returns (y32, y16)."""
+
+    @staticmethod
+    def forward(ctx, x32, x16, w1, b1, w2, b2, cache1, cache2, dilation):
+        B, C8, L, _ = x16.shape
+        C = C8 * 8
+        d1 = ops.conv_desc(MS_CONV, B, C, C, L, 3, dilation, dilation, leaky=True)
+        d2 = ops.conv_desc(MS_CONV, B, C, C, L, 3, 1, 1, leaky=True)
+        h16, _ = ops.conv_fwd(d1, x16, cache1.fwd(d1, w1), b1)
+        y16, y32 = ops.conv_fwd(d2, h16, cache2.fwd(d2, w2), b2, res32=x32, want16=True,
+                                want32=True)
+        ctx.save_for_backward(x32, x16, h16, y32, w1, w2)
+        ctx.cfg = (cache1, cache2, dilation)
+        ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, _unused):
+        x32, x16, h16, y32, w1, w2 = ctx.saved_tensors
+        cache1, cache2, dilation = ctx.cfg
+        need_w = ctx.needs_input_grad[2]
+        dy32 = dy32.contiguous()
+        # outer LeakyReLU: its output is y - x (sign of the fp32 difference)
+        dz2, db2 = grad_ops.act_bwd(dy32, ya32=y32, yb32=x32, want_bias=need_w)
+        dw2 = grad_ops.conv_wgrad(dz2, h16, tuple(w2.shape), 1, 1) if need_w else None
+        dh32 = _dgrad_conv(cache2, w2, dz2, MS_CONV, 1, 1, 1)
+        dz1, db1 = grad_ops.act_bwd(dh32, sign16=h16, want_bias=need_w)
+        dw1 = grad_ops.conv_wgrad(dz1, x16, tuple(w1.shape), dilation, dilation) if need_w else None
+        dx32 = None
+        if ctx.needs_input_grad[0]:
+            dx32 = _dgrad_conv(cache1, w1, dz1, MS_CONV, dilation, dilation, 1, res32=dy32)
+        return dx32, None, dw1, db1, dw2, db2, None, None, None
+
+
+class MonoConv(Function):
+    """(B,C,L) BLK f32 -> (B,1,L): single-output-channel conv (+ tanh): the generator's last
+    layer (generator/full.py:43-44) and the discriminator's judge (discriminator/full.py:22)."""
+
+    @staticmethod
+    def forward(ctx, x32, w, b, ksize, pad, tanh_out):
+        y = ops.conv_to_mono(x32, w, b, ksize, pad, tanh_out)
+        ctx.save_for_backward(x32, w, y)
+        ctx.cfg = (ksize, pad, tanh_out, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x32, w, y = ctx.saved_tensors
+        ksize, pad, tanh_out, has_bias = ctx.cfg
+        dx32, dw, db = grad_ops.conv_to_mono_bwd(dy, y if tanh_out else None, x32, w, ksize, pad,
+                                                 need_dx=ctx.needs_input_grad[0],
+                                                 need_dw=ctx.needs_input_grad[1],
+                                                 has_bias=has_bias)
+        return dx32, dw, (db if ctx.needs_input_grad[2] else None), None, None, None
+
+
+class PackBlk32(Function):
+    """NCL f32 -> BLK f32 (entry of a stand-alone block called with (B,C,L) tensors)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return grad_ops.pack_ncl32(x)
+
+    @staticmethod
+    def backward(ctx, dy32):
+        return ops.unpack_blk32(dy32.contiguous())
+
+
+class UnpackBlk32(Function):
+    """BLK f32 -> NCL f32 (feature maps handed to the losses)."""
+
+    @staticmethod
+    def forward(ctx, x32):
+        return ops.unpack_blk32(x32)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return grad_ops.pack_ncl32(dy)
+
+
+class DirectConv(Function):
+    """grouped / strided fp32 conv1d (+ LeakyReLU), NCL in / out (discriminator/full.py:13-18)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, groups, leaky):
+        y = ops.conv1d_direct(x, w, b, stride, pad, groups, leaky)
+        ctx.save_for_backward(x, w, y)
+        ctx.cfg = (stride, pad, groups, leaky, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        stride, pad, groups, leaky, has_bias = ctx.cfg
+        dx, dw, db = grad_ops.conv1d_direct_bwd(dy, y if leaky else None, x, w, stride, pad, groups,
+                                                leaky, need_dx=ctx.needs_input_grad[0],
+                                                need_dw=ctx.needs_input_grad[1], has_bias=has_bias)
+        return dx, dw, (db if ctx.needs_input_grad[2] else None), None, None, None, None
+
+
+# power-of-two operand scales of the split-precision layer: keep the lo terms of activations
+# (|x| >~ 4e-3) and weights (|w| >~ 1e-3) normal in fp16, overflow only beyond |x| ~ 1e3 / |w| ~ 250
+SPLIT_SX, SPLIT_SW = 64.0, 256.0
+
+
+def dense_split_fwd(x, w, b, cache, pad, leaky, want16=True):
+    """LeakyReLU(dense Conv1d) in split precision: [x_hi, x_lo, x_hi] * [W_hi, W_hi, W_lo] over 3C
+    fp16 channels = x*W to ~2^-22.  The discriminator's top-layer activations are bias-dominated
+    and the real / fake gradients of a GAN step cancel to first order: which LeakyReLU masks
+    differ between the two batches -- and with them the whole gradient of the top layers --
+    hinges on differences of ~1e-4 relative, below a single fp16 rounding of x or W."""
+    B, C, L = x.shape
+    cout, _, k = w.shape
+    x16 = ops.pack_ncl_split(x, terms=3, scale=SPLIT_SX)
+    d = ops.conv_desc(MS_CONV, B, 3 * C, cout, L, k, 1, pad, leaky=leaky,
+                      alpha=1.0 / (SPLIT_SX * SPLIT_SW))
+    return ops.conv_fwd(d, x16, cache.fwd_dup(d, w), b, want16=want16, want32=True)
+
+
+class DenseConvNCL(Function):
+    """NCL f32 in -> BLK f32 out: LeakyReLU(dense Conv1d) on the tcgen05 kernel
+    (discriminator/full.py:19, the 1024 -> 1024 k5 layer), split-precision input."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, cache, pad, leaky):
+        y16, y32 = dense_split_fwd(x, w, b, cache, pad, leaky)
+        ctx.save_for_backward(x, w, y16)
+        ctx.cfg = (cache, pad, leaky, b is not None)
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy32):
+        x, w, y16 = ctx.saved_tensors
+        cache, pad, leaky, has_bias = ctx.cfg
+        need_w = ctx.needs_input_grad[1]
+        dz16, db = grad_ops.act_bwd(dy32, sign16=y16 if leaky else None,
+                                    want_bias=has_bias and ctx.needs_input_grad[2])
+        dw = None
+        if need_w:
+            xs = ops.pack_ncl_split(x, operand=GRAD_FMT)             # (hi, lo) in the gradient format
+            dw = grad_ops.conv_wgrad(dz16, xs, tuple(w.shape), 1, pad, fmt_x=GRAD_FMT, fold=2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.unpack_blk32(_dgrad_conv(cache, w, dz16, MS_CONV, 1, pad, 1))
+        return dx, dw, db, None, None, None
+
+
+class AvgPool(Function):
+    @staticmethod
+    def forward(ctx, x, ksize, stride, pad, include_pad):
+        ctx.cfg = (x.shape[-1], ksize, stride, pad, include_pad)
+        return ops.avg_pool1d(x, ksize, stride, pad, include_pad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lin, ksize, stride, pad, include_pad = ctx.cfg
+        return grad_ops.avg_pool1d_bwd(dy, lin, ksize, stride, pad, include_pad), None, None, None, None
+
+
+class WeightedLoss(Function):
+    """sum_i weight_i * L_{mode_i}(a_i, b_i) as ONE device scalar (featuresynth/loss/loss.py);
+    spec: list of (mode, index of a, index of b or -1, weight)."""
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        dev = tensors[0].device
+        out = torch.zeros(1, dtype=torch.float32, device=dev)
+        ws = torch.empty(_lib.lib().ms_reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
+        keep = [t.contiguous() for t in tensors]
+        for mode, ia, ib, weight in spec:
+            a = keep[ia]
+            b = keep[ib] if ib >= 0 else None
+            check(_lib.lib().ms_reduce_fwd(mode, ptr(a), ptr(b), a.numel(), float(weight), ptr(out),
+                                           1, ptr(ws), stream_ptr()), "ms_reduce_fwd")
+        ctx.spec = spec
+        ctx.save_for_backward(*keep)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        tensors = ctx.saved_tensors
+        g = g.contiguous().reshape(1)
+        grads = [None] * len(tensors)
+
+        def acc(i, t):
+            grads[i] = t if grads[i] is None else grads[i] + t
+
+        for mode, ia, ib, weight in ctx.spec:
+            need_a = ctx.needs_input_grad[1 + ia]
+            need_b = ib >= 0 and ctx.needs_input_grad[1 + ib]
+            if not (need_a or need_b):
+                continue
+            da, db = grad_ops.reduce_bwd(mode, tensors[ia], tensors[ib] if ib >= 0 else None, weight,
+                                         g, need_a, need_b)
+            if need_a:
+                acc(ia, da)
+            if need_b:
+                acc(ib, db)
+        return (None, *grads)
+
+
+def needs_grad(module, *inputs):
+    """True when the call must be recorded on the autograd tape."""
+    if not torch.is_grad_enabled():
+        return False
+    return any(t is not None and t.requires_grad for t in inputs) or \
+        any(p.requires_grad for p in module.parameters())

@@ -228,24 +228,30 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
 }
 
-// out[map(t, m, n)] = beta * out[...] + sum_split part[split][t][m][n]   (fixed order)
-//   mode MS_CONV : Conv1d weight (Cout = Cm, Cin = Cn, K = taps):   (m*Cn + n)*K + t
+// out[map(t, m, n)] = beta * out[...] + sum_split sum_f part[split][t][m][n + f*Cn/fold]
+// (fixed order).  fold = 2: the X operand carried a two-term (hi, lo) split of the layer input in
+// its two channel halves -- both halves are gradients of the same weight.
+//   mode MS_CONV : Conv1d weight (Cout = Cm, Cin = Cn/fold, K = taps):   (m*Cin + n)*K + t
 //   mode MS_CONVT: ConvTranspose1d weight (Cin = Cm, Cout, K = 2s); n = r*Cout + co,
 //                  k = s*shift_t + r + pad (taps whose k falls outside [0, K) do not exist)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                    int nsplit, int taps, int Cm, int Cn, int mode, int stride,
-                                    int pad, int cout, int shift0, float beta, size_t total) {
+                                    int nsplit, int taps, int Cm, int Cn, int fold, int mode,
+                                    int stride, int pad, int cout, int shift0, float beta,
+                                    size_t total) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
+  const int cn_out = Cn / fold;
+  const int n = static_cast<int>(i % cn_out);
+  const int m = static_cast<int>((i / cn_out) % Cm);
+  const int t = static_cast<int>(i / (static_cast<size_t>(cn_out) * Cm));
   const size_t plane = static_cast<size_t>(taps) * Cm * Cn;
+  const size_t src = (static_cast<size_t>(t) * Cm + m) * Cn + n;
   float acc = 0.f;
-  for (int s = 0; s < nsplit; ++s) acc += __ldg(part + s * plane + i);
-  const int n = static_cast<int>(i % Cn);
-  const int m = static_cast<int>((i / Cn) % Cm);
-  const int t = static_cast<int>(i / (static_cast<size_t>(Cn) * Cm));
+  for (int s = 0; s < nsplit; ++s)
+    for (int f = 0; f < fold; ++f) acc += __ldg(part + s * plane + src + f * cn_out);
   size_t o;
   if (mode == MS_CONV) {
-    o = (static_cast<size_t>(m) * Cn + n) * taps + t;
+    o = (static_cast<size_t>(m) * cn_out + n) * taps + t;
   } else {
     const int r = n / cout, co = n - r * cout;
     const int k = stride * (shift0 + t) + r + pad;
@@ -328,7 +334,7 @@ size_t ms_wgrad_workspace_bytes(int batch, int cm, int cn, int la, int lx, int t
 
 ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int cn, int la,
                        int lx, int taps, const int* shifts, int fmt, int mode, int stride,
-                       int pad, int cout, float beta, float* dw, void* workspace,
+                       int pad, int cout, int fold, float beta, float* dw, void* workspace,
                        size_t workspace_bytes, void* stream) {
   WgradCfg c;
   if (a16 == nullptr || x16 == nullptr || dw == nullptr || shifts == nullptr ||
@@ -336,6 +342,7 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
     return MS_ERR_INVALID;
   if (fmt != MS_F16 && fmt != MS_BF16) return MS_ERR_INVALID;
   if (mode != MS_CONV && mode != MS_CONVT) return MS_ERR_INVALID;
+  if (fold != 1 && !(fold == 2 && mode == MS_CONV && cn % 2 == 0)) return MS_ERR_INVALID;
   if (mode == MS_CONVT) {
     if (stride < 1 || cout < 1 || cn != stride * cout) return MS_ERR_INVALID;
     for (int t = 1; t < taps; ++t)
@@ -371,9 +378,9 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
   wgrad_kernel<<<grid, kWgThreads, c.smem_bytes, st>>>(p);
   ms_status s = after_launch("wgrad_kernel");
   if (s != MS_OK) return s;
-  const size_t total = static_cast<size_t>(taps) * cm * cn;
+  const size_t total = static_cast<size_t>(taps) * cm * (cn / fold);
   wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
-      p.part, dw, c.ksplit, taps, cm, cn, mode, stride, pad, cout, shifts[0], beta, total);
+      p.part, dw, c.ksplit, taps, cm, cn, fold, mode, stride, pad, cout, shifts[0], beta, total);
   return after_launch("wgrad_reduce_kernel");
 }
 

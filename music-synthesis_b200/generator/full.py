@@ -8,8 +8,9 @@ with fused bias / LeakyReLU / residual epilogues and an fp32 residual stream.
 import torch
 from torch import nn
 
+from .. import autograd as ag
 from .. import ops
-from .._lib import MS_F16, MsbError
+from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
 from ..util.modules import ResidualStack
 
 
@@ -49,6 +50,7 @@ class MelGanGenerator(nn.Module):
         self._weights = None
         self._weights_key = None
         self._workspace = None
+        self._caches = {i: ag.WeightCache() for i in (1, 3, 6, 9, 12)}
 
     # ---- packed-weight cache ------------------------------------------------
     def _packed_weights(self):
@@ -115,12 +117,29 @@ class MelGanGenerator(nn.Module):
         comp.wait_stream(s_out)
         return out
 
+    def _forward_train(self, x):
+        """autograd-recorded layer-wise path (training): every block is a Function whose
+        forward / backward are C-ABI calls; saves the 16-bit operand images for the backward."""
+        if x.requires_grad:
+            raise MsbError("gradients w.r.t. the conditioning features are not on this path")
+        if self.operand != MS_F16:
+            raise MsbError("training runs with fp16 forward operands")
+        main = self.main
+        x16 = ops.pack_ncl(x, 3, 1)                                  # ReflectionPad1d(3)
+        h32, h16 = ag.ConvBlk.apply(None, x16, main[1].weight, main[1].bias, self._caches[1],
+                                    MS_CONV, 1, 0, 1, True)
+        for idx in (3, 6, 9, 12):
+            ct = main[idx]
+            h32, h16 = ag.ConvBlk.apply(h32, h16, ct.weight, ct.bias, self._caches[idx], MS_CONVT,
+                                        1, ct.padding[0], ct.stride[0], True)
+            h32, h16 = main[idx + 2].forward_blocked_train(h32, h16)
+        last = main[15]
+        return ag.MonoConv.apply(h32, last.weight, last.bias, 7, 3, True)
+
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or
-                                        any(p.requires_grad for p in self.parameters())):
-            raise MsbError("MelGanGenerator (sm_100a path) is forward-only in this build: "
-                           "call under torch.no_grad()")
         if x.dim() != 3 or x.shape[1] != self.in_channels:
             raise MsbError("expected (B, %d, T) features" % self.in_channels)
+        if ag.needs_grad(self, x):
+            return self._forward_train(x.contiguous())
         ws = self._get_workspace(x.shape[0], x.shape[2], x.device)
         return ops.melgan_generator_fwd(self._packed_weights(), x, ws)

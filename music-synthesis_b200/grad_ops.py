@@ -10,7 +10,7 @@ from ._lib import MS_CONV, MS_CONVT, MS_F16, MS_BF16, check, ptr, stream_ptr
 # 16-bit format of the backward GEMMs: bf16 has the range of fp32, so the small GAN gradients need
 # no loss scaling.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, so the weights (dgrad)
 # and the saved forward activations (wgrad) are converted to bf16 for the backward pass.
-GRAD_FMT = MS_BF16
+GRAD_FMT = MS_F16 if __import__('os').environ.get('MSB_GRAD_FMT') == 'f16' else MS_BF16
 
 
 def convert16(x16, src_fmt, dst_fmt):
@@ -79,7 +79,7 @@ def _workspace(nbytes, device):
     return buf
 
 
-def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0):
+def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0, fold=1):
     """Weight gradient (reference layout `w_shape`) on the tcgen05 time-reduction GEMM."""
     B, Cm8, La, _ = a16.shape
     _, Cn8, Lx, _ = x16.shape
@@ -93,16 +93,17 @@ def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0):
     dw = torch.empty(w_shape, dtype=torch.float32, device=a16.device)
     cout = w_shape[1] if mode == MS_CONVT else 0
     check(L.ms_wgrad_fwd(ptr(a16), ptr(x16), B, Cm8 * 8, Cn8 * 8, La, Lx, taps, sh, fmt,
-                         mode, stride, pad, cout, 0.0, ptr(dw), ptr(ws), ws.numel(), stream_ptr()),
+                         mode, stride, pad, cout, fold, 0.0, ptr(dw), ptr(ws), ws.numel(), stream_ptr()),
           "ms_wgrad_fwd")
     return dw
 
 
-def conv_wgrad(dz16, x16, w_shape, dilation=1, pad=0, fmt_dz=GRAD_FMT, fmt_x=MS_F16):
-    """dW of a stride-1 Conv1d: dz16 (B,Cout/8,Lout,8), x16 (B,Cin/8,Lin,8)."""
+def conv_wgrad(dz16, x16, w_shape, dilation=1, pad=0, fmt_dz=GRAD_FMT, fmt_x=MS_F16, fold=1):
+    """dW of a stride-1 Conv1d: dz16 (B,Cout/8,Lout,8), x16 (B,fold*Cin/8,Lin,8); fold = 2:
+    x16 is a two-term split (ops.pack_ncl_split) of the layer input."""
     k = w_shape[2]
     return wgrad(dz16, convert16(x16, fmt_x, fmt_dz), [t * dilation - pad for t in range(k)],
-                 MS_CONV, w_shape, fmt_dz)
+                 MS_CONV, w_shape, fmt_dz, fold=fold)
 
 
 def convt_wgrad(x16, dzs16, w_shape, stride, pad, fmt_dz=GRAD_FMT, fmt_x=MS_F16):

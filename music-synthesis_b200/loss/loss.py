@@ -3,59 +3,70 @@
 Same function names and signatures; each returns a 0-dim CUDA tensor.  The composite
 losses accumulate every term into ONE device scalar through `ms_reduce_fwd` (deterministic
 two-stage reductions, no atomics) instead of materialising 18-38 intermediate tensors.
-Forward only in this round (no autograd).
+Differentiable: the gradient of every term is one `ms_reduce_bwd` launch.
 """
 import torch
 
 from .. import _lib
-from .._lib import check, ptr, stream_ptr
+from ..autograd import WeightedLoss
 
 L1, HINGE_D, HINGE_G, LSQ_D, LSQ_G = 0, 1, 2, 3, 4
 
 
 class _Acc:
-    """A device scalar that sums weighted reductions."""
+    """Collects weighted reduction terms; `value()` evaluates them into ONE device scalar
+    through `WeightedLoss` (forward: ms_reduce_fwd per term; backward: ms_reduce_bwd)."""
 
-    def __init__(self, device):
-        self.out = torch.zeros(1, dtype=torch.float32, device=device)
-        self.ws = torch.empty(_lib.lib().ms_reduce_workspace_bytes(), dtype=torch.uint8,
-                              device=device)
+    def __init__(self, device=None):
+        self.tensors = []
+        self.index = {}
+        self.spec = []
+
+    def _slot(self, t):
+        _lib.require_cuda(t, "loss operand")
+        k = id(t)
+        if k not in self.index:
+            self.index[k] = len(self.tensors)
+            self.tensors.append(t)
+        return self.index[k]
 
     def add(self, mode, a, b=None, weight=1.0):
-        _lib.require_cuda(a, "a")
-        a = a.contiguous()
-        if b is not None:
-            _lib.require_cuda(b, "b")
-            b = b.contiguous()
-            if b.numel() != a.numel():
-                raise _lib.MsbError("loss operands differ in size")
-        check(_lib.lib().ms_reduce_fwd(mode, ptr(a), ptr(b), a.numel(), float(weight),
-                                       ptr(self.out), 1, ptr(self.ws), stream_ptr()),
-              "ms_reduce_fwd")
+        if b is not None and b.numel() != a.numel():
+            raise _lib.MsbError("loss operands differ in size")
+        self.spec.append((mode, self._slot(a), self._slot(b) if b is not None else -1,
+                          float(weight)))
         return self
 
     def value(self):
-        return self.out.reshape(())
+        return WeightedLoss.apply(tuple(self.spec), *self.tensors)
+
+
+def _term(acc, mode, a, b, w):
+    """sub-loss called stand-alone (returns its value) or as a term of a composite loss"""
+    if acc is not None:
+        acc.add(mode, a, b, w)
+        return None
+    return _Acc().add(mode, a, b, w).value()
 
 
 def least_squares_generator_loss(j, _acc=None, _w=1.0):
     """loss.py:5-6"""
-    return (_acc or _Acc(j.device)).add(LSQ_G, j, None, _w).value()
+    return _term(_acc, LSQ_G, j, None, _w)
 
 
 def hinge_generator_loss(j, _acc=None, _w=1.0):
     """loss.py:9-10"""
-    return (_acc or _Acc(j.device)).add(HINGE_G, j, None, _w).value()
+    return _term(_acc, HINGE_G, j, None, _w)
 
 
 def least_squares_disc_loss(r_j, f_j, _acc=None, _w=1.0):
     """loss.py:13-14"""
-    return (_acc or _Acc(r_j.device)).add(LSQ_D, r_j, f_j, _w).value()
+    return _term(_acc, LSQ_D, r_j, f_j, _w)
 
 
 def hinge_discriminator_loss(r_j, f_j, _acc=None, _w=1.0):
     """loss.py:17-18"""
-    return (_acc or _Acc(r_j.device)).add(HINGE_D, r_j, f_j, _w).value()
+    return _term(_acc, HINGE_D, r_j, f_j, _w)
 
 
 def mel_gan_disc_loss(real_judgements, fake_judgements, gan_loss=hinge_discriminator_loss):

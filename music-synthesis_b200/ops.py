@@ -38,6 +38,28 @@ def pack_ncl(x, pad=0, pad_mode=0, operand=MS_F16):
     return y
 
 
+def pack_ncl_split(x, operand=MS_F16, terms=2, scale=1.0):
+    """(B,C,L) f32 -> (B,terms*C/8,L,8) 16-bit split: channels [0,C) hi, [C,2C) lo, [2C,3C) hi."""
+    _lib.require_cuda(x, "x")
+    x = x.contiguous()
+    B, C, L = x.shape
+    y = torch.empty((B, terms * C // 8, L, 8), dtype=torch.int16, device=x.device)
+    check(_lib.lib().ms_pack_ncl_split_blk16(ptr(x), ptr(y), B, C, L, operand, terms,
+                                             float(scale), stream_ptr()), "ms_pack_ncl_split_blk16")
+    return y
+
+
+def weight_split(w, operand=MS_F16, scale=1.0):
+    """(Cout,Cin,K) -> (Cout,3Cin,K) = [w, w, w - to16(w)] (see ms_weight_split)"""
+    w = w.contiguous()
+    cout, cin, k = w.shape
+    out = torch.empty((cout, 3 * cin, k), dtype=torch.float32, device=w.device)
+    check(_lib.lib().ms_weight_split(ptr(w), ptr(out), cout, cin, k, operand, float(scale),
+                                     stream_ptr()),
+          "ms_weight_split")
+    return out
+
+
 def unpack_blk32(x32):
     B, C8, L, _ = x32.shape
     y = torch.empty((B, C8 * 8, L), dtype=torch.float32, device=x32.device)

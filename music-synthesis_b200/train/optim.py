@@ -1,0 +1,92 @@
+"""Adam with the reference's configuration (featuresynth/experiment/experiment.py:111-117:
+`Adam(parameters, lr=1e-4, betas=(0.5, 0.9))`, eps 1e-8, no weight decay / amsgrad) as ONE
+kernel launch per step over a flat parameter buffer.
+
+Construction re-points every parameter (and its .grad) at a slice of one contiguous fp32
+buffer -- the layout a data-parallel step wants anyway: the gradient all-reduce of the network
+being stepped is a single NCCL call over NVLink on the flat gradient buffer
+(featuresynth trains single-device; SURVEY section 8(e) defines the data-parallel contract:
+sum over ranks, then 1/world_size because the losses are batch means).
+"""
+import torch
+import torch.distributed as dist
+
+from .. import grad_ops
+
+
+class Adam:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("optimizer got an empty parameter list")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise ValueError("parameters must live on a CUDA device (no CPU path)")
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.process_group = process_group
+        self.step_count = 0
+        n = sum(p.numel() for p in self.params)
+        # 16-byte aligned slices so the packed-weight kernels' vector loads stay aligned
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, offs):
+                view = self.flat[o:o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        self.numel = n
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+        for p in self.params:          # someone may have dropped the views (p.grad = None)
+            if p.grad is None or p.grad.data_ptr() < self.flat_grad.data_ptr() or \
+                    p.grad.data_ptr() >= self.flat_grad.data_ptr() + self.flat_grad.numel() * 4:
+                self._rebind()
+                break
+
+    def _rebind(self):
+        o = 0
+        for p in self.params:
+            g = self.flat_grad[o:o + p.numel()].view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)
+            p.grad = g
+            o += (p.numel() + 3) // 4 * 4
+
+    def world_size(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(self.process_group)
+        return 1
+
+    def all_reduce_grads(self):
+        """sum the flat gradient over the data-parallel ranks (one collective)"""
+        if self.world_size() > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def step(self):
+        world = self.world_size()
+        if world > 1:
+            self.all_reduce_grads()
+        self.step_count += 1
+        grad_ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
+                           self.betas[0], self.betas[1], self.eps, self.step_count, 1.0 / world)
+        # the kernel wrote the parameters behind autograd's back: bump the version counters so
+        # the packed 16-bit weight images are rebuilt
+        for p in self.params:
+            torch.autograd.graph.increment_version(p)
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

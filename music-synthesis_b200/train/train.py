@@ -1,0 +1,107 @@
+"""Drop-in mirrors of featuresynth/train/train.py:8-74 (GeneratorTrainer / DiscriminatorTrainer):
+same constructor arguments, `train(samples, features)` contract and return dictionaries.
+
+One optimiser step each, same arithmetic as the reference; two pieces of work the reference does
+and then throws away are skipped:
+  * DiscriminatorTrainer: the reference back-propagates through the generator and discards
+    those gradients (zero_grad at the next step, App. E.4) -- here the fake batch comes from the
+    fused inference kernels under no_grad;
+  * GeneratorTrainer: the discriminator's weight gradients are not formed (its parameters are
+    frozen for the call) and the real batch runs without a tape.
+`exact_reference_grads=True` restores the reference's behaviour (all .grad fields populated).
+Data-parallel: when torch.distributed is initialised, the gradients of the network being
+stepped are summed over ranks before the step (optimisers from .optim do it in one NCCL call).
+"""
+import contextlib
+
+import torch
+import torch.distributed as dist
+
+from ..loss.loss import hinge_discriminator_loss, hinge_generator_loss
+from ..util.modules import zero_grad
+
+
+@contextlib.contextmanager
+def _frozen(module):
+    flags = [p.requires_grad for p in module.parameters()]
+    for p in module.parameters():
+        p.requires_grad_(False)
+    try:
+        yield
+    finally:
+        for p, f in zip(module.parameters(), flags):
+            p.requires_grad_(f)
+
+
+def _sync_grads(optim, module):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    if hasattr(optim, "all_reduce_grads"):
+        return                                   # .optim.Adam reduces inside step()
+    world = dist.get_world_size()
+    for p in module.parameters():
+        if p.grad is not None:
+            dist.all_reduce(p.grad)
+            p.grad.div_(world)
+
+
+class GeneratorTrainer(object):
+    def __init__(self, generator, g_optim, discriminator, d_optim, loss,
+                 sub_loss=hinge_generator_loss, exact_reference_grads=False):
+        super().__init__()
+        self.sub_loss = sub_loss
+        self.loss = loss
+        self.d_optim = d_optim
+        self.discriminator = discriminator
+        self.g_optim = g_optim
+        self.generator = generator
+        self.exact_reference_grads = exact_reference_grads
+
+    def train(self, samples, features):
+        zero_grad(self.g_optim, self.d_optim)
+        fake = self.generator(features)
+        if self.exact_reference_grads:
+            f_features, f_score = self.discriminator(fake, features)
+            r_features, r_score = self.discriminator(samples, features)
+        else:
+            with _frozen(self.discriminator):
+                f_features, f_score = self.discriminator(fake, features)
+                with torch.no_grad():
+                    r_features, r_score = self.discriminator(samples, features)
+        loss = self.loss(r_features, f_features, r_score, f_score, gan_loss=self.sub_loss)
+        loss.backward()
+        _sync_grads(self.g_optim, self.generator)
+        self.g_optim.step()
+        try:
+            fake = fake.data.cpu().numpy()
+        except AttributeError:
+            fake = {k: v.data.cpu().numpy() for k, v in fake.items()}
+        return {'g_loss': loss.item(), 'fake': fake}
+
+
+class DiscriminatorTrainer(object):
+    def __init__(self, generator, g_optim, discriminator, d_optim, loss,
+                 sub_loss=hinge_discriminator_loss, exact_reference_grads=False):
+        super().__init__()
+        self.sub_loss = sub_loss
+        self.loss = loss
+        self.d_optim = d_optim
+        self.discriminator = discriminator
+        self.g_optim = g_optim
+        self.generator = generator
+        self.exact_reference_grads = exact_reference_grads
+
+    def train(self, samples, features):
+        zero_grad(self.g_optim, self.d_optim)
+        if self.exact_reference_grads:
+            fake = self.generator(features)
+        else:
+            with torch.no_grad():
+                fake = self.generator(features)
+        _, f_score = self.discriminator(fake, features)
+        _, r_score = self.discriminator(samples, features)
+        loss = self.loss(r_score, f_score, gan_loss=self.sub_loss)
+        loss.backward()
+        _sync_grads(self.d_optim, self.discriminator)
+        self.d_optim.step()
+        return {'d_loss': loss.item()}

@@ -4,11 +4,13 @@ Same class names, constructor signatures, forward contracts and state-dict keys 
 the reference; parameters live in ordinary nn.Conv1d / nn.ConvTranspose1d containers
 (so `module.apply(weights_init)`, `.parameters()`, `.state_dict()` and checkpoints
 behave identically) but `forward` dispatches to the tcgen05 kernels through the C ABI.
-Inference only in this round (no autograd through the CUDA path yet).
+Under torch.no_grad() the fused inference kernels run; with autograd enabled the same modules
+record torch.autograd.Functions whose forward and backward are C-ABI calls (see ../autograd.py).
 """
 import torch
 from torch import nn
 
+from .. import autograd as ag
 from .. import ops
 from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
 
@@ -38,7 +40,7 @@ class _PackedConv:
 def _no_grad_check(*tensors):
     if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
         raise MsbError(
-            "the sm_100a path is forward-only in this build: call under torch.no_grad()")
+            "this block has no backward on the sm_100a path yet: call under torch.no_grad()")
 
 
 class ResidualAtom(nn.Module):
@@ -57,6 +59,15 @@ class ResidualAtom(nn.Module):
         second = nn.Conv1d(channels, channels, 3, 1, 1)
         self.main = nn.Sequential(first, second)
         self._packed = (_PackedConv(), _PackedConv())
+        self._cache = (ag.WeightCache(), ag.WeightCache())
+
+    def forward_blocked_train(self, x32, x16):
+        """autograd-recorded form: (x32, x16) -> (y32, y16)"""
+        if self.operand != MS_F16:
+            raise MsbError("training runs with fp16 forward operands")
+        c1, c2 = self.main[0], self.main[1]
+        return ag.ResidualAtomBlk.apply(x32, x16, c1.weight, c1.bias, c2.weight, c2.bias,
+                                        self._cache[0], self._cache[1], self.dilation)
 
     def forward_blocked(self, x16, x32):
         """(x16, x32) channel-blocked in -> channel-blocked out (no layout conversion)."""
@@ -71,7 +82,9 @@ class ResidualAtom(nn.Module):
                             want16=True, want32=True)
 
     def forward(self, x):
-        _no_grad_check(x, *self.parameters())
+        if ag.needs_grad(self, x):
+            y32, _ = self.forward_blocked_train(ag.PackBlk32.apply(x), ops.pack_ncl(x.detach()))
+            return ag.UnpackBlk32.apply(y32)
         x16 = ops.pack_ncl(x, operand=self.operand)
         x32 = _blk32_from_ncl(x)
         _, y32 = self.forward_blocked(x16, x32)
@@ -105,8 +118,15 @@ class ResidualStack(nn.Module):
             self._blob_key = key
         return self._blob
 
+    def forward_blocked_train(self, x32, x16):
+        for atom in self.main:
+            x32, x16 = atom.forward_blocked_train(x32, x16)
+        return x32, x16
+
     def forward(self, x):
-        _no_grad_check(x, *self.parameters())
+        if ag.needs_grad(self, x):
+            y32, _ = self.forward_blocked_train(ag.PackBlk32.apply(x), ops.pack_ncl(x.detach()))
+            return ag.UnpackBlk32.apply(y32)
         if (len(self.dilations) == 3 and ops.resstack_supported(self.channels)
                 and sum(self.dilations) + 3 <= 16):
             # one fused kernel: activations in SMEM, fp32 residual stream in TMEM

@@ -204,7 +204,64 @@ def realmelgan():
     save("realmelgan_disc_n4096", **arrays)
 
 
+def train_step():
+    """One DiscriminatorTrainer.train then one GeneratorTrainer.train (the `cycle` order of
+    experiment/experiment.py:141-144) of the UNMODIFIED reference trainers
+    (featuresynth/train/train.py:8-74) with torch Adam(1e-4, (0.5, 0.9)) on MelGanGenerator +
+    MelGanDiscriminator (behind a 2-argument wrapper, the trainers pass the features too)."""
+    ref_harness.load()
+    from featuresynth.generator.full import MelGanGenerator
+    from featuresynth.discriminator.melgan import MelGanDiscriminator
+    from featuresynth.train.train import GeneratorTrainer, DiscriminatorTrainer
+    from featuresynth.loss import loss as ref_loss
+
+    class TwoArg(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inner = MelGanDiscriminator()
+
+        def forward(self, x, feat):
+            return self.inner(x)
+
+    B, T = 2, 8
+    g = MelGanGenerator(T, 128)
+    g.load_state_dict(restate.randomize_biases(restate.melgan_generator_state(111), 1111))
+    d = TwoArg()
+    d.inner.load_state_dict(restate.randomize_biases(restate.melgan_discriminator_state(112), 1112))
+    g_optim = torch.optim.Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_optim = torch.optim.Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, ref_loss.mel_gan_disc_loss)
+    g_tr = GeneratorTrainer(g, g_optim, d, d_optim, ref_loss.mel_gan_gen_loss)
+    samples = synth.randn(113, B, 1, 256 * T) * 0.1
+    features = synth.mel_features(114, B, T)
+    arrays = {"B": B, "T": T}
+
+    def sub(t):      # small tensors (biases) whole, large ones subsampled
+        t = t.detach().reshape(-1)
+        return (t if t.numel() <= 4096 else t[::257]).numpy().copy()
+
+    g0 = {k: v.clone() for k, v in g.state_dict().items()}
+    d0 = {k: v.clone() for k, v in d.inner.state_dict().items()}
+    r = d_tr.train(samples, features)
+    arrays["d_loss"] = r["d_loss"]
+    for k, p in d.inner.named_parameters():
+        arrays["dgrad." + k] = sub(p.grad)
+        arrays["dgrad_norm." + k] = float(p.grad.norm())
+        arrays["dnew." + k] = sub(p.detach() - d0[k])
+    r = g_tr.train(samples, features)
+    arrays["g_loss"] = r["g_loss"]
+    arrays["fake"] = r["fake"][..., ::4]
+    for k, p in g.named_parameters():
+        arrays["ggrad." + k] = sub(p.grad)
+        arrays["ggrad_norm." + k] = float(p.grad.norm())
+        arrays["gnew." + k] = sub(p.detach() - g0[k])
+    save("train_step_melgan_b2_t8", **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "train_step":
+        train_step()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "realmelgan":
         realmelgan()
         sys.exit(0)

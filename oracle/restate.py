@@ -540,3 +540,64 @@ MELGAN_FLOP_PER_SAMPLE = 409536  # SURVEY.md App. A.1 (2 x MAC, conv/convT only)
 
 def melgan_generator_flops(batch, frames):
     return MELGAN_FLOP_PER_SAMPLE * batch * frames * 256
+
+
+# ---------------------------------------------------------------------------------------
+# GAN training step: featuresynth/train/train.py:26-42 (GeneratorTrainer.train), 63-74
+# (DiscriminatorTrainer.train) with Adam(lr 1e-4, betas (0.5, 0.9)) from
+# featuresynth/experiment/experiment.py:111-117, on the MelGanGenerator / MelGanDiscriminator
+# pair (the discriminator ignores the conditioning features it is handed).
+# ---------------------------------------------------------------------------------------
+def adam_restated(params, grads, state, lr=1e-4, betas=(0.5, 0.9), eps=1e-8):
+    """torch.optim.Adam.step (no amsgrad / weight decay) written out; state: dict name ->
+    (step, exp_avg, exp_avg_sq), updated in place; returns the new parameter dict."""
+    out = {}
+    for name, p in params.items():
+        g = grads[name]
+        step, m, v = state.get(name, (0, torch.zeros_like(p), torch.zeros_like(p)))
+        step += 1
+        m = betas[0] * m + (1 - betas[0]) * g
+        v = betas[1] * v + (1 - betas[1]) * g * g
+        bc1 = 1 - betas[0] ** step
+        bc2 = 1 - betas[1] ** step
+        denom = v.sqrt() / (bc2 ** 0.5) + eps
+        out[name] = p - (lr / bc1) * (m / denom)
+        state[name] = (step, m, v)
+    return out
+
+
+def _leaf(sd):
+    return {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+
+
+@torch.enable_grad()
+def discriminator_train_step(g_sd, d_sd, samples, features, d_state,
+                             sub_loss=None):
+    """train/train.py:63-74 -> (d_loss, grads of D, new D state dict)"""
+    sub_loss = sub_loss or hinge_discriminator_loss
+    d = _leaf(d_sd)
+    with torch.no_grad():
+        fake = melgan_generator(features, g_sd)
+    _, f_score = melgan_discriminator(fake, d)
+    _, r_score = melgan_discriminator(samples, d)
+    loss = mel_gan_disc_loss(r_score, f_score, gan_loss=sub_loss)
+    names = list(d)
+    grads = dict(zip(names, torch.autograd.grad(loss, [d[n] for n in names])))
+    new = adam_restated({k: v.detach() for k, v in d.items()}, grads, d_state)
+    return loss.item(), grads, new
+
+
+@torch.enable_grad()
+def generator_train_step(g_sd, d_sd, samples, features, g_state, sub_loss=None):
+    """train/train.py:26-42 -> (g_loss, fake, grads of G, new G state dict)"""
+    sub_loss = sub_loss or hinge_generator_loss
+    g = _leaf(g_sd)
+    fake = melgan_generator(features, g)
+    f_features, f_score = melgan_discriminator(fake, d_sd)
+    with torch.no_grad():
+        r_features, r_score = melgan_discriminator(samples, d_sd)
+    loss = mel_gan_gen_loss(r_features, f_features, r_score, f_score, gan_loss=sub_loss)
+    names = list(g)
+    grads = dict(zip(names, torch.autograd.grad(loss, [g[n] for n in names])))
+    new = adam_restated({k: v.detach() for k, v in g.items()}, grads, g_state)
+    return loss.item(), fake.detach(), grads, new

