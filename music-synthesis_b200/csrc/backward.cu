@@ -281,6 +281,180 @@ direct_wgrad_kernel(const DirectBwdParams p) {
   }
 }
 
+
+// ---- register-tiled variants for the discriminators' shapes (COG in {4,16}, CIG in {1,4}) ----
+// dgrad: one thread = one input time step x all CIG input channels of the group; taps visited
+// are k = kfirst + s*j with output row l = lq - j (no integer division in the loop); weights in
+// shared memory as [oc][k][c] so one 16-byte broadcast read feeds CIG FMAs.
+template <int COG, int CIG>
+__global__ void __launch_bounds__(kDgTile)
+direct_dgrad_tiled_kernel(const DirectBwdParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int i0 = blockIdx.x * kDgTile;
+  const int s = p.stride;
+  int l0 = (i0 + p.pad - (p.k - 1));
+  l0 = l0 < 0 ? -((-l0 + s - 1) / s) : l0 / s;
+  const int l1 = (i0 + kDgTile - 1 + p.pad) / s;
+  const int nl = l1 - l0 + 1;
+  float* sw = sm;                               // [COG][k][4]  (c padded to 4)
+  float* sz = sm + COG * p.k * 4;               // [COG][nl]
+  for (int i = threadIdx.x; i < COG * p.k * 4; i += kDgTile) {
+    const int c = i & 3, k = (i >> 2) % p.k, oc = (i >> 2) / p.k;
+    sw[i] = c < CIG ? __ldg(p.w + (static_cast<size_t>(g * COG + oc) * CIG + c) * p.k + k) : 0.f;
+  }
+  for (int i = threadIdx.x; i < COG * nl; i += kDgTile) {
+    const int oc = i / nl, l = l0 + (i - oc * nl);
+    float v = 0.f;
+    if (l >= 0 && l < p.lout) {
+      const size_t idx = (static_cast<size_t>(b) * p.cout + g * COG + oc) * p.lout + l;
+      v = __ldg(p.dy + idx);
+      if (p.y != nullptr) v = masked(v, __ldg(p.y + idx), p.leaky);
+    }
+    sz[i] = v;
+  }
+  __syncthreads();
+  const int i = i0 + threadIdx.x;
+  if (i >= p.lin) return;
+  const int ip = i + p.pad;
+  const int kfirst = ip % s;
+  const int lq = (ip - kfirst) / s;             // output row of tap kfirst
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int oc = 0; oc < COG; ++oc) {
+    const float* zr = sz + oc * nl - l0 + lq;   // zr[-j] = dz[oc][lq - j]
+    const float4* wr = reinterpret_cast<const float4*>(sw + (oc * p.k + kfirst) * 4);
+    int j = 0;
+    for (int k = kfirst; k < p.k && j <= lq; k += s, ++j) {
+      const float z = zr[-j];
+      const float4 w = wr[j * s];
+      acc[0] = fmaf(w.x, z, acc[0]);
+      acc[1] = fmaf(w.y, z, acc[1]);
+      acc[2] = fmaf(w.z, z, acc[2]);
+      acc[3] = fmaf(w.w, z, acc[3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CIG; ++c)
+    p.dx[(static_cast<size_t>(b) * p.cin + g * CIG + c) * p.lin + i] = acc[c];
+}
+
+// wgrad: one CTA = one group x one tile of kWgTileL output rows x a set of clips; one thread =
+// (input channel, 4 consecutive taps) x ALL COG output channels x every `lanes`-th row:
+// 4*COG FMAs per 4 input reads + COG/4 broadcast 16-byte reads of dz ([l][oc] in smem).
+template <int COG, int CIG>
+__global__ void __launch_bounds__(kWgDirectThreads)
+direct_wgrad_tiled_kernel(const DirectBwdParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.x;
+  const int s = p.stride;
+  const int l0 = blockIdx.y * kWgTileL;
+  const int nl = min(kWgTileL, p.lout - l0);
+  const int kq = (p.k + 3) / 4;                          // tap quads
+  const int win = (kWgTileL - 1) * s + 4 * kq;
+  float* sz = sm;                                        // [kWgTileL][COG]
+  float* sx = sm + kWgTileL * COG;                       // [CIG][win]
+  const int nthr = CIG * kq;                             // threads per lane group
+  const int lanes = kWgDirectThreads / nthr;             // row-interleaved lane groups
+  const int o = threadIdx.x % nthr, lg = threadIdx.x / nthr;
+  const bool active = lg < lanes;
+  const int c = o / kq, k0 = (o - c * kq) * 4;
+  float acc[4][COG];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int oc = 0; oc < COG; ++oc) acc[q][oc] = 0.f;
+  float bacc[COG];
+#pragma unroll
+  for (int oc = 0; oc < COG; ++oc) bacc[oc] = 0.f;
+  for (int b = blockIdx.z; b < p.B; b += gridDim.z) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nl * COG; i += kWgDirectThreads) {
+      const int l = i % nl, oc = i / nl;
+      const size_t idx = (static_cast<size_t>(b) * p.cout + g * COG + oc) * p.lout + l0 + l;
+      float v = __ldg(p.dy + idx);
+      if (p.y != nullptr) v = masked(v, __ldg(p.y + idx), p.leaky);
+      sz[l * COG + oc] = v;
+    }
+    const int in0 = l0 * s - p.pad;
+    const int nwin = (nl - 1) * s + 4 * kq;
+    for (int i = threadIdx.x; i < CIG * nwin; i += kWgDirectThreads) {
+      const int cc = i / nwin, j = i - cc * nwin;
+      const int ti = in0 + j;
+      sx[cc * win + j] = (ti >= 0 && ti < p.lin)
+          ? __ldg(p.x + (static_cast<size_t>(b) * p.cin + g * CIG + cc) * p.lin + ti) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      const float* xr = sx + c * win + k0;
+      for (int l = lg; l < nl; l += lanes) {
+        const float x0 = xr[l * s], x1 = xr[l * s + 1], x2 = xr[l * s + 2], x3 = xr[l * s + 3];
+        const float4* z4 = reinterpret_cast<const float4*>(sz + l * COG);
+#pragma unroll
+        for (int q4 = 0; q4 < COG / 4; ++q4) {
+          const float4 z = z4[q4];
+          const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int oc = q4 * 4 + e;
+            acc[0][oc] = fmaf(zz[e], x0, acc[0][oc]);
+            acc[1][oc] = fmaf(zz[e], x1, acc[1][oc]);
+            acc[2][oc] = fmaf(zz[e], x2, acc[2][oc]);
+            acc[3][oc] = fmaf(zz[e], x3, acc[3][oc]);
+            if (o == 0) bacc[oc] += zz[e];
+          }
+        }
+      }
+    }
+  }
+  // lane groups combine in shared memory: result [COG][CIG][4*kq] (+ COG bias sums)
+  __syncthreads();
+  float* red = sm;                                       // COG * CIG * 4*kq floats (<= sz + sx)
+  float* bred = red + COG * CIG * 4 * kq;
+  for (int i = threadIdx.x; i < COG * CIG * 4 * kq + COG; i += kWgDirectThreads) red[i] = 0.f;
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int oc = 0; oc < COG; ++oc) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(&red[(oc * CIG + c) * 4 * kq + k0 + q], acc[q][oc]);
+      if (o == 0) atomicAdd(&bred[oc], bacc[oc]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < COG * CIG * p.k; i += kWgDirectThreads) {
+    const int k = i % p.k, oc_c = i / p.k;
+    atomicAdd(p.dw + (static_cast<size_t>(g) * COG * CIG + oc_c) * p.k + k, red[oc_c * 4 * kq + k]);
+  }
+  if (p.dbias != nullptr && threadIdx.x < COG) atomicAdd(p.dbias + g * COG + threadIdx.x, bred[threadIdx.x]);
+}
+
+template <int COG, int CIG>
+static ms_status launch_dgrad_tiled(const DirectBwdParams& p, cudaStream_t st) {
+  const int nl = (kDgTile + p.k) / p.stride + 3;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(COG) * p.k * 4 + static_cast<size_t>(COG) * nl);
+  if (smem > 48 * 1024) return MS_ERR_INVALID;
+  dim3 grid(ceil_div(p.lin, kDgTile), p.groups, p.B);
+  direct_dgrad_tiled_kernel<COG, CIG><<<grid, kDgTile, smem, st>>>(p);
+  return after_launch("direct_dgrad_tiled_kernel");
+}
+
+template <int COG, int CIG>
+static ms_status launch_wgrad_tiled(const DirectBwdParams& p, cudaStream_t st) {
+  const int kq = (p.k + 3) / 4;
+  if (CIG * kq > kWgDirectThreads) return MS_ERR_INVALID;
+  const int win = (kWgTileL - 1) * p.stride + 4 * kq;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(kWgTileL) * COG + static_cast<size_t>(CIG) * win);
+  if (smem > 48 * 1024 || COG * CIG * 4 * kq + COG > kWgTileL * COG + CIG * win) return MS_ERR_INVALID;
+  const int ltiles = ceil_div(p.lout, kWgTileL);
+  if (ltiles > 65535) return MS_ERR_INVALID;
+  long long z = 2048LL / (static_cast<long long>(p.groups) * ltiles);
+  if (z < 1) z = 1;
+  if (z > p.B) z = p.B;
+  dim3 grid(p.groups, ltiles, static_cast<unsigned>(z));
+  direct_wgrad_tiled_kernel<COG, CIG><<<grid, kWgDirectThreads, smem, st>>>(p);
+  return after_launch("direct_wgrad_tiled_kernel");
+}
+
 // --------------------------------------------------------- single-output-channel conv backward
 // forward: y[b,l] = act(bias + sum_c sum_k w[c,k] x[b,c,l+k-pad]),  x BLK f32.
 // dzm[b,l] = dy[b,l] * (tanh ? 1 - y^2 : 1)
@@ -529,6 +703,15 @@ ms_status ms_conv1d_direct_dgrad(const float* dy, const float* y, const float* w
   DirectBwdParams p{dy, y, nullptr, w, dx, nullptr, nullptr, batch, cin, cout, lin, lout,
                     ksize, stride, pad, groups, leaky};
   const int cin_g = cin / groups, cout_g = cout / groups;
+  if (groups > 65535 || batch > 65535) return MS_ERR_INVALID;
+  {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ms_status ts = MS_ERR_INVALID;
+    if (cout_g == 16 && cin_g == 4) ts = launch_dgrad_tiled<16, 4>(p, st);
+    else if (cout_g == 16 && cin_g == 1) ts = launch_dgrad_tiled<16, 1>(p, st);
+    else if (cout_g == 4 && cin_g == 4) ts = launch_dgrad_tiled<4, 4>(p, st);
+    if (ts != MS_ERR_INVALID) return ts;
+  }
   const int nl = (kDgTile + ksize) / stride + 3;
   const size_t smem = sizeof(float) * (static_cast<size_t>(cout_g) * cin_g * ksize +
                                        static_cast<size_t>(cout_g) * nl);
@@ -560,6 +743,17 @@ ms_status ms_conv1d_direct_wgrad(const float* dy, const float* y, const float* x
   if (cin_g * ksize > kWgDirectThreads) return MS_ERR_INVALID;
   DirectBwdParams p{dy, y, x, nullptr, nullptr, dw, dbias, batch, cin, cout, lin, lout,
                     ksize, stride, pad, groups, leaky};
+  {
+    const int cout_g = cout / groups;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ms_status ts = MS_ERR_INVALID;
+    if (groups <= 65535) {
+      if (cout_g == 16 && cin_g == 4) ts = launch_wgrad_tiled<16, 4>(p, st);
+      else if (cout_g == 16 && cin_g == 1) ts = launch_wgrad_tiled<16, 1>(p, st);
+      else if (cout_g == 4 && cin_g == 4) ts = launch_wgrad_tiled<4, 4>(p, st);
+    }
+    if (ts != MS_ERR_INVALID) return ts;
+  }
   const int win = (kWgTileL - 1) * stride + ksize;
   const size_t smem = sizeof(float) * (kWgTileL + static_cast<size_t>(cin_g) * win);
   if (smem > 200 * 1024 || cout > 0x7fffffff) return MS_ERR_INVALID;

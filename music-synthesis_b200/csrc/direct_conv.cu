@@ -64,6 +64,84 @@ direct_conv_kernel(const DirectConvParams p) {
   }
 }
 
+
+// Register-tiled variant for the shapes the discriminators actually use (COG = output channels
+// per group in {4, 16}, CIG = input channels per group in {1, 4}): one thread = one output time
+// step x ALL COG output channels of the group, so every staged input sample feeds COG FMAs and
+// the weights are read as broadcast 16-byte vectors ([c][k][oc] in shared memory).  The input
+// window is stored de-interleaved by stride phase so that the stride-s reads of neighbouring
+// threads hit consecutive banks.
+template <int COG, int CIG>
+__global__ void __launch_bounds__(kDcTile)
+direct_conv_tiled_kernel(const DirectConvParams p) {
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * kDcTile;
+  const int s = p.stride;
+  const int win = (kDcTile - 1) * s + p.k;
+  const int plen = (win + s - 1) / s;            // samples per phase
+  float* sw = sm;                                // [CIG][k][COG]
+  float* sx = sm + CIG * p.k * COG;              // [CIG][s][plen]
+  for (int i = threadIdx.x; i < CIG * p.k * COG; i += kDcTile) {
+    const int oc = i % COG, k = (i / COG) % p.k, c = i / (COG * p.k);
+    sw[i] = __ldg(p.w + (static_cast<size_t>(g * COG + oc) * CIG + c) * p.k + k);
+  }
+  const int in0 = t0 * s - p.pad;
+  for (int i = threadIdx.x; i < CIG * win; i += kDcTile) {
+    const int c = i / win, j = i - c * win;
+    int ti = in0 + j;
+    if (p.pad_mode == 1) {
+      if (ti < 0) ti = -ti;
+      else if (ti >= p.lin) ti = 2 * (p.lin - 1) - ti;
+    }
+    const float v = (ti >= 0 && ti < p.lin)
+        ? __ldg(p.x + (static_cast<size_t>(b) * p.cin + g * CIG + c) * p.lin + ti) : 0.f;
+    sx[(c * s + (j % s)) * plen + j / s] = v;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= p.lout) return;
+  float acc[COG];
+#pragma unroll
+  for (int o = 0; o < COG; ++o) acc[o] = 0.f;
+  for (int c = 0; c < CIG; ++c) {
+    for (int r = 0; r < s; ++r) {                 // taps k = r, r+s, ...: phase r of the window
+      const float* xp = sx + (c * s + r) * plen + threadIdx.x;
+      for (int k = r; k < p.k; k += s, ++xp) {
+        const float xv = *xp;
+        const float4* w4 = reinterpret_cast<const float4*>(sw + (c * p.k + k) * COG);
+#pragma unroll
+        for (int o = 0; o < COG / 4; ++o) {
+          const float4 w = w4[o];
+          acc[4 * o + 0] = fmaf(xv, w.x, acc[4 * o + 0]);
+          acc[4 * o + 1] = fmaf(xv, w.y, acc[4 * o + 1]);
+          acc[4 * o + 2] = fmaf(xv, w.z, acc[4 * o + 2]);
+          acc[4 * o + 3] = fmaf(xv, w.w, acc[4 * o + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < COG; ++o) {
+    const int co = g * COG + o;
+    float v = acc[o] + (p.bias != nullptr ? __ldg(p.bias + co) : 0.f);
+    if (p.leaky) v = fmaxf(v, 0.2f * v);
+    p.y[(static_cast<size_t>(b) * p.cout + co) * p.lout + t] = v;
+  }
+}
+
+template <int COG, int CIG>
+static ms_status launch_direct_tiled(const DirectConvParams& p, cudaStream_t st) {
+  const int win = (kDcTile - 1) * p.stride + p.k;
+  const int plen = (win + p.stride - 1) / p.stride;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(CIG) * p.k * COG +
+                                       static_cast<size_t>(CIG) * p.stride * plen);
+  if (smem > 48 * 1024) return MS_ERR_INVALID;
+  dim3 grid(ceil_div(p.lout, kDcTile), p.groups, p.B);
+  direct_conv_tiled_kernel<COG, CIG><<<grid, kDcTile, smem, st>>>(p);
+  return after_launch("direct_conv_tiled_kernel");
+}
+
 // y[b,c,t] = (1/k) * sum_j x[b,c,t*stride - pad + j]   (zero padding counted: the
 // reference's count_include_pad=True default)
 __global__ void avg_pool_kernel(const float* __restrict__ x, float* __restrict__ y, int lin,
@@ -107,9 +185,18 @@ ms_status ms_conv1d_direct_fwd(const float* x, const float* w, const float* bias
   if (pad_mode == 1 && pad >= lin) return MS_ERR_INVALID;
   DirectConvParams p{x, w, bias, y, batch, cin, cout, lin, lout, ksize, stride, pad, groups, leaky,
                      pad_mode};
-  const int cin_g = cin / groups;
+  const int cin_g = cin / groups, cout_g = cout / groups;
+  if (groups > 65535 || batch > 65535) return MS_ERR_INVALID;
+  {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ms_status ts = MS_ERR_INVALID;
+    if (cout_g == 16 && cin_g == 4) ts = launch_direct_tiled<16, 4>(p, st);
+    else if (cout_g == 16 && cin_g == 1) ts = launch_direct_tiled<16, 1>(p, st);
+    else if (cout_g == 4 && cin_g == 4) ts = launch_direct_tiled<4, 4>(p, st);
+    if (ts != MS_ERR_INVALID) return ts;        // otherwise: generic kernel below
+  }
   const size_t smem = sizeof(float) * cin_g * ((kDcTile - 1) * stride + ksize);
-  if (smem > 200 * 1024 || groups > 65535 || batch > 65535) return MS_ERR_INVALID;
+  if (smem > 200 * 1024) return MS_ERR_INVALID;
   if (smem > 48 * 1024) {
     static thread_local size_t attr_set = 0;
     if (smem > attr_set) {
