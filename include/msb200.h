@@ -346,6 +346,11 @@ ms_status ms_reduce_bwd(int mode, const float* a, const float* b, size_t n, floa
 ms_status ms_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                        size_t n, float lr, float beta1, float beta2, float eps, int step,
                        float grad_scale, void* stream);
+/* same with the step counter in device memory: *step_dev is incremented, then used -- a CUDA
+ * graph of the whole training step can be replayed without host-side state */
+ms_status ms_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           size_t n, float lr, float beta1, float beta2, float eps, int* step_dev,
+                           float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

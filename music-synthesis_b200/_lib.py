@@ -106,6 +106,8 @@ SIGNATURES = {
                                   c_void_p]),
     "ms_reduce_bwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_void_p,
                               c_void_p, c_void_p]),
+    "ms_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float,
+                                 c_float, c_float, c_float, c_void_p, c_float, c_void_p]),
     "ms_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
                              c_float, c_float, c_int, c_float, c_void_p]),
 }

@@ -628,6 +628,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// same, with the step count in device memory (CUDA-graph replays advance it on the device)
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                float* __restrict__ m, float* __restrict__ v, size_t n, float lr,
+                                float beta1, float beta2, float eps, const int* __restrict__ step,
+                                float grad_scale) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float t = static_cast<float>(*step);
+  const float bc1 = 1.f - powf(beta1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  const float gi = g[i] * grad_scale;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+  const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
 }  // namespace msb
 
 using namespace msb;
@@ -848,6 +869,21 @@ ms_status ms_adam_step(float* param, const float* grad, float* exp_avg, float* e
                                                      beta2, eps, static_cast<float>(bc1),
                                                      static_cast<float>(sqrt(bc2)), grad_scale);
   return after_launch("adam_kernel");
+}
+
+ms_status ms_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           size_t n, float lr, float beta1, float beta2, float eps, int* step_dev,
+                           float grad_scale, void* stream) {
+  if (param == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr ||
+      step_dev == nullptr)
+    return MS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+  ms_status s = after_launch("adam_tick_kernel");
+  if (s != MS_OK || n == 0) return s;
+  adam_dev_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev, grad_scale);
+  return after_launch("adam_dev_kernel");
 }
 
 }  // extern "C"

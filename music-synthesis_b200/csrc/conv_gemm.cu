@@ -85,8 +85,39 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     mx = c->off[t] > mx ? c->off[t] : mx;
   }
   c->min_off = mn;
+  c->fold_slots = 0;
+  c->fold_stride = 0;
+  // short sequences (the discriminators' top layers run on 3..64 time steps): several clips
+  // share one 128-row tile, each in a slot of Lm + span rows so that no tap crosses clips
+  const bool fold = d.kind == MS_CONV && d.batch > 1 && 2 * c->Lm + (mx - mn) <= 128;
   c->NT = pick_nt(c->Ntot);
   if (c->NT == 0) return false;
+  // geometry of a folded launch; NT / KB / nnt (the packed-weight layout) are already final
+  auto apply_fold = [&]() {
+    c->nkb = d.cin / c->KB;
+    c->MBLK = 1;
+    c->RA = 128 + mx - mn;
+    c->fold_stride = c->Lm + (mx - mn);
+    c->fold_slots = (128 - c->Lm) / c->fold_stride + 1;
+    if (c->fold_slots > d.batch) c->fold_slots = d.batch;
+    c->mtiles = 1;
+    c->a_stage_bytes = (c->KB / 8) * c->RA * 16;
+    c->w_stage_bytes = c->taps * (c->KB / 8) * c->NT * 16;
+    c->stage_bytes = (c->a_stage_bytes + c->w_stage_bytes + 127) / 128 * 128;
+    int fs = (kSmemBudget - kSmemHeader) / c->stage_bytes;
+    if (fs > kMaxStages) fs = kMaxStages;
+    if (fs < 2) return false;
+    c->stages = fs;
+    c->acc_stages = 2;
+    int fcols = 32;
+    while (fcols < 2 * c->NT) fcols *= 2;
+    c->tmem_cols = fcols;
+    size_t fsmem = kSmemHeader + static_cast<size_t>(c->stages) * c->stage_bytes;
+    if (fsmem < 120 * 1024) fsmem = 120 * 1024;
+    c->smem_bytes = fsmem;
+    c->packed_weight_bytes = static_cast<size_t>(c->nnt) * c->nkb * c->w_stage_bytes;
+    return true;
+  };
   // the pair kernel pays off when a tile carries enough K work to amortise the cross-CTA
   // hand-offs (measured: wins for K*taps >= 512, loses for the small s=2 upsamplers)
   c->pair = (pair_enabled() && c->NT % 32 == 0 && d.cin * c->taps >= 512) ? 1 : 0;
@@ -117,7 +148,13 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     if (psmem < 120 * 1024) psmem = 120 * 1024;
     c->smem_bytes = psmem;
     c->packed_weight_bytes = static_cast<size_t>(c->nnt) * 2 * c->nkb * c->w_stage_bytes;
-    return true;
+    if (!fold) return true;
+    // folded tiles run on the single-CTA kernel: the pair layout IS a single-CTA layout with
+    // n-tiles of half the width, so the packed image stays the same for every length
+    c->pair = 0;
+    c->NT = nth;
+    c->nnt = 2 * c->nnt;
+    return apply_fold();
   }
   c->MBLK = c->Lm > 128 ? 2 : 1;
   c->RA = 128 * c->MBLK + mx - mn;
@@ -139,6 +176,7 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
   }
   if (stage(c->KB, c->NT) * 2 > budget) return false;
   c->nnt = c->Ntot / c->NT;
+  if (fold) return apply_fold();
   c->nkb = d.cin / c->KB;
   c->mtiles = (c->Lm + 128 * c->MBLK - 1) / (128 * c->MBLK);
   c->a_stage_bytes = (c->KB / 8) * c->RA * 16;
@@ -211,6 +249,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     tmem_alloc(smem_u32(tmem_slot), p.tmem_cols);
     tmem_relinquish();
   }
+  if (p.fold_slots > 0) {
+    // folded tiles: the rows between clip slots are never written by the copies -- they are the
+    // convolution's zero padding, cleared once for every stage of the ring
+    for (int st = 0; st < p.stages; ++st) {
+      const uint32_t sA = data_base + static_cast<uint32_t>(st) * p.stage_bytes;
+      for (int i = threadIdx.x; i < p.a_stage_bytes / 16; i += kConvThreads)
+        st_shared_v4(sA + static_cast<uint32_t>(i) * 16u, 0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -233,11 +281,43 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int lo = r0 < 0 ? 0 : r0;
       const int hi = (r0 + p.RA) > p.lin ? p.lin : (r0 + p.RA);
       const int nrows = hi > lo ? hi - lo : 0;
-      const bool ragged = (nrows != p.RA);
+      const bool ragged = (nrows != p.RA) && p.fold_slots == 0;
       for (int kb = 0; kb < p.nkb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
         const uint32_t sW = sA + p.a_stage_bytes;
+        if (p.fold_slots > 0) {
+          // slot j of the tile holds clip b*slots + j: A row j*stride + a <-> input row min_off + a
+          const int b0 = b * p.fold_slots;
+          const int nclips = min(p.fold_slots, p.B - b0);
+          const int a_lo = p.min_off < 0 ? -p.min_off : 0;                 // first valid A row
+          int a_hi = p.lin - p.min_off;                                    // one past the last
+          if (a_hi > p.fold_stride) a_hi = p.fold_stride;
+          const int frows = a_hi > a_lo ? a_hi - a_lo : 0;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full_bar(stage),
+                                  static_cast<uint32_t>(frows) * 16u * chunks * nclips +
+                                      p.w_stage_bytes);
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) +
+                                  (static_cast<size_t>(nt_idx) * p.nkb + kb) * p.w_stage_bytes;
+            bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
+            if (frows > 0) {
+              for (int j = 0; j < nclips; ++j) {
+                const size_t cbase = static_cast<size_t>(b0 + j) * (p.cin >> 3) + kb * chunks;
+                for (int c = 0; c < chunks; ++c)
+                  bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + j * p.fold_stride + a_lo) * 16u,
+                           p.x + ((cbase + c) * p.lin + (p.min_off + a_lo)) * 8,
+                           static_cast<uint32_t>(frows) * 16u, full_bar(stage));
+              }
+            }
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          continue;
+        }
         if (ragged) {
           // rows outside [0, lin) are the convolution's zero padding
           const int head = lo - r0;                    // rows [0, head)
@@ -368,7 +448,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int mb = 0; mb < p.MBLK; ++mb) {
-        const int m = mt * rows_per_tile + mb * 128 + q * 32 + lane;
+        int m = mt * rows_per_tile + mb * 128 + q * 32 + lane;
+        int bb = b;
+        bool slot_ok = true;
+        if (p.fold_slots > 0) {
+          const int j = m / p.fold_stride;
+          m -= j * p.fold_stride;                       // row inside the clip
+          bb = b * p.fold_slots + j;
+          slot_ok = j < p.fold_slots && bb < p.B;
+        }
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * acc_cols + mb * p.NT);
         // this warp handles group pairs (2 x 16 columns) g = 2*half, 2*half+4, ...
@@ -390,7 +478,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const int2 rc = ttab[cidx];
             const int ch = rc.y;
             const int orow = (p.kind == MS_CONVT) ? p.stride * m + rc.x - p.pad : m;
-            const bool valid = (m < p.Lm) && orow >= 0 && orow < p.Lout;
+            const bool valid = slot_ok && (m < p.Lm) && orow >= 0 && orow < p.Lout;
             if (!valid) continue;
             float f[8];
             {
@@ -409,7 +497,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
             }
-            const size_t idx = (static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + orow;
+            const size_t idx = (static_cast<size_t>(bb) * cout8 + (ch >> 3)) * p.Lout + orow;
             if (p.res32 != nullptr) {
               float r8[8];
               ld_global_nc_v8(p.res32 + idx * 8, r8);
@@ -561,7 +649,9 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   p.stage_bytes = c.stage_bytes; p.tmem_cols = c.tmem_cols;
   p.kind = d.kind; p.stride = d.stride; p.pad = d.pad; p.leaky = d.leaky;
   p.operand = d.operand; p.alpha = d.alpha;
-  const long long tiles = static_cast<long long>(d.batch) * c.mtiles * c.nnt;
+  p.fold_slots = c.fold_slots; p.fold_stride = c.fold_stride;
+  p.btiles = c.fold_slots > 0 ? (d.batch + c.fold_slots - 1) / c.fold_slots : d.batch;
+  const long long tiles = static_cast<long long>(p.btiles) * c.mtiles * c.nnt;
   if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
   p.total_tiles = static_cast<int>(tiles);
 

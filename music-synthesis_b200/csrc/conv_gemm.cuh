@@ -27,6 +27,8 @@ struct ConvCfg {
   int Lout;
   int mtiles;          // ceil(Lm/(128*MBLK))
   int acc_stages;      // TMEM accumulator sets (2 = epilogue overlaps the next tile)
+  int fold_slots;      // >0: short sequences, this many clips share one 128-row tile
+  int fold_stride;     // rows per clip slot (Lm + tap span)
   int a_stage_bytes, w_stage_bytes, stage_bytes;
   int stages;
   int tmem_cols;       // power of two >= 2*NT
@@ -49,6 +51,7 @@ struct ConvGemmParams {
   int off[kMaxTaps];
   int min_off, RA;
   int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages, pair;
+  int fold_slots, fold_stride, btiles;
   int stages, a_stage_bytes, w_stage_bytes, stage_bytes, tmem_cols;
   int kind, stride, pad, leaky, operand;
   float alpha;

@@ -166,6 +166,51 @@ __global__ void conv_to_mono_kernel(const float* __restrict__ x, const float* __
   y[static_cast<size_t>(b) * L + t] = v;
 }
 
+// Same for wide inputs / short sequences (the discriminators' 1024 -> 1 judges run on 3..64 time
+// steps): 32 outputs x 8 channel lanes per block, each lane sums every 8th channel block, the
+// lanes combine in shared memory -- the serial 128-block channel loop becomes 16 steps.
+__global__ void __launch_bounds__(256)
+conv_to_mono_wide_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                         const float* __restrict__ bias, float* __restrict__ y, int cin, int L,
+                         int ksize, int pad, int tanh_out) {
+  __shared__ float sh[8][33];
+  const int chunks = cin >> 3;
+  const int tx = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + tx;
+  const int b = blockIdx.y;
+  float acc = 0.f;
+  if (t < L) {
+    for (int c = lane; c < chunks; c += 8) {
+      const float4* xr = reinterpret_cast<const float4*>(
+          x + (static_cast<size_t>(b) * chunks + c) * static_cast<size_t>(L) * 8);
+      for (int k = 0; k < ksize; ++k) {
+        const int ti = t + k - pad;
+        if (ti < 0 || ti >= L) continue;
+        const float4 a = __ldg(xr + 2 * static_cast<size_t>(ti));
+        const float4 bq = __ldg(xr + 2 * static_cast<size_t>(ti) + 1);
+        const float* wk = w + static_cast<size_t>(c) * 8 * ksize + k;     // w[(c*8+e)*ksize + k]
+        acc = fmaf(a.x, __ldg(wk), acc);
+        acc = fmaf(a.y, __ldg(wk + ksize), acc);
+        acc = fmaf(a.z, __ldg(wk + 2 * ksize), acc);
+        acc = fmaf(a.w, __ldg(wk + 3 * ksize), acc);
+        acc = fmaf(bq.x, __ldg(wk + 4 * ksize), acc);
+        acc = fmaf(bq.y, __ldg(wk + 5 * ksize), acc);
+        acc = fmaf(bq.z, __ldg(wk + 6 * ksize), acc);
+        acc = fmaf(bq.w, __ldg(wk + 7 * ksize), acc);
+      }
+    }
+  }
+  sh[lane][tx] = acc;
+  __syncthreads();
+  if (lane != 0 || t >= L) return;
+  float v = acc;
+#pragma unroll
+  for (int l = 1; l < 8; ++l) v += sh[l][tx];
+  v += bias != nullptr ? bias[0] : 0.f;
+  if (tanh_out) v = tanhf(v);
+  y[static_cast<size_t>(b) * L + t] = v;
+}
+
 // Filter-bank analysis, step 1: sliding-window expansion of a mono signal into 16 channels,
 //   Y[b, u, i] = x[b, u + i - shift]   (0 outside the clip),  i = 0..15,  BLK 16-bit out.
 // A 1 -> n-channel k-tap convolution then becomes a 16 -> n-channel conv with k/16 taps of
@@ -295,6 +340,12 @@ ms_status conv_to_mono(const float* x32, const float* w, const float* bias, floa
                        int cin, int len, int ksize, int pad, int tanh_out,
                        cudaStream_t stream) {
   if (batch <= 0 || cin <= 0 || cin % 8 != 0 || len <= 0 || ksize <= 0) return MS_ERR_INVALID;
+  if (cin >= 256 && batch <= 65535) {
+    dim3 wgrid(ceil_div(len, 32), batch);
+    conv_to_mono_wide_kernel<<<wgrid, 256, 0, stream>>>(x32, w, bias, y, cin, len, ksize, pad,
+                                                        tanh_out);
+    return after_launch("conv_to_mono_wide_kernel");
+  }
   const size_t smem = static_cast<size_t>(cin) * ksize * sizeof(float);
   if (smem > 48 * 1024) return MS_ERR_INVALID;
   dim3 grid(ceil_div(len, 256), batch);

@@ -41,6 +41,7 @@ struct WgradParams {
   int min_shift, RX;    // RX = kWgRK + max_shift - min_shift rows of X per stage
   int NT, nnt, mblks;
   int chunks_per_clip, total_chunks, chunks_per_split;
+  int fold_slots, fold_stride;   // >0: short clips, several per K chunk (slot = La + span rows)
   int stages, a_stage_bytes, x_stage_bytes, stage_bytes, tmem_cols;
   uint32_t idesc;
 };
@@ -95,12 +96,74 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
     }
     fence_proxy_async_smem();
   }
+  if (p.fold_slots > 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      const uint32_t sA = data_base + static_cast<uint32_t>(s) * p.stage_bytes;
+      for (int i = threadIdx.x; i < p.stage_bytes / 16; i += kWgThreads)
+        st_shared_v4(sA + static_cast<uint32_t>(i) * 16u, 0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 0 && p.fold_slots > 0) {
+    // ====================== producer, several short clips per chunk ======================
+    // slot j of a chunk holds clip ch*slots + j: A row j*S + l <-> dz row l, X row j*S + a <->
+    // input row min_shift + a; everything else in the stage stays zero (cleared once above;
+    // the copy pattern is the same for every chunk except a last one with fewer clips)
+    int stage = 0;
+    uint32_t phase = 0;
+    const int S = p.fold_stride;
+    const int x_lo = p.min_shift < 0 ? -p.min_shift : 0;
+    int x_hi = p.Lx - p.min_shift;
+    if (x_hi > S) x_hi = S;
+    const int x_rows = x_hi > x_lo ? x_hi - x_lo : 0;
+    for (int ch = c_begin; ch < c_end; ++ch) {
+      const int b0 = ch * p.fold_slots;
+      const int nclips = min(p.fold_slots, p.B - b0);
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+      const uint32_t sX = sA + p.a_stage_bytes;
+      if (nclips < p.fold_slots) {
+        // fewer clips than slots: the unused slots may hold rows of an earlier chunk
+        const int r_first = nclips * S;
+        const int nz = kWgRK - r_first;
+        for (int i = lane; i < nz * a_groups; i += 32) {
+          const int g = i / nz, r = r_first + (i - g * nz);
+          st_shared_v4(sA + static_cast<uint32_t>(g * kWgRK + r) * 16u, 0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
+      if (elect_one()) {
+        const uint32_t bytes = (static_cast<uint32_t>(p.La) * 16u * a_groups +
+                                static_cast<uint32_t>(x_rows) * 16u * x_groups) * nclips;
+        mbar_arrive_expect_tx(full_bar(stage), bytes);
+        for (int j = 0; j < nclips; ++j) {
+          const size_t abase = static_cast<size_t>(b0 + j) * (p.Cm >> 3) + mb * 16;
+          for (int g = 0; g < a_groups; ++g)
+            bulk_g2s(sA + static_cast<uint32_t>(g * kWgRK + j * S) * 16u,
+                     p.a + ((abase + g) * p.La) * 8, static_cast<uint32_t>(p.La) * 16u,
+                     full_bar(stage));
+          if (x_rows > 0) {
+            const size_t xbase = static_cast<size_t>(b0 + j) * (p.Cn >> 3) + nt_idx * x_groups;
+            for (int g = 0; g < x_groups; ++g)
+              bulk_g2s(sX + static_cast<uint32_t>(g * p.RX + j * S + x_lo) * 16u,
+                       p.x + ((xbase + g) * p.Lx + (p.min_shift + x_lo)) * 8,
+                       static_cast<uint32_t>(x_rows) * 16u, full_bar(stage));
+          }
+        }
+      }
+      __syncwarp();
+      if (++stage == p.stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 0) {
     // =============================== producer ===============================
     int stage = 0;
     uint32_t phase = 0;
@@ -234,21 +297,33 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 //   mode MS_CONV : Conv1d weight (Cout = Cm, Cin = Cn/fold, K = taps):   (m*Cin + n)*K + t
 //   mode MS_CONVT: ConvTranspose1d weight (Cin = Cm, Cout, K = 2s); n = r*Cout + co,
 //                  k = s*shift_t + r + pad (taps whose k falls outside [0, K) do not exist)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                    int nsplit, int taps, int Cm, int Cn, int fold, int mode,
-                                    int stride, int pad, int cout, int shift0, float beta,
-                                    size_t total) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
+constexpr int kRedLanes = 8;   // threads that share the split loop of one output element
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int taps,
+                    int Cm, int Cn, int fold, int mode, int stride, int pad, int cout, int shift0,
+                    float beta, size_t total) {
+  // block = 32 consecutive outputs x kRedLanes split lanes: coalesced 128-byte reads per split,
+  // the (up to 148-long) split loop is cut into kRedLanes independent chains
+  __shared__ float sh[kRedLanes][33];
+  const int ox = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const size_t i = blockIdx.x * static_cast<size_t>(32) + ox;
   const int cn_out = Cn / fold;
-  const int n = static_cast<int>(i % cn_out);
-  const int m = static_cast<int>((i / cn_out) % Cm);
-  const int t = static_cast<int>(i / (static_cast<size_t>(cn_out) * Cm));
-  const size_t plane = static_cast<size_t>(taps) * Cm * Cn;
-  const size_t src = (static_cast<size_t>(t) * Cm + m) * Cn + n;
   float acc = 0.f;
-  for (int s = 0; s < nsplit; ++s)
-    for (int f = 0; f < fold; ++f) acc += __ldg(part + s * plane + src + f * cn_out);
+  int n = 0, m = 0, t = 0;
+  if (i < total) {
+    n = static_cast<int>(i % cn_out);
+    m = static_cast<int>((i / cn_out) % Cm);
+    t = static_cast<int>(i / (static_cast<size_t>(cn_out) * Cm));
+    const size_t plane = static_cast<size_t>(taps) * Cm * Cn;
+    const size_t src = (static_cast<size_t>(t) * Cm + m) * Cn + n;
+    for (int s = lane; s < nsplit; s += kRedLanes)
+      for (int f = 0; f < fold; ++f) acc += __ldg(part + s * plane + src + f * cn_out);
+  }
+  sh[lane][ox] = acc;
+  __syncthreads();
+  if (lane != 0 || i >= total) return;
+#pragma unroll
+  for (int l = 1; l < kRedLanes; ++l) acc += sh[l][ox];
   size_t o;
   if (mode == MS_CONV) {
     o = (static_cast<size_t>(m) * cn_out + n) * taps + t;
@@ -263,6 +338,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
 
 struct WgradCfg {
   int NT, nnt, mblks, RX, min_shift, chunks_per_clip, total_chunks, ksplit, chunks_per_split;
+  int fold_slots, fold_stride;
   int stages, a_stage_bytes, x_stage_bytes, stage_bytes, tmem_cols;
   size_t smem_bytes, workspace_bytes;
 };
@@ -303,7 +379,14 @@ static bool make_wgrad_cfg(int B, int Cm, int Cn, int La, int Lx, int taps, cons
   if (cols > 512) return false;
   c->tmem_cols = cols;
   c->chunks_per_clip = (La + kWgRK - 1) / kWgRK;
-  const long long total = static_cast<long long>(B) * c->chunks_per_clip;
+  c->fold_slots = c->fold_stride = 0;
+  long long total = static_cast<long long>(B) * c->chunks_per_clip;
+  if (B > 1 && 2 * La + (mx - mn) <= kWgRK) {
+    c->fold_stride = La + (mx - mn);
+    c->fold_slots = (kWgRK - La) / c->fold_stride + 1;
+    if (c->fold_slots > B) c->fold_slots = B;
+    total = (B + c->fold_slots - 1) / c->fold_slots;
+  }
   if (total > 0x7fffffffLL) return false;
   c->total_chunks = static_cast<int>(total);
   int sms = sm_count();
@@ -361,6 +444,7 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
   p.NT = c.NT; p.nnt = c.nnt; p.mblks = c.mblks;
   p.chunks_per_clip = c.chunks_per_clip; p.total_chunks = c.total_chunks;
   p.chunks_per_split = c.chunks_per_split;
+  p.fold_slots = c.fold_slots; p.fold_stride = c.fold_stride;
   p.stages = c.stages; p.a_stage_bytes = c.a_stage_bytes; p.x_stage_bytes = c.x_stage_bytes;
   p.stage_bytes = c.stage_bytes; p.tmem_cols = c.tmem_cols;
   // D = F32, A/B format (must be the same), both operands MN-major (bits 15, 16), N, M = 128
@@ -379,7 +463,7 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
   ms_status s = after_launch("wgrad_kernel");
   if (s != MS_OK) return s;
   const size_t total = static_cast<size_t>(taps) * cm * (cn / fold);
-  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 256, 0, st>>>(
       p.part, dw, c.ksplit, taps, cm, cn, fold, mode, stride, pad, cout, shifts[0], beta, total);
   return after_launch("wgrad_reduce_kernel");
 }

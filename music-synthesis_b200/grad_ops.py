@@ -180,3 +180,11 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, gra
     check(_lib.lib().ms_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq),
                                   param.numel(), lr, beta1, beta2, eps, step, grad_scale,
                                   stream_ptr()), "ms_adam_step")
+
+
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step_dev,
+                  grad_scale=1.0):
+    """Adam step with the step counter in device memory (int32 tensor): graph-capturable"""
+    check(_lib.lib().ms_adam_step_dev(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq),
+                                      param.numel(), lr, beta1, beta2, eps, ptr(step_dev),
+                                      grad_scale, stream_ptr()), "ms_adam_step_dev")

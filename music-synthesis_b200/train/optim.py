@@ -25,6 +25,7 @@ class Adam:
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.process_group = process_group
         self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step counter
         n = sum(p.numel() for p in self.params)
         # 16-byte aligned slices so the packed-weight kernels' vector loads stay aligned
         offs, total = [], 0
@@ -75,18 +76,22 @@ class Adam:
         if world > 1:
             self.all_reduce_grads()
         self.step_count += 1
-        grad_ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
-                           self.betas[0], self.betas[1], self.eps, self.step_count, 1.0 / world)
-        # the kernel wrote the parameters behind autograd's back: bump the version counters so
-        # the packed 16-bit weight images are rebuilt
+        grad_ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
+                               self.betas[0], self.betas[1], self.eps, self.step_dev, 1.0 / world)
+        self.mark_updated()
+
+    def mark_updated(self):
+        """the kernel wrote the parameters behind autograd's back: bump the version counters so
+        that the packed 16-bit weight images are rebuilt (also called after a graph replay)"""
         for p in self.params:
             torch.autograd.graph.increment_version(p)
 
     def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+        return {"step": int(self.step_dev.item()), "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
                 "lr": self.lr, "betas": self.betas, "eps": self.eps}
 
     def load_state_dict(self, sd):
         self.step_count = int(sd["step"])
+        self.step_dev.fill_(self.step_count)
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -11,6 +11,11 @@ and then throws away are skipped:
 `exact_reference_grads=True` restores the reference's behaviour (all .grad fields populated).
 Data-parallel: when torch.distributed is initialised, the gradients of the network being
 stepped are summed over ranks before the step (optimisers from .optim do it in one NCCL call).
+
+`cuda_graph=True` (needs the optimisers from .optim): after two eager calls per input shape the
+whole step -- zero_grad, forward, backward, gradient all-reduce, Adam -- is captured into ONE CUDA
+graph and replayed, so the ~650 kernel launches of a cycle cost one host call; only the loss
+read-back (and the fake batch for GeneratorTrainer) stay outside.
 """
 import contextlib
 
@@ -45,10 +50,53 @@ def _sync_grads(optim, module):
             p.grad.div_(world)
 
 
-class GeneratorTrainer(object):
+class _Graphed:
+    """captured step for one input shape: static input buffers, the graph, static outputs"""
+
+    def __init__(self):
+        self.calls = 0
+        self.graph = None
+        self.samples = self.features = None
+        self.outputs = None
+
+
+class _GraphMixin:
+    def _init_graph(self, cuda_graph):
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
+
+    def _all_params(self):
+        return list(self.generator.parameters()) + list(self.discriminator.parameters())
+
+    def _run(self, samples, features):
+        """eager or graphed execution of self._step -> tuple of output tensors"""
+        if not self.cuda_graph:
+            return self._step(samples, features)
+        key = (tuple(samples.shape), tuple(features.shape))
+        st = self._graphs.setdefault(key, _Graphed())
+        st.calls += 1
+        if st.calls <= 2:                       # warm-up: lazy initialisation, allocator, NCCL
+            return self._step(samples, features)
+        if st.graph is None:
+            st.samples, st.features = samples.clone(), features.clone()
+            for p in self._all_params():        # every packed-weight image is rebuilt IN the graph
+                torch.autograd.graph.increment_version(p)
+            torch.cuda.synchronize()
+            st.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.graph):
+                st.outputs = self._step(st.samples, st.features)
+        st.samples.copy_(samples)
+        st.features.copy_(features)
+        st.graph.replay()
+        self._stepped_optim().mark_updated()
+        return st.outputs
+
+
+class GeneratorTrainer(_GraphMixin):
     def __init__(self, generator, g_optim, discriminator, d_optim, loss,
-                 sub_loss=hinge_generator_loss, exact_reference_grads=False):
+                 sub_loss=hinge_generator_loss, exact_reference_grads=False, cuda_graph=False):
         super().__init__()
+        self._init_graph(cuda_graph)
         self.sub_loss = sub_loss
         self.loss = loss
         self.d_optim = d_optim
@@ -57,7 +105,10 @@ class GeneratorTrainer(object):
         self.generator = generator
         self.exact_reference_grads = exact_reference_grads
 
-    def train(self, samples, features):
+    def _stepped_optim(self):
+        return self.g_optim
+
+    def _step(self, samples, features):
         zero_grad(self.g_optim, self.d_optim)
         fake = self.generator(features)
         if self.exact_reference_grads:
@@ -72,6 +123,10 @@ class GeneratorTrainer(object):
         loss.backward()
         _sync_grads(self.g_optim, self.generator)
         self.g_optim.step()
+        return loss.detach(), fake.detach()
+
+    def train(self, samples, features):
+        loss, fake = self._run(samples, features)
         try:
             fake = fake.data.cpu().numpy()
         except AttributeError:
@@ -79,10 +134,11 @@ class GeneratorTrainer(object):
         return {'g_loss': loss.item(), 'fake': fake}
 
 
-class DiscriminatorTrainer(object):
+class DiscriminatorTrainer(_GraphMixin):
     def __init__(self, generator, g_optim, discriminator, d_optim, loss,
-                 sub_loss=hinge_discriminator_loss, exact_reference_grads=False):
+                 sub_loss=hinge_discriminator_loss, exact_reference_grads=False, cuda_graph=False):
         super().__init__()
+        self._init_graph(cuda_graph)
         self.sub_loss = sub_loss
         self.loss = loss
         self.d_optim = d_optim
@@ -91,7 +147,10 @@ class DiscriminatorTrainer(object):
         self.generator = generator
         self.exact_reference_grads = exact_reference_grads
 
-    def train(self, samples, features):
+    def _stepped_optim(self):
+        return self.d_optim
+
+    def _step(self, samples, features):
         zero_grad(self.g_optim, self.d_optim)
         if self.exact_reference_grads:
             fake = self.generator(features)
@@ -104,4 +163,8 @@ class DiscriminatorTrainer(object):
         loss.backward()
         _sync_grads(self.d_optim, self.discriminator)
         self.d_optim.step()
+        return (loss.detach(),)
+
+    def train(self, samples, features):
+        (loss,) = self._run(samples, features)
         return {'d_loss': loss.item()}

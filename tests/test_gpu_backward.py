@@ -11,6 +11,13 @@ from tests.gpu_util import rel_l2
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _grad_on():
+    # other test modules switch autograd off process-wide
+    with torch.enable_grad():
+        yield
+
+
 def _r16(x, fmt):
     return x.to(torch.bfloat16 if fmt == 1 else torch.float16).float()
 
@@ -36,7 +43,10 @@ def test_wgrad_operand_formats(fmt_dz, fmt_x):
 
 @pytest.mark.parametrize("B,Co,Ci,L,K,d,pad", [(2, 32, 32, 700, 3, 9, 9), (2, 256, 256, 130, 3, 1, 1),
                                                (1, 512, 128, 40, 7, 1, 0), (2, 1024, 1024, 33, 5, 1, 2),
-                                               (5, 64, 64, 128, 3, 1, 1)])
+                                               (5, 64, 64, 128, 3, 1, 1),
+                                               # short clips: several per tile / K chunk (folded)
+                                               (5, 64, 64, 20, 3, 3, 3), (7, 128, 256, 9, 5, 1, 2),
+                                               (33, 1024, 1024, 5, 5, 1, 2), (4, 32, 32, 61, 3, 1, 1)])
 def test_conv_backward_matches_autograd(B, Co, Ci, L, K, d, pad):
     from music_synthesis_b200 import ops, grad_ops
     x = synth.randn(3, B, Ci, L).requires_grad_()

@@ -75,13 +75,25 @@ def test_generator_reacts_to_weight_updates():
     assert rel_l2(y1, restate.melgan_generator(x.cpu(), sd2)) < WAVEFORM_TOL
 
 
-def test_generator_refuses_cpu_and_autograd():
+def test_generator_refuses_cpu_and_feature_gradients():
     from music_synthesis_b200._lib import MsbError
     m = _module(restate.melgan_generator_state(5))
     with pytest.raises(MsbError):
         m(torch.zeros(1, 128, 8))                      # CPU input: no CPU path
     with torch.enable_grad(), pytest.raises(MsbError):
-        m(torch.zeros(1, 128, 8, device="cuda"))       # grad enabled: forward-only
+        m(torch.zeros(1, 128, 8, device="cuda", requires_grad=True))   # no d/d(features)
+
+
+def test_generator_training_forward_equals_inference_forward():
+    """grad mode records the layer-wise autograd path; its output must agree with the fused
+    inference kernels (same fp16 operands / fp32 accumulation, different tiling)"""
+    m = _module(restate.melgan_generator_state(5))
+    x = synth.mel_features(6, 2, 8).cuda()
+    with torch.no_grad():
+        y0 = m(x)
+    with torch.enable_grad():
+        y1 = m(x)
+    assert y1.requires_grad and rel_l2(y1, y0) < 2e-4
 
 
 @pytest.mark.parametrize("C,L", [(32, 96), (128, 64)])

@@ -14,6 +14,13 @@ from tests.gpu_util import rel_l2
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _grad_on():
+    # other test modules switch autograd off process-wide
+    with torch.enable_grad():
+        yield
+
 GRAD_TOL = 5e-2
 
 
@@ -183,3 +190,34 @@ def test_exact_reference_grads_mode_populates_all_grads():
         tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, exact_reference_grads=True)
         tr.train((synth.randn(133, B, 1, 256 * T) * 0.1).cuda(), synth.mel_features(134, B, T).cuda())
     assert all(p.grad is not None and float(p.grad.abs().sum()) > 0 for p in d.parameters())
+
+
+def test_cuda_graph_steps_follow_the_eager_trajectory():
+    """graphed trainers (whole step = one CUDA graph replay) vs eager trainers, 5 cycles on
+    changing inputs: same losses (atomics in the direct-conv weight gradients reorder fp32 sums,
+    so not bit-identical)"""
+    from music_synthesis_b200.train import GeneratorTrainer, DiscriminatorTrainer, Adam
+    from music_synthesis_b200.loss.loss import mel_gan_disc_loss, mel_gan_gen_loss
+    B, T = 2, 8
+    runs = []
+    for graph in (False, True):
+        with torch.enable_grad():
+            g, d = _pair(restate.melgan_generator_state(141), restate.melgan_discriminator_state(142), T)
+            g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
+            d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
+            d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss, cuda_graph=graph)
+            g_tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, cuda_graph=graph)
+            out = []
+            for cyc in range(5):
+                samples = (synth.randn(143 + cyc, B, 1, 256 * T) * 0.1).cuda()
+                features = synth.mel_features(150 + cyc, B, T).cuda()
+                out.append((d_tr.train(samples, features)["d_loss"], g_tr.train(samples, features)["g_loss"]))
+            with torch.no_grad():
+                probe = g(synth.mel_features(160, 1, T).cuda()).cpu()
+        runs.append((out, probe, int(g_optim.step_dev.item())))
+    (eager, pe, se), (graphed, pg, sg) = runs
+    assert se == sg == 5
+    for (d0, g0), (d1, g1) in zip(eager, graphed):
+        assert abs(d0 - d1) < 1e-3 * abs(d0) and abs(g0 - g1) < 1e-3 * max(1.0, abs(g0)), (eager, graphed)
+    assert eager[0] != eager[-1]                 # the weights really moved
+    assert rel_l2(pg, pe) < 2e-2                 # generator after 5 steps, fresh input, eager inference

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="GLOBAL batch (clips)")
     ap.add_argument("--frames", type=int, default=32)
+    ap.add_argument("--graph", type=int, default=1, help="1: CUDA-graph the steps (default)")
     args = ap.parse_args()
 
     import torch
@@ -53,8 +54,8 @@ def main():
     d.apply(weights_init)
     g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
     d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
-    d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss)
-    g_tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss)
+    d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss, cuda_graph=bool(args.graph))
+    g_tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, cuda_graph=bool(args.graph))
     per = args.batch // world
     gen = torch.Generator(device="cuda").manual_seed(1 + rank)
     feats = torch.randn(per, 128, args.frames, device="cuda", generator=gen) * 0.5 - 2.0
@@ -93,7 +94,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_cycle,
             "host_ms_per_step": host * 1000.0 / args.steps, "gpu_launches_per_step": launches,
             "higher_is_better": True, "scaling": "strong", "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate",
-            "data": "synthetic", "d_loss": losses[0], "g_loss": losses[1],
+            "data": "synthetic", "cuda_graph": bool(args.graph), "d_loss": losses[0], "g_loss": losses[1],
             "config": {"workload": "cfg4: MelGanGenerator + MelGanDiscriminator train cycle, "
                                    "global batch %d x %d samples, Adam(1e-4,(0.5,0.9)), DP x%d"
                                    % (args.batch, 256 * args.frames, world)}}))
