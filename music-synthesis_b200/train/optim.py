@@ -24,6 +24,7 @@ class Adam:
             raise ValueError("parameters must live on a CUDA device (no CPU path)")
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.process_group = process_group
+        self.distributed = True       # False: never reduce (a single-process copy inside a DP job)
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step counter
         n = sum(p.numel() for p in self.params)
@@ -62,7 +63,7 @@ class Adam:
             o += (p.numel() + 3) // 4 * 4
 
     def world_size(self):
-        if dist.is_available() and dist.is_initialized():
+        if self.distributed and dist.is_available() and dist.is_initialized():
             return dist.get_world_size(self.process_group)
         return 1
 

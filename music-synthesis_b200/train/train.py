@@ -12,10 +12,11 @@ and then throws away are skipped:
 Data-parallel: when torch.distributed is initialised, the gradients of the network being
 stepped are summed over ranks before the step (optimisers from .optim do it in one NCCL call).
 
-`cuda_graph=True` (needs the optimisers from .optim): after two eager calls per input shape the
-whole step -- zero_grad, forward, backward, gradient all-reduce, Adam -- is captured into ONE CUDA
-graph and replayed, so the ~650 kernel launches of a cycle cost one host call; only the loss
-read-back (and the fake batch for GeneratorTrainer) stay outside.
+`cuda_graph=True` (needs the optimisers from .optim): after two eager calls per input shape
+zero_grad + forward + backward (~320 kernel launches per step) are captured into ONE CUDA graph
+and replayed; the gradient all-reduce (NCCL, kept outside the capture so that no collective
+depends on capture-mode restrictions), the fused Adam kernel and the loss read-back follow
+eagerly.
 """
 import contextlib
 
@@ -43,6 +44,8 @@ def _sync_grads(optim, module):
         return
     if hasattr(optim, "all_reduce_grads"):
         return                                   # .optim.Adam reduces inside step()
+    if not getattr(optim, "distributed", True):
+        return
     world = dist.get_world_size()
     for p in module.parameters():
         if p.grad is not None:
@@ -69,14 +72,14 @@ class _GraphMixin:
         return list(self.generator.parameters()) + list(self.discriminator.parameters())
 
     def _run(self, samples, features):
-        """eager or graphed execution of self._step -> tuple of output tensors"""
+        """eager or graphed zero_grad + forward + backward -> tuple of output tensors"""
         if not self.cuda_graph:
-            return self._step(samples, features)
+            return self._fwd_bwd(samples, features)
         key = (tuple(samples.shape), tuple(features.shape))
         st = self._graphs.setdefault(key, _Graphed())
         st.calls += 1
-        if st.calls <= 2:                       # warm-up: lazy initialisation, allocator, NCCL
-            return self._step(samples, features)
+        if st.calls <= 2:                       # warm-up: lazy initialisation, allocator
+            return self._fwd_bwd(samples, features)
         if st.graph is None:
             st.samples, st.features = samples.clone(), features.clone()
             for p in self._all_params():        # every packed-weight image is rebuilt IN the graph
@@ -84,11 +87,10 @@ class _GraphMixin:
             torch.cuda.synchronize()
             st.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(st.graph):
-                st.outputs = self._step(st.samples, st.features)
+                st.outputs = self._fwd_bwd(st.samples, st.features)
         st.samples.copy_(samples)
         st.features.copy_(features)
         st.graph.replay()
-        self._stepped_optim().mark_updated()
         return st.outputs
 
 
@@ -105,10 +107,7 @@ class GeneratorTrainer(_GraphMixin):
         self.generator = generator
         self.exact_reference_grads = exact_reference_grads
 
-    def _stepped_optim(self):
-        return self.g_optim
-
-    def _step(self, samples, features):
+    def _fwd_bwd(self, samples, features):
         zero_grad(self.g_optim, self.d_optim)
         fake = self.generator(features)
         if self.exact_reference_grads:
@@ -121,12 +120,12 @@ class GeneratorTrainer(_GraphMixin):
                     r_features, r_score = self.discriminator(samples, features)
         loss = self.loss(r_features, f_features, r_score, f_score, gan_loss=self.sub_loss)
         loss.backward()
-        _sync_grads(self.g_optim, self.generator)
-        self.g_optim.step()
         return loss.detach(), fake.detach()
 
     def train(self, samples, features):
         loss, fake = self._run(samples, features)
+        _sync_grads(self.g_optim, self.generator)
+        self.g_optim.step()
         try:
             fake = fake.data.cpu().numpy()
         except AttributeError:
@@ -147,10 +146,7 @@ class DiscriminatorTrainer(_GraphMixin):
         self.generator = generator
         self.exact_reference_grads = exact_reference_grads
 
-    def _stepped_optim(self):
-        return self.d_optim
-
-    def _step(self, samples, features):
+    def _fwd_bwd(self, samples, features):
         zero_grad(self.g_optim, self.d_optim)
         if self.exact_reference_grads:
             fake = self.generator(features)
@@ -161,10 +157,10 @@ class DiscriminatorTrainer(_GraphMixin):
         _, r_score = self.discriminator(samples, features)
         loss = self.loss(r_score, f_score, gan_loss=self.sub_loss)
         loss.backward()
-        _sync_grads(self.d_optim, self.discriminator)
-        self.d_optim.step()
         return (loss.detach(),)
 
     def train(self, samples, features):
         (loss,) = self._run(samples, features)
+        _sync_grads(self.d_optim, self.discriminator)
+        self.d_optim.step()
         return {'d_loss': loss.item()}

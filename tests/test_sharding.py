@@ -46,3 +46,28 @@ def test_two_rank_gloo_gather_preserves_clip_order(n):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def _grad_sync_worker(rank, world, port):
+    """data-parallel gradient exchange of the trainers (train/train.py:_sync_grads): sum over
+    ranks then 1/world -- rank r holds gradient r+1 everywhere, every rank must end with 1.5"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from music_synthesis_b200.train.train import _sync_grads
+        net = torch.nn.Sequential(torch.nn.Conv1d(2, 3, 3), torch.nn.Conv1d(3, 1, 1))
+        for p in net.parameters():
+            p.grad = torch.full_like(p, float(rank + 1))
+        _sync_grads(torch.optim.SGD(net.parameters(), lr=0.1), net)
+        for p in net.parameters():
+            assert torch.allclose(p.grad, torch.full_like(p, 1.5))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_average():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_grad_sync_worker, args=(2, port), nprocs=2, join=True)
