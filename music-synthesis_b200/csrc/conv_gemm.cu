@@ -294,21 +294,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           int a_hi = p.lin - p.min_off;                                    // one past the last
           if (a_hi > p.fold_stride) a_hi = p.fold_stride;
           const int frows = a_hi > a_lo ? a_hi - a_lo : 0;
-          if (elect_one()) {
+          if (lane == 0) {
             mbar_arrive_expect_tx(full_bar(stage),
                                   static_cast<uint32_t>(frows) * 16u * chunks * nclips +
                                       p.w_stage_bytes);
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) +
                                   (static_cast<size_t>(nt_idx) * p.nkb + kb) * p.w_stage_bytes;
             bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
-            if (frows > 0) {
-              for (int j = 0; j < nclips; ++j) {
-                const size_t cbase = static_cast<size_t>(b0 + j) * (p.cin >> 3) + kb * chunks;
-                for (int c = 0; c < chunks; ++c)
-                  bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + j * p.fold_stride + a_lo) * 16u,
-                           p.x + ((cbase + c) * p.lin + (p.min_off + a_lo)) * 8,
-                           static_cast<uint32_t>(frows) * 16u, full_bar(stage));
-              }
+          }
+          __syncwarp();
+          if (frows > 0) {
+            // one small copy per (clip, channel chunk): all 32 lanes issue them
+            for (int i = lane; i < nclips * chunks; i += 32) {
+              const int j = i / chunks, c = i - j * chunks;
+              const size_t cbase = static_cast<size_t>(b0 + j) * (p.cin >> 3) + kb * chunks;
+              bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + j * p.fold_stride + a_lo) * 16u,
+                       p.x + ((cbase + c) * p.lin + (p.min_off + a_lo)) * 8,
+                       static_cast<uint32_t>(frows) * 16u, full_bar(stage));
             }
           }
           __syncwarp();

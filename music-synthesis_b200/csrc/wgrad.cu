@@ -138,23 +138,27 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         fence_proxy_async_smem();
         __syncwarp();
       }
-      if (elect_one()) {
+      if (lane == 0) {
         const uint32_t bytes = (static_cast<uint32_t>(p.La) * 16u * a_groups +
                                 static_cast<uint32_t>(x_rows) * 16u * x_groups) * nclips;
         mbar_arrive_expect_tx(full_bar(stage), bytes);
-        for (int j = 0; j < nclips; ++j) {
-          const size_t abase = static_cast<size_t>(b0 + j) * (p.Cm >> 3) + mb * 16;
-          for (int g = 0; g < a_groups; ++g)
-            bulk_g2s(sA + static_cast<uint32_t>(g * kWgRK + j * S) * 16u,
-                     p.a + ((abase + g) * p.La) * 8, static_cast<uint32_t>(p.La) * 16u,
-                     full_bar(stage));
-          if (x_rows > 0) {
-            const size_t xbase = static_cast<size_t>(b0 + j) * (p.Cn >> 3) + nt_idx * x_groups;
-            for (int g = 0; g < x_groups; ++g)
-              bulk_g2s(sX + static_cast<uint32_t>(g * p.RX + j * S + x_lo) * 16u,
-                       p.x + ((xbase + g) * p.Lx + (p.min_shift + x_lo)) * 8,
-                       static_cast<uint32_t>(x_rows) * 16u, full_bar(stage));
-          }
+      }
+      __syncwarp();
+      // many small copies (one per clip and channel group): all 32 lanes issue them
+      for (int i = lane; i < nclips * a_groups; i += 32) {
+        const int j = i / a_groups, g = i - j * a_groups;
+        const size_t abase = static_cast<size_t>(b0 + j) * (p.Cm >> 3) + mb * 16;
+        bulk_g2s(sA + static_cast<uint32_t>(g * kWgRK + j * S) * 16u,
+                 p.a + ((abase + g) * p.La) * 8, static_cast<uint32_t>(p.La) * 16u,
+                 full_bar(stage));
+      }
+      if (x_rows > 0) {
+        for (int i = lane; i < nclips * x_groups; i += 32) {
+          const int j = i / x_groups, g = i - j * x_groups;
+          const size_t xbase = static_cast<size_t>(b0 + j) * (p.Cn >> 3) + nt_idx * x_groups;
+          bulk_g2s(sX + static_cast<uint32_t>(g * p.RX + j * S + x_lo) * 16u,
+                   p.x + ((xbase + g) * p.Lx + (p.min_shift + x_lo)) * 8,
+                   static_cast<uint32_t>(x_rows) * 16u, full_bar(stage));
         }
       }
       __syncwarp();
@@ -297,43 +301,62 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 //   mode MS_CONV : Conv1d weight (Cout = Cm, Cin = Cn/fold, K = taps):   (m*Cin + n)*K + t
 //   mode MS_CONVT: ConvTranspose1d weight (Cin = Cm, Cout, K = 2s); n = r*Cout + co,
 //                  k = s*shift_t + r + pad (taps whose k falls outside [0, K) do not exist)
-constexpr int kRedLanes = 8;   // threads that share the split loop of one output element
+// Block = one output row m x 32 consecutive n x 8 split-lanes.  Each thread owns (m, n), ALL
+// taps and every 8th split: reads are 128-byte rows, the (up to 148-long) split loop becomes 8
+// independent chains, the lanes combine in shared memory.  MS_CONV: the block's 32*taps outputs
+// are contiguous in the (Cout, Cin, K) weight -> coalesced writes.  MS_CONVT: scattered element
+// writes (small tensors).
+constexpr int kRedLanes = 8;
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int taps,
                     int Cm, int Cn, int fold, int mode, int stride, int pad, int cout, int shift0,
-                    float beta, size_t total) {
-  // block = 32 consecutive outputs x kRedLanes split lanes: coalesced 128-byte reads per split,
-  // the (up to 148-long) split loop is cut into kRedLanes independent chains
-  __shared__ float sh[kRedLanes][33];
-  const int ox = threadIdx.x & 31, lane = threadIdx.x >> 5;
-  const size_t i = blockIdx.x * static_cast<size_t>(32) + ox;
+                    float beta, int sl /* split lanes per row: 1, 2, 4 or 8 */) {
+  __shared__ float sh[kRedLanes][32 * kMaxTaps + 1];
   const int cn_out = Cn / fold;
-  float acc = 0.f;
-  int n = 0, m = 0, t = 0;
-  if (i < total) {
-    n = static_cast<int>(i % cn_out);
-    m = static_cast<int>((i / cn_out) % Cm);
-    t = static_cast<int>(i / (static_cast<size_t>(cn_out) * Cm));
-    const size_t plane = static_cast<size_t>(taps) * Cm * Cn;
-    const size_t src = (static_cast<size_t>(t) * Cm + m) * Cn + n;
-    for (int s = lane; s < nsplit; s += kRedLanes)
-      for (int f = 0; f < fold; ++f) acc += __ldg(part + s * plane + src + f * cn_out);
-  }
-  sh[lane][ox] = acc;
-  __syncthreads();
-  if (lane != 0 || i >= total) return;
+  const int nx = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int rows = kRedLanes / sl;              // output rows m per block
+  const int row = wl / sl, lane = wl - row * sl;
+  const int n0 = blockIdx.x * 32;
+  const int n = n0 + nx;
+  const int m = blockIdx.y * rows + row;
+  float acc[kMaxTaps];
 #pragma unroll
-  for (int l = 1; l < kRedLanes; ++l) acc += sh[l][ox];
-  size_t o;
-  if (mode == MS_CONV) {
-    o = (static_cast<size_t>(m) * cn_out + n) * taps + t;
-  } else {
-    const int r = n / cout, co = n - r * cout;
-    const int k = stride * (shift0 + t) + r + pad;
-    if (k < 0 || k >= 2 * stride) return;
-    o = (static_cast<size_t>(m) * cout + co) * (2 * stride) + k;
+  for (int t = 0; t < kMaxTaps; ++t) acc[t] = 0.f;
+  if (n < cn_out && m < Cm) {
+    const size_t plane = static_cast<size_t>(taps) * Cm * Cn;
+    for (int s = lane; s < nsplit; s += sl) {
+      const float* base = part + s * plane + static_cast<size_t>(m) * Cn + n;
+#pragma unroll
+      for (int t = 0; t < kMaxTaps; ++t) {
+        if (t >= taps) break;
+        for (int f = 0; f < fold; ++f)
+          acc[t] += __ldg(base + static_cast<size_t>(t) * Cm * Cn + f * cn_out);
+      }
+    }
   }
-  out[o] = (beta != 0.f ? beta * out[o] : 0.f) + acc;
+#pragma unroll
+  for (int t = 0; t < kMaxTaps; ++t)
+    if (t < taps) sh[wl][nx * taps + t] = acc[t];
+  __syncthreads();
+  const int cnt = min(32, cn_out - n0) * taps;
+  for (int ii = threadIdx.x; ii < cnt * rows; ii += 256) {
+    const int rr = ii / cnt, i = ii - rr * cnt;
+    const int m = blockIdx.y * rows + rr;
+    if (m >= Cm) break;
+    float v = 0.f;
+    for (int l = 0; l < sl; ++l) v += sh[rr * sl + l][i];
+    size_t o;
+    if (mode == MS_CONV) {
+      o = (static_cast<size_t>(m) * cn_out + n0) * taps + i;
+    } else {
+      const int nn = n0 + i / taps, t = i % taps;
+      const int r = nn / cout, co = nn - r * cout;
+      const int k = stride * (shift0 + t) + r + pad;
+      if (k < 0 || k >= 2 * stride) continue;
+      o = (static_cast<size_t>(m) * cout + co) * (2 * stride) + k;
+    }
+    out[o] = (beta != 0.f ? beta * out[o] : 0.f) + v;
+  }
 }
 
 struct WgradCfg {
@@ -462,9 +485,11 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
   wgrad_kernel<<<grid, kWgThreads, c.smem_bytes, st>>>(p);
   ms_status s = after_launch("wgrad_kernel");
   if (s != MS_OK) return s;
-  const size_t total = static_cast<size_t>(taps) * cm * (cn / fold);
-  wgrad_reduce_kernel<<<static_cast<unsigned>((total + 31) / 32), 256, 0, st>>>(
-      p.part, dw, c.ksplit, taps, cm, cn, fold, mode, stride, pad, cout, shifts[0], beta, total);
+  int sl = 1;
+  while (sl < kRedLanes && sl * 2 <= c.ksplit) sl *= 2;
+  dim3 rgrid(ceil_div(cn / fold, 32), ceil_div(cm, kRedLanes / sl));
+  wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(p.part, dw, c.ksplit, taps, cm, cn, fold, mode, stride,
+                                            pad, cout, shifts[0], beta, sl);
   return after_launch("wgrad_reduce_kernel");
 }
 
