@@ -63,8 +63,9 @@ uint64_t ms_launch_count(void);
  *                      - 2*pad ... for the reference's (16,8,4),(4,2,1),(8,4,2)
  *                      this is stride*Lin.  Computed in polyphase form (2 taps at the
  *                      input rate, N = stride*Cout) so there is no overlap-add.
- *   epilogue         : y = act(alpha * acc + bias) [+ res32]; act = LeakyReLU(0.2)
- *                      when `leaky` != 0.  Writes BLK f16 (y16) and/or BLK f32 (y32).
+ *   epilogue         : y = act(alpha * acc + bias) [+ res32] (`leaky` = 1) or
+ *                      y = act(alpha * acc + bias + res32) (`leaky` = 2); act = LeakyReLU(0.2).
+ *                      Writes BLK f16 (y16) and/or BLK f32 (y32).
  *   operands         : fp16 (default) or bf16, fp32 accumulate in tensor memory.
  * ------------------------------------------------------------------------- */
 enum { MS_CONV = 0, MS_CONVT = 1 };
@@ -80,7 +81,8 @@ typedef struct {
   int dilation;  /* MS_CONV only */
   int pad;       /* zero padding (both sides) */
   int stride;    /* MS_CONVT only (MS_CONV: must be 1) */
-  int leaky;     /* 1: LeakyReLU(0.2) in the epilogue */
+  int leaky;     /* 1: y = LeakyReLU(acc+bias) [+ res32]; 2: y = LeakyReLU(acc+bias+res32)
+                    (DilatedStack, util/modules.py:130-135); 0: no activation */
   int operand;   /* MS_F16 | MS_BF16 */
   float alpha;   /* accumulator scale (1.0f normally) */
   int crop;      /* MS_CONV: output rows dropped at the end (asymmetric padding) */

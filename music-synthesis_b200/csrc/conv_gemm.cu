@@ -495,7 +495,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), p.alpha, b1.z);
               f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), p.alpha, b1.w);
             }
-            if (p.leaky) {
+            if (p.leaky == 1) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
             }
@@ -505,6 +505,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               ld_global_nc_v8(p.res32 + idx * 8, r8);
 #pragma unroll
               for (int j = 0; j < 8; ++j) f[j] += r8[j];
+            }
+            if (p.leaky == 2) {                       // activation AFTER the residual add
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
             }
             if (p.y32 != nullptr) st_global_v8(p.y32 + idx * 8, f);
             if (p.y16 != nullptr) {
@@ -578,9 +582,10 @@ __global__ void convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-ti
     }
   }
   float v = acc * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
-  if (p.leaky) v = leaky02(v);
+  if (p.leaky == 1) v = leaky02(v);
   const size_t idx = ((static_cast<size_t>(b) * (p.cout >> 3) + (co >> 3)) * p.Lout + orow) * 8 + (co & 7);
   if (p.res32 != nullptr) v += p.res32[idx];
+  if (p.leaky == 2) v = leaky02(v);
   if (p.y32 != nullptr) p.y32[idx] = v;
   if (p.y16 != nullptr) {
     if (p.operand == MS_BF16) {

@@ -7,7 +7,7 @@
 
 namespace msb {
 
-constexpr int kMaxTaps = 16;
+constexpr int kMaxTaps = 24;   // k41 stride-2 convs are 21-tap stride-1 convs over space-to-depth input
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 3072;          // barriers [0,512) | bias tables [512,2560) | index tables [2560,3072)
 constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100

@@ -273,7 +273,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
             f[6] = fmaf(__uint_as_float(v[h * 8 + 6]), p.alpha, b1.z);
             f[7] = fmaf(__uint_as_float(v[h * 8 + 7]), p.alpha, b1.w);
           }
-          if (p.leaky) {
+          if (p.leaky == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
           }
@@ -283,6 +283,10 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
             ld_global_nc_v8(p.res32 + idx * 8, r8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += r8[j];
+          }
+          if (p.leaky == 2) {                         // activation AFTER the residual add
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
           }
           if (p.y32 != nullptr) st_global_v8(p.y32 + idx * 8, f);
           if (p.y16 != nullptr) {

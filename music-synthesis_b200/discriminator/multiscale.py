@@ -187,3 +187,161 @@ class FilterBankMultiScaleDiscriminator(nn.Module):
         features.append(final_features)
         judgements.append(ops.conv_to_mono(h32, self.judge.weight, self.judge.bias, 3, 1, False))
         return features, judgements
+
+
+# ---------------------------------------------------------------------------------------
+# Non-filterbank multiscale discriminator, featuresynth/discriminator/multiscale.py:10-67,
+# 255-410 (MultiScaleDiscriminator, MultiScaleMultiResDiscriminator)
+# ---------------------------------------------------------------------------------------
+class ChannelDiscriminator(nn.Module):
+    """discriminator/multiscale.py:10-67: four dense strided convs (kernel_size 41 or 9, stride 4 or
+    2, channels 1 -> 32 -> 64 -> 128 -> 256) + optional judgement head.  The 1-input-channel first
+    layer is a direct fp32 conv; the others run on the tcgen05 kernel as stride-1 convs over the
+    space-to-depth input (k41: 11 taps at stride 4, 21 taps at stride 2)."""
+
+    def __init__(self, scale_factors, channels, return_judgements=False, conditioning_channels=0,
+                 kernel_size=41):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.conditioning_channels = conditioning_channels
+        self.return_judgements = return_judgements
+        self.channels = channels
+        self.scale_factors = scale_factors
+        self.main = nn.Sequential(*[
+            nn.Conv1d(channels[i], channels[i + 1], kernel_size, scale_factors[i],
+                      padding=kernel_size // 2) for i in range(len(scale_factors))])
+        if return_judgements:
+            start = channels[-1] + (conditioning_channels if conditioning_channels > 0 else 0)
+            self.mj = nn.Sequential(
+                nn.Conv1d(start, channels[-1], 3, 1, 1),
+                nn.Conv1d(channels[-1], channels[-1], 3, 1, 1),
+                nn.Conv1d(channels[-1], channels[-1], 3, 1, 1))
+            self.judge = nn.Conv1d(channels[-1], 1, 3, 1, 1)
+            self._pj = [_PackedConv() for _ in self.mj]
+        self._pm = [_PackedStrided() for _ in self.main]
+
+    def forward_blocked(self, x, feat16):
+        """x (B,1,L) f32 -> ([maps NCL f32], last map BLK16, last map NCL f32, judgement|None)"""
+        B = x.shape[0]
+        features = []
+        first = self.main[0]
+        h = ops.conv1d_direct(x, first.weight, first.bias, first.stride[0], first.padding[0], 1,
+                              leaky=True)
+        features.append(h)
+        h16, length = ops.pack_ncl(h), h.shape[-1]
+        for conv, pm in list(zip(self.main, self._pm))[1:]:
+            s = conv.stride[0]
+            xs = ops.space_to_depth(h16, s, length)
+            lx = xs.shape[2]
+
+            def make(taps, pad, B=B, conv=conv, s=s, lx=lx):
+                lout_full = lx + 2 * pad - (taps - 1)
+                return ops.conv_desc(MS_CONV, B, s * conv.in_channels, conv.out_channels, lx, taps,
+                                     1, pad, leaky=True, crop=lout_full - lx)
+            d, packed = pm.get(conv.weight, s, make)
+            h16, h32 = ops.conv_fwd(d, xs, packed, conv.bias, want16=True, want32=True)
+            features.append(ops.unpack_blk32(h32))
+            length = lx
+        if not self.return_judgements:
+            return features, h16, features[-1], None
+        if self.conditioning_channels > 0:
+            h16 = torch.cat([h16, feat16], dim=1)
+        h32 = None
+        for conv, pj in zip(self.mj, self._pj):
+            h16, h32 = _k3(conv, pj, h16)
+            features.append(ops.unpack_blk32(h32))
+        j = ops.conv_to_mono(h32, self.judge.weight, self.judge.bias, 3, 1, False)
+        return features, h16, features[-1], j
+
+    def forward(self, x, feat=None):
+        _fwd_only(self, x)
+        feat16 = ops.pack_ncl(feat) if (self.return_judgements and
+                                        self.conditioning_channels > 0) else None
+        f, _, last, j = self.forward_blocked(x, feat16)
+        return (f, last, j) if self.return_judgements else (f, last)
+
+
+class MultiScaleDiscriminator(nn.Module):
+    """discriminator/multiscale.py:255-375."""
+
+    def __init__(self, input_size, decompose=True, channel_judgements=False,
+                 conditioning_channels=0, kernel_size=41):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.conditioning_channels = conditioning_channels
+        self.channel_judgements = channel_judgements
+        self.decompose = decompose
+        self.input_size = input_size
+        band_sizes = [int(2 ** (np.log2(self.input_size) - i)) for i in range(5)]
+        factors = ([4, 4, 4, 4], [4, 4, 4, 2], [4, 4, 2, 2], [4, 2, 2, 2], [2, 2, 2, 2])
+        self.spec = {bs: {"scale_factors": sf, "channels": [1, 32, 64, 128, 256]}
+                     for bs, sf in zip(band_sizes, factors)}
+        self.smallest_band = min(self.spec.keys())
+        self.channel_discs = {}
+        for key, value in self.spec.items():
+            disc = ChannelDiscriminator(**value, return_judgements=self.channel_judgements,
+                                        conditioning_channels=self.conditioning_channels,
+                                        kernel_size=kernel_size)
+            self.add_module(f"channel_{key}", disc)
+            self.channel_discs[key] = disc
+        final_channels = sum(v["channels"][-1] for v in self.spec.values())
+        channels = 512
+        self.final = nn.Sequential(
+            nn.Conv1d(final_channels + self.conditioning_channels, channels, 3, 1, 1),
+            nn.Conv1d(channels, channels, 3, 1, 1),
+            nn.Conv1d(channels, channels, 3, 1, 1))
+        self.judge = nn.Conv1d(channels, 1, 3, 1, 1)
+        self.recon = None
+        self._pf = [_PackedConv() for _ in self.final]
+
+    def forward(self, x, feat):
+        _fwd_only(self, x)
+        bands = fft_frequency_decompose(x, self.smallest_band) if self.decompose else x
+        cond = self.conditioning_channels > 0
+        feat16 = ops.pack_ncl(feat) if cond else None
+        features, channels, judgements = [], [], []
+        for size, layer in self.channel_discs.items():
+            f, h16, _, j = layer.forward_blocked(bands[size], feat16)
+            features.append(f)
+            channels.append(h16)
+            if self.channel_judgements:
+                judgements.append(j)
+        x16 = torch.cat(channels, dim=1)
+        if cond:
+            T = x16.shape[2]
+            if feat.shape[-1] != T:      # F.upsample(feat, size=T): nearest neighbour
+                idx = (torch.arange(T, device=feat.device) * feat.shape[-1]) // T
+                feat16 = ops.pack_ncl(feat[..., idx].contiguous())
+            x16 = torch.cat([x16, feat16], dim=1)
+        final_features = []
+        h32 = None
+        for conv, pf in zip(self.final, self._pf):
+            x16, h32 = _k3(conv, pf, x16)
+            final_features.append(ops.unpack_blk32(h32))
+        features.append(final_features)
+        judgements.append(ops.conv_to_mono(h32, self.judge.weight, self.judge.bias, 3, 1, False))
+        return features, judgements
+
+
+class MultiScaleMultiResDiscriminator(nn.Module):
+    """discriminator/multiscale.py:378-410."""
+
+    def __init__(self, input_size, flatten_multiscale_features=False, decompose=True,
+                 channel_judgements=False, conditioning_channels=0, kernel_size=41):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.conditioning_channels = conditioning_channels
+        self.input_size = input_size
+        self.flatten_multiscale_features = flatten_multiscale_features
+        self.multiscale = MultiScaleDiscriminator(input_size, decompose, channel_judgements,
+                                                  conditioning_channels, kernel_size)
+
+    def forward(self, x, feat):
+        features, judgements = [], []
+        f, j = self.multiscale(x, feat)
+        if self.flatten_multiscale_features:
+            features.append([m for group in f for m in group])
+        else:
+            features.extend(f)
+        judgements.extend(j)
+        return features, judgements

@@ -126,3 +126,126 @@ class FilterBankMultiScaleGenerator(nn.Module):
         if self.recompose:
             return fft_frequency_recompose(results, input_size * self.upsample_ratio)
         return results
+
+
+# ---------------------------------------------------------------------------------------
+# Non-filterbank multiscale generator, featuresynth/generator/multiscale.py:10-57, 180-251
+# ---------------------------------------------------------------------------------------
+class DilatedStack(nn.Module):
+    """featuresynth/util/modules.py:79-139 as configured by ChannelGenerator: bias-free k3 convs
+    with zero padding = dilation, x <- LeakyReLU(conv_d(x) + x) (activation AFTER the residual
+    add: epilogue mode 2 of the tcgen05 conv kernel)."""
+
+    def __init__(self, in_channels, channels, kernel_size, dilations, activation=None,
+                 residual=True, groups=None, reflection_padding=False):
+        super().__init__()
+        if kernel_size != 3 or groups is not None or reflection_padding or in_channels != channels \
+                or not residual:
+            raise NotImplementedError("DilatedStack: only the ChannelGenerator configuration")
+        self.in_channels = in_channels
+        self.channels = channels
+        self.kernel_size = kernel_size
+        self.dilations = dilations
+        self.residual = residual
+        self.main = nn.Sequential(*[
+            nn.Conv1d(channels, channels, kernel_size, padding=d, dilation=d, bias=False)
+            for d in dilations])
+        self._packed = [_PackedConv() for _ in dilations]
+
+    def forward_blocked(self, x16, x32):
+        B, _, L, _ = x16.shape
+        for conv, pk, d in zip(self.main, self._packed, self.dilations):
+            desc = ops.conv_desc(MS_CONV, B, self.channels, self.channels, L, 3, d, d, leaky=2)
+            x16, x32 = ops.conv_fwd(desc, x16, pk.get(desc, conv.weight), None, res32=x32,
+                                    want16=True, want32=True)
+        return x16, x32
+
+
+class ChannelGenerator(nn.Module):
+    """generator/multiscale.py:10-57 (transposed_conv=True, the configuration of every experiment
+    in experiment/multiscale.py): 4 x [LearnedUpSample + DilatedStack] then Conv1d(C,1,7,1,3)."""
+
+    def __init__(self, scale_factors, channels, transposed_conv=False, kernel_size=40):
+        super().__init__()
+        if not transposed_conv:
+            raise NotImplementedError("ChannelGenerator: nearest-neighbour UpSample variant is "
+                                      "not on this path (the experiments use transposed_conv=True)")
+        self.kernel_size = kernel_size
+        self.transposed_conv = transposed_conv
+        self.channels = channels
+        self.scale_factors = scale_factors
+        layers = []
+        for i in range(len(scale_factors)):
+            layers.append(LearnedUpSample(in_channels=channels[i], out_channels=channels[i + 1],
+                                          kernel_size=scale_factors[i] * 2,
+                                          scale_factor=scale_factors[i], activation=None))
+            layers.append(DilatedStack(channels[i + 1], channels[i + 1], 3, [1, 3, 9]))
+        self.main = nn.Sequential(*layers)
+        self.to_samples = nn.Conv1d(channels[-1], 1, 7, 1, 3)
+        self._packed = [_PackedConv() for _ in scale_factors]
+
+    def forward_blocked(self, x16, T):
+        B = x16.shape[0]
+        L = T
+        h16, h32 = x16, None
+        for i in range(len(self.scale_factors)):
+            up, stack = self.main[2 * i], self.main[2 * i + 1]
+            s = up.scale_factor
+            d = ops.conv_desc(MS_CONVT, B, up.in_channels, up.out_channels, L, 2 * s, 1, s // 2, s,
+                              leaky=True)
+            h16, h32 = ops.conv_fwd(d, h16, self._packed[i].get(d, up.conv.weight), None,
+                                    want16=True, want32=True)
+            L *= s
+            h16, h32 = stack.forward_blocked(h16, h32)
+        return ops.conv_to_mono(h32, self.to_samples.weight, self.to_samples.bias, 7, 3, False)
+
+    def forward(self, x):
+        _fwd_only_g(self, x)
+        return self.forward_blocked(ops.pack_ncl(x), x.shape[-1])
+
+
+def _fwd_only_g(module, x):
+    if torch.is_grad_enabled() and (x.requires_grad or
+                                    any(p.requires_grad for p in module.parameters())):
+        raise MsbError("this model has no backward on the sm_100a path yet: use torch.no_grad()")
+
+
+class MultiScaleGenerator(nn.Module):
+    """generator/multiscale.py:180-251: ReflectionPad1d(3) + Conv1d(C,512,7) + LeakyReLU embedding
+    shared by five ChannelGenerators (one per octave band, 512->256->128->64->32 channels);
+    state-dict keys `embedding.*`, `channel_{size}.main.{0,2,4,6}.conv.weight`,
+    `channel_{size}.main.{1,3,5,7}.main.{0,1,2}.weight`, `channel_{size}.to_samples.*`."""
+
+    def __init__(self, feature_channels, input_size, output_size, transposed_conv=False,
+                 recompose=True, kernel_size=40):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.recompose = recompose
+        self.input_size = input_size
+        self.output_size = output_size
+        self.feature_channels = feature_channels
+        self.embedding = nn.Conv1d(feature_channels, 512, 7, 1, padding=0)
+        self.upsample_ratio = output_size // input_size
+        band_sizes = [int(2 ** (np.log2(output_size) - i)) for i in range(5)]
+        factors = ([4, 4, 4, 4], [4, 4, 4, 2], [4, 4, 2, 2], [4, 2, 2, 2], [2, 2, 2, 2])
+        self.spec = {bs: {"scale_factors": sf, "channels": [512, 256, 128, 64, 32]}
+                     for bs, sf in zip(band_sizes, factors)}
+        self.channel_generators = {}
+        for key, value in self.spec.items():
+            generator = ChannelGenerator(**value, transposed_conv=transposed_conv)
+            self.add_module(f"channel_{key}", generator)
+            self.channel_generators[key] = generator
+        self._pe = _PackedConv()
+
+    def forward(self, x):
+        _fwd_only_g(self, x)
+        B, _, T = x.shape
+        x16 = ops.pack_ncl(x, 3, 1)                                   # ReflectionPad1d(3)
+        d = ops.conv_desc(MS_CONV, B, self.feature_channels, 512, T + 6, 7, 1, 0, leaky=True)
+        e16, _ = ops.conv_fwd(d, x16, self._pe.get(d, self.embedding.weight), self.embedding.bias)
+        results = {}
+        for size, layer in self.channel_generators.items():
+            results[size] = layer.forward_blocked(e16, T)
+        if self.recompose:
+            return fft_frequency_recompose(results, T * self.upsample_ratio)
+        return results

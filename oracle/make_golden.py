@@ -258,7 +258,54 @@ def train_step():
     save("train_step_melgan_b2_t8", **arrays)
 
 
+def multiscale():
+    """MultiScaleGenerator (generator/multiscale.py:180-251) and MultiScaleMultiResDiscriminator
+    (discriminator/multiscale.py:378-410) as wired by experiment/multiscale.py:81-93."""
+    ref_harness.load()
+    from featuresynth.generator.multiscale import MultiScaleGenerator
+    from featuresynth.discriminator.multiscale import MultiScaleMultiResDiscriminator
+    torch.set_grad_enabled(False)
+    T, N = 8, 2048
+    for recompose in (False, True):
+        g = MultiScaleGenerator(128, T, N, transposed_conv=True, recompose=recompose).eval()
+        sd = restate.multiscale_generator_state(171, N)
+        assert list(g.state_dict()) == list(sd), "generator key order differs from the reference"
+        g.load_state_dict(sd)
+        y = g(synth.mel_features(172, 2, T))
+        if recompose:
+            save("ms_generator_recomposed_t8", seed=171, y=y.numpy())
+        else:
+            save("ms_generator_t8", seed=171, **{f"band_{k}": v.numpy() for k, v in y.items()})
+    for name, kw in (("ms_discriminator_cond_n2048", dict(decompose=True, channel_judgements=True,
+                                                          conditioning_channels=128)),
+                     ("ms_discriminator_k9_n2048", dict(decompose=False, channel_judgements=True,
+                                                        kernel_size=9))):
+        d = MultiScaleMultiResDiscriminator(N, flatten_multiscale_features=False, **kw).eval()
+        dsd = restate.multiscale_discriminator_state(
+            173, N, conditioning_channels=kw.get("conditioning_channels", 0),
+            kernel_size=kw.get("kernel_size", 41))
+        assert list(d.state_dict()) == list(dsd), "discriminator key order differs"
+        d.load_state_dict(dsd)
+        if kw["decompose"]:
+            x = synth.randn(174, 2, 1, N) * 0.1
+        else:
+            x = {s: synth.randn(175 + i, 2, 1, s) * 0.1 for i, s in enumerate(restate.fb_band_sizes(N))}
+        feats, judg = d(x, synth.mel_features(180, 2, T))
+        arrays = {"seed": 173, "n_groups": len(feats), "n_judgements": len(judg)}
+        for i, j in enumerate(judg):
+            arrays[f"j{i}"] = j.numpy()
+        for gi, fl in enumerate(feats):
+            arrays[f"n_f{gi}"] = len(fl)
+            for i, f in enumerate(fl):
+                arrays[f"f{gi}_{i}_shape"] = np.array(f.shape)
+                arrays[f"f{gi}_{i}_sub"] = f.numpy().reshape(-1)[::13]
+        save(name, **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "multiscale":
+        multiscale()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "train_step":
         train_step()
         sys.exit(0)

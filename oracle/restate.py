@@ -601,3 +601,127 @@ def generator_train_step(g_sd, d_sd, samples, features, g_state, sub_loss=None):
     grads = dict(zip(names, torch.autograd.grad(loss, [g[n] for n in names])))
     new = adam_restated({k: v.detach() for k, v in g.items()}, grads, g_state)
     return loss.item(), fake.detach(), grads, new
+
+
+# ---------------------------------------------------------------------------------------
+# Non-filterbank multiscale pair: MultiScaleGenerator (generator/multiscale.py:10-57, 180-251)
+# and MultiScaleMultiResDiscriminator (discriminator/multiscale.py:10-67, 255-410)
+# ---------------------------------------------------------------------------------------
+MS_FACTORS = ((4, 4, 4, 4), (4, 4, 4, 2), (4, 4, 2, 2), (4, 2, 2, 2), (2, 2, 2, 2))
+MS_G_CHANNELS = (512, 256, 128, 64, 32)
+MS_D_CHANNELS = (1, 32, 64, 128, 256)
+
+
+def _seeded(seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+
+    def w(*shape):
+        return torch.from_numpy((rs.standard_normal(shape) * 0.02).astype(np.float32))
+
+    def b(n):
+        return torch.from_numpy((rs.standard_normal((n,)) * 0.01).astype(np.float32))
+    return w, b
+
+
+def multiscale_generator_state(seed, output_size, feature_channels=128):
+    """state dict in the reference's key order (transposed_conv=True)"""
+    w, b = _seeded(seed)
+    sd = {"embedding.weight": w(512, feature_channels, 7), "embedding.bias": b(512)}
+    for size, factors in zip(fb_band_sizes(output_size), MS_FACTORS):
+        for i, s_ in enumerate(factors):
+            cin, cout = MS_G_CHANNELS[i], MS_G_CHANNELS[i + 1]
+            sd[f"channel_{size}.main.{2 * i}.conv.weight"] = w(cin, cout, 2 * s_)
+            for j in range(3):
+                sd[f"channel_{size}.main.{2 * i + 1}.main.{j}.weight"] = w(cout, cout, 3)
+        sd[f"channel_{size}.to_samples.weight"] = w(1, 32, 7)
+        sd[f"channel_{size}.to_samples.bias"] = b(1)
+    return sd
+
+
+def multiscale_generator(x, sd, output_size, recompose=False):
+    """generator/multiscale.py:228-244 (forward), 53-56 (ChannelGenerator.forward),
+    util/modules.py:120-137 (DilatedStack: x <- leaky(conv_d(x)[..., :L] + x)), 168-188."""
+    T = x.shape[-1]
+    e = leaky(F.conv1d(F.pad(x, (3, 3), mode="reflect"), sd["embedding.weight"],
+                       sd["embedding.bias"]))
+    results = {}
+    for size, factors in zip(fb_band_sizes(output_size), MS_FACTORS):
+        h = e
+        for i, s_ in enumerate(factors):
+            h = leaky(F.conv_transpose1d(h, sd[f"channel_{size}.main.{2 * i}.conv.weight"],
+                                         stride=s_, padding=s_ // 2))
+            for j, d in enumerate((1, 3, 9)):
+                z = F.conv1d(h, sd[f"channel_{size}.main.{2 * i + 1}.main.{j}.weight"],
+                             padding=d, dilation=d)[:, :, :h.shape[-1]]
+                h = leaky(z + h)
+        results[size] = F.conv1d(h, sd[f"channel_{size}.to_samples.weight"],
+                                 sd[f"channel_{size}.to_samples.bias"], padding=3)
+    if recompose:
+        return fft_frequency_recompose(results, T * (output_size // T))
+    return results
+
+
+def multiscale_discriminator_state(seed, input_size, conditioning_channels=128, kernel_size=41,
+                                   channel_judgements=True):
+    w, b = _seeded(seed)
+    sd = {}
+    p = "multiscale."
+    for size in fb_band_sizes(input_size):
+        for i in range(4):
+            sd[f"{p}channel_{size}.main.{i}.weight"] = w(MS_D_CHANNELS[i + 1], MS_D_CHANNELS[i], kernel_size)
+            sd[f"{p}channel_{size}.main.{i}.bias"] = b(MS_D_CHANNELS[i + 1])
+        if channel_judgements:
+            for i in range(3):
+                cin = 256 + conditioning_channels if i == 0 else 256
+                sd[f"{p}channel_{size}.mj.{i}.weight"] = w(256, cin, 3)
+                sd[f"{p}channel_{size}.mj.{i}.bias"] = b(256)
+            sd[f"{p}channel_{size}.judge.weight"] = w(1, 256, 3)
+            sd[f"{p}channel_{size}.judge.bias"] = b(1)
+    for i in range(3):
+        cin = 5 * 256 + conditioning_channels if i == 0 else 512
+        sd[f"{p}final.{i}.weight"] = w(512, cin, 3)
+        sd[f"{p}final.{i}.bias"] = b(512)
+    sd[f"{p}judge.weight"] = w(1, 512, 3)
+    sd[f"{p}judge.bias"] = b(1)
+    return sd
+
+
+def multiscale_multires_discriminator(x, feat, sd, input_size, decompose=True,
+                                      channel_judgements=True, conditioning_channels=128,
+                                      kernel_size=41):
+    """discriminator/multiscale.py:50-67 (ChannelDiscriminator.forward), 327-375
+    (MultiScaleDiscriminator.forward), 397-410 (flatten_multiscale_features=False)."""
+    p = "multiscale."
+    sizes = fb_band_sizes(input_size)
+    bands = fft_frequency_decompose(x, min(sizes)) if decompose else x
+    features, channels, judgements = [], [], []
+    for size, factors in zip(sizes, MS_FACTORS):
+        h = bands[size]
+        f = []
+        for i, s_ in enumerate(factors):
+            h = leaky(F.conv1d(h, sd[f"{p}channel_{size}.main.{i}.weight"],
+                               sd[f"{p}channel_{size}.main.{i}.bias"], stride=s_,
+                               padding=kernel_size // 2))
+            f.append(h)
+        if channel_judgements:
+            if conditioning_channels > 0:
+                h = torch.cat([h, feat], dim=1)
+            for i in range(3):
+                h = leaky(F.conv1d(h, sd[f"{p}channel_{size}.mj.{i}.weight"],
+                                   sd[f"{p}channel_{size}.mj.{i}.bias"], padding=1))
+                f.append(h)
+            judgements.append(F.conv1d(h, sd[f"{p}channel_{size}.judge.weight"],
+                                       sd[f"{p}channel_{size}.judge.bias"], padding=1))
+        features.append(f)
+        channels.append(h)
+    h = torch.cat(channels, dim=1)
+    if conditioning_channels > 0:
+        h = torch.cat([h, F.interpolate(feat, size=h.shape[-1])], dim=1)
+    final = []
+    for i in range(3):
+        h = leaky(F.conv1d(h, sd[f"{p}final.{i}.weight"], sd[f"{p}final.{i}.bias"], padding=1))
+        final.append(h)
+    features.append(final)
+    judgements.append(F.conv1d(h, sd[f"{p}judge.weight"], sd[f"{p}judge.bias"], padding=1))
+    return features, judgements
