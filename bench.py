@@ -209,12 +209,15 @@ def main():
 
     # ---- device-resident timing ------------------------------------------------
     with torch.no_grad():
-        for _ in range(args.warmup):
-            y = gen(x_dev)
-        sync_all()
+        # clocks are sampled from before the warm-up (nvidia-smi needs ~0.5 s to deliver its first
+        # row) through the timed region; a short timed region is followed by an UNTIMED
+        # continuation of the same step until enough rows exist -- all of it under this load
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            y = gen(x_dev)
+        sync_all()
         launches0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -224,6 +227,11 @@ def main():
         sync_all()
         launches = _lib.launch_count() - launches0
         ms = e0.elapsed_time(e1)
+        if rank == 0:
+            t_hold = time.time()
+            while len(sampler.rows) < 10 and time.time() - t_hold < 4.0:
+                y = gen(x_dev)
+                torch.cuda.synchronize()
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- end to end through the module with HOST buffers ---------------------

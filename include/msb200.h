@@ -281,7 +281,8 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
  * (experiment/experiment.py:111-117); here they are explicit kernels called from
  * torch.autograd.Function.backward through this ABI.
  *   Gradients travel as BLK f32 between layers and are converted to a 16-bit GEMM operand
- *   (bf16: the range of fp32, so no loss scaling) by ms_blk_act_bwd, which also applies LeakyReLU' and
+ *   (bf16 -- the default: the range of fp32, no loss scaling -- or fp16 under the dynamic loss
+ *   scaler of train/train.py) by ms_blk_act_bwd, which also applies LeakyReLU' and
  *   accumulates the bias gradient.
  * ------------------------------------------------------------------------- */
 /* dz16 = to16(dy32 * LeakyReLU'(.)), dbias[c] += sum_{b,l} dz.  Sign source: `sign16` (BLK
@@ -308,15 +309,15 @@ ms_status ms_weight_dgrad_view(const float* w, float* out, int kind, int cout, i
  *   mode MS_CONVT: ConvTranspose1d weight (cin=cm, cout, 2*stride); a16 = layer input,
  *                  x16 = space-to-depth dz (cn = stride*cout), shifts = {-1,0,1}.
  * fmt: MS_F16 | MS_BF16 of BOTH operands (tcgen05 kind::f16 does not mix them: a mixed
- * instruction descriptor raises an illegal-instruction fault on sm_100a).  dw = beta*dw + G.
+ * instruction descriptor raises an illegal-instruction fault on sm_100a).  dw = beta*dw + alpha*G.
  * fold = 2 (MS_CONV): x16 holds a two-term split (ms_pack_ncl_split_blk16) of the layer input in
  * its two channel halves; the halves of G are summed into the cn/2-channel weight gradient. */
 size_t ms_wgrad_workspace_bytes(int batch, int cm, int cn, int la, int lx, int taps,
                                 const int* shifts);
 ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int cn, int la,
                        int lx, int taps, const int* shifts, int fmt, int mode, int stride,
-                       int pad, int cout, int fold, float beta, float* dw, void* workspace,
-                       size_t workspace_bytes, void* stream);
+                       int pad, int cout, int fold, float alpha, float beta, float* dw,
+                       void* workspace, size_t workspace_bytes, void* stream);
 /* 16-bit operand format conversion (fp16 forward activations -> bf16 for the weight-gradient
  * GEMM, whose other operand is a bf16 gradient) */
 ms_status ms_blk16_convert(const void* src, void* dst, size_t elems, int src_fmt, int dst_fmt,
@@ -352,7 +353,12 @@ ms_status ms_adam_step(float* param, const float* grad, float* exp_avg, float* e
  * graph of the whole training step can be replayed without host-side state */
 ms_status ms_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                            size_t n, float lr, float beta1, float beta2, float eps, int* step_dev,
-                           float grad_scale, void* stream);
+                           float grad_scale, const int* skip_flag, void* stream);
+/* dynamic loss scaling of the fp16 backward: grad *= *inv_scale_dev in place; *flag_dev = 1 when any
+ * element is not finite (an fp16 gradient operand overflowed), else 0.  ms_adam_step_dev with
+ * skip_flag = flag_dev then leaves parameters, moments and the step counter untouched. */
+ms_status ms_grad_unscale_check(float* grad, size_t n, const float* inv_scale_dev, int* flag_dev,
+                                void* stream);
 
 #ifdef __cplusplus
 }

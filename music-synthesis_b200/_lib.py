@@ -87,7 +87,7 @@ SIGNATURES = {
                                             POINTER(c_int)]),
     "ms_wgrad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                              POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                             c_void_p, c_void_p, c_size_t, c_void_p]),
+                             c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ms_pack_ncl_split_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                         c_float, c_void_p]),
     "ms_weight_split": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
@@ -107,7 +107,8 @@ SIGNATURES = {
     "ms_reduce_bwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_void_p,
                               c_void_p, c_void_p]),
     "ms_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float,
-                                 c_float, c_float, c_float, c_void_p, c_float, c_void_p]),
+                                 c_float, c_float, c_float, c_void_p, c_float, c_void_p, c_void_p]),
+    "ms_grad_unscale_check": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ms_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
                              c_float, c_float, c_int, c_float, c_void_p]),
 }

@@ -255,8 +255,10 @@ class DenseConvNCL(Function):
                                     want_bias=has_bias and ctx.needs_input_grad[2])
         dw = None
         if need_w:
-            xs = ops.pack_ncl_split(x, operand=GRAD_FMT)             # (hi, lo) in the gradient format
-            dw = grad_ops.conv_wgrad(dz16, xs, tuple(w.shape), 1, pad, fmt_x=GRAD_FMT, fold=2)
+            # (hi, lo) of the layer input in the gradient format, scaled out of the subnormals
+            xs = ops.pack_ncl_split(x, operand=GRAD_FMT, scale=SPLIT_SX)
+            dw = grad_ops.conv_wgrad(dz16, xs, tuple(w.shape), 1, pad, fmt_x=GRAD_FMT, fold=2,
+                                     alpha=1.0 / SPLIT_SX)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.unpack_blk32(_dgrad_conv(cache, w, dz16, MS_CONV, 1, pad, 1))

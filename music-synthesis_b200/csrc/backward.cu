@@ -628,15 +628,29 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// loss-scaled fp16 backward: g *= inv_scale in place, *flag |= 1 if any element is not finite
+// (an overflowed fp16 gradient operand) -- the step is then skipped and the scale lowered
+__global__ void grad_unscale_check_kernel(float* __restrict__ g, size_t n,
+                                          const float* __restrict__ inv_scale, int* flag) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float v = g[i] * __ldg(inv_scale);
+  g[i] = v;
+  if (!isfinite(v)) *flag = 1;
+}
+
 // same, with the step count in device memory (CUDA-graph replays advance it on the device)
-__global__ void adam_tick_kernel(int* step) { *step += 1; }
+__global__ void adam_tick_kernel(int* step, const int* __restrict__ skip) {
+  if (skip == nullptr || *skip == 0) *step += 1;
+}
 
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
                                 float* __restrict__ m, float* __restrict__ v, size_t n, float lr,
                                 float beta1, float beta2, float eps, const int* __restrict__ step,
-                                float grad_scale) {
+                                float grad_scale, const int* __restrict__ skip) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
+  if (skip != nullptr && *skip != 0) return;          // non-finite gradients: no update
   const float t = static_cast<float>(*step);
   const float bc1 = 1.f - powf(beta1, t);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, t));
@@ -873,17 +887,29 @@ ms_status ms_adam_step(float* param, const float* grad, float* exp_avg, float* e
 
 ms_status ms_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                            size_t n, float lr, float beta1, float beta2, float eps, int* step_dev,
-                           float grad_scale, void* stream) {
+                           float grad_scale, const int* skip_flag, void* stream) {
   if (param == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr ||
       step_dev == nullptr)
     return MS_ERR_INVALID;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+  adam_tick_kernel<<<1, 1, 0, st>>>(step_dev, skip_flag);
   ms_status s = after_launch("adam_tick_kernel");
   if (s != MS_OK || n == 0) return s;
   adam_dev_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev, grad_scale);
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step_dev, grad_scale, skip_flag);
   return after_launch("adam_dev_kernel");
+}
+
+ms_status ms_grad_unscale_check(float* grad, size_t n, const float* inv_scale_dev, int* flag_dev,
+                                void* stream) {
+  if (grad == nullptr || inv_scale_dev == nullptr || flag_dev == nullptr) return MS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(flag_dev, 0, sizeof(int), st);
+  if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(flag)");
+  if (n == 0) return MS_OK;
+  grad_unscale_check_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      grad, n, inv_scale_dev, flag_dev);
+  return after_launch("grad_unscale_check_kernel");
 }
 
 }  // extern "C"

@@ -310,7 +310,7 @@ constexpr int kRedLanes = 8;
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int taps,
                     int Cm, int Cn, int fold, int mode, int stride, int pad, int cout, int shift0,
-                    float beta, int sl /* split lanes per row: 1, 2, 4 or 8 */) {
+                    float beta, float alpha, int sl /* split lanes per row: 1, 2, 4 or 8 */) {
   __shared__ float sh[kRedLanes][32 * kMaxTaps + 1];
   const int cn_out = Cn / fold;
   const int nx = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -355,7 +355,7 @@ wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int
       if (k < 0 || k >= 2 * stride) continue;
       o = (static_cast<size_t>(m) * cout + co) * (2 * stride) + k;
     }
-    out[o] = (beta != 0.f ? beta * out[o] : 0.f) + v;
+    out[o] = (beta != 0.f ? beta * out[o] : 0.f) + alpha * v;
   }
 }
 
@@ -440,8 +440,8 @@ size_t ms_wgrad_workspace_bytes(int batch, int cm, int cn, int la, int lx, int t
 
 ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int cn, int la,
                        int lx, int taps, const int* shifts, int fmt, int mode, int stride,
-                       int pad, int cout, int fold, float beta, float* dw, void* workspace,
-                       size_t workspace_bytes, void* stream) {
+                       int pad, int cout, int fold, float alpha, float beta, float* dw,
+                       void* workspace, size_t workspace_bytes, void* stream) {
   WgradCfg c;
   if (a16 == nullptr || x16 == nullptr || dw == nullptr || shifts == nullptr ||
       !make_wgrad_cfg(batch, cm, cn, la, lx, taps, shifts, &c))
@@ -489,7 +489,7 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
   while (sl < kRedLanes && sl * 2 <= c.ksplit) sl *= 2;
   dim3 rgrid(ceil_div(cn / fold, 32), ceil_div(cm, kRedLanes / sl));
   wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(p.part, dw, c.ksplit, taps, cm, cn, fold, mode, stride,
-                                            pad, cout, shifts[0], beta, sl);
+                                            pad, cout, shifts[0], beta, alpha, sl);
   return after_launch("wgrad_reduce_kernel");
 }
 

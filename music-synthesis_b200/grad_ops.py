@@ -7,10 +7,16 @@ import torch
 from . import _lib, ops
 from ._lib import MS_CONV, MS_CONVT, MS_F16, MS_BF16, check, ptr, stream_ptr
 
-# 16-bit format of the backward GEMMs: bf16 has the range of fp32, so the small GAN gradients need
-# no loss scaling.  tcgen05 kind::f16 cannot mix fp16 and bf16 operands, so the weights (dgrad)
-# and the saved forward activations (wgrad) are converted to bf16 for the backward pass.
+# 16-bit format of the backward GEMMs.  Default bf16: the range of fp32, so the GAN gradients
+# (1e-2 at the discriminator's input down to 1e-9 deep in the generator within ONE backward pass --
+# wider than fp16's normal range) need no loss scaling.  tcgen05 kind::f16 cannot mix fp16 and
+# bf16 operands, so dgrad weights are packed in bf16 and the saved fp16 activations are converted
+# for the wgrad.  MSB_GRAD_FMT=f16 selects fp16 operands under the dynamic loss scaler of
+# train/train.py (measured: discriminator gradients 9x closer to the oracle, 3e-4; generator
+# gradients unchanged at 4e-2 -- their error is LeakyReLU mask flips caused by the fp16 FORWARD,
+# not backward rounding -- and NaN / underflow at either end of the generator step's range).
 GRAD_FMT = MS_F16 if __import__('os').environ.get('MSB_GRAD_FMT') == 'f16' else MS_BF16
+NEEDS_LOSS_SCALE = GRAD_FMT == MS_F16
 
 
 def convert16(x16, src_fmt, dst_fmt):
@@ -79,7 +85,7 @@ def _workspace(nbytes, device):
     return buf
 
 
-def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0, fold=1):
+def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0, fold=1, alpha=1.0):
     """Weight gradient (reference layout `w_shape`) on the tcgen05 time-reduction GEMM."""
     B, Cm8, La, _ = a16.shape
     _, Cn8, Lx, _ = x16.shape
@@ -93,17 +99,18 @@ def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0, fold=1):
     dw = torch.empty(w_shape, dtype=torch.float32, device=a16.device)
     cout = w_shape[1] if mode == MS_CONVT else 0
     check(L.ms_wgrad_fwd(ptr(a16), ptr(x16), B, Cm8 * 8, Cn8 * 8, La, Lx, taps, sh, fmt,
-                         mode, stride, pad, cout, fold, 0.0, ptr(dw), ptr(ws), ws.numel(), stream_ptr()),
+                         mode, stride, pad, cout, fold, float(alpha), 0.0, ptr(dw), ptr(ws), ws.numel(), stream_ptr()),
           "ms_wgrad_fwd")
     return dw
 
 
-def conv_wgrad(dz16, x16, w_shape, dilation=1, pad=0, fmt_dz=GRAD_FMT, fmt_x=MS_F16, fold=1):
+def conv_wgrad(dz16, x16, w_shape, dilation=1, pad=0, fmt_dz=GRAD_FMT, fmt_x=MS_F16, fold=1,
+               alpha=1.0):
     """dW of a stride-1 Conv1d: dz16 (B,Cout/8,Lout,8), x16 (B,fold*Cin/8,Lin,8); fold = 2:
     x16 is a two-term split (ops.pack_ncl_split) of the layer input."""
     k = w_shape[2]
     return wgrad(dz16, convert16(x16, fmt_x, fmt_dz), [t * dilation - pad for t in range(k)],
-                 MS_CONV, w_shape, fmt_dz, fold=fold)
+                 MS_CONV, w_shape, fmt_dz, fold=fold, alpha=alpha)
 
 
 def convt_wgrad(x16, dzs16, w_shape, stride, pad, fmt_dz=GRAD_FMT, fmt_x=MS_F16):
@@ -183,8 +190,15 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, gra
 
 
 def adam_step_dev(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step_dev,
-                  grad_scale=1.0):
-    """Adam step with the step counter in device memory (int32 tensor): graph-capturable"""
+                  grad_scale=1.0, skip_flag=None):
+    """Adam step with the step counter in device memory (int32 tensor): graph-capturable;
+    skip_flag (int32 device tensor): non-zero = leave everything untouched"""
     check(_lib.lib().ms_adam_step_dev(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq),
                                       param.numel(), lr, beta1, beta2, eps, ptr(step_dev),
-                                      grad_scale, stream_ptr()), "ms_adam_step_dev")
+                                      grad_scale, ptr(skip_flag), stream_ptr()), "ms_adam_step_dev")
+
+
+def grad_unscale_check(grad, inv_scale_dev, flag_dev):
+    """grad *= inv_scale (device scalar) in place; flag_dev <- any non-finite element"""
+    check(_lib.lib().ms_grad_unscale_check(ptr(grad), grad.numel(), ptr(inv_scale_dev),
+                                           ptr(flag_dev), stream_ptr()), "ms_grad_unscale_check")

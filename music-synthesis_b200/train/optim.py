@@ -27,6 +27,8 @@ class Adam:
         self.distributed = True       # False: never reduce (a single-process copy inside a DP job)
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step counter
+        self.found_inf = torch.zeros(1, dtype=torch.int32, device=dev)  # set by unscale_()
+        self._skip = None
         n = sum(p.numel() for p in self.params)
         # 16-byte aligned slices so the packed-weight kernels' vector loads stay aligned
         offs, total = [], 0
@@ -72,13 +74,26 @@ class Adam:
         if self.world_size() > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
 
+    def unscale_(self, inv_scale_dev):
+        """loss-scaled backward: reduce over ranks, multiply the flat gradient by the device
+        scalar `inv_scale_dev` in place and record whether any element is non-finite; the next
+        step() is then skipped on the device (no host round trip)"""
+        if self.world_size() > 1:
+            self.all_reduce_grads()
+        grad_ops.grad_unscale_check(self.flat_grad, inv_scale_dev, self.found_inf)
+        self._skip = self.found_inf
+        self._reduced = True
+
     def step(self):
         world = self.world_size()
-        if world > 1:
+        if world > 1 and not getattr(self, "_reduced", False):
             self.all_reduce_grads()
+        self._reduced = False
         self.step_count += 1
         grad_ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
-                               self.betas[0], self.betas[1], self.eps, self.step_dev, 1.0 / world)
+                               self.betas[0], self.betas[1], self.eps, self.step_dev, 1.0 / world,
+                               skip_flag=self._skip)
+        self._skip = None
         self.mark_updated()
 
     def mark_updated(self):

@@ -23,8 +23,46 @@ import contextlib
 import torch
 import torch.distributed as dist
 
+from .. import grad_ops
 from ..loss.loss import hinge_discriminator_loss, hinge_generator_loss
 from ..util.modules import zero_grad
+
+
+class LossScaler:
+    """Dynamic loss scaling, active only with MSB_GRAD_FMT=f16 (the default bf16 backward needs
+    none; see grad_ops.GRAD_FMT).  Same policy as torch.amp.GradScaler:
+    the backward pass is seeded with `scale` instead of 1, the flat gradient is multiplied by
+    1/scale before the step; a non-finite gradient skips the step (on the device) and halves the
+    scale, `growth_interval` clean steps double it.  The scale lives in device memory so that a
+    captured CUDA graph reads the current value."""
+
+    def __init__(self, device, init_scale=2.0 ** 16, growth_interval=500, max_scale=2.0 ** 30):
+        self.enabled = grad_ops.NEEDS_LOSS_SCALE
+        self.scale = float(init_scale) if self.enabled else 1.0
+        self.growth_interval = growth_interval
+        self.max_scale = max_scale
+        self.clean = 0
+        self.skipped = 0
+        self.scale_dev = torch.full((), self.scale, dtype=torch.float32, device=device)
+        self.inv_scale_dev = torch.full((1,), 1.0 / self.scale, dtype=torch.float32, device=device)
+
+    def _set(self, scale):
+        self.scale = scale
+        self.scale_dev.fill_(scale)
+        self.inv_scale_dev.fill_(1.0 / scale)
+
+    def update(self, found_inf):
+        if not self.enabled:
+            return
+        if found_inf:
+            self.skipped += 1
+            self.clean = 0
+            self._set(max(self.scale * 0.5, 1.0))
+        else:
+            self.clean += 1
+            if self.clean >= self.growth_interval and self.scale < self.max_scale:
+                self.clean = 0
+                self._set(self.scale * 2.0)
 
 
 @contextlib.contextmanager
@@ -71,6 +109,37 @@ class _GraphMixin:
     def _all_params(self):
         return list(self.generator.parameters()) + list(self.discriminator.parameters())
 
+    #: initial loss scale of this trainer's backward (None: LossScaler default)
+    init_loss_scale = None
+
+    def _scaler(self, device):
+        if getattr(self, "scaler", None) is None:
+            kw = {} if self.init_loss_scale is None else {"init_scale": self.init_loss_scale}
+            self.scaler = LossScaler(device, **kw)
+        return self.scaler
+
+    def _finish(self, optim, module):
+        """after backward: data-parallel reduction, un-scaling + overflow check, optimiser step,
+        loss-scale update"""
+        sc = self.scaler
+        if hasattr(optim, "unscale_"):                    # .optim.Adam: all on the device
+            if sc.enabled:
+                optim.unscale_(sc.inv_scale_dev)
+            optim.step()
+            if sc.enabled:
+                sc.update(bool(optim.found_inf.item()))
+            return
+        _sync_grads(optim, module)                        # any torch optimiser
+        bad = False
+        if sc.enabled:
+            for p in module.parameters():
+                if p.grad is not None:
+                    p.grad.mul_(1.0 / sc.scale)
+                    bad = bad or not bool(torch.isfinite(p.grad).all())
+        if not bad:
+            optim.step()
+        sc.update(bad)
+
     def _run(self, samples, features):
         """eager or graphed zero_grad + forward + backward -> tuple of output tensors"""
         if not self.cuda_graph:
@@ -95,6 +164,10 @@ class _GraphMixin:
 
 
 class GeneratorTrainer(_GraphMixin):
+    # the generator's gradient passes through the discriminator and batch means over whole
+    # feature maps: activation gradients of 1e-6 .. 1e-9
+    init_loss_scale = 2.0 ** 22
+
     def __init__(self, generator, g_optim, discriminator, d_optim, loss,
                  sub_loss=hinge_generator_loss, exact_reference_grads=False, cuda_graph=False):
         super().__init__()
@@ -119,13 +192,12 @@ class GeneratorTrainer(_GraphMixin):
                 with torch.no_grad():
                     r_features, r_score = self.discriminator(samples, features)
         loss = self.loss(r_features, f_features, r_score, f_score, gan_loss=self.sub_loss)
-        loss.backward()
+        loss.backward(self._scaler(loss.device).scale_dev)
         return loss.detach(), fake.detach()
 
     def train(self, samples, features):
         loss, fake = self._run(samples, features)
-        _sync_grads(self.g_optim, self.generator)
-        self.g_optim.step()
+        self._finish(self.g_optim, self.generator)
         try:
             fake = fake.data.cpu().numpy()
         except AttributeError:
@@ -156,11 +228,10 @@ class DiscriminatorTrainer(_GraphMixin):
         _, f_score = self.discriminator(fake, features)
         _, r_score = self.discriminator(samples, features)
         loss = self.loss(r_score, f_score, gan_loss=self.sub_loss)
-        loss.backward()
+        loss.backward(self._scaler(loss.device).scale_dev)
         return (loss.detach(),)
 
     def train(self, samples, features):
         (loss,) = self._run(samples, features)
-        _sync_grads(self.d_optim, self.discriminator)
-        self.d_optim.step()
+        self._finish(self.d_optim, self.discriminator)
         return {'d_loss': loss.item()}

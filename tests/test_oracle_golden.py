@@ -250,3 +250,37 @@ def test_multiscale_pair_restatement_matches_reference(golden):
             for i, f in enumerate(fl):
                 assert tuple(f.shape) == tuple(gd[f"f{gi}_{i}_shape"])
                 assert rel_l2(f.reshape(-1)[::13], gd[f"f{gi}_{i}_sub"]) < 2e-5
+
+
+def test_generator_gradient_tolerance_is_set_by_forward_rounding():
+    """Why the training parity tests allow 5e-2 on generator gradients: the oracle with an EXACT
+    fp32 backward but the tensor-core layers' forward operands rounded to fp16 (what the parity
+    bar of 1e-3 on the waveform permits) already differs from the fp32 reference by ~4e-2 --
+    LeakyReLU masks flip where activations are within the rounding error of zero.  The GPU
+    path measures the same 4.2e-2 with bf16 AND with fp16 backward operands."""
+    import torch.nn.functional as F
+    B, T = 2, 8
+    g_sd = restate.randomize_biases(restate.melgan_generator_state(121), 1121)
+    d_sd = restate.randomize_biases(restate.melgan_discriminator_state(122), 1122)
+    samples = synth.randn(123, B, 1, 256 * T) * 0.1
+    features = synth.mel_features(125, B, T)
+    kw = dict(sub_loss=restate.least_squares_generator_loss)
+    _, _, ref, _ = restate.generator_train_step(g_sd, d_sd, samples, features, {}, **kw)
+    c1, ct = F.conv1d, F.conv_transpose1d
+
+    def r(t):                                   # round in the forward, identity in the backward
+        return t + (t.half().float() - t).detach()
+
+    def conv1d(x, w, b=None, *a, **k):
+        if w.shape[0] == 1 or k.get("groups", 1) > 1 or x.shape[1] == 1:
+            return c1(x, w, b, *a, **k)         # fp32 layers: mono convs, grouped / direct convs
+        return c1(r(x), r(w), b, *a, **k)
+
+    F.conv1d = conv1d
+    F.conv_transpose1d = lambda x, w, b=None, *a, **k: ct(r(x), r(w), b, *a, **k)
+    try:
+        _, _, emu, _ = restate.generator_train_step(g_sd, d_sd, samples, features, {}, **kw)
+    finally:
+        F.conv1d, F.conv_transpose1d = c1, ct
+    worst = max(rel_l2(emu[k], ref[k]) for k in ref)
+    assert 5e-3 < worst < 8e-2, worst
