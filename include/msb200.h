@@ -322,6 +322,18 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
  * GEMM, whose other operand is a bf16 gradient) */
 ms_status ms_blk16_convert(const void* src, void* dst, size_t elems, int src_fmt, int dst_fmt,
                            void* stream);
+/* gradients of the layout kernels of the filter-bank / strided-conv paths:
+ *   ms_diag_sum_bwd          dz32[b,u,i] = dy[b, u-i-skew] (i < nphase), BLK f32 (B,channels/8,z_len,8)
+ *   ms_expand_mono_bwd       dx[b,t] = sum_{i<16} de32[b, t-i+shift, i], de32 BLK f32 (B,2,exp_len,8)
+ *   ms_depth_to_space_blk32  dx32[b,c,t] = dys32[b,(t%s)*C/8+c8,t/s+row_offset] for t < len and
+ *                            t/s < rows_valid, else 0; dys32 BLK f32 (B, s*C/8, src_rows, 8), dx32 (B, C/8, out_rows, 8) */
+ms_status ms_diag_sum_bwd(const float* dy, float* dz32, int batch, int channels, int z_len,
+                          int out_len, int nphase, int skew, void* stream);
+ms_status ms_expand_mono_bwd(const float* de32, float* dx, int batch, int len, int exp_len,
+                             int shift, void* stream);
+ms_status ms_depth_to_space_blk32(const float* dys32, float* dx32, int batch, int channels,
+                                  int src_rows, int rows_valid, int row_offset, int out_rows,
+                                  int len, int stride, void* stream);
 /* NCL f32 -> BLK f32 (gradient of ms_unpack_blk32_to_ncl) */
 ms_status ms_pack_ncl_to_blk32(const float* x, float* y32, int batch, int channels, int len,
                                void* stream);

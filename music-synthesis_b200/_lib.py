@@ -93,6 +93,11 @@ SIGNATURES = {
     "ms_weight_split": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                 c_void_p]),
     "ms_blk16_convert": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "ms_diag_sum_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_void_p]),
+    "ms_expand_mono_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ms_depth_to_space_blk32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_void_p]),
     "ms_pack_ncl_to_blk32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ms_conv1d_direct_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -93,10 +93,24 @@ class FilterBank:
         d = ops.conv_desc(MS_CONV, B, 16, n, Lx, taps, 16, 0, operand=self.operand)
         key = ("a", x.device)
         if key not in self._packed:
-            # W[f, i, j] = bank[f, 16 j + i]
-            w = self.filter_bank.to(x.device).reshape(n, taps, 16).permute(0, 2, 1).contiguous()
-            self._packed[key] = ops.pack_conv_weight(d, w)
+            self._packed[key] = ops.pack_conv_weight(d, self.analysis_weight(x.device))
         return ops.conv_fwd(d, x16, self._packed[key], None, want16=want16, want32=want32)
+
+    def analysis_weight(self, device):
+        """(n, 16, k/16) weight of the analysis conv over the 16-wide sliding-window expansion:
+        W[f, i, j] = bank[f, 16 j + i]"""
+        n, taps = self.n_bands, self.kernel_size // 16
+        return self.filter_bank.to(device).reshape(n, taps, 16).permute(0, 2, 1).contiguous()
+
+    def synthesis_weight(self, device):
+        """(16, n, k/8) weight of the synthesis conv (8 phase channels used):
+        Wg[i, c, j] = flip(bank)[c, 8 j + i]"""
+        n, k = self.n_bands, self.kernel_size
+        taps = k // 8
+        wf = torch.flip(self.filter_bank.to(device).reshape(n, k), dims=[1])
+        w = torch.zeros((16, n, taps), dtype=torch.float32, device=device)
+        w[:8] = wf.reshape(n, taps, 8).permute(2, 0, 1)
+        return w.contiguous()
 
     def convolve(self, x):
         return ops.unpack_blk32(self._analysis(x, False, True)[1])
@@ -110,12 +124,7 @@ class FilterBank:
     def _synth_weights(self, d, device):
         key = ("s", device)
         if key not in self._packed:
-            n, k = self.n_bands, self.kernel_size
-            taps = k // 8
-            wf = torch.flip(self.filter_bank.to(device).reshape(n, k), dims=[1])   # w'[c, k']
-            w = torch.zeros((16, n, taps), dtype=torch.float32, device=device)
-            w[:8] = wf.reshape(n, taps, 8).permute(2, 0, 1)      # Wg[i, c, j] = w'[c, 8 j + i]
-            self._packed[key] = ops.pack_conv_weight(d, w.contiguous())
+            self._packed[key] = ops.pack_conv_weight(d, self.synthesis_weight(device))
         return self._packed[key]
 
     def transposed_convolve_blocked(self, x16, L):

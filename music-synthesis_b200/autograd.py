@@ -62,13 +62,16 @@ class WeightCache:
         return self._bwd[1]
 
 
-def _dgrad_conv(cache, w, dz16, kind, dilation, pad, stride, res32=None):
-    """input gradient (BLK f32) of a dense conv / transposed conv; `res32` added in the epilogue"""
+def _dgrad_conv(cache, w, dz16, kind, dilation, pad, stride, res32=None, extra_pad=0):
+    """input gradient (BLK f32) of a dense conv / transposed conv; `res32` added in the epilogue.
+    extra_pad: the forward conv dropped `extra_pad` output rows at the end (crop = a smaller right
+    padding); its input gradient needs that much more padding -- the result then starts
+    `extra_pad` rows early (row u of the true gradient is row u + extra_pad)."""
     B, _, L, _ = dz16.shape
     if kind == MS_CONV:
         cout, cin, k = w.shape
-        d = ops.conv_desc(MS_CONV, B, cout, cin, L, k, dilation, dilation * (k - 1) - pad,
-                          operand=GRAD_FMT)
+        d = ops.conv_desc(MS_CONV, B, cout, cin, L, k, dilation,
+                          dilation * (k - 1) - pad + extra_pad, operand=GRAD_FMT)
     else:
         cin, cout, k = w.shape
         d = ops.conv_desc(MS_CONV, B, stride * cout, cin, L, 3, 1, 1, operand=GRAD_FMT)
@@ -263,6 +266,119 @@ class DenseConvNCL(Function):
         if ctx.needs_input_grad[0]:
             dx = ops.unpack_blk32(_dgrad_conv(cache, w, dz16, MS_CONV, 1, pad, 1))
         return dx, dw, db, None, None, None
+
+
+class BankSynthesis(Function):
+    """zounds FilterBank.transposed_convolve on the last generator activation
+    (generator/multiscale.py:90-91): (h32, h16) BLK (B,n/8,L,8) -> (B,1,L).  The bank is fixed:
+    backward = ms_diag_sum_bwd -> bf16 operand -> input-gradient conv with the bank weights."""
+
+    @staticmethod
+    def forward(ctx, h32, h16, bank):
+        L = h16.shape[2]
+        ctx.bank = bank
+        ctx.shape = tuple(h16.shape)
+        return bank.transposed_convolve_blocked(h16, L)
+
+    @staticmethod
+    def backward(ctx, dy):
+        bank = ctx.bank
+        B, _, L, _ = ctx.shape
+        k = bank.kernel_size
+        lz = L + 2 * (k // 2) - 8 * (k // 8 - 1)
+        dz32 = grad_ops.diag_sum_bwd(dy, 16, lz, 8, 1)
+        dz16, _ = grad_ops.act_bwd(dz32, want_bias=False)
+        w = bank.synthesis_weight(dy.device)
+        cache = bank.__dict__.setdefault("_synth_dgrad_cache", WeightCache())
+        return _dgrad_conv(cache, w, dz16, MS_CONV, 8, k // 2, 1), None, None
+
+
+class BankAnalysis(Function):
+    """zounds FilterBank.convolve (discriminator/multiscale.py:112) with a differentiable input:
+    x (B,1,L) -> (a32, a16) BLK (B,n/8,L+1,8).  Backward = input-gradient conv with the bank
+    weights over the 16-wide expansion, then ms_expand_mono_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, bank):
+        a16, a32 = bank._analysis(x, True, True)
+        ctx.bank = bank
+        ctx.L = x.shape[-1]
+        ctx.mark_non_differentiable(a16)
+        return a32, a16
+
+    @staticmethod
+    def backward(ctx, da32, _unused):
+        bank = ctx.bank
+        k = bank.kernel_size
+        dz16, _ = grad_ops.act_bwd(da32, want_bias=False)
+        w = bank.analysis_weight(da32.device)
+        cache = bank.__dict__.setdefault("_analysis_dgrad_cache", WeightCache())
+        de32 = _dgrad_conv(cache, w, dz16, MS_CONV, 16, 0, 1)
+        return grad_ops.expand_mono_bwd(de32, ctx.L, k // 2), None
+
+
+class StridedCache:
+    """weights of a stride-s conv rewritten as a stride-1 conv over the space-to-depth input
+    (ops.strided_conv_weight) + their packed forward / input-gradient images"""
+
+    def __init__(self):
+        self.key = None
+        self.w1 = self.taps = self.pad = None
+        self.cache = WeightCache()
+
+    def get(self, w, stride):
+        key = (w.data_ptr(), w._version, stride)
+        if key != self.key:
+            self.w1, self.taps, self.pad = ops.strided_conv_weight(w.detach(), stride)
+            self.key = key
+        return self.w1, self.taps, self.pad
+
+
+class StridedConvBlk(Function):
+    """LeakyReLU(Conv1d(C, Cout, k, stride s, padding k//2)) on channel-blocked tensors
+    (discriminator/multiscale.py:83-88, 103-107): space-to-depth + stride-1 tcgen05 conv.
+    `length` = valid rows of the input (its tensor may carry one extra row).  -> (y32, y16)"""
+
+    @staticmethod
+    def forward(ctx, h32, h16, w, b, sc, stride, length):
+        B = h16.shape[0]
+        cout, cin, k = w.shape
+        xs = ops.space_to_depth(h16, stride, length)
+        lx = xs.shape[2]
+        w1, taps, pad = sc.get(w, stride)
+        crop = lx + 2 * pad - (taps - 1) - lx
+        d = ops.conv_desc(MS_CONV, B, stride * cin, cout, lx, taps, 1, pad, leaky=True, crop=crop)
+        y16, y32 = ops.conv_fwd(d, xs, sc.cache.fwd(d, w1), b, want16=True, want32=True)
+        ctx.save_for_backward(xs, w, y16)
+        ctx.cfg = (sc, stride, length, h16.shape[2], crop, b is not None)
+        ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, _unused):
+        xs, w, y16 = ctx.saved_tensors
+        sc, stride, length, in_rows, crop, has_bias = ctx.cfg
+        cout, cin, k = w.shape
+        w1, taps, pad = sc.get(w, stride)
+        dz16, db = grad_ops.act_bwd(dy32, sign16=y16, want_bias=has_bias and ctx.needs_input_grad[3])
+        dw = None
+        if ctx.needs_input_grad[2]:
+            dw1 = grad_ops.conv_wgrad(dz16, xs, tuple(w1.shape), 1, pad)
+            # back to the (Cout, C, k) layout: tap kk = (j, i) with kk - k//2 = s*j + i
+            half = k // 2
+            j_min = -((half + stride - 1) // stride)
+            dw = torch.empty_like(w)
+            for kk in range(k):
+                m = kk - half
+                j, i = m // stride, m % stride
+                dw[:, :, kk] = dw1[:, i * cin:(i + 1) * cin, j - j_min]
+        dx32 = None
+        if ctx.needs_input_grad[0]:
+            dxs = _dgrad_conv(sc.cache, w1, dz16, MS_CONV, 1, pad, 1, extra_pad=crop)
+            lx = xs.shape[2]                       # dxs: lx + crop rows, true row u at u + crop
+            dx32 = grad_ops.depth_to_space32(dxs, cin, stride, in_rows, length, rows_valid=lx,
+                                             row_offset=crop)
+        return dx32, None, dw, db, None, None, None
 
 
 class AvgPool(Function):

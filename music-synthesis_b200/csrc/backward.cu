@@ -150,6 +150,61 @@ __global__ void pack_ncl_to_blk32_kernel(const float* __restrict__ x, float* __r
   st_global_v8(y + i * 8, f);
 }
 
+// ---- backward of the layout kernels of the filter-bank / strided-conv paths (csrc/layout.cu) ----
+// ms_diag_sum: y[b,t] = sum_{i<nphase} z[b, t+i+skew, i]  ->  dz[b,u,i] = dy[b, u-i-skew]
+__global__ void diag_sum_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dz, int C8,
+                                    int Lz, int L, int nphase, int skew, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;                       // one thread per (b, c8, u): 8 channels
+  const int u = static_cast<int>(gid % Lz);
+  const size_t bc = gid / Lz;
+  const int c8 = static_cast<int>(bc % C8);
+  const size_t b = bc / C8;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = c8 * 8 + j;
+    const int t = u - i - skew;
+    f[j] = (i < nphase && t >= 0 && t < L) ? __ldg(dy + b * L + t) : 0.f;
+  }
+  st_global_v8(dz + gid * 8, f);
+}
+
+// ms_expand_mono_to_blk16: Y[b,u,i] = x[b, u+i-shift]  ->  dx[b,t] = sum_i dY[b, t-i+shift, i]
+__global__ void expand_mono_bwd_kernel(const float* __restrict__ dE, float* __restrict__ dx, int L,
+                                       int Lx, int shift, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = static_cast<int>(gid % L);
+  const size_t b = gid / L;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int u = t - i + shift;
+    if (u >= 0 && u < Lx) acc += __ldg(dE + ((b * 2 + (i >> 3)) * Lx + u) * 8 + (i & 7));
+  }
+  dx[gid] = acc;
+}
+
+// ms_space_to_depth_blk16: Y[b, i*C8+c, u] = X[b, c, s*u+i]  ->  dX[b,c,t] = dY[b,(t%s)*C8+c,t/s]
+// (fp32; dY row u is stored at row u + row_off; rows u >= rows_valid do not exist = zero; rows
+// t >= len of dX are zero)
+__global__ void depth_to_space_blk32_kernel(const float* __restrict__ dys, float* __restrict__ dx,
+                                            int C8, int lx_rows, int rows_valid, int row_off,
+                                            int out_rows, int len, int stride, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = static_cast<int>(gid % out_rows);
+  const size_t bc = gid / out_rows;
+  const int c = static_cast<int>(bc % C8);
+  const size_t b = bc / C8;
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int u = t / stride, i = t - u * stride;
+  if (t < len && u < rows_valid)
+    ld_global_nc_v8(dys + ((b * stride * C8 + static_cast<size_t>(i) * C8 + c) * lx_rows + u + row_off) * 8, f);
+  st_global_v8(dx + gid * 8, f);
+}
+
 // ------------------------------------------------------------ direct conv backward (NCL f32)
 struct DirectBwdParams {
   const float* dy;   // (B, cout, lout)
@@ -910,6 +965,42 @@ ms_status ms_grad_unscale_check(float* grad, size_t n, const float* inv_scale_de
   grad_unscale_check_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
       grad, n, inv_scale_dev, flag_dev);
   return after_launch("grad_unscale_check_kernel");
+}
+
+ms_status ms_diag_sum_bwd(const float* dy, float* dz32, int batch, int channels, int z_len,
+                          int out_len, int nphase, int skew, void* stream) {
+  if (dy == nullptr || dz32 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
+      z_len <= 0 || out_len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * z_len;
+  diag_sum_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(dy, dz32, channels / 8, z_len, out_len,
+                                                             nphase, skew, total);
+  return after_launch("diag_sum_bwd_kernel");
+}
+
+ms_status ms_expand_mono_bwd(const float* de32, float* dx, int batch, int len, int exp_len,
+                             int shift, void* stream) {
+  if (de32 == nullptr || dx == nullptr || batch <= 0 || len <= 0 || exp_len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * len;
+  expand_mono_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                           static_cast<cudaStream_t>(stream)>>>(de32, dx, len, exp_len, shift, total);
+  return after_launch("expand_mono_bwd_kernel");
+}
+
+ms_status ms_depth_to_space_blk32(const float* dys32, float* dx32, int batch, int channels,
+                                  int src_rows, int rows_valid, int row_offset, int out_rows,
+                                  int len, int stride, void* stream) {
+  if (dys32 == nullptr || dx32 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
+      src_rows <= 0 || out_rows <= 0 || stride < 1 || row_offset < 0 ||
+      rows_valid + row_offset > src_rows)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * out_rows;
+  depth_to_space_blk32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                                static_cast<cudaStream_t>(stream)>>>(
+      dys32, dx32, channels / 8, src_rows, rows_valid, row_offset, out_rows, len, stride, total);
+  return after_launch("depth_to_space_blk32_kernel");
 }
 
 }  // extern "C"

@@ -16,7 +16,8 @@ import numpy as np
 import torch
 from torch import nn
 
-from .. import ops
+from .. import autograd as ag
+from .. import grad_ops, ops
 from .._lib import MS_CONV, MS_F16, MsbError
 from ..audio.filterbank import FilterBank, linear_center_frequencies
 from ..audio.transform import fft_frequency_decompose
@@ -73,6 +74,32 @@ class FilterBankChannelDiscriminator(nn.Module):
         self.judge = nn.Conv1d(channels[-1], 1, 3, 1, 1)
         self._pm = [_PackedStrided() for _ in self.main]
         self._pj = [_PackedConv() for _ in self.mj]
+        self._sc = [ag.StridedCache() for _ in self.main]
+        self._cj = [ag.WeightCache() for _ in self.mj]
+
+    def forward_blocked_train(self, x, feat32, feat16):
+        """autograd-recorded form: x (B,1,L) (may require grad); conditioning as BLK f32 / f16.
+        Returns ([7 NCL maps], h32, h16 of the last map, judgement)."""
+        L = x.shape[-1]
+        features = []
+        if x.requires_grad:
+            h32, h16 = ag.BankAnalysis.apply(x, self.filter_bank)
+        else:
+            h16, h32 = self.filter_bank._analysis(x, True, False)
+        length = L
+        for conv, sc in zip(self.main, self._sc):
+            s = conv.stride[0]
+            h32, h16 = ag.StridedConvBlk.apply(h32, h16, conv.weight, conv.bias, sc, s, length)
+            features.append(ag.UnpackBlk32.apply(h32))
+            length = h16.shape[2]
+        if self.conditioning_channels > 0:
+            h32 = torch.cat([h32, feat32], dim=1)
+            h16 = torch.cat([h16, feat16], dim=1)
+        for conv, cj in zip(self.mj, self._cj):
+            h32, h16 = ag.ConvBlk.apply(h32, h16, conv.weight, conv.bias, cj, MS_CONV, 1, 1, 1, True)
+            features.append(ag.UnpackBlk32.apply(h32))
+        j = ag.MonoConv.apply(h32, self.judge.weight, self.judge.bias, 3, 1, False)
+        return features, h32, h16, j
 
     def forward_blocked(self, x, feat16):
         """x (B,1,L) f32; feat16 BLK 16-bit conditioning or None.
@@ -153,6 +180,7 @@ class FilterBankMultiScaleDiscriminator(nn.Module):
             nn.Conv1d(channels, channels, 3, 1, 1))
         self.judge = nn.Conv1d(channels, 1, 3, 1, 1)
         self._pf = [_PackedConv() for _ in self.final]
+        self._cf = [ag.WeightCache() for _ in self.final]
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -161,8 +189,41 @@ class FilterBankMultiScaleDiscriminator(nn.Module):
             d.filter_bank.to(probe.device)
         return out
 
+    def _forward_train(self, bands, feat):
+        """autograd-recorded path (training): Functions over the C ABI, see ../autograd.py"""
+        cond = self.conditioning_channels > 0
+        feat32 = grad_ops.pack_ncl32(feat) if cond else None
+        feat16 = ops.pack_ncl(feat) if cond else None
+        features, c32, c16, judgements = [], [], [], []
+        for size, layer in self.channel_discs.items():
+            f, h32, h16, j = layer.forward_blocked_train(bands[size], feat32, feat16)
+            features.append(f)
+            c32.append(h32)
+            c16.append(h16)
+            judgements.append(j)
+        x32, x16 = torch.cat(c32, dim=1), torch.cat(c16, dim=1)
+        if cond:
+            T = x16.shape[2]
+            if feat.shape[-1] != T:      # F.upsample(feat, size=T): nearest neighbour
+                idx = (torch.arange(T, device=feat.device) * feat.shape[-1]) // T
+                up = feat[..., idx].contiguous()
+                feat32, feat16 = grad_ops.pack_ncl32(up), ops.pack_ncl(up)
+            x32, x16 = torch.cat([x32, feat32], dim=1), torch.cat([x16, feat16], dim=1)
+        final_features = []
+        for conv, cf in zip(self.final, self._cf):
+            x32, x16 = ag.ConvBlk.apply(x32, x16, conv.weight, conv.bias, cf, MS_CONV, 1, 1, 1, True)
+            final_features.append(ag.UnpackBlk32.apply(x32))
+        features.append(final_features)
+        judgements.append(ag.MonoConv.apply(x32, self.judge.weight, self.judge.bias, 3, 1, False))
+        return features, judgements
+
     def forward(self, x, feat):
-        _fwd_only(self, x)
+        probe = x if isinstance(x, torch.Tensor) else next(iter(x.values()))
+        if ag.needs_grad(self, probe):
+            if self.decompose:
+                raise MsbError("training with decompose=True is not on this path (the experiment "
+                               "feeds band dictionaries: experiment/multiscale.py:42-46)")
+            return self._forward_train(x, feat)
         bands = fft_frequency_decompose(x, self.smallest_band) if self.decompose else x
         cond = self.conditioning_channels > 0
         feat16 = ops.pack_ncl(feat) if cond else None

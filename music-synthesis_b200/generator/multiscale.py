@@ -15,6 +15,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from .. import autograd as ag
 from .. import ops
 from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
 from ..audio.filterbank import FilterBank, SampleRate, linear_center_frequencies
@@ -49,6 +50,19 @@ class FilterBankChannelGenerator(nn.Module):
                     activation=None, operand=operand))
         self.main = nn.Sequential(*layers)
         self._packed = [_PackedConv() for _ in layers]
+        self._cache = [ag.WeightCache() for _ in layers]
+
+    def forward_blocked_train(self, x16):
+        """autograd-recorded form (training): every block is a Function over the C ABI"""
+        emb = self.main[0][0]
+        h32, h16 = ag.ConvBlk.apply(None, x16, emb.weight, emb.bias, self._cache[0], MS_CONV, 1, 3,
+                                    1, True)
+        for i in range(1, len(self.main)):
+            up = self.main[i]
+            s = up.scale_factor
+            h32, h16 = ag.ConvBlk.apply(h32, h16, up.conv.weight, None, self._cache[i], MS_CONVT, 1,
+                                        s // 2, s, True)
+        return ag.BankSynthesis.apply(h32, h16, self.filter_bank)
 
     def forward_blocked(self, x16, T):
         """x16: BLK 16-bit (B, Cin/8, T, 8) features (shared by all bands)."""
@@ -69,9 +83,10 @@ class FilterBankChannelGenerator(nn.Module):
         return self.filter_bank.transposed_convolve_blocked(h16, L)
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or
-                                        any(p.requires_grad for p in self.parameters())):
-            raise MsbError("sm_100a path is forward-only in this build: use torch.no_grad()")
+        if ag.needs_grad(self, x):
+            if x.requires_grad:
+                raise MsbError("gradients w.r.t. the conditioning features are not on this path")
+            return self.forward_blocked_train(ops.pack_ncl(x))
         return self.forward_blocked(ops.pack_ncl(x, operand=self.operand), x.shape[-1])
 
 
@@ -115,14 +130,15 @@ class FilterBankMultiScaleGenerator(nn.Module):
         return out
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or
-                                        any(p.requires_grad for p in self.parameters())):
-            raise MsbError("sm_100a path is forward-only in this build: use torch.no_grad()")
+        train = ag.needs_grad(self, x)
+        if train and x.requires_grad:
+            raise MsbError("gradients w.r.t. the conditioning features are not on this path")
         input_size = x.shape[-1]
         x16 = ops.pack_ncl(x)
         results = {}
         for size, layer in self.channel_generators.items():
-            results[size] = layer.forward_blocked(x16, input_size)
+            results[size] = layer.forward_blocked_train(x16) if train else \
+                layer.forward_blocked(x16, input_size)
         if self.recompose:
             return fft_frequency_recompose(results, input_size * self.upsample_ratio)
         return results

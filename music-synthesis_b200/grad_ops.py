@@ -202,3 +202,34 @@ def grad_unscale_check(grad, inv_scale_dev, flag_dev):
     """grad *= inv_scale (device scalar) in place; flag_dev <- any non-finite element"""
     check(_lib.lib().ms_grad_unscale_check(ptr(grad), grad.numel(), ptr(inv_scale_dev),
                                            ptr(flag_dev), stream_ptr()), "ms_grad_unscale_check")
+
+
+def diag_sum_bwd(dy, channels, z_len, nphase, skew):
+    dy = dy.contiguous()
+    B, _, L = dy.shape
+    dz = torch.empty((B, channels // 8, z_len, 8), dtype=torch.float32, device=dy.device)
+    check(_lib.lib().ms_diag_sum_bwd(ptr(dy), ptr(dz), B, channels, z_len, L, nphase, skew,
+                                     stream_ptr()), "ms_diag_sum_bwd")
+    return dz
+
+
+def expand_mono_bwd(de32, length, shift):
+    de32 = de32.contiguous()
+    B, _, Lx, _ = de32.shape
+    dx = torch.empty((B, 1, length), dtype=torch.float32, device=de32.device)
+    check(_lib.lib().ms_expand_mono_bwd(ptr(de32), ptr(dx), B, length, Lx, shift, stream_ptr()),
+          "ms_expand_mono_bwd")
+    return dx
+
+
+def depth_to_space32(dys32, channels, stride, out_rows, length, rows_valid=None, row_offset=0):
+    """gradient of ops.space_to_depth: (B, s*C/8, rows, 8) f32 -> (B, C/8, out_rows, 8) f32;
+    space-to-depth row u is read from row u + row_offset, rows u >= rows_valid count as zero"""
+    dys32 = dys32.contiguous()
+    B, _, lx, _ = dys32.shape
+    dx = torch.empty((B, channels // 8, out_rows, 8), dtype=torch.float32, device=dys32.device)
+    check(_lib.lib().ms_depth_to_space_blk32(ptr(dys32), ptr(dx), B, channels, lx,
+                                             (lx - row_offset) if rows_valid is None else rows_valid,
+                                             row_offset, out_rows, length, stride, stream_ptr()),
+          "ms_depth_to_space_blk32")
+    return dx

@@ -193,7 +193,8 @@ class GeneratorTrainer(_GraphMixin):
                     r_features, r_score = self.discriminator(samples, features)
         loss = self.loss(r_features, f_features, r_score, f_score, gan_loss=self.sub_loss)
         loss.backward(self._scaler(loss.device).scale_dev)
-        return loss.detach(), fake.detach()
+        fake = {k: v.detach() for k, v in fake.items()} if isinstance(fake, dict) else fake.detach()
+        return loss.detach(), fake
 
     def train(self, samples, features):
         loss, fake = self._run(samples, features)

@@ -570,16 +570,29 @@ def _leaf(sd):
     return {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
 
 
+def _melgan_gen(features, g_sd):
+    return melgan_generator(features, g_sd)
+
+
+def _melgan_disc(x, features, d_sd):
+    return melgan_discriminator(x, d_sd)          # unconditioned: ignores the features
+
+
+def _detach(x):
+    return {k: v.detach() for k, v in x.items()} if isinstance(x, dict) else x.detach()
+
+
 @torch.enable_grad()
-def discriminator_train_step(g_sd, d_sd, samples, features, d_state,
-                             sub_loss=None):
-    """train/train.py:63-74 -> (d_loss, grads of D, new D state dict)"""
+def discriminator_train_step(g_sd, d_sd, samples, features, d_state, sub_loss=None,
+                             gen_fn=_melgan_gen, disc_fn=_melgan_disc):
+    """train/train.py:63-74 -> (d_loss, grads of D, new D state dict).  gen_fn / disc_fn select
+    the model pair (default MelGanGenerator / MelGanDiscriminator)."""
     sub_loss = sub_loss or hinge_discriminator_loss
     d = _leaf(d_sd)
     with torch.no_grad():
-        fake = melgan_generator(features, g_sd)
-    _, f_score = melgan_discriminator(fake, d)
-    _, r_score = melgan_discriminator(samples, d)
+        fake = gen_fn(features, g_sd)
+    _, f_score = disc_fn(fake, features, d)
+    _, r_score = disc_fn(samples, features, d)
     loss = mel_gan_disc_loss(r_score, f_score, gan_loss=sub_loss)
     names = list(d)
     grads = dict(zip(names, torch.autograd.grad(loss, [d[n] for n in names])))
@@ -588,19 +601,20 @@ def discriminator_train_step(g_sd, d_sd, samples, features, d_state,
 
 
 @torch.enable_grad()
-def generator_train_step(g_sd, d_sd, samples, features, g_state, sub_loss=None):
+def generator_train_step(g_sd, d_sd, samples, features, g_state, sub_loss=None,
+                         gen_fn=_melgan_gen, disc_fn=_melgan_disc):
     """train/train.py:26-42 -> (g_loss, fake, grads of G, new G state dict)"""
     sub_loss = sub_loss or hinge_generator_loss
     g = _leaf(g_sd)
-    fake = melgan_generator(features, g)
-    f_features, f_score = melgan_discriminator(fake, d_sd)
+    fake = gen_fn(features, g)
+    f_features, f_score = disc_fn(fake, features, d_sd)
     with torch.no_grad():
-        r_features, r_score = melgan_discriminator(samples, d_sd)
+        r_features, r_score = disc_fn(samples, features, d_sd)
     loss = mel_gan_gen_loss(r_features, f_features, r_score, f_score, gan_loss=sub_loss)
     names = list(g)
     grads = dict(zip(names, torch.autograd.grad(loss, [g[n] for n in names])))
     new = adam_restated({k: v.detach() for k, v in g.items()}, grads, g_state)
-    return loss.item(), fake.detach(), grads, new
+    return loss.item(), _detach(fake), grads, new
 
 
 # ---------------------------------------------------------------------------------------

@@ -210,3 +210,63 @@ def test_short_sequences_top_of_discriminator(L):
         e = rel_l2(got, ref)
         print("short L", L, name, e)
         assert e < 5e-3, (name, e)
+
+
+@pytest.mark.parametrize("B,C,Co,L,s", [(2, 128, 128, 512, 4), (2, 128, 128, 128, 2), (3, 128, 128, 33, 4),
+                                        (2, 64, 128, 100, 2)])
+def test_strided_conv_block_backward(B, C, Co, L, s):
+    """stride-s k7 conv + LeakyReLU as space-to-depth + tcgen05 conv (discriminator/multiscale.py:
+    83-88): forward, input gradient (depth-to-space of the dgrad conv) and weight gradient (tap
+    re-mapping of the wgrad GEMM) vs CPU autograd; the input carries one extra row like the
+    filter bank's analysis output"""
+    from music_synthesis_b200 import autograd as ag, grad_ops, ops
+    x = synth.randn(40, B, C, L + 1).requires_grad_()
+    w = (synth.randn(41, Co, C, 7) * 0.05).requires_grad_()
+    b = (synth.randn(42, Co) * 0.1).requires_grad_()
+    y = F.leaky_relu(F.conv1d(x[:, :, :L], w, b, stride=s, padding=3), 0.2)
+    r = synth.randn(43, *y.shape)
+    (y * r).sum().backward()
+    xg = x.detach().cuda().requires_grad_()
+    wg, bg = w.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+    x32 = ag.PackBlk32.apply(xg)
+    y32, _ = ag.StridedConvBlk.apply(x32, ops.pack_ncl(xg.detach()), wg, bg, ag.StridedCache(), s, L)
+    yg = ag.UnpackBlk32.apply(y32)
+    assert yg.shape == y.shape and rel_l2(yg, y) < 1e-3
+    yg.backward(r.cuda())
+    errs = {name: rel_l2(got, ref) for name, got, ref in
+            (("dx", xg.grad, x.grad), ("dw", wg.grad, w.grad), ("db", bg.grad, b.grad))}
+    print("strided", (B, C, Co, L, s), errs)
+    # 1.4e-2 measured with bf16 AND fp16 backward operands alike (db, a pure fp32 sum, included):
+    # ~3e-4 of the LeakyReLU masks differ because the forward ran on fp16 operands
+    assert max(errs.values()) < 3e-2, errs
+
+
+def test_filter_bank_ops_backward():
+    """fixed Morlet bank: analysis (differentiable input) and synthesis (differentiable
+    activations) vs CPU autograd on the same bank tensor"""
+    from music_synthesis_b200 import autograd as ag, ops
+    from music_synthesis_b200.audio.filterbank import FilterBank, linear_center_frequencies
+    fb = FilterBank(22050, 128, linear_center_frequencies(0, 11025, 128), scaling_factors=0.05).to("cuda")
+    bank = fb.filter_bank.cpu()
+    B, L = 2, 300
+    x = (synth.randn(44, B, 1, L) * 0.1).requires_grad_()
+    a = F.conv1d(x, bank, padding=64)                      # (B,128,L+1)
+    ra = synth.randn(45, *a.shape)
+    (a * ra).sum().backward()
+    xg = x.detach().cuda().requires_grad_()
+    a32, _ = ag.BankAnalysis.apply(xg, fb)
+    ag.UnpackBlk32.apply(a32).backward(ra.cuda())
+    e = rel_l2(xg.grad, x.grad)
+    print("bank analysis dx", e)
+    assert e < 6e-3
+    h = synth.randn(46, B, 128, L).requires_grad_()
+    yb = F.conv_transpose1d(F.pad(h, (0, 1)), bank, padding=64)
+    rb = synth.randn(47, *yb.shape)
+    (yb * rb).sum().backward()
+    hg = h.detach().cuda().requires_grad_()
+    ys = ag.BankSynthesis.apply(ag.PackBlk32.apply(hg), ops.pack_ncl(hg.detach()), fb)
+    assert rel_l2(ys, yb) < 1e-3
+    ys.backward(rb.cuda())
+    e = rel_l2(hg.grad, h.grad)
+    print("bank synthesis dh", e)
+    assert e < 6e-3
