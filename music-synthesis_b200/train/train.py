@@ -144,20 +144,27 @@ class _GraphMixin:
         """eager or graphed zero_grad + forward + backward -> tuple of output tensors"""
         if not self.cuda_graph:
             return self._fwd_bwd(samples, features)
-        key = (tuple(samples.shape), tuple(features.shape))
+        multi = isinstance(samples, dict)            # MultiScale audio: {band size: tensor}
+        key = (tuple((k, tuple(v.shape)) for k, v in samples.items()) if multi
+               else tuple(samples.shape), tuple(features.shape))
         st = self._graphs.setdefault(key, _Graphed())
         st.calls += 1
         if st.calls <= 2:                       # warm-up: lazy initialisation, allocator
             return self._fwd_bwd(samples, features)
         if st.graph is None:
-            st.samples, st.features = samples.clone(), features.clone()
+            st.samples = {k: v.clone() for k, v in samples.items()} if multi else samples.clone()
+            st.features = features.clone()
             for p in self._all_params():        # every packed-weight image is rebuilt IN the graph
                 torch.autograd.graph.increment_version(p)
             torch.cuda.synchronize()
             st.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(st.graph):
                 st.outputs = self._fwd_bwd(st.samples, st.features)
-        st.samples.copy_(samples)
+        if multi:
+            for k, v in samples.items():
+                st.samples[k].copy_(v)
+        else:
+            st.samples.copy_(samples)
         st.features.copy_(features)
         st.graph.replay()
         return st.outputs

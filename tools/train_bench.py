@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="GLOBAL batch (clips)")
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--graph", type=int, default=1, help="1: CUDA-graph the steps (default)")
+    ap.add_argument("--pair", default="melgan", choices=["melgan", "fb"],
+                    help="melgan: cfg4 (MelGAN pair, hinge); fb: cfg5 (filter-bank multiscale pair, "
+                         "least squares, 65536-sample clips: use --batch 64 --frames 256)")
     args = ap.parse_args()
 
     import torch
@@ -48,18 +51,36 @@ def main():
     from music_synthesis_b200.loss.loss import mel_gan_disc_loss, mel_gan_gen_loss
 
     torch.manual_seed(0)                       # same init on every rank
-    g = MelGanGenerator(args.frames, 128).cuda()
-    d = MelGanDiscriminator().cuda()
+    per = args.batch // world
+    gen = torch.Generator(device="cuda").manual_seed(1 + rank)
+    feats = torch.randn(per, 128, args.frames, device="cuda", generator=gen) * 0.5 - 2.0
+    real = torch.randn(per, 1, 256 * args.frames, device="cuda", generator=gen) * 0.1
+    sub = {}
+    if args.pair == "fb":
+        # experiment/multiscale.py:16-67: band dictionaries in, least-squares sub-losses
+        from music_synthesis_b200.generator.multiscale import FilterBankMultiScaleGenerator
+        from music_synthesis_b200.discriminator.multiscale import FilterBankMultiScaleDiscriminator
+        from music_synthesis_b200.audio.transform import fft_frequency_decompose
+        from music_synthesis_b200.loss.loss import (least_squares_disc_loss,
+                                                    least_squares_generator_loss)
+        n = 256 * args.frames
+        g = FilterBankMultiScaleGenerator(22050, 128, args.frames, n, recompose=False).cuda()
+        d = FilterBankMultiScaleDiscriminator(n, 22050, decompose=False,
+                                              conditioning_channels=128).cuda()
+        with torch.no_grad():
+            real = fft_frequency_decompose(real, n // 16)
+        sub = {"d": least_squares_disc_loss, "g": least_squares_generator_loss}
+    else:
+        g = MelGanGenerator(args.frames, 128).cuda()
+        d = MelGanDiscriminator().cuda()
     g.apply(weights_init)
     d.apply(weights_init)
     g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
     d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
     d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss, cuda_graph=bool(args.graph))
     g_tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, cuda_graph=bool(args.graph))
-    per = args.batch // world
-    gen = torch.Generator(device="cuda").manual_seed(1 + rank)
-    feats = torch.randn(per, 128, args.frames, device="cuda", generator=gen) * 0.5 - 2.0
-    real = torch.randn(per, 1, 256 * args.frames, device="cuda", generator=gen) * 0.1
+    if sub:
+        d_tr.sub_loss, g_tr.sub_loss = sub["d"], sub["g"]
 
     def cycle():
         a = d_tr.train(real, feats)
@@ -95,9 +116,12 @@ def main():
             "host_ms_per_step": host * 1000.0 / args.steps, "gpu_launches_per_step": launches,
             "higher_is_better": True, "scaling": "strong", "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate",
             "data": "synthetic", "cuda_graph": bool(args.graph), "d_loss": losses[0], "g_loss": losses[1],
-            "config": {"workload": "cfg4: MelGanGenerator + MelGanDiscriminator train cycle, "
-                                   "global batch %d x %d samples, Adam(1e-4,(0.5,0.9)), DP x%d"
-                                   % (args.batch, 256 * args.frames, world)}}))
+            "config": {"workload": "%s train cycle, global batch %d x %d samples, "
+                                   "Adam(1e-4,(0.5,0.9)), DP x%d"
+                                   % ("cfg5: FilterBankMultiScaleGenerator + FilterBankMultiScale"
+                                      "Discriminator (least squares)" if args.pair == "fb" else
+                                      "cfg4: MelGanGenerator + MelGanDiscriminator (hinge)",
+                                      args.batch, 256 * args.frames, world)}}))
     if world > 1:
         dist.destroy_process_group()
 
