@@ -289,10 +289,12 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
  * 16-bit saved activation) or the fp32 pair (ya32 - yb32 > 0; the branch of a ResidualAtom,
  * util/modules.py:384-388); none = no activation.  s2d_stride > 1 writes dz16 in the
  * space-to-depth layout of ms_space_to_depth_blk16 (input of the ConvTranspose1d dgrad).
- * dbias may be NULL; otherwise it must be zero-initialised (atomic accumulation). */
+ * dz32 (optional, NULL to skip): the same masked gradient in fp32, BLK f32 like dy32 -- the skip
+ * path of a residual DilatedStack layer.  dbias may be NULL; otherwise it must be zero-initialised
+ * (atomic accumulation). */
 ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya32,
-                         const float* yb32, void* dz16, float* dbias, int batch, int channels,
-                         int len, int fmt, int s2d_stride, void* stream);
+                         const float* yb32, void* dz16, float* dz32, float* dbias, int batch,
+                         int channels, int len, int fmt, int s2d_stride, void* stream);
 /* reference-layout fp32 weights of the convolution that computes the INPUT gradient, to be
  * packed with ms_conv_pack_weight and run with ms_conv_fwd:
  *   MS_CONV  w (cout,cin,k)  -> out (cin,cout,k) tap-reversed; run as MS_CONV cin'=cout,

@@ -79,8 +79,8 @@ SIGNATURES = {
     "ms_audio2mel_frames": (c_int, [c_int, c_int, c_int]),
     "ms_audio2mel_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_int, c_int, c_int, c_void_p]),
-    "ms_blk_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                               c_int, c_int, c_int, c_int, c_void_p]),
+    "ms_blk_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ms_weight_dgrad_view": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "ms_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int,

@@ -153,6 +153,36 @@ class ResidualAtomBlk(Function):
         return dx32, None, dw1, db1, dw2, db2, None, None, None
 
 
+class DilatedLayerBlk(Function):
+    """one layer of a residual DilatedStack (util/modules.py:120-137 as configured by
+    ChannelGenerator): y = LeakyReLU(conv_k3_dil_d(x) + x), bias-free.  -> (y32, y16)"""
+
+    @staticmethod
+    def forward(ctx, x32, x16, w, cache, dilation):
+        B, C8, L, _ = x16.shape
+        C = C8 * 8
+        d = ops.conv_desc(MS_CONV, B, C, C, L, 3, dilation, dilation, leaky=2)
+        y16, y32 = ops.conv_fwd(d, x16, cache.fwd(d, w), None, res32=x32, want16=True, want32=True)
+        ctx.save_for_backward(x16, y16, w)
+        ctx.cfg = (cache, dilation)
+        ctx.mark_non_differentiable(y16)
+        return y32, y16
+
+    @staticmethod
+    def backward(ctx, dy32, _unused):
+        x16, y16, w = ctx.saved_tensors
+        cache, dilation = ctx.cfg
+        # dz = dy * LeakyReLU'(y) is the gradient of BOTH the conv output and the skip input
+        # (the skip path takes it in fp32, the GEMMs as a 16-bit operand)
+        dz16, _, dz32 = grad_ops.act_bwd(dy32, sign16=y16, want_bias=False, want32=True)
+        dw = grad_ops.conv_wgrad(dz16, x16, tuple(w.shape), dilation, dilation) \
+            if ctx.needs_input_grad[2] else None
+        dx32 = None
+        if ctx.needs_input_grad[0]:
+            dx32 = _dgrad_conv(cache, w, dz16, MS_CONV, dilation, dilation, 1, res32=dz32)
+        return dx32, None, dw, None, None
+
+
 class MonoConv(Function):
     """(B,C,L) BLK f32 -> (B,1,L): single-output-channel conv (+ tanh): the generator's last
     layer (generator/full.py:43-44) and the discriminator's judge (discriminator/full.py:22)."""

@@ -32,6 +32,7 @@ struct ActBwdParams {
   const float* yb;      // BLK f32 or null
   uint16_t* dz;         // BLK 16-bit (B, C/8, L, 8) or s2d (B, s*C/8, L/s, 8)
   float* dbias;         // [C] accumulated with atomics, or null
+  float* dz32;          // optional fp32 copy of dz (BLK f32, same layout as dy), or null
   int C8, L, fmt, s2d;
 };
 
@@ -68,6 +69,7 @@ act_bwd_kernel(const ActBwdParams p) {
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) bsum[j] += g[j];
+    if (p.dz32 != nullptr) st_global_v8(p.dz32 + idx * 8, g);
     uint4 o;
     o.x = bw_pack2(g[0], g[1], p.fmt); o.y = bw_pack2(g[2], g[3], p.fmt);
     o.z = bw_pack2(g[4], g[5], p.fmt); o.w = bw_pack2(g[6], g[7], p.fmt);
@@ -725,8 +727,8 @@ using namespace msb;
 extern "C" {
 
 ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya32,
-                         const float* yb32, void* dz16, float* dbias, int batch, int channels,
-                         int len, int fmt, int s2d_stride, void* stream) {
+                         const float* yb32, void* dz16, float* dz32, float* dbias, int batch,
+                         int channels, int len, int fmt, int s2d_stride, void* stream) {
   if (dy32 == nullptr || dz16 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
       len <= 0)
     return MS_ERR_INVALID;
@@ -736,7 +738,7 @@ ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya3
   const long long rows = static_cast<long long>(batch) * (channels / 8);
   if (rows > 65535) return MS_ERR_INVALID;
   ActBwdParams p{dy32, static_cast<const uint16_t*>(sign16), ya32, yb32,
-                 static_cast<uint16_t*>(dz16), dbias, channels / 8, len, fmt, s2d_stride};
+                 static_cast<uint16_t*>(dz16), dbias, dz32, channels / 8, len, fmt, s2d_stride};
   dim3 grid(ceil_div(len, kActBwdRows), static_cast<unsigned>(rows));
   act_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return after_launch("act_bwd_kernel");

@@ -279,7 +279,33 @@ class ChannelDiscriminator(nn.Module):
                 nn.Conv1d(channels[-1], channels[-1], 3, 1, 1))
             self.judge = nn.Conv1d(channels[-1], 1, 3, 1, 1)
             self._pj = [_PackedConv() for _ in self.mj]
+            self._cj = [ag.WeightCache() for _ in self.mj]
         self._pm = [_PackedStrided() for _ in self.main]
+        self._sc = [ag.StridedCache() for _ in self.main]
+
+    def forward_blocked_train(self, x, feat32, feat16):
+        """autograd-recorded form -> ([maps NCL f32], h32, h16 of the last map, judgement|None)"""
+        features = []
+        first = self.main[0]
+        h = ag.DirectConv.apply(x, first.weight, first.bias, first.stride[0], first.padding[0], 1,
+                                True)
+        features.append(h)
+        h32, h16 = ag.PackBlk32.apply(h), ops.pack_ncl(h.detach())
+        length = h.shape[-1]
+        for conv, sc in list(zip(self.main, self._sc))[1:]:
+            h32, h16 = ag.StridedConvBlk.apply(h32, h16, conv.weight, conv.bias, sc, conv.stride[0],
+                                               length)
+            features.append(ag.UnpackBlk32.apply(h32))
+            length = h16.shape[2]
+        if not self.return_judgements:
+            return features, h32, h16, None
+        if self.conditioning_channels > 0:
+            h32, h16 = torch.cat([h32, feat32], dim=1), torch.cat([h16, feat16], dim=1)
+        for conv, cj in zip(self.mj, self._cj):
+            h32, h16 = ag.ConvBlk.apply(h32, h16, conv.weight, conv.bias, cj, MS_CONV, 1, 1, 1, True)
+            features.append(ag.UnpackBlk32.apply(h32))
+        j = ag.MonoConv.apply(h32, self.judge.weight, self.judge.bias, 3, 1, False)
+        return features, h32, h16, j
 
     def forward_blocked(self, x, feat16):
         """x (B,1,L) f32 -> ([maps NCL f32], last map BLK16, last map NCL f32, judgement|None)"""
@@ -354,9 +380,43 @@ class MultiScaleDiscriminator(nn.Module):
         self.judge = nn.Conv1d(channels, 1, 3, 1, 1)
         self.recon = None
         self._pf = [_PackedConv() for _ in self.final]
+        self._cf = [ag.WeightCache() for _ in self.final]
+
+    def _forward_train(self, bands, feat):
+        cond = self.conditioning_channels > 0
+        feat32 = grad_ops.pack_ncl32(feat) if cond else None
+        feat16 = ops.pack_ncl(feat) if cond else None
+        features, c32, c16, judgements = [], [], [], []
+        for size, layer in self.channel_discs.items():
+            f, h32, h16, j = layer.forward_blocked_train(bands[size], feat32, feat16)
+            features.append(f)
+            c32.append(h32)
+            c16.append(h16)
+            if self.channel_judgements:
+                judgements.append(j)
+        x32, x16 = torch.cat(c32, dim=1), torch.cat(c16, dim=1)
+        if cond:
+            T = x16.shape[2]
+            if feat.shape[-1] != T:
+                idx = (torch.arange(T, device=feat.device) * feat.shape[-1]) // T
+                up = feat[..., idx].contiguous()
+                feat32, feat16 = grad_ops.pack_ncl32(up), ops.pack_ncl(up)
+            x32, x16 = torch.cat([x32, feat32], dim=1), torch.cat([x16, feat16], dim=1)
+        final_features = []
+        for conv, cf in zip(self.final, self._cf):
+            x32, x16 = ag.ConvBlk.apply(x32, x16, conv.weight, conv.bias, cf, MS_CONV, 1, 1, 1, True)
+            final_features.append(ag.UnpackBlk32.apply(x32))
+        features.append(final_features)
+        judgements.append(ag.MonoConv.apply(x32, self.judge.weight, self.judge.bias, 3, 1, False))
+        return features, judgements
 
     def forward(self, x, feat):
-        _fwd_only(self, x)
+        probe = x if isinstance(x, torch.Tensor) else next(iter(x.values()))
+        if ag.needs_grad(self, probe):
+            if self.decompose:
+                raise MsbError("training with decompose=True (FFT band split in the graph) is not "
+                               "on this path; feed band dictionaries (decompose=False)")
+            return self._forward_train(x, feat)
         bands = fft_frequency_decompose(x, self.smallest_band) if self.decompose else x
         cond = self.conditioning_channels > 0
         feat16 = ops.pack_ncl(feat) if cond else None

@@ -167,6 +167,12 @@ class DilatedStack(nn.Module):
             nn.Conv1d(channels, channels, kernel_size, padding=d, dilation=d, bias=False)
             for d in dilations])
         self._packed = [_PackedConv() for _ in dilations]
+        self._cache = [ag.WeightCache() for _ in dilations]
+
+    def forward_blocked_train(self, x32, x16):
+        for conv, cache, d in zip(self.main, self._cache, self.dilations):
+            x32, x16 = ag.DilatedLayerBlk.apply(x32, x16, conv.weight, cache, d)
+        return x32, x16
 
     def forward_blocked(self, x16, x32):
         B, _, L, _ = x16.shape
@@ -199,6 +205,18 @@ class ChannelGenerator(nn.Module):
         self.main = nn.Sequential(*layers)
         self.to_samples = nn.Conv1d(channels[-1], 1, 7, 1, 3)
         self._packed = [_PackedConv() for _ in scale_factors]
+        self._cache = [ag.WeightCache() for _ in scale_factors]
+
+    def forward_blocked_train(self, e32, e16):
+        """autograd-recorded form; (e32, e16) = the shared embedding"""
+        h32, h16 = e32, e16
+        for i in range(len(self.scale_factors)):
+            up, stack = self.main[2 * i], self.main[2 * i + 1]
+            s = up.scale_factor
+            h32, h16 = ag.ConvBlk.apply(h32, h16, up.conv.weight, None, self._cache[i], MS_CONVT, 1,
+                                        s // 2, s, True)
+            h32, h16 = stack.forward_blocked_train(h32, h16)
+        return ag.MonoConv.apply(h32, self.to_samples.weight, self.to_samples.bias, 7, 3, False)
 
     def forward_blocked(self, x16, T):
         B = x16.shape[0]
@@ -216,7 +234,8 @@ class ChannelGenerator(nn.Module):
         return ops.conv_to_mono(h32, self.to_samples.weight, self.to_samples.bias, 7, 3, False)
 
     def forward(self, x):
-        _fwd_only_g(self, x)
+        if ag.needs_grad(self, x):
+            return self.forward_blocked_train(ag.PackBlk32.apply(x), ops.pack_ncl(x.detach()))
         return self.forward_blocked(ops.pack_ncl(x), x.shape[-1])
 
 
@@ -252,9 +271,24 @@ class MultiScaleGenerator(nn.Module):
             self.add_module(f"channel_{key}", generator)
             self.channel_generators[key] = generator
         self._pe = _PackedConv()
+        self._ce = ag.WeightCache()
+
+    def _forward_train(self, x):
+        if x.requires_grad:
+            raise MsbError("gradients w.r.t. the conditioning features are not on this path")
+        if self.recompose:
+            raise MsbError("training with recompose=True (FFT band merge in the graph) is not on "
+                           "this path; the MultiScale experiments train on band dictionaries "
+                           "(experiment/multiscale.py:120-160)")
+        x16 = ops.pack_ncl(x, 3, 1)
+        e32, e16 = ag.ConvBlk.apply(None, x16, self.embedding.weight, self.embedding.bias, self._ce,
+                                    MS_CONV, 1, 0, 1, True)
+        return {size: layer.forward_blocked_train(e32, e16)
+                for size, layer in self.channel_generators.items()}
 
     def forward(self, x):
-        _fwd_only_g(self, x)
+        if ag.needs_grad(self, x):
+            return self._forward_train(x.contiguous())
         B, _, T = x.shape
         x16 = ops.pack_ncl(x, 3, 1)                                   # ReflectionPad1d(3)
         d = ops.conv_desc(MS_CONV, B, self.feature_channels, 512, T + 6, 7, 1, 0, leaky=True)

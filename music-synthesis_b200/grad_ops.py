@@ -28,8 +28,10 @@ def convert16(x16, src_fmt, dst_fmt):
     return out
 
 
-def act_bwd(dy32, sign16=None, ya32=None, yb32=None, want_bias=True, fmt=GRAD_FMT, s2d=1):
-    """dz16 = to16(dy32 * LeakyReLU'(.)) (+ bias gradient).  Returns (dz16, dbias|None)."""
+def act_bwd(dy32, sign16=None, ya32=None, yb32=None, want_bias=True, fmt=GRAD_FMT, s2d=1,
+            want32=False):
+    """dz16 = to16(dy32 * LeakyReLU'(.)) (+ bias gradient).  Returns (dz16, dbias|None), or
+    (dz16, dbias|None, dz32) with want32 (the masked gradient also in fp32)."""
     dy32 = dy32.contiguous()
     B, C8, L, _ = dy32.shape
     if s2d > 1:
@@ -37,9 +39,11 @@ def act_bwd(dy32, sign16=None, ya32=None, yb32=None, want_bias=True, fmt=GRAD_FM
     else:
         dz = torch.empty((B, C8, L, 8), dtype=torch.int16, device=dy32.device)
     db = torch.zeros(C8 * 8, dtype=torch.float32, device=dy32.device) if want_bias else None
-    check(_lib.lib().ms_blk_act_bwd(ptr(dy32), ptr(sign16), ptr(ya32), ptr(yb32), ptr(dz), ptr(db),
-                                    B, C8 * 8, L, fmt, s2d, stream_ptr()), "ms_blk_act_bwd")
-    return dz, db
+    dz32 = torch.empty_like(dy32) if want32 else None
+    check(_lib.lib().ms_blk_act_bwd(ptr(dy32), ptr(sign16), ptr(ya32), ptr(yb32), ptr(dz),
+                                    ptr(dz32), ptr(db), B, C8 * 8, L, fmt, s2d, stream_ptr()),
+          "ms_blk_act_bwd")
+    return (dz, db, dz32) if want32 else (dz, db)
 
 
 def weight_dgrad_view(w, kind, stride=1, pad=0):

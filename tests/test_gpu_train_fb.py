@@ -85,3 +85,60 @@ def test_filterbank_pair_train_cycle_matches_oracle():
     worst_g = max(errs.values())
     assert not bad, ("G", bad)
     print("filter-bank pair: worst grad rel_l2 D %.4f G %.4f" % (worst_d, worst_g))
+
+
+def test_multiscale_pair_train_cycle_matches_oracle():
+    """the non-filterbank multiscale pair as wired by experiment/multiscale.py:120-160
+    (MultiScaleNoDeRecompose: band dictionaries, conditioned k41 discriminator, least squares)"""
+    from music_synthesis_b200.generator.multiscale import MultiScaleGenerator
+    from music_synthesis_b200.discriminator.multiscale import MultiScaleMultiResDiscriminator
+    from music_synthesis_b200.train import GeneratorTrainer, DiscriminatorTrainer, Adam
+    from music_synthesis_b200.loss.loss import (mel_gan_disc_loss, mel_gan_gen_loss,
+                                                least_squares_disc_loss,
+                                                least_squares_generator_loss)
+    B, T, N = 2, 8, 2048
+    g_sd = restate.multiscale_generator_state(201, N)
+    d_sd = restate.multiscale_discriminator_state(202, N)
+    g = MultiScaleGenerator(128, T, N, transposed_conv=True, recompose=False)
+    g.load_state_dict(g_sd)
+    d = MultiScaleMultiResDiscriminator(N, flatten_multiscale_features=False, decompose=False,
+                                        channel_judgements=True, conditioning_channels=128)
+    d.load_state_dict(d_sd)
+    g, d = g.cuda(), d.cuda()
+    sizes = restate.fb_band_sizes(N)
+
+    def gen_fn(features, sd):
+        return restate.multiscale_generator(features, sd, N)
+
+    def disc_fn(x, features, sd):
+        return restate.multiscale_multires_discriminator(x, features, sd, N, decompose=False)
+
+    g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss, least_squares_disc_loss)
+    g_tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, least_squares_generator_loss)
+    real = {s: synth.randn(203 + i, B, 1, s) * 0.1 for i, s in enumerate(sizes)}
+    feats = synth.mel_features(209, B, T)
+    real_gpu = {s: v.cuda() for s, v in real.items()}
+    rd = d_tr.train(real_gpu, feats.cuda())
+    d_loss, d_grads, d_new = restate.discriminator_train_step(
+        g_sd, d_sd, real, feats, {}, sub_loss=restate.least_squares_disc_loss,
+        gen_fn=gen_fn, disc_fn=disc_fn)
+    assert abs(rd["d_loss"] - d_loss) < 2e-3 * abs(d_loss), (rd["d_loss"], d_loss)
+    errs = {k: rel_l2(p.grad, d_grads[k]) for k, p in d.named_parameters()}
+    bad = {k: round(e, 4) for k, e in errs.items() if not e < D_TOL}
+    worst_d = max(errs.values())
+    assert not bad, ("D", bad)
+    d.load_state_dict(d_new)
+    rg = g_tr.train(real_gpu, feats.cuda())
+    g_loss, fake, g_grads, _ = restate.generator_train_step(
+        g_sd, d_new, real, feats, {}, sub_loss=restate.least_squares_generator_loss,
+        gen_fn=gen_fn, disc_fn=disc_fn)
+    assert abs(rg["g_loss"] - g_loss) < 2e-3 * max(1.0, abs(g_loss)), (rg["g_loss"], g_loss)
+    for s in sizes:
+        assert rel_l2(rg["fake"][s], fake[s]) < 1.5e-3
+    errs = {k: rel_l2(p.grad, g_grads[k]) for k, p in g.named_parameters()}
+    bad = {k: round(e, 4) for k, e in errs.items() if not e < G_TOL}
+    worst_g = max(errs.values())
+    assert not bad, ("G", bad)
+    print("multiscale pair: worst grad rel_l2 D %.4f G %.4f" % (worst_d, worst_g))
