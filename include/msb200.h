@@ -336,6 +336,14 @@ ms_status ms_expand_mono_bwd(const float* de32, float* dx, int batch, int len, i
 ms_status ms_depth_to_space_blk32(const float* dys32, float* dx32, int batch, int channels,
                                   int src_rows, int rows_valid, int row_offset, int out_rows,
                                   int len, int stride, void* stream);
+/* gradient of ms_blk_act_pad on the fp32 stream: dx32[t] = act'(x[t]) * (dy32[t+pad] + the rows that
+ * reflect onto t); sign16 = BLK 16-bit image of x (LeakyReLU mask) or NULL (no activation).
+ * dy32 BLK f32 (B,C/8,len+2*pad,8), dx32 (B,C/8,len,8). */
+ms_status ms_blk_act_pad_bwd(const float* dy32, const void* sign16, float* dx32, int batch,
+                             int channels, int len, int pad, int pad_mode, void* stream);
+/* gradient of ms_weight_norm_fold: dW (rows,cols) -> dv (rows,cols), dg (rows) */
+ms_status ms_weight_norm_bwd(const float* dw, const float* v, const float* g, float* dv, float* dg,
+                             int rows, int cols, void* stream);
 /* NCL f32 -> BLK f32 (gradient of ms_unpack_blk32_to_ncl) */
 ms_status ms_pack_ncl_to_blk32(const float* x, float* y32, int batch, int channels, int len,
                                void* stream);

@@ -98,6 +98,10 @@ SIGNATURES = {
     "ms_expand_mono_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ms_depth_to_space_blk32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                         c_int, c_int, c_int, c_void_p]),
+    "ms_blk_act_pad_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p]),
+    "ms_weight_norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_void_p]),
     "ms_pack_ncl_to_blk32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ms_conv1d_direct_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

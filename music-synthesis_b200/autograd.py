@@ -38,8 +38,9 @@ class WeightCache:
 
     @staticmethod
     def _key(w, desc):
-        return (w.data_ptr(), w._version, desc.kind, desc.cin, desc.cout, desc.ksize, desc.stride,
-                desc.operand)
+        # derived weights (weight-norm folds) carry the identity of their parameters
+        ident = getattr(w, "_msb_key", None) or (w.data_ptr(), w._version)
+        return (ident, desc.kind, desc.cin, desc.cout, desc.ksize, desc.stride, desc.operand)
 
     def fwd(self, desc, w):
         key = self._key(w, desc)
@@ -85,16 +86,20 @@ class ConvBlk(Function):
     ConvTranspose1d).  Returns (y32, y16)."""
 
     @staticmethod
-    def forward(ctx, x32, x16, w, b, cache, kind, dilation, pad, stride, leaky):
+    def forward(ctx, x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32=None):
+        """res32 (optional, BLK f32): added after the activation, y = act(conv + b) + res32"""
         B, _, L, _ = x16.shape
         if kind == MS_CONV:
             cout, cin, k = w.shape
         else:
             cin, cout, k = w.shape
+        if res32 is not None and leaky:
+            raise _lib.MsbError("ConvBlk: residual input only with a linear epilogue")
         d = ops.conv_desc(kind, B, cin, cout, L, k, dilation, pad, stride, leaky=leaky)
-        y16, y32 = ops.conv_fwd(d, x16, cache.fwd(d, w), b, want16=True, want32=True)
+        y16, y32 = ops.conv_fwd(d, x16, cache.fwd(d, w), b, res32=res32, want16=True, want32=True)
         ctx.save_for_backward(x16, w, y16)
         ctx.cfg = (cache, kind, dilation, pad, stride, leaky, b is not None)
+        ctx.has_res = res32 is not None
         ctx.mark_non_differentiable(y16)
         return y32, y16
 
@@ -102,6 +107,7 @@ class ConvBlk(Function):
     def backward(ctx, dy32, _unused):
         x16, w, y16 = ctx.saved_tensors
         cache, kind, dilation, pad, stride, leaky, has_bias = ctx.cfg
+        dres = dy32 if (ctx.has_res and ctx.needs_input_grad[10]) else None
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
         s2d = stride if kind == MS_CONVT else 1
         dz16, db = grad_ops.act_bwd(dy32, sign16=y16 if leaky else None,
@@ -114,7 +120,12 @@ class ConvBlk(Function):
                 dw = grad_ops.convt_wgrad(x16, dz16, tuple(w.shape), stride, pad)
         if need_x:
             dx32 = _dgrad_conv(cache, w, dz16, kind, dilation, pad, stride)
-        return dx32, None, dw, db, None, None, None, None, None, None
+        return dx32, None, dw, db, None, None, None, None, None, None, dres
+
+
+def conv_blk(x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32=None):
+    """ConvBlk.apply with every argument spelled out (autograd wants one gradient per argument)"""
+    return ConvBlk.apply(x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32)
 
 
 class ResidualAtomBlk(Function):
@@ -181,6 +192,41 @@ class DilatedLayerBlk(Function):
         if ctx.needs_input_grad[0]:
             dx32 = _dgrad_conv(cache, w, dz16, MS_CONV, dilation, dilation, 1, res32=dz32)
         return dx32, None, dw, None, None
+
+
+class WeightNorm(Function):
+    """torch.nn.utils.weight_norm (dim 0): W = g * v / ||v|| (experiment/realmelgan.py:24-29)"""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        ctx.save_for_backward(v, g)
+        return ops.weight_norm_fold(v, g)
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g = ctx.saved_tensors
+        return grad_ops.weight_norm_bwd(dw, v, g)
+
+
+class ActPadBlk(Function):
+    """(x32, x16) -> (a32, a16) = LeakyReLU / padding (zero or reflection) of both images: the
+    nn.LeakyReLU(0.2) + nn.ReflectionPad1d in front of the convs of the official MelGAN blocks
+    (experiment/realmelgan.py:35-37, 60-61, 80-81)"""
+
+    @staticmethod
+    def forward(ctx, x32, x16, pad, pad_mode, leaky):
+        a16 = ops.act_pad(x16, pad, pad_mode, leaky)
+        a32 = ops.act_pad(x32, pad, pad_mode, leaky)
+        ctx.save_for_backward(x16)
+        ctx.cfg = (x16.shape[2], pad, pad_mode, leaky)
+        ctx.mark_non_differentiable(a16)
+        return a32, a16
+
+    @staticmethod
+    def backward(ctx, da32, _unused):
+        (x16,) = ctx.saved_tensors
+        length, pad, pad_mode, leaky = ctx.cfg
+        return grad_ops.act_pad_bwd(da32, x16 if leaky else None, length, pad, pad_mode), None, None, None, None
 
 
 class MonoConv(Function):

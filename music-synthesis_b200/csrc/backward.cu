@@ -207,6 +207,76 @@ __global__ void depth_to_space_blk32_kernel(const float* __restrict__ dys, float
   st_global_v8(dx + gid * 8, f);
 }
 
+// gradient of ms_blk_act_pad (fp32 stream): y[tp] = act(x[map(tp - pad)]), zero (mode 0) or
+// reflection (mode 1) padding: dx[t] = act'(x[t]) * (dy[t+pad] + reflected copies of row t).
+// sign16: BLK 16-bit image of x (LeakyReLU mask) or null (no activation).
+__global__ void act_pad_bwd_kernel(const float* __restrict__ dy, const uint4* __restrict__ sign16,
+                                   float* __restrict__ dx, int L, int pad, int mode,
+                                   size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int Lp = L + 2 * pad;
+  const int t = static_cast<int>(gid % L);
+  const size_t bc = gid / L;
+  const float* row = dy + bc * static_cast<size_t>(Lp) * 8;
+  float g[8];
+  ld_global_nc_v8(row + static_cast<size_t>(t + pad) * 8, g);
+  if (mode == 1) {
+    float r[8];
+    if (t >= 1 && t <= pad) {                     // left reflection: padded row pad - t
+      ld_global_nc_v8(row + static_cast<size_t>(pad - t) * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += r[j];
+    }
+    if (t <= L - 2 && t >= L - 1 - pad) {         // right reflection: padded row pad + 2(L-1) - t
+      ld_global_nc_v8(row + static_cast<size_t>(pad + 2 * (L - 1) - t) * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += r[j];
+    }
+  }
+  if (sign16 != nullptr) {
+    const uint4 v = __ldg(sign16 + gid);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (w[j] & 0x8000u) g[2 * j] *= 0.2f;
+      if (w[j] & 0x80000000u) g[2 * j + 1] *= 0.2f;
+    }
+  }
+  st_global_v8(dx + gid * 8, g);
+}
+
+// gradient of ms_weight_norm_fold (W = g * v / ||v||, rows = dim 0): one block per row
+//   dg[r] = <dW_r, v_r> / ||v_r||,   dv_r = (g_r/||v_r||) * (dW_r - (dg[r]/||v_r||) * v_r)
+__global__ void weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                       const float* __restrict__ g, float* __restrict__ dv,
+                                       float* __restrict__ dg, int cols) {
+  __shared__ float sh[2][256];
+  const size_t base = static_cast<size_t>(blockIdx.x) * cols;
+  float nn = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    const float vi = v[base + i];
+    nn += vi * vi;
+    dot += dw[base + i] * vi;
+  }
+  sh[0][threadIdx.x] = nn;
+  sh[1][threadIdx.x] = dot;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  const float n = sqrtf(sh[0][0]);
+  const float dgr = sh[1][0] / n;
+  const float gr = g[blockIdx.x];
+  if (threadIdx.x == 0) dg[blockIdx.x] = dgr;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x)
+    dv[base + i] = (gr / n) * (dw[base + i] - (dgr / n) * v[base + i]);
+}
+
 // ------------------------------------------------------------ direct conv backward (NCL f32)
 struct DirectBwdParams {
   const float* dy;   // (B, cout, lout)
@@ -1003,6 +1073,27 @@ ms_status ms_depth_to_space_blk32(const float* dys32, float* dx32, int batch, in
                                 static_cast<cudaStream_t>(stream)>>>(
       dys32, dx32, channels / 8, src_rows, rows_valid, row_offset, out_rows, len, stride, total);
   return after_launch("depth_to_space_blk32_kernel");
+}
+
+ms_status ms_blk_act_pad_bwd(const float* dy32, const void* sign16, float* dx32, int batch,
+                             int channels, int len, int pad, int pad_mode, void* stream) {
+  if (dy32 == nullptr || dx32 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
+      len <= 0 || pad < 0 || (pad_mode == 1 && pad >= len))
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * len;
+  act_pad_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(
+      dy32, static_cast<const uint4*>(sign16), dx32, len, pad, pad_mode, total);
+  return after_launch("act_pad_bwd_kernel");
+}
+
+ms_status ms_weight_norm_bwd(const float* dw, const float* v, const float* g, float* dv, float* dg,
+                             int rows, int cols, void* stream) {
+  if (dw == nullptr || v == nullptr || g == nullptr || dv == nullptr || dg == nullptr ||
+      rows <= 0 || cols <= 0)
+    return MS_ERR_INVALID;
+  weight_norm_bwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw, v, g, dv, dg, cols);
+  return after_launch("weight_norm_bwd_kernel");
 }
 
 }  // extern "C"

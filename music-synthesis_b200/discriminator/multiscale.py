@@ -96,7 +96,7 @@ class FilterBankChannelDiscriminator(nn.Module):
             h32 = torch.cat([h32, feat32], dim=1)
             h16 = torch.cat([h16, feat16], dim=1)
         for conv, cj in zip(self.mj, self._cj):
-            h32, h16 = ag.ConvBlk.apply(h32, h16, conv.weight, conv.bias, cj, MS_CONV, 1, 1, 1, True)
+            h32, h16 = ag.conv_blk(h32, h16, conv.weight, conv.bias, cj, MS_CONV, 1, 1, 1, True)
             features.append(ag.UnpackBlk32.apply(h32))
         j = ag.MonoConv.apply(h32, self.judge.weight, self.judge.bias, 3, 1, False)
         return features, h32, h16, j
@@ -211,7 +211,7 @@ class FilterBankMultiScaleDiscriminator(nn.Module):
             x32, x16 = torch.cat([x32, feat32], dim=1), torch.cat([x16, feat16], dim=1)
         final_features = []
         for conv, cf in zip(self.final, self._cf):
-            x32, x16 = ag.ConvBlk.apply(x32, x16, conv.weight, conv.bias, cf, MS_CONV, 1, 1, 1, True)
+            x32, x16 = ag.conv_blk(x32, x16, conv.weight, conv.bias, cf, MS_CONV, 1, 1, 1, True)
             final_features.append(ag.UnpackBlk32.apply(x32))
         features.append(final_features)
         judgements.append(ag.MonoConv.apply(x32, self.judge.weight, self.judge.bias, 3, 1, False))
@@ -302,7 +302,7 @@ class ChannelDiscriminator(nn.Module):
         if self.conditioning_channels > 0:
             h32, h16 = torch.cat([h32, feat32], dim=1), torch.cat([h16, feat16], dim=1)
         for conv, cj in zip(self.mj, self._cj):
-            h32, h16 = ag.ConvBlk.apply(h32, h16, conv.weight, conv.bias, cj, MS_CONV, 1, 1, 1, True)
+            h32, h16 = ag.conv_blk(h32, h16, conv.weight, conv.bias, cj, MS_CONV, 1, 1, 1, True)
             features.append(ag.UnpackBlk32.apply(h32))
         j = ag.MonoConv.apply(h32, self.judge.weight, self.judge.bias, 3, 1, False)
         return features, h32, h16, j
@@ -404,7 +404,7 @@ class MultiScaleDiscriminator(nn.Module):
             x32, x16 = torch.cat([x32, feat32], dim=1), torch.cat([x16, feat16], dim=1)
         final_features = []
         for conv, cf in zip(self.final, self._cf):
-            x32, x16 = ag.ConvBlk.apply(x32, x16, conv.weight, conv.bias, cf, MS_CONV, 1, 1, 1, True)
+            x32, x16 = ag.conv_blk(x32, x16, conv.weight, conv.bias, cf, MS_CONV, 1, 1, 1, True)
             final_features.append(ag.UnpackBlk32.apply(x32))
         features.append(final_features)
         judgements.append(ag.MonoConv.apply(x32, self.judge.weight, self.judge.bias, 3, 1, False))

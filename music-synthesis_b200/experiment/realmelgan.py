@@ -12,13 +12,19 @@ is (re)packed.  Generator chain, channel-blocked on the tcgen05 kernel:
   LeakyReLU + ReflectionPad(3) -> fp32 32->1 k7 conv + tanh.
 Discriminator: reflect-padded direct conv, grouped strided direct convs, tcgen05 dense k5 conv,
 fp32 judge, AvgPool1d(4,2,1,count_include_pad=False) between the three independent scales.
-Forward (inference) only in this round.
+With autograd enabled the same kernels are recorded as torch.autograd.Functions with C-ABI backward
+passes (../autograd.py): `WeightNorm` (fold + its gradient to weight_g / weight_v), `ActPadBlk`
+(LeakyReLU + reflection pad and the scatter of its gradient), `ConvBlk` with a residual input (the
+ResnetBlock shortcut), `DenseConvNCL`, `DirectConv`, `MonoConv`, `AvgPool`.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 import warnings
 
+import torch.nn.functional as F
+
+from .. import autograd as ag
 from .. import ops
 from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
 from ..loss.loss import _Acc, L1, hinge_generator_loss
@@ -67,6 +73,15 @@ def _fwd_only(module, x):
         raise MsbError("sm_100a path is forward-only in this build: use torch.no_grad()")
 
 
+def _wn(m):
+    """differentiable weight-norm fold of a weight-normed layer; the folded tensor is new on
+    every call, so the packed-image caches key on the underlying parameters instead"""
+    w = ag.WeightNorm.apply(m.weight_v, m.weight_g)
+    w._msb_key = ("wn", m.weight_v.data_ptr(), m.weight_v._version,
+                  m.weight_g.data_ptr(), m.weight_g._version)
+    return w
+
+
 class ResnetBlock(nn.Module):
     def __init__(self, dim, dilation=1):
         super().__init__()
@@ -81,6 +96,17 @@ class ResnetBlock(nn.Module):
         )
         self.shortcut = WNConv1d(dim, dim, kernel_size=1)
         self._p = (_PackedWN(), _PackedWN(), _PackedWN())
+        self._c = (ag.WeightCache(), ag.WeightCache(), ag.WeightCache())
+
+    def forward_blocked_train(self, x32, x16):
+        """autograd-recorded form: (x32, x16) -> (y32, y16)"""
+        d = self.dilation
+        s32, _ = ag.conv_blk(x32, x16, _wn(self.shortcut), self.shortcut.bias, self._c[2], MS_CONV,
+                             1, 0, 1, False)
+        a32, a16 = ag.ActPadBlk.apply(x32, x16, d, 1, True)
+        c1, c2 = self.block[2], self.block[4]
+        h32, h16 = ag.conv_blk(a32, a16, _wn(c1), c1.bias, self._c[0], MS_CONV, d, 0, 1, True)
+        return ag.conv_blk(h32, h16, _wn(c2), c2.bias, self._c[1], MS_CONV, 1, 0, 1, False, s32)
 
     def forward_blocked(self, x16):
         """x16 (B, dim/8, L, 8) un-activated 16-bit operand -> (x16', x32')"""
@@ -96,7 +122,9 @@ class ResnetBlock(nn.Module):
                             res32=s32, want16=True, want32=True)
 
     def forward(self, x):
-        _fwd_only(self, x)
+        if ag.needs_grad(self, x):
+            y32, _ = self.forward_blocked_train(ag.PackBlk32.apply(x), ops.pack_ncl(x.detach()))
+            return ag.UnpackBlk32.apply(y32)
         _, y32 = self.forward_blocked(ops.pack_ncl(x))
         return ops.unpack_blk32(y32)
 
@@ -125,8 +153,39 @@ class Generator(nn.Module):
             self._p[idx] = _PackedWN()
         return self._p[idx]
 
+    def _forward_train(self, x):
+        if x.requires_grad:
+            raise MsbError("gradients w.r.t. the conditioning features are not on this path")
+        layers = list(self.model)
+        caches = self.__dict__.setdefault("_c", {})
+        x16 = ops.pack_ncl(x, 3, 1)                                   # ReflectionPad1d(3)
+        first = layers[1]
+        h32, h16 = ag.conv_blk(None, x16, _wn(first), first.bias,
+                               caches.setdefault(1, ag.WeightCache()), MS_CONV, 1, 0, 1, False)
+        L = x.shape[-1]
+        i = 2
+        while i < len(layers):
+            m = layers[i]
+            if isinstance(m, nn.ConvTranspose1d):
+                r = m.stride[0]
+                if m.output_padding[0] != 0 or m.kernel_size[0] != 2 * r:
+                    raise NotImplementedError("odd upsampling ratios are not on this path")
+                a32, a16 = ag.ActPadBlk.apply(h32, h16, 0, 0, True)   # the LeakyReLU before it
+                h32, h16 = ag.conv_blk(a32, a16, _wn(m), m.bias, caches.setdefault(i, ag.WeightCache()),
+                                       MS_CONVT, 1, m.padding[0], r, False)
+                L *= r
+            elif isinstance(m, ResnetBlock):
+                h32, h16 = m.forward_blocked_train(h32, h16)
+            elif isinstance(m, nn.Conv1d):                            # final k7 conv + tanh
+                a32, _ = ag.ActPadBlk.apply(h32, h16, 3, 1, True)     # LeakyReLU + ReflectionPad1d(3)
+                # valid conv over the padded stream: the first L outputs are the layer's output
+                return ag.MonoConv.apply(a32, _wn(m), m.bias, 7, 0, True)[:, :, :L].contiguous()
+            i += 1
+        raise MsbError("malformed generator")
+
     def forward(self, x):
-        _fwd_only(self, x)
+        if ag.needs_grad(self, x):
+            return self._forward_train(x.contiguous())
         B, _, T = x.shape
         layers = list(self.model)
         x16 = ops.pack_ncl(x, 3, 1)                                   # ReflectionPad1d(3)
@@ -182,9 +241,32 @@ class NLayerDiscriminator(nn.Module):
         self.model = model
         self.n_layers = n_layers
         self._p = {k: _PackedWN() for k in model}
+        self._dense_cache = ag.WeightCache()
+
+    def _forward_train(self, x):
+        results = []
+        keys = list(self.model.keys())
+        conv0 = self.model["layer_0"][1]
+        # ReflectionPad1d(7) on the 1-channel input: torch data movement (and its scatter backward)
+        h = ag.DirectConv.apply(F.pad(x, (7, 7), mode="reflect"), _wn(conv0), conv0.bias, 1, 0, 1,
+                                True)
+        results.append(h)
+        for n in range(1, self.n_layers + 1):
+            c = self.model["layer_%d" % n][0]
+            h = ag.DirectConv.apply(h, _wn(c), c.bias, c.stride[0], c.padding[0], c.groups, True)
+            results.append(h)
+        dense = self.model[keys[-2]][0]
+        y32 = ag.DenseConvNCL.apply(h, _wn(dense), dense.bias, self._dense_cache, dense.padding[0],
+                                    True)
+        results.append(ag.UnpackBlk32.apply(y32))
+        judge = self.model[keys[-1]]
+        results.append(ag.MonoConv.apply(y32, _wn(judge), judge.bias, judge.kernel_size[0],
+                                         judge.padding[0], False))
+        return results
 
     def forward(self, x, feat):
-        _fwd_only(self, x)
+        if ag.needs_grad(self, x):
+            return self._forward_train(x.contiguous())
         results = []
         keys = list(self.model.keys())
         conv0 = self.model["layer_0"][1]
@@ -197,11 +279,13 @@ class NLayerDiscriminator(nn.Module):
                                   c.padding[0], c.groups, leaky=True)
             results.append(h)
         dense = self.model[keys[-2]][0]
-        B, C, L = h.shape
-        d = ops.conv_desc(MS_CONV, B, C, dense.out_channels, L, dense.kernel_size[0], 1,
-                          dense.padding[0], leaky=True)
-        _, y32 = ops.conv_fwd(d, ops.pack_ncl(h), self._p[keys[-2]].get(d, dense), dense.bias,
-                              want16=False, want32=True)
+        # split-precision dense layer, like the training path: the real and the fake batch must
+        # see the SAME arithmetic (the feature-matching loss differences them)
+        wd = self._p[keys[-2]].folded(dense)[0]
+        wd._msb_key = ("wn", dense.weight_v.data_ptr(), dense.weight_v._version,
+                       dense.weight_g.data_ptr(), dense.weight_g._version)
+        _, y32 = ag.dense_split_fwd(h, wd, dense.bias, self._dense_cache, dense.padding[0], True,
+                                    want16=False)
         results.append(ops.unpack_blk32(y32))
         judge = self.model[keys[-1]]
         results.append(ops.conv_to_mono(y32, self._p[keys[-1]].folded(judge)[0], judge.bias,
@@ -226,7 +310,10 @@ class Discriminator(nn.Module):
             z = disc(x, feat)
             features.append(z[:-1])
             judgements.append(z[-1])
-            x = ops.avg_pool1d(x, 4, 2, 1, count_include_pad=False)
+            if torch.is_grad_enabled() and x.requires_grad:
+                x = ag.AvgPool.apply(x, 4, 2, 1, False)
+            else:
+                x = ops.avg_pool1d(x, 4, 2, 1, count_include_pad=False)
         return features, judgements
 
 

@@ -126,11 +126,11 @@ class MelGanGenerator(nn.Module):
             raise MsbError("training runs with fp16 forward operands")
         main = self.main
         x16 = ops.pack_ncl(x, 3, 1)                                  # ReflectionPad1d(3)
-        h32, h16 = ag.ConvBlk.apply(None, x16, main[1].weight, main[1].bias, self._caches[1],
+        h32, h16 = ag.conv_blk(None, x16, main[1].weight, main[1].bias, self._caches[1],
                                     MS_CONV, 1, 0, 1, True)
         for idx in (3, 6, 9, 12):
             ct = main[idx]
-            h32, h16 = ag.ConvBlk.apply(h32, h16, ct.weight, ct.bias, self._caches[idx], MS_CONVT,
+            h32, h16 = ag.conv_blk(h32, h16, ct.weight, ct.bias, self._caches[idx], MS_CONVT,
                                         1, ct.padding[0], ct.stride[0], True)
             h32, h16 = main[idx + 2].forward_blocked_train(h32, h16)
         last = main[15]

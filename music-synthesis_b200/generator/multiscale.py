@@ -55,12 +55,12 @@ class FilterBankChannelGenerator(nn.Module):
     def forward_blocked_train(self, x16):
         """autograd-recorded form (training): every block is a Function over the C ABI"""
         emb = self.main[0][0]
-        h32, h16 = ag.ConvBlk.apply(None, x16, emb.weight, emb.bias, self._cache[0], MS_CONV, 1, 3,
+        h32, h16 = ag.conv_blk(None, x16, emb.weight, emb.bias, self._cache[0], MS_CONV, 1, 3,
                                     1, True)
         for i in range(1, len(self.main)):
             up = self.main[i]
             s = up.scale_factor
-            h32, h16 = ag.ConvBlk.apply(h32, h16, up.conv.weight, None, self._cache[i], MS_CONVT, 1,
+            h32, h16 = ag.conv_blk(h32, h16, up.conv.weight, None, self._cache[i], MS_CONVT, 1,
                                         s // 2, s, True)
         return ag.BankSynthesis.apply(h32, h16, self.filter_bank)
 
@@ -213,7 +213,7 @@ class ChannelGenerator(nn.Module):
         for i in range(len(self.scale_factors)):
             up, stack = self.main[2 * i], self.main[2 * i + 1]
             s = up.scale_factor
-            h32, h16 = ag.ConvBlk.apply(h32, h16, up.conv.weight, None, self._cache[i], MS_CONVT, 1,
+            h32, h16 = ag.conv_blk(h32, h16, up.conv.weight, None, self._cache[i], MS_CONVT, 1,
                                         s // 2, s, True)
             h32, h16 = stack.forward_blocked_train(h32, h16)
         return ag.MonoConv.apply(h32, self.to_samples.weight, self.to_samples.bias, 7, 3, False)
@@ -281,7 +281,7 @@ class MultiScaleGenerator(nn.Module):
                            "this path; the MultiScale experiments train on band dictionaries "
                            "(experiment/multiscale.py:120-160)")
         x16 = ops.pack_ncl(x, 3, 1)
-        e32, e16 = ag.ConvBlk.apply(None, x16, self.embedding.weight, self.embedding.bias, self._ce,
+        e32, e16 = ag.conv_blk(None, x16, self.embedding.weight, self.embedding.bias, self._ce,
                                     MS_CONV, 1, 0, 1, True)
         return {size: layer.forward_blocked_train(e32, e16)
                 for size, layer in self.channel_generators.items()}

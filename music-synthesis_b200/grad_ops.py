@@ -237,3 +237,24 @@ def depth_to_space32(dys32, channels, stride, out_rows, length, rows_valid=None,
                                              row_offset, out_rows, length, stride, stream_ptr()),
           "ms_depth_to_space_blk32")
     return dx
+
+
+def act_pad_bwd(dy32, sign16, length, pad, pad_mode):
+    """gradient of ops.act_pad on the fp32 stream (LeakyReLU mask from the 16-bit image of x)"""
+    dy32 = dy32.contiguous()
+    B, C8, _, _ = dy32.shape
+    dx = torch.empty((B, C8, length, 8), dtype=torch.float32, device=dy32.device)
+    check(_lib.lib().ms_blk_act_pad_bwd(ptr(dy32), ptr(sign16), ptr(dx), B, C8 * 8, length, pad,
+                                        pad_mode, stream_ptr()), "ms_blk_act_pad_bwd")
+    return dx
+
+
+def weight_norm_bwd(dw, v, g):
+    """gradient of ops.weight_norm_fold -> (dv, dg with the shape of g)"""
+    dw, v = dw.contiguous(), v.contiguous()
+    rows = v.shape[0]
+    dv = torch.empty_like(v)
+    dg = torch.empty(rows, dtype=torch.float32, device=v.device)
+    check(_lib.lib().ms_weight_norm_bwd(ptr(dw), ptr(v), ptr(g.contiguous()), ptr(dv), ptr(dg), rows,
+                                        v.numel() // rows, stream_ptr()), "ms_weight_norm_bwd")
+    return dv, dg.reshape(g.shape)

@@ -142,3 +142,56 @@ def test_multiscale_pair_train_cycle_matches_oracle():
     worst_g = max(errs.values())
     assert not bad, ("G", bad)
     print("multiscale pair: worst grad rel_l2 D %.4f G %.4f" % (worst_d, worst_g))
+
+
+def test_realmelgan_pair_train_cycle_matches_oracle():
+    """the official-MelGAN pair (experiment/realmelgan.py: weight-normed, reflection-padded
+    generator; three independent NLayerDiscriminators) through the trainers: gradients reach
+    weight_g / weight_v through the weight-norm fold"""
+    from music_synthesis_b200.experiment.realmelgan import Generator, Discriminator
+    from music_synthesis_b200.train import GeneratorTrainer, DiscriminatorTrainer, Adam
+    from music_synthesis_b200.loss.loss import (mel_gan_disc_loss, mel_gan_gen_loss,
+                                                least_squares_disc_loss,
+                                                least_squares_generator_loss)
+    B, T = 2, 8
+    g_sd = restate.realmelgan_generator_state(211)
+    d_sd = restate.realmelgan_discriminator_state(212)
+    g = Generator(128, 32, n_residual_layers=3)
+    g.load_state_dict(g_sd)
+    d = Discriminator(3, 16, 4, 4)
+    d.load_state_dict(d_sd)
+    g, d = g.cuda(), d.cuda()
+
+    def gen_fn(features, sd):
+        return restate.realmelgan_generator(features, sd)
+
+    def disc_fn(x, features, sd):
+        return restate.realmelgan_discriminator(x, sd)
+
+    g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss, least_squares_disc_loss)
+    g_tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, least_squares_generator_loss)
+    real = synth.randn(213, B, 1, 256 * T) * 0.1
+    feats = synth.mel_features(214, B, T)
+    rd = d_tr.train(real.cuda(), feats.cuda())
+    d_loss, d_grads, d_new = restate.discriminator_train_step(
+        g_sd, d_sd, real, feats, {}, sub_loss=restate.least_squares_disc_loss,
+        gen_fn=gen_fn, disc_fn=disc_fn)
+    assert abs(rd["d_loss"] - d_loss) < 2e-3 * abs(d_loss), (rd["d_loss"], d_loss)
+    errs = {k: rel_l2(p.grad, d_grads[k]) for k, p in d.named_parameters()}
+    bad = {k: round(e, 4) for k, e in errs.items() if not e < D_TOL}
+    worst_d = max(errs.values())
+    assert not bad, ("D", bad)
+    d.load_state_dict(d_new)
+    rg = g_tr.train(real.cuda(), feats.cuda())
+    g_loss, fake, g_grads, _ = restate.generator_train_step(
+        g_sd, d_new, real, feats, {}, sub_loss=restate.least_squares_generator_loss,
+        gen_fn=gen_fn, disc_fn=disc_fn)
+    assert abs(rg["g_loss"] - g_loss) < 2e-3 * max(1.0, abs(g_loss)), (rg["g_loss"], g_loss)
+    assert rel_l2(rg["fake"], fake) < 2e-3
+    errs = {k: rel_l2(p.grad, g_grads[k]) for k, p in g.named_parameters()}
+    bad = {k: round(e, 4) for k, e in errs.items() if not e < G_TOL}
+    worst_g = max(errs.values())
+    assert not bad, ("G", bad)
+    print("realmelgan pair: worst grad rel_l2 D %.4f G %.4f" % (worst_d, worst_g))
