@@ -410,9 +410,12 @@ direct_wgrad_kernel(const DirectBwdParams p) {
 
 
 // ---- register-tiled variants for the discriminators' shapes (COG in {4,16}, CIG in {1,4}) ----
-// dgrad: one thread = one input time step x all CIG input channels of the group; taps visited
-// are k = kfirst + s*j with output row l = lq - j (no integer division in the loop); weights in
-// shared memory as [oc][k][c] so one 16-byte broadcast read feeds CIG FMAs.
+// dgrad: one thread = one input time step x all CIG input channels of the group.  Taps visited
+// are k = kfirst + s*j with output row l = lq - j (no integer division in the loop); the tap
+// loop is the OUTER loop and the COG output channels are unrolled inside it: dz is staged as
+// [l][oc] and the weights as [oc][k][c] (threads of a warp differ in k by < s: consecutive
+// 16-byte words, no bank conflict), so one step reads COG/4 + COG 16-byte vectors for 4*COG
+// FMAs (1.3 instructions per FMA instead of the 6 of the (oc, tap) loop order).
 template <int COG, int CIG>
 __global__ void __launch_bounds__(kDgTile)
 direct_dgrad_tiled_kernel(const DirectBwdParams p) {
@@ -425,20 +428,20 @@ direct_dgrad_tiled_kernel(const DirectBwdParams p) {
   const int l1 = (i0 + kDgTile - 1 + p.pad) / s;
   const int nl = l1 - l0 + 1;
   float* sw = sm;                               // [COG][k][4]  (c padded to 4)
-  float* sz = sm + COG * p.k * 4;               // [COG][nl]
-  for (int i = threadIdx.x; i < COG * p.k * 4; i += kDgTile) {
+  float* sz = sm + p.k * COG * 4;               // [nl][COG]
+  for (int i = threadIdx.x; i < p.k * COG * 4; i += kDgTile) {
     const int c = i & 3, k = (i >> 2) % p.k, oc = (i >> 2) / p.k;
     sw[i] = c < CIG ? __ldg(p.w + (static_cast<size_t>(g * COG + oc) * CIG + c) * p.k + k) : 0.f;
   }
   for (int i = threadIdx.x; i < COG * nl; i += kDgTile) {
-    const int oc = i / nl, l = l0 + (i - oc * nl);
+    const int oc = i / nl, li = i - oc * nl, l = l0 + li;     // coalesced along l
     float v = 0.f;
     if (l >= 0 && l < p.lout) {
       const size_t idx = (static_cast<size_t>(b) * p.cout + g * COG + oc) * p.lout + l;
       v = __ldg(p.dy + idx);
       if (p.y != nullptr) v = masked(v, __ldg(p.y + idx), p.leaky);
     }
-    sz[i] = v;
+    sz[li * COG + oc] = v;
   }
   __syncthreads();
   const int i = i0 + threadIdx.x;
@@ -447,17 +450,24 @@ direct_dgrad_tiled_kernel(const DirectBwdParams p) {
   const int kfirst = ip % s;
   const int lq = (ip - kfirst) / s;             // output row of tap kfirst
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int oc = 0; oc < COG; ++oc) {
-    const float* zr = sz + oc * nl - l0 + lq;   // zr[-j] = dz[oc][lq - j]
-    const float4* wr = reinterpret_cast<const float4*>(sw + (oc * p.k + kfirst) * 4);
-    int j = 0;
-    for (int k = kfirst; k < p.k && j <= lq; k += s, ++j) {
-      const float z = zr[-j];
-      const float4 w = wr[j * s];
-      acc[0] = fmaf(w.x, z, acc[0]);
-      acc[1] = fmaf(w.y, z, acc[1]);
-      acc[2] = fmaf(w.z, z, acc[2]);
-      acc[3] = fmaf(w.w, z, acc[3]);
+  const float4* zrow = reinterpret_cast<const float4*>(sz + (lq - l0) * COG);
+  const float4* wrow = reinterpret_cast<const float4*>(sw) + kfirst;
+  int j = 0;
+  for (int k = kfirst; k < p.k && j <= lq; k += s, ++j) {
+    const float4* z4 = zrow - j * (COG / 4);            // dz[lq - j][0..COG)
+    const float4* w4 = wrow + j * s;                    // w[oc][k][0..4) at w4[oc * K]
+#pragma unroll
+    for (int q = 0; q < COG / 4; ++q) {
+      const float4 z = z4[q];
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 w = w4[(q * 4 + e) * p.k];
+        acc[0] = fmaf(w.x, zz[e], acc[0]);
+        acc[1] = fmaf(w.y, zz[e], acc[1]);
+        acc[2] = fmaf(w.z, zz[e], acc[2]);
+        acc[3] = fmaf(w.w, zz[e], acc[3]);
+      }
     }
   }
 #pragma unroll
