@@ -50,49 +50,106 @@ audio2mel_kernel(const A2MParams p) {
   const int f0 = (blockIdx.x % p.groups) * kFramesPerCta;
   const float* a = p.audio + static_cast<size_t>(b) * p.N;
 
-  for (int i = tid; i < n - 1; i += kA2MThreads) {
-    const int half = 1 << (31 - __clz(i + 1));      // largest power of two <= i+1
-    const int pos = i + 1 - half;
-    float s, c;
-    sincospif(-static_cast<float>(pos) / static_cast<float>(half), &s, &c);
-    tw_c[i] = c;
-    tw_s[i] = s;
-  }
-  // load 8 windowed frames, bit-reversed, frame 2j -> real part, 2j+1 -> imaginary part
-  for (int i = tid; i < 4 * n; i += kA2MThreads) {
-    const int j = i / n;
-    const int t = i - j * n;
-    const int rev = static_cast<int>(__brev(static_cast<unsigned>(t)) >> (32 - log2n));
-    const float w = __ldg(p.window + t);
-    const int fa = f0 + 2 * j, fb = fa + 1;
-    const long long sa = static_cast<long long>(fa) * p.hop + t;
-    const long long sb = static_cast<long long>(fb) * p.hop + t;
-    const float va = (fa < p.F && sa < p.N) ? __ldg(a + sa) : 0.f;
-    const float vb = (fb < p.F && sb < p.N) ? __ldg(a + sb) : 0.f;
-    zr[j * n + rev] = va * w;
-    zi[j * n + rev] = vb * w;
-  }
-  __syncthreads();
-  // 4 in-place radix-2 DIT FFTs side by side
-  for (int s = 0; s < log2n; ++s) {
-    const int half = 1 << s;
-    const float* twc = tw_c + half - 1;
-    const float* tws_ = tw_s + half - 1;
-    for (int i = tid; i < 2 * n; i += kA2MThreads) {   // 4 * n/2 butterflies
-      const int j = i / (n / 2);
-      const int bf = i - j * (n / 2);
-      const int pos = bf & (half - 1);
-      const int i0 = ((bf >> s) << (s + 1)) + pos + j * n;
-      const int i1 = i0 + half;
-      const float c = twc[pos], sn = tws_[pos];
-      const float xr = zr[i1], xi = zi[i1];
-      const float tr = xr * c - xi * sn;
-      const float ti = xr * sn + xi * c;
-      const float ur = zr[i0], ui = zi[i0];
-      zr[i0] = ur + tr; zi[i0] = ui + ti;
-      zr[i1] = ur - tr; zi[i1] = ui - ti;
+  if (LOG2N == 10) {
+    // ---- n = 1024 = 4^5: radix-4 decimation in time, 5 passes (half the shared-memory traffic
+    // and barriers of the radix-2 form).  One twiddle table tw[k] = exp(-2*pi*i*k/n), k < n.
+    for (int i = tid; i < n; i += kA2MThreads) {
+      float sn, cs;
+      sincospif(-2.f * static_cast<float>(i) / static_cast<float>(n), &sn, &cs);
+      tw_c[i] = cs;
+      tw_s[i] = sn;
+    }
+    // load 8 windowed frames in base-4 digit-reversed order; frame 2j -> re, 2j+1 -> im
+    for (int i = tid; i < 4 * n; i += kA2MThreads) {
+      const int j = i >> 10;
+      const int t = i & 1023;
+      const int rev = ((t & 3) << 8) | (((t >> 2) & 3) << 6) | (((t >> 4) & 3) << 4) |
+                      (((t >> 6) & 3) << 2) | ((t >> 8) & 3);
+      const float w = __ldg(p.window + t);
+      const int fa = f0 + 2 * j, fb = fa + 1;
+      const long long sa = static_cast<long long>(fa) * p.hop + t;
+      const long long sb = static_cast<long long>(fb) * p.hop + t;
+      const float va = (fa < p.F && sa < p.N) ? __ldg(a + sa) : 0.f;
+      const float vb = (fb < p.F && sb < p.N) ? __ldg(a + sb) : 0.f;
+      zr[j * n + rev] = va * w;
+      zi[j * n + rev] = vb * w;
     }
     __syncthreads();
+#pragma unroll 1
+    for (int st = 0; st < 5; ++st) {
+      const int q = 1 << (2 * st);                 // butterfly span
+      const int tstep = 256 >> (2 * st);           // n / (4q): twiddle index step
+      for (int i = tid; i < n; i += kA2MThreads) {  // 4 transforms x n/4 butterflies
+        const int j = i >> 8;
+        const int bf = i & 255;
+        const int pos = bf & (q - 1);
+        const int i0 = ((bf >> (2 * st)) << (2 * st + 2)) + pos + j * n;
+        const int i1 = i0 + q, i2 = i1 + q, i3 = i2 + q;
+        const int k1 = pos * tstep;
+        const float c1 = tw_c[k1], s1 = tw_s[k1];
+        const float c2 = tw_c[2 * k1], s2 = tw_s[2 * k1];
+        const float c3 = tw_c[3 * k1], s3 = tw_s[3 * k1];
+        const float ar = zr[i0], ai = zi[i0];
+        float xr = zr[i1], xi = zi[i1];
+        const float br = xr * c1 - xi * s1, bi = xr * s1 + xi * c1;
+        xr = zr[i2]; xi = zi[i2];
+        const float cr = xr * c2 - xi * s2, ci = xr * s2 + xi * c2;
+        xr = zr[i3]; xi = zi[i3];
+        const float dr = xr * c3 - xi * s3, di = xr * s3 + xi * c3;
+        const float t0r = ar + cr, t0i = ai + ci, t1r = ar - cr, t1i = ai - ci;
+        const float t2r = br + dr, t2i = bi + di, t3r = br - dr, t3i = bi - di;
+        zr[i0] = t0r + t2r; zi[i0] = t0i + t2i;
+        zr[i2] = t0r - t2r; zi[i2] = t0i - t2i;
+        zr[i1] = t1r + t3i; zi[i1] = t1i - t3r;     // (a - c) - j (b - d)
+        zr[i3] = t1r - t3i; zi[i3] = t1i + t3r;     // (a - c) + j (b - d)
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int i = tid; i < n - 1; i += kA2MThreads) {
+      const int half = 1 << (31 - __clz(i + 1));      // largest power of two <= i+1
+      const int pos = i + 1 - half;
+      float s, c;
+      sincospif(-static_cast<float>(pos) / static_cast<float>(half), &s, &c);
+      tw_c[i] = c;
+      tw_s[i] = s;
+    }
+    // load 8 windowed frames, bit-reversed, frame 2j -> real part, 2j+1 -> imaginary part
+    for (int i = tid; i < 4 * n; i += kA2MThreads) {
+      const int j = i / n;
+      const int t = i - j * n;
+      const int rev = static_cast<int>(__brev(static_cast<unsigned>(t)) >> (32 - log2n));
+      const float w = __ldg(p.window + t);
+      const int fa = f0 + 2 * j, fb = fa + 1;
+      const long long sa = static_cast<long long>(fa) * p.hop + t;
+      const long long sb = static_cast<long long>(fb) * p.hop + t;
+      const float va = (fa < p.F && sa < p.N) ? __ldg(a + sa) : 0.f;
+      const float vb = (fb < p.F && sb < p.N) ? __ldg(a + sb) : 0.f;
+      zr[j * n + rev] = va * w;
+      zi[j * n + rev] = vb * w;
+    }
+    __syncthreads();
+    // 4 in-place radix-2 DIT FFTs side by side
+    for (int s = 0; s < log2n; ++s) {
+      const int half = 1 << s;
+      const float* twc = tw_c + half - 1;
+      const float* tws_ = tw_s + half - 1;
+      for (int i = tid; i < 2 * n; i += kA2MThreads) {   // 4 * n/2 butterflies
+        const int j = i / (n / 2);
+        const int bf = i - j * (n / 2);
+        const int pos = bf & (half - 1);
+        const int i0 = ((bf >> s) << (s + 1)) + pos + j * n;
+        const int i1 = i0 + half;
+        const float c = twc[pos], sn = tws_[pos];
+        const float xr = zr[i1], xi = zi[i1];
+        const float tr = xr * c - xi * sn;
+        const float ti = xr * sn + xi * c;
+        const float ur = zr[i0], ui = zi[i0];
+        zr[i0] = ur + tr; zi[i0] = ui + ti;
+        zr[i1] = ur - tr; zi[i1] = ui - ti;
+      }
+      __syncthreads();
+    }
   }
   // untangle the two real spectra of each complex transform, take magnitudes
   for (int i = tid; i < 4 * bins; i += kA2MThreads) {

@@ -56,5 +56,31 @@ xa = (synth.randn(5, 32, 1, 8192) * 0.1).cuda()
 t = timeit(lambda: md(xa), n=10)
 out.append({"row": "a6 MelGanDiscriminator fwd", "workload": "32 clips x 8192 (cfg4 batch)", "us": t * 1e6,
             "bound": "tensor", "achieved_TFLOPs": 0.861e9 * 32 / t / 1e12})
+from music_synthesis_b200.experiment.realmelgan import Generator as RealG, Discriminator as RealD
+rg = RealG(128, 32, n_residual_layers=3).eval()
+rg.load_state_dict(restate.realmelgan_generator_state(101)); rg = rg.cuda()
+f64 = synth.mel_features(6, 32, 64).cuda()
+t = timeit(lambda: rg(f64), n=10)
+out.append({"row": "a5 realmelgan.Generator fwd", "workload": "32 clips x 64 frames -> 16384 samples", "us": t * 1e6,
+            "bound": "tensor", "achieved_TFLOPs": 5.804e9 * 32 / t / 1e12, "frac": 5.804e9 * 32 / t / PEAK_TF})
+rd = RealD(3, 16, 4, 4).eval()
+rd.load_state_dict(restate.realmelgan_discriminator_state(103)); rd = rd.cuda()
+t = timeit(lambda: rd(xa, None), n=10)
+out.append({"row": "a7 realmelgan.Discriminator fwd", "workload": "32 clips x 8192 (cfg4 batch)", "us": t * 1e6,
+            "bound": "tensor", "achieved_TFLOPs": 0.839e9 * 32 / t / 1e12})
+from music_synthesis_b200.generator.multiscale import MultiScaleGenerator
+from music_synthesis_b200.discriminator.multiscale import MultiScaleMultiResDiscriminator
+mg = MultiScaleGenerator(128, 256, 65536, transposed_conv=True, recompose=False).eval()
+mg.load_state_dict(restate.multiscale_generator_state(171, 65536)); mg = mg.cuda()
+t = timeit(lambda: mg(feat), n=10)
+out.append({"row": "a12 MultiScaleGenerator fwd", "workload": "8 clips x 256 frames -> 5 bands of 65536..4096", "us": t * 1e6,
+            "bound": "tensor", "achieved_TFLOPs": 23.084e9 * 8 / t / 1e12, "frac": 23.084e9 * 8 / t / PEAK_TF})
+mdisc = MultiScaleMultiResDiscriminator(65536, decompose=False, channel_judgements=True,
+                                        conditioning_channels=128).eval()
+mdisc.load_state_dict(restate.multiscale_discriminator_state(173, 65536)); mdisc = mdisc.cuda()
+mb = mg(feat)
+t = timeit(lambda: mdisc(mb, feat), n=10)
+out.append({"row": "a12 MultiScaleMultiResDiscriminator fwd", "workload": "8 clips x 65536 (band dict)", "us": t * 1e6,
+            "bound": "tensor", "achieved_TFLOPs": 10.814e9 * 8 / t / 1e12, "frac": 10.814e9 * 8 / t / PEAK_TF})
 for o in out:
     print(json.dumps(o))
