@@ -91,8 +91,11 @@ __device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
   return pack_h2(a, b);
 }
 
-template <int C, bool PAIR>
+// BF: bf16 operands (compile-time: a runtime format makes ptxas emit BOTH predicated F2FP
+// variants in the epilogue, which is instruction-issue-bound)
+template <int C, bool PAIR, bool BF>
 __device__ __forceinline__ void resstack_body(const StackParams& p) {
+  constexpr int kOp = BF ? MS_BF16 : MS_F16;
   using G = StackGeom<C>;
   constexpr int MB = G::MB, HB = G::HB, R = G::R, EW = G::EW;
   constexpr int NSLOT = PAIR ? G::NSLOT_P : G::NSLOT;
@@ -194,7 +197,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
     // Warp-uniform control flow; only the tcgen05 instructions are predicated on one
     // elected lane, so descriptors stay in uniform registers.
     {
-      const uint32_t idesc = PAIR ? umma_idesc_f16_m256(C, p.operand) : umma_idesc_f16(C, p.operand);
+      const uint32_t idesc = PAIR ? umma_idesc_f16_m256(C, kOp) : umma_idesc_f16(C, kOp);
       const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);
       const uint64_t bdesc0 = umma_desc_base_nosw(NB * 16, 128);
       uint32_t pos = 0;      // ring position of the current conv's first tap
@@ -314,10 +317,10 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
           for (int c = 0; c < COLS / 8; ++c) {
             const uint32_t dst = sX + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
             st_shared_v4(dst,
-                         pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), p.operand),
-                         pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), p.operand),
-                         pack2s(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]), p.operand),
-                         pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), p.operand));
+                         pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), kOp),
+                         pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), kOp),
+                         pack2s(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]), kOp),
+                         pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), kOp));
           }
 #pragma unroll
           for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
@@ -404,10 +407,10 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
 #pragma unroll
               for (int c = 0; c < COLS / 8; ++c) {
                 const uint32_t dst = dstbuf + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
-                st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
-                             pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
-                             pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
-                             pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
+                st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], kOp),
+                             pack2s(f[c * 8 + 2], f[c * 8 + 3], kOp),
+                             pack2s(f[c * 8 + 4], f[c * 8 + 5], kOp),
+                             pack2s(f[c * 8 + 6], f[c * 8 + 7], kOp));
               }
             } else if (mono) {
               // fused tail, step 1: this thread's 16 channels of its row contribute
@@ -434,10 +437,10 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
                 const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk0 + c) * p.L + t;
                 if (p.y16 != nullptr)
                   *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
-                      make_uint4(pack2s(f[c * 8 + 0], f[c * 8 + 1], p.operand),
-                                 pack2s(f[c * 8 + 2], f[c * 8 + 3], p.operand),
-                                 pack2s(f[c * 8 + 4], f[c * 8 + 5], p.operand),
-                                 pack2s(f[c * 8 + 6], f[c * 8 + 7], p.operand));
+                      make_uint4(pack2s(f[c * 8 + 0], f[c * 8 + 1], kOp),
+                                 pack2s(f[c * 8 + 2], f[c * 8 + 3], kOp),
+                                 pack2s(f[c * 8 + 4], f[c * 8 + 5], kOp),
+                                 pack2s(f[c * 8 + 6], f[c * 8 + 7], kOp));
                 if (p.y32 != nullptr) {
                   const float o8[8] = {f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3],
                                        f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]};
@@ -488,7 +491,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
 template <int C>
 __global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
 resstack_kernel(const __grid_constant__ StackParams p) {
-  resstack_body<C, false>(p);
+  resstack_body<C, false, false>(p);
 }
 
 // CTA-pair variant (cta_group::2): the two CTAs of a cluster work on adjacent tiles in
@@ -496,9 +499,15 @@ resstack_kernel(const __grid_constant__ StackParams p) {
 // stages half of every weight tap.  Used for C = 128, where a single CTA's N = 128 MMAs
 // saturate the shared-memory port (A 4 KB + B 4 KB per 64 cycles) and starve the epilogue.
 template <int C>
+__global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
+resstack_bf16_kernel(const __grid_constant__ StackParams p) {
+  resstack_body<C, false, true>(p);
+}
+
+template <int C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
 resstack_pair_kernel(const __grid_constant__ StackParams p) {
-  resstack_body<C, true>(p);
+  resstack_body<C, true, false>(p);
 }
 
 // MSB_STACK_PAIR=1 enables the CTA-pair variant (process-wide, read once).  Off by default:
@@ -544,6 +553,17 @@ ms_status launch_stack(const StackParams& p, cudaStream_t stream) {
   const int sms = sm_count();
   if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (p.operand == MS_BF16) {
+    static thread_local bool attr_set_bf = false;
+    if (!attr_set_bf) {
+      cudaError_t e = cudaFuncSetAttribute(resstack_bf16_kernel<C>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(resstack_bf16_kernel)");
+      attr_set_bf = true;
+    }
+    resstack_bf16_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+    return after_launch("resstack_bf16_kernel");
+  }
   resstack_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
   return after_launch("resstack_kernel");
 }
@@ -590,7 +610,7 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   p.total_tiles = static_cast<int>(tiles);
   switch (channels) {
     case 128:
-      return stack_pair_enabled(128) ? launch_stack_pair<128>(p, stream)
+      return (stack_pair_enabled(128) && p.operand != MS_BF16) ? launch_stack_pair<128>(p, stream)
                                      : launch_stack<128>(p, stream);
     case 64: return launch_stack<64>(p, stream);
     default: return launch_stack<32>(p, stream);
