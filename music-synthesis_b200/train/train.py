@@ -144,6 +144,11 @@ class _GraphMixin:
         """eager or graphed zero_grad + forward + backward -> tuple of output tensors"""
         if not self.cuda_graph:
             return self._fwd_bwd(samples, features)
+        for o in (self.g_optim, self.d_optim):
+            if not hasattr(o, "flat_grad"):
+                raise ValueError("cuda_graph=True needs the flat-buffer optimisers of "
+                                 "music_synthesis_b200.train.optim (gradients must keep their "
+                                 "addresses across replays)")
         multi = isinstance(samples, dict)            # MultiScale audio: {band size: tensor}
         key = (tuple((k, tuple(v.shape)) for k, v in samples.items()) if multi
                else tuple(samples.shape), tuple(features.shape))
