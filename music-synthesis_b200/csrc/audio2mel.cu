@@ -28,7 +28,7 @@ struct A2MParams {
 
 // LOG2N > 0: compile-time FFT size (index arithmetic becomes shifts / masks); 0: runtime size
 template <int LOG2N>
-__global__ void __launch_bounds__(kA2MThreads)
+__global__ void __launch_bounds__(kA2MThreads, 4)
 audio2mel_kernel(const A2MParams p) {
   extern __shared__ float sm[];
   const int n = LOG2N > 0 ? (1 << LOG2N) : p.n_fft;
@@ -38,9 +38,12 @@ audio2mel_kernel(const A2MParams p) {
   // per-stage CONTIGUOUS twiddle tables: stage with butterfly span `half` uses entries
   // [half-1, 2*half-1) = exp(-2*pi*i*pos/(2*half)) -- conflict-free (a single strided table
   // would be read with a power-of-two stride: up to 32-way bank conflicts)
-  float* tw_c = sm;                     // [n]
-  float* tw_s = tw_c + n;               // [n]
-  float* mag = tw_s + n;                // [8][magld]
+  // twiddle tables: [n] each for the radix-2 form, [3n/4] for the radix-4 form of n = 1024
+  // (indices k1, 2k1, 3k1 < 3n/4) -- 55.4 KB per CTA, four CTAs per SM
+  const int twn = LOG2N == 10 ? 3 * n / 4 : n;
+  float* tw_c = sm;                     // [twn]
+  float* tw_s = tw_c + twn;             // [twn]
+  float* mag = tw_s + twn;              // [8][magld]
   float* zr = mag + kFramesPerCta * magld;   // [4][n]   (re)  -- reused as basis tile
   float* zi = zr + 4 * n;                    // [4][n]   (im)
   float* tile = zr;                          // [128][33]
@@ -53,7 +56,7 @@ audio2mel_kernel(const A2MParams p) {
   if (LOG2N == 10) {
     // ---- n = 1024 = 4^5: radix-4 decimation in time, 5 passes (half the shared-memory traffic
     // and barriers of the radix-2 form).  One twiddle table tw[k] = exp(-2*pi*i*k/n), k < n.
-    for (int i = tid; i < n; i += kA2MThreads) {
+    for (int i = tid; i < twn; i += kA2MThreads) {
       float sn, cs;
       sincospif(-2.f * static_cast<float>(i) / static_cast<float>(n), &sn, &cs);
       tw_c[i] = cs;
@@ -259,7 +262,8 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
   p.bins = n_fft / 2 + 1; p.F = F; p.groups = (F + kFramesPerCta - 1) / kFramesPerCta;
   const size_t fft_floats = 8 * static_cast<size_t>(n_fft);
   const size_t tile_floats = 128 * 33;
-  const size_t smem = sizeof(float) * (2 * n_fft + kFramesPerCta * (p.bins + 3) +
+  const size_t tw_floats = n_fft == 1024 ? 2 * (3 * n_fft / 4) : 2 * n_fft;
+  const size_t smem = sizeof(float) * (tw_floats + kFramesPerCta * (p.bins + 3) +
                                        (fft_floats > tile_floats ? fft_floats : tile_floats));
   static thread_local size_t attr_set = 0;
   if (smem > attr_set) {
