@@ -447,6 +447,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
       const float* tbias = s_bias + (acc & 1) * 256;
       const int2* ttab = s_tab + (acc & 1) * 32;
+      if (p.res32 != nullptr && p.kind == MS_CONV && p.fold_slots == 0) {
+        // residual rows of this tile into L2 while the MMAs still run (the epilogue is
+        // latency-bound on these loads)
+        for (int mb = 0; mb < p.MBLK; ++mb) {
+          const int pm = mt * rows_per_tile + mb * 128 + q * 32 + lane;
+          if (pm >= p.Lm) continue;
+          for (int g = 2 * half; g < ngroups; g += 4) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int cidx = g * 2 + h;
+              if (cidx * 8 >= p.NT) break;
+              const int ch = n0 + cidx * 8;
+              prefetch_l2(p.res32 + ((static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + pm) * 8);
+            }
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int mb = 0; mb < p.MBLK; ++mb) {

@@ -234,9 +234,22 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       }
       const float* tbias = s_bias + (acc & 1) * 256;
       const int2* ttab = s_tab + (acc & 1) * 32;
+      const int m = mt * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+      if (p.res32 != nullptr && p.kind == MS_CONV && m < p.Lm) {
+        // residual rows of this tile into L2 while the MMAs still run: the epilogue is
+        // latency-bound on these loads (8 warps, one 32-byte vector per thread per chunk)
+        for (int g = 2 * half; g < ngroups; g += 4) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int cidx = g * 2 + h;
+            if (cidx * 8 >= p.NT) break;
+            const int ch = n0 + cidx * 8;
+            prefetch_l2(p.res32 + ((static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + m) * 8);
+          }
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = mt * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * p.NT);
       bool arrived = false;
