@@ -104,3 +104,43 @@ def test_packed_weight_layout_is_length_independent(lib):
             d = ops.conv_desc(kind, 3, cin, cout, lin, k, 1, p, s)
             sizes.add(lib.ms_conv_packed_weight_bytes(ctypes.byref(d)))
         assert len(sizes) == 1 and 0 not in sizes
+
+
+@pytest.mark.parametrize("k,s", [(7, 2), (7, 4), (41, 4), (41, 2), (9, 4)])
+def test_strided_conv_weight_rewrite_is_exact_on_cpu(k, s):
+    """host logic behind every strided conv on the tcgen05 path: Conv1d(k, stride s, pad k//2)
+    == stride-1 conv over the space-to-depth input with ops.strided_conv_weight (checked here
+    with CPU torch ops; the GPU tests check the kernels)"""
+    import torch
+    import torch.nn.functional as F
+    from music_synthesis_b200 import ops
+    torch.manual_seed(0)
+    B, C, Co, L = 2, 3, 5, 37
+    x = torch.randn(B, C, L)
+    w = torch.randn(Co, C, k)
+    ref = F.conv1d(x, w, stride=s, padding=k // 2)
+    w1, taps, pad = ops.strided_conv_weight(w, s)
+    lx = (L + s - 1) // s
+    xp = F.pad(x, (0, lx * s - L))
+    xs = xp.reshape(B, C, lx, s).permute(0, 3, 1, 2).reshape(B, s * C, lx)      # Y[i*C + c, u] = X[c, s*u + i]
+    y = F.conv1d(xs, w1, padding=pad)[:, :, :lx]
+    assert y.shape[-1] >= ref.shape[-1]
+    assert torch.allclose(y[:, :, :ref.shape[-1]], ref, atol=1e-4)
+
+
+def test_loss_scaler_policy(monkeypatch):
+    import torch
+    from music_synthesis_b200 import grad_ops
+    from music_synthesis_b200.train.train import LossScaler
+    monkeypatch.setattr(grad_ops, "NEEDS_LOSS_SCALE", True)
+    sc = LossScaler(torch.device("cpu"), init_scale=1024.0, growth_interval=3)
+    assert sc.enabled and float(sc.scale_dev) == 1024.0 and float(sc.inv_scale_dev) == 1 / 1024.0
+    sc.update(True)                                   # overflow: halve, count the skipped step
+    assert sc.scale == 512.0 and sc.skipped == 1 and float(sc.scale_dev) == 512.0
+    for _ in range(3):
+        sc.update(False)                              # growth_interval clean steps: double
+    assert sc.scale == 1024.0
+    monkeypatch.setattr(grad_ops, "NEEDS_LOSS_SCALE", False)
+    off = LossScaler(torch.device("cpu"))
+    off.update(True)
+    assert not off.enabled and off.scale == 1.0       # bf16 backward: no scaling at all
