@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=CLIPS, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -237,13 +238,14 @@ def main():
         # ---- end to end through the module with HOST buffers ---------------------
         # the public host-to-host call: pinned features in, pinned waveform out, every step
         # copies its 33.5 MB of inputs H2D and its 67 MB of audio D2H inside the timed region
+        ekw = {"chunk_clips": args.e2e_chunk} if args.e2e_chunk > 0 else {}
         for _ in range(2):
-            gen.generate(x_host, out=y_host)
+            gen.generate(x_host, out=y_host, **ekw)
         sync_all()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(args.steps):
-            gen.generate(x_host, out=y_host)
+            gen.generate(x_host, out=y_host, **ekw)
         f1.record()
         sync_all()
         ms_e2e = f0.elapsed_time(f1)
