@@ -35,6 +35,8 @@ constexpr int kStackHeader = 1024;
 
 struct StackParams {
   const float* x32;      // BLK f32 (B, C/8, L, 8): stack input (upsampler output)
+  const uint16_t* x16in; // alternative input: BLK 16-bit (the stream then starts from the rounded
+                         // operand: 2 instead of 4 bytes per element in and out of HBM)
   const uint16_t* w;     // [6 convs][3 taps][C/8][C][8] 16-bit
   const float* bias;     // [6][C]
   uint16_t* y16;         // BLK 16-bit output or null
@@ -306,12 +308,31 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
               p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8;
           const size_t cstride = static_cast<size_t>(p.L) * 8;   // floats per chunk
           uint32_t v[COLS];
+          if (p.x16in != nullptr) {
+            const uint16_t* src16 =
+                p.x16in + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8;
 #pragma unroll
-          for (int c = 0; c < COLS / 8; ++c) {
-            float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (inside) ld_global_nc_v8(src + c * cstride, a8);
+            for (int c = 0; c < COLS / 8; ++c) {
+              uint4 q16 = make_uint4(0u, 0u, 0u, 0u);
+              if (inside) q16 = __ldg(reinterpret_cast<const uint4*>(src16 + c * cstride));
+              const uint32_t w16[4] = {q16.x, q16.y, q16.z, q16.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[c * 8 + j] = __float_as_uint(a8[j]);
+              for (int j = 0; j < 4; ++j) {
+                float2 f2;
+                if (BF) f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w16[j]));
+                else f2 = __half22float2(*reinterpret_cast<const __half2*>(&w16[j]));
+                v[c * 8 + 2 * j] = __float_as_uint(f2.x);
+                v[c * 8 + 2 * j + 1] = __float_as_uint(f2.y);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < COLS / 8; ++c) {
+              float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (inside) ld_global_nc_v8(src + c * cstride, a8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[c * 8 + j] = __float_as_uint(a8[j]);
+            }
           }
 #pragma unroll
           for (int c = 0; c < COLS / 8; ++c) {
@@ -347,8 +368,10 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
               const int t = nt0 + mb * 128 + q * 32 + lane;
               if (t >= 0 && t < p.L) {
 #pragma unroll
-                for (int c = 0; c < COLS / 8; ++c)
-                  prefetch_l2(p.x32 + ((static_cast<size_t>(nb) * G::NCH + chunk0 + c) * p.L + t) * 8);
+                for (int c = 0; c < COLS / 8; ++c) {
+                  const size_t e = ((static_cast<size_t>(nb) * G::NCH + chunk0 + c) * p.L + t) * 8;
+                  if (p.x16in != nullptr) prefetch_l2(p.x16in + e); else prefetch_l2(p.x32 + e);
+                }
               }
             }
           }
@@ -573,8 +596,8 @@ static thread_local long long* g_stack_dbg = nullptr;
 ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int operand,
                        const float* x32, const void* packed, void* y16, float* y32,
                        cudaStream_t stream, const float* mono_w, const float* mono_b,
-                       float* mono_out) {
-  if (batch <= 0 || len <= 0 || x32 == nullptr || packed == nullptr ||
+                       float* mono_out, const void* x16in) {
+  if (batch <= 0 || len <= 0 || (x32 == nullptr && x16in == nullptr) || packed == nullptr ||
       (y16 == nullptr && y32 == nullptr && mono_out == nullptr))
     return MS_ERR_INVALID;
   if (mono_out != nullptr && (channels != 32 || mono_w == nullptr || mono_b == nullptr))
@@ -586,6 +609,7 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   if (dil[0] + dil[1] + dil[2] + 3 > kStackHalo) return MS_ERR_INVALID;
   StackParams p;
   p.x32 = x32;
+  p.x16in = static_cast<const uint16_t*>(x16in);
   p.w = static_cast<const uint16_t*>(packed);
   p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) +
                                           static_cast<size_t>(18) * channels * channels * 2);
@@ -692,7 +716,7 @@ ms_status ms_resstack_fwd(int channels, int batch, int len, const int* dilations
                           void* stream) {
   if (dilations == nullptr || !ms_resstack_supported(channels)) return MS_ERR_INVALID;
   return resstack_fwd(channels, batch, len, dilations, operand, x32, packed, y16, y32,
-                      static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr);
+                      static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr);
 }
 
 ms_status ms_resstack_tail_fwd(int batch, int len, const int* dilations, int operand,
@@ -701,7 +725,7 @@ ms_status ms_resstack_tail_fwd(int batch, int len, const int* dilations, int ope
   if (dilations == nullptr || tail_w == nullptr || tail_b == nullptr || y == nullptr)
     return MS_ERR_INVALID;
   return resstack_fwd(32, batch, len, dilations, operand, x32, packed, nullptr, nullptr,
-                      static_cast<cudaStream_t>(stream), tail_w, tail_b, y);
+                      static_cast<cudaStream_t>(stream), tail_w, tail_b, y, nullptr);
 }
 
 }  // extern "C"
