@@ -77,7 +77,7 @@ typedef struct {
   int cin;       /* multiple of 16 */
   int cout;      /* multiple of 8 (MS_CONV: multiple of 16) */
   int lin;       /* input length */
-  int ksize;     /* taps (MS_CONVT: == 2*stride) */
+  int ksize;     /* taps, 1..24 (MS_CONVT: == 2*stride) */
   int dilation;  /* MS_CONV only */
   int pad;       /* zero padding (both sides) */
   int stride;    /* MS_CONVT only (MS_CONV: must be 1) */
