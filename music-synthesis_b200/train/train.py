@@ -5,7 +5,8 @@ One optimiser step each, same arithmetic as the reference; two pieces of work th
 and then throws away are skipped:
   * DiscriminatorTrainer: the reference back-propagates through the generator and discards
     those gradients (zero_grad at the next step, App. E.4) -- here the fake batch comes from the
-    fused inference kernels under no_grad;
+    fused inference kernels under no_grad, and the fake and real batches go through the
+    discriminator in ONE pass (concatenated along the batch axis; same per-clip arithmetic);
   * GeneratorTrainer: the discriminator's weight gradients are not formed (its parameters are
     frozen for the call) and the real batch runs without a tape.
 `exact_reference_grads=True` restores the reference's behaviour (all .grad fields populated).
@@ -238,8 +239,20 @@ class DiscriminatorTrainer(_GraphMixin):
         else:
             with torch.no_grad():
                 fake = self.generator(features)
-        _, f_score = self.discriminator(fake, features)
-        _, r_score = self.discriminator(samples, features)
+        if self.exact_reference_grads:
+            _, f_score = self.discriminator(fake, features)
+            _, r_score = self.discriminator(samples, features)
+        else:
+            # one pass over [fake; real]: the discriminators have no cross-clip operation, so this
+            # is the same arithmetic per clip with half the kernel launches
+            B = features.shape[0]
+            if isinstance(fake, dict):
+                both = {k: torch.cat([fake[k], samples[k]], dim=0) for k in fake}
+            else:
+                both = torch.cat([fake, samples], dim=0)
+            _, score = self.discriminator(both, torch.cat([features, features], dim=0))
+            f_score = [j[:B] for j in score]
+            r_score = [j[B:] for j in score]
         loss = self.loss(r_score, f_score, gan_loss=self.sub_loss)
         loss.backward(self._scaler(loss.device).scale_dev)
         return (loss.detach(),)
