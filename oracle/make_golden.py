@@ -202,6 +202,12 @@ def realmelgan():
             arrays[f"f{i}_{k}_shape"] = np.array(f.shape)
             arrays[f"f{i}_{k}_sub"] = f.numpy().reshape(-1)[::41]
     save("realmelgan_disc_n4096", **arrays)
+    # the pair's own losses (experiment/realmelgan.py:185-217) on D(real) vs D(second input)
+    a2 = synth.randn(105, 2, 1, 4096) * 0.1
+    feats2, judg2 = d(a2, None)
+    save("realmelgan_losses",
+         feature=float(rm.real_mel_gan_feature_loss(feats, feats2)),
+         gen=float(rm.mel_gan_gen_loss(feats, feats2, judg, judg2)))
 
 
 def train_step():

@@ -284,3 +284,14 @@ def test_generator_gradient_tolerance_is_set_by_forward_rounding():
         F.conv1d, F.conv_transpose1d = c1, ct
     worst = max(rel_l2(emu[k], ref[k]) for k in ref)
     assert 5e-3 < worst < 8e-2, worst
+
+
+def test_realmelgan_losses_match_reference(golden):
+    g = golden("realmelgan_losses")
+    dsd = restate.realmelgan_discriminator_state(103)
+    f1, j1 = restate.realmelgan_discriminator(synth.randn(104, 2, 1, 4096) * 0.1, dsd)
+    f2, j2 = restate.realmelgan_discriminator(synth.randn(105, 2, 1, 4096) * 0.1, dsd)
+    feat = restate.real_mel_gan_feature_loss(f1, f2)
+    gen = sum(restate.hinge_generator_loss(j) for j in j2) + 10 * feat
+    assert abs(float(feat) - float(g["feature"])) < 1e-6 * max(1.0, abs(float(g["feature"])))
+    assert abs(float(gen) - float(g["gen"])) < 1e-5 * max(1.0, abs(float(g["gen"])))
