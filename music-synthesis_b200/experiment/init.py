@@ -1,12 +1,15 @@
-"""featuresynth/experiment/init.py:3-9: N(0, 0.02) weights and zero biases on every module whose
-class name contains 'Conv' -- the random-init contract of the parity tests."""
+"""The reference's initialiser contract (featuresynth/experiment/init.py:3-9), the "random-init
+weights" of every parity test: modules whose class name contains "Conv" get N(0, 0.02) weights
+and, when they have one, a zero bias.  Used through `module.apply(weights_init)` exactly like
+the reference's Experiment does (experiment/experiment.py:109-115)."""
+import torch
 
 
-def weights_init(m):
-    classname = m.__class__.__name__
-    if 'Conv' in classname:
-        m.weight.data.normal_(0, 0.02)
-        try:
-            m.bias.data.fill_(0)
-        except AttributeError:
-            pass
+@torch.no_grad()
+def weights_init(module, std=0.02):
+    if "Conv" not in type(module).__name__:
+        return
+    torch.nn.init.normal_(module.weight, mean=0.0, std=std)
+    bias = getattr(module, "bias", None)
+    if bias is not None:
+        torch.nn.init.zeros_(bias)
