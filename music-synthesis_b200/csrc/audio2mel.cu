@@ -10,6 +10,9 @@
 // all 8 frames.  HBM traffic = audio in + log-mel out (+ the L2-resident basis).
 #include <math_constants.h>
 
+#include <cstdlib>
+
+#include "a2m_fft.cuh"
 #include "runtime.cuh"
 
 namespace msb {
@@ -25,6 +28,91 @@ struct A2MParams {
   const int2* ranges;   // per mel row [first, last+1) non-zero bin, or null (dense basis)
   int N, n_fft, log2n, hop, n_mels, bins, F, groups;
 };
+
+// Shared tail of both kernels: untangle the two real spectra packed in each complex transform
+// (transform j: re plane zr + j * zstride, im plane zi + j * zstride, natural order), take
+// magnitudes, project onto the mel basis, log10(clamp).
+__device__ __forceinline__ void a2m_tail(const A2MParams& p, const float* zr, const float* zi,
+                                         const int zstride, float* mag, float* tile, const int n,
+                                         const int b, const int f0) {
+  const int tid = threadIdx.x;
+  const int bins = p.bins;
+  const int magld = bins + 3;
+  // untangle the two real spectra of each complex transform, take magnitudes
+  for (int i = tid; i < 4 * bins; i += kA2MThreads) {
+    const int j = i / bins;
+    const int k = i - j * bins;
+    const int kn = (n - k) & (n - 1);
+    const float ar = zr[j * zstride + k], ai = zi[j * zstride + k];
+    const float br = zr[j * zstride + kn], bi = zi[j * zstride + kn];
+    const float xar = 0.5f * (ar + br), xai = 0.5f * (ai - bi);
+    const float xbr = 0.5f * (ai + bi), xbi = -0.5f * (ar - br);
+    mag[(2 * j) * magld + k] = sqrtf(xar * xar + xai * xai);
+    mag[(2 * j + 1) * magld + k] = sqrtf(xbr * xbr + xbi * xbi);
+  }
+  __syncthreads();
+  // mel projection: thread (m, gh) accumulates frames gh*4 .. gh*4+3 of mel row m
+  const int ml = tid & 127;
+  const int gh = tid >> 7;
+  if (p.ranges != nullptr) {
+    // banded basis (triangular mel filters): walk only the row's non-zero bins, in the same
+    // ascending order as the dense product -> bit-identical sums
+    for (int mb = 0; mb < p.n_mels; mb += 128) {
+      const int m = mb + ml;
+      if (m >= p.n_mels) continue;
+      const int2 r = __ldg(p.ranges + m);
+      const float* brow = p.basis + static_cast<size_t>(m) * bins;
+      const float* mg = mag + (gh * 4) * magld;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = r.x; k < r.y; ++k) {
+        const float w = __ldg(brow + k);
+        acc[0] = fmaf(w, mg[k], acc[0]);
+        acc[1] = fmaf(w, mg[magld + k], acc[1]);
+        acc[2] = fmaf(w, mg[2 * magld + k], acc[2]);
+        acc[3] = fmaf(w, mg[3 * magld + k], acc[3]);
+      }
+      float* o = p.out + (static_cast<size_t>(b) * p.n_mels + m) * p.F;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int f = f0 + gh * 4 + g;
+        if (f < p.F) o[f] = log10f(fmaxf(acc[g], 1e-5f));
+      }
+    }
+    return;
+  }
+  for (int mb = 0; mb < p.n_mels; mb += 128) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < bins; k0 += 32) {
+      // stage basis[mb .. mb+128)[k0 .. k0+32) : coalesced 128-byte row segments
+      for (int i = tid; i < 128 * 32; i += kA2MThreads) {
+        const int r = i >> 5, kk = i & 31;
+        const int m = mb + r, k = k0 + kk;
+        tile[r * 33 + kk] =
+            (m < p.n_mels && k < bins) ? __ldg(p.basis + static_cast<size_t>(m) * bins + k) : 0.f;
+      }
+      __syncthreads();
+      const int kmax = (bins - k0) < 32 ? (bins - k0) : 32;
+      const float* mg = mag + (gh * 4) * magld + k0;
+      for (int kk = 0; kk < kmax; ++kk) {
+        const float w = tile[ml * 33 + kk];
+        acc[0] = fmaf(w, mg[kk], acc[0]);
+        acc[1] = fmaf(w, mg[magld + kk], acc[1]);
+        acc[2] = fmaf(w, mg[2 * magld + kk], acc[2]);
+        acc[3] = fmaf(w, mg[3 * magld + kk], acc[3]);
+      }
+      __syncthreads();
+    }
+    const int m = mb + ml;
+    if (m < p.n_mels) {
+      float* o = p.out + (static_cast<size_t>(b) * p.n_mels + m) * p.F;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int f = f0 + gh * 4 + g;
+        if (f < p.F) o[f] = log10f(fmaxf(acc[g], 1e-5f));
+      }
+    }
+  }
+}
 
 // LOG2N > 0: compile-time FFT size (index arithmetic becomes shifts / masks); 0: runtime size
 template <int LOG2N>
@@ -154,80 +242,54 @@ audio2mel_kernel(const A2MParams p) {
       __syncthreads();
     }
   }
-  // untangle the two real spectra of each complex transform, take magnitudes
-  for (int i = tid; i < 4 * bins; i += kA2MThreads) {
-    const int j = i / bins;
-    const int k = i - j * bins;
-    const int kn = (n - k) & (n - 1);
-    const float ar = zr[j * n + k], ai = zi[j * n + k];
-    const float br = zr[j * n + kn], bi = zi[j * n + kn];
-    const float xar = 0.5f * (ar + br), xai = 0.5f * (ai - bi);
-    const float xbr = 0.5f * (ai + bi), xbi = -0.5f * (ar - br);
-    mag[(2 * j) * magld + k] = sqrtf(xar * xar + xai * xai);
-    mag[(2 * j + 1) * magld + k] = sqrtf(xbr * xbr + xbi * xbi);
+  a2m_tail(p, zr, zi, n, mag, tile, n, b, f0);
+}
+
+// n_fft = 1024, register-resident form (a2m_fft.cuh): 64 threads per complex transform, the
+// 16 samples of a thread come straight from global memory (coalesced 256-byte runs), two
+// exchanges through a conflict-free padded array, 5 CTA barriers in all.  Shared memory:
+// 8 planes of 1088 floats + the magnitudes = 51.3 KB -> four CTAs per SM.
+__global__ void __launch_bounds__(kA2MThreads, 4)
+audio2mel_r16_kernel(const A2MParams p) {
+  extern __shared__ float sm[];
+  float* zr = sm;                            // [4][kPlane] (re)  -- reused as basis tile
+  float* zi = sm + 4 * a2m::kPlane;          // [4][kPlane] (im)
+  float* mag = sm + 8 * a2m::kPlane;         // [8][bins + 3]
+  const int tid = threadIdx.x;
+  const int j = tid >> 6, t = tid & 63;
+  const int b = blockIdx.x / p.groups;
+  const int f0 = (blockIdx.x % p.groups) * kFramesPerCta;
+  const float* a = p.audio + static_cast<size_t>(b) * p.N;
+  float* sr = zr + j * a2m::kPlane;
+  float* si = zi + j * a2m::kPlane;
+  {
+    // frame 2j -> real part, frame 2j+1 -> imaginary part; right zero padding past the clip
+    float re[16], im[16];
+    const int fa = f0 + 2 * j;
+    const long long sa = static_cast<long long>(fa) * p.hop + t;
+    const long long sb = sa + p.hop;
+    const bool oka = fa < p.F, okb = fa + 1 < p.F;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const float w = __ldg(p.window + 64 * q + t);
+      const float va = (oka && sa + 64 * q < p.N) ? __ldg(a + sa + 64 * q) : 0.f;
+      const float vb = (okb && sb + 64 * q < p.N) ? __ldg(a + sb + 64 * q) : 0.f;
+      re[q] = va * w;
+      im[q] = vb * w;
+    }
+    a2m::pass_a(t, re, im, sr, si);
   }
   __syncthreads();
-  // mel projection: thread (m, gh) accumulates frames gh*4 .. gh*4+3 of mel row m
-  const int ml = tid & 127;
-  const int gh = tid >> 7;
-  if (p.ranges != nullptr) {
-    // banded basis (triangular mel filters): walk only the row's non-zero bins, in the same
-    // ascending order as the dense product -> bit-identical sums
-    for (int mb = 0; mb < p.n_mels; mb += 128) {
-      const int m = mb + ml;
-      if (m >= p.n_mels) continue;
-      const int2 r = __ldg(p.ranges + m);
-      const float* brow = p.basis + static_cast<size_t>(m) * bins;
-      const float* mg = mag + (gh * 4) * magld;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int k = r.x; k < r.y; ++k) {
-        const float w = __ldg(brow + k);
-        acc[0] = fmaf(w, mg[k], acc[0]);
-        acc[1] = fmaf(w, mg[magld + k], acc[1]);
-        acc[2] = fmaf(w, mg[2 * magld + k], acc[2]);
-        acc[3] = fmaf(w, mg[3 * magld + k], acc[3]);
-      }
-      float* o = p.out + (static_cast<size_t>(b) * p.n_mels + m) * p.F;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int f = f0 + gh * 4 + g;
-        if (f < p.F) o[f] = log10f(fmaxf(acc[g], 1e-5f));
-      }
-    }
-    return;
+  a2m::pass_b(t, sr, si);
+  __syncthreads();
+  {
+    float re[16], im[16];
+    a2m::pass_c_read(t, sr, si, re, im);
+    __syncthreads();
+    a2m::pass_c_write(t, re, im, sr, si);
   }
-  for (int mb = 0; mb < p.n_mels; mb += 128) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < bins; k0 += 32) {
-      // stage basis[mb .. mb+128)[k0 .. k0+32) : coalesced 128-byte row segments
-      for (int i = tid; i < 128 * 32; i += kA2MThreads) {
-        const int r = i >> 5, kk = i & 31;
-        const int m = mb + r, k = k0 + kk;
-        tile[r * 33 + kk] =
-            (m < p.n_mels && k < bins) ? __ldg(p.basis + static_cast<size_t>(m) * bins + k) : 0.f;
-      }
-      __syncthreads();
-      const int kmax = (bins - k0) < 32 ? (bins - k0) : 32;
-      const float* mg = mag + (gh * 4) * magld + k0;
-      for (int kk = 0; kk < kmax; ++kk) {
-        const float w = tile[ml * 33 + kk];
-        acc[0] = fmaf(w, mg[kk], acc[0]);
-        acc[1] = fmaf(w, mg[magld + kk], acc[1]);
-        acc[2] = fmaf(w, mg[2 * magld + kk], acc[2]);
-        acc[3] = fmaf(w, mg[3 * magld + kk], acc[3]);
-      }
-      __syncthreads();
-    }
-    const int m = mb + ml;
-    if (m < p.n_mels) {
-      float* o = p.out + (static_cast<size_t>(b) * p.n_mels + m) * p.F;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int f = f0 + gh * 4 + g;
-        if (f < p.F) o[f] = log10f(fmaxf(acc[g], 1e-5f));
-      }
-    }
-  }
+  __syncthreads();
+  a2m_tail(p, zr, zi, a2m::kPlane, mag, zr, a2m::kN, b, f0);
 }
 
 }  // namespace msb
@@ -260,8 +322,29 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
   p.ranges = reinterpret_cast<const int2*>(row_ranges);
   p.N = samples; p.n_fft = n_fft; p.log2n = log2n; p.hop = hop; p.n_mels = n_mels;
   p.bins = n_fft / 2 + 1; p.F = F; p.groups = (F + kFramesPerCta - 1) / kFramesPerCta;
-  const size_t fft_floats = 8 * static_cast<size_t>(n_fft);
+  const long long blocks = static_cast<long long>(batch) * p.groups;
+  if (blocks > 0x7fffffffLL) return MS_ERR_INVALID;
   const size_t tile_floats = 128 * 33;
+  // MSB_A2M_RADIX4=1: the shared-memory radix-4 form of n_fft = 1024 (kept for A/B timing;
+  // read per call so one process can time both)
+  const char* env_r4 = getenv("MSB_A2M_RADIX4");
+  const bool radix4 = env_r4 != nullptr && env_r4[0] == '1';
+  if (n_fft == 1024 && !radix4) {
+    const size_t smem = sizeof(float) * (8 * a2m::kPlane + kFramesPerCta * (p.bins + 3));
+    static_assert(8 * a2m::kPlane >= 128 * 33, "basis tile must fit in the FFT planes");
+    static thread_local bool attr_r16 = false;
+    if (!attr_r16) {
+      cudaError_t e = cudaFuncSetAttribute(audio2mel_r16_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(audio2mel_r16_kernel)");
+      attr_r16 = true;
+    }
+    audio2mel_r16_kernel<<<static_cast<unsigned>(blocks), kA2MThreads, smem,
+                           static_cast<cudaStream_t>(stream)>>>(p);
+    return after_launch("audio2mel_r16_kernel");
+  }
+  const size_t fft_floats = 8 * static_cast<size_t>(n_fft);
   const size_t tw_floats = n_fft == 1024 ? 2 * (3 * n_fft / 4) : 2 * n_fft;
   const size_t smem = sizeof(float) * (tw_floats + kFramesPerCta * (p.bins + 3) +
                                        (fft_floats > tile_floats ? fft_floats : tile_floats));
@@ -276,8 +359,6 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(audio2mel_kernel)");
     attr_set = smem;
   }
-  const long long blocks = static_cast<long long>(batch) * p.groups;
-  if (blocks > 0x7fffffffLL) return MS_ERR_INVALID;
   if (n_fft == 1024)
     audio2mel_kernel<10><<<static_cast<unsigned>(blocks), kA2MThreads, smem,
                            static_cast<cudaStream_t>(stream)>>>(p);

@@ -4,10 +4,17 @@
 //   size S keeps bins [S/4, S/2] -- the lowest keeps [0, S/2] -- and is inverse-transformed
 //   at length S; recompose zero-stuffs each band's spectrum to the full length and sums,
 //   including the reference's double-counted boundary bins).
-// HBM-bound, fp32.  Transforms are power-of-two Stockham autosort FFTs, out of place between
-// two workspace buffers: radix-4 passes (+ one radix-2 pass when log2 n is odd), twiddles
-// from sincospif (no recurrences).  Because irFFT is linear, recompose sums the bands'
-// spectra first and runs ONE inverse transform.
+// HBM/L2-bound, fp32.  Transforms are power-of-two Stockham autosort FFTs, out of place between
+// two workspace buffers.  Default form (fft_passes.cuh): register-resident radix-16 passes
+// (+ one radix-2 / radix-4 pass for the odd bits of log2 n), real-input load, band cut-out,
+// Hermitian expansion and real-part store folded into the first / last pass of a transform:
+// n = 65536 is 4 passes and no boundary kernels instead of 8 radix-4 passes + 3 copies.
+// MSB_FFT_LEGACY=1 selects the first version (radix-4 passes, separate boundary kernels).
+// Because irFFT is linear, recompose sums the bands' spectra first and runs ONE inverse
+// transform.
+#include <cstdlib>
+
+#include "fft_passes.cuh"
 #include "runtime.cuh"
 
 namespace msb {
@@ -157,6 +164,83 @@ __global__ void hermitian_expand_kernel(const float2* __restrict__ half, float2*
   z[gid] = v;
 }
 
+// ---- register-resident passes (fft_passes.cuh) ------------------------------------------
+template <int R, int LD, int ST>
+__global__ void __launch_bounds__(256) fft_pass_kernel(const fftb::PassArgs a) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
+  if (gid < a.total) fftb::pass_thread<R, LD, ST>(a, gid);
+}
+
+// First radix-16 pass of a transform (p = 1): a thread's 16 outputs are consecutive and a
+// warp's 512 outputs are ONE contiguous 4 KB run, so they are exchanged through shared memory
+// and stored as full 256-byte rows per instruction (direct stores would hit 32 different
+// 128-byte lines per instruction, a quarter of a sector each).  Requires (n / 16) % 32 == 0
+// and complex output.  Row pitch 17 float2: both the per-thread writes and the transposed
+// reads are bank-conflict free.
+template <int LD>
+__global__ void __launch_bounds__(256) fft_pass16_first_kernel(const fftb::PassArgs a) {
+  __shared__ float2 stage[8][32][17];
+  const size_t gid = blockIdx.x * static_cast<size_t>(256) + threadIdx.x;
+  if (gid >= a.total) return;      // total % 32 == 0: whole warps leave together
+  float re[16], im[16];
+  size_t row;
+  int j;
+  fftb::pass_compute<16, LD>(a, gid, re, im, row, j);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int m = 0; m < 16; ++m) stage[warp][lane][m] = make_float2(re[m], im[m]);
+  __syncwarp();
+  float2* y = static_cast<float2*>(a.y) + row * a.n + (j - 16 * lane);
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int idx = r * 32 + lane;
+    y[idx] = stage[warp][idx >> 4][idx & 15];
+  }
+}
+
+static bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr || e[0] == 0) return dflt;
+  return e[0] != '0';
+}
+
+// the knobs are read per call (not cached) so one process can time both settings
+struct PassLauncher {
+  cudaStream_t st;
+  bool staged;
+  explicit PassLauncher(cudaStream_t s) : st(s), staged(env_flag("MSB_FFT_STAGED", true)) {}
+  int operator()(int radix, int load, int store, const fftb::PassArgs& a) const {
+    const unsigned grid = static_cast<unsigned>((a.total + 255) / 256);
+    if (staged && radix == 16 && a.p == 1 && store == fftb::kStoreComplex &&
+        (a.n / 16) % 32 == 0) {
+      switch (load) {
+        case fftb::kLoadComplex:
+          fft_pass16_first_kernel<fftb::kLoadComplex><<<grid, 256, 0, st>>>(a); break;
+        case fftb::kLoadReal:
+          fft_pass16_first_kernel<fftb::kLoadReal><<<grid, 256, 0, st>>>(a); break;
+        case fftb::kLoadBand:
+          fft_pass16_first_kernel<fftb::kLoadBand><<<grid, 256, 0, st>>>(a); break;
+        default:
+          fft_pass16_first_kernel<fftb::kLoadHalf><<<grid, 256, 0, st>>>(a); break;
+      }
+      return after_launch("fft_pass16_first_kernel");
+    }
+    cudaStream_t s = st;
+    return fftb::dispatch(radix, load, store, [&](auto r, auto ld, auto sto) -> int {
+      fft_pass_kernel<decltype(r)::value, decltype(ld)::value, decltype(sto)::value>
+          <<<grid, 256, 0, s>>>(a);
+      return after_launch("fft_pass_kernel");
+    });
+  }
+};
+
+__global__ void accumulate_band2_kernel(const float2* __restrict__ zs, float2* __restrict__ acc,
+                                        int S, int D, int lo, float scale, int first,
+                                        size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid < total) fftb::accumulate_one(zs, acc, S, D, lo, scale, first, gid);
+}
+
 inline unsigned nblk(size_t total) { return static_cast<unsigned>((total + 255) / 256); }
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -187,6 +271,10 @@ ms_status ms_fft_frequency_decompose(const float* x, int batch, int n, int min_s
   float2* coef = static_cast<float2*>(workspace);
   float2* w0 = coef + bn;
   float2* w1 = w0 + bn;
+  const bool legacy = env_flag("MSB_FFT_LEGACY", false);
+  if (!legacy)
+    return static_cast<ms_status>(
+        fftb::decompose(x, batch, n, min_size, bands_out, coef, w0, w1, PassLauncher(st)));
   real_to_complex_kernel<<<nblk(bn), 256, 0, st>>>(x, w0, bn);
   ms_status s = after_launch("real_to_complex_kernel");
   if (s != MS_OK) return s;
@@ -233,6 +321,16 @@ ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes
   float2* w1 = w0 + bd;
   const size_t bh = static_cast<size_t>(batch) * (D / 2 + 1);
   ms_status s = MS_OK;
+  const bool legacy = env_flag("MSB_FFT_LEGACY", false);
+  if (!legacy) {
+    auto accum = [&](const float2* zs, float2* ac, int S, int Dd, int lo, float scale,
+                     int first) -> int {
+      accumulate_band2_kernel<<<nblk(bh), 256, 0, st>>>(zs, ac, S, Dd, lo, scale, first, bh);
+      return after_launch("accumulate_band2_kernel");
+    };
+    return static_cast<ms_status>(fftb::recompose(bands, sizes, nbands, batch, D, out, acc, w0,
+                                                  w1, PassLauncher(st), accum));
+  }
   for (int i = 0; i < nbands; ++i) {
     const int S = sizes[i];
     const size_t bs = static_cast<size_t>(batch) * S;

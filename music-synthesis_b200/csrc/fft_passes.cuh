@@ -1,0 +1,273 @@
+// Stockham autosort FFT passes of radix 2 / 4 / 16 for the octave-band split / merge
+// (fft_bands.cu), with the boundary work folded into the first and last pass of a transform:
+//   first pass loads   complex data | real data (imag = 0) | a band's Hermitian spectrum cut
+//                      out of the full-length coefficients | the full Hermitian spectrum
+//                      expanded from its stored half
+//   last pass stores   complex data | the real part only
+// Every pass is forward (exp(-i...)) arithmetic: an inverse transform is conj . forward . conj,
+// the input conjugation sits in the two spectrum loaders and the output conjugation is moot
+// because only the real part is kept.
+//
+// One pass, radix R, p = product of the radices already applied, t = n / R, thread i < t of a
+// row:  k = i mod p,  v_q = x[i + q t] W_(R p)^(q k),  y[(i - k) R + k + m p] = sum_q v_q W_R^(q m).
+//
+// The per-thread body and the pass plan are __host__ __device__ / host templates so that
+// tests/native/fft_bands_host.cu runs the same code on the CPU.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <type_traits>
+
+#include "a2m_fft.cuh"
+
+namespace msb {
+namespace fftb {
+
+enum Load { kLoadComplex = 0, kLoadReal = 1, kLoadBand = 2, kLoadHalf = 3 };
+enum Store { kStoreComplex = 0, kStoreReal = 1 };
+
+struct PassArgs {
+  const void* x;   // float2 rows of n | float rows of n | float2 rows of src_n (band / half)
+  void* y;         // float2 rows of n | float rows of n
+  int n;           // transform length
+  int p;           // product of the radices of the earlier passes
+  size_t total;    // batch * n / R threads
+  int src_n;       // kLoadBand: row length of the coefficient array; kLoadHalf: n / 2 + 1
+  int lo;          // kLoadBand: first kept bin
+  float scale;     // kLoadBand: applied to the kept bins
+};
+
+template <int LD>
+A2M_HD void load_one(const PassArgs& a, size_t row, int idx, float& re, float& im) {
+  if (LD == kLoadComplex) {
+    const float2 v = static_cast<const float2*>(a.x)[row * a.n + idx];
+    re = v.x;
+    im = v.y;
+  } else if (LD == kLoadReal) {
+    re = static_cast<const float*>(a.x)[row * a.n + idx];
+    im = 0.f;
+  } else if (LD == kLoadBand) {
+    // Z[k] = scale * C[k] for lo <= k <= n/2 (imaginary part of k = 0 and k = n/2 dropped, as a
+    // c2r transform ignores it), Z[n-k] = conj(Z[k]), 0 elsewhere; conjugated for the inverse
+    const int half = a.n >> 1;
+    const int kk = idx <= half ? idx : a.n - idx;
+    re = 0.f;
+    im = 0.f;
+    if (kk >= a.lo) {
+      const float2 v = static_cast<const float2*>(a.x)[row * a.src_n + kk];
+      re = v.x * a.scale;
+      im = (kk == 0 || kk == half) ? 0.f : (idx <= half ? -a.scale : a.scale) * v.y;
+    }
+  } else {
+    // full Hermitian spectrum from its n/2+1 half; conjugated for the inverse
+    const int half = a.n >> 1;
+    const int kk = idx <= half ? idx : a.n - idx;
+    const float2 v = static_cast<const float2*>(a.x)[row * a.src_n + kk];
+    re = v.x;
+    im = (kk == 0 || kk == half) ? 0.f : (idx <= half ? -v.y : v.y);
+  }
+}
+
+// loads, twiddles and transforms the R inputs of butterfly `gid`; returns the output base
+// index j (outputs go to row * n + j + m * p)
+template <int R, int LD>
+A2M_HD void pass_compute(const PassArgs& a, size_t gid, float (&re)[R], float (&im)[R],
+                         size_t& row, int& j) {
+  const int t = a.n / R;
+  const int i = static_cast<int>(gid % t);
+  row = gid / t;
+  const int k = i & (a.p - 1);
+  j = (i - k) * R + k;
+#pragma unroll
+  for (int q = 0; q < R; ++q) load_one<LD>(a, row, i + q * t, re[q], im[q]);
+  float s1 = 0.f, c1 = 1.f;
+  if (a.p > 1)
+    sincospif(-2.f * static_cast<float>(k) / (static_cast<float>(R) * static_cast<float>(a.p)),
+              &s1, &c1);
+  if constexpr (R == 16) {
+    if (a.p > 1) a2m::twiddle16(re, im, c1, s1);
+    a2m::dft16(re, im);
+  } else if constexpr (R == 4) {
+    if (a.p > 1) {
+      const float c2 = c1 * c1 - s1 * s1, s2 = 2.f * c1 * s1;
+      const float c3 = c2 * c1 - s2 * s1, s3 = c2 * s1 + s2 * c1;
+      a2m::cmul(re[1], im[1], c1, s1);
+      a2m::cmul(re[2], im[2], c2, s2);
+      a2m::cmul(re[3], im[3], c3, s3);
+    }
+    a2m::dft4(re[0], im[0], re[1], im[1], re[2], im[2], re[3], im[3]);
+  } else {
+    if (a.p > 1) a2m::cmul(re[1], im[1], c1, s1);
+    const float ur = re[0], ui = im[0];
+    re[0] = ur + re[1]; im[0] = ui + im[1];
+    re[1] = ur - re[1]; im[1] = ui - im[1];
+  }
+}
+
+template <int R, int LD, int ST>
+A2M_HD void pass_thread(const PassArgs& a, size_t gid) {
+  float re[R], im[R];
+  size_t row;
+  int j;
+  pass_compute<R, LD>(a, gid, re, im, row, j);
+  const size_t o = row * a.n + j;
+#pragma unroll
+  for (int m = 0; m < R; ++m) {
+    if (ST == kStoreComplex)
+      static_cast<float2*>(a.y)[o + static_cast<size_t>(m) * a.p] = make_float2(re[m], im[m]);
+    else
+      static_cast<float*>(a.y)[o + static_cast<size_t>(m) * a.p] = re[m];
+  }
+}
+
+// run-time (radix, load, store) -> compile-time constants: f(IC<R>, IC<LD>, IC<ST>) -> int
+template <int V>
+using IC = std::integral_constant<int, V>;
+
+template <class F>
+int dispatch(int radix, int load, int store, F&& f) {
+  auto with_store = [&](auto r, auto ld) -> int {
+    if (store == kStoreComplex) return f(r, ld, IC<kStoreComplex>{});
+    return f(r, ld, IC<kStoreReal>{});
+  };
+  auto with_load = [&](auto r) -> int {
+    switch (load) {
+      case kLoadComplex: return with_store(r, IC<kLoadComplex>{});
+      case kLoadReal: return with_store(r, IC<kLoadReal>{});
+      case kLoadBand: return with_store(r, IC<kLoadBand>{});
+      default: return with_store(r, IC<kLoadHalf>{});
+    }
+  };
+  switch (radix) {
+    case 2: return with_load(IC<2>{});
+    case 4: return with_load(IC<4>{});
+    case 16: return with_load(IC<16>{});
+    default: return -1;
+  }
+}
+
+// ---- the plan of one batched transform --------------------------------------------------
+struct Xform {
+  int n, batch;
+  int load;            // Load of the first pass
+  const void* src;
+  int src_n, lo;
+  float scale;
+  int store;           // Store of the last pass
+  void* dst;
+  float2* w0;          // ping-pong scratch for the passes in between (batch * n each)
+  float2* w1;
+};
+
+inline int plan_radices(int n, int* radix) {   // n = power of two >= 2; returns the pass count
+  int log2n = 0;
+  while ((1 << log2n) < n) ++log2n;
+  int c = 0;
+  if (log2n & 1) radix[c++] = 2;
+  if (log2n & 2) radix[c++] = 4;
+  for (int s = log2n >> 2; s > 0; --s) radix[c++] = 16;
+  return c;
+}
+
+// launch(radix, load, store, args) -> 0 on success
+template <class Launch>
+int run_xform(const Xform& x, Launch&& launch) {
+  int radix[16];
+  const int count = plan_radices(x.n, radix);
+  const void* src = x.src;
+  int p = 1;
+  for (int i = 0; i < count; ++i) {
+    const bool last = i == count - 1;
+    PassArgs a;
+    a.x = src;
+    a.y = last ? x.dst : static_cast<void*>((i & 1) ? x.w1 : x.w0);
+    a.n = x.n;
+    a.p = p;
+    a.total = static_cast<size_t>(x.batch) * (x.n / radix[i]);
+    a.src_n = x.src_n;
+    a.lo = x.lo;
+    a.scale = x.scale;
+    const int rc = launch(radix[i], i == 0 ? x.load : static_cast<int>(kLoadComplex),
+                          last ? x.store : static_cast<int>(kStoreComplex), a);
+    if (rc != 0) return rc;
+    src = a.y;
+    p *= radix[i];
+  }
+  return 0;
+}
+
+// ---- the two public operations as sequences of transforms ---------------------------------
+// decompose (audio/transform.py:50-82): forward transform of the whole clip into `coef`, then
+// per band of size S an inverse transform of bins [S/4, S/2] (lowest band: [0, S/2]).
+// ortho scaling of both directions (1/sqrt(n), 1/sqrt(S)) is applied where the band is cut out.
+template <class Launch>
+int decompose(const float* x, int batch, int n, int min_size, float* const* bands_out,
+              float2* coef, float2* w0, float2* w1, Launch&& launch) {
+  Xform f;
+  f.n = n; f.batch = batch; f.load = kLoadReal; f.src = x; f.src_n = n; f.lo = 0; f.scale = 1.f;
+  f.store = kStoreComplex; f.dst = coef; f.w0 = w0; f.w1 = w1;
+  int rc = run_xform(f, launch);
+  if (rc != 0) return rc;
+  int bi = 0;
+  for (int S = min_size; S <= n; S <<= 1, ++bi) {
+    Xform b;
+    b.n = S; b.batch = batch; b.load = kLoadBand; b.src = coef; b.src_n = n;
+    b.lo = (S > min_size) ? S / 4 : 0;
+    b.scale = 1.0f / (sqrtf(static_cast<float>(n)) * sqrtf(static_cast<float>(S)));
+    b.store = kStoreReal; b.dst = bands_out[bi]; b.w0 = w0; b.w1 = w1;
+    rc = run_xform(b, launch);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// recompose (audio/transform.py:85-115): forward transform of each band, its kept bins scaled
+// and summed into the half spectrum `acc` (batch rows of D/2+1), one inverse transform.
+// accum(spectrum, acc, S, D, lo, scale, first) -> 0 on success
+template <class Launch, class Accum>
+int recompose(const float* const* bands, const int* sizes, int nbands, int batch, int D,
+              float* out, float2* acc, float2* w0, float2* w1, Launch&& launch, Accum&& accum) {
+  int smin = sizes[0];
+  for (int i = 1; i < nbands; ++i) smin = sizes[i] < smin ? sizes[i] : smin;
+  for (int i = 0; i < nbands; ++i) {
+    const int S = sizes[i];
+    int radix[16];
+    const int count = plan_radices(S, radix);
+    Xform f;
+    f.n = S; f.batch = batch; f.load = kLoadReal; f.src = bands[i]; f.src_n = S; f.lo = 0;
+    f.scale = 1.f; f.store = kStoreComplex;
+    f.dst = ((count - 1) & 1) ? w1 : w0;      // continues the ping-pong: never the last source
+    f.w0 = w0; f.w1 = w1;
+    int rc = run_xform(f, launch);
+    if (rc != 0) return rc;
+    // fft_resample: the lowest band keeps bins [0, S/2], the others [S/4, S/2]
+    // (n_coeffs // 2 with n_coeffs = S/2 + 1), audio/transform.py:93-96
+    const int lo = (S == smin) ? 0 : (S / 2 + 1) / 2;
+    const float scale = 1.0f / (sqrtf(static_cast<float>(S)) * sqrtf(static_cast<float>(D)));
+    rc = accum(static_cast<const float2*>(f.dst), acc, S, D, lo, scale, i == 0 ? 1 : 0);
+    if (rc != 0) return rc;
+  }
+  Xform inv;
+  inv.n = D; inv.batch = batch; inv.load = kLoadHalf; inv.src = acc; inv.src_n = D / 2 + 1;
+  inv.lo = 0; inv.scale = 1.f; inv.store = kStoreReal; inv.dst = out; inv.w0 = w0; inv.w1 = w1;
+  return run_xform(inv, launch);
+}
+
+// one element of the band accumulation (gid over batch * (D/2+1))
+A2M_HD void accumulate_one(const float2* zs, float2* acc, int S, int D, int lo, float scale,
+                           int first, size_t gid) {
+  const int k = static_cast<int>(gid % (D / 2 + 1));
+  const size_t b = gid / (D / 2 + 1);
+  float2 v = first ? make_float2(0.f, 0.f) : acc[gid];
+  if (k >= lo && k <= S / 2) {
+    const float2 c = zs[b * S + k];
+    v.x += c.x * scale;
+    v.y += c.y * scale;
+  }
+  acc[gid] = v;
+}
+
+}  // namespace fftb
+}  // namespace msb

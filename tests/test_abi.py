@@ -144,3 +144,60 @@ def test_loss_scaler_policy(monkeypatch):
     off = LossScaler(torch.device("cpu"))
     off.update(True)
     assert not off.enabled and off.scale == 1.0       # bf16 backward: no scaling at all
+
+
+def test_audio2mel_fft_passes_on_host(tmp_path):
+    """csrc/a2m_fft.cuh (the register-resident 1024-point FFT of the Audio2Mel kernel) is
+    __host__ __device__: tests/native/a2m_fft_host.cu runs the per-thread pass bodies on the CPU
+    against a double-precision DFT (rel-L2 < 2e-6 or a non-zero exit status)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "a2m_fft_host")
+    subprocess.run([nvcc, "-O2", "-Wno-deprecated-gpu-targets",
+                    "-I", os.path.join(ROOT, "music-synthesis_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "native", "a2m_fft_host.cu")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert float(r.stdout.split()[1]) < 2e-6
+
+
+@pytest.mark.parametrize("batch,n,min_size", [(2, 65536, 4096), (2, 8192, 256), (3, 2048, 16),
+                                              (1, 32768, 1024), (1, 16, 16), (1, 8, 4)])
+def test_fft_band_passes_on_host(tmp_path, batch, n, min_size):
+    """csrc/fft_passes.cuh (radix-2/4/16 Stockham passes with fused boundary loads / stores, the
+    pass plan and the decompose / recompose sequences of fft_bands.cu) is host-callable:
+    tests/native/fft_bands_host.cu runs it on the CPU; compared with the oracle's restatement of
+    featuresynth/audio/transform.py:50-115."""
+    import shutil
+    import subprocess
+    import torch
+    from oracle import restate
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = os.path.join(ROOT, "tests", "native", "_fft_bands_host")
+    src = os.path.join(ROOT, "tests", "native", "fft_bands_host.cu")
+    hdr = os.path.join(ROOT, "music-synthesis_b200", "csrc", "fft_passes.cuh")
+    if (not os.path.exists(exe) or
+            os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets",
+                        "-I", os.path.dirname(hdr), "-o", exe, src], check=True)
+    x = (np.random.RandomState(n + batch).randn(batch, n) * 0.1).astype(np.float32)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    x.tofile(fin)
+    r = subprocess.run([exe, fin, fout, str(batch), str(n), str(min_size)])
+    assert r.returncode == 0
+    out = np.fromfile(fout, dtype=np.float32)
+    ref = restate.fft_frequency_decompose(torch.from_numpy(x)[:, None, :], min_size)
+    o = 0
+    for s in sorted(ref):
+        got = out[o:o + batch * s].reshape(batch, s)
+        o += batch * s
+        want = ref[s][:, 0].numpy()
+        assert np.linalg.norm(got - want) <= 3e-6 * np.linalg.norm(want), s
+    want = restate.fft_frequency_recompose(ref, n)[:, 0].numpy()
+    got = out[o:].reshape(batch, n)
+    assert np.linalg.norm(got - want) <= 3e-6 * np.linalg.norm(want)

@@ -40,3 +40,45 @@ def test_bands_match_oracle(B, N, min_size):
     gxy = fft_frequency_decompose((x + 2 * y).cuda(), min_size)
     for k in got:
         assert rel_l2(gxy[k], got[k] + 2 * gy[k]) < 5e-6
+
+
+def test_multiscale_representation_matches_golden(golden):
+    """`MultiScale.from_audio / to_audio` (audio/representation.py:82-103)
+    on the GPU.  The reference's MultiScale run on this input reproduces the fft_bands_n8192
+    fixture bit for bit (tests/test_oracle_golden.py pins that in the build container)."""
+    from music_synthesis_b200.audio.representation import MultiScale, RawAudio
+    g = golden("fft_bands_n8192")
+    x = (synth.randn(51, 2, 1, 8192) * 0.1).numpy()
+    ms = MultiScale.from_audio(x, 22050)
+    assert sorted(ms.data) == [512, 1024, 2048, 4096, 8192]
+    for k, v in ms.data.items():
+        assert v.shape == (2, 1, k) and v.dtype.name == "float32"
+        assert rel_l2(torch.from_numpy(v), g[f"band_{k}"]) < 5e-6
+    audio = ms.to_audio()
+    assert audio.shape == (2, 8192)
+    assert rel_l2(torch.from_numpy(audio), g["recomposed"].reshape(2, 8192)) < 5e-6
+    dev = MultiScale.from_audio(x, 22050, device_bands=True)
+    assert all(v.is_cuda for v in dev.data.values())
+    assert torch.equal(dev.data[512].cpu(), torch.from_numpy(ms.data[512]))
+    assert RawAudio.from_audio(x, 22050).to_audio().shape == (2, 8192)
+
+
+@pytest.mark.parametrize("knob", ["MSB_FFT_STAGED=0", "MSB_FFT_LEGACY=1"])
+def test_pass_variants_agree(monkeypatch, knob):
+    """The library reads its knobs per call: the first radix-16 pass with direct stores
+    (MSB_FFT_STAGED=0) is bit-identical to the shared-memory staged one; the first-version
+    radix-4 path (MSB_FFT_LEGACY=1) agrees to rounding."""
+    from music_synthesis_b200.audio.transform import fft_frequency_decompose, fft_frequency_recompose
+    x = (synth.randn(54, 3, 1, 65536) * 0.1).cuda()
+    a = fft_frequency_decompose(x, 4096)
+    ra = fft_frequency_recompose(a, 65536)
+    name, value = knob.split("=")
+    monkeypatch.setenv(name, value)
+    b = fft_frequency_decompose(x, 4096)
+    rb = fft_frequency_recompose(b, 65536)
+    for k in a:
+        if name == "MSB_FFT_STAGED":
+            assert torch.equal(a[k], b[k])
+        else:
+            assert rel_l2(a[k], b[k]) < 3e-6
+    assert rel_l2(ra, rb) < 3e-6

@@ -207,3 +207,24 @@ def test_audio2mel_banded_projection_is_bit_identical_to_dense():
     a2m.mel_basis[3, 500] = 0.01
     a2m.mel_basis[3, 2] = 0.02
     assert torch.equal(a2m(a), ops.audio2mel(a, a2m.window, a2m.mel_basis, 1024, 256, None))
+
+
+def test_audio2mel_fft_forms_agree(monkeypatch):
+    """n_fft = 1024 runs the register-resident 16x16x4 FFT (csrc/a2m_fft.cuh) by default;
+    MSB_A2M_RADIX4=1 (read per call) selects the shared-memory radix-4 form.  Both against the
+    oracle, and against each other, on ragged shapes (last frame group partial, clip shorter
+    than the padded frames)."""
+    from music_synthesis_b200.feature.feature import Audio2Mel
+    a2m = Audio2Mel(1024, 256, 1024, 22050, 128).cuda()
+    for seed, B, N in ((21, 3, 16384), (22, 2, 5000), (23, 1, 700)):
+        a = synth.uniform_audio(seed, B, N)
+        ref = restate.audio2mel(a, a2m.mel_basis.cpu(), a2m.window.cpu())
+        monkeypatch.delenv("MSB_A2M_RADIX4", raising=False)
+        new = a2m(a.cuda())
+        monkeypatch.setenv("MSB_A2M_RADIX4", "1")
+        old = a2m(a.cuda())
+        monkeypatch.delenv("MSB_A2M_RADIX4", raising=False)
+        assert new.shape == ref.shape
+        assert (new.cpu() - ref).abs().max().item() < 1e-4
+        assert (old.cpu() - ref).abs().max().item() < 1e-4
+        assert (new - old).abs().max().item() < 1e-4

@@ -295,3 +295,24 @@ def test_realmelgan_losses_match_reference(golden):
     gen = sum(restate.hinge_generator_loss(j) for j in j2) + 10 * feat
     assert abs(float(feat) - float(g["feature"])) < 1e-6 * max(1.0, abs(float(g["feature"])))
     assert abs(float(gen) - float(g["gen"])) < 1e-5 * max(1.0, abs(float(g["gen"])))
+
+
+def test_reference_multiscale_representation_is_the_fft_bands_fixture(golden):
+    """Build container only: the reference's `MultiScale.from_audio / to_audio`
+    (audio/representation.py:82-103) reproduce the fft_bands_n8192 fixture exactly, so that
+    fixture also pins the GPU `MultiScale` (tests/test_gpu_fft_bands.py)."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("/root/reference not present on this box")
+    ref_harness.load()
+    import os
+    cwd = os.getcwd()
+    from featuresynth.audio.representation import MultiScale
+    os.chdir(cwd)
+    g = golden("fft_bands_n8192")
+    x = (synth.randn(51, 2, 1, 8192) * 0.1).numpy()
+    ms = MultiScale.from_audio(x, 22050)
+    assert sorted(ms.data) == [512, 1024, 2048, 4096, 8192]
+    for k, v in ms.data.items():
+        assert np.array_equal(v, g[f"band_{k}"])
+    assert np.array_equal(ms.to_audio(), g["recomposed"].reshape(2, 8192))

@@ -1,0 +1,66 @@
+"""Timings of the HBM-bound side rows (a1 Audio2Mel, a8 FFT band split / merge): CUDA events over
+warm back-to-back launches, one JSON line per row.  Run with the knobs the library reads per call (MSB_A2M_RADIX4, MSB_FFT_LEGACY, MSB_FFT_STAGED) toggled in
+this process for the A/B numbers of profiles/."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from music_synthesis_b200.feature.feature import Audio2Mel
+from music_synthesis_b200.audio.transform import fft_frequency_decompose, fft_frequency_recompose
+from oracle import synth
+
+torch.set_grad_enabled(False)
+try:
+    PEAK_HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
+    PEAK_HBM = float(PEAK_HBM.get("hbm_gbps", PEAK_HBM.get("hbm_gbs", 6536.7))) * 1e9
+except Exception:
+    PEAK_HBM = 6536.7e9
+KNOBS = ("MSB_A2M_RADIX4", "MSB_FFT_LEGACY", "MSB_FFT_STAGED")
+
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / n
+
+
+
+
+def run(knobs):
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update(knobs)
+    a2m = Audio2Mel(1024, 256, 1024, 22050, 128).cuda()
+    for B in (64, 4096):
+        a = synth.uniform_audio(3, min(B, 64), 16384).repeat(B // min(B, 64), 1, 1).cuda()
+        t = timeit(lambda: a2m(a))
+        nbytes = 4 * B * 16384 + 4 * B * 128 * 62
+        print(json.dumps({"row": "a1 Audio2Mel", "workload": "B=%d x 16384 samples" % B, "us": round(t * 1e6, 2),
+                          "samples_per_s": B * 16384 / t, "bound": "hbm", "achieved_GBs": nbytes / t / 1e9,
+                          "frac": nbytes / t / PEAK_HBM, "knobs": knobs}))
+    for B in (64, 512):
+        x = (synth.randn(4, 8, 1, 65536) * 0.1).repeat(B // 8, 1, 1).cuda()
+        t = timeit(lambda: fft_frequency_decompose(x, 4096))
+        # algorithmic bytes: the clip in, the five bands (31/16 of the clip) out
+        nbytes = x.numel() * 4 * (1 + 31 / 16)
+        print(json.dumps({"row": "a8 fft_frequency_decompose", "workload": "B=%d x 65536, 5 bands" % B,
+                          "us": round(t * 1e6, 2), "bound": "hbm", "achieved_GBs": nbytes / t / 1e9,
+                          "frac": nbytes / t / PEAK_HBM, "knobs": knobs}))
+        bands = fft_frequency_decompose(x, 4096)
+        t = timeit(lambda: fft_frequency_recompose(bands, 65536))
+        print(json.dumps({"row": "a8 fft_frequency_recompose", "workload": "B=%d x 65536, 5 bands" % B,
+                          "us": round(t * 1e6, 2), "bound": "hbm", "achieved_GBs": nbytes / t / 1e9,
+                          "frac": nbytes / t / PEAK_HBM, "knobs": knobs}))
+        del bands, x
+
+
+# the library reads the knobs per call: default (new kernels), then the A/B settings
+run({})
+run({"MSB_FFT_STAGED": "0"})
+run({"MSB_A2M_RADIX4": "1", "MSB_FFT_LEGACY": "1"})
