@@ -382,6 +382,17 @@ ms_status ms_adam_step_dev(float* param, const float* grad, float* exp_avg, floa
 ms_status ms_grad_unscale_check(float* grad, size_t n, const float* inv_scale_dev, int* flag_dev,
                                 void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Data feed: aligned random crops of the resident audio / log-mel stores into a training batch.
+ *   replaces the per-example slicing of batch_stream / random_slice,
+ *   featuresynth/data/datastore.py:8-80 (positions are drawn by the caller).
+ *   store: flat f32 buffer holding every chunk; plan: device int64 (B,3) rows
+ *   {origin, pitch, valid}: out[b,c,t] = store[origin + c*pitch + t] for t < valid, else 0
+ *   (the reference's zero padding of short chunks); out: (B, channels, len) f32.
+ * ------------------------------------------------------------------------- */
+ms_status ms_gather_crops(const float* store, const long long* plan, float* out, int batch,
+                          int channels, int len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,7 @@ SIGNATURES = {
     "ms_grad_unscale_check": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "ms_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
                              c_float, c_float, c_int, c_float, c_void_p]),
+    "ms_gather_crops": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

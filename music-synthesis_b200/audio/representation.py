@@ -50,7 +50,11 @@ class MultiScale(BaseAudioRepresentation):
     N_BANDS = 5
 
     @classmethod
-    def from_audio(cls, samples, samplerate, device="cuda", device_bands=False):
+    def from_audio(cls, samples, samplerate, device="cuda", device_bands=None):
+        """device_bands: keep the bands as CUDA tensors (default: when `samples` already is one,
+        i.e. inside the training loop) instead of the reference's numpy arrays."""
+        if device_bands is None:
+            device_bands = isinstance(samples, torch.Tensor) and samples.is_cuda
         with torch.no_grad():
             time = samples.shape[-1]
             start = int(np.log2(time))

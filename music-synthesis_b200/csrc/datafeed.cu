@@ -1,0 +1,50 @@
+// Training-batch assembly on the GPU: aligned random crops of the resident audio and log-mel
+// stores.  Replaces the per-example Python loop of batch_stream / random_slice
+// (featuresynth/data/datastore.py:8-80: slice [start, start+size) of the anchor feature, the
+// aligned slice [start*ratio, end*ratio) of every other feature, zero padding when the chunk is
+// shorter) -- the crop positions are still drawn on the host (same distribution as the
+// reference), only the data movement happens here: one launch per feature, coalesced reads of
+// the store, coalesced writes of the (B, channels, len) batch.  HBM-bound:
+// 2 * 4 * B * channels * len bytes.
+#include "runtime.cuh"
+
+namespace msb {
+
+struct CropArgs {
+  const float* store;
+  const long long* plan;   // (B, 3): origin, pitch, valid
+  float* out;
+  int channels, len;
+};
+
+// grid (ceil(len / 256), channels, B)
+__global__ void __launch_bounds__(256) gather_crops_kernel(const CropArgs a) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= a.len) return;
+  const long long origin = __ldg(a.plan + 3 * b);
+  const long long pitch = __ldg(a.plan + 3 * b + 1);
+  const long long valid = __ldg(a.plan + 3 * b + 2);
+  const float v = t < valid ? __ldg(a.store + origin + c * pitch + t) : 0.f;
+  a.out[(static_cast<size_t>(b) * a.channels + c) * a.len + t] = v;
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+ms_status ms_gather_crops(const float* store, const long long* plan, float* out, int batch,
+                          int channels, int len, void* stream) {
+  if (store == nullptr || plan == nullptr || out == nullptr || batch <= 0 || channels <= 0 ||
+      len <= 0 || channels > 65535 || batch > 65535)
+    return MS_ERR_INVALID;
+  CropArgs a;
+  a.store = store; a.plan = plan; a.out = out; a.channels = channels; a.len = len;
+  const dim3 grid((len + 255) / 256, channels, batch);
+  gather_crops_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return after_launch("gather_crops_kernel");
+}
+
+}  // extern "C"

@@ -1,2 +1,2 @@
-from .train import GeneratorTrainer, DiscriminatorTrainer  # noqa: F401
+from .train import GeneratorTrainer, DiscriminatorTrainer, training_loop  # noqa: F401
 from .optim import Adam  # noqa: F401

@@ -261,3 +261,31 @@ class DiscriminatorTrainer(_GraphMixin):
         (loss,) = self._run(samples, features)
         self._finish(self.d_optim, self.discriminator)
         return {'d_loss': loss.item()}
+
+
+def training_loop(batch_stream, experiment, device, loggers):
+    """featuresynth/train/train.py:77-106: pre-process each batch, run the experiment's next
+    training step (discriminator and generator alternate), hand the result to the loggers.
+    Batches may already be CUDA tensors (data/datastore.py) -- then nothing is copied."""
+    from datetime import datetime, timezone
+
+    def to_device(x):
+        if isinstance(x, dict):
+            return {k: to_device(v) for k, v in x.items()}
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(x)
+        return x.to(device).float()
+
+    start_time = datetime.now(timezone.utc)
+    for i, batch in enumerate(batch_stream):
+        preprocessed = experiment.preprocess_batch(batch)
+        tensors = [to_device(x) for x in preprocessed]
+        step = next(experiment.training_steps)
+        step_result = step(*tensors)
+        elapsed_time = datetime.now(timezone.utc) - start_time
+        log_results = {}
+        for logger in loggers:
+            log_result = logger(experiment, preprocessed, step_result, i, elapsed_time)
+            if log_result is not None:
+                log_results.update(log_result)
+        yield i, elapsed_time, log_results

@@ -308,7 +308,33 @@ def multiscale():
         save(name, **arrays)
 
 
+def data_feed():
+    """featuresynth/data/datastore.py:19-80 `batch_stream`, unmodified, over in-memory chunks:
+    `iter_audio_chunks` is pointed at a chunk-id list and `feature_funcs` at array lookups (the
+    reference's own extension points); python `random` and numpy's global generator are seeded."""
+    import random
+    ref_harness.load()
+    import featuresynth.data.datastore as ds
+    audio, spec = synth.feed_chunks(91)
+    spec_spec = {"audio": (2048, 1), "spectrogram": (32, 16)}
+    ds.iter_audio_chunks = lambda path, pattern: [(i, 0, 0) for i in range(len(audio))]
+    funcs = {"audio": (lambda chunk: audio[chunk[0]], ()),
+             "spectrogram": (lambda chunk: spec[chunk[0]], ())}
+    random.seed(7)
+    np.random.seed(7)
+    stream = ds.batch_stream("unused", "unused", 6, spec_spec, "spectrogram", funcs)
+    arrays = {"seed": 7, "chunk_seed": 91, "batch_size": 6}
+    for i in range(3):
+        a, s_ = next(stream)
+        arrays[f"audio_{i}"] = a
+        arrays[f"spectrogram_{i}"] = s_
+    save("batch_stream", **arrays)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "data_feed":
+        data_feed()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "multiscale":
         multiscale()
         sys.exit(0)

@@ -739,3 +739,50 @@ def multiscale_multires_discriminator(x, feat, sd, input_size, decompose=True,
     features.append(final)
     judgements.append(F.conv1d(h, sd[f"{p}judge.weight"], sd[f"{p}judge.bias"], padding=1))
     return features, judgements
+
+
+# ---------------------------------------------------------------- data feed
+def batch_stream(audio_chunks, spec_chunks, batch_size, feature_spec, anchor_feature, seed,
+                 n_batches):
+    """featuresynth/data/datastore.py:8-80 with the chunk features given as arrays (the
+    reference reads them from its LMDB cache through `feature_funcs`): per example
+    `random.choice` of a chunk, `random_slice` of the anchor feature, the aligned slice
+    [start*ratio, end*ratio) of every other feature, zero padding, `conform` to
+    (1, channels, size); batches are tuples in `feature_spec` order.  numpy, host only."""
+    import random
+    import numpy as np
+    py_rng = random.Random(seed)
+    np_rng = np.random.RandomState(seed)
+    feats = {"audio": audio_chunks, "spectrogram": spec_chunks}
+
+    def pad(x, length):
+        if len(x) == length:
+            return x
+        widths = [(0, 0)] * x.ndim
+        widths[0] = (0, length - len(x))
+        return np.pad(x, widths, mode="constant")
+
+    def conform(x, spec):
+        size, channels = spec
+        return x.T.reshape((-1, channels, size))
+
+    anchor_size = feature_spec[anchor_feature][0]
+    out = []
+    for _ in range(n_batches):
+        batch = {k: [] for k in feature_spec}
+        for _ in range(batch_size):
+            pick = py_rng.choice(range(len(audio_chunks)))
+            arr = feats[anchor_feature][pick]
+            room = len(arr) - anchor_size
+            start = np_rng.randint(0, room) if room > 0 else 0
+            end = start + anchor_size
+            batch[anchor_feature].append(
+                conform(pad(arr[start:end], anchor_size), feature_spec[anchor_feature]))
+            for feat, spec in feature_spec.items():
+                if feat == anchor_feature:
+                    continue
+                ratio = spec[0] // anchor_size
+                ns, ne = start * ratio, end * ratio
+                batch[feat].append(conform(pad(feats[feat][pick][ns:ne], ne - ns), spec))
+        out.append(tuple(np.concatenate(batch[f], axis=0) for f in feature_spec))
+    return out

@@ -33,3 +33,16 @@ def residual_stack_state(seed, channels, prefix="s", bias_std=0.01):
             sd[f"{prefix}.main.{a}.main.{c}.bias"] = torch.from_numpy(
                 (rs.standard_normal((channels,)) * bias_std).astype(np.float32))
     return sd
+
+
+def feed_chunks(seed, lengths=(6000, 3000, 1200, 400), channels=16, hop=64, frame_pad=192):
+    """Decoded 'file chunks' for the data-feed tests: audio (n,) and a stand-in cached
+    spectrogram (frames, channels) per chunk, frames = (n + frame_pad - 4*hop)//hop + 1 like
+    Audio2Mel's framing.  The last chunks are shorter than a crop (zero-padding cases)."""
+    rs = np.random.RandomState(seed)
+    audio, spec = [], []
+    for n in lengths:
+        audio.append((rs.random_sample(n) * 2 - 1).astype(np.float32))
+        frames = max((n + frame_pad - 4 * hop) // hop + 1, 0)
+        spec.append(rs.standard_normal((frames, channels)).astype(np.float32))
+    return audio, spec

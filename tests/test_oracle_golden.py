@@ -316,3 +316,42 @@ def test_reference_multiscale_representation_is_the_fft_bands_fixture(golden):
     for k, v in ms.data.items():
         assert np.array_equal(v, g[f"band_{k}"])
     assert np.array_equal(ms.to_audio(), g["recomposed"].reshape(2, 8192))
+
+
+FEED_SPEC = {"audio": (2048, 1), "spectrogram": (32, 16)}
+
+
+def test_batch_stream_restatement_matches_reference(golden):
+    """oracle/restate.py::batch_stream vs three batches of the unmodified reference's
+    batch_stream (data/datastore.py:19-80) over the same chunks and seeds: bit-exact."""
+    g = golden("batch_stream")
+    audio, spec = synth.feed_chunks(int(g["chunk_seed"]))
+    got = restate.batch_stream(audio, spec, int(g["batch_size"]), FEED_SPEC, "spectrogram",
+                               int(g["seed"]), 3)
+    for i, (a, s) in enumerate(got):
+        assert np.array_equal(a, g[f"audio_{i}"]) and a.shape == (6, 1, 2048)
+        assert np.array_equal(s, g[f"spectrogram_{i}"]) and s.shape == (6, 16, 32)
+    # the fixture exercises the zero-padding path (chunks shorter than a crop)
+    assert any((g[f"audio_{i}"][:, 0, -1] == 0).any() for i in range(3))
+
+
+def test_data_feed_host_logic_matches_reference(golden):
+    """The product's crop drawing and crop plans (data/datastore.py), with the gather itself
+    emulated in numpy from the (origin, pitch, valid) rows ms_gather_crops consumes."""
+    import random
+    from music_synthesis_b200.data import DeviceAudioStore, draw_crops
+    g = golden("batch_stream")
+    audio, spec = synth.feed_chunks(int(g["chunk_seed"]))
+    store = DeviceAudioStore(audio, spectrograms=spec, device="cpu")
+    py_rng, np_rng = random.Random(int(g["seed"])), np.random.RandomState(int(g["seed"]))
+    flat = {"audio": store.audio.numpy(), "spectrogram": store.spec.numpy()}
+    for i in range(3):
+        picks, starts = draw_crops(py_rng, np_rng, store.frames, 32, 6)
+        plans = store.crop_plans(picks, starts, FEED_SPEC)
+        for feat, (size, channels) in FEED_SPEC.items():
+            out = np.zeros((6, channels, size), dtype=np.float32)
+            for b, (origin, pitch, valid) in enumerate(plans[feat]):
+                for c in range(channels):
+                    lo = origin + c * pitch
+                    out[b, c, :valid] = flat[feat][lo: lo + valid]
+            assert np.array_equal(out, g[f"{feat}_{i}"]), (feat, i)
