@@ -431,14 +431,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         int2* tt = s_tab + (acc & 1) * 32;
         if (et < p.NT) {
           const int n = n0 + et;
-          const int ch = (p.kind == MS_CONVT) ? n % p.cout : n;
+          const int ch = (p.kind == MS_CONVT) ? convt_col_channel(n, p.stride) : n;
           tb[et] = p.bias != nullptr ? __ldg(p.bias + ch) : 0.f;
         }
         if (et < (p.NT >> 3)) {
           const int n = n0 + et * 8;
           if (p.kind == MS_CONVT) {
-            const int r = n / p.cout;
-            tt[et] = make_int2(r, n - r * p.cout);
+            tt[et] = make_int2(convt_col_phase(n, p.stride), convt_col_channel(n, p.stride));
           } else {
             tt[et] = make_int2(0, n);
           }
@@ -481,6 +480,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // this warp handles group pairs (2 x 16 columns) g = 2*half, 2*half+4, ...
         for (int g = 2 * half; g < ngroups; g += 4) {
           const bool two = (g + 1) < ngroups;
+          // the residual vectors of this group's (up to four) chunks are requested BEFORE the
+          // accumulator is read: four independent loads in flight per thread instead of one L2
+          // round trip per chunk (the loads used to sit between the stores of consecutive chunks)
+          float r8[4][8];
+          if (p.res32 != nullptr) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              if (h >= 2 && !two) break;
+              const int2 rc = ttab[g * 2 + h];
+              const int orow = (p.kind == MS_CONVT) ? p.stride * m + rc.x - p.pad : m;
+              if (slot_ok && (m < p.Lm) && orow >= 0 && orow < p.Lout)
+                ld_global_nc_v8(p.res32 + ((static_cast<size_t>(bb) * cout8 + (rc.y >> 3)) * p.Lout + orow) * 8,
+                                r8[h]);
+            }
+          }
           uint32_t v[32];
           tmem_ld16p(taddr + g * 16, &v[0]);
           if (two) tmem_ld16p(taddr + (g + 1) * 16, &v[16]);
@@ -518,10 +532,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
             const size_t idx = (static_cast<size_t>(bb) * cout8 + (ch >> 3)) * p.Lout + orow;
             if (p.res32 != nullptr) {
-              float r8[8];
-              ld_global_nc_v8(p.res32 + idx * 8, r8);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += r8[j];
+              for (int j = 0; j < 8; ++j) f[j] += r8[h][j];
             }
             if (p.leaky == 2) {                       // activation AFTER the residual add
 #pragma unroll
@@ -571,7 +583,7 @@ __global__ void convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-ti
   if (co >= p.cout) return;
   const int orow = p.stride * p.lin + r - p.pad;
   if (orow < 0 || orow >= p.Lout) return;
-  const int n = r * p.cout + co;            // GEMM column
+  const int n = convt_col(r, co, p.stride);   // GEMM column
   const int nt = n / ntp, nn = n - nt * ntp;
   const int chunks = p.KB >> 3;
   float acc = 0.f;
@@ -636,8 +648,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
   if (kind == MS_CONV) {
     v = w[(static_cast<size_t>(n) * cin + ci) * ksize + t];
   } else {
-    const int ph = n / cout;
-    const int co = n - ph * cout;
+    const int ph = convt_col_phase(n, stride);
+    const int co = convt_col_channel(n, stride);
     const int kk = (t == 0) ? ph + stride : ph;
     v = w[(static_cast<size_t>(ci) * cout + co) * ksize + kk];
   }

@@ -36,6 +36,20 @@ struct ConvCfg {
   size_t packed_weight_bytes;
 };
 
+// GEMM column order of the polyphase ConvTranspose: n = ((co / 8) * stride + phase) * 8 + co % 8.
+// A thread of the epilogue (one input-rate row q) then meets the `stride` phases of an
+// 8-channel block in consecutive 8-column chunks = consecutive output rows s*q + r - pad = one
+// contiguous stride*32-byte (fp32) run, so every 128-byte line is written whole by one thread
+// within one tile.  (With the phase-major order n = r * cout + co the four rows of a line came
+// from different n-tiles, i.e. different CTAs at different times: partial-line writes.)
+__host__ __device__ inline int convt_col(int phase, int co, int stride) {
+  return ((co >> 3) * stride + phase) * 8 + (co & 7);
+}
+__host__ __device__ inline int convt_col_phase(int n, int stride) { return (n >> 3) % stride; }
+__host__ __device__ inline int convt_col_channel(int n, int stride) {
+  return ((n >> 3) / stride) * 8 + (n & 7);
+}
+
 // returns false when the descriptor is unsupported
 bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* cfg);
 

@@ -218,14 +218,13 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
         int2* tt = s_tab + (acc & 1) * 32;
         if (et < p.NT) {
           const int n = n0 + et;
-          const int ch = (p.kind == MS_CONVT) ? n % p.cout : n;
+          const int ch = (p.kind == MS_CONVT) ? convt_col_channel(n, p.stride) : n;
           tb[et] = p.bias != nullptr ? __ldg(p.bias + ch) : 0.f;
         }
         if (et < (p.NT >> 3)) {
           const int n = n0 + et * 8;
           if (p.kind == MS_CONVT) {
-            const int r = n / p.cout;
-            tt[et] = make_int2(r, n - r * p.cout);
+            tt[et] = make_int2(convt_col_phase(n, p.stride), convt_col_channel(n, p.stride));
           } else {
             tt[et] = make_int2(0, n);
           }
@@ -255,6 +254,21 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       bool arrived = false;
       for (int g = 2 * half; g < ngroups; g += 4) {
         const bool two = (g + 1) < ngroups;
+        // the residual vectors of this group's (up to four) chunks are requested BEFORE the
+        // accumulator is read: four independent loads in flight per thread instead of one L2
+        // round trip per chunk (the loads used to sit between the stores of consecutive chunks)
+        float r8[4][8];
+        if (p.res32 != nullptr) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h >= 2 && !two) break;
+            const int2 rc = ttab[g * 2 + h];
+            const int orow = (p.kind == MS_CONVT) ? p.stride * m + rc.x - p.pad : m;
+            if ((m < p.Lm) && orow >= 0 && orow < p.Lout)
+              ld_global_nc_v8(p.res32 + ((static_cast<size_t>(b) * cout8 + (rc.y >> 3)) * p.Lout + orow) * 8,
+                              r8[h]);
+          }
+        }
         uint32_t v[32];
         tmem_ld16p(taddr + g * 16, &v[0]);
         if (two) tmem_ld16p(taddr + (g + 1) * 16, &v[16]);
@@ -292,10 +306,8 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           const size_t idx = (static_cast<size_t>(b) * cout8 + (ch >> 3)) * p.Lout + orow;
           if (p.res32 != nullptr) {
-            float r8[8];
-            ld_global_nc_v8(p.res32 + idx * 8, r8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += r8[j];
+            for (int j = 0; j < 8; ++j) f[j] += r8[h][j];
           }
           if (p.leaky == 2) {                         // activation AFTER the residual add
 #pragma unroll

@@ -228,3 +228,18 @@ def test_audio2mel_fft_forms_agree(monkeypatch):
         assert (new.cpu() - ref).abs().max().item() < 1e-4
         assert (old.cpu() - ref).abs().max().item() < 1e-4
         assert (new - old).abs().max().item() < 1e-4
+
+
+def test_neural_vocoder_long_sequence():
+    """the stage-one caller runs the generator through `NeuralVocoder` on
+    512-frame feature sequences (featureexperiment.py:94-100) -- 131072 samples per clip."""
+    from music_synthesis_b200.generator.full import MelGanGenerator
+    from music_synthesis_b200.experiment.featureexperiment import NeuralVocoder
+    sd = restate.melgan_generator_state(31)
+    g = MelGanGenerator(512, 128).eval()
+    g.load_state_dict(sd)
+    vocoder = NeuralVocoder(g.cuda())
+    x = synth.mel_features(32, 1, 512)
+    y = vocoder(x.cuda())
+    assert y.shape == (1, 1, 131072) and not y.requires_grad
+    assert rel_l2(y, restate.melgan_generator(x, sd)) < WAVEFORM_TOL
