@@ -25,8 +25,14 @@
 namespace msb {
 namespace fftb {
 
-enum Load { kLoadComplex = 0, kLoadReal = 1, kLoadBand = 2, kLoadHalf = 3 };
-enum Store { kStoreComplex = 0, kStoreReal = 1 };
+enum Load {
+  kLoadComplex = 0, kLoadReal = 1, kLoadBand = 2, kLoadHalf = 3,
+  // real-input packing (default): a real sequence of length 2h is transformed as the h-point
+  // complex sequence x[2m] + i x[2m+1]; these loaders build the packed inverse input V[k]
+  // straight from the packed forward output Z (band cut-out) or from the stored half spectrum
+  kLoadBandPk = 4, kLoadHalfPk = 5
+};
+enum Store { kStoreComplex = 0, kStoreReal = 1, kStoreConj = 2 };
 
 struct PassArgs {
   const void* x;   // float2 rows of n | float rows of n | float2 rows of src_n (band / half)
@@ -38,6 +44,31 @@ struct PassArgs {
   int lo;          // kLoadBand: first kept bin
   float scale;     // kLoadBand: applied to the kept bins
 };
+
+// X[k], 0 <= k <= h, of a real sequence of length 2h from Z = FFT_h(x[2m] + i x[2m+1]):
+//   X[k] = (Z[k] + conj(Z[h-k])) / 2 - i W_2h^k (Z[k] - conj(Z[h-k])) / 2,   Z[h] := Z[0]
+A2M_HD float2 real_bin(const float2* Z, int h, int k) {
+  const float2 a = Z[k == h ? 0 : k];
+  const float2 b = Z[(k == 0 || k == h) ? 0 : h - k];
+  const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
+  const float dr = 0.5f * (a.x - b.x), di = 0.5f * (a.y + b.y);
+  float s, c;
+  sincospif(-static_cast<float>(k) / static_cast<float>(h), &s, &c);
+  return make_float2(er + (c * di + s * dr), ei - (c * dr - s * di));
+}
+
+// conj(V[k]), 0 <= k < H, the packed input of the H-point transform whose output is
+// y[2m] - i y[2m+1] for the real sequence y of length 2H with Hermitian spectrum Y[0..H]:
+//   V[k] = (Y[k] + conj(Y[H-k])) + i W_2H^-k (Y[k] - conj(Y[H-k]))
+A2M_HD void packed_inverse_input(float2 ya, float2 yb, int k, int H, float& re, float& im) {
+  const float px = ya.x + yb.x, py = ya.y - yb.y;
+  const float qx = ya.x - yb.x, qy = ya.y + yb.y;
+  float s, c;
+  sincospif(static_cast<float>(k) / static_cast<float>(H), &s, &c);
+  const float ex = c * qx - s * qy, ey = c * qy + s * qx;
+  re = px - ey;
+  im = -(py + ex);
+}
 
 template <int LD>
 A2M_HD void load_one(const PassArgs& a, size_t row, int idx, float& re, float& im) {
@@ -60,13 +91,36 @@ A2M_HD void load_one(const PassArgs& a, size_t row, int idx, float& re, float& i
       re = v.x * a.scale;
       im = (kk == 0 || kk == half) ? 0.f : (idx <= half ? -a.scale : a.scale) * v.y;
     }
-  } else {
+  } else if (LD == kLoadHalf) {
     // full Hermitian spectrum from its n/2+1 half; conjugated for the inverse
     const int half = a.n >> 1;
     const int kk = idx <= half ? idx : a.n - idx;
     const float2 v = static_cast<const float2*>(a.x)[row * a.src_n + kk];
     re = v.x;
     im = (kk == 0 || kk == half) ? 0.f : (idx <= half ? -v.y : v.y);
+  } else if (LD == kLoadBandPk) {
+    // band of size S = 2 a.n cut out of the packed forward transform Z (rows of src_n = h):
+    // Y[k] = scale * X[k] for lo <= k <= S/2 (imaginary part of k = 0 and k = S/2 dropped)
+    const int H = a.n;
+    const float2* Z = static_cast<const float2*>(a.x) + row * a.src_n;
+    float2 y[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = e == 0 ? idx : H - idx;
+      y[e] = make_float2(0.f, 0.f);
+      if (k >= a.lo) {
+        const float2 x = real_bin(Z, a.src_n, k);
+        y[e] = make_float2(x.x * a.scale, (k == 0 || k == H) ? 0.f : x.y * a.scale);
+      }
+    }
+    packed_inverse_input(y[0], y[1], idx, H, re, im);
+  } else {
+    // kLoadHalfPk: Y[0 .. H] stored (rows of src_n = H + 1), transform length H = a.n
+    const int H = a.n;
+    const float2* Y = static_cast<const float2*>(a.x) + row * a.src_n;
+    float2 ya = Y[idx], yb = Y[H - idx];
+    if (idx == 0) { ya.y = 0.f; yb.y = 0.f; }
+    packed_inverse_input(ya, yb, idx, H, re, im);
   }
 }
 
@@ -117,6 +171,8 @@ A2M_HD void pass_thread(const PassArgs& a, size_t gid) {
   for (int m = 0; m < R; ++m) {
     if (ST == kStoreComplex)
       static_cast<float2*>(a.y)[o + static_cast<size_t>(m) * a.p] = make_float2(re[m], im[m]);
+    else if (ST == kStoreConj)     // packed inverse: (y[2j], y[2j+1]) = conj of the forward result
+      static_cast<float2*>(a.y)[o + static_cast<size_t>(m) * a.p] = make_float2(re[m], -im[m]);
     else
       static_cast<float*>(a.y)[o + static_cast<size_t>(m) * a.p] = re[m];
   }
@@ -130,6 +186,7 @@ template <class F>
 int dispatch(int radix, int load, int store, F&& f) {
   auto with_store = [&](auto r, auto ld) -> int {
     if (store == kStoreComplex) return f(r, ld, IC<kStoreComplex>{});
+    if (store == kStoreConj) return f(r, ld, IC<kStoreConj>{});
     return f(r, ld, IC<kStoreReal>{});
   };
   auto with_load = [&](auto r) -> int {
@@ -137,7 +194,9 @@ int dispatch(int radix, int load, int store, F&& f) {
       case kLoadComplex: return with_store(r, IC<kLoadComplex>{});
       case kLoadReal: return with_store(r, IC<kLoadReal>{});
       case kLoadBand: return with_store(r, IC<kLoadBand>{});
-      default: return with_store(r, IC<kLoadHalf>{});
+      case kLoadHalf: return with_store(r, IC<kLoadHalf>{});
+      case kLoadBandPk: return with_store(r, IC<kLoadBandPk>{});
+      default: return with_store(r, IC<kLoadHalfPk>{});
     }
   };
   switch (radix) {
@@ -253,6 +312,74 @@ int recompose(const float* const* bands, const int* sizes, int nbands, int batch
   inv.n = D; inv.batch = batch; inv.load = kLoadHalf; inv.src = acc; inv.src_n = D / 2 + 1;
   inv.lo = 0; inv.scale = 1.f; inv.store = kStoreReal; inv.dst = out; inv.w0 = w0; inv.w1 = w1;
   return run_xform(inv, launch);
+}
+
+// ---- the same two operations with real-input packing: every transform runs at half length --
+// Z (batch rows of n/2) = packed forward transform of the clip; a band's inverse transform of
+// length S/2 builds its input from Z while loading and stores (y[2j], y[2j+1]) pairs.
+template <class Launch>
+int decompose_packed(const float* x, int batch, int n, int min_size, float* const* bands_out,
+                     float2* Z, float2* w0, float2* w1, Launch&& launch) {
+  Xform f;
+  f.n = n / 2; f.batch = batch; f.load = kLoadComplex; f.src = x; f.src_n = n / 2; f.lo = 0;
+  f.scale = 1.f; f.store = kStoreComplex; f.dst = Z; f.w0 = w0; f.w1 = w1;
+  int rc = run_xform(f, launch);
+  if (rc != 0) return rc;
+  int bi = 0;
+  for (int S = min_size; S <= n; S <<= 1, ++bi) {
+    Xform b;
+    b.n = S / 2; b.batch = batch; b.load = kLoadBandPk; b.src = Z; b.src_n = n / 2;
+    b.lo = (S > min_size) ? S / 4 : 0;
+    b.scale = 1.0f / (sqrtf(static_cast<float>(n)) * sqrtf(static_cast<float>(S)));
+    b.store = kStoreConj; b.dst = bands_out[bi]; b.w0 = w0; b.w1 = w1;
+    rc = run_xform(b, launch);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// accum(packed spectrum (batch rows of S/2), acc, S, D, lo, scale, first) -> 0 on success
+template <class Launch, class Accum>
+int recompose_packed(const float* const* bands, const int* sizes, int nbands, int batch, int D,
+                     float* out, float2* acc, float2* w0, float2* w1, Launch&& launch,
+                     Accum&& accum) {
+  int smin = sizes[0];
+  for (int i = 1; i < nbands; ++i) smin = sizes[i] < smin ? sizes[i] : smin;
+  for (int i = 0; i < nbands; ++i) {
+    const int S = sizes[i];
+    int radix[16];
+    const int count = plan_radices(S / 2, radix);
+    Xform f;
+    f.n = S / 2; f.batch = batch; f.load = kLoadComplex; f.src = bands[i]; f.src_n = S / 2;
+    f.lo = 0; f.scale = 1.f; f.store = kStoreComplex;
+    f.dst = ((count - 1) & 1) ? w1 : w0;
+    f.w0 = w0; f.w1 = w1;
+    int rc = run_xform(f, launch);
+    if (rc != 0) return rc;
+    const int lo = (S == smin) ? 0 : (S / 2 + 1) / 2;
+    const float scale = 1.0f / (sqrtf(static_cast<float>(S)) * sqrtf(static_cast<float>(D)));
+    rc = accum(static_cast<const float2*>(f.dst), acc, S, D, lo, scale, i == 0 ? 1 : 0);
+    if (rc != 0) return rc;
+  }
+  Xform inv;
+  inv.n = D / 2; inv.batch = batch; inv.load = kLoadHalfPk; inv.src = acc; inv.src_n = D / 2 + 1;
+  inv.lo = 0; inv.scale = 1.f; inv.store = kStoreConj; inv.dst = out; inv.w0 = w0; inv.w1 = w1;
+  return run_xform(inv, launch);
+}
+
+// one element of the packed band accumulation: bin k of the band = real_bin of its packed
+// transform (gid over batch * (D/2+1))
+A2M_HD void accumulate_one_packed(const float2* zs, float2* acc, int S, int D, int lo,
+                                  float scale, int first, size_t gid) {
+  const int k = static_cast<int>(gid % (D / 2 + 1));
+  const size_t b = gid / (D / 2 + 1);
+  float2 v = first ? make_float2(0.f, 0.f) : acc[gid];
+  if (k >= lo && k <= S / 2) {
+    const float2 c = real_bin(zs + b * (S / 2), S / 2, k);
+    v.x += c.x * scale;
+    v.y += c.y * scale;
+  }
+  acc[gid] = v;
 }
 
 // one element of the band accumulation (gid over batch * (D/2+1))

@@ -1,7 +1,7 @@
 // CPU harness for csrc/fft_passes.cuh: runs the band split and merge of fft_bands.cu -- the same
 // pass bodies, pass plan and transform sequences, a loop over butterflies standing in for each
 // kernel launch -- on float32 rows read from a file.
-//   usage: fft_bands_host <in.bin> <out.bin> <batch> <n> <min_size>
+//   usage: fft_bands_host <in.bin> <out.bin> <batch> <n> <min_size> [packed = 1]
 //   out.bin = the bands in ascending size, (batch, size) float32 each, then the (batch, n)
 //   recomposition of those bands.  tests/test_abi.py compares both with the oracle.
 #include <cstdio>
@@ -13,7 +13,8 @@
 using namespace msb::fftb;
 
 int main(int argc, char** argv) {
-  if (argc != 6) return 2;
+  if (argc != 6 && argc != 7) return 2;
+  const bool packed = argc == 7 ? std::atoi(argv[6]) != 0 : true;
   const int batch = std::atoi(argv[3]), n = std::atoi(argv[4]), min_size = std::atoi(argv[5]);
   std::vector<float> x(static_cast<size_t>(batch) * n);
   FILE* fi = std::fopen(argv[1], "rb");
@@ -41,12 +42,23 @@ int main(int argc, char** argv) {
     for (size_t gid = 0; gid < total; ++gid) accumulate_one(zs, ac, S, D, lo, scale, first, gid);
     return 0;
   };
-  if (decompose(x.data(), batch, n, min_size, band_ptr.data(), coef.data(), w0.data(), w1.data(),
-                launch) != 0)
+  auto accum_pk = [&](const float2* zs, float2* ac, int S, int D, int lo, float scale, int first) {
+    const size_t total = static_cast<size_t>(batch) * (D / 2 + 1);
+    for (size_t gid = 0; gid < total; ++gid)
+      accumulate_one_packed(zs, ac, S, D, lo, scale, first, gid);
+    return 0;
+  };
+  if ((packed ? decompose_packed(x.data(), batch, n, min_size, band_ptr.data(), coef.data(),
+                                 w0.data(), w1.data(), launch)
+              : decompose(x.data(), batch, n, min_size, band_ptr.data(), coef.data(), w0.data(),
+                          w1.data(), launch)) != 0)
     return 4;
   std::vector<float> y(bn);
-  if (recompose(band_ptr.data(), sizes.data(), static_cast<int>(sizes.size()), batch, n, y.data(),
-                acc.data(), w0.data(), w1.data(), launch, accum) != 0)
+  if ((packed ? recompose_packed(band_ptr.data(), sizes.data(), static_cast<int>(sizes.size()),
+                                 batch, n, y.data(), acc.data(), w0.data(), w1.data(), launch,
+                                 accum_pk)
+              : recompose(band_ptr.data(), sizes.data(), static_cast<int>(sizes.size()), batch, n,
+                          y.data(), acc.data(), w0.data(), w1.data(), launch, accum)) != 0)
     return 5;
   FILE* fo = std::fopen(argv[2], "wb");
   if (fo == nullptr) return 6;
