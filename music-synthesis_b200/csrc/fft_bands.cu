@@ -9,9 +9,13 @@
 // (+ one radix-2 / radix-4 pass for the odd bits of log2 n), real-input load, band cut-out,
 // Hermitian expansion and real-part store folded into the first / last pass of a transform:
 // n = 65536 is 4 passes and no boundary kernels instead of 8 radix-4 passes + 3 copies.
+// Real-input packing: a real sequence of length 2h runs as the h-point complex transform of
+// x[2m] + i x[2m+1]; the band cut-out builds the packed inverse input straight from the packed
+// forward output (MSB_FFT_PACKED=0: full-length complex transforms).
 // MSB_FFT_LEGACY=1 selects the first version (radix-4 passes, separate boundary kernels).
 // Because irFFT is linear, recompose sums the bands' spectra first and runs ONE inverse
 // transform.
+#include <cstdint>
 #include <cstdlib>
 
 #include "fft_passes.cuh"
@@ -220,8 +224,12 @@ struct PassLauncher {
           fft_pass16_first_kernel<fftb::kLoadReal><<<grid, 256, 0, st>>>(a); break;
         case fftb::kLoadBand:
           fft_pass16_first_kernel<fftb::kLoadBand><<<grid, 256, 0, st>>>(a); break;
-        default:
+        case fftb::kLoadHalf:
           fft_pass16_first_kernel<fftb::kLoadHalf><<<grid, 256, 0, st>>>(a); break;
+        case fftb::kLoadBandPk:
+          fft_pass16_first_kernel<fftb::kLoadBandPk><<<grid, 256, 0, st>>>(a); break;
+        default:
+          fft_pass16_first_kernel<fftb::kLoadHalfPk><<<grid, 256, 0, st>>>(a); break;
       }
       return after_launch("fft_pass16_first_kernel");
     }
@@ -240,6 +248,15 @@ __global__ void accumulate_band2_kernel(const float2* __restrict__ zs, float2* _
   const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (gid < total) fftb::accumulate_one(zs, acc, S, D, lo, scale, first, gid);
 }
+
+__global__ void accumulate_band_packed_kernel(const float2* __restrict__ zs,
+                                              float2* __restrict__ acc, int S, int D, int lo,
+                                              float scale, int first, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid < total) fftb::accumulate_one_packed(zs, acc, S, D, lo, scale, first, gid);
+}
+
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 inline unsigned nblk(size_t total) { return static_cast<unsigned>((total + 255) / 256); }
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -272,9 +289,16 @@ ms_status ms_fft_frequency_decompose(const float* x, int batch, int n, int min_s
   float2* w0 = coef + bn;
   float2* w1 = w0 + bn;
   const bool legacy = env_flag("MSB_FFT_LEGACY", false);
-  if (!legacy)
+  if (!legacy) {
+    // real-input packing (half-length transforms) needs 8-byte aligned rows: float2 accesses
+    bool packed = env_flag("MSB_FFT_PACKED", true) && aligned8(x);
+    for (int i = 0; i < nbands; ++i) packed = packed && aligned8(bands_out[i]);
+    if (packed)
+      return static_cast<ms_status>(fftb::decompose_packed(x, batch, n, min_size, bands_out, coef,
+                                                           w0, w1, PassLauncher(st)));
     return static_cast<ms_status>(
         fftb::decompose(x, batch, n, min_size, bands_out, coef, w0, w1, PassLauncher(st)));
+  }
   real_to_complex_kernel<<<nblk(bn), 256, 0, st>>>(x, w0, bn);
   ms_status s = after_launch("real_to_complex_kernel");
   if (s != MS_OK) return s;
@@ -328,6 +352,19 @@ ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes
       accumulate_band2_kernel<<<nblk(bh), 256, 0, st>>>(zs, ac, S, Dd, lo, scale, first, bh);
       return after_launch("accumulate_band2_kernel");
     };
+    bool packed = env_flag("MSB_FFT_PACKED", true) && aligned8(out);
+    for (int i = 0; i < nbands; ++i) packed = packed && aligned8(bands[i]);
+    if (packed) {
+      auto accum_pk = [&](const float2* zs, float2* ac, int S, int Dd, int lo, float scale,
+                          int first) -> int {
+        accumulate_band_packed_kernel<<<nblk(bh), 256, 0, st>>>(zs, ac, S, Dd, lo, scale, first,
+                                                                bh);
+        return after_launch("accumulate_band_packed_kernel");
+      };
+      return static_cast<ms_status>(fftb::recompose_packed(bands, sizes, nbands, batch, D, out,
+                                                           acc, w0, w1, PassLauncher(st),
+                                                           accum_pk));
+    }
     return static_cast<ms_status>(fftb::recompose(bands, sizes, nbands, batch, D, out, acc, w0,
                                                   w1, PassLauncher(st), accum));
   }

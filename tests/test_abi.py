@@ -166,9 +166,11 @@ def test_audio2mel_fft_passes_on_host(tmp_path):
 
 @pytest.mark.parametrize("batch,n,min_size", [(2, 65536, 4096), (2, 8192, 256), (3, 2048, 16),
                                               (1, 32768, 1024), (1, 16, 16), (1, 8, 4)])
-def test_fft_band_passes_on_host(tmp_path, batch, n, min_size):
+@pytest.mark.parametrize("packed", [1, 0])
+def test_fft_band_passes_on_host(tmp_path, batch, n, min_size, packed):
     """csrc/fft_passes.cuh (radix-2/4/16 Stockham passes with fused boundary loads / stores, the
-    pass plan and the decompose / recompose sequences of fft_bands.cu) is host-callable:
+    pass plan and the decompose / recompose sequences of fft_bands.cu, with real-input packing
+    and without) is host-callable:
     tests/native/fft_bands_host.cu runs it on the CPU; compared with the oracle's restatement of
     featuresynth/audio/transform.py:50-115."""
     import shutil
@@ -188,7 +190,7 @@ def test_fft_band_passes_on_host(tmp_path, batch, n, min_size):
     x = (np.random.RandomState(n + batch).randn(batch, n) * 0.1).astype(np.float32)
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     x.tofile(fin)
-    r = subprocess.run([exe, fin, fout, str(batch), str(n), str(min_size)])
+    r = subprocess.run([exe, fin, fout, str(batch), str(n), str(min_size), str(packed)])
     assert r.returncode == 0
     out = np.fromfile(fout, dtype=np.float32)
     ref = restate.fft_frequency_decompose(torch.from_numpy(x)[:, None, :], min_size)

@@ -63,11 +63,12 @@ def test_multiscale_representation_matches_golden(golden):
     assert RawAudio.from_audio(x, 22050).to_audio().shape == (2, 8192)
 
 
-@pytest.mark.parametrize("knob", ["MSB_FFT_STAGED=0", "MSB_FFT_LEGACY=1"])
+@pytest.mark.parametrize("knob", ["MSB_FFT_STAGED=0", "MSB_FFT_PACKED=0", "MSB_FFT_LEGACY=1"])
 def test_pass_variants_agree(monkeypatch, knob):
     """The library reads its knobs per call: the first radix-16 pass with direct stores
-    (MSB_FFT_STAGED=0) is bit-identical to the shared-memory staged one; the first-version
-    radix-4 path (MSB_FFT_LEGACY=1) agrees to rounding."""
+    (MSB_FFT_STAGED=0) is bit-identical to the shared-memory staged one; full-length complex
+    transforms (MSB_FFT_PACKED=0) and the first-version radix-4 path (MSB_FFT_LEGACY=1) agree
+    with the default real-packed half-length transforms to rounding."""
     from music_synthesis_b200.audio.transform import fft_frequency_decompose, fft_frequency_recompose
     x = (synth.randn(54, 3, 1, 65536) * 0.1).cuda()
     a = fft_frequency_decompose(x, 4096)
