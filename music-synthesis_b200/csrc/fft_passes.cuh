@@ -1,4 +1,4 @@
-// Stockham autosort FFT passes of radix 2 / 4 / 16 for the octave-band split / merge
+// Stockham autosort FFT passes of radix 2 / 4 / 8 / 16 for the octave-band split / merge
 // (fft_bands.cu), with the boundary work folded into the first and last pass of a transform:
 //   first pass loads   complex data | real data (imag = 0) | a band's Hermitian spectrum cut
 //                      out of the full-length coefficients | the full Hermitian spectrum
@@ -44,6 +44,46 @@ struct PassArgs {
   int lo;          // kLoadBand: first kept bin
   float scale;     // kLoadBand: applied to the kept bins
 };
+
+// forward 8-point DFT, natural order in and out (n = 4a + b, k = c + 2d)
+A2M_HD void dft8(float (&re)[8], float (&im)[8]) {
+  constexpr float H = 0.70710678118654752f;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const float ur = re[b], ui = im[b];
+    re[b] = ur + re[4 + b]; im[b] = ui + im[4 + b];
+    re[4 + b] = ur - re[4 + b]; im[4 + b] = ui - im[4 + b];
+  }
+  a2m::cmul(re[5], im[5], H, -H);                 // W_8^1
+  {                                               // W_8^2 = -i
+    const float t = re[6];
+    re[6] = im[6];
+    im[6] = -t;
+  }
+  a2m::cmul(re[7], im[7], -H, -H);                // W_8^3
+  a2m::dft4(re[0], im[0], re[1], im[1], re[2], im[2], re[3], im[3]);
+  a2m::dft4(re[4], im[4], re[5], im[5], re[6], im[6], re[7], im[7]);
+  // position 4c + d holds X[c + 2d]
+  const float r[8] = {re[0], re[4], re[1], re[5], re[2], re[6], re[3], re[7]};
+  const float i[8] = {im[0], im[4], im[1], im[5], im[2], im[6], im[3], im[7]};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { re[k] = r[k]; im[k] = i[k]; }
+}
+
+// v[q] *= w^q, q = 1..7
+A2M_HD void twiddle8(float (&re)[8], float (&im)[8], float c1, float s1) {
+  const float c2 = c1 * c1 - s1 * s1, s2 = 2.f * c1 * s1;
+  const float c4 = c2 * c2 - s2 * s2, s4 = 2.f * c2 * s2;
+  const float c3 = c2 * c1 - s2 * s1, s3 = c2 * s1 + s2 * c1;
+  a2m::cmul(re[1], im[1], c1, s1);
+  a2m::cmul(re[2], im[2], c2, s2);
+  a2m::cmul(re[3], im[3], c3, s3);
+  a2m::cmul(re[4], im[4], c4, s4);
+  float c, s;
+  c = c4 * c1 - s4 * s1; s = c4 * s1 + s4 * c1; a2m::cmul(re[5], im[5], c, s);
+  c = c4 * c2 - s4 * s2; s = c4 * s2 + s4 * c2; a2m::cmul(re[6], im[6], c, s);
+  c = c4 * c3 - s4 * s3; s = c4 * s3 + s4 * c3; a2m::cmul(re[7], im[7], c, s);
+}
 
 // X[k], 0 <= k <= h, of a real sequence of length 2h from Z = FFT_h(x[2m] + i x[2m+1]):
 //   X[k] = (Z[k] + conj(Z[h-k])) / 2 - i W_2h^k (Z[k] - conj(Z[h-k])) / 2,   Z[h] := Z[0]
@@ -143,6 +183,9 @@ A2M_HD void pass_compute(const PassArgs& a, size_t gid, float (&re)[R], float (&
   if constexpr (R == 16) {
     if (a.p > 1) a2m::twiddle16(re, im, c1, s1);
     a2m::dft16(re, im);
+  } else if constexpr (R == 8) {
+    if (a.p > 1) twiddle8(re, im, c1, s1);
+    dft8(re, im);
   } else if constexpr (R == 4) {
     if (a.p > 1) {
       const float c2 = c1 * c1 - s1 * s1, s2 = 2.f * c1 * s1;
@@ -202,6 +245,7 @@ int dispatch(int radix, int load, int store, F&& f) {
   switch (radix) {
     case 2: return with_load(IC<2>{});
     case 4: return with_load(IC<4>{});
+    case 8: return with_load(IC<8>{});
     case 16: return with_load(IC<16>{});
     default: return -1;
   }
@@ -224,8 +268,9 @@ inline int plan_radices(int n, int* radix) {   // n = power of two >= 2; returns
   int log2n = 0;
   while ((1 << log2n) < n) ++log2n;
   int c = 0;
-  if (log2n & 1) radix[c++] = 2;
-  if (log2n & 2) radix[c++] = 4;
+  if ((log2n & 3) == 3) radix[c++] = 8;
+  else if (log2n & 1) radix[c++] = 2;
+  else if (log2n & 2) radix[c++] = 4;
   for (int s = log2n >> 2; s > 0; --s) radix[c++] = 16;
   return c;
 }
