@@ -228,8 +228,10 @@ struct PassLauncher {
           fft_pass16_first_kernel<fftb::kLoadHalf><<<grid, 256, 0, st>>>(a); break;
         case fftb::kLoadBandPk:
           fft_pass16_first_kernel<fftb::kLoadBandPk><<<grid, 256, 0, st>>>(a); break;
-        default:
+        case fftb::kLoadHalfPk:
           fft_pass16_first_kernel<fftb::kLoadHalfPk><<<grid, 256, 0, st>>>(a); break;
+        default:
+          fft_pass16_first_kernel<fftb::kLoadMergePk><<<grid, 256, 0, st>>>(a); break;
       }
       return after_launch("fft_pass16_first_kernel");
     }
@@ -354,6 +356,13 @@ ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes
     };
     bool packed = env_flag("MSB_FFT_PACKED", true) && aligned8(out);
     for (int i = 0; i < nbands; ++i) packed = packed && aligned8(bands[i]);
+    if (packed && env_flag("MSB_FFT_MERGE_GATHER", true)) {
+      // the bands' packed spectra are kept side by side in the first workspace region and the
+      // inverse transform gathers from them while loading: no accumulation passes
+      const int rc = fftb::recompose_merged(bands, sizes, nbands, batch, D, out, acc, w0, w1,
+                                            PassLauncher(st));
+      if (rc != -2) return static_cast<ms_status>(rc);
+    }
     if (packed) {
       auto accum_pk = [&](const float2* zs, float2* ac, int S, int Dd, int lo, float scale,
                           int first) -> int {

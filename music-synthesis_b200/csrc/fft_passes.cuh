@@ -30,7 +30,19 @@ enum Load {
   // real-input packing (default): a real sequence of length 2h is transformed as the h-point
   // complex sequence x[2m] + i x[2m+1]; these loaders build the packed inverse input V[k]
   // straight from the packed forward output Z (band cut-out) or from the stored half spectrum
-  kLoadBandPk = 4, kLoadHalfPk = 5
+  kLoadBandPk = 4, kLoadHalfPk = 5,
+  // merge: the Hermitian spectrum is the scaled sum of the kept bins of every band's packed
+  // forward transform, gathered while loading (no accumulation passes over a spectrum array)
+  kLoadMergePk = 6
+};
+
+constexpr int kMaxBands = 12;
+struct BandTable {        // kLoadMergePk: band b = rows of size[b]/2 float2 at x + offset[b]
+  int count;
+  int size[kMaxBands];
+  int lo[kMaxBands];
+  float scale[kMaxBands];
+  long long offset[kMaxBands];
 };
 enum Store { kStoreComplex = 0, kStoreReal = 1, kStoreConj = 2 };
 
@@ -43,6 +55,7 @@ struct PassArgs {
   int src_n;       // kLoadBand: row length of the coefficient array; kLoadHalf: n / 2 + 1
   int lo;          // kLoadBand: first kept bin
   float scale;     // kLoadBand: applied to the kept bins
+  BandTable bands; // kLoadMergePk
 };
 
 // forward 8-point DFT, natural order in and out (n = 4a + b, k = c + 2d)
@@ -154,6 +167,28 @@ A2M_HD void load_one(const PassArgs& a, size_t row, int idx, float& re, float& i
       }
     }
     packed_inverse_input(y[0], y[1], idx, H, re, im);
+  } else if (LD == kLoadMergePk) {
+    // Y[k] = sum over bands of scale_b * X_b[k] for lo_b <= k <= S_b/2 (fft_resample +
+    // the sum of fft_frequency_recompose, audio/transform.py:85-115), X_b un-tangled from
+    // band b's packed transform; imaginary part of k = 0 and k = H dropped
+    const int H = a.n;
+    const float2* base = static_cast<const float2*>(a.x);
+    float2 y[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int k = e == 0 ? idx : H - idx;
+      float yr = 0.f, yi = 0.f;
+      for (int b = 0; b < a.bands.count; ++b) {
+        const int hb = a.bands.size[b] >> 1;
+        if (k >= a.bands.lo[b] && k <= hb) {
+          const float2 x = real_bin(base + a.bands.offset[b] + row * hb, hb, k);
+          yr += x.x * a.bands.scale[b];
+          yi += x.y * a.bands.scale[b];
+        }
+      }
+      y[e] = make_float2(yr, (k == 0 || k == H) ? 0.f : yi);
+    }
+    packed_inverse_input(y[0], y[1], idx, H, re, im);
   } else {
     // kLoadHalfPk: Y[0 .. H] stored (rows of src_n = H + 1), transform length H = a.n
     const int H = a.n;
@@ -239,7 +274,8 @@ int dispatch(int radix, int load, int store, F&& f) {
       case kLoadBand: return with_store(r, IC<kLoadBand>{});
       case kLoadHalf: return with_store(r, IC<kLoadHalf>{});
       case kLoadBandPk: return with_store(r, IC<kLoadBandPk>{});
-      default: return with_store(r, IC<kLoadHalfPk>{});
+      case kLoadHalfPk: return with_store(r, IC<kLoadHalfPk>{});
+      default: return with_store(r, IC<kLoadMergePk>{});
     }
   };
   switch (radix) {
@@ -262,6 +298,7 @@ struct Xform {
   void* dst;
   float2* w0;          // ping-pong scratch for the passes in between (batch * n each)
   float2* w1;
+  const BandTable* bands = nullptr;   // kLoadMergePk
 };
 
 inline int plan_radices(int n, int* radix) {   // n = power of two >= 2; returns the pass count
@@ -293,6 +330,7 @@ int run_xform(const Xform& x, Launch&& launch) {
     a.src_n = x.src_n;
     a.lo = x.lo;
     a.scale = x.scale;
+    if (i == 0 && x.bands != nullptr) a.bands = *x.bands; else a.bands.count = 0;
     const int rc = launch(radix[i], i == 0 ? x.load : static_cast<int>(kLoadComplex),
                           last ? x.store : static_cast<int>(kStoreComplex), a);
     if (rc != 0) return rc;
@@ -409,6 +447,45 @@ int recompose_packed(const float* const* bands, const int* sizes, int nbands, in
   Xform inv;
   inv.n = D / 2; inv.batch = batch; inv.load = kLoadHalfPk; inv.src = acc; inv.src_n = D / 2 + 1;
   inv.lo = 0; inv.scale = 1.f; inv.store = kStoreConj; inv.dst = out; inv.w0 = w0; inv.w1 = w1;
+  return run_xform(inv, launch);
+}
+
+// merge without accumulation passes: every band's packed forward transform is kept (in
+// `spectra`, batch * sum(S_b / 2) float2 <= batch * D when the sizes are distinct powers of
+// two) and the inverse transform gathers its input from all of them while loading.
+// Returns -2 when the table or the buffer cannot hold the bands (caller falls back).
+template <class Launch>
+int recompose_merged(const float* const* bands, const int* sizes, int nbands, int batch, int D,
+                     float* out, float2* spectra, float2* w0, float2* w1, Launch&& launch) {
+  if (nbands > kMaxBands) return -2;
+  long long total = 0;
+  int smin = sizes[0];
+  for (int i = 0; i < nbands; ++i) {
+    total += sizes[i] / 2;
+    smin = sizes[i] < smin ? sizes[i] : smin;
+  }
+  if (total > D) return -2;
+  BandTable t;
+  t.count = nbands;
+  long long off = 0;
+  for (int i = 0; i < nbands; ++i) {
+    const int S = sizes[i];
+    Xform f;
+    f.n = S / 2; f.batch = batch; f.load = kLoadComplex; f.src = bands[i]; f.src_n = S / 2;
+    f.lo = 0; f.scale = 1.f; f.store = kStoreComplex; f.dst = spectra + off;
+    f.w0 = w0; f.w1 = w1;
+    const int rc = run_xform(f, launch);
+    if (rc != 0) return rc;
+    t.size[i] = S;
+    t.lo[i] = (S == smin) ? 0 : (S / 2 + 1) / 2;
+    t.scale[i] = 1.0f / (sqrtf(static_cast<float>(S)) * sqrtf(static_cast<float>(D)));
+    t.offset[i] = off;
+    off += static_cast<long long>(batch) * (S / 2);
+  }
+  Xform inv;
+  inv.n = D / 2; inv.batch = batch; inv.load = kLoadMergePk; inv.src = spectra; inv.src_n = 0;
+  inv.lo = 0; inv.scale = 1.f; inv.store = kStoreConj; inv.dst = out; inv.w0 = w0; inv.w1 = w1;
+  inv.bands = &t;
   return run_xform(inv, launch);
 }
 

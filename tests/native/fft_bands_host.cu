@@ -1,7 +1,9 @@
 // CPU harness for csrc/fft_passes.cuh: runs the band split and merge of fft_bands.cu -- the same
 // pass bodies, pass plan and transform sequences, a loop over butterflies standing in for each
 // kernel launch -- on float32 rows read from a file.
-//   usage: fft_bands_host <in.bin> <out.bin> <batch> <n> <min_size> [packed = 1]
+//   usage: fft_bands_host <in.bin> <out.bin> <batch> <n> <min_size> [mode = 2]
+//   mode 0: full-length complex transforms, 1: real-input packing with accumulation passes,
+//   2 (what the library runs): real-input packing, merge gathered by the inverse loader
 //   out.bin = the bands in ascending size, (batch, size) float32 each, then the (batch, n)
 //   recomposition of those bands.  tests/test_abi.py compares both with the oracle.
 #include <cstdio>
@@ -14,7 +16,8 @@ using namespace msb::fftb;
 
 int main(int argc, char** argv) {
   if (argc != 6 && argc != 7) return 2;
-  const bool packed = argc == 7 ? std::atoi(argv[6]) != 0 : true;
+  const int mode = argc == 7 ? std::atoi(argv[6]) : 2;
+  const bool packed = mode != 0;
   const int batch = std::atoi(argv[3]), n = std::atoi(argv[4]), min_size = std::atoi(argv[5]);
   std::vector<float> x(static_cast<size_t>(batch) * n);
   FILE* fi = std::fopen(argv[1], "rb");
@@ -54,7 +57,14 @@ int main(int argc, char** argv) {
                           w1.data(), launch)) != 0)
     return 4;
   std::vector<float> y(bn);
-  if ((packed ? recompose_packed(band_ptr.data(), sizes.data(), static_cast<int>(sizes.size()),
+  int rc_merge = -2;
+  if (mode == 2)
+    rc_merge = recompose_merged(band_ptr.data(), sizes.data(), static_cast<int>(sizes.size()),
+                                batch, n, y.data(), coef.data(), w0.data(), w1.data(), launch);
+  if (rc_merge != 0 && rc_merge != -2) return 7;
+  std::fprintf(stderr, "merge path: %s\n", rc_merge == 0 ? "gathered" : "accumulated");
+  if (rc_merge == -2 &&
+      (packed ? recompose_packed(band_ptr.data(), sizes.data(), static_cast<int>(sizes.size()),
                                  batch, n, y.data(), acc.data(), w0.data(), w1.data(), launch,
                                  accum_pk)
               : recompose(band_ptr.data(), sizes.data(), static_cast<int>(sizes.size()), batch, n,

@@ -63,7 +63,7 @@ def test_multiscale_representation_matches_golden(golden):
     assert RawAudio.from_audio(x, 22050).to_audio().shape == (2, 8192)
 
 
-@pytest.mark.parametrize("knob", ["MSB_FFT_STAGED=0", "MSB_FFT_PACKED=0", "MSB_FFT_LEGACY=1"])
+@pytest.mark.parametrize("knob", ["MSB_FFT_STAGED=0", "MSB_FFT_MERGE_GATHER=0", "MSB_FFT_PACKED=0", "MSB_FFT_LEGACY=1"])
 def test_pass_variants_agree(monkeypatch, knob):
     """The library reads its knobs per call: the first radix-16 pass with direct stores
     (MSB_FFT_STAGED=0) is bit-identical to the shared-memory staged one; full-length complex

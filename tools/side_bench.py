@@ -14,7 +14,7 @@ try:
     PEAK_HBM = float(PEAK_HBM.get("hbm_gbps", PEAK_HBM.get("hbm_gbs", 6536.7))) * 1e9
 except Exception:
     PEAK_HBM = 6536.7e9
-KNOBS = ("MSB_A2M_RADIX4", "MSB_FFT_LEGACY", "MSB_FFT_STAGED", "MSB_FFT_PACKED")
+KNOBS = ("MSB_A2M_RADIX4", "MSB_FFT_LEGACY", "MSB_FFT_STAGED", "MSB_FFT_PACKED", "MSB_FFT_MERGE_GATHER")
 
 
 def timeit(fn, n=20, warm=3):
@@ -62,6 +62,7 @@ def run(knobs):
 
 # the library reads the knobs per call: default (new kernels), then the A/B settings
 run({})
+run({"MSB_FFT_MERGE_GATHER": "0"})
 run({"MSB_FFT_PACKED": "0"})
 run({"MSB_FFT_STAGED": "0"})
 run({"MSB_A2M_RADIX4": "1", "MSB_FFT_LEGACY": "1"})
