@@ -17,11 +17,14 @@ struct CropArgs {
   int channels, len;
 };
 
-// grid (ceil(len / 256), channels, B)
+// grid (ceil(channels * len / 256), B): (channel, time) flattened so that short crops of many
+// channels (32 log-mel frames x 128 bins) still fill their CTAs
 __global__ void __launch_bounds__(256) gather_crops_kernel(const CropArgs a) {
-  const int b = blockIdx.z, c = blockIdx.y;
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= a.len) return;
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.channels * a.len) return;
+  const int c = i / a.len;
+  const int t = i - c * a.len;
   const long long origin = __ldg(a.plan + 3 * b);
   const long long pitch = __ldg(a.plan + 3 * b + 1);
   const long long valid = __ldg(a.plan + 3 * b + 2);
@@ -38,11 +41,11 @@ extern "C" {
 ms_status ms_gather_crops(const float* store, const long long* plan, float* out, int batch,
                           int channels, int len, void* stream) {
   if (store == nullptr || plan == nullptr || out == nullptr || batch <= 0 || channels <= 0 ||
-      len <= 0 || channels > 65535 || batch > 65535)
+      len <= 0 || batch > 65535 || static_cast<long long>(channels) * len > 0x7fffffffLL)
     return MS_ERR_INVALID;
   CropArgs a;
   a.store = store; a.plan = plan; a.out = out; a.channels = channels; a.len = len;
-  const dim3 grid((len + 255) / 256, channels, batch);
+  const dim3 grid((channels * len + 255) / 256, batch);
   gather_crops_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return after_launch("gather_crops_kernel");
 }

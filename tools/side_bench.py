@@ -60,6 +60,30 @@ def run(knobs):
         del bands, x
 
 
+def feed_rows():
+    """one training batch from the resident stores (host-side crop drawing +
+    plan upload + two ms_gather_crops launches), and the gather alone at a bandwidth-sized batch."""
+    import numpy as np
+    from music_synthesis_b200.data import DeviceAudioStore, batch_stream
+    rs = np.random.RandomState(0)
+    chunks = [(rs.random_sample(661500) * 2 - 1).astype(np.float32) for _ in range(8)]   # 8 x 30 s
+    store = DeviceAudioStore(chunks)
+    spec = {"audio": (8192, 1), "spectrogram": (32, 128)}
+    for B in (32, 4096):
+        stream = batch_stream(store, B, spec, seed=0)
+        t = timeit(lambda: next(stream), n=20)
+        nbytes = 2 * 4 * B * (8192 + 128 * 32)
+        print(json.dumps({"row": "f3 data feed: batch_stream next()", "workload": "B=%d x (8192 samples + 128x32 log-mel)" % B,
+                          "us": round(t * 1e6, 2), "clips_per_s": B / t, "bound": "hbm",
+                          "achieved_GBs": nbytes / t / 1e9, "frac": nbytes / t / PEAK_HBM,
+                          "note": "includes the host-side crop drawing (python) and the plan upload"}))
+        picks, starts = np.zeros(B, dtype=np.int64), np.arange(B, dtype=np.int64) % 2000
+        t = timeit(lambda: store.gather(picks, starts, spec), n=20)
+        print(json.dumps({"row": "f3 data feed: gather only", "workload": "B=%d" % B, "us": round(t * 1e6, 2),
+                          "bound": "hbm", "achieved_GBs": nbytes / t / 1e9, "frac": nbytes / t / PEAK_HBM}))
+
+
+feed_rows()
 # the library reads the knobs per call: default (new kernels), then the A/B settings
 run({})
 run({"MSB_FFT_MERGE_GATHER": "0"})
