@@ -176,7 +176,7 @@ def main():
     import torch.distributed as dist
     from music_synthesis_b200 import _lib
     from music_synthesis_b200.generator.full import MelGanGenerator
-    from oracle import restate, synth   # seeded synthetic inputs + cpu_baseline leg only
+    from music_synthesis_b200.experiment.init import weights_init
 
     if args.warmup < 3:
         args.warmup = 3
@@ -188,16 +188,20 @@ def main():
 
     clips = args.clips
     # ---- model + synthetic inputs (each rank: its own contiguous shard of clips)
-    sd = restate.melgan_generator_state(0)
+    # random-init weights by the reference's own contract (experiment/init.py: N(0, 0.02) weights,
+    # zero biases); nothing on this arm touches oracle/ (only cpu_baseline() below does)
+    torch.manual_seed(0)
     gen = MelGanGenerator(FRAMES, MELS).eval()
-    gen.load_state_dict(sd)
+    gen.apply(weights_init)
     gen = gen.to(dev)
     # weak scaling: the global synthetic batch has clips*world clips; this rank's contiguous
     # shard (no data-path collective) is regenerated locally from its own seed
     from music_synthesis_b200.sharding import clip_shard
     lo, hi = clip_shard(clips * world, rank, world)
     assert hi - lo == clips
-    x_host = synth.mel_features(1000 + rank, clips, FRAMES).pin_memory()
+    import numpy as np
+    x_host = torch.from_numpy(np.random.RandomState(1000 + rank).standard_normal(
+        (clips, MELS, FRAMES)).astype(np.float32)).pin_memory()
     x_dev = x_host.to(dev, non_blocking=True)
     y_host = torch.empty((clips, 1, 256 * FRAMES), dtype=torch.float32).pin_memory()
     samples_per_step = clips * 256 * FRAMES

@@ -39,3 +39,23 @@ def test_b200_arm_fails_loudly_without_a_gpu():
                        timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert not any(l.startswith("{") for l in r.stdout.splitlines())
+
+
+def test_only_the_cpu_baseline_leg_of_bench_touches_the_oracle():
+    """bench.py may execute oracle/ only as the reported CPU baseline (`cpu_port`, shared by the
+    cpu_baseline key and the `--impl reference` arm): no other function imports it."""
+    import ast
+
+    def oracle_imports(node):
+        for n in ast.walk(node):
+            if isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle":
+                yield n
+            if isinstance(n, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in n.names):
+                yield n
+
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    owners = set()
+    for top in tree.body:
+        if list(oracle_imports(top)):
+            owners.add(getattr(top, "name", "<module level>"))
+    assert owners == {"cpu_port"}, owners
