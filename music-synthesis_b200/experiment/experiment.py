@@ -26,39 +26,32 @@ from ..train.optim import Adam
 from .init import weights_init
 
 
+def _required(name):
+    def getter(self):
+        raise NotImplementedError(name)
+    return property(getter, doc="experiments must provide `%s`" % name)
+
+
 class BaseGanExperiment(object):
-    @property
-    def generator(self):
-        raise NotImplementedError()
-
-    @property
-    def discriminator(self):
-        raise NotImplementedError()
-
-    @property
-    def generator_trainer(self):
-        raise NotImplementedError()
-
-    @property
-    def discriminator_trainer(self):
-        raise NotImplementedError()
-
-    @property
-    def feature_spec(self):
-        raise NotImplementedError()
+    """What the training loop and the reporting code of the reference ask of an experiment."""
+    generator = _required("generator")
+    discriminator = _required("discriminator")
+    generator_trainer = _required("generator_trainer")
+    discriminator_trainer = _required("discriminator_trainer")
+    feature_spec = _required("feature_spec")
 
     def from_audio(self, samples, sr):
-        raise NotImplementedError()
+        raise NotImplementedError("from_audio")
 
     def audio_representation(self, data, sr):
-        raise NotImplementedError()
+        raise NotImplementedError("audio_representation")
 
     def preprocess_batch(self, batch):
         return batch
 
     def to(self, device):
-        self.generator.to(device)
-        self.discriminator.to(device)
+        for net in (self.generator, self.discriminator):
+            net.to(device)
         return self
 
 
@@ -135,33 +128,39 @@ class Experiment(BaseGanExperiment):
         return cls.__name__.lower().replace('experiment', '')
 
     @classmethod
+    def _path(cls, role, prefix):
+        """trained_models/{prefix}{name}_{gen|disc}.dat -- the reference's file names"""
+        return '%s/%s%s_%s.dat' % (cls.CHECKPOINT_DIR, prefix, cls._name(), role)
+
+    @classmethod
     def _gen_name(cls, prefix=''):
-        return f'{cls.CHECKPOINT_DIR}/{prefix}{cls._name()}_gen.dat'
+        return cls._path('gen', prefix)
 
     @classmethod
     def _disc_name(cls, prefix=''):
-        return f'{cls.CHECKPOINT_DIR}/{prefix}{cls._name()}_disc.dat'
+        return cls._path('disc', prefix)
+
+    def _networks(self):
+        return (('gen', self.generator), ('disc', self.discriminator))
 
     @classmethod
     def load_generator_weights(cls, generator, prefix=''):
-        generator.load_state_dict(torch.load(cls._gen_name(prefix), map_location='cpu'))
+        generator.load_state_dict(torch.load(cls._path('gen', prefix), map_location='cpu'))
         return generator
 
-    @staticmethod
-    def _host_state(module):
-        # parameters are views of one flat buffer: clone, or every file would carry all of it
-        return {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}
-
     def checkpoint(self, prefix=''):
+        """plain state-dict pickles, as the reference writes them.  Parameters are views of one
+        flat optimiser buffer: they are cloned, or every file would carry all of it."""
         os.makedirs(self.CHECKPOINT_DIR, exist_ok=True)
-        torch.save(self._host_state(self.generator), self._gen_name(prefix))
-        torch.save(self._host_state(self.discriminator), self._disc_name(prefix))
+        for role, net in self._networks():
+            host = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+            torch.save(host, self._path(role, prefix))
 
     def resume(self, prefix=''):
-        self.generator.load_state_dict(torch.load(self._gen_name(prefix), map_location='cpu'))
-        self.discriminator.load_state_dict(torch.load(self._disc_name(prefix), map_location='cpu'))
+        for role, net in self._networks():
+            net.load_state_dict(torch.load(self._path(role, prefix), map_location='cpu'))
         for optim in (self.__g_optim, self.__d_optim):
-            if optim is not None:
+            if optim is not None:        # the kernels cache packed weights by tensor version
                 optim.mark_updated()
 
     # -- the reference's accessors -----------------------------------------------------------

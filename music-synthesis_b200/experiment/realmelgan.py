@@ -27,10 +27,7 @@ import torch.nn.functional as F
 from .. import autograd as ag
 from .. import ops
 from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
-from ..audio.representation import RawAudio
-from ..loss.loss import _Acc, L1, hinge_generator_loss, mel_gan_disc_loss
-from .experiment import Experiment
-from .init import weights_init
+from ..loss.loss import _Acc, L1, hinge_generator_loss
 
 
 def _weight_norm(m):
@@ -343,26 +340,10 @@ def mel_gan_gen_loss(real_features, fake_features, real_judgements, fake_judgeme
     return acc.value()
 
 
-class RealMelGanExperiment(Experiment):
-    """experiment/realmelgan.py:219-254: official MelGAN generator + three independent
-    NLayerDiscriminators, hinge sub-losses, this module's feature-matching weighting."""
 
-    def __init__(self, **kw):
-        n_mels, size, samplerate, total_samples = 128, 32, 22050, 8192
-        super().__init__(
-            Generator(n_mels, size, n_residual_layers=3),
-            Discriminator(num_D=3, ndf=16, n_layers=4, downsampling_factor=4),
-            learning_rate=1e-4,
-            feature_size=size,
-            audio_repr_class=RawAudio,
-            generator_loss=mel_gan_gen_loss,
-            discriminator_loss=mel_gan_disc_loss,
-            g_init=weights_init,
-            d_init=weights_init,
-            feature_funcs={'audio': ('DeviceAudioStore.audio', (samplerate,)),
-                           'spectrogram': ('Audio2Mel', (samplerate,))},
-            total_samples=total_samples,
-            feature_channels=n_mels,
-            samplerate=samplerate,
-            inference_sequence_factor=4,
-            **kw)
+def __getattr__(name):
+    # `RealMelGanExperiment` lives with the other wirings (wirings.py imports this module)
+    if name == "RealMelGanExperiment":
+        from .wirings import RealMelGanExperiment
+        return RealMelGanExperiment
+    raise AttributeError(name)
