@@ -206,3 +206,20 @@ def test_fft_band_passes_on_host(tmp_path, batch, n, min_size, packed):
     want = restate.fft_frequency_recompose(ref, n)[:, 0].numpy()
     got = out[o:].reshape(batch, n)
     assert np.linalg.norm(got - want) <= 3e-6 * np.linalg.norm(want)
+
+
+def test_convtranspose_column_order_is_a_bijection(tmp_path):
+    """csrc/conv_gemm.cuh::convt_col (GEMM column of (phase, channel) in the polyphase
+    ConvTranspose) and its two inverses, checked on the host for every stride / channel count
+    the kernels accept: tests/native/convt_col_host.cu."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "convt_col_host")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets",
+                    "-I", os.path.join(ROOT, "music-synthesis_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "native", "convt_col_host.cu")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout)
