@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libmsb200.so")
 SOURCES = ["runtime.cu", "conv_gemm.cu", "layout.cu", "generator.cu", "audio2mel.cu",
-           "resstack.cu", "microbench.cu", "conv_gemm2.cu", "direct_conv.cu", "losses.cu", "fft_bands.cu",
+           "resstack.cu", "conv_gemm2.cu", "direct_conv.cu", "losses.cu", "fft_bands.cu",
            "wgrad.cu", "backward.cu", "datafeed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -59,6 +59,23 @@ def build_library(force=False, verbose=False):
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs)
     return LIB
+
+
+def build_debug_library(force=False):
+    """tools/native/libmsb200_dbg.so: the measurement kernels of tools/microbench.py (not part of
+    the product library)."""
+    root = os.path.join(os.path.dirname(CSRC), "..", "tools", "native")
+    src = os.path.join(root, "microbench.cu")
+    lib = os.path.join(root, "libmsb200_dbg.so")
+    deps = [src, os.path.join(CSRC, "ptx.cuh"), os.path.join(CSRC, "runtime.cuh"),
+            os.path.join(CSRC, "runtime.cu")]
+    if force or _stale(lib, deps):
+        r = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-shared", "-o", lib, src,
+                                                     os.path.join(CSRC, "runtime.cu")],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed (debug library):\n%s%s" % (r.stdout, r.stderr))
+    return lib
 
 
 if __name__ == "__main__":

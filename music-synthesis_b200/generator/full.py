@@ -115,6 +115,9 @@ class MelGanGenerator(nn.Module):
                 out[lo:hi].copy_(ybuf[k][:n], non_blocking=True)
                 y_free[k] = s_out.record_event()
         comp.wait_stream(s_out)
+        # host-to-host contract: the caller may read `out` (e.g. `.numpy()`) as soon as this
+        # returns, so block the host on the last device-to-host copy
+        s_out.synchronize()
         return out
 
     def _forward_train(self, x):

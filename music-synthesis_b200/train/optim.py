@@ -35,6 +35,7 @@ class Adam:
         for p in self.params:
             offs.append(total)
             total += (p.numel() + 3) // 4 * 4
+        self.offs = offs
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -46,23 +47,48 @@ class Adam:
                 p.data = view
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
         self.numel = n
+        self.sync_parameters()
+
+    def sync_parameters(self):
+        """data-parallel replicas must start from the same weights (`weights_init` is random and
+        runs on every rank; ranks may resume from different files): broadcast rank 0's flat
+        parameter and moment buffers.  Called at construction and after load_state_dict."""
+        if self.world_size() > 1:
+            for t in (self.flat, self.exp_avg, self.exp_avg_sq):
+                dist.broadcast(t, src=dist.get_global_rank(self.process_group, 0)
+                               if self.process_group is not None else 0, group=self.process_group)
+            dist.broadcast(self.step_dev, src=dist.get_global_rank(self.process_group, 0)
+                           if self.process_group is not None else 0, group=self.process_group)
+            self.mark_updated()
+
+    def _grad_view(self, i):
+        p, o = self.params[i], self.offs[i]
+        return self.flat_grad[o:o + p.numel()].view_as(p)
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
-        for p in self.params:          # someone may have dropped the views (p.grad = None)
-            if p.grad is None or p.grad.data_ptr() < self.flat_grad.data_ptr() or \
-                    p.grad.data_ptr() >= self.flat_grad.data_ptr() + self.flat_grad.numel() * 4:
-                self._rebind()
-                break
+        for i, p in enumerate(self.params):
+            # someone may have dropped the views (module.zero_grad(), p.grad = None): the buffer
+            # was just zeroed, so re-point without copying anything back
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * self.offs[i]:
+                p.grad = self._grad_view(i)
 
-    def _rebind(self):
-        o = 0
-        for p in self.params:
-            g = self.flat_grad[o:o + p.numel()].view_as(p)
-            if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
-                g.copy_(p.grad)
-            p.grad = g
-            o += (p.numel() + 3) // 4 * 4
+    def _check_views(self):
+        """step()/unscale_() read the flat buffers: a gradient that autograd allocated afresh
+        (the view was dropped after zero_grad) is copied in; a parameter that no longer lives in
+        the flat buffer (`.to()`, `.half()` after construction) cannot be stepped -> raise."""
+        base_g, base_p = self.flat_grad.data_ptr(), self.flat.data_ptr()
+        for i, p in enumerate(self.params):
+            if p.data_ptr() != base_p + 4 * self.offs[i]:
+                raise RuntimeError(
+                    "parameter %d was moved out of the optimizer's flat buffer (module.to()/"
+                    ".half() after constructing Adam); rebuild the optimizer" % i)
+            if p.grad is None:
+                p.grad = self._grad_view(i)          # no gradient this step: stays zero
+            elif p.grad.data_ptr() != base_g + 4 * self.offs[i]:
+                view = self._grad_view(i)
+                view.copy_(p.grad)
+                p.grad = view
 
     def world_size(self):
         if self.distributed and dist.is_available() and dist.is_initialized():
@@ -78,6 +104,7 @@ class Adam:
         """loss-scaled backward: reduce over ranks, multiply the flat gradient by the device
         scalar `inv_scale_dev` in place and record whether any element is non-finite; the next
         step() is then skipped on the device (no host round trip)"""
+        self._check_views()
         if self.world_size() > 1:
             self.all_reduce_grads()
         grad_ops.grad_unscale_check(self.flat_grad, inv_scale_dev, self.found_inf)
@@ -86,8 +113,10 @@ class Adam:
 
     def step(self):
         world = self.world_size()
-        if world > 1 and not getattr(self, "_reduced", False):
-            self.all_reduce_grads()
+        if not getattr(self, "_reduced", False):
+            self._check_views()
+            if world > 1:
+                self.all_reduce_grads()
         self._reduced = False
         self.step_count += 1
         grad_ops.adam_step_dev(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr,
@@ -111,3 +140,4 @@ class Adam:
         self.step_dev.fill_(self.step_count)
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.sync_parameters()

@@ -151,11 +151,10 @@ def test_generate_host_pipeline_matches_forward():
     x = synth.mel_features(10, 7, 12)
     with torch.no_grad():
         ref = m(x.cuda()).cpu()
+    # no synchronize here: generate() is host-to-host, its result must be readable on return
     got = m.generate(x.pin_memory(), chunk_clips=3)
-    torch.cuda.synchronize()
     assert got.shape == ref.shape and torch.equal(got, ref)
     got2 = m.generate(x, chunk_clips=64)          # pageable input, single chunk
-    torch.cuda.synchronize()
     assert torch.equal(got2, ref)
 
 

@@ -2,8 +2,8 @@
 // built from (not part of the public ABI; used by tools/microbench.py).
 #include <cuda_runtime.h>
 
-#include "ptx.cuh"
-#include "runtime.cuh"
+#include "../../music-synthesis_b200/csrc/ptx.cuh"
+#include "../../music-synthesis_b200/csrc/runtime.cuh"
 
 namespace msb {
 
@@ -169,6 +169,44 @@ __global__ void __launch_bounds__(128, 1) microbench_kernel(long long* out) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+
+// TMEM read bandwidth: W warps (W in {4,8,16}; warp w reads lane quarter w%4) each issue `iters`
+// tcgen05.ld of 32 lanes x NCOL fp32 columns back to back (one wait per 4 loads).
+// out[0] = cycles from the CTA barrier before to the barrier after; bytes = W*iters*128*NCOL.
+template <int NCOL>
+__global__ void __launch_bounds__(512, 1) tmem_bw_kernel(long long* out, int warps, int iters) {
+  __shared__ uint32_t tmem_slot;
+  __shared__ long long tstart;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) tstart = clock64();
+  __syncthreads();
+  if (warp < warps) {
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t col = static_cast<uint32_t>(((i + u) * NCOL + (warp >> 2) * 64) & (511 & ~(NCOL - 1)));
+        if (NCOL == 16) { uint32_t v[16]; tmem_ld16(base + col, v); acc ^= v[0] ^ v[15]; }
+        else if (NCOL == 32) { uint32_t v[32]; tmem_ld32(base + col, v); acc ^= v[0] ^ v[31]; }
+        else { uint32_t v[64]; tmem_ld64(base + col, v); acc ^= v[0] ^ v[63]; }
+      }
+      tmem_ld_wait();
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { out[0] = clock64() - tstart; out[1] = acc == 0x12345u; }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 }  // namespace msb
 
 extern "C" int ms_debug_microbench(long long* dev_out, void* stream) {
@@ -176,4 +214,12 @@ extern "C" int ms_debug_microbench(long long* dev_out, void* stream) {
   cudaFuncSetAttribute(msb::microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   msb::microbench_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(dev_out);
   return msb::after_launch("microbench_kernel");
+}
+
+extern "C" int ms_debug_tmem_bw(long long* dev_out, int ncol, int warps, int iters, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ncol == 16) msb::tmem_bw_kernel<16><<<1, 512, 0, st>>>(dev_out, warps, iters);
+  else if (ncol == 32) msb::tmem_bw_kernel<32><<<1, 512, 0, st>>>(dev_out, warps, iters);
+  else msb::tmem_bw_kernel<64><<<1, 512, 0, st>>>(dev_out, warps, iters);
+  return msb::after_launch("tmem_bw_kernel");
 }
