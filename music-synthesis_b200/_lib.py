@@ -9,7 +9,9 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_ui
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmsb200.so")
+# MSB_LIB_PATH: load another build of the same ABI (e.g. the clock-traced debug build of
+# tools/stack_trace.py); there is still no fallback -- a missing file raises
+LIB_PATH = os.environ.get("MSB_LIB_PATH") or os.path.join(_HERE, "csrc", "libmsb200.so")
 
 MS_CONV, MS_CONVT = 0, 1
 MS_F16, MS_BF16 = 0, 1

@@ -21,6 +21,7 @@
 // MMA and epilogue overlap at M-block granularity: conv l+1 starts on M-block 0 while
 // the epilogue of conv l is still draining M-block 1.
 #include <cstdlib>
+#include <type_traits>
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -82,7 +83,13 @@ struct StackGeom {
   static constexpr int TAP_BYTES_P = TAP_BYTES / 2;
   static constexpr int NSLOT_P = (96 * 1024 / TAP_BYTES_P) < 18 ? (96 * 1024 / TAP_BYTES_P) : 18;
   static constexpr int MONO_BYTES = 1024;        // [7][32] fp32 tail-conv weights
-  static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES;
+  // fused-tail partial sums P[2 parts][7 taps][R rows] (C == 32 only): a region of their own,
+  // so that the X buffer is free during the last conv for the NEXT tile's operand
+  static constexpr int P_BYTES = (C == 32) ? 14 * R * 4 : 0;
+  // fold the next tile's prologue into the last conv's epilogue (needs COLS + 2 x 16 live
+  // registers per row: fits the 96-register budget of 18-warp CTAs only at 16 columns per thread)
+  static constexpr bool MERGE_PROLOGUE = (C == 32);
+  static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES + P_BYTES;
 };
 
 __device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
@@ -115,6 +122,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
   const uint32_t sW = sY + G::ACT_BYTES;
   float* sMono = reinterpret_cast<float*>(smem + kStackHeader + 2 * G::ACT_BYTES +
                                           G::NSLOT * G::TAP_BYTES);
+  float* sP = sMono + G::MONO_BYTES / 4;
   const bool mono = (C == 32) && !PAIR && (p.mono_out != nullptr);
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0);
@@ -223,9 +231,9 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
                 for (int k16 = 0; k16 < C / 16; ++k16) {
                   const uint64_t a_k = ad + static_cast<uint64_t>(k16 * (2 * R * 16 / 16));
                   const uint64_t b_k = bd + static_cast<uint64_t>(k16 * (2 * NB * 16 / 16));
-                  const uint32_t accum = (t == 0 && k16 == 0) ? 0u : 1u;
-                  if (PAIR) umma2_f16_ss(dst, a_k, b_k, idesc, accum);
-                  else umma_f16_ss(dst, a_k, b_k, idesc, accum);
+                  // always accumulate: the epilogue pre-loaded the accumulator with the bias
+                  if (PAIR) umma2_f16_ss(dst, a_k, b_k, idesc, 1u);
+                  else umma_f16_ss(dst, a_k, b_k, idesc, 1u);
                 }
               }
             }
@@ -246,9 +254,11 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
           // (act_ready(i)): tap +d of part i-1's last M-block (it reads into part i) completes
           // part i-1; then every tap of part i except tap +d of ITS last M-block.
           for (int part = 0; part < NP; ++part) {
+            MSB_TRACE(nconv * 16 + part * 4 + 0);
             if (PAIR) mbar_wait_cluster(act_ready(part), ready_par);
             else mbar_wait(act_ready(part), ready_par);
             tc_fence_after();
+            MSB_TRACE(nconv * 16 + part * 4 + 1);
             const int m0 = part * HB, m1 = m0 + HB;
             if (part > 0) {
               issue(2, m0 - 1, m0);
@@ -273,14 +283,24 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
     }
   } else {
     // ====================== prologue / epilogue warps ======================
+    // Thread = one row (TMEM lane) x COLS channels of IT M-blocks per pipeline part.  The
+    // epilogue is instruction-issue bound, so everything that is not arithmetic on the
+    // elements is hoisted: the conv index is a compile-time parameter of the loop body
+    // (no per-element branches), the bias is not added here at all -- the accumulator
+    // columns are PRE-LOADED with the next conv's bias (one tcgen05.st per 16 columns; every
+    // MMA accumulates), and addresses are a per-thread base + compile-time offsets.
     const int e = warp - 2;            // 0 .. EW-1
     const int q = warp & 3;            // TMEM lane quarter accessible to this warp
     const int part = (e >> 2) % G::PARTS;    // which slice of the channels
     const int ms = (e >> 2) / G::PARTS;      // which M-blocks of a half
     constexpr int COLS = C / G::PARTS; // channels per thread
     constexpr int NG = COLS / 16;      // 16-column groups per thread
+    constexpr int IT = HB / G::MSPLIT; // M-blocks per thread per pipeline part
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int chunk0 = part * (COLS / 8);
+    const int row0 = q * 32 + lane;                                     // row within an M-block
+    const uint32_t tm0 = tmem_base + lane_off + static_cast<uint32_t>(part * COLS);
+    const uint32_t so0 = static_cast<uint32_t>((chunk0 * R + row0) * 16);   // offset in sX / sY
     uint32_t nconv = 0;
     // one arrival per warp on act_ready (local, or on the leader's barrier in pair mode)
     auto arrive_act = [&](int h) {
@@ -290,74 +310,110 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         else mbar_arrive_remote(act_ready(h), 0);
       }
     };
-    for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
-      const bool live = tile < p.total_tiles;      // false: rank 1's dummy tile of an odd pair
-      const int b = live ? tile / p.tiles_per_clip : 0;
-      // a dummy tile sits entirely before the clip: every row is masked to zero
-      const int t0 = live ? (tile % p.tiles_per_clip) * p.V - p.halo : -2 * R;
-      const bool edge = (t0 < 0) || (t0 + R > p.L);                 // warp-uniform
-      // ---- prologue: x32 (global) -> TMEM residual stream + 16-bit operand in sX
-      if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2);
-      for (int h = 0; h < NP; ++h) {
-        for (int mb = h * HB + ms; mb < (h + 1) * HB; mb += G::MSPLIT) {
-          const int row = mb * 128 + q * 32 + lane;
-          const int t = t0 + row;
-          const bool inside = (t >= 0) && (t < p.L);
-          const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
-          const float* src =
-              p.x32 + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8;
-          const size_t cstride = static_cast<size_t>(p.L) * 8;   // floats per chunk
-          uint32_t v[COLS];
-          if (p.x16in != nullptr) {
-            const uint16_t* src16 =
-                p.x16in + ((static_cast<size_t>(b) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8;
+    // accumulator columns [ta, ta + COLS) <- bias of conv l (the MMAs of conv l accumulate)
+    auto store_bias = [&](int l, uint32_t ta) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + l * C + part * COLS);
 #pragma unroll
-            for (int c = 0; c < COLS / 8; ++c) {
-              uint4 q16 = make_uint4(0u, 0u, 0u, 0u);
-              if (inside) q16 = __ldg(reinterpret_cast<const uint4*>(src16 + c * cstride));
-              const uint32_t w16[4] = {q16.x, q16.y, q16.z, q16.w};
+      for (int g = 0; g < NG; ++g) {
+        uint32_t bv[16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f2;
-                if (BF) f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w16[j]));
-                else f2 = __half22float2(*reinterpret_cast<const __half2*>(&w16[j]));
-                v[c * 8 + 2 * j] = __float_as_uint(f2.x);
-                v[c * 8 + 2 * j + 1] = __float_as_uint(f2.y);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < COLS / 8; ++c) {
-              float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (inside) ld_global_nc_v8(src + c * cstride, a8);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[c * 8 + j] = __float_as_uint(a8[j]);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < COLS / 8; ++c) {
-            const uint32_t dst = sX + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
-            st_shared_v4(dst,
-                         pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), kOp),
-                         pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), kOp),
-                         pack2s(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]), kOp),
-                         pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), kOp));
-          }
-#pragma unroll
-          for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 t4 = __ldg(b4 + g * 4 + j4);
+          bv[j4 * 4 + 0] = __float_as_uint(t4.x); bv[j4 * 4 + 1] = __float_as_uint(t4.y);
+          bv[j4 * 4 + 2] = __float_as_uint(t4.z); bv[j4 * 4 + 3] = __float_as_uint(t4.w);
         }
-        tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before();
-        arrive_act(h);
+        tmem_st16p(ta + g * 16, bv);
+      }
+    };
+    // row (M-block mb, this thread's lane) of the tile with origin tt0 in clip tb: this thread's
+    // COLS channels as fp32 bit patterns (zeros outside the clip)
+    auto load_row = [&](int tb, int tt0, int mb, uint32_t* v) {
+      const int t = tt0 + mb * 128 + row0;
+      const bool inside = (t >= 0) && (t < p.L);
+      const size_t cstride = static_cast<size_t>(p.L) * 8;   // elements per channel chunk
+      const size_t off = ((static_cast<size_t>(tb) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8;
+      if (p.x16in != nullptr) {
+#pragma unroll
+        for (int c = 0; c < COLS / 8; ++c) {
+          uint4 q16 = make_uint4(0u, 0u, 0u, 0u);
+          if (inside) q16 = __ldg(reinterpret_cast<const uint4*>(p.x16in + off + c * cstride));
+          const uint32_t w16[4] = {q16.x, q16.y, q16.z, q16.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f2;
+            if (BF) f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w16[j]));
+            else f2 = __half22float2(*reinterpret_cast<const __half2*>(&w16[j]));
+            v[c * 8 + 2 * j] = __float_as_uint(f2.x);
+            v[c * 8 + 2 * j + 1] = __float_as_uint(f2.y);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < COLS / 8; ++c) {
+          float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (inside) ld_global_nc_v8(p.x32 + off + c * cstride, a8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[c * 8 + j] = __float_as_uint(a8[j]);
+        }
+      }
+    };
+    // ... -> 16-bit operand in sX, fp32 residual stream in TMEM, conv 0's bias in the accumulator
+    auto store_row = [&](int mb, const uint32_t* v) {
+      const uint32_t tx = tm0 + static_cast<uint32_t>(mb * 2 * C);
+#pragma unroll
+      for (int c = 0; c < COLS / 8; ++c) {
+        const uint32_t dst = sX + so0 + static_cast<uint32_t>((c * R + mb * 128) * 16);
+        st_shared_v4(dst,
+                     pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), kOp),
+                     pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), kOp),
+                     pack2s(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]), kOp),
+                     pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), kOp));
+      }
+#pragma unroll
+      for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+      store_bias(0, tx + C);
+    };
+    auto tile_origin = [&](int tl, int& tb, int& tt0) {
+      const bool lv = tl < p.total_tiles;          // false: rank 1's dummy tile of an odd pair
+      tb = lv ? tl / p.tiles_per_clip : 0;
+      // a dummy tile sits entirely before the clip: every row is masked to zero
+      tt0 = lv ? (tl % p.tiles_per_clip) * p.V - p.halo : -2 * R;
+    };
+    for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
+      const bool live = tile < p.total_tiles;
+      int b, t0;
+      tile_origin(tile, b, t0);
+      const bool edge = (t0 < 0) || (t0 + R > p.L);                 // warp-uniform
+      // the NEXT tile's prologue is folded into this tile's last conv epilogue (below): its
+      // global loads are issued before the wait for the last accumulator, its operand / stream /
+      // bias stores follow each row's output, so the MMA warp never idles between tiles
+      const bool has_next = G::MERGE_PROLOGUE && pair_has_work(tile + tile_stride);
+      int nb = 0, nt0 = 0;
+      if (has_next) tile_origin(tile + tile_stride, nb, nt0);
+      // ---- stand-alone prologue (first tile of this CTA only):
+      //      x32 (global) -> TMEM residual stream + 16-bit operand in sX
+      if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2);
+      if (tile == tile_first || !G::MERGE_PROLOGUE) {
+        for (int h = 0; h < NP; ++h) {
+#pragma unroll
+          for (int u = 0; u < IT; ++u) {
+            const int mb = h * HB + ms + u * G::MSPLIT;
+            uint32_t v[COLS];
+            load_row(b, t0, mb, v);
+            store_row(mb, v);
+          }
+          tmem_st_wait();
+          fence_proxy_async_smem();
+          tc_fence_before();
+          arrive_act(h);
+        }
       }
       if (warp == 2) MSB_TRACE(480 + (nconv / 6) * 2 + 1);
-      // ---- six convolutions
-      for (int l = 0; l < 6; ++l, ++nconv) {
-        const bool second = (l & 1) != 0;     // second conv of an atom: residual add
-        const bool last = (l == 5);
+      // ---- six convolutions: conv_epi<second conv of an atom, last conv of the stack>(l)
+      auto conv_epi = [&](auto second_t, auto last_t, const int l) {
+        constexpr bool second = decltype(second_t)::value;   // residual add
+        constexpr bool last = decltype(last_t)::value;
         const uint32_t dstbuf = second ? sX : sY;
-        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + l * C + part * COLS);
         if (l == 4) {
           // warm L2 with the next tile's input while this tile finishes
           const int ntile = tile + tile_stride;
@@ -365,7 +421,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
             const int nb = ntile / p.tiles_per_clip;
             const int nt0 = (ntile % p.tiles_per_clip) * p.V - p.halo;
             for (int mb = ms; mb < MB; mb += G::MSPLIT) {
-              const int t = nt0 + mb * 128 + q * 32 + lane;
+              const int t = nt0 + mb * 128 + row0;
               if (t >= 0 && t < p.L) {
 #pragma unroll
                 for (int c = 0; c < COLS / 8; ++c) {
@@ -378,114 +434,128 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         }
         for (int h = 0; h < NP; ++h) {
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 0);
+          uint32_t nx[last ? IT : 1][last ? COLS : 1];
+          if (last && has_next) {
+#pragma unroll
+            for (int u = 0; u < IT; ++u) load_row(nb, nt0, h * HB + ms + u * G::MSPLIT, nx[last ? u : 0]);
+          }
           mbar_wait(acc_full(h), nconv & 1u);
           tc_fence_after();
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 1);
-          for (int mb = h * HB + ms; mb < (h + 1) * HB; mb += G::MSPLIT) {
-            const int row = mb * 128 + q * 32 + lane;
+#pragma unroll
+          for (int u = 0; u < IT; ++u) {
+            const int mb = h * HB + ms + u * G::MSPLIT;
+            const int row = mb * 128 + row0;
             const int t = t0 + row;
-            const uint32_t tx = tmem_base + lane_off + static_cast<uint32_t>(mb * 2 * C + part * COLS);
+            const uint32_t tx = tm0 + static_cast<uint32_t>(mb * 2 * C);
             const uint32_t ta = tx + C;
-            uint32_t v[COLS];
+            const bool zero_row = edge && (t < 0 || t >= p.L);
+            // the last conv also carries the next tile's row in registers: it works through its
+            // columns 16 at a time to stay inside the register budget
+            constexpr int GS = last ? 16 : COLS;
 #pragma unroll
-            for (int g = 0; g < NG; ++g) tmem_ld16p(ta + g * 16, &v[g * 16]);
-            float f[COLS];
-            if (second) {
-              uint32_t xr[COLS];
+            for (int c0 = 0; c0 < COLS; c0 += GS) {
+              uint32_t v[GS];
 #pragma unroll
-              for (int g = 0; g < NG; ++g) tmem_ld16p(tx + g * 16, &xr[g * 16]);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j4 = 0; j4 < COLS / 4; ++j4) {
-                const float4 bv = __ldg(bias4 + j4);
-                f[j4 * 4 + 0] = __uint_as_float(xr[j4 * 4 + 0]) + leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
-                f[j4 * 4 + 1] = __uint_as_float(xr[j4 * 4 + 1]) + leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
-                f[j4 * 4 + 2] = __uint_as_float(xr[j4 * 4 + 2]) + leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
-                f[j4 * 4 + 3] = __uint_as_float(xr[j4 * 4 + 3]) + leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
-              }
-            } else {
-              tmem_ld_wait();
-#pragma unroll
-              for (int j4 = 0; j4 < COLS / 4; ++j4) {
-                const float4 bv = __ldg(bias4 + j4);
-                f[j4 * 4 + 0] = leaky02(__uint_as_float(v[j4 * 4 + 0]) + bv.x);
-                f[j4 * 4 + 1] = leaky02(__uint_as_float(v[j4 * 4 + 1]) + bv.y);
-                f[j4 * 4 + 2] = leaky02(__uint_as_float(v[j4 * 4 + 2]) + bv.z);
-                f[j4 * 4 + 3] = leaky02(__uint_as_float(v[j4 * 4 + 3]) + bv.w);
-              }
-            }
-            if (edge) {
-              if (t < 0 || t >= p.L) {
-#pragma unroll
-                for (int j = 0; j < COLS; ++j) f[j] = 0.f;
-              }
-            }
-            if (!last) {
+              for (int g = 0; g < GS / 16; ++g) tmem_ld16p(ta + c0 + g * 16, &v[g * 16]);
+              float f[GS];
               if (second) {
+                uint32_t xr[GS];
 #pragma unroll
-                for (int j = 0; j < COLS; ++j) v[j] = __float_as_uint(f[j]);
+                for (int g = 0; g < GS / 16; ++g) tmem_ld16p(tx + c0 + g * 16, &xr[g * 16]);
+                tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
+                for (int j = 0; j < GS; ++j)
+                  f[j] = __uint_as_float(xr[j]) + leaky02(__uint_as_float(v[j]));
+              } else {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < GS; ++j) f[j] = leaky02(__uint_as_float(v[j]));
               }
+              if (zero_row) {
 #pragma unroll
-              for (int c = 0; c < COLS / 8; ++c) {
-                const uint32_t dst = dstbuf + static_cast<uint32_t>(((chunk0 + c) * R + row) * 16);
-                st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], kOp),
-                             pack2s(f[c * 8 + 2], f[c * 8 + 3], kOp),
-                             pack2s(f[c * 8 + 4], f[c * 8 + 5], kOp),
-                             pack2s(f[c * 8 + 6], f[c * 8 + 7], kOp));
+                for (int j = 0; j < GS; ++j) f[j] = 0.f;
               }
-            } else if (mono) {
-              // fused tail, step 1: this thread's 16 channels of its row contribute
-              // 7 per-tap partial dot products; P[part][tap][row] lives in the X buffer
-              // (free during the last conv).
-              float pk[7];
+              if (!last) {
+                if (second) {
 #pragma unroll
-              for (int k = 0; k < 7; ++k) {
-                float a0 = 0.f, a1 = 0.f;
+                  for (int j = 0; j < GS; ++j) v[j] = __float_as_uint(f[j]);
 #pragma unroll
-                for (int j4 = 0; j4 < COLS / 4; ++j4) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(sMono + k * 32 + part * COLS + j4 * 4);
-                  a0 = fmaf(f[j4 * 4 + 0], w4.x, a0); a1 = fmaf(f[j4 * 4 + 1], w4.y, a1);
-                  a0 = fmaf(f[j4 * 4 + 2], w4.z, a0); a1 = fmaf(f[j4 * 4 + 3], w4.w, a1);
+                  for (int g = 0; g < GS / 16; ++g) tmem_st16p(tx + c0 + g * 16, &v[g * 16]);
                 }
-                pk[k] = a0 + a1;
-              }
-              float* P = reinterpret_cast<float*>(smem + kStackHeader) + (part * 7) * R + row;
 #pragma unroll
-              for (int k = 0; k < 7; ++k) P[k * R] = pk[k];
-            } else if (live && t >= 0 && t < p.L && row >= p.halo && row < R - p.halo) {
+                for (int c = 0; c < GS / 8; ++c) {
+                  const uint32_t dst =
+                      dstbuf + so0 + static_cast<uint32_t>(((c0 / 8 + c) * R + mb * 128) * 16);
+                  st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], kOp),
+                               pack2s(f[c * 8 + 2], f[c * 8 + 3], kOp),
+                               pack2s(f[c * 8 + 4], f[c * 8 + 5], kOp),
+                               pack2s(f[c * 8 + 6], f[c * 8 + 7], kOp));
+                }
+              } else if (mono) {
+                // fused tail, step 1 (C == 32: GS == COLS == 16): this thread's 16 channels of
+                // its row contribute 7 per-tap partial dot products, P[part][tap][row]
+                float pk[7];
 #pragma unroll
-              for (int c = 0; c < COLS / 8; ++c) {
-                const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk0 + c) * p.L + t;
-                if (p.y16 != nullptr)
-                  *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
-                      make_uint4(pack2s(f[c * 8 + 0], f[c * 8 + 1], kOp),
-                                 pack2s(f[c * 8 + 2], f[c * 8 + 3], kOp),
-                                 pack2s(f[c * 8 + 4], f[c * 8 + 5], kOp),
-                                 pack2s(f[c * 8 + 6], f[c * 8 + 7], kOp));
-                if (p.y32 != nullptr) {
-                  const float o8[8] = {f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3],
-                                       f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]};
-                  st_global_v8(p.y32 + idx * 8, o8);
+                for (int k = 0; k < 7; ++k) {
+                  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                  for (int j4 = 0; j4 < GS / 4; ++j4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(sMono + k * 32 + part * COLS + c0 + j4 * 4);
+                    a0 = fmaf(f[j4 * 4 + 0], w4.x, a0); a1 = fmaf(f[j4 * 4 + 1], w4.y, a1);
+                    a0 = fmaf(f[j4 * 4 + 2], w4.z, a0); a1 = fmaf(f[j4 * 4 + 3], w4.w, a1);
+                  }
+                  pk[k] = a0 + a1;
+                }
+                float* P = sP + (part * 7) * R + row;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) P[k * R] = pk[k];
+              } else if (live && t >= 0 && t < p.L && row >= p.halo && row < R - p.halo) {
+#pragma unroll
+                for (int c = 0; c < GS / 8; ++c) {
+                  const size_t idx = (static_cast<size_t>(b) * G::NCH + chunk0 + c0 / 8 + c) * p.L + t;
+                  if (p.y16 != nullptr)
+                    *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
+                        make_uint4(pack2s(f[c * 8 + 0], f[c * 8 + 1], kOp),
+                                   pack2s(f[c * 8 + 2], f[c * 8 + 3], kOp),
+                                   pack2s(f[c * 8 + 4], f[c * 8 + 5], kOp),
+                                   pack2s(f[c * 8 + 6], f[c * 8 + 7], kOp));
+                  if (p.y32 != nullptr) {
+                    const float o8[8] = {f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3],
+                                         f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]};
+                    st_global_v8(p.y32 + idx * 8, o8);
+                  }
                 }
               }
             }
+            // the accumulator has been read: seed it with the next conv's bias
+            if (!last) store_bias(l + 1, ta);
+            // this row is done with the old tile: bring in the next tile's row
+            if (last && has_next) store_row(mb, nx[last ? u : 0]);
           }
-          if (!last) {
-            if (second) tmem_st_wait();
+          if (!last || has_next) {
+            tmem_st_wait();
             fence_proxy_async_smem();
             tc_fence_before();
             arrive_act(h);
           }
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 2);
         }
-      }
+        ++nconv;
+      };
+      using T_ = std::true_type;
+      using F_ = std::false_type;
+      conv_epi(F_{}, F_{}, 0);
+      conv_epi(T_{}, F_{}, 1);
+      conv_epi(F_{}, F_{}, 2);
+      conv_epi(T_{}, F_{}, 3);
+      conv_epi(F_{}, F_{}, 4);
+      conv_epi(T_{}, T_{}, 5);
       if (mono) {
         // ---- fused tail, step 2: y[row] = tanh(b + sum_k sum_part P[part][k][row+k-3])
         named_bar_sync(1, 32 * EW);            // partial sums complete (epilogue warps only)
         const float bias0 = __ldg(p.mono_b);
-        const float* P = reinterpret_cast<const float*>(smem + kStackHeader);
+        const float* P = sP;
         for (int row = threadIdx.x - 64; row < R - p.halo; row += 32 * EW) {
           const int t = t0 + row;
           if (row < p.halo || t < 0 || t >= p.L) continue;
@@ -497,7 +567,8 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
           }
           p.mono_out[static_cast<size_t>(b) * p.L + t] = tanhf(a0 + a1);
         }
-        named_bar_sync(1, 32 * EW);            // staging consumed before the next prologue
+        // no second barrier: no warp can reach the next tile's last conv (the next writer of P)
+        // before every warp has passed this point -- the convs in between need all 16 arrivals
       }
     }
   }
