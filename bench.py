@@ -153,6 +153,173 @@ def workload_config(world, sample_clips=None):
     return cfg
 
 
+def _events(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def _max_over_ranks(torch, dist, world, dev, *vals):
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def bench_strong(torch, dist, gen, world, rank, dev, steps):
+    """BASELINE config 3 as written: ONE global batch of 256 clips sharded by clip over the ranks
+    (256/N per GPU, no communication).  Returns ms per step (max over ranks)."""
+    import numpy as np
+    from music_synthesis_b200.sharding import clip_shard
+    lo, hi = clip_shard(CLIPS, rank, world)
+    x = torch.from_numpy(np.random.RandomState(2000 + rank).standard_normal(
+        (hi - lo, MELS, FRAMES)).astype(np.float32)).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            gen(x)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = _events(torch)
+        e0.record()
+        for _ in range(steps):
+            gen(x)
+        e1.record()
+        torch.cuda.synchronize()
+    (ms,) = _max_over_ranks(torch, dist, world, dev, e0.elapsed_time(e1) / steps)
+    return {"global_clips": CLIPS, "clips_per_gpu": hi - lo, "ms_per_step": ms,
+            "value": CLIPS * 256 * FRAMES / (ms * 1e-3), "unit": UNIT, "scaling": "strong"}
+
+
+def bench_train(torch, dist, pair, global_batch, frames, world, rank, dev, cycles, warmup=3):
+    """BASELINE configs 4 / 5: one training cycle = DiscriminatorTrainer.train + GeneratorTrainer.train
+    (the reference's order, experiment/experiment.py:141-144) on a global batch sharded over the
+    ranks; the gradient all-reduce (NCCL) of the network being stepped is inside the timed region.
+    pair = "melgan" (cfg4: MelGanGenerator + MelGanDiscriminator, hinge) or "fb" (cfg5:
+    FilterBankMultiScale pair, least squares, band dictionaries)."""
+    from music_synthesis_b200 import _lib
+    from music_synthesis_b200.experiment.init import weights_init
+    from music_synthesis_b200.train import GeneratorTrainer, DiscriminatorTrainer, Adam
+    from music_synthesis_b200.loss.loss import mel_gan_disc_loss, mel_gan_gen_loss
+    per = max(1, global_batch // world)
+    torch.manual_seed(10 + rank)            # Adam broadcasts rank 0's initial weights
+    gsrc = torch.Generator(device=dev).manual_seed(100 + rank)
+    feats = torch.randn(per, MELS, frames, device=dev, generator=gsrc) * 0.5 - 2.0
+    real = torch.randn(per, 1, 256 * frames, device=dev, generator=gsrc) * 0.1
+    kw = {}
+    if pair == "fb":
+        from music_synthesis_b200.generator.multiscale import FilterBankMultiScaleGenerator
+        from music_synthesis_b200.discriminator.multiscale import FilterBankMultiScaleDiscriminator
+        from music_synthesis_b200.audio.transform import fft_frequency_decompose
+        from music_synthesis_b200.loss.loss import (least_squares_disc_loss,
+                                                    least_squares_generator_loss)
+        n = 256 * frames
+        g = FilterBankMultiScaleGenerator(SAMPLE_RATE, MELS, frames, n, recompose=False).to(dev)
+        d = FilterBankMultiScaleDiscriminator(n, SAMPLE_RATE, decompose=False,
+                                              conditioning_channels=MELS).to(dev)
+        with torch.no_grad():
+            real = fft_frequency_decompose(real, n // 16)
+        kw = {"d": least_squares_disc_loss, "g": least_squares_generator_loss}
+    else:
+        from music_synthesis_b200.generator.full import MelGanGenerator
+        from music_synthesis_b200.discriminator.melgan import MelGanDiscriminator
+        g = MelGanGenerator(frames, MELS).to(dev)
+        d = MelGanDiscriminator().to(dev)
+    g.apply(weights_init)
+    d.apply(weights_init)
+    g_optim = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_optim = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
+    d_tr = DiscriminatorTrainer(g, g_optim, d, d_optim, mel_gan_disc_loss, cuda_graph=True)
+    g_tr = GeneratorTrainer(g, g_optim, d, d_optim, mel_gan_gen_loss, cuda_graph=True)
+    if kw:
+        d_tr.sub_loss, g_tr.sub_loss = kw["d"], kw["g"]
+    with torch.enable_grad():
+        for _ in range(warmup + 1):          # two eager calls per shape, then the capture
+            d_tr.train(real, feats)
+            g_tr.train(real, feats)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = _events(torch)
+        e0.record()
+        for _ in range(cycles):
+            dl = d_tr.train(real, feats)["d_loss"]
+            gl = g_tr.train(real, feats)["g_loss"]
+        e1.record()
+        torch.cuda.synchronize()
+    launches = (_lib.launch_count() - l0) / cycles
+    ms = e0.elapsed_time(e1) / cycles
+    # the two all-reduces of a cycle (D gradients, G gradients) timed alone
+    ar = 0.0
+    if world > 1:
+        dist.barrier()
+        a0, a1 = _events(torch)
+        a0.record()
+        for _ in range(5):
+            d_optim.all_reduce_grads()
+            g_optim.all_reduce_grads()
+        a1.record()
+        torch.cuda.synchronize()
+        ar = a0.elapsed_time(a1) / 5
+    ms, ar = _max_over_ranks(torch, dist, world, dev, ms, ar)
+    out = {"global_batch": per * world, "clips_per_gpu": per, "samples_per_clip": 256 * frames,
+           "ms_per_cycle": ms, "clips_per_s": per * world / (ms * 1e-3), "allreduce_ms": ar,
+           "allreduce_bytes": 4 * (g_optim.flat_grad.numel() + d_optim.flat_grad.numel()),
+           "launches_per_cycle": launches, "cuda_graph": True, "d_loss": dl, "g_loss": gl,
+           "scaling": "strong"}
+    del d_tr, g_tr, g, d, g_optim, d_optim
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_cfg1(torch, dev):
+    """BASELINE config 1 on the GPU: batch 1 x 128 mel x 64 frames -> 16384 samples, latency."""
+    from music_synthesis_b200.generator.full import MelGanGenerator
+    from music_synthesis_b200.experiment.init import weights_init
+    torch.manual_seed(0)
+    g = MelGanGenerator(64, MELS).eval()
+    g.apply(weights_init)
+    g = g.to(dev)
+    x = torch.randn(1, MELS, 64, device=dev)
+    with torch.no_grad():
+        for _ in range(5):
+            g(x)
+        torch.cuda.synchronize()
+        e0, e1 = _events(torch)
+        e0.record()
+        for _ in range(50):
+            g(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 50
+    return {"gpu_ms": ms, "gpu_samples_per_s": 16384 / (ms * 1e-3)}
+
+
+def bench_cfg2(torch, dev, hbm_gbs):
+    """BASELINE config 2: Audio2Mel (STFT 1024 / hop 256 + 128-bin mel) on 64 x 16384 samples;
+    HBM-bound: algorithmic bytes = 4*B*N in + 4*B*128*F out."""
+    from music_synthesis_b200.feature.feature import Audio2Mel
+    a2m = Audio2Mel(1024, 256, 1024, SAMPLE_RATE, 128).to(dev)
+    out = {}
+    for B in (64, 4096):
+        a = torch.rand(B, 1, 16384, device=dev) * 2 - 1
+        with torch.no_grad():
+            for _ in range(5):
+                m = a2m(a)
+            torch.cuda.synchronize()
+            e0, e1 = _events(torch)
+            e0.record()
+            for _ in range(50):
+                m = a2m(a)
+            e1.record()
+            torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 50
+        nbytes = 4 * B * 16384 + 4 * m.numel()
+        out["b%d" % B] = {"us": us, "samples_per_s": B * 16384 / (us * 1e-6),
+                          "achieved_gbs": nbytes / (us * 1e-6) / 1e9,
+                          "hbm_frac": nbytes / (us * 1e-6) / 1e9 / hbm_gbs}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,6 +328,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips", type=int, default=CLIPS, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="skip the strong-scaling / training / cfg1 / cfg2 side measurements")
     ap.add_argument("--e2e-chunk", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
 
@@ -277,6 +446,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    # ---- what else the north star asks for, on every N (all ranks take part):
+    extras = {}
+    if not args.headline_only:
+        extras["strong"] = bench_strong(torch, dist, gen, world, rank, dev, max(5, args.steps // 2))
+        del gen
+        torch.cuda.empty_cache()
+        extras["train_cfg4"] = bench_train(torch, dist, "melgan", 32, 32, world, rank, dev, 10)
+        extras["train_cfg5"] = bench_train(torch, dist, "fb", 64, 256, world, rank, dev, 5)
+        if rank == 0:
+            extras["cfg1"] = bench_cfg1(torch, dev)
+            extras["cfg2"] = bench_cfg2(torch, dev, peaks()["hbm_gbs"])
+
     if rank == 0:
         pk = peaks()
         total_samples = samples_per_step * world * args.steps
@@ -310,6 +491,9 @@ def main():
                 # (776.7 MB per 64-clip launch, scaled to this launch's clip count); the
                 # algorithmic bytes are 4C in + 2C out per row = 805 MB per 64 clips
                 "traffic": 776.7e6 * clips / 64,
+                "traffic_source": "ncu constant (dram__bytes_read+write of this kernel at 64 clips, "
+                                  "profiles/r01_ncu_final_summary.tsv), scaled by clip count; not "
+                                  "measured in this run",
             },
             # the whole step (15 kernels) against the same roofline: algorithmic generator FLOPs
             # (409 536 per sample) / CUDA-event step time, sustained peak (seconds-long step)
@@ -321,9 +505,17 @@ def main():
             },
             "clocks": clocks,
         }
+        if "strong" in extras:
+            # x of one GPU: this run's own 256-clips-on-one-GPU time is the weak step above
+            extras["strong"]["x_of_one_gpu"] = step_ms / extras["strong"]["ms_per_step"]
+        line.update(extras)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port(8, FRAMES, 2, 1)
             line["cpu_baseline"].pop("ms_per_pass", None)
+            if "cfg1" in line:
+                c1 = cpu_port(1, 64, 5, 2)
+                line["cfg1"].update({"cpu_port_ms": c1["ms_per_pass"], "cpu_cores": c1["cores"],
+                                     "cpu_samples_per_s": c1["value"]})
         print(json.dumps(line), flush=True)
 
     if world > 1:

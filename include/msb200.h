@@ -283,18 +283,29 @@ ms_status ms_audio2mel_fwd(const float* audio, const float* window, const float*
  *   Gradients travel as BLK f32 between layers and are converted to a 16-bit GEMM operand
  *   (bf16 -- the default: the range of fp32, no loss scaling -- or fp16 under the dynamic loss
  *   scaler of train/train.py) by ms_blk_act_bwd, which also applies LeakyReLU' and
- *   accumulates the bias gradient.
+ *   forms the bias gradient.
+ *   Determinism: no floating-point number is added in arrival order anywhere in the backward
+ *   pass.  The kernels that reduce across thread blocks (bias / direct-conv / single-channel
+ *   weight gradients) write per-block partial sums into `workspace` and the block that draws
+ *   the last integer ticket adds them in block-index order (csrc/det_reduce.cuh).  Workspace
+ *   contract of those entry points: the first MS_TICKET_BYTES bytes are counters that must be
+ *   ZERO when the buffer is first used; every launch leaves them zero again, so one zero-fill
+ *   at allocation serves all later launches on the same stream (CUDA-graph replays included).
+ *   The results are ASSIGNED (dw = ..., dbias = ...), no zero-initialisation is needed.
  * ------------------------------------------------------------------------- */
+#define MS_TICKET_BYTES 65536
 /* dz16 = to16(dy32 * LeakyReLU'(.)), dbias[c] += sum_{b,l} dz.  Sign source: `sign16` (BLK
  * 16-bit saved activation) or the fp32 pair (ya32 - yb32 > 0; the branch of a ResidualAtom,
  * util/modules.py:384-388); none = no activation.  s2d_stride > 1 writes dz16 in the
  * space-to-depth layout of ms_space_to_depth_blk16 (input of the ConvTranspose1d dgrad).
  * dz32 (optional, NULL to skip): the same masked gradient in fp32, BLK f32 like dy32 -- the skip
- * path of a residual DilatedStack layer.  dbias may be NULL; otherwise it must be zero-initialised
- * (atomic accumulation). */
+ * path of a residual DilatedStack layer.  dbias may be NULL; otherwise `workspace` (see the
+ * contract above, ms_blk_act_bwd_workspace_bytes) is required and dbias[c] = sum_{b,l} dz. */
+size_t ms_blk_act_bwd_workspace_bytes(int batch, int channels, int len);
 ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya32,
                          const float* yb32, void* dz16, float* dz32, float* dbias, int batch,
-                         int channels, int len, int fmt, int s2d_stride, void* stream);
+                         int channels, int len, int fmt, int s2d_stride, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* reference-layout fp32 weights of the convolution that computes the INPUT gradient, to be
  * packed with ms_conv_pack_weight and run with ms_conv_fwd:
  *   MS_CONV  w (cout,cin,k)  -> out (cin,cout,k) tap-reversed; run as MS_CONV cin'=cout,
@@ -348,18 +359,25 @@ ms_status ms_weight_norm_bwd(const float* dw, const float* v, const float* g, fl
 ms_status ms_pack_ncl_to_blk32(const float* x, float* y32, int batch, int channels, int len,
                                void* stream);
 /* backward of ms_conv1d_direct_fwd (zero padding).  `y` = forward output (LeakyReLU mask) when
- * leaky.  dw / dbias must be zero-initialised (atomic accumulation); dbias may be NULL. */
+ * leaky.  dw / dbias are assigned (deterministic two-stage sums through `workspace`, contract
+ * above); dbias may be NULL. */
 ms_status ms_conv1d_direct_dgrad(const float* dy, const float* y, const float* w, float* dx,
                                  int batch, int cin, int cout, int lin, int ksize, int stride,
                                  int pad, int groups, int leaky, void* stream);
+size_t ms_conv1d_direct_wgrad_workspace_bytes(int batch, int cin, int cout, int lin, int ksize,
+                                              int stride, int pad, int groups);
 ms_status ms_conv1d_direct_wgrad(const float* dy, const float* y, const float* x, float* dw,
                                  float* dbias, int batch, int cin, int cout, int lin, int ksize,
-                                 int stride, int pad, int groups, int leaky, void* stream);
+                                 int stride, int pad, int groups, int leaky, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 /* backward of ms_conv_to_mono: dzm (B,1,L) scratch/out = dy * (1 - y_tanh^2) (y_tanh NULL: no
- * tanh); dx32 BLK f32 (may be NULL); dw (cin,k) / dbias (1) zero-initialised, may be NULL. */
+ * tanh); dx32 BLK f32 (may be NULL); dw (cin,k) / dbias (1) assigned, may be NULL (`workspace`,
+ * contract above, is needed with dw). */
+size_t ms_conv_to_mono_bwd_workspace_bytes(int batch, int cin, int len, int ksize);
 ms_status ms_conv_to_mono_bwd(const float* dy, const float* y_tanh, const float* x32,
                               const float* w, float* dzm, float* dx32, float* dw, float* dbias,
-                              int batch, int cin, int len, int ksize, int pad, void* stream);
+                              int batch, int cin, int len, int ksize, int pad, void* workspace,
+                              size_t workspace_bytes, void* stream);
 ms_status ms_avg_pool1d_bwd(const float* dy, float* dx, int batch_channels, int lin, int ksize,
                             int stride, int pad, int count_include_pad, void* stream);
 /* gradients of the ms_reduce_fwd terms wrt a (da) and b (db), either may be NULL;

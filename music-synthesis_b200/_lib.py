@@ -81,8 +81,9 @@ SIGNATURES = {
     "ms_audio2mel_frames": (c_int, [c_int, c_int, c_int]),
     "ms_audio2mel_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_int, c_int, c_int, c_void_p]),
+    "ms_blk_act_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ms_blk_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                               c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ms_weight_dgrad_view": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "ms_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int,
@@ -107,12 +108,15 @@ SIGNATURES = {
     "ms_pack_ncl_to_blk32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ms_conv1d_direct_dgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ms_conv1d_direct_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int,
+                                                          c_int, c_int]),
     "ms_conv1d_direct_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                       c_void_p]),
+                                       c_void_p, c_size_t, c_void_p]),
+    "ms_conv_to_mono_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "ms_conv_to_mono_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                    c_void_p]),
+                                    c_void_p, c_size_t, c_void_p]),
     "ms_avg_pool1d_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p]),
     "ms_reduce_bwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_void_p,

@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "det_reduce.cuh"
 #include "ptx.cuh"
 #include "runtime.cuh"
 
@@ -31,12 +32,23 @@ struct ActBwdParams {
   const float* ya;      // BLK f32 or null
   const float* yb;      // BLK f32 or null
   uint16_t* dz;         // BLK 16-bit (B, C/8, L, 8) or s2d (B, s*C/8, L/s, 8)
-  float* dbias;         // [C] accumulated with atomics, or null
+  float* dbias;         // [C] = sum over batch and time (fixed order), or null
   float* dz32;          // optional fp32 copy of dz (BLK f32, same layout as dy), or null
   int C8, L, fmt, s2d;
+  int rows_per_block;   // multiple of 256; gridDim.x = ceil(L / rows_per_block) <= kActBwdMaxXT
+  float* part;          // [B * gridDim.x][C] partial bias sums (workspace), with dbias
+  unsigned int* ticket; // one counter for the launch (workspace)
 };
 
-constexpr int kActBwdRows = 1024;   // rows per block (256 threads x 4)
+constexpr int kActBwdRows = 1024;   // minimum rows per block (256 threads x 4)
+constexpr int kActBwdMaxXT = 8;     // at most 8 time tiles per (clip, channel group)
+
+static int act_bwd_rows_per_block(int len) {
+  int rows = kActBwdRows;
+  const int need = ceil_div(len, kActBwdMaxXT);
+  if (need > rows) rows = ceil_div(need, 256) * 256;
+  return rows;
+}
 
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const ActBwdParams p) {
@@ -46,8 +58,8 @@ act_bwd_kernel(const ActBwdParams p) {
   float bsum[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
-  const int t_end = min(p.L, (static_cast<int>(blockIdx.x) + 1) * kActBwdRows);
-  for (int t = blockIdx.x * kActBwdRows + threadIdx.x; t < t_end; t += 256) {
+  const int t_end = min(p.L, (static_cast<int>(blockIdx.x) + 1) * p.rows_per_block);
+  for (int t = blockIdx.x * p.rows_per_block + threadIdx.x; t < t_end; t += 256) {
     const size_t idx = bc * p.L + t;
     float g[8];
     ld_global_nc_v8(p.dy + idx * 8, g);
@@ -90,11 +102,16 @@ act_bwd_kernel(const ActBwdParams p) {
     if (lane == 0) sh[warp][j] = v;
   }
   __syncthreads();
+  const int C = p.C8 * 8;
   if (threadIdx.x < 8) {
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
-    atomicAdd(p.dbias + c8 * 8 + threadIdx.x, v);
+    p.part[(b * gridDim.x + blockIdx.x) * C + c8 * 8 + threadIdx.x] = v;
   }
+  // the last block of the launch adds the partials in (clip, time tile) order
+  if (!det_last_block(p.ticket, gridDim.x * gridDim.y)) return;
+  const int np = static_cast<int>(gridDim.y / p.C8) * gridDim.x;
+  for (int c = threadIdx.x; c < C; c += 256) p.dbias[c] = det_sum_strided(p.part, np, C, c);
 }
 
 // reference-layout weights of the convolution that computes the INPUT gradient:
@@ -284,9 +301,11 @@ struct DirectBwdParams {
   const float* x;    // (B, cin, lin)          [wgrad]
   const float* w;    // (cout, cin/groups, k)  [dgrad]
   float* dx;         // (B, cin, lin)          [dgrad]
-  float* dw;         // (cout, cin/groups, k)  [wgrad, atomics]
-  float* dbias;      // (cout)                 [wgrad, atomics] or null
+  float* dw;         // (cout, cin/groups, k)  [wgrad] = sum over clips and time, fixed order
+  float* dbias;      // (cout)                 [wgrad] or null
   int B, cin, cout, lin, lout, k, stride, pad, groups, leaky;
+  float* part;          // [wgrad] per-block partial sums (workspace)
+  unsigned int* ticket; // [wgrad] one counter per reduction group (workspace)
 };
 
 __device__ __forceinline__ float masked(float g, float y, int leaky) {
@@ -382,7 +401,7 @@ direct_wgrad_kernel(const DirectBwdParams p) {
     if (active) {
       const float* xr = sx + cil * win + k;
       for (int l = lg; l < nl; l += ngroups) acc = fmaf(sz[l], xr[l * p.stride], acc);
-      if (o == 0 && p.dbias != nullptr)
+      if (o == 0)
         for (int l = lg; l < nl; l += ngroups) bacc += sz[l];
     }
   }
@@ -391,21 +410,30 @@ direct_wgrad_kernel(const DirectBwdParams p) {
   float* red = sm;                // [ngroups][nout] <= 256 floats
   if (active) red[lg * nout + o] = acc;
   __syncthreads();
+  // partial slot of this block: [co][slot][nout + 1]
+  const int nslots = gridDim.y * gridDim.z;
+  const int slot = blockIdx.y * gridDim.z + blockIdx.z;
+  float* mine = p.part + (static_cast<size_t>(co) * nslots + slot) * (nout + 1);
   if (threadIdx.x < nout) {
     float v = 0.f;
     for (int q = 0; q < ngroups; ++q) v += red[q * nout + threadIdx.x];
-    atomicAdd(p.dw + static_cast<size_t>(co) * nout + threadIdx.x, v);
+    mine[threadIdx.x] = v;
   }
-  if (p.dbias != nullptr) {
-    __syncthreads();
-    if (active && o == 0) red[lg] = bacc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float v = 0.f;
-      for (int q = 0; q < ngroups; ++q) v += red[q];
-      atomicAdd(p.dbias + co, v);
-    }
+  __syncthreads();
+  if (active && o == 0) red[lg] = bacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int q = 0; q < ngroups; ++q) v += red[q];
+    mine[nout] = v;
   }
+  // the last block of this output channel adds the partials in slot order
+  if (!det_last_block(p.ticket + co, nslots)) return;
+  const float* grp = p.part + static_cast<size_t>(co) * nslots * (nout + 1);
+  for (int i = threadIdx.x; i < nout; i += kWgDirectThreads)
+    p.dw[static_cast<size_t>(co) * nout + i] = det_sum_strided(grp, nslots, nout + 1, i);
+  if (p.dbias != nullptr && threadIdx.x == 0)
+    p.dbias[co] = det_sum_strided(grp, nslots, nout + 1, nout);
 }
 
 
@@ -543,26 +571,41 @@ direct_wgrad_tiled_kernel(const DirectBwdParams p) {
       }
     }
   }
-  // lane groups combine in shared memory: result [COG][CIG][4*kq] (+ COG bias sums)
+  // lane groups combine in shared memory, one after the other (fixed order):
+  // result [COG][CIG][4*kq] (+ COG bias sums)
   __syncthreads();
   float* red = sm;                                       // COG * CIG * 4*kq floats (<= sz + sx)
   float* bred = red + COG * CIG * 4 * kq;
   for (int i = threadIdx.x; i < COG * CIG * 4 * kq + COG; i += kWgDirectThreads) red[i] = 0.f;
   __syncthreads();
-  if (active) {
+  for (int turn = 0; turn < lanes; ++turn) {
+    if (active && lg == turn) {
 #pragma unroll
-    for (int oc = 0; oc < COG; ++oc) {
+      for (int oc = 0; oc < COG; ++oc) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) atomicAdd(&red[(oc * CIG + c) * 4 * kq + k0 + q], acc[q][oc]);
-      if (o == 0) atomicAdd(&bred[oc], bacc[oc]);
+        for (int q = 0; q < 4; ++q) red[(oc * CIG + c) * 4 * kq + k0 + q] += acc[q][oc];
+        if (o == 0) bred[oc] += bacc[oc];
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
+  // partial slot of this block: [g][slot][COG*CIG*k + COG]
+  const int nel = COG * CIG * p.k + COG;
+  const int nslots = gridDim.y * gridDim.z;
+  const int slot = blockIdx.y * gridDim.z + blockIdx.z;
+  float* mine = p.part + (static_cast<size_t>(g) * nslots + slot) * nel;
   for (int i = threadIdx.x; i < COG * CIG * p.k; i += kWgDirectThreads) {
     const int k = i % p.k, oc_c = i / p.k;
-    atomicAdd(p.dw + (static_cast<size_t>(g) * COG * CIG + oc_c) * p.k + k, red[oc_c * 4 * kq + k]);
+    mine[i] = red[oc_c * 4 * kq + k];
   }
-  if (p.dbias != nullptr && threadIdx.x < COG) atomicAdd(p.dbias + g * COG + threadIdx.x, bred[threadIdx.x]);
+  if (threadIdx.x < COG) mine[COG * CIG * p.k + threadIdx.x] = bred[threadIdx.x];
+  // the last block of this group adds the partials in slot order
+  if (!det_last_block(p.ticket + g, nslots)) return;
+  const float* grp = p.part + static_cast<size_t>(g) * nslots * nel;
+  for (int i = threadIdx.x; i < COG * CIG * p.k; i += kWgDirectThreads)
+    p.dw[static_cast<size_t>(g) * COG * CIG * p.k + i] = det_sum_strided(grp, nslots, nel, i);
+  if (p.dbias != nullptr && threadIdx.x < COG)
+    p.dbias[g * COG + threadIdx.x] = det_sum_strided(grp, nslots, nel, COG * CIG * p.k + threadIdx.x);
 }
 
 template <int COG, int CIG>
@@ -575,19 +618,33 @@ static ms_status launch_dgrad_tiled(const DirectBwdParams& p, cudaStream_t st) {
   return after_launch("direct_dgrad_tiled_kernel");
 }
 
+// grid of the direct weight-gradient kernels: x = reduction groups (tiled: conv groups, generic:
+// output channels), y = time tiles, z = clip slices; `budget` caps the total block count
+static dim3 direct_wgrad_grid(int ngroups, int lout, int batch, long long budget) {
+  const int ltiles = ceil_div(lout, kWgTileL);
+  long long z = budget / (static_cast<long long>(ngroups) * ltiles);
+  if (z < 1) z = 1;
+  if (z > batch) z = batch;
+  return dim3(ngroups, ltiles, static_cast<unsigned>(z));
+}
+
+static bool direct_wgrad_is_tiled(int cout_g, int cin_g, int ksize, int stride, int groups) {
+  if (groups > 65535) return false;
+  if (!((cout_g == 16 && (cin_g == 4 || cin_g == 1)) || (cout_g == 4 && cin_g == 4))) return false;
+  const int kq = (ksize + 3) / 4;
+  if (cin_g * kq > kWgDirectThreads) return false;
+  const int win = (kWgTileL - 1) * stride + 4 * kq;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(kWgTileL) * cout_g + static_cast<size_t>(cin_g) * win);
+  return smem <= 48 * 1024 && cout_g * cin_g * 4 * kq + cout_g <= kWgTileL * cout_g + cin_g * win;
+}
+
 template <int COG, int CIG>
 static ms_status launch_wgrad_tiled(const DirectBwdParams& p, cudaStream_t st) {
   const int kq = (p.k + 3) / 4;
-  if (CIG * kq > kWgDirectThreads) return MS_ERR_INVALID;
   const int win = (kWgTileL - 1) * p.stride + 4 * kq;
   const size_t smem = sizeof(float) * (static_cast<size_t>(kWgTileL) * COG + static_cast<size_t>(CIG) * win);
-  if (smem > 48 * 1024 || COG * CIG * 4 * kq + COG > kWgTileL * COG + CIG * win) return MS_ERR_INVALID;
-  const int ltiles = ceil_div(p.lout, kWgTileL);
-  if (ltiles > 65535) return MS_ERR_INVALID;
-  long long z = 2048LL / (static_cast<long long>(p.groups) * ltiles);
-  if (z < 1) z = 1;
-  if (z > p.B) z = p.B;
-  dim3 grid(p.groups, ltiles, static_cast<unsigned>(z));
+  const dim3 grid = direct_wgrad_grid(p.groups, p.lout, p.B, 2048);
+  if (grid.y > 65535) return MS_ERR_INVALID;
   direct_wgrad_tiled_kernel<COG, CIG><<<grid, kWgDirectThreads, smem, st>>>(p);
   return after_launch("direct_wgrad_tiled_kernel");
 }
@@ -638,7 +695,7 @@ constexpr int kMonoMaxK = 8;
 __global__ void __launch_bounds__(256)
 mono_wgrad_kernel(const float* __restrict__ dzm, const float* __restrict__ x,
                   float* __restrict__ dw, float* __restrict__ dbias, int B, int C8, int L,
-                  int ksize, int pad) {
+                  int ksize, int pad, float* __restrict__ part, unsigned int* ticket) {
   const int c8 = blockIdx.y;
   float acc[kMonoMaxK][8];
 #pragma unroll
@@ -682,17 +739,30 @@ mono_wgrad_kernel(const float* __restrict__ dzm, const float* __restrict__ x,
     if (lane == 0) sh[warp][kMonoMaxK * 8] = v;
   }
   __syncthreads();
+  // partial slot of this block: [c8][slot][ksize*8 + 1]
+  const int nel = ksize * 8 + 1;
+  const int nslots = gridDim.x * gridDim.z;
+  const int slot = blockIdx.x * gridDim.z + blockIdx.z;
+  float* mine = part + (static_cast<size_t>(c8) * nslots + slot) * nel;
   if (threadIdx.x < ksize * 8) {
-    const int k = threadIdx.x / 8, j = threadIdx.x - k * 8;
     float v = 0.f;
-    for (int w = 0; w < 8; ++w) v += sh[w][k * 8 + j];
-    atomicAdd(dw + (c8 * 8 + j) * ksize + k, v);
+    for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
+    mine[threadIdx.x] = v;
   }
-  if (c8 == 0 && dbias != nullptr && threadIdx.x == 0) {
+  if (threadIdx.x == 0) {
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += sh[w][kMonoMaxK * 8];
-    atomicAdd(dbias, v);
+    mine[ksize * 8] = v;
   }
+  // the last block of this channel group adds the partials in slot order
+  if (!det_last_block(ticket + c8, nslots)) return;
+  const float* grp = part + static_cast<size_t>(c8) * nslots * nel;
+  if (threadIdx.x < ksize * 8) {
+    const int k = threadIdx.x / 8, j = threadIdx.x - k * 8;
+    dw[(c8 * 8 + j) * ksize + k] = det_sum_strided(grp, nslots, nel, threadIdx.x);
+  }
+  if (c8 == 0 && dbias != nullptr && threadIdx.x == 0)
+    dbias[0] = det_sum_strided(grp, nslots, nel, ksize * 8);
 }
 
 // ---------------------------------------------------------------- pooling / losses / Adam
@@ -806,9 +876,16 @@ using namespace msb;
 
 extern "C" {
 
+size_t ms_blk_act_bwd_workspace_bytes(int batch, int channels, int len) {
+  if (batch <= 0 || channels <= 0 || len <= 0) return 0;
+  const int xt = ceil_div(len, act_bwd_rows_per_block(len));
+  return kTicketBytes + sizeof(float) * static_cast<size_t>(batch) * xt * channels;
+}
+
 ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya32,
                          const float* yb32, void* dz16, float* dz32, float* dbias, int batch,
-                         int channels, int len, int fmt, int s2d_stride, void* stream) {
+                         int channels, int len, int fmt, int s2d_stride, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   if (dy32 == nullptr || dz16 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
       len <= 0)
     return MS_ERR_INVALID;
@@ -817,9 +894,16 @@ ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya3
   if (fmt != MS_F16 && fmt != MS_BF16) return MS_ERR_INVALID;
   const long long rows = static_cast<long long>(batch) * (channels / 8);
   if (rows > 65535) return MS_ERR_INVALID;
+  if (dbias != nullptr && (workspace == nullptr ||
+                           workspace_bytes < ms_blk_act_bwd_workspace_bytes(batch, channels, len)))
+    return MS_ERR_WORKSPACE;
+  const int rpb = act_bwd_rows_per_block(len);
   ActBwdParams p{dy32, static_cast<const uint16_t*>(sign16), ya32, yb32,
-                 static_cast<uint16_t*>(dz16), dbias, dz32, channels / 8, len, fmt, s2d_stride};
-  dim3 grid(ceil_div(len, kActBwdRows), static_cast<unsigned>(rows));
+                 static_cast<uint16_t*>(dz16), dbias, dz32, channels / 8, len, fmt, s2d_stride,
+                 rpb,
+                 reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kTicketBytes),
+                 static_cast<unsigned int*>(workspace)};
+  dim3 grid(ceil_div(len, rpb), static_cast<unsigned>(rows));
   act_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return after_launch("act_bwd_kernel");
 }
@@ -873,7 +957,7 @@ ms_status ms_conv1d_direct_dgrad(const float* dy, const float* y, const float* w
   const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
   if (lout <= 0) return MS_ERR_INVALID;
   DirectBwdParams p{dy, y, nullptr, w, dx, nullptr, nullptr, batch, cin, cout, lin, lout,
-                    ksize, stride, pad, groups, leaky};
+                    ksize, stride, pad, groups, leaky, nullptr, nullptr};
   const int cin_g = cin / groups, cout_g = cout / groups;
   if (groups > 65535 || batch > 65535) return MS_ERR_INVALID;
   {
@@ -903,32 +987,55 @@ ms_status ms_conv1d_direct_dgrad(const float* dy, const float* y, const float* w
   return after_launch("direct_dgrad_kernel");
 }
 
+size_t ms_conv1d_direct_wgrad_workspace_bytes(int batch, int cin, int cout, int lin, int ksize,
+                                              int stride, int pad, int groups) {
+  if (batch <= 0 || cin <= 0 || cout <= 0 || groups <= 0 || cin % groups != 0 ||
+      cout % groups != 0)
+    return 0;
+  const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
+  if (lout <= 0) return 0;
+  const int cin_g = cin / groups, cout_g = cout / groups;
+  size_t blocks, nel;
+  if (direct_wgrad_is_tiled(cout_g, cin_g, ksize, stride, groups)) {
+    const dim3 g = direct_wgrad_grid(groups, lout, batch, 2048);
+    blocks = static_cast<size_t>(g.x) * g.y * g.z;
+    nel = static_cast<size_t>(cout_g) * cin_g * ksize + cout_g;
+  } else {
+    const dim3 g = direct_wgrad_grid(cout, lout, batch, 4096);
+    blocks = static_cast<size_t>(g.x) * g.y * g.z;
+    nel = static_cast<size_t>(cin_g) * ksize + 1;
+  }
+  return kTicketBytes + sizeof(float) * blocks * nel;
+}
+
 ms_status ms_conv1d_direct_wgrad(const float* dy, const float* y, const float* x, float* dw,
                                  float* dbias, int batch, int cin, int cout, int lin, int ksize,
-                                 int stride, int pad, int groups, int leaky, void* stream) {
+                                 int stride, int pad, int groups, int leaky, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   if (dy == nullptr || x == nullptr || dw == nullptr || batch <= 0 || cin <= 0 || cout <= 0 ||
       groups <= 0 || cin % groups != 0 || cout % groups != 0 || (leaky && y == nullptr))
     return MS_ERR_INVALID;
   const int lout = ms_conv1d_out_len(lin, ksize, stride, pad);
   if (lout <= 0) return MS_ERR_INVALID;
-  const int cin_g = cin / groups;
+  const int cin_g = cin / groups, cout_g = cout / groups;
   if (cin_g * ksize > kWgDirectThreads) return MS_ERR_INVALID;
+  const size_t need = ms_conv1d_direct_wgrad_workspace_bytes(batch, cin, cout, lin, ksize, stride,
+                                                             pad, groups);
+  if (workspace == nullptr || need == 0 || workspace_bytes < need) return MS_ERR_WORKSPACE;
   DirectBwdParams p{dy, y, x, nullptr, nullptr, dw, dbias, batch, cin, cout, lin, lout,
-                    ksize, stride, pad, groups, leaky};
-  {
-    const int cout_g = cout / groups;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ms_status ts = MS_ERR_INVALID;
-    if (groups <= 65535) {
-      if (cout_g == 16 && cin_g == 4) ts = launch_wgrad_tiled<16, 4>(p, st);
-      else if (cout_g == 16 && cin_g == 1) ts = launch_wgrad_tiled<16, 1>(p, st);
-      else if (cout_g == 4 && cin_g == 4) ts = launch_wgrad_tiled<4, 4>(p, st);
-    }
-    if (ts != MS_ERR_INVALID) return ts;
+                    ksize, stride, pad, groups, leaky,
+                    reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kTicketBytes),
+                    static_cast<unsigned int*>(workspace)};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (direct_wgrad_is_tiled(cout_g, cin_g, ksize, stride, groups)) {
+    if (groups > kMaxTickets) return MS_ERR_INVALID;
+    if (cout_g == 16 && cin_g == 4) return launch_wgrad_tiled<16, 4>(p, st);
+    if (cout_g == 16 && cin_g == 1) return launch_wgrad_tiled<16, 1>(p, st);
+    return launch_wgrad_tiled<4, 4>(p, st);
   }
   const int win = (kWgTileL - 1) * stride + ksize;
   const size_t smem = sizeof(float) * (kWgTileL + static_cast<size_t>(cin_g) * win);
-  if (smem > 200 * 1024 || cout > 0x7fffffff) return MS_ERR_INVALID;
+  if (smem > 200 * 1024 || cout > kMaxTickets) return MS_ERR_INVALID;
   if (smem > 48 * 1024) {
     static thread_local size_t attr_set = 0;
     if (smem > attr_set) {
@@ -939,19 +1046,31 @@ ms_status ms_conv1d_direct_wgrad(const float* dy, const float* y, const float* x
       attr_set = smem;
     }
   }
-  const int ltiles = ceil_div(lout, kWgTileL);
-  if (ltiles > 65535) return MS_ERR_INVALID;
-  long long z = 4096LL / (static_cast<long long>(cout) * ltiles);
-  if (z < 1) z = 1;
-  if (z > batch) z = batch;
-  dim3 grid(cout, ltiles, static_cast<unsigned>(z));
-  direct_wgrad_kernel<<<grid, kWgDirectThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  const dim3 grid = direct_wgrad_grid(cout, lout, batch, 4096);
+  if (grid.y > 65535) return MS_ERR_INVALID;
+  direct_wgrad_kernel<<<grid, kWgDirectThreads, smem, st>>>(p);
   return after_launch("direct_wgrad_kernel");
+}
+
+static dim3 mono_wgrad_grid(int batch, int cin, int len) {
+  int xb = ceil_div(len, 256 * 8);
+  if (xb > 64) xb = 64;
+  int zb = 2048 / (xb * (cin / 8));
+  if (zb < 1) zb = 1;
+  if (zb > batch) zb = batch;
+  return dim3(xb, cin / 8, zb);
+}
+
+size_t ms_conv_to_mono_bwd_workspace_bytes(int batch, int cin, int len, int ksize) {
+  if (batch <= 0 || cin <= 0 || cin % 8 != 0 || len <= 0 || ksize <= 0) return 0;
+  const dim3 g = mono_wgrad_grid(batch, cin, len);
+  return kTicketBytes + sizeof(float) * static_cast<size_t>(g.x) * g.y * g.z * (ksize * 8 + 1);
 }
 
 ms_status ms_conv_to_mono_bwd(const float* dy, const float* y_tanh, const float* x32,
                               const float* w, float* dzm, float* dx32, float* dw, float* dbias,
-                              int batch, int cin, int len, int ksize, int pad, void* stream) {
+                              int batch, int cin, int len, int ksize, int pad, void* workspace,
+                              size_t workspace_bytes, void* stream) {
   if (dy == nullptr || dzm == nullptr || w == nullptr || batch <= 0 || cin <= 0 ||
       cin % 8 != 0 || len <= 0 || ksize <= 0 || ksize > kMonoMaxK || batch > 65535)
     return MS_ERR_INVALID;
@@ -969,13 +1088,14 @@ ms_status ms_conv_to_mono_bwd(const float* dy, const float* y_tanh, const float*
   }
   if (dw != nullptr) {
     if (x32 == nullptr) return MS_ERR_INVALID;
-    int xb = ceil_div(len, 256 * 8);
-    if (xb > 64) xb = 64;
-    int zb = 2048 / (xb * (cin / 8));
-    if (zb < 1) zb = 1;
-    if (zb > batch) zb = batch;
-    dim3 grid(xb, cin / 8, zb);
-    mono_wgrad_kernel<<<grid, 256, 0, st>>>(dzm, x32, dw, dbias, batch, cin / 8, len, ksize, pad);
+    if (workspace == nullptr ||
+        workspace_bytes < ms_conv_to_mono_bwd_workspace_bytes(batch, cin, len, ksize))
+      return MS_ERR_WORKSPACE;
+    const dim3 grid = mono_wgrad_grid(batch, cin, len);
+    mono_wgrad_kernel<<<grid, 256, 0, st>>>(
+        dzm, x32, dw, dbias, batch, cin / 8, len, ksize, pad,
+        reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kTicketBytes),
+        static_cast<unsigned int*>(workspace));
     s = after_launch("mono_wgrad_kernel");
   }
   return s;

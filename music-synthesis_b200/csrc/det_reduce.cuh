@@ -19,9 +19,11 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/msb200.h"
+
 namespace msb {
 
-constexpr size_t kTicketBytes = 64 * 1024;            // 16384 reduction groups per launch
+constexpr size_t kTicketBytes = MS_TICKET_BYTES;       // 16384 reduction groups per launch
 constexpr int kMaxTickets = static_cast<int>(kTicketBytes / sizeof(unsigned int));
 
 // Called by ALL threads of a block after they wrote the block's partials.  Block-uniform

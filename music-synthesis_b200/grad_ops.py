@@ -19,6 +19,22 @@ GRAD_FMT = MS_F16 if __import__('os').environ.get('MSB_GRAD_FMT') == 'f16' else 
 NEEDS_LOSS_SCALE = GRAD_FMT == MS_F16
 
 
+TICKET_BYTES = 65536      # MS_TICKET_BYTES (include/msb200.h)
+_ws = {}
+
+
+def _workspace(nbytes, device):
+    """Scratch buffer of the current (device, stream) for kernels that reduce across thread
+    blocks.  Zero-filled at allocation: its first MS_TICKET_BYTES are the ticket counters of the
+    deterministic two-stage reductions (include/msb200.h), which every launch leaves zero."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(nbytes, 4 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
 def convert16(x16, src_fmt, dst_fmt):
     if src_fmt == dst_fmt:
         return x16
@@ -38,10 +54,14 @@ def act_bwd(dy32, sign16=None, ya32=None, yb32=None, want_bias=True, fmt=GRAD_FM
         dz = torch.empty((B, s2d * C8, L // s2d, 8), dtype=torch.int16, device=dy32.device)
     else:
         dz = torch.empty((B, C8, L, 8), dtype=torch.int16, device=dy32.device)
-    db = torch.zeros(C8 * 8, dtype=torch.float32, device=dy32.device) if want_bias else None
+    db = ws = None
+    if want_bias:
+        db = torch.empty(C8 * 8, dtype=torch.float32, device=dy32.device)
+        ws = _workspace(_lib.lib().ms_blk_act_bwd_workspace_bytes(B, C8 * 8, L), dy32.device)
     dz32 = torch.empty_like(dy32) if want32 else None
     check(_lib.lib().ms_blk_act_bwd(ptr(dy32), ptr(sign16), ptr(ya32), ptr(yb32), ptr(dz),
-                                    ptr(dz32), ptr(db), B, C8 * 8, L, fmt, s2d, stream_ptr()),
+                                    ptr(dz32), ptr(db), B, C8 * 8, L, fmt, s2d, ptr(ws),
+                                    0 if ws is None else ws.numel(), stream_ptr()),
           "ms_blk_act_bwd")
     return (dz, db, dz32) if want32 else (dz, db)
 
@@ -77,18 +97,6 @@ def conv_dgrad(w, dz16, kind, dilation=1, pad=0, stride=1, res32=None, operand=G
     return dx32
 
 
-_ws = {}
-
-
-def _workspace(nbytes, device):
-    key = (device.index, torch.cuda.current_stream().cuda_stream)
-    buf = _ws.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _ws[key] = buf
-    return buf
-
-
 def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0, fold=1, alpha=1.0):
     """Weight gradient (reference layout `w_shape`) on the tcgen05 time-reduction GEMM."""
     B, Cm8, La, _ = a16.shape
@@ -99,7 +107,8 @@ def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0, fold=1, alpha=1
     n = L.ms_wgrad_workspace_bytes(B, Cm8 * 8, Cn8 * 8, La, Lx, taps, sh)
     if n == 0:
         raise _lib.MsbError("unsupported weight-gradient geometry")
-    ws = _workspace(n, a16.device)
+    # split-K partial tiles live behind the ticket counters of the shared scratch buffer
+    ws = _workspace(n + TICKET_BYTES, a16.device)[TICKET_BYTES:]
     dw = torch.empty(w_shape, dtype=torch.float32, device=a16.device)
     cout = w_shape[1] if mode == MS_CONVT else 0
     check(L.ms_wgrad_fwd(ptr(a16), ptr(x16), B, Cm8 * 8, Cn8 * 8, La, Lx, taps, sh, fmt,
@@ -146,11 +155,13 @@ def conv1d_direct_bwd(dy, y, x, w, stride, pad, groups, leaky, need_dx=True, nee
                                        lin, k, stride, pad, groups, int(leaky), stream_ptr()),
               "ms_conv1d_direct_dgrad")
     if need_dw:
-        dw = torch.zeros_like(w)
-        db = torch.zeros(cout, dtype=torch.float32, device=x.device) if has_bias else None
+        dw = torch.empty_like(w)
+        db = torch.empty(cout, dtype=torch.float32, device=x.device) if has_bias else None
+        ws = _workspace(L.ms_conv1d_direct_wgrad_workspace_bytes(B, cin, cout, lin, k, stride, pad,
+                                                                 groups), x.device)
         check(L.ms_conv1d_direct_wgrad(ptr(dy), ptr(y), ptr(x.contiguous()), ptr(dw), ptr(db), B,
                                        cin, cout, lin, k, stride, pad, groups, int(leaky),
-                                       stream_ptr()), "ms_conv1d_direct_wgrad")
+                                       ptr(ws), ws.numel(), stream_ptr()), "ms_conv1d_direct_wgrad")
     return dx, dw, db
 
 
@@ -160,11 +171,14 @@ def conv_to_mono_bwd(dy, y_tanh, x32, w, ksize, pad, need_dx=True, need_dw=True,
     B, C8, L, _ = x32.shape
     dzm = torch.empty((B, 1, L), dtype=torch.float32, device=x32.device)
     dx = torch.empty_like(x32) if need_dx else None
-    dw = torch.zeros_like(w) if need_dw else None
-    db = torch.zeros(1, dtype=torch.float32, device=x32.device) if (need_dw and has_bias) else None
+    dw = torch.empty_like(w) if need_dw else None
+    db = torch.empty(1, dtype=torch.float32, device=x32.device) if (need_dw and has_bias) else None
+    ws = _workspace(_lib.lib().ms_conv_to_mono_bwd_workspace_bytes(B, C8 * 8, L, ksize),
+                    x32.device) if need_dw else None
     check(_lib.lib().ms_conv_to_mono_bwd(ptr(dy), ptr(y_tanh), ptr(x32), ptr(w.contiguous()),
                                          ptr(dzm), ptr(dx), ptr(dw), ptr(db), B, C8 * 8, L, ksize,
-                                         pad, stream_ptr()), "ms_conv_to_mono_bwd")
+                                         pad, ptr(ws), 0 if ws is None else ws.numel(),
+                                         stream_ptr()), "ms_conv_to_mono_bwd")
     return dx, dw, db
 
 

@@ -15,7 +15,8 @@ from .. import grad_ops
 
 
 class Adam:
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, process_group=None,
+                 distributed=True):
         self.params = [p for p in params]
         if not self.params:
             raise ValueError("optimizer got an empty parameter list")
@@ -24,7 +25,8 @@ class Adam:
             raise ValueError("parameters must live on a CUDA device (no CPU path)")
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.process_group = process_group
-        self.distributed = True       # False: never reduce (a single-process copy inside a DP job)
+        # False: never reduce / broadcast (a single-process copy inside a data-parallel job)
+        self.distributed = bool(distributed)
         self.step_count = 0
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step counter
         self.found_inf = torch.zeros(1, dtype=torch.int32, device=dev)  # set by unscale_()

@@ -31,14 +31,15 @@ def main():
     T, per = 8, 2
 
     def build(distributed, graph):
-        torch.manual_seed(0)
+        # data-parallel replicas draw DIFFERENT initial weights per rank on purpose: Adam's
+        # constructor broadcasts rank 0's; the single-process copy re-draws rank 0's
+        torch.manual_seed(1000 * rank if distributed else 0)
         g = MelGanGenerator(T, 128).cuda()
         d = MelGanDiscriminator().cuda()
         g.apply(weights_init)
         d.apply(weights_init)
-        go = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9))
-        do = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9))
-        go.distributed = do.distributed = distributed
+        go = Adam(g.parameters(), lr=1e-4, betas=(0.5, 0.9), distributed=distributed)
+        do = Adam(d.parameters(), lr=1e-4, betas=(0.5, 0.9), distributed=distributed)
         dt = DiscriminatorTrainer(g, go, d, do, mel_gan_disc_loss, least_squares_disc_loss, cuda_graph=graph)
         gt = GeneratorTrainer(g, go, d, do, mel_gan_gen_loss, least_squares_generator_loss, cuda_graph=graph)
         return g, d, dt, gt
