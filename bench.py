@@ -246,7 +246,8 @@ def bench_train(torch, dist, pair, global_batch, frames, world, rank, dev, cycle
             gl = g_tr.train(real, feats)["g_loss"]
         e1.record()
         torch.cuda.synchronize()
-    launches = (_lib.launch_count() - l0) / cycles
+    # replayed graph nodes are not individual launch calls: add the captured counts
+    launches = (_lib.launch_count() - l0) / cycles + d_tr.graph_launches + g_tr.graph_launches
     ms = e0.elapsed_time(e1) / cycles
     # the two all-reduces of a cycle (D gradients, G gradients) timed alone
     ar = 0.0

@@ -116,16 +116,25 @@ ms_status ms_unpack_blk32_to_ncl(const float* x32, float* y, int batch, int chan
                                  int len, void* stream);
 /* split-precision operands.  ms_pack_ncl_split_blk16: NCL f32 (B,C,L) -> BLK 16-bit
  * (B, terms*C/8, L, 8): channels [0,C) = hi = to16(s*x), [C,2C) = lo = to16(s*x - hi) and, for
- * terms = 3, [2C,3C) = hi again.  ms_weight_split: w (cout,cin,k) -> (cout,3cin,k) = [s*w, s*w,
- * s*w - to16(s*w)].  The 3C-channel conv [x_hi,x_lo,x_hi]*[W_hi,W_hi,W_lo] (alpha = 1/(s_x*s_w))
- * equals x*W to ~2^-22; the power-of-two scales keep the lo terms out of the fp16 subnormals.
+ * terms = 3, [2C,3C) = hi again.  ms_blk32_split_blk16: the same split of a BLK f32 tensor
+ * (optionally LeakyReLU and zero / reflection padding first).  ms_weight_split: w (cout,cin,k) ->
+ * (cout,terms*cin,k) = [s*w, s*w, s*w - to16(s*w)] (terms = 3) or [s*w, s*w - to16(s*w)]
+ * (terms = 2; a ConvTranspose1d weight (cin,cout,k) is split along cin by passing cout = 1,
+ * cin = cin, ksize = cout*k).  The 3C-channel conv [x_hi,x_lo,x_hi]*[W_hi,W_hi,W_lo]
+ * (alpha = 1/(s_x*s_w)) equals x*W to ~2^-22 (fp16) / ~2^-16 (bf16: the "exact" operand mode,
+ * range of fp32, no scales needed); the 2C-channel conv [x,x]*[W_hi,W_lo] removes the weight
+ * rounding only ("weight-split" mode: 2x the MMA work, ~30 % less forward error).
+ * The power-of-two scales keep the fp16 lo terms out of the subnormals.
  * Used for the dense 1024 -> 1024 layer of the discriminator (discriminator/full.py:19): its
  * activations are bias-dominated and the real/fake gradients of a GAN step cancel to first
  * order, so LeakyReLU masks and weight gradients hinge on differences of ~1e-4 relative. */
 ms_status ms_pack_ncl_split_blk16(const float* x, void* y16, int batch, int channels, int len,
                                   int operand, int terms, float scale, void* stream);
 ms_status ms_weight_split(const float* w, float* out, int cout, int cin, int ksize, int operand,
-                          float scale, void* stream);
+                          float scale, int terms, void* stream);
+ms_status ms_blk32_split_blk16(const float* x32, void* y16, int batch, int channels, int len,
+                               int pad, int pad_mode, int leaky, int operand, int terms,
+                               float scale, void* stream);
 /* space-to-depth along time: BLK 16-bit (B,C/8,src_rows,8) -> (B, s*C/8, ceil(len/s), 8) with
  * Y[u, i*C + c] = X[s*u + i, c] for s*u + i < len (0 beyond).  Turns the stride-s k7 convs of
  * featuresynth/discriminator/multiscale.py:83-88 into stride-1 convs over s*C channels. */

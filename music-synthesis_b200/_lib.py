@@ -93,8 +93,10 @@ SIGNATURES = {
                              c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ms_pack_ncl_split_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                         c_float, c_void_p]),
-    "ms_weight_split": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
+    "ms_weight_split": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
                                 c_void_p]),
+    "ms_blk32_split_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_float, c_void_p]),
     "ms_blk16_convert": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "ms_diag_sum_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_void_p]),

@@ -121,19 +121,28 @@ class FilterBank:
         return self._analysis(x, True, False)[0]
 
     # -- synthesis: conv_transpose1d(x(B,n,L+1), bank, padding=k/2) -> (B,1,L) --------------
-    def _synth_weights(self, d, device):
-        key = ("s", device)
+    def _synth_weights(self, d, device, wsplit=False):
+        key = ("s2" if wsplit else "s", device)
         if key not in self._packed:
-            self._packed[key] = ops.pack_conv_weight(d, self.synthesis_weight(device))
+            w = self.synthesis_weight(device)
+            if wsplit:
+                w = ops.weight_split(w, self.operand, ops.W_SPLIT_SCALE, terms=2)
+            self._packed[key] = ops.pack_conv_weight(d, w)
         return self._packed[key]
 
-    def transposed_convolve_blocked(self, x16, L):
+    def transposed_convolve_blocked(self, x16, L, wsplit=False):
         """x16: BLK 16-bit (B, n/8, L, 8) holding rows 0..L-1 of the (zero-padded to L+1)
-        input of `transposed_convolve`; returns (B, 1, L) f32."""
+        input of `transposed_convolve`; returns (B, 1, L) f32.  wsplit: bank weights as a
+        (hi, lo) pair over the duplicated operand (no weight rounding)."""
         B = x16.shape[0]
         n, k = self.n_bands, self.kernel_size
-        d = ops.conv_desc(MS_CONV, B, n, 16, L, k // 8, 8, k // 2, operand=self.operand)
-        _, z32 = ops.conv_fwd(d, x16, self._synth_weights(d, x16.device), None,
+        if wsplit:
+            d = ops.conv_desc(MS_CONV, B, 2 * n, 16, L, k // 8, 8, k // 2, operand=self.operand,
+                              alpha=1.0 / ops.W_SPLIT_SCALE)
+            x16 = ops.dup_channels(x16)
+        else:
+            d = ops.conv_desc(MS_CONV, B, n, 16, L, k // 8, 8, k // 2, operand=self.operand)
+        _, z32 = ops.conv_fwd(d, x16, self._synth_weights(d, x16.device, wsplit), None,
                               want16=False, want32=True)
         Lz = z32.shape[2]
         y = torch.empty((B, 1, L), dtype=torch.float32, device=x16.device)

@@ -55,6 +55,15 @@ class WeightCache:
             self._fwd = (key, ops.pack_conv_weight(desc, ops.weight_split(w.detach(), scale=SPLIT_SW)))
         return self._fwd[1]
 
+    def fwd_wsplit(self, desc, w, kind):
+        """forward image of [W_hi, W_lo] along the input-channel axis (weight-split forward:
+        the conv sees the activation operand twice, `desc.cin` = 2 x the layer's)"""
+        key = self._key(w, desc)
+        if self._fwd[0] != key:
+            ws = ops.weight_split(w.detach(), scale=ops.W_SPLIT_SCALE, terms=2, kind=kind)
+            self._fwd = (key, ops.pack_conv_weight(desc, ws))
+        return self._fwd[1]
+
     def dgrad(self, desc, w, kind, stride, pad):
         key = self._key(w, desc)
         if self._bwd[0] != key:
@@ -86,8 +95,11 @@ class ConvBlk(Function):
     ConvTranspose1d).  Returns (y32, y16)."""
 
     @staticmethod
-    def forward(ctx, x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32=None):
-        """res32 (optional, BLK f32): added after the activation, y = act(conv + b) + res32"""
+    def forward(ctx, x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32=None,
+                wsplit=False):
+        """res32 (optional, BLK f32): added after the activation, y = act(conv + b) + res32.
+        wsplit: weight-split forward ([x, x] * [W_hi, W_lo]: no weight rounding, 2x the MMA work);
+        the backward is the same either way."""
         B, _, L, _ = x16.shape
         if kind == MS_CONV:
             cout, cin, k = w.shape
@@ -95,8 +107,15 @@ class ConvBlk(Function):
             cin, cout, k = w.shape
         if res32 is not None and leaky:
             raise _lib.MsbError("ConvBlk: residual input only with a linear epilogue")
-        d = ops.conv_desc(kind, B, cin, cout, L, k, dilation, pad, stride, leaky=leaky)
-        y16, y32 = ops.conv_fwd(d, x16, cache.fwd(d, w), b, res32=res32, want16=True, want32=True)
+        if wsplit:
+            d = ops.conv_desc(kind, B, 2 * cin, cout, L, k, dilation, pad, stride, leaky=leaky,
+                              alpha=1.0 / ops.W_SPLIT_SCALE)
+            y16, y32 = ops.conv_fwd(d, ops.dup_channels(x16), cache.fwd_wsplit(d, w, kind), b,
+                                    res32=res32, want16=True, want32=True)
+        else:
+            d = ops.conv_desc(kind, B, cin, cout, L, k, dilation, pad, stride, leaky=leaky)
+            y16, y32 = ops.conv_fwd(d, x16, cache.fwd(d, w), b, res32=res32, want16=True,
+                                    want32=True)
         ctx.save_for_backward(x16, w, y16)
         ctx.cfg = (cache, kind, dilation, pad, stride, leaky, b is not None)
         ctx.has_res = res32 is not None
@@ -120,12 +139,12 @@ class ConvBlk(Function):
                 dw = grad_ops.convt_wgrad(x16, dz16, tuple(w.shape), stride, pad)
         if need_x:
             dx32 = _dgrad_conv(cache, w, dz16, kind, dilation, pad, stride)
-        return dx32, None, dw, db, None, None, None, None, None, None, dres
+        return dx32, None, dw, db, None, None, None, None, None, None, dres, None
 
 
-def conv_blk(x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32=None):
+def conv_blk(x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32=None, wsplit=False):
     """ConvBlk.apply with every argument spelled out (autograd wants one gradient per argument)"""
-    return ConvBlk.apply(x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32)
+    return ConvBlk.apply(x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32, wsplit)
 
 
 class ResidualAtomBlk(Function):
@@ -350,11 +369,11 @@ class BankSynthesis(Function):
     backward = ms_diag_sum_bwd -> bf16 operand -> input-gradient conv with the bank weights."""
 
     @staticmethod
-    def forward(ctx, h32, h16, bank):
+    def forward(ctx, h32, h16, bank, wsplit=False):
         L = h16.shape[2]
         ctx.bank = bank
         ctx.shape = tuple(h16.shape)
-        return bank.transposed_convolve_blocked(h16, L)
+        return bank.transposed_convolve_blocked(h16, L, wsplit)
 
     @staticmethod
     def backward(ctx, dy):
@@ -366,7 +385,7 @@ class BankSynthesis(Function):
         dz16, _ = grad_ops.act_bwd(dz32, want_bias=False)
         w = bank.synthesis_weight(dy.device)
         cache = bank.__dict__.setdefault("_synth_dgrad_cache", WeightCache())
-        return _dgrad_conv(cache, w, dz16, MS_CONV, 8, k // 2, 1), None, None
+        return _dgrad_conv(cache, w, dz16, MS_CONV, 8, k // 2, 1), None, None, None
 
 
 class BankAnalysis(Function):

@@ -79,7 +79,7 @@ __global__ void pack_ncl_split_blk16_kernel(const float* __restrict__ x, uint4* 
 // weight of the three-term split conv: out (Co, 3*Ci, K) = [w, w, w - to16(w)] along Ci, so that
 // [x_hi, x_lo, x_hi] * [W_hi, W_hi, W_lo] = x*W to ~2^-22 after the 16-bit pack
 __global__ void weight_split_kernel(const float* __restrict__ w, float* __restrict__ out, int Ci,
-                                    int K, int operand, float scale, size_t total) {
+                                    int K, int operand, float scale, int terms, size_t total) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   const int k = static_cast<int>(i % K);
@@ -88,10 +88,50 @@ __global__ void weight_split_kernel(const float* __restrict__ w, float* __restri
   const float v = scale * __ldg(w + i);
   const float hi = operand == MS_BF16 ? __bfloat162float(__float2bfloat16_rn(v))
                                       : __half2float(__float2half_rn(v));
-  float* o = out + (co * 3 * Ci) * K;
+  float* o = out + (co * terms * Ci) * K;
   o[(static_cast<size_t>(ci)) * K + k] = v;
-  o[(static_cast<size_t>(Ci + ci)) * K + k] = v;
-  o[(static_cast<size_t>(2 * Ci + ci)) * K + k] = v - hi;
+  if (terms == 3) o[(static_cast<size_t>(Ci + ci)) * K + k] = v;
+  o[(static_cast<size_t>((terms - 1) * Ci + ci)) * K + k] = v - hi;
+}
+
+// (hi, lo[, hi]) split of a BLK f32 tensor (B, C/8, L, 8) into the channel thirds / halves of a
+// BLK 16-bit tensor (B, terms*C/8, L, 8); optional LeakyReLU / zero or reflection padding first
+// (the activation + padding in front of the convs of a layer-wise chain)
+__global__ void blk32_split_blk16_kernel(const float* __restrict__ x, uint4* __restrict__ y,
+                                         int C8, int L, int pad, int pad_mode, int leaky,
+                                         int operand, int terms, float scale, size_t total) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int Lp = L + 2 * pad;
+  const int tp = static_cast<int>(i % Lp);
+  const size_t bc = i / Lp;            // b * C8 + c8
+  const size_t b = bc / C8;
+  const int c8 = static_cast<int>(bc - b * C8);
+  int t = tp - pad;
+  bool zero = false;
+  if (t < 0 || t >= L) {
+    if (pad_mode == 1) t = t < 0 ? -t : 2 * (L - 1) - t;
+    else zero = true;
+  }
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lo[8];
+  if (!zero) ld_global_nc_v8(x + (bc * L + t) * 8, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = scale * (leaky ? leaky02(f[j]) : f[j]);
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = pack2op(f[2 * j], f[2 * j + 1], operand);
+    float2 back;
+    if (operand == MS_BF16) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h[j]));
+    else back = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+    lo[2 * j] = f[2 * j] - back.x;
+    lo[2 * j + 1] = f[2 * j + 1] - back.y;
+  }
+  y[(b * terms * C8 + c8) * Lp + tp] = make_uint4(h[0], h[1], h[2], h[3]);
+  if (terms == 3) y[(b * terms * C8 + 2 * C8 + c8) * Lp + tp] = make_uint4(h[0], h[1], h[2], h[3]);
+  y[(b * terms * C8 + C8 + c8) * Lp + tp] =
+      make_uint4(pack2op(lo[0], lo[1], operand), pack2op(lo[2], lo[3], operand),
+                 pack2op(lo[4], lo[5], operand), pack2op(lo[6], lo[7], operand));
 }
 
 __global__ void unpack_blk32_to_ncl_kernel(const float4* __restrict__ x, float* __restrict__ y,
@@ -373,12 +413,29 @@ using namespace msb;
 extern "C" {
 
 ms_status ms_weight_split(const float* w, float* out, int cout, int cin, int ksize, int operand,
-                          float scale, void* stream) {
-  if (w == nullptr || out == nullptr || cout <= 0 || cin <= 0 || ksize <= 0) return MS_ERR_INVALID;
+                          float scale, int terms, void* stream) {
+  if (w == nullptr || out == nullptr || cout <= 0 || cin <= 0 || ksize <= 0 ||
+      (terms != 2 && terms != 3))
+    return MS_ERR_INVALID;
   const size_t total = static_cast<size_t>(cout) * cin * ksize;
   weight_split_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
-                        static_cast<cudaStream_t>(stream)>>>(w, out, cin, ksize, operand, scale, total);
+                        static_cast<cudaStream_t>(stream)>>>(w, out, cin, ksize, operand, scale,
+                                                             terms, total);
   return after_launch("weight_split_kernel");
+}
+
+ms_status ms_blk32_split_blk16(const float* x32, void* y16, int batch, int channels, int len,
+                               int pad, int pad_mode, int leaky, int operand, int terms,
+                               float scale, void* stream) {
+  if (x32 == nullptr || y16 == nullptr || batch <= 0 || channels <= 0 || channels % 8 != 0 ||
+      len <= 0 || pad < 0 || (pad_mode == 1 && pad >= len) || (terms != 2 && terms != 3))
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * (len + 2 * pad);
+  blk32_split_blk16_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(
+      x32, static_cast<uint4*>(y16), channels / 8, len, pad, pad_mode, leaky, operand, terms,
+      scale, total);
+  return after_launch("blk32_split_blk16_kernel");
 }
 
 ms_status ms_pack_ncl_split_blk16(const float* x, void* y16, int batch, int channels, int len,

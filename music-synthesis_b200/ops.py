@@ -49,15 +49,45 @@ def pack_ncl_split(x, operand=MS_F16, terms=2, scale=1.0):
     return y
 
 
-def weight_split(w, operand=MS_F16, scale=1.0):
-    """(Cout,Cin,K) -> (Cout,3Cin,K) = [w, w, w - to16(w)] (see ms_weight_split)"""
+def weight_split(w, operand=MS_F16, scale=1.0, terms=3, kind=MS_CONV):
+    """Split-precision weight along the INPUT-channel axis (see ms_weight_split): a Conv1d
+    weight (Cout,Cin,K) -> (Cout,terms*Cin,K), a ConvTranspose1d weight (Cin,Cout,K) ->
+    (terms*Cin,Cout,K); terms 3 = [w, w, w - to16(w)], terms 2 = [w, w - to16(w)]."""
     w = w.contiguous()
-    cout, cin, k = w.shape
-    out = torch.empty((cout, 3 * cin, k), dtype=torch.float32, device=w.device)
-    check(_lib.lib().ms_weight_split(ptr(w), ptr(out), cout, cin, k, operand, float(scale),
+    if kind == MS_CONV:
+        cout, cin, k = w.shape
+        out = torch.empty((cout, terms * cin, k), dtype=torch.float32, device=w.device)
+        args = (cout, cin, k)
+    else:
+        cin, cout, k = w.shape
+        out = torch.empty((terms * cin, cout, k), dtype=torch.float32, device=w.device)
+        args = (1, cin, cout * k)
+    check(_lib.lib().ms_weight_split(ptr(w), ptr(out), *args, operand, float(scale), terms,
                                      stream_ptr()),
           "ms_weight_split")
     return out
+
+
+#: power-of-two weight scale of the weight-split forward: N(0, 0.02)-sized weights give lo terms
+#: of ~1e-5, inside the fp16 subnormals; x256 moves them to ~2.5e-3 (overflow beyond |w| ~ 250)
+W_SPLIT_SCALE = 256.0
+
+
+def dup_channels(x16, times=2):
+    """BLK 16-bit (B,C/8,L,8) -> (B,times*C/8,L,8): the operand of a weight-split conv (data
+    movement only)"""
+    return torch.cat([x16] * times, dim=1)
+
+
+def blk32_split(x32, pad=0, pad_mode=0, leaky=False, operand=MS_BF16, terms=3, scale=1.0):
+    """BLK f32 (B,C/8,L,8) -> split BLK 16-bit (B,terms*C/8,L+2*pad,8) = [hi, lo(, hi)] of
+    act(pad(x)) (see ms_blk32_split_blk16)"""
+    B, C8, L, _ = x32.shape
+    y = torch.empty((B, terms * C8, L + 2 * pad, 8), dtype=torch.int16, device=x32.device)
+    check(_lib.lib().ms_blk32_split_blk16(ptr(x32.contiguous()), ptr(y), B, C8 * 8, L, pad,
+                                          pad_mode, int(leaky), operand, terms, float(scale),
+                                          stream_ptr()), "ms_blk32_split_blk16")
+    return y
 
 
 def unpack_blk32(x32):

@@ -100,12 +100,15 @@ class _Graphed:
         self.graph = None
         self.samples = self.features = None
         self.outputs = None
+        self.launches = 0           # kernel launches recorded in the graph
 
 
 class _GraphMixin:
     def _init_graph(self, cuda_graph):
         self.cuda_graph = cuda_graph
         self._graphs = {}
+        #: library kernel launches inside the most recently captured step graph
+        self.graph_launches = 0
 
     def _all_params(self):
         return list(self.generator.parameters()) + list(self.discriminator.parameters())
@@ -164,8 +167,12 @@ class _GraphMixin:
                 torch.autograd.graph.increment_version(p)
             torch.cuda.synchronize()
             st.graph = torch.cuda.CUDAGraph()
+            from .. import _lib
+            n0 = _lib.launch_count()
             with torch.cuda.graph(st.graph):
                 st.outputs = self._fwd_bwd(st.samples, st.features)
+            st.launches = _lib.launch_count() - n0
+            self.graph_launches = st.launches
         if multi:
             for k, v in samples.items():
                 st.samples[k].copy_(v)
