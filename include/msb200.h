@@ -135,6 +135,15 @@ ms_status ms_weight_split(const float* w, float* out, int cout, int cin, int ksi
 ms_status ms_blk32_split_blk16(const float* x32, void* y16, int batch, int channels, int len,
                                int pad, int pad_mode, int leaky, int operand, int terms,
                                float scale, void* stream);
+/* front end of LowResSpectrogramDiscriminator (util/modules.py:315-325): relu, then the mean
+ * over (channel_window x time_window) windows: BLK f32 (B,C/8,L,8) -> BLK f32 and/or 16-bit
+ * (B,(C/cw)/8,L/tw,8).  cw must divide 8 or be a multiple of 8; tw must divide L. */
+ms_status ms_relu_avgpool2d_fwd(const float* x32, void* y16, float* y32, int batch, int channels,
+                                int len, int channel_window, int time_window, int operand,
+                                void* stream);
+ms_status ms_relu_avgpool2d_bwd(const float* dy32, const float* x32, float* dx32, int batch,
+                                int channels, int len, int channel_window, int time_window,
+                                void* stream);
 /* space-to-depth along time: BLK 16-bit (B,C/8,src_rows,8) -> (B, s*C/8, ceil(len/s), 8) with
  * Y[u, i*C + c] = X[s*u + i, c] for s*u + i < len (0 beyond).  Turns the stride-s k7 convs of
  * featuresynth/discriminator/multiscale.py:83-88 into stride-1 convs over s*C channels. */
@@ -319,8 +328,11 @@ ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya3
  * packed with ms_conv_pack_weight and run with ms_conv_fwd:
  *   MS_CONV  w (cout,cin,k)  -> out (cin,cout,k) tap-reversed; run as MS_CONV cin'=cout,
  *            cout'=cin, same k / dilation, pad' = dilation*(k-1) - pad;
- *   MS_CONVT w (cin,cout,2s) -> out (cin, s*cout, 3); run as MS_CONV over the space-to-depth
- *            gradient (s*cout channels), k 3, pad 1. */
+ *   MS_CONVT w (cin,cout,k), k = J*s -> out (cin, s*cout, ntaps); run as MS_CONV over the
+ *            space-to-depth gradient (s*cout channels), ntaps taps, pad = -first_shift, with
+ *            ntaps / first_shift from ms_convt_dgrad_taps (k = 2s, pad = s/2: 3 taps, shift -1;
+ *            k = 4s, pad = 3s/2: 5 taps, shift -2). */
+int ms_convt_dgrad_taps(int ksize, int stride, int pad, int* first_shift);
 ms_status ms_weight_dgrad_view(const float* w, float* out, int kind, int cout, int cin, int ksize,
                                int stride, int pad, void* stream);
 /* Weight gradient as a tcgen05 GEMM reduced over time (MN-major operands straight from the
@@ -328,8 +340,9 @@ ms_status ms_weight_dgrad_view(const float* w, float* out, int kind, int cout, i
  * (rows outside [0,lx) are zero), scattered into dw:
  *   mode MS_CONV : Conv1d weight (cout=cm, cin=cn, k=taps); a16 = dz, x16 = layer input,
  *                  shifts[t] = t*dilation - pad;
- *   mode MS_CONVT: ConvTranspose1d weight (cin=cm, cout, 2*stride); a16 = layer input,
- *                  x16 = space-to-depth dz (cn = stride*cout), shifts = {-1,0,1}.
+ *   mode MS_CONVT: ConvTranspose1d weight (cin=cm, cout, ksize); a16 = layer input,
+ *                  x16 = space-to-depth dz (cn = stride*cout), shifts = first_shift ..
+ *                  first_shift + ntaps - 1 of ms_convt_dgrad_taps ({-1,0,1} for k = 2*stride).
  * fmt: MS_F16 | MS_BF16 of BOTH operands (tcgen05 kind::f16 does not mix them: a mixed
  * instruction descriptor raises an illegal-instruction fault on sm_100a).  dw = beta*dw + alpha*G.
  * fold = 2 (MS_CONV): x16 holds a two-term split (ms_pack_ncl_split_blk16) of the layer input in
@@ -338,7 +351,7 @@ size_t ms_wgrad_workspace_bytes(int batch, int cm, int cn, int la, int lx, int t
                                 const int* shifts);
 ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int cn, int la,
                        int lx, int taps, const int* shifts, int fmt, int mode, int stride,
-                       int pad, int cout, int fold, float alpha, float beta, float* dw,
+                       int pad, int cout, int ksize, int fold, float alpha, float beta, float* dw,
                        void* workspace, size_t workspace_bytes, void* stream);
 /* 16-bit operand format conversion (fp16 forward activations -> bf16 for the weight-gradient
  * GEMM, whose other operand is a bf16 gradient) */

@@ -46,6 +46,10 @@ SIGNATURES = {
                                         c_void_p]),
     "ms_diag_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_void_p]),
+    "ms_relu_avgpool2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_void_p]),
+    "ms_relu_avgpool2d_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_int, c_void_p]),
     "ms_space_to_depth_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p]),
     "ms_conv_to_mono": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -84,13 +88,14 @@ SIGNATURES = {
     "ms_blk_act_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "ms_blk_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "ms_convt_dgrad_taps": (c_int, [c_int, c_int, c_int, POINTER(c_int)]),
     "ms_weight_dgrad_view": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "ms_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int,
                                             POINTER(c_int)]),
     "ms_wgrad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                             POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                             c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+                             POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                             c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ms_pack_ncl_split_blk16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                         c_float, c_void_p]),
     "ms_weight_split": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,

@@ -57,10 +57,16 @@ def morlet_bank(samplerate, kernel_size, center_frequencies, scaling_factor=0.05
 
 
 class FilterBank:
+    """kernel_size: any length up to 512 taps.  Internally the bank is zero-padded at the end to
+    kp = the next multiple of 16 taps (a no-op on both operations); banks of more than 128 taps
+    (the 511-tap bank of experiment/filterbank.py:34-45) use 16 synthesis phases, shorter ones 8.
+    torch conventions kept: `convolve` = conv1d(padding = k // 2) -> L + 1 rows for even k, L for
+    odd k; `transposed_convolve` = conv_transpose1d(padding = k // 2)."""
+
     def __init__(self, samplerate, kernel_size, center_frequencies, scaling_factors=0.05,
                  normalize_filters=True, a_weighting=False, operand=MS_F16, bank=None):
-        if kernel_size % 16 != 0 or kernel_size > 128:
-            raise NotImplementedError("FilterBank: kernel_size must be a multiple of 16, <= 128")
+        if kernel_size < 16 or kernel_size > 512:
+            raise NotImplementedError("FilterBank: 16 <= kernel_size <= 512")
         self.samplerate = samplerate
         self.kernel_size = kernel_size
         self.operand = operand
@@ -72,6 +78,14 @@ class FilterBank:
         if self.n_bands % 16 != 0:
             raise NotImplementedError("FilterBank: n_bands must be a multiple of 16")
         self.filter_bank = bank.reshape(self.n_bands, 1, kernel_size)
+        self.pad = kernel_size // 2                       # torch padding of both operations
+        self.kp = (kernel_size + 15) // 16 * 16           # padded tap count
+        self.extra = 1 - kernel_size % 2                  # convolve returns L + extra rows
+        # synthesis as a conv: nph phase channels, kp / nph taps of dilation nph, padding syn_pad,
+        # then y[t] = sum_i z[t + i + 1, i] (ms_diag_sum, skew 1)
+        self.syn_nph = 16 if self.kp > 128 else 8
+        self.syn_taps = self.kp // self.syn_nph
+        self.syn_pad = kernel_size - self.pad
         self._packed = {}
 
     def to(self, device):
@@ -79,17 +93,30 @@ class FilterBank:
         self._packed = {}
         return self
 
-    # -- analysis: conv1d(x, bank, padding=k/2) -> (B, n, L+1) ------------------------------
+    def _padded(self, device, flip=False):
+        n, k = self.n_bands, self.kernel_size
+        b = self.filter_bank.to(device).reshape(n, k)
+        if flip:
+            b = torch.flip(b, dims=[1])
+        if self.kp != k:
+            b = torch.cat([b, torch.zeros((n, self.kp - k), dtype=b.dtype, device=device)], dim=1)
+        return b
+
+    # -- analysis: conv1d(x, bank, padding=k//2) -> (B, n, L + extra) -------------------------
+    def analysis_len(self, L):
+        return L + 2 * self.pad - self.kernel_size + 1
+
     def _analysis(self, x, want16, want32):
         _lib.require_cuda(x, "x")
         L = x.shape[-1]
         x = x.reshape(-1, 1, L).contiguous()
-        B, k, n = x.shape[0], self.kernel_size, self.n_bands
-        taps = k // 16
-        Lx = L + 1 + 16 * (taps - 1)
+        B, n = x.shape[0], self.n_bands
+        taps = self.kp // 16
+        Lx = self.analysis_len(L) + 16 * (taps - 1)
         x16 = torch.empty((B, 2, Lx, 8), dtype=torch.int16, device=x.device)
-        check(_lib.lib().ms_expand_mono_to_blk16(ptr(x), ptr(x16), B, L, Lx, k // 2, self.operand,
-                                                 stream_ptr()), "ms_expand_mono_to_blk16")
+        check(_lib.lib().ms_expand_mono_to_blk16(ptr(x), ptr(x16), B, L, Lx, self.pad,
+                                                 self.operand, stream_ptr()),
+              "ms_expand_mono_to_blk16")
         d = ops.conv_desc(MS_CONV, B, 16, n, Lx, taps, 16, 0, operand=self.operand)
         key = ("a", x.device)
         if key not in self._packed:
@@ -97,70 +124,82 @@ class FilterBank:
         return ops.conv_fwd(d, x16, self._packed[key], None, want16=want16, want32=want32)
 
     def analysis_weight(self, device):
-        """(n, 16, k/16) weight of the analysis conv over the 16-wide sliding-window expansion:
+        """(n, 16, kp/16) weight of the analysis conv over the 16-wide sliding-window expansion:
         W[f, i, j] = bank[f, 16 j + i]"""
-        n, taps = self.n_bands, self.kernel_size // 16
-        return self.filter_bank.to(device).reshape(n, taps, 16).permute(0, 2, 1).contiguous()
+        n, taps = self.n_bands, self.kp // 16
+        return self._padded(device).reshape(n, taps, 16).permute(0, 2, 1).contiguous()
 
     def synthesis_weight(self, device):
-        """(16, n, k/8) weight of the synthesis conv (8 phase channels used):
-        Wg[i, c, j] = flip(bank)[c, 8 j + i]"""
-        n, k = self.n_bands, self.kernel_size
-        taps = k // 8
-        wf = torch.flip(self.filter_bank.to(device).reshape(n, k), dims=[1])
+        """(16, n, kp/nph) weight of the synthesis conv (nph phase channels used):
+        Wg[i, c, j] = flip(bank)[c, nph j + i]"""
+        n, nph, taps = self.n_bands, self.syn_nph, self.syn_taps
+        wf = self._padded(device, flip=True)
         w = torch.zeros((16, n, taps), dtype=torch.float32, device=device)
-        w[:8] = wf.reshape(n, taps, 8).permute(2, 0, 1)
+        w[:nph] = wf.reshape(n, taps, nph).permute(2, 0, 1)
         return w.contiguous()
 
     def convolve(self, x):
         return ops.unpack_blk32(self._analysis(x, False, True)[1])
 
     def convolve_blocked(self, x):
-        """Same as `convolve` but returns the channel-blocked 16-bit tensor (B, n/8, L+1, 8)
+        """Same as `convolve` but returns the channel-blocked 16-bit tensor (B, n/8, L+extra, 8)
         the next tcgen05 conv consumes directly."""
         return self._analysis(x, True, False)[0]
 
-    # -- synthesis: conv_transpose1d(x(B,n,L+1), bank, padding=k/2) -> (B,1,L) --------------
-    def _synth_weights(self, d, device, wsplit=False):
-        key = ("s2" if wsplit else "s", device)
+    # -- synthesis: conv_transpose1d(x(B,n,L+extra), bank, padding=k//2) -> (B,1,L) -----------
+    #: power-of-two operand scales of the full-split synthesis (activations of ~1e-2, unit-norm
+    #: filters of ~5e-2 per tap: keeps the lo terms out of the fp16 subnormals)
+    SPLIT_SX, SPLIT_SW = 64.0, 256.0
+
+    def _synth_weights(self, d, device, wsplit=0):
+        key = ("s%d" % int(wsplit), device)
         if key not in self._packed:
             w = self.synthesis_weight(device)
-            if wsplit:
+            if wsplit == 2:
+                w = ops.weight_split(w, self.operand, self.SPLIT_SW, terms=3)
+            elif wsplit:
                 w = ops.weight_split(w, self.operand, ops.W_SPLIT_SCALE, terms=2)
             self._packed[key] = ops.pack_conv_weight(d, w)
         return self._packed[key]
 
-    def transposed_convolve_blocked(self, x16, L, wsplit=False):
-        """x16: BLK 16-bit (B, n/8, L, 8) holding rows 0..L-1 of the (zero-padded to L+1)
-        input of `transposed_convolve`; returns (B, 1, L) f32.  wsplit: bank weights as a
-        (hi, lo) pair over the duplicated operand (no weight rounding)."""
-        B = x16.shape[0]
-        n, k = self.n_bands, self.kernel_size
-        if wsplit:
-            d = ops.conv_desc(MS_CONV, B, 2 * n, 16, L, k // 8, 8, k // 2, operand=self.operand,
-                              alpha=1.0 / ops.W_SPLIT_SCALE)
+    def synthesis_rows(self, L):
+        """rows of the phase tensor z for L input rows"""
+        return L + 2 * self.syn_pad - self.syn_nph * (self.syn_taps - 1)
+
+    def _synthesis(self, x16, Lin, Lout, wsplit, x32=None):
+        """wsplit: 0 = 16-bit operands, 1 = weight split over the duplicated operand, 2 = full
+        split precision from the fp32 activations x32.  The synthesis output is a heavily
+        cancelling sum (narrow-band filters over a broadband input): rounding its INPUT to fp16
+        alone puts 1.9e-3 on the waveform of the 511-tap bank (5e-4 for the 128-tap banks)."""
+        B, n = x16.shape[0], self.n_bands
+        if wsplit == 2:
+            if x32 is None:
+                raise _lib.MsbError("full-split synthesis needs the fp32 activations")
+            mult, alpha = 3, 1.0 / (self.SPLIT_SX * self.SPLIT_SW)
+            x16 = ops.blk32_split(x32, operand=self.operand, terms=3, scale=self.SPLIT_SX)
+        elif wsplit:
+            mult, alpha = 2, 1.0 / ops.W_SPLIT_SCALE
             x16 = ops.dup_channels(x16)
         else:
-            d = ops.conv_desc(MS_CONV, B, n, 16, L, k // 8, 8, k // 2, operand=self.operand)
+            mult, alpha = 1, 1.0
+        d = ops.conv_desc(MS_CONV, B, mult * n, 16, Lin, self.syn_taps, self.syn_nph, self.syn_pad,
+                          operand=self.operand, alpha=alpha)
         _, z32 = ops.conv_fwd(d, x16, self._synth_weights(d, x16.device, wsplit), None,
                               want16=False, want32=True)
-        Lz = z32.shape[2]
-        y = torch.empty((B, 1, L), dtype=torch.float32, device=x16.device)
-        check(_lib.lib().ms_diag_sum(ptr(z32), ptr(y), B, 16, Lz, L, 8, 1, stream_ptr()),
-              "ms_diag_sum")
+        y = torch.empty((B, 1, Lout), dtype=torch.float32, device=x16.device)
+        check(_lib.lib().ms_diag_sum(ptr(z32), ptr(y), B, 16, z32.shape[2], Lout, self.syn_nph, 1,
+                                     stream_ptr()), "ms_diag_sum")
         return y
+
+    def transposed_convolve_blocked(self, x16, L, wsplit=0, x32=None):
+        """x16: BLK 16-bit (B, n/8, L, 8) holding rows 0..L-1 of the input of
+        `transposed_convolve` (for an even kernel the reference appends one zero row first,
+        generator/multiscale.py:90 -- it contributes nothing); returns (B, 1, L) f32.  wsplit:
+        bank weights as a (hi, lo) pair over the duplicated operand (no weight rounding)."""
+        return self._synthesis(x16, L, L, wsplit, x32)
 
     def transposed_convolve(self, x):
         _lib.require_cuda(x, "x")
         B, n, Lp = x.shape
-        # the last input row only ever meets taps that fall outside the output: it is the
-        # reference's F.pad(x, (0, 1)) zero (generator/multiscale.py:90) -- but keep general
         x16 = ops.pack_ncl(x.contiguous(), operand=self.operand)
-        d = ops.conv_desc(MS_CONV, B, n, 16, Lp, self.kernel_size // 8, 8, self.kernel_size // 2,
-                          operand=self.operand)
-        _, z32 = ops.conv_fwd(d, x16, self._synth_weights(d, x.device), None,
-                              want16=False, want32=True)
-        y = torch.empty((B, 1, Lp - 1), dtype=torch.float32, device=x.device)
-        check(_lib.lib().ms_diag_sum(ptr(z32), ptr(y), B, 16, z32.shape[2], Lp - 1, 8, 1,
-                                     stream_ptr()), "ms_diag_sum")
-        return y
+        return self._synthesis(x16, Lp, Lp - self.extra, 0)

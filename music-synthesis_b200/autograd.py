@@ -64,6 +64,14 @@ class WeightCache:
             self._fwd = (key, ops.pack_conv_weight(desc, ws))
         return self._fwd[1]
 
+    def fwd_split3(self, desc, w, kind):
+        """forward image of [W_hi, W_hi, W_lo] for a Conv1d or ConvTranspose1d weight"""
+        key = self._key(w, desc)
+        if self._fwd[0] != key:
+            ws = ops.weight_split(w.detach(), scale=SPLIT_SW, terms=3, kind=kind)
+            self._fwd = (key, ops.pack_conv_weight(desc, ws))
+        return self._fwd[1]
+
     def dgrad(self, desc, w, kind, stride, pad):
         key = self._key(w, desc)
         if self._bwd[0] != key:
@@ -84,7 +92,8 @@ def _dgrad_conv(cache, w, dz16, kind, dilation, pad, stride, res32=None, extra_p
                           dilation * (k - 1) - pad + extra_pad, operand=GRAD_FMT)
     else:
         cin, cout, k = w.shape
-        d = ops.conv_desc(MS_CONV, B, stride * cout, cin, L, 3, 1, 1, operand=GRAD_FMT)
+        ntaps, first = grad_ops.convt_dgrad_taps(k, stride, pad)
+        d = ops.conv_desc(MS_CONV, B, stride * cout, cin, L, ntaps, 1, -first, operand=GRAD_FMT)
     _, dx32 = ops.conv_fwd(d, dz16, cache.dgrad(d, w, kind, stride, pad), None, res32=res32,
                            want16=False, want32=True)
     return dx32
@@ -98,8 +107,8 @@ class ConvBlk(Function):
     def forward(ctx, x32, x16, w, b, cache, kind, dilation, pad, stride, leaky, res32=None,
                 wsplit=False):
         """res32 (optional, BLK f32): added after the activation, y = act(conv + b) + res32.
-        wsplit: weight-split forward ([x, x] * [W_hi, W_lo]: no weight rounding, 2x the MMA work);
-        the backward is the same either way."""
+        wsplit: 1 = weight-split forward ([x, x] * [W_hi, W_lo]: no weight rounding, 2x the MMA
+        work), 2 = full split precision (3x); the backward is the same either way."""
         B, _, L, _ = x16.shape
         if kind == MS_CONV:
             cout, cin, k = w.shape
@@ -107,7 +116,16 @@ class ConvBlk(Function):
             cin, cout, k = w.shape
         if res32 is not None and leaky:
             raise _lib.MsbError("ConvBlk: residual input only with a linear epilogue")
-        if wsplit:
+        if wsplit == 2:
+            # full split precision: [x_hi, x_lo, x_hi] * [W_hi, W_hi, W_lo] = x*W to ~2^-22
+            if x32 is None:
+                raise _lib.MsbError("ConvBlk: the full-split forward needs the fp32 input")
+            d = ops.conv_desc(kind, B, 3 * cin, cout, L, k, dilation, pad, stride, leaky=leaky,
+                              alpha=1.0 / (SPLIT_SX * SPLIT_SW))
+            xs = ops.blk32_split(x32, operand=MS_F16, terms=3, scale=SPLIT_SX)
+            y16, y32 = ops.conv_fwd(d, xs, cache.fwd_split3(d, w, kind), b, res32=res32,
+                                    want16=True, want32=True)
+        elif wsplit:
             d = ops.conv_desc(kind, B, 2 * cin, cout, L, k, dilation, pad, stride, leaky=leaky,
                               alpha=1.0 / ops.W_SPLIT_SCALE)
             y16, y32 = ops.conv_fwd(d, ops.dup_channels(x16), cache.fwd_wsplit(d, w, kind), b,
@@ -373,19 +391,17 @@ class BankSynthesis(Function):
         L = h16.shape[2]
         ctx.bank = bank
         ctx.shape = tuple(h16.shape)
-        return bank.transposed_convolve_blocked(h16, L, wsplit)
+        return bank.transposed_convolve_blocked(h16, L, wsplit, h32 if wsplit == 2 else None)
 
     @staticmethod
     def backward(ctx, dy):
         bank = ctx.bank
         B, _, L, _ = ctx.shape
-        k = bank.kernel_size
-        lz = L + 2 * (k // 2) - 8 * (k // 8 - 1)
-        dz32 = grad_ops.diag_sum_bwd(dy, 16, lz, 8, 1)
+        dz32 = grad_ops.diag_sum_bwd(dy, 16, bank.synthesis_rows(L), bank.syn_nph, 1)
         dz16, _ = grad_ops.act_bwd(dz32, want_bias=False)
         w = bank.synthesis_weight(dy.device)
         cache = bank.__dict__.setdefault("_synth_dgrad_cache", WeightCache())
-        return _dgrad_conv(cache, w, dz16, MS_CONV, 8, k // 2, 1), None, None, None
+        return _dgrad_conv(cache, w, dz16, MS_CONV, bank.syn_nph, bank.syn_pad, 1), None, None, None
 
 
 class BankAnalysis(Function):
@@ -404,12 +420,11 @@ class BankAnalysis(Function):
     @staticmethod
     def backward(ctx, da32, _unused):
         bank = ctx.bank
-        k = bank.kernel_size
         dz16, _ = grad_ops.act_bwd(da32, want_bias=False)
         w = bank.analysis_weight(da32.device)
         cache = bank.__dict__.setdefault("_analysis_dgrad_cache", WeightCache())
         de32 = _dgrad_conv(cache, w, dz16, MS_CONV, 16, 0, 1)
-        return grad_ops.expand_mono_bwd(de32, ctx.L, k // 2), None
+        return grad_ops.expand_mono_bwd(de32, ctx.L, bank.pad), None
 
 
 class StridedCache:
@@ -474,6 +489,35 @@ class StridedConvBlk(Function):
             dx32 = grad_ops.depth_to_space32(dxs, cin, stride, in_rows, length, rows_valid=lx,
                                              row_offset=crop)
         return dx32, None, dw, db, None, None, None
+
+
+class ReluAvgPool(Function):
+    """front end of LowResSpectrogramDiscriminator (util/modules.py:315-325): relu, then the mean
+    over (channel_window x time_window) windows of a BLK f32 tensor -> (p32, p16)"""
+
+    @staticmethod
+    def forward(ctx, a32, cw, tw):
+        B, C8, L, _ = a32.shape
+        shape = (B, C8 // cw, L // tw, 8)
+        p32 = torch.empty(shape, dtype=torch.float32, device=a32.device)
+        p16 = torch.empty(shape, dtype=torch.int16, device=a32.device)
+        check(_lib.lib().ms_relu_avgpool2d_fwd(ptr(a32.contiguous()), ptr(p16), ptr(p32), B, C8 * 8,
+                                               L, cw, tw, MS_F16, stream_ptr()),
+              "ms_relu_avgpool2d_fwd")
+        ctx.save_for_backward(a32)
+        ctx.cfg = (cw, tw)
+        ctx.mark_non_differentiable(p16)
+        return p32, p16
+
+    @staticmethod
+    def backward(ctx, dp32, _unused):
+        (a32,) = ctx.saved_tensors
+        cw, tw = ctx.cfg
+        B, C8, L, _ = a32.shape
+        dx = torch.empty_like(a32)
+        check(_lib.lib().ms_relu_avgpool2d_bwd(ptr(dp32.contiguous()), ptr(a32), ptr(dx), B, C8 * 8,
+                                               L, cw, tw, stream_ptr()), "ms_relu_avgpool2d_bwd")
+        return dx, None, None
 
 
 class AvgPool(Function):

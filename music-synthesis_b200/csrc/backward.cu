@@ -116,11 +116,12 @@ act_bwd_kernel(const ActBwdParams p) {
 
 // reference-layout weights of the convolution that computes the INPUT gradient:
 //   MS_CONV : w (Co,Ci,K) -> out (Ci,Co,K), out[ci][co][k] = w[co][ci][K-1-k]
-//   MS_CONVT: w (Ci,Co,2s), padding p -> out (Ci, s*Co, 3) over the space-to-depth gradient,
-//             out[ci][r*Co+co][t] = w[ci][co][s*(t-1) + r + p]  (0 where that tap does not exist)
+//   MS_CONVT: w (Ci,Co,K), stride s, padding p -> out (Ci, s*Co, ntaps) over the space-to-depth
+//             gradient, out[ci][r*Co+co][t] = w[ci][co][s*(t + dmin) + r + p]  (0 where that tap
+//             does not exist); ntaps = dmax - dmin + 1, see ms_convt_dgrad_taps
 __global__ void weight_dgrad_view_kernel(const float* __restrict__ w, float* __restrict__ out,
                                          int kind, int co_n, int ci_n, int K, int stride, int pad,
-                                         size_t total) {
+                                         int ntaps, int dmin, size_t total) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= total) return;
   if (kind == MS_CONV) {
@@ -129,11 +130,11 @@ __global__ void weight_dgrad_view_kernel(const float* __restrict__ w, float* __r
     const int ci = static_cast<int>(i / (static_cast<size_t>(K) * co_n));
     out[i] = w[(static_cast<size_t>(co) * ci_n + ci) * K + (K - 1 - k)];
   } else {
-    const int t = static_cast<int>(i % 3);
-    const int n = static_cast<int>((i / 3) % (stride * co_n));
-    const int ci = static_cast<int>(i / (static_cast<size_t>(3) * stride * co_n));
+    const int t = static_cast<int>(i % ntaps);
+    const int n = static_cast<int>((i / ntaps) % (stride * co_n));
+    const int ci = static_cast<int>(i / (static_cast<size_t>(ntaps) * stride * co_n));
     const int r = n / co_n, co = n - r * co_n;
-    const int k = stride * (t - 1) + r + pad;
+    const int k = stride * (t + dmin) + r + pad;
     out[i] = (k >= 0 && k < K) ? w[(static_cast<size_t>(ci) * co_n + co) * K + k] : 0.f;
   }
 }
@@ -292,6 +293,29 @@ __global__ void weight_norm_bwd_kernel(const float* __restrict__ dw, const float
   if (threadIdx.x == 0) dg[blockIdx.x] = dgr;
   for (int i = threadIdx.x; i < cols; i += blockDim.x)
     dv[base + i] = (gr / n) * (dw[base + i] - (dgr / n) * v[base + i]);
+}
+
+// gradient of ms_relu_avgpool2d_fwd: dx[b,c,t] = (x > 0) * dy[b, c/cw, t/tw] / (cw*tw)
+__global__ void relu_avgpool2d_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                          float* __restrict__ dx, int C8, int L, int cw, int tw,
+                                          size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = static_cast<int>(gid % L);
+  const size_t bc = gid / L;
+  const int c8 = static_cast<int>(bc % C8);
+  const size_t b = bc / C8;
+  const int F = C8 * 8 / cw, S = L / tw;
+  const float inv = 1.f / static_cast<float>(cw * tw);
+  float f[8], g[8];
+  ld_global_nc_v8(x + gid * 8, f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int fo = (c8 * 8 + j) / cw;
+    const float d = __ldg(dy + ((b * (F / 8) + (fo >> 3)) * S + t / tw) * 8 + (fo & 7));
+    g[j] = f[j] > 0.f ? d * inv : 0.f;
+  }
+  st_global_v8(dx + gid * 8, g);
 }
 
 // ------------------------------------------------------------ direct conv backward (NCL f32)
@@ -908,21 +932,32 @@ ms_status ms_blk_act_bwd(const float* dy32, const void* sign16, const float* ya3
   return after_launch("act_bwd_kernel");
 }
 
+int ms_convt_dgrad_taps(int ksize, int stride, int pad, int* first_shift) {
+  if (stride < 1 || ksize < stride || ksize % stride != 0 || pad < 0) return -1;
+  const int dmin = -((pad + stride - 1) / stride);
+  const int dmax = (ksize - 1 - pad) / stride;
+  if (dmax < dmin) return -1;
+  if (first_shift != nullptr) *first_shift = dmin;
+  return dmax - dmin + 1;
+}
+
 ms_status ms_weight_dgrad_view(const float* w, float* out, int kind, int cout, int cin, int ksize,
                                int stride, int pad, void* stream) {
   if (w == nullptr || out == nullptr || cout <= 0 || cin <= 0 || ksize <= 0) return MS_ERR_INVALID;
   size_t total;
+  int ntaps = 0, dmin = 0;
   if (kind == MS_CONV) {
     total = static_cast<size_t>(cin) * cout * ksize;
   } else if (kind == MS_CONVT) {
-    if (stride < 1 || ksize != 2 * stride) return MS_ERR_INVALID;
-    total = static_cast<size_t>(cin) * stride * cout * 3;
+    ntaps = ms_convt_dgrad_taps(ksize, stride, pad, &dmin);
+    if (ntaps < 1) return MS_ERR_INVALID;
+    total = static_cast<size_t>(cin) * stride * cout * ntaps;
   } else {
     return MS_ERR_INVALID;
   }
   weight_dgrad_view_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
                              static_cast<cudaStream_t>(stream)>>>(w, out, kind, cout, cin, ksize,
-                                                                  stride, pad, total);
+                                                                  stride, pad, ntaps, dmin, total);
   return after_launch("weight_dgrad_view_kernel");
 }
 
@@ -1215,6 +1250,20 @@ ms_status ms_blk_act_pad_bwd(const float* dy32, const void* sign16, float* dx32,
                        static_cast<cudaStream_t>(stream)>>>(
       dy32, static_cast<const uint4*>(sign16), dx32, len, pad, pad_mode, total);
   return after_launch("act_pad_bwd_kernel");
+}
+
+ms_status ms_relu_avgpool2d_bwd(const float* dy32, const float* x32, float* dx32, int batch,
+                                int channels, int len, int channel_window, int time_window,
+                                void* stream) {
+  if (dy32 == nullptr || x32 == nullptr || dx32 == nullptr || batch <= 0 || channels <= 0 ||
+      len <= 0 || channel_window < 1 || time_window < 1 || channels % (8 * channel_window) != 0 ||
+      len % time_window != 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * len;
+  relu_avgpool2d_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                              static_cast<cudaStream_t>(stream)>>>(
+      dy32, x32, dx32, channels / 8, len, channel_window, time_window, total);
+  return after_launch("relu_avgpool2d_bwd_kernel");
 }
 
 ms_status ms_weight_norm_bwd(const float* dw, const float* v, const float* g, float* dv, float* dg,

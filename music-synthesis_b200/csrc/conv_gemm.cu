@@ -64,16 +64,23 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     c->Lout = d.lin + 2 * d.pad - d.dilation * (d.ksize - 1) - d.crop;
     c->Lm = c->Lout;
   } else if (d.kind == MS_CONVT) {
-    if (d.stride < 1 || d.ksize != 2 * d.stride) return false;
-    if (d.pad < 1 || d.pad > d.stride) return false;
-    c->taps = 2;
-    c->off[0] = -1;  // weight tap k = r + stride
-    c->off[1] = 0;   // weight tap k = r
+    // polyphase form, J = ksize / stride taps at the input rate:
+    //   out[s*q + r - pad] = sum_{j<J} x[q - j] * W[:, :, r + s*j]
+    // GEMM tap t reads x[q + off[t]], off[t] = t - (J - 1), with weight tap r + s*(J - 1 - t)
+    // (k = 2s: the upsamplers of generator/full.py; k = 4s: LearnedUpSample(.., 8, 2) of
+    // generator/filterbank.py:108-114)
+    if (d.stride < 1 || d.ksize % d.stride != 0) return false;
+    const int J = d.ksize / d.stride;
+    if (J < 2 || J > kMaxTaps) return false;
+    if (d.pad < 0 || d.pad > (J - 1) * d.stride) return false;
+    c->taps = J;
+    for (int t = 0; t < J; ++t) c->off[t] = t - (J - 1);
     c->Ntot = d.stride * d.cout;
     if (c->Ntot % 16 != 0) return false;
     c->Lout = (d.lin - 1) * d.stride - 2 * d.pad + d.ksize;
-    // GEMM rows q = 0 .. lin-1; the extra row q = lin (only tap x[lin-1], last `pad` output
-    // rows of each clip) is computed by convt_tail_kernel so that lin = 256 is ONE tile
+    // GEMM rows q = 0 .. lin-1; the J - 1 extra rows q = lin .. lin+J-2 (they only meet the
+    // last input rows; the last output rows of each clip) are computed by convt_tail_kernel so
+    // that lin = 256 is ONE tile
     c->Lm = d.lin;
   } else {
     return false;
@@ -571,43 +578,49 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 }
 
-// ------------------------------------------------- ConvTranspose tail (GEMM row q = lin)
-// out[b, co, s*lin + r - pad] = act(bias[co] + sum_ci x[b, ci, lin-1] * W[ci, co, r + s]),
-// r < pad.  Reads the SAME packed 16-bit weights / 16-bit activations as the main GEMM
-// (tap 0 of the polyphase form), accumulates in fp32.  Tiny: pad*cout outputs per clip.
+// ------------------------------------- ConvTranspose tail (GEMM rows q = lin .. lin+J-2)
+// out[b, co, s*(lin+e) + r - pad] = act(bias[co] + sum_{t <= J-2-e} sum_ci
+//                                       x[b, ci, lin + e + t - (J-1)] * W[ci, co, r + s*(J-1-t)])
+// Reads the SAME packed 16-bit weights / 16-bit activations as the main GEMM, accumulates in
+// fp32.  Tiny: at most (J-1)*stride*cout outputs per clip.  blockIdx.y = e * stride + r.
 __global__ void convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */,
                                   int nnt_p /* packed n-tiles */) {
-  const int r = blockIdx.y;                 // phase < pad
+  const int e = blockIdx.y / p.stride;      // tail row
+  const int r = blockIdx.y - e * p.stride;  // phase
   const int b = blockIdx.z;
   const int co = blockIdx.x * blockDim.x + threadIdx.x;
   if (co >= p.cout) return;
-  const int orow = p.stride * p.lin + r - p.pad;
+  const int orow = p.stride * (p.lin + e) + r - p.pad;
   if (orow < 0 || orow >= p.Lout) return;
   const int n = convt_col(r, co, p.stride);   // GEMM column
   const int nt = n / ntp, nn = n - nt * ntp;
   const int chunks = p.KB >> 3;
   float acc = 0.f;
-  for (int c8 = 0; c8 < (p.cin >> 3); ++c8) {        // 8 input channels per step (16-byte loads)
-    const int ci = c8 * 8;
-    const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
-    // packed[nt][kb][tap = 0][c][nn][0..7]
-    const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + 0) * chunks + c) * ntp + nn) * 8;
-    const size_t xi = ((static_cast<size_t>(b) * (p.cin >> 3) + c8) * p.lin + (p.lin - 1)) * 8;
-    const uint4 wq = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
-    const uint4 xq = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
-    const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w};
+  for (int t = 0; t <= p.taps - 2 - e; ++t) {
+    const int xrow = p.lin + e + t - (p.taps - 1);
+    if (xrow < 0) continue;
+    for (int c8 = 0; c8 < (p.cin >> 3); ++c8) {      // 8 input channels per step (16-byte loads)
+      const int ci = c8 * 8;
+      const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
+      // packed[nt][kb][tap][c][nn][0..7]
+      const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
+      const size_t xi = ((static_cast<size_t>(b) * (p.cin >> 3) + c8) * p.lin + xrow) * 8;
+      const uint4 wq = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
+      const uint4 xq = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
+      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 wf, xf;
-      if (p.operand == MS_BF16) {
-        wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
-        xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
-      } else {
-        wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
-        xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+      for (int j = 0; j < 4; ++j) {
+        float2 wf, xf;
+        if (p.operand == MS_BF16) {
+          wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+          xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
+        } else {
+          wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+          xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+        }
+        acc = fmaf(xf.x, wf.x, acc);
+        acc = fmaf(xf.y, wf.y, acc);
       }
-      acc = fmaf(xf.x, wf.x, acc);
-      acc = fmaf(xf.y, wf.y, acc);
     }
   }
   float v = acc * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
@@ -650,7 +663,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, uint16_t* __rest
   } else {
     const int ph = convt_col_phase(n, stride);
     const int co = convt_col_channel(n, stride);
-    const int kk = (t == 0) ? ph + stride : ph;
+    const int kk = ph + stride * (taps - 1 - t);
     v = w[(static_cast<size_t>(ci) * cout + co) * ksize + kk];
   }
   if (operand == MS_BF16) {
@@ -692,8 +705,8 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   p.total_tiles = static_cast<int>(tiles);
 
   if (d.kind == MS_CONVT) {
-    // the q = lin row first (independent outputs: last `pad` rows of each clip)
-    dim3 tgrid((d.cout + 127) / 128, d.pad, d.batch);
+    // the rows q >= lin first (independent outputs: the last rows of each clip)
+    dim3 tgrid((d.cout + 127) / 128, (c.taps - 1) * d.stride, d.batch);
     convt_tail_kernel<<<tgrid, 128, 0, stream>>>(p, c.pair ? c.NT / 2 : c.NT,
                                                  c.pair ? 2 * c.nnt : c.nnt);
     ms_status ts = after_launch("convt_tail_kernel");

@@ -7,7 +7,7 @@
 
 namespace msb {
 
-constexpr int kMaxTaps = 24;   // k41 stride-2 convs are 21-tap stride-1 convs over space-to-depth input
+constexpr int kMaxTaps = 32;   // k41 stride-2 convs: 21 taps over space-to-depth input; 511-tap banks: 32 taps of dilation 16
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 3072;          // barriers [0,512) | bias tables [512,2560) | index tables [2560,3072)
 constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100
@@ -15,7 +15,7 @@ constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100
 // Tile configuration + derived geometry, a pure function of the descriptor so that
 // weight packing and the forward launch always agree.
 struct ConvCfg {
-  int taps;            // GEMM taps (MS_CONV: ksize; MS_CONVT: 2)
+  int taps;            // GEMM taps (MS_CONV: ksize; MS_CONVT: ksize / stride)
   int off[kMaxTaps];   // input row of tap t for GEMM row m is m + off[t]
   int pair;            // 1: CTA-pair kernel (cta_group::2, 256-row cluster tile, W split)
   int MBLK;            // 128-row M-blocks per CTA tile (1 or 2): they share each W stage

@@ -294,6 +294,55 @@ __global__ void diag_sum_kernel(const float* __restrict__ z, float* __restrict__
   y[gid] = acc;
 }
 
+// LowResSpectrogramDiscriminator front end (featuresynth/util/modules.py:315-325):
+//   y[b, f, s] = mean over channels [f*cw, (f+1)*cw) x time [s*tw, (s+1)*tw) of relu(x[b, c, t])
+// x: BLK f32 (B, C/8, L, 8) (filter-bank analysis), y: BLK f32 / 16-bit (B, (C/cw)/8, L/tw, 8).
+// One block = one (b, output channel block, s): 8 outputs from 8*cw channels x tw time steps;
+// fixed-order block reduction (warp shuffles, then the warps in order).
+__global__ void __launch_bounds__(128)
+relu_avgpool2d_kernel(const float* __restrict__ x, float* __restrict__ y32,
+                      uint4* __restrict__ y16, int C8, int L, int cw, int tw, int operand) {
+  const int s = blockIdx.x, f8 = blockIdx.y, b = blockIdx.z;
+  const int F8 = gridDim.y, S = gridDim.x;
+  const int nin = cw;                          // input channel blocks feeding this output block
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int i = threadIdx.x; i < nin * tw; i += blockDim.x) {
+    const int ic = i / tw, t = s * tw + (i - ic * tw);
+    const int c8 = f8 * cw + ic;               // input channel block: channels c8*8 .. c8*8+7
+    float f[8];
+    ld_global_nc_v8(x + ((static_cast<size_t>(b) * C8 + c8) * L + t) * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = (ic * 8 + j) / cw;         // output bin within this block (0..7)
+      const float v = fmaxf(f[j], 0.f);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += (q == o) ? v : 0.f;
+    }
+  }
+  __shared__ float sh[4][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = acc[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float inv = 1.f / static_cast<float>(cw * tw);
+    float o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o8[j] = (((sh[0][j] + sh[1][j]) + sh[2][j]) + sh[3][j]) * inv;
+    const size_t oi = (static_cast<size_t>(b) * F8 + f8) * S + s;
+    if (y32 != nullptr) st_global_v8(y32 + oi * 8, o8);
+    if (y16 != nullptr)
+      y16[oi] = make_uint4(pack2op(o8[0], o8[1], operand), pack2op(o8[2], o8[3], operand),
+                           pack2op(o8[4], o8[5], operand), pack2op(o8[6], o8[7], operand));
+  }
+}
+
 // y[b, c, t'] = act(x[b, c, map(t' - pad)]) on channel-blocked tensors: zero (mode 0) or
 // reflection (mode 1) padding with an optional LeakyReLU(0.2) -- the pre-activation +
 // ReflectionPad1d that precede the convs of the official MelGAN blocks
@@ -536,6 +585,21 @@ ms_status ms_diag_sum(const float* z32, float* y, int batch, int channels, int z
                     static_cast<cudaStream_t>(stream)>>>(z32, y, channels / 8, z_len, out_len,
                                                          nphase, skew, total);
   return after_launch("diag_sum_kernel");
+}
+
+ms_status ms_relu_avgpool2d_fwd(const float* x32, void* y16, float* y32, int batch, int channels,
+                                int len, int channel_window, int time_window, int operand,
+                                void* stream) {
+  if (x32 == nullptr || (y16 == nullptr && y32 == nullptr) || batch <= 0 || channels <= 0 ||
+      len <= 0 || channel_window < 1 || time_window < 1 || channels % (8 * channel_window) != 0 ||
+      len % time_window != 0 || (8 % channel_window != 0 && channel_window % 8 != 0))
+    return MS_ERR_INVALID;
+  const int F8 = channels / channel_window / 8, S = len / time_window;
+  if (F8 > 65535 || batch > 65535) return MS_ERR_INVALID;
+  dim3 grid(S, F8, batch);
+  relu_avgpool2d_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x32, y32, static_cast<uint4*>(y16), channels / 8, len, channel_window, time_window, operand);
+  return after_launch("relu_avgpool2d_kernel");
 }
 
 ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, float* y,

@@ -299,7 +299,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 // (fixed order).  fold = 2: the X operand carried a two-term (hi, lo) split of the layer input in
 // its two channel halves -- both halves are gradients of the same weight.
 //   mode MS_CONV : Conv1d weight (Cout = Cm, Cin = Cn/fold, K = taps):   (m*Cin + n)*K + t
-//   mode MS_CONVT: ConvTranspose1d weight (Cin = Cm, Cout, K = 2s); n = r*Cout + co,
+//   mode MS_CONVT: ConvTranspose1d weight (Cin = Cm, Cout, K = ksize); n = r*Cout + co,
 //                  k = s*shift_t + r + pad (taps whose k falls outside [0, K) do not exist)
 // Block = one output row m x 32 consecutive n x 8 split-lanes.  Each thread owns (m, n), ALL
 // taps and every 8th split: reads are 128-byte rows, the (up to 148-long) split loop becomes 8
@@ -309,8 +309,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 constexpr int kRedLanes = 8;
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int nsplit, int taps,
-                    int Cm, int Cn, int fold, int mode, int stride, int pad, int cout, int shift0,
-                    float beta, float alpha, int sl /* split lanes per row: 1, 2, 4 or 8 */) {
+                    int Cm, int Cn, int fold, int mode, int stride, int pad, int cout, int ksize,
+                    int shift0, float beta, float alpha,
+                    int sl /* split lanes per row: 1, 2, 4 or 8 */) {
   __shared__ float sh[kRedLanes][32 * kMaxTaps + 1];
   const int cn_out = Cn / fold;
   const int nx = threadIdx.x & 31, wl = threadIdx.x >> 5;
@@ -352,8 +353,8 @@ wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int
       const int nn = n0 + i / taps, t = i % taps;
       const int r = nn / cout, co = nn - r * cout;
       const int k = stride * (shift0 + t) + r + pad;
-      if (k < 0 || k >= 2 * stride) continue;
-      o = (static_cast<size_t>(m) * cout + co) * (2 * stride) + k;
+      if (k < 0 || k >= ksize) continue;
+      o = (static_cast<size_t>(m) * cout + co) * ksize + k;
     }
     out[o] = (beta != 0.f ? beta * out[o] : 0.f) + alpha * v;
   }
@@ -440,7 +441,7 @@ size_t ms_wgrad_workspace_bytes(int batch, int cm, int cn, int la, int lx, int t
 
 ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int cn, int la,
                        int lx, int taps, const int* shifts, int fmt, int mode, int stride,
-                       int pad, int cout, int fold, float alpha, float beta, float* dw,
+                       int pad, int cout, int ksize, int fold, float alpha, float beta, float* dw,
                        void* workspace, size_t workspace_bytes, void* stream) {
   WgradCfg c;
   if (a16 == nullptr || x16 == nullptr || dw == nullptr || shifts == nullptr ||
@@ -450,7 +451,7 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
   if (mode != MS_CONV && mode != MS_CONVT) return MS_ERR_INVALID;
   if (fold != 1 && !(fold == 2 && mode == MS_CONV && cn % 2 == 0)) return MS_ERR_INVALID;
   if (mode == MS_CONVT) {
-    if (stride < 1 || cout < 1 || cn != stride * cout) return MS_ERR_INVALID;
+    if (stride < 1 || cout < 1 || cn != stride * cout || ksize < stride) return MS_ERR_INVALID;
     for (int t = 1; t < taps; ++t)
       if (shifts[t] != shifts[0] + t) return MS_ERR_INVALID;
   }
@@ -489,7 +490,7 @@ ms_status ms_wgrad_fwd(const void* a16, const void* x16, int batch, int cm, int 
   while (sl < kRedLanes && sl * 2 <= c.ksplit) sl *= 2;
   dim3 rgrid(ceil_div(cn / fold, 32), ceil_div(cm, kRedLanes / sl));
   wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(p.part, dw, c.ksplit, taps, cm, cn, fold, mode, stride,
-                                            pad, cout, shifts[0], beta, alpha, sl);
+                                            pad, cout, ksize, shifts[0], beta, alpha, sl);
   return after_launch("wgrad_reduce_kernel");
 }
 

@@ -8,6 +8,8 @@ with 32 log-mel frames of 128 bins at 22 050 Hz, inference on 4x longer sequence
   FilterBankMultiscaleExperiment                  featuresynth/experiment/multiscale.py:17-63
   MultiScaleNoDeRecomposeUnconditionedShortKernel featuresynth/experiment/multiscale.py:112-155
   MultiScaleNoDeRecompose                         featuresynth/experiment/multiscale.py:158-201
+  FilterBankExperiment                            featuresynth/experiment/filterbank.py:14-78
+  ConditionalFilterBankExperiment                 featuresynth/experiment/filterbank.py:81-128
 """
 from ..audio.representation import MultiScale, RawAudio
 from ..loss import (hinge_discriminator_loss, hinge_generator_loss, least_squares_disc_loss,
@@ -118,3 +120,39 @@ class MultiScaleNoDeRecomposeUnconditionedShortKernel(_BandDictionaryPair):
 
 class MultiScaleNoDeRecompose(_BandDictionaryPair):
     discriminator_options = dict(conditioning_channels=N_MELS)
+
+
+class FilterBankExperiment(_Wired):
+    """experiment/filterbank.py:14-78: FilterBankGenerator + (unconditioned)
+    FilterBankDiscriminator over one fixed 511-tap, 128-band linear-scale Morlet bank
+    (20 Hz .. nyquist - 20 Hz, scaling factor 0.9), least-squares sub-losses, raw audio"""
+    sub_losses = LEAST_SQUARES
+    N_MELS = N_MELS
+    FEATURE_SIZE = FEATURE_SIZE
+    TOTAL_SAMPLES = TOTAL_SAMPLES
+    conditioning_channels = 0
+
+    @classmethod
+    def make_filter_bank(cls, samplerate=SAMPLERATE):
+        from ..audio.filterbank import FilterBank, SampleRate, linear_center_frequencies
+        sr = SampleRate(float(samplerate))
+        return FilterBank(sr, 511, linear_center_frequencies(20, sr.nyquist - 20, 128),
+                          scaling_factors=0.9, normalize_filters=True, a_weighting=False)
+
+    @classmethod
+    def make_generator(cls, filter_bank=None):
+        from ..generator.filterbank import FilterBankGenerator
+        return FilterBankGenerator(filter_bank or cls.make_filter_bank(), FEATURE_SIZE,
+                                   TOTAL_SAMPLES, N_MELS)
+
+    def build(self):
+        from ..discriminator.filterbank import FilterBankDiscriminator
+        return self.make_generator(), FilterBankDiscriminator(
+            self.make_filter_bank(), TOTAL_SAMPLES,
+            conditioning_channels=self.conditioning_channels)
+
+
+class ConditionalFilterBankExperiment(FilterBankExperiment):
+    """experiment/filterbank.py:81-128: the same pair with the discriminator conditioned on the
+    128 log-mel channels"""
+    conditioning_channels = N_MELS

@@ -66,6 +66,19 @@ def act_bwd(dy32, sign16=None, ya32=None, yb32=None, want_bias=True, fmt=GRAD_FM
     return (dz, db, dz32) if want32 else (dz, db)
 
 
+def convt_dgrad_taps(ksize, stride, pad):
+    """(ntaps, first_shift) of the stride-1 conv over the space-to-depth gradient that computes
+    the input gradient of a ConvTranspose1d (ms_convt_dgrad_taps)"""
+    first = ctypes.c_int(0)
+    n = _lib.lib().ms_convt_dgrad_taps(ksize, stride, pad, ctypes.byref(first))
+    if n < 1:
+        raise _lib.MsbError("unsupported ConvTranspose1d geometry for the backward pass")
+    if first.value != -(n - 1) // 2 or n % 2 == 0:
+        raise _lib.MsbError("ConvTranspose1d backward: asymmetric tap range (padding must be "
+                            "(kernel_size - stride) / 2)")
+    return n, first.value
+
+
 def weight_dgrad_view(w, kind, stride=1, pad=0):
     """reference-layout weight of the conv that computes the input gradient (see msb200.h)"""
     w = w.contiguous()
@@ -74,7 +87,8 @@ def weight_dgrad_view(w, kind, stride=1, pad=0):
         out = torch.empty((cin, cout, k), dtype=torch.float32, device=w.device)
     else:
         cin, cout, k = w.shape
-        out = torch.empty((cin, stride * cout, 3), dtype=torch.float32, device=w.device)
+        ntaps, _ = convt_dgrad_taps(k, stride, pad)
+        out = torch.empty((cin, stride * cout, ntaps), dtype=torch.float32, device=w.device)
     check(_lib.lib().ms_weight_dgrad_view(ptr(w), ptr(out), kind, cout, cin, k, stride, pad,
                                           stream_ptr()), "ms_weight_dgrad_view")
     return out
@@ -91,7 +105,8 @@ def conv_dgrad(w, dz16, kind, dilation=1, pad=0, stride=1, res32=None, operand=G
                           operand=operand)
     else:
         cin, cout, k = w.shape
-        d = ops.conv_desc(MS_CONV, B, stride * cout, cin, L, 3, 1, 1, operand=operand)
+        ntaps, first = convt_dgrad_taps(k, stride, pad)
+        d = ops.conv_desc(MS_CONV, B, stride * cout, cin, L, ntaps, 1, -first, operand=operand)
     _, dx32 = ops.conv_fwd(d, dz16, ops.pack_conv_weight(d, wv), None, res32=res32,
                            want16=False, want32=True)
     return dx32
@@ -112,7 +127,8 @@ def wgrad(a16, x16, shifts, mode, w_shape, fmt, stride=1, pad=0, fold=1, alpha=1
     dw = torch.empty(w_shape, dtype=torch.float32, device=a16.device)
     cout = w_shape[1] if mode == MS_CONVT else 0
     check(L.ms_wgrad_fwd(ptr(a16), ptr(x16), B, Cm8 * 8, Cn8 * 8, La, Lx, taps, sh, fmt,
-                         mode, stride, pad, cout, fold, float(alpha), 0.0, ptr(dw), ptr(ws), ws.numel(), stream_ptr()),
+                         mode, stride, pad, cout, w_shape[2], fold, float(alpha), 0.0, ptr(dw),
+                         ptr(ws), ws.numel(), stream_ptr()),
           "ms_wgrad_fwd")
     return dw
 
@@ -127,9 +143,10 @@ def conv_wgrad(dz16, x16, w_shape, dilation=1, pad=0, fmt_dz=GRAD_FMT, fmt_x=MS_
 
 
 def convt_wgrad(x16, dzs16, w_shape, stride, pad, fmt_dz=GRAD_FMT, fmt_x=MS_F16):
-    """dW of a ConvTranspose1d (k = 2*stride): x16 layer input, dzs16 space-to-depth dz."""
-    return wgrad(convert16(x16, fmt_x, fmt_dz), dzs16, [-1, 0, 1], MS_CONVT, w_shape, fmt_dz,
-                 stride, pad)
+    """dW of a ConvTranspose1d (k = J*stride): x16 layer input, dzs16 space-to-depth dz."""
+    ntaps, first = convt_dgrad_taps(w_shape[2], stride, pad)
+    return wgrad(convert16(x16, fmt_x, fmt_dz), dzs16, list(range(first, first + ntaps)),
+                 MS_CONVT, w_shape, fmt_dz, stride, pad)
 
 
 def pack_ncl32(x):

@@ -142,8 +142,9 @@ class ResidualStack(nn.Module):
 
 class LearnedUpSample(nn.Module):
     """featuresynth/util/modules.py:168-188: ConvTranspose1d(k, stride=s,
-    padding=(k-s)//2, bias=False) followed by `activation`.  Only k == 2*s with
-    LeakyReLU(0.2) (the configuration every hot-path experiment uses) is fused."""
+    padding=(k-s)//2, bias=False) followed by `activation`.  k = 2*s (multiscale generators)
+    and k = 4*s (generator/filterbank.py:108-114) with LeakyReLU(0.2) -- the configurations the
+    hot-path experiments use -- run as polyphase implicit GEMMs with the activation fused."""
 
     def __init__(self, in_channels, out_channels, kernel_size, scale_factor, activation=None,
                  operand=MS_F16):
@@ -154,8 +155,10 @@ class LearnedUpSample(nn.Module):
         self.scale_factor = scale_factor
         self.activation = activation
         self.operand = operand
-        if kernel_size != 2 * scale_factor:
-            raise NotImplementedError("LearnedUpSample: only kernel_size == 2*scale_factor")
+        if kernel_size % scale_factor != 0 or kernel_size < 2 * scale_factor or \
+                (kernel_size - scale_factor) % 2 != 0:
+            raise NotImplementedError("LearnedUpSample: kernel_size must be an even multiple "
+                                      "(>= 2) of scale_factor")
         self.conv = nn.ConvTranspose1d(in_channels, out_channels, kernel_size,
                                        stride=scale_factor,
                                        padding=(kernel_size - scale_factor) // 2, bias=False)
@@ -171,3 +174,127 @@ class LearnedUpSample(nn.Module):
         _, y32 = ops.conv_fwd(d, x16, self._packed.get(d, self.conv.weight), None,
                               want16=False, want32=True)
         return ops.unpack_blk32(y32)
+
+
+class UpsamplingStack(nn.Module):
+    """featuresynth/util/modules.py:191-223: log_scale(target / start) layers from `layer_func`."""
+
+    def __init__(self, start_size, target_size, scale_factor, layer_func):
+        super().__init__()
+        import math
+        self.layer_func = layer_func
+        self.start_size = start_size
+        self.target_size = target_size
+        self.scale_factor = scale_factor
+        n_layers = int(math.log(target_size, scale_factor) - math.log(start_size, scale_factor))
+        layers = []
+        curr_size = start_size
+        for i in range(n_layers):
+            out_size = curr_size * scale_factor
+            layers.append(layer_func(i, curr_size, out_size, i == 0, i == n_layers - 1))
+            curr_size = out_size
+        self.main = nn.Sequential(*layers)
+
+    def __iter__(self):
+        yield from self.main
+
+    def forward(self, x):
+        for layer in self.main:
+            x = layer(x)
+        return x
+
+
+class DownsamplingStack(nn.Module):
+    """featuresynth/util/modules.py:226-272 (container; the owning discriminator runs the layers
+    on the channel-blocked path)."""
+
+    def __init__(self, start_size, target_size, scale_factor, layer_func, activation=None):
+        super().__init__()
+        import math
+        self.activation = activation
+        self.scale_factor = scale_factor
+        self.target_size = target_size
+        self.start_size = start_size
+        n_layers = int(math.log(start_size, scale_factor) - math.log(target_size, scale_factor))
+        layers = []
+        curr_size = start_size
+        for i in range(n_layers):
+            out_size = curr_size // scale_factor
+            layers.append(layer_func(i, curr_size, out_size, i == 0, i == n_layers - 1))
+            curr_size = out_size
+        self.main = nn.Sequential(*layers)
+
+    def __len__(self):
+        return len(self.main)
+
+    def __iter__(self):
+        yield from self.main
+
+    @property
+    def out_channels(self):
+        return self.main[-1].out_channels
+
+
+def nearest_upsample(feat, size):
+    """F.upsample(feat, size=size) (nearest neighbour, the default mode): an index gather"""
+    if feat.shape[-1] == size:
+        return feat
+    idx = (torch.arange(size, device=feat.device) * feat.shape[-1]) // size
+    return feat[..., idx].contiguous()
+
+
+class LowResSpectrogramDiscriminator(nn.Module):
+    """featuresynth/util/modules.py:275-344: relu + mean over (channel window x time window) of the
+    filter-bank analysis, then stride-2 convs down to `n_judgements` time steps and a judge."""
+
+    def __init__(self, freq_bins, time_steps, n_judgements, kernel_size, max_channels,
+                 conditioning_channels=0, log_scaling=False):
+        super().__init__()
+        import numpy as np
+        if log_scaling:
+            raise NotImplementedError("LowResSpectrogramDiscriminator: log_scaling is not on this "
+                                      "path (no experiment of experiment/filterbank.py sets it)")
+        self.log_scaling = log_scaling
+        self.conditioning_channels = conditioning_channels
+        self.max_channels = max_channels
+        self.kernel_size = kernel_size
+        self.n_judgements = n_judgements
+        self.time_steps = time_steps
+        self.freq_bins = freq_bins
+        log_channels = np.log2(freq_bins)
+
+        def build(i, curr_size, out_size, first, last):
+            cin = min(max_channels, 2 ** (i + log_channels))
+            if first:
+                cin += conditioning_channels
+            cout = min(max_channels, 2 ** (i + log_channels + 1))
+            return nn.Conv1d(int(cin), int(cout), kernel_size, stride=2, padding=kernel_size // 2)
+
+        self.stack = DownsamplingStack(time_steps, n_judgements, 2, build)
+        self.judge = nn.Conv1d(self.stack.out_channels, 1, 3, 1, 1)
+        self._sc = [ag.StridedCache() for _ in self.stack]
+
+    def forward_blocked(self, a32, feat):
+        """a32: BLK f32 (B, C/8, L, 8) filter-bank analysis (autograd-tracked when training);
+        feat (B, conditioning_channels, T) NCL or None -> ([NCL feature maps], judgement)"""
+        from .. import grad_ops
+        B, C8, L, _ = a32.shape
+        cw, tw = (C8 * 8) // self.freq_bins, L // self.time_steps
+        h32, h16 = ag.ReluAvgPool.apply(a32, cw, tw)
+        if self.conditioning_channels > 0:
+            T = h16.shape[2]
+            if feat.shape[-1] < T:
+                feat = nearest_upsample(feat, T)
+            elif feat.shape[-1] > T:
+                f = feat.shape[-1] // T
+                feat = ops.avg_pool1d(feat, f, f, 0)
+            h32 = torch.cat([h32, grad_ops.pack_ncl32(feat)], dim=1)
+            h16 = torch.cat([h16, ops.pack_ncl(feat)], dim=1)
+        features = []
+        length = h16.shape[2]
+        for conv, sc in zip(self.stack, self._sc):
+            h32, h16 = ag.StridedConvBlk.apply(h32, h16, conv.weight, conv.bias, sc, 2, length)
+            features.append(ag.UnpackBlk32.apply(h32))
+            length = h16.shape[2]
+        j = ag.MonoConv.apply(h32, self.judge.weight, self.judge.bias, 3, 1, False)
+        return features, j

@@ -177,6 +177,46 @@ def fb_discriminator():
     save("fb_discriminator_n2048", **arrays)
 
 
+def filterbank_pair():
+    """FilterBankGenerator (generator/filterbank.py:93-128) and FilterBankDiscriminator
+    (discriminator/filterbank.py:114-202) as FilterBankExperiment / ConditionalFilterBankExperiment
+    build them (experiment/filterbank.py:34-68, 93-106): unmodified reference classes, the
+    zounds FilterBank stand-in of oracle/bases.py."""
+    ref_harness.load()
+    import zounds
+    from featuresynth.generator.filterbank import FilterBankGenerator
+    from featuresynth.discriminator.filterbank import FilterBankDiscriminator
+    torch.set_grad_enabled(False)
+    sr = zounds.SR22050()
+    scale = zounds.LinearScale(zounds.FrequencyBand(20, sr.nyquist - 20), 128)
+    fb = zounds.learn.FilterBank(sr, 511, scale, 0.9, normalize_filters=True, a_weighting=False)
+    g = FilterBankGenerator(fb, 32, 8192, 128).eval()
+    sd = restate.filterbank_generator_state(401)
+    assert list(g.state_dict()) == list(sd), (list(g.state_dict()), list(sd))
+    g.load_state_dict(sd)
+    x = synth.mel_features(402, 2, 32)
+    y = g(x)
+    save("filterbank_generator_t32", seed=401, y=y.numpy(),
+         bank_checksum=float(fb.filter_bank.double().abs().sum()),
+         bank_sub=fb.filter_bank.numpy().reshape(-1)[::97])
+    for cond in (0, 128):
+        d = FilterBankDiscriminator(fb, 8192, conditioning_channels=cond).eval()
+        dsd = restate.filterbank_discriminator_state(403 + cond, conditioning_channels=cond)
+        assert list(d.state_dict()) == list(dsd), (list(d.state_dict()), list(dsd))
+        d.load_state_dict(dsd)
+        a = synth.randn(404, 2, 1, 8192) * 0.1
+        feat = synth.mel_features(405, 2, 32)
+        feats, judg = d(a, feat)
+        arrays = {"seed": 403 + cond}
+        for i, j in enumerate(judg):
+            arrays[f"j{i}"] = j.numpy()
+        for gi, fl in enumerate(feats):
+            for i, f in enumerate(fl):
+                arrays[f"f{gi}_{i}_shape"] = np.array(f.shape)
+                arrays[f"f{gi}_{i}_sub"] = f.numpy().reshape(-1)[::53]
+        save("filterbank_discriminator_n8192" + ("_cond" if cond else ""), **arrays)
+
+
 def realmelgan():
     """experiment/realmelgan.py Generator (48-89) and Discriminator (158-181)."""
     ref_harness.load()
@@ -343,6 +383,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "realmelgan":
         realmelgan()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "filterbank_pair":
+        filterbank_pair()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fb_discriminator":
         fb_discriminator()

@@ -543,6 +543,134 @@ def melgan_generator_flops(batch, frames):
 
 
 # ---------------------------------------------------------------------------------------
+# FilterBankExperiment pair: FilterBankGenerator (generator/filterbank.py:93-128) and
+# FilterBankDiscriminator (discriminator/filterbank.py:114-202) with
+# LowResSpectrogramDiscriminator (util/modules.py:275-344) over ONE fixed 511-tap, 128-band
+# linear-scale Morlet bank (experiment/filterbank.py:34-45)
+# ---------------------------------------------------------------------------------------
+def filterbank_experiment_bank(samplerate=22050, kernel_size=511, n_bands=128):
+    """experiment/filterbank.py:34-45: LinearScale(FrequencyBand(20, nyquist - 20), 128), 511 taps,
+    scaling factor 0.9, unit-norm filters -> (n_bands, 1, kernel_size)"""
+    from oracle import bases
+    sr = bases.SampleRate(samplerate)
+    scale = bases.LinearScale(bases.FrequencyBand(20, sr.nyquist - 20), n_bands)
+    return torch.from_numpy(bases.morlet_filter_bank(sr, kernel_size, scale, 0.9)).view(
+        n_bands, 1, kernel_size)
+
+
+def filterbank_generator_state(seed, in_size=32, out_size=8192, in_channels=128, n_bands=128):
+    import math
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    n_layers = int(math.log(out_size, 2) - math.log(in_size, 2))
+    sd = {}
+    for i in range(n_layers):
+        cin = in_channels if i == 0 else 256
+        sd[f"main.main.{i}.conv.weight"] = torch.from_numpy(
+            (rs.standard_normal((cin, 256, 8)) * 0.02).astype(np.float32))
+    sd["to_frames.weight"] = torch.from_numpy(
+        (rs.standard_normal((n_bands, 256, 7)) * 0.02).astype(np.float32))
+    sd["to_frames.bias"] = torch.from_numpy((rs.standard_normal((n_bands,)) * 0.01).astype(np.float32))
+    return sd
+
+
+def filterbank_generator(x, sd, bank):
+    """generator/filterbank.py:122-128: UpsamplingStack of LearnedUpSample(C, 256, 8, 2) =
+    ConvTranspose1d(k 8, stride 2, padding 3, bias=False) + leaky (util/modules.py:168-188),
+    to_frames Conv1d(256, n_bands, 7, 1, 3), filter_bank.transposed_convolve"""
+    h = x
+    i = 0
+    while f"main.main.{i}.conv.weight" in sd:
+        h = leaky(F.conv_transpose1d(h, sd[f"main.main.{i}.conv.weight"], stride=2, padding=3))
+        i += 1
+    h = F.conv1d(h, sd["to_frames.weight"], sd["to_frames.bias"], padding=3)
+    return F.conv_transpose1d(h, bank, padding=bank.shape[-1] // 2)
+
+
+def _lowres_channels(freq_bins, max_channels, n_layers, conditioning_channels):
+    import math
+    out = []
+    lc = math.log2(freq_bins)
+    for i in range(n_layers):
+        cin = int(min(max_channels, 2 ** (i + lc))) + (conditioning_channels if i == 0 else 0)
+        cout = int(min(max_channels, 2 ** (i + lc + 1)))
+        out.append((cin, cout))
+    return out
+
+
+FBD_MAIN = ((None, 256), (256, 256), (256, 512), (512, 512), (512, 1024), (1024, 1024),
+            (1024, 1024), (1024, 1024))
+FBD_LOWRES = {"medium_res": (128, 128, 16, 1024), "low_res": (32, 32, 4, 512)}
+
+
+def filterbank_discriminator_state(seed, n_bands=128, conditioning_channels=0):
+    import math
+    import numpy as np
+    rs = np.random.RandomState(seed)
+
+    def t(*shape, std=0.02):
+        return torch.from_numpy((rs.standard_normal(shape) * std).astype(np.float32))
+
+    sd = {}
+    for i, (cin, cout) in enumerate(FBD_MAIN):
+        cin = n_bands + conditioning_channels if cin is None else cin
+        sd[f"main.{i}.weight"] = t(cout, cin, 7)
+        sd[f"main.{i}.bias"] = t(cout, std=0.01)
+    sd["judge.weight"] = t(1, 1024, 3)
+    sd["judge.bias"] = t(1, std=0.01)
+    for name, (fb, ts, nj, mx) in FBD_LOWRES.items():
+        n_layers = int(math.log(ts, 2) - math.log(nj, 2))
+        chans = _lowres_channels(fb, mx, n_layers, conditioning_channels)
+        for i, (cin, cout) in enumerate(chans):
+            sd[f"{name}.stack.main.{i}.weight"] = t(cout, cin, 7)
+            sd[f"{name}.stack.main.{i}.bias"] = t(cout, std=0.01)
+        sd[f"{name}.judge.weight"] = t(1, chans[-1][1], 3)
+        sd[f"{name}.judge.bias"] = t(1, std=0.01)
+    return sd
+
+
+def _lowres_discriminator(a, feat, sd, name, conditioning_channels):
+    """util/modules.py:315-344"""
+    fb, ts, nj, mx = FBD_LOWRES[name]
+    batch, channels, time = a.shape
+    cw, tw = channels // fb, time // ts
+    low = F.avg_pool2d(F.relu(a)[:, None, :, :], (cw, tw)).view(-1, fb, ts)
+    if conditioning_channels > 0:
+        if feat.shape[-1] < low.shape[-1]:
+            feat = F.interpolate(feat, size=low.shape[-1])
+        elif feat.shape[-1] > low.shape[-1]:
+            feat = F.avg_pool1d(feat, feat.shape[-1] // low.shape[-1])
+        low = torch.cat([low, feat], dim=1)
+    features = []
+    i = 0
+    while f"{name}.stack.main.{i}.weight" in sd:
+        low = leaky(F.conv1d(low, sd[f"{name}.stack.main.{i}.weight"],
+                             sd[f"{name}.stack.main.{i}.bias"], stride=2, padding=3))
+        features.append(low)
+        i += 1
+    return features, F.conv1d(low, sd[f"{name}.judge.weight"], sd[f"{name}.judge.bias"], padding=1)
+
+
+def filterbank_discriminator(x, feat, sd, bank, conditioning_channels=0):
+    """discriminator/filterbank.py:163-202 -> ([8 maps, 3 maps, 3 maps], [3 judgements])"""
+    a = F.conv1d(x.view(-1, 1, x.shape[-1]), bank, padding=bank.shape[-1] // 2)
+    h = a
+    if conditioning_channels > 0:
+        h = torch.cat([h, F.interpolate(feat, size=h.shape[-1])], dim=1)
+    full = []
+    for i in range(len(FBD_MAIN)):
+        h = leaky(F.conv1d(h, sd[f"main.{i}.weight"], sd[f"main.{i}.bias"], stride=2, padding=3))
+        full.append(h)
+    features = [full]
+    judgements = [F.conv1d(h, sd["judge.weight"], sd["judge.bias"], padding=1)]
+    for name in ("medium_res", "low_res"):
+        f, j = _lowres_discriminator(a, feat, sd, name, conditioning_channels)
+        features.append(f)
+        judgements.append(j)
+    return features, judgements
+
+
+# ---------------------------------------------------------------------------------------
 # GAN training step: featuresynth/train/train.py:26-42 (GeneratorTrainer.train), 63-74
 # (DiscriminatorTrainer.train) with Adam(lr 1e-4, betas (0.5, 0.9)) from
 # featuresynth/experiment/experiment.py:111-117, on the MelGanGenerator / MelGanDiscriminator

@@ -179,6 +179,43 @@ def test_fb_discriminator_matches_reference(golden):
             assert rel_l2(f.reshape(-1)[::13], g[f"f{gi}_{i}_sub"]) < 5e-6
 
 
+def test_filterbank_experiment_pair_matches_reference(golden):
+    """FilterBankGenerator / FilterBankDiscriminator: the restatement vs
+    the unmodified reference classes over the 511-tap bank"""
+    g = golden("filterbank_generator_t32")
+    bank = restate.filterbank_experiment_bank()
+    assert abs(float(bank.double().abs().sum()) - float(g["bank_checksum"])) < 1e-6
+    assert np.abs(bank.numpy().reshape(-1)[::97] - g["bank_sub"]).max() < 1e-7
+    sd = restate.filterbank_generator_state(401)
+    y = restate.filterbank_generator(synth.mel_features(402, 2, 32), sd, bank)
+    assert y.shape == (2, 1, 8192) and rel_l2(y, g["y"]) < 3e-6
+    a = synth.randn(404, 2, 1, 8192) * 0.1
+    feat = synth.mel_features(405, 2, 32)
+    for cond, name in ((0, "filterbank_discriminator_n8192"),
+                       (128, "filterbank_discriminator_n8192_cond")):
+        gd = golden(name)
+        dsd = restate.filterbank_discriminator_state(403 + cond, conditioning_channels=cond)
+        feats, judg = restate.filterbank_discriminator(a, feat, dsd, bank, cond)
+        assert [len(f) for f in feats] == [8, 3, 3]
+        assert [tuple(j.shape) for j in judg] == [(2, 1, 32), (2, 1, 16), (2, 1, 4)]
+        for i, j in enumerate(judg):
+            assert rel_l2(j, gd[f"j{i}"]) < 2e-5
+        for gi, fl in enumerate(feats):
+            for i, f in enumerate(fl):
+                assert tuple(f.shape) == tuple(gd[f"f{gi}_{i}_shape"])
+                assert rel_l2(f.reshape(-1)[::53], gd[f"f{gi}_{i}_sub"]) < 2e-5
+
+
+def test_product_511_tap_bank_equals_the_reference_bank(golden):
+    """the product's own bank construction (audio/filterbank.py) for FilterBankExperiment"""
+    from music_synthesis_b200.experiment.wirings import FilterBankExperiment
+    g = golden("filterbank_generator_t32")
+    fb = FilterBankExperiment.make_filter_bank()
+    assert fb.kernel_size == 511 and fb.kp == 512 and fb.syn_nph == 16 and fb.extra == 0
+    assert abs(float(fb.filter_bank.double().abs().sum()) - float(g["bank_checksum"])) < 1e-4
+    assert np.abs(fb.filter_bank.numpy().reshape(-1)[::97] - g["bank_sub"]).max() < 2e-7
+
+
 def test_realmelgan_pair_matches_reference(golden):
     g = golden("realmelgan_gen_t8")
     sd = restate.realmelgan_generator_state(101)
