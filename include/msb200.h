@@ -135,6 +135,13 @@ ms_status ms_weight_split(const float* w, float* out, int cout, int cin, int ksi
 ms_status ms_blk32_split_blk16(const float* x32, void* y16, int batch, int channels, int len,
                                int pad, int pad_mode, int leaky, int operand, int terms,
                                float scale, void* stream);
+/* noise head of ResidualStackFilterBankGenerator (generator/filterbank.py:76-86):
+ * y[b,t] = add[b,t] + sum_c a32[b,c,t] * n32[c,t]; a32 BLK f32 (B,C/8,L,8), n32 BLK f32
+ * (1,C/8,L,8) shared by the batch, add (B,1,L) or NULL.  _bwd: da32 = dy[b,t] * n32[c,t]. */
+ms_status ms_noise_mix_fwd(const float* a32, const float* n32, const float* add, float* y,
+                           int batch, int channels, int len, void* stream);
+ms_status ms_noise_mix_bwd(const float* dy, const float* n32, float* da32, int batch, int channels,
+                           int len, void* stream);
 /* front end of LowResSpectrogramDiscriminator (util/modules.py:315-325): relu, then the mean
  * over (channel_window x time_window) windows: BLK f32 (B,C/8,L,8) -> BLK f32 and/or 16-bit
  * (B,(C/cw)/8,L/tw,8).  cw must divide 8 or be a multiple of 8; tw must divide L. */

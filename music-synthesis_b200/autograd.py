@@ -136,6 +136,7 @@ class ConvBlk(Function):
                                     want32=True)
         ctx.save_for_backward(x16, w, y16)
         ctx.cfg = (cache, kind, dilation, pad, stride, leaky, b is not None)
+        ctx.wkey = getattr(w, "_msb_key", None)      # identity of a derived (weight-normed) weight
         ctx.has_res = res32 is not None
         ctx.mark_non_differentiable(y16)
         return y32, y16
@@ -144,6 +145,8 @@ class ConvBlk(Function):
     def backward(ctx, dy32, _unused):
         x16, w, y16 = ctx.saved_tensors
         cache, kind, dilation, pad, stride, leaky, has_bias = ctx.cfg
+        if ctx.wkey is not None:
+            w._msb_key = ctx.wkey
         dres = dy32 if (ctx.has_res and ctx.needs_input_grad[10]) else None
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
         s2d = stride if kind == MS_CONVT else 1
@@ -180,6 +183,7 @@ class ResidualAtomBlk(Function):
                                 want32=True)
         ctx.save_for_backward(x32, x16, h16, y32, w1, w2)
         ctx.cfg = (cache1, cache2, dilation)
+        ctx.wkeys = (getattr(w1, "_msb_key", None), getattr(w2, "_msb_key", None))
         ctx.mark_non_differentiable(y16)
         return y32, y16
 
@@ -187,6 +191,9 @@ class ResidualAtomBlk(Function):
     def backward(ctx, dy32, _unused):
         x32, x16, h16, y32, w1, w2 = ctx.saved_tensors
         cache1, cache2, dilation = ctx.cfg
+        for w_, k_ in zip((w1, w2), ctx.wkeys):
+            if k_ is not None:
+                w_._msb_key = k_
         need_w = ctx.needs_input_grad[2]
         dy32 = dy32.contiguous()
         # outer LeakyReLU: its output is y - x (sign of the fp32 difference)
@@ -489,6 +496,34 @@ class StridedConvBlk(Function):
             dx32 = grad_ops.depth_to_space32(dxs, cin, stride, in_rows, length, rows_valid=lx,
                                              row_offset=crop)
         return dx32, None, dw, db, None, None, None
+
+
+class NoiseMix(Function):
+    """y = add + sum_c a[:, c] * n[c] (generator/filterbank.py:83-91): a32 BLK f32 (B,C/8,L,8),
+    n32 BLK f32 (1,C/8,L,8) fixed noise (no gradient), add (B,1,L)"""
+
+    @staticmethod
+    def forward(ctx, a32, n32, add):
+        B, C8, L, _ = a32.shape
+        y = torch.empty((B, 1, L), dtype=torch.float32, device=a32.device)
+        check(_lib.lib().ms_noise_mix_fwd(ptr(a32.contiguous()), ptr(n32.contiguous()),
+                                          ptr(add.contiguous()), ptr(y), B, C8 * 8, L,
+                                          stream_ptr()), "ms_noise_mix_fwd")
+        ctx.save_for_backward(n32)
+        ctx.shape = (B, C8, L)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (n32,) = ctx.saved_tensors
+        B, C8, L = ctx.shape
+        dy = dy.contiguous()
+        da = None
+        if ctx.needs_input_grad[0]:
+            da = torch.empty((B, C8, L, 8), dtype=torch.float32, device=dy.device)
+            check(_lib.lib().ms_noise_mix_bwd(ptr(dy), ptr(n32), ptr(da), B, C8 * 8, L,
+                                              stream_ptr()), "ms_noise_mix_bwd")
+        return da, None, (dy if ctx.needs_input_grad[2] else None)
 
 
 class ReluAvgPool(Function):

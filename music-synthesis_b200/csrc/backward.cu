@@ -295,6 +295,23 @@ __global__ void weight_norm_bwd_kernel(const float* __restrict__ dw, const float
     dv[base + i] = (gr / n) * (dw[base + i] - (dgr / n) * v[base + i]);
 }
 
+// gradient of ms_noise_mix_fwd wrt a: da[b, c, t] = dy[b, t] * n[c, t]  (d add = dy)
+__global__ void noise_mix_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ n,
+                                     float* __restrict__ da, int C8, int L, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = static_cast<int>(gid % L);
+  const size_t bc = gid / L;
+  const int c = static_cast<int>(bc % C8);
+  const size_t b = bc / C8;
+  const float g = __ldg(dy + b * L + t);
+  float fn[8], o[8];
+  ld_global_nc_v8(n + (static_cast<size_t>(c) * L + t) * 8, fn);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = g * fn[j];
+  st_global_v8(da + gid * 8, o);
+}
+
 // gradient of ms_relu_avgpool2d_fwd: dx[b,c,t] = (x > 0) * dy[b, c/cw, t/tw] / (cw*tw)
 __global__ void relu_avgpool2d_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                           float* __restrict__ dx, int C8, int L, int cw, int tw,
@@ -1250,6 +1267,18 @@ ms_status ms_blk_act_pad_bwd(const float* dy32, const void* sign16, float* dx32,
                        static_cast<cudaStream_t>(stream)>>>(
       dy32, static_cast<const uint4*>(sign16), dx32, len, pad, pad_mode, total);
   return after_launch("act_pad_bwd_kernel");
+}
+
+ms_status ms_noise_mix_bwd(const float* dy, const float* n32, float* da32, int batch, int channels,
+                           int len, void* stream) {
+  if (dy == nullptr || n32 == nullptr || da32 == nullptr || batch <= 0 || channels <= 0 ||
+      channels % 8 != 0 || len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * (channels / 8) * len;
+  noise_mix_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                         static_cast<cudaStream_t>(stream)>>>(dy, n32, da32, channels / 8, len,
+                                                              total);
+  return after_launch("noise_mix_bwd_kernel");
 }
 
 ms_status ms_relu_avgpool2d_bwd(const float* dy32, const float* x32, float* dx32, int batch,

@@ -294,6 +294,28 @@ __global__ void diag_sum_kernel(const float* __restrict__ z, float* __restrict__
   y[gid] = acc;
 }
 
+// Noise head of ResidualStackFilterBankGenerator (featuresynth/generator/filterbank.py:76-86):
+//   y[b, t] = add[b, t] + sum_c a[b, c, t] * n[c, t]
+// a: BLK f32 (B, C/8, L, 8) (`to_noise(x)`), n: BLK f32 (1, C/8, L, 8) (the filter-bank analysis
+// of one white-noise row, shared by the batch), add: (B, 1, L) harmonic part or null.
+__global__ void noise_mix_kernel(const float* __restrict__ a, const float* __restrict__ n,
+                                 const float* __restrict__ add, float* __restrict__ y, int C8,
+                                 int L, size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int t = static_cast<int>(gid % L);
+  const size_t b = gid / L;
+  float acc = add != nullptr ? __ldg(add + gid) : 0.f;
+  for (int c = 0; c < C8; ++c) {
+    float fa[8], fn[8];
+    ld_global_nc_v8(a + ((b * C8 + c) * L + t) * 8, fa);
+    ld_global_nc_v8(n + (static_cast<size_t>(c) * L + t) * 8, fn);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(fa[j], fn[j], acc);
+  }
+  y[gid] = acc;
+}
+
 // LowResSpectrogramDiscriminator front end (featuresynth/util/modules.py:315-325):
 //   y[b, f, s] = mean over channels [f*cw, (f+1)*cw) x time [s*tw, (s+1)*tw) of relu(x[b, c, t])
 // x: BLK f32 (B, C/8, L, 8) (filter-bank analysis), y: BLK f32 / 16-bit (B, (C/cw)/8, L/tw, 8).
@@ -585,6 +607,17 @@ ms_status ms_diag_sum(const float* z32, float* y, int batch, int channels, int z
                     static_cast<cudaStream_t>(stream)>>>(z32, y, channels / 8, z_len, out_len,
                                                          nphase, skew, total);
   return after_launch("diag_sum_kernel");
+}
+
+ms_status ms_noise_mix_fwd(const float* a32, const float* n32, const float* add, float* y,
+                           int batch, int channels, int len, void* stream) {
+  if (a32 == nullptr || n32 == nullptr || y == nullptr || batch <= 0 || channels <= 0 ||
+      channels % 8 != 0 || len <= 0)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(batch) * len;
+  noise_mix_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                     static_cast<cudaStream_t>(stream)>>>(a32, n32, add, y, channels / 8, len, total);
+  return after_launch("noise_mix_kernel");
 }
 
 ms_status ms_relu_avgpool2d_fwd(const float* x32, void* y16, float* y32, int batch, int channels,

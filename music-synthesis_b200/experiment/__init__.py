@@ -4,7 +4,8 @@ from .experiment import BaseGanExperiment, Experiment  # noqa: F401
 from .init import weights_init  # noqa: F401
 from .realmelgan import Generator, Discriminator, NLayerDiscriminator, ResnetBlock  # noqa: F401
 from . import wirings as _wirings
-from .wirings import (ConditionalFilterBankExperiment, FilterBankExperiment,  # noqa: F401
+from .wirings import (AlternateFilterBankExperiment, ConditionalFilterBankExperiment,  # noqa: F401
+                      FilterBankExperiment,
                       FilterBankMultiscaleExperiment, MultiScaleMelGanExperiment,
                       MultiScaleNoDeRecompose, MultiScaleNoDeRecomposeUnconditionedShortKernel,
                       RealMelGanExperiment)

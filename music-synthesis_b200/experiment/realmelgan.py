@@ -30,10 +30,7 @@ from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
 from ..loss.loss import _Acc, L1, hinge_generator_loss
 
 
-def _weight_norm(m):
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        return torch.nn.utils.weight_norm(m)
+from ..util.modules import weight_norm as _weight_norm, wn_weight as _wn  # noqa: E402
 
 
 def WNConv1d(*args, **kwargs):
@@ -71,15 +68,6 @@ def _fwd_only(module, x):
     if torch.is_grad_enabled() and (x.requires_grad or
                                     any(p.requires_grad for p in module.parameters())):
         raise MsbError("sm_100a path is forward-only in this build: use torch.no_grad()")
-
-
-def _wn(m):
-    """differentiable weight-norm fold of a weight-normed layer; the folded tensor is new on
-    every call, so the packed-image caches key on the underlying parameters instead"""
-    w = ag.WeightNorm.apply(m.weight_v, m.weight_g)
-    w._msb_key = ("wn", m.weight_v.data_ptr(), m.weight_v._version,
-                  m.weight_g.data_ptr(), m.weight_g._version)
-    return w
 
 
 class ResnetBlock(nn.Module):

@@ -10,6 +10,7 @@ with 32 log-mel frames of 128 bins at 22 050 Hz, inference on 4x longer sequence
   MultiScaleNoDeRecompose                         featuresynth/experiment/multiscale.py:158-201
   FilterBankExperiment                            featuresynth/experiment/filterbank.py:14-78
   ConditionalFilterBankExperiment                 featuresynth/experiment/filterbank.py:81-128
+  AlternateFilterBankExperiment                   featuresynth/experiment/filterbank.py:131-206
 """
 from ..audio.representation import MultiScale, RawAudio
 from ..loss import (hinge_discriminator_loss, hinge_generator_loss, least_squares_disc_loss,
@@ -156,3 +157,16 @@ class ConditionalFilterBankExperiment(FilterBankExperiment):
     """experiment/filterbank.py:81-128: the same pair with the discriminator conditioned on the
     128 log-mel channels"""
     conditioning_channels = N_MELS
+
+
+class AlternateFilterBankExperiment(FilterBankExperiment):
+    """experiment/filterbank.py:131-206: the MelGAN-shaped, weight-normed
+    ResidualStackFilterBankGenerator (harmonic + noise heads) against the conditioned
+    FilterBankDiscriminator, each over its own (identically configured) bank"""
+    conditioning_channels = N_MELS
+
+    @classmethod
+    def make_generator(cls, filter_bank=None):
+        from ..generator.filterbank import ResidualStackFilterBankGenerator
+        return ResidualStackFilterBankGenerator(filter_bank or cls.make_filter_bank(), FEATURE_SIZE,
+                                                TOTAL_SAMPLES, N_MELS, add_weight_norm=True)

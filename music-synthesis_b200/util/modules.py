@@ -15,6 +15,30 @@ from .. import ops
 from .._lib import MS_CONV, MS_CONVT, MS_F16, MsbError
 
 
+def weight_norm(m):
+    """torch.nn.utils.weight_norm (the legacy hook form the reference uses: `weight_g` /
+    `weight_v` parameters, norm over all dims but 0)"""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return torch.nn.utils.weight_norm(m)
+
+
+def wn_weight(m):
+    """differentiable weight-norm fold g * v / ||v|| of a weight-normed layer on the device
+    (ms_weight_norm_fold / ms_weight_norm_bwd); the folded tensor is new on every call, so the
+    packed-image caches key on the underlying parameters instead"""
+    w = ag.WeightNorm.apply(m.weight_v, m.weight_g)
+    w._msb_key = ("wn", m.weight_v.data_ptr(), m.weight_v._version,
+                  m.weight_g.data_ptr(), m.weight_g._version)
+    return w
+
+
+def layer_weight(m):
+    """the (possibly weight-normed) conv weight of a layer as an autograd-visible tensor"""
+    return wn_weight(m) if hasattr(m, "weight_v") else m.weight
+
+
 def zero_grad(*optims):
     """featuresynth/util/modules.py:38-40."""
     for o in optims:
@@ -49,14 +73,14 @@ class ResidualAtom(nn.Module):
 
     def __init__(self, channels, dilation, add_weight_norm=False, operand=MS_F16):
         super().__init__()
-        if add_weight_norm:
-            raise NotImplementedError("weight-normed ResidualAtom is not on this path yet")
         self.add_weight_norm = add_weight_norm
         self.dilation = dilation
         self.channels = channels
         self.operand = operand
         first = nn.Conv1d(channels, channels, 3, 1, dilation=dilation, padding=dilation)
         second = nn.Conv1d(channels, channels, 3, 1, 1)
+        if add_weight_norm:         # util/modules.py:366-368 (generator/filterbank.py stacks)
+            first, second = weight_norm(first), weight_norm(second)
         self.main = nn.Sequential(first, second)
         self._packed = (_PackedConv(), _PackedConv())
         self._cache = (ag.WeightCache(), ag.WeightCache())
@@ -66,8 +90,8 @@ class ResidualAtom(nn.Module):
         if self.operand != MS_F16:
             raise MsbError("training runs with fp16 forward operands")
         c1, c2 = self.main[0], self.main[1]
-        return ag.ResidualAtomBlk.apply(x32, x16, c1.weight, c1.bias, c2.weight, c2.bias,
-                                        self._cache[0], self._cache[1], self.dilation)
+        return ag.ResidualAtomBlk.apply(x32, x16, layer_weight(c1), c1.bias, layer_weight(c2),
+                                        c2.bias, self._cache[0], self._cache[1], self.dilation)
 
     def forward_blocked(self, x16, x32):
         """(x16, x32) channel-blocked in -> channel-blocked out (no layout conversion)."""
@@ -82,7 +106,7 @@ class ResidualAtom(nn.Module):
                             want16=True, want32=True)
 
     def forward(self, x):
-        if ag.needs_grad(self, x):
+        if ag.needs_grad(self, x) or self.add_weight_norm:
             y32, _ = self.forward_blocked_train(ag.PackBlk32.apply(x), ops.pack_ncl(x.detach()))
             return ag.UnpackBlk32.apply(y32)
         x16 = ops.pack_ncl(x, operand=self.operand)
@@ -105,6 +129,7 @@ class ResidualStack(nn.Module):
         self.dilations = dilations
         self.channels = channels
         self.operand = operand
+        self.add_weight_norm = add_weight_norm
         self.main = nn.Sequential(
             *[ResidualAtom(channels, d, add_weight_norm, operand) for d in dilations])
         self._blob = None
@@ -124,7 +149,7 @@ class ResidualStack(nn.Module):
         return x32, x16
 
     def forward(self, x):
-        if ag.needs_grad(self, x):
+        if ag.needs_grad(self, x) or self.add_weight_norm:
             y32, _ = self.forward_blocked_train(ag.PackBlk32.apply(x), ops.pack_ncl(x.detach()))
             return ag.UnpackBlk32.apply(y32)
         if (len(self.dilations) == 3 and ops.resstack_supported(self.channels)

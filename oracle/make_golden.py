@@ -199,6 +199,19 @@ def filterbank_pair():
     save("filterbank_generator_t32", seed=401, y=y.numpy(),
          bank_checksum=float(fb.filter_bank.double().abs().sum()),
          bank_sub=fb.filter_bank.numpy().reshape(-1)[::97])
+    # ResidualStackFilterBankGenerator (generator/filterbank.py:8-90): the noise row comes from
+    # torch.normal on the global host generator -- seeded right before the call
+    from featuresynth.generator.filterbank import ResidualStackFilterBankGenerator
+    rg = ResidualStackFilterBankGenerator(fb, 8, 2048, 128, add_weight_norm=True).eval()
+    rsd = restate.resstack_filterbank_generator_state(411)
+    assert list(rg.state_dict()) == list(rsd), (list(rg.state_dict())[:12], list(rsd)[:12])
+    rg.load_state_dict(rsd)
+    xr = synth.mel_features(412, 2, 8)
+    torch.manual_seed(413)
+    yr = rg(xr)
+    torch.manual_seed(413)
+    raw = torch.normal(0, 1, (1, 1, 2048))
+    save("resstack_filterbank_generator_t8", seed=411, y=yr.numpy(), raw_noise=raw.numpy())
     for cond in (0, 128):
         d = FilterBankDiscriminator(fb, 8192, conditioning_channels=cond).eval()
         dsd = restate.filterbank_discriminator_state(403 + cond, conditioning_channels=cond)

@@ -587,6 +587,71 @@ def filterbank_generator(x, sd, bank):
     return F.conv_transpose1d(h, bank, padding=bank.shape[-1] // 2)
 
 
+RSFB_CONVT = ((0, 128, 512, 7, 1, 3), (2, 512, 256, 16, 8, 4), (5, 256, 256, 16, 8, 4),
+              (8, 256, 256, 4, 2, 1), (11, 256, 256, 4, 2, 1))
+RSFB_STACKS = (4, 7, 10, 13)
+
+
+def resstack_filterbank_generator_state(seed, in_channels=128):
+    """state dict of ResidualStackFilterBankGenerator(add_weight_norm=True)
+    (generator/filterbank.py:8-66): legacy weight_norm layout bias / weight_g / weight_v; for a
+    ConvTranspose1d the norm runs over dim 0 (in_channels): weight_g (cin, 1, 1)"""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+
+    def t(*shape, std=0.02):
+        return torch.from_numpy((rs.standard_normal(shape) * std).astype(np.float32))
+
+    sd = {}
+
+    def wn(prefix, v):
+        sd[prefix + ".bias"] = None                 # placeholder keeps the key order
+        sd[prefix + ".weight_g"] = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1) * \
+            torch.from_numpy((1.0 + 0.1 * rs.standard_normal((v.shape[0], 1, 1))).astype(np.float32))
+        sd[prefix + ".weight_v"] = v
+
+    order = []
+    for idx, cin, cout, k, s, p in RSFB_CONVT:
+        order.append(("convt", idx, cin, cout, k))
+    layers = {idx: (cin, cout, k) for idx, cin, cout, k, s, p in RSFB_CONVT}
+    for idx in range(14):
+        if idx in layers:
+            cin, cout, k = layers[idx]
+            wn(f"main.{idx}", t(cin, cout, k))
+            sd[f"main.{idx}.bias"] = t(cout, std=0.01)
+        elif idx in RSFB_STACKS:
+            for a in range(3):
+                for c in range(2):
+                    wn(f"main.{idx}.main.{a}.main.{c}", t(256, 256, 3))
+                    sd[f"main.{idx}.main.{a}.main.{c}.bias"] = t(256, std=0.01)
+    for name in ("to_frames", "to_noise"):
+        wn(name, t(256, 128, 7))
+        sd[name + ".bias"] = t(128, std=0.01)
+    return sd
+
+
+def resstack_filterbank_generator(x, sd, bank, raw_noise):
+    """generator/filterbank.py:68-90; raw_noise (1,1,256*T) stands for the torch.normal draw"""
+    def w(prefix):
+        return _wn(sd, prefix)
+
+    h = x
+    for idx, cin, cout, k, s, p in RSFB_CONVT:
+        h = leaky(F.conv_transpose1d(h, w(f"main.{idx}"), sd[f"main.{idx}.bias"], stride=s, padding=p))
+        stack = {0: None, 2: 4, 5: 7, 8: 10, 11: 13}[idx]
+        if stack is not None:
+            for a, d in enumerate((1, 3, 9)):
+                pre = f"main.{stack}.main.{a}.main"
+                h = residual_atom(h, w(pre + ".0"), sd[pre + ".0.bias"], w(pre + ".1"),
+                                  sd[pre + ".1.bias"], d)
+    noise = F.conv_transpose1d(h, w("to_noise"), sd["to_noise.bias"], padding=3)
+    filtered = F.conv1d(raw_noise.view(-1, 1, raw_noise.shape[-1]), bank, padding=bank.shape[-1] // 2)
+    noise = (noise * filtered).sum(dim=1, keepdim=True)
+    harmonic = F.conv_transpose1d(h, w("to_frames"), sd["to_frames.bias"], padding=3)
+    harmonic = F.conv_transpose1d(harmonic, bank, padding=bank.shape[-1] // 2)
+    return harmonic + noise
+
+
 def _lowres_channels(freq_bins, max_channels, n_layers, conditioning_channels):
     import math
     out = []

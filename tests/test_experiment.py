@@ -14,6 +14,9 @@ EXPERIMENTS = [
     ("multiscale", "FilterBankMultiscaleExperiment"),
     ("multiscale", "MultiScaleNoDeRecompose"),
     ("multiscale", "MultiScaleNoDeRecomposeUnconditionedShortKernel"),
+    ("filterbank", "FilterBankExperiment"),
+    ("filterbank", "ConditionalFilterBankExperiment"),
+    ("filterbank", "AlternateFilterBankExperiment"),
 ]
 
 

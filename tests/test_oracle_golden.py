@@ -206,6 +206,17 @@ def test_filterbank_experiment_pair_matches_reference(golden):
                 assert rel_l2(f.reshape(-1)[::53], gd[f"f{gi}_{i}_sub"]) < 2e-5
 
 
+def test_resstack_filterbank_generator_matches_reference(golden):
+    g = golden("resstack_filterbank_generator_t8")
+    sd = restate.resstack_filterbank_generator_state(411)
+    torch.manual_seed(413)
+    raw = torch.normal(0, 1, (1, 1, 2048))
+    assert np.array_equal(raw.numpy(), g["raw_noise"])      # the host generator is reproducible
+    y = restate.resstack_filterbank_generator(synth.mel_features(412, 2, 8), sd,
+                                              restate.filterbank_experiment_bank(), raw)
+    assert y.shape == (2, 1, 2048) and rel_l2(y, g["y"]) < 5e-6
+
+
 def test_product_511_tap_bank_equals_the_reference_bank(golden):
     """the product's own bank construction (audio/filterbank.py) for FilterBankExperiment"""
     from music_synthesis_b200.experiment.wirings import FilterBankExperiment
