@@ -171,9 +171,64 @@ class Generator(nn.Module):
             i += 1
         raise MsbError("malformed generator")
 
+    #: "fast" (fp16 operands) | "exact" (three-term bf16 split, ops.ExactConv) | "auto"; see
+    #: generator/full.py::MelGanGenerator.precision.  The weight-normed generator's activations
+    #: sit around 3e-6 rms at init -- inside the fp16 subnormals -- and still make the 1e-3 bar in
+    #: the fast mode (2.9e-4); a trained checkpoint with other scales can use "exact".
+    precision = "fast"
+    auto_tolerance = 5e-4
+
+    @torch.no_grad()
+    def _forward_exact(self, x):
+        from .. import grad_ops
+        ex = self.__dict__.setdefault("_exact", {})
+
+        def conv(name):
+            return ex.setdefault(name, ops.ExactConv())
+
+        def w(m):
+            t = ops.weight_norm_fold(m.weight_v.detach(), m.weight_g.detach())
+            t._msb_key = ("wn", m.weight_v.data_ptr(), m.weight_v._version,
+                          m.weight_g.data_ptr(), m.weight_g._version)
+            return t
+
+        layers = list(self.model)
+        h = grad_ops.pack_ncl32(x.contiguous())
+        first = layers[1]
+        h = conv(1)(h, w(first), first.bias, MS_CONV, 1, 0, 1, False, pad_in=3, pad_mode=1)
+        L = x.shape[-1]
+        i = 2
+        while i < len(layers):
+            m = layers[i]
+            if isinstance(m, nn.ConvTranspose1d):
+                r = m.stride[0]
+                h = conv(i)(h, w(m), m.bias, MS_CONVT, 1, m.padding[0], r, False, act_in=True)
+                L *= r
+            elif isinstance(m, ResnetBlock):
+                d = m.dilation
+                s32 = conv((i, "s"))(h, w(m.shortcut), m.shortcut.bias, MS_CONV, 1, 0, 1, False)
+                t = conv((i, 0))(h, w(m.block[2]), m.block[2].bias, MS_CONV, d, 0, 1, True,
+                                 act_in=True, pad_in=d, pad_mode=1)
+                h = conv((i, 1))(t, w(m.block[4]), m.block[4].bias, MS_CONV, 1, 0, 1, False, res32=s32)
+            elif isinstance(m, nn.Conv1d):
+                a32 = ops.act_pad(h, 3, 1, leaky=True)
+                y = ops.conv_to_mono(a32, w(m), m.bias, 7, 0, True)
+                return y[:, :, :L].contiguous()
+            i += 1
+        raise MsbError("malformed generator")
+
     def forward(self, x):
         if ag.needs_grad(self, x):
             return self._forward_train(x.contiguous())
+        if self.precision == "exact":
+            return self._forward_exact(x)
+        if self.precision == "auto":
+            from ..generator.full import auto_precision_ok
+            if not auto_precision_ok(self, x, self._forward_fast):
+                return self._forward_exact(x)
+        return self._forward_fast(x)
+
+    def _forward_fast(self, x):
         B, _, T = x.shape
         layers = list(self.model)
         x16 = ops.pack_ncl(x, 3, 1)                                   # ReflectionPad1d(3)

@@ -312,3 +312,36 @@ def melgan_generator_fwd(weights, x, workspace, out=None):
                                              workspace.numel(), stream_ptr()),
           "ms_melgan_generator_fwd")
     return out
+
+
+# ------------------------------------------------------------------ "exact" operand mode
+class ExactConv:
+    """One dense conv / transposed conv in the EXACT operand mode: both operands as three-term
+    bf16 splits, [x_hi, x_lo, x_hi] * [W_hi, W_hi, W_lo] over 3C channels on the same tcgen05
+    kernel = x*W to ~2^-16 with the RANGE of fp32 (no operand scales, nothing can overflow or
+    fall into subnormals the way fp16 operands can with weights far from the N(0, 0.02) init).
+    3x the MMA work plus one split pass per layer: the parity / dynamic-range fallback of the
+    fast fp16 path, not the production path.  Caches the packed weight image per weight version."""
+
+    def __init__(self):
+        self.key = None
+        self.packed = None
+
+    def __call__(self, x32, w, bias, kind=MS_CONV, dilation=1, pad=0, stride=1, leaky=False,
+                 res32=None, act_in=False, pad_in=0, pad_mode=0):
+        """x32 BLK f32 (B,C/8,L,8) -> y32 BLK f32.  act_in / pad_in / pad_mode: LeakyReLU and
+        zero (0) / reflection (1) padding applied to the input first (fused into the split pass)."""
+        B, C8, L, _ = x32.shape
+        xs = blk32_split(x32, pad_in, pad_mode, act_in, MS_BF16, 3, 1.0)
+        if kind == MS_CONV:
+            cout, cin, k = w.shape
+        else:
+            cin, cout, k = w.shape
+        d = conv_desc(kind, B, 3 * cin, cout, L + 2 * pad_in, k, dilation, pad, stride,
+                      leaky=leaky, operand=MS_BF16)
+        key = (getattr(w, "_msb_key", None) or (w.data_ptr(), w._version), kind, k, stride)
+        if key != self.key:
+            self.packed = pack_conv_weight(d, weight_split(w.detach(), MS_BF16, 1.0, 3, kind))
+            self.key = key
+        _, y32 = conv_fwd(d, xs, self.packed, bias, res32=res32, want16=False, want32=True)
+        return y32
