@@ -77,7 +77,7 @@ typedef struct {
   int cin;       /* multiple of 16 */
   int cout;      /* multiple of 8 (MS_CONV: multiple of 16) */
   int lin;       /* input length */
-  int ksize;     /* taps, 1..24 (MS_CONVT: == 2*stride) */
+  int ksize;     /* taps, 1..32 (MS_CONVT: a multiple >= 2 of stride) */
   int dilation;  /* MS_CONV only */
   int pad;       /* zero padding (both sides) */
   int stride;    /* MS_CONVT only (MS_CONV: must be 1) */
@@ -86,6 +86,9 @@ typedef struct {
   int operand;   /* MS_F16 | MS_BF16 */
   float alpha;   /* accumulator scale (1.0f normally) */
   int crop;      /* MS_CONV: output rows dropped at the end (asymmetric padding) */
+  int x_repeat;  /* 0 / 1: x16 has cin channels.  r > 1: x16 has cin / r channels and the K loop
+                    wraps around them r times -- the operand of a weight-split conv
+                    [x, x] * [W_hi, W_lo] without materialising the duplicated tensor */
 } ms_conv_desc;
 
 /* output length for a descriptor (or <0 on invalid) */
@@ -135,6 +138,11 @@ ms_status ms_weight_split(const float* w, float* out, int cout, int cin, int ksi
 ms_status ms_blk32_split_blk16(const float* x32, void* y16, int batch, int channels, int len,
                                int pad, int pad_mode, int leaky, int operand, int terms,
                                float scale, void* stream);
+/* weight of a stride-s conv with padding k/2 as the stride-1 conv over the space-to-depth input
+ * (ms_space_to_depth_blk16): w (cout, C, k) -> w1 (cout, s*C, taps) with taps = (k/2)/s +
+ * ceil((k/2)/s) + 1 (backward = 0), or the inverse gather of its gradient dw1 -> dw (backward = 1) */
+ms_status ms_strided_weight_view(const float* src, float* dst, int cout, int channels, int ksize,
+                                 int stride, int backward, void* stream);
 /* noise head of ResidualStackFilterBankGenerator (generator/filterbank.py:76-86):
  * y[b,t] = add[b,t] + sum_c a32[b,c,t] * n32[c,t]; a32 BLK f32 (B,C/8,L,8), n32 BLK f32
  * (1,C/8,L,8) shared by the batch, add (B,1,L) or NULL.  _bwd: da32 = dy[b,t] * n32[c,t]. */

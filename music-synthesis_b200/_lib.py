@@ -23,7 +23,7 @@ class ConvDesc(Structure):
     _fields_ = [("kind", c_int), ("batch", c_int), ("cin", c_int), ("cout", c_int),
                 ("lin", c_int), ("ksize", c_int), ("dilation", c_int), ("pad", c_int),
                 ("stride", c_int), ("leaky", c_int), ("operand", c_int),
-                ("alpha", c_float), ("crop", c_int)]
+                ("alpha", c_float), ("crop", c_int), ("x_repeat", c_int)]
 
 
 # name -> (restype, argtypes); every symbol include/msb200.h declares
@@ -46,6 +46,8 @@ SIGNATURES = {
                                         c_void_p]),
     "ms_diag_sum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_void_p]),
+    "ms_strided_weight_view": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p]),
     "ms_noise_mix_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_void_p]),
     "ms_noise_mix_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

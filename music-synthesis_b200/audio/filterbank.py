@@ -172,18 +172,18 @@ class FilterBank:
         cancelling sum (narrow-band filters over a broadband input): rounding its INPUT to fp16
         alone puts 1.9e-3 on the waveform of the 511-tap bank (5e-4 for the 128-tap banks)."""
         B, n = x16.shape[0], self.n_bands
+        xrep = 1
         if wsplit == 2:
             if x32 is None:
                 raise _lib.MsbError("full-split synthesis needs the fp32 activations")
             mult, alpha = 3, 1.0 / (self.SPLIT_SX * self.SPLIT_SW)
             x16 = ops.blk32_split(x32, operand=self.operand, terms=3, scale=self.SPLIT_SX)
         elif wsplit:
-            mult, alpha = 2, 1.0 / ops.W_SPLIT_SCALE
-            x16 = ops.dup_channels(x16)
+            mult, alpha, xrep = 2, 1.0 / ops.W_SPLIT_SCALE, 2    # the K loop wraps over x16 twice
         else:
             mult, alpha = 1, 1.0
         d = ops.conv_desc(MS_CONV, B, mult * n, 16, Lin, self.syn_taps, self.syn_nph, self.syn_pad,
-                          operand=self.operand, alpha=alpha)
+                          operand=self.operand, alpha=alpha, x_repeat=xrep)
         _, z32 = ops.conv_fwd(d, x16, self._synth_weights(d, x16.device, wsplit), None,
                               want16=False, want32=True)
         y = torch.empty((B, 1, Lout), dtype=torch.float32, device=x16.device)

@@ -127,9 +127,9 @@ class ConvBlk(Function):
                                     want16=True, want32=True)
         elif wsplit:
             d = ops.conv_desc(kind, B, 2 * cin, cout, L, k, dilation, pad, stride, leaky=leaky,
-                              alpha=1.0 / ops.W_SPLIT_SCALE)
-            y16, y32 = ops.conv_fwd(d, ops.dup_channels(x16), cache.fwd_wsplit(d, w, kind), b,
-                                    res32=res32, want16=True, want32=True)
+                              alpha=1.0 / ops.W_SPLIT_SCALE, x_repeat=2)
+            y16, y32 = ops.conv_fwd(d, x16, cache.fwd_wsplit(d, w, kind), b, res32=res32,
+                                    want16=True, want32=True)
         else:
             d = ops.conv_desc(kind, B, cin, cout, L, k, dilation, pad, stride, leaky=leaky)
             y16, y32 = ops.conv_fwd(d, x16, cache.fwd(d, w), b, res32=res32, want16=True,
@@ -139,6 +139,7 @@ class ConvBlk(Function):
         ctx.wkey = getattr(w, "_msb_key", None)      # identity of a derived (weight-normed) weight
         ctx.has_res = res32 is not None
         ctx.mark_non_differentiable(y16)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradient" for the 16-bit image
         return y32, y16
 
     @staticmethod
@@ -185,6 +186,7 @@ class ResidualAtomBlk(Function):
         ctx.cfg = (cache1, cache2, dilation)
         ctx.wkeys = (getattr(w1, "_msb_key", None), getattr(w2, "_msb_key", None))
         ctx.mark_non_differentiable(y16)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradient" for the 16-bit image
         return y32, y16
 
     @staticmethod
@@ -221,6 +223,7 @@ class DilatedLayerBlk(Function):
         ctx.save_for_backward(x16, y16, w)
         ctx.cfg = (cache, dilation)
         ctx.mark_non_differentiable(y16)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradient" for the 16-bit image
         return y32, y16
 
     @staticmethod
@@ -264,6 +267,7 @@ class ActPadBlk(Function):
         ctx.save_for_backward(x16)
         ctx.cfg = (x16.shape[2], pad, pad_mode, leaky)
         ctx.mark_non_differentiable(a16)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradient" for the 16-bit image
         return a32, a16
 
     @staticmethod
@@ -422,6 +426,7 @@ class BankAnalysis(Function):
         ctx.bank = bank
         ctx.L = x.shape[-1]
         ctx.mark_non_differentiable(a16)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradient" for the 16-bit image
         return a32, a16
 
     @staticmethod
@@ -469,6 +474,7 @@ class StridedConvBlk(Function):
         ctx.save_for_backward(xs, w, y16)
         ctx.cfg = (sc, stride, length, h16.shape[2], crop, b is not None)
         ctx.mark_non_differentiable(y16)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradient" for the 16-bit image
         return y32, y16
 
     @staticmethod
@@ -482,13 +488,7 @@ class StridedConvBlk(Function):
         if ctx.needs_input_grad[2]:
             dw1 = grad_ops.conv_wgrad(dz16, xs, tuple(w1.shape), 1, pad)
             # back to the (Cout, C, k) layout: tap kk = (j, i) with kk - k//2 = s*j + i
-            half = k // 2
-            j_min = -((half + stride - 1) // stride)
-            dw = torch.empty_like(w)
-            for kk in range(k):
-                m = kk - half
-                j, i = m // stride, m % stride
-                dw[:, :, kk] = dw1[:, i * cin:(i + 1) * cin, j - j_min]
+            dw = ops.strided_conv_weight_grad(dw1, tuple(w.shape), stride)
         dx32 = None
         if ctx.needs_input_grad[0]:
             dxs = _dgrad_conv(sc.cache, w1, dz16, MS_CONV, 1, pad, 1, extra_pad=crop)
@@ -542,6 +542,7 @@ class ReluAvgPool(Function):
         ctx.save_for_backward(a32)
         ctx.cfg = (cw, tw)
         ctx.mark_non_differentiable(p16)
+        ctx.set_materialize_grads(False)   # no zero-filled "gradient" for the 16-bit image
         return p32, p16
 
     @staticmethod

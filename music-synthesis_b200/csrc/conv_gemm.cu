@@ -53,6 +53,9 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
   if (d.batch <= 0 || d.lin <= 0 || d.cin <= 0 || d.cout <= 0) return false;
   if (d.cin % 16 != 0 || d.cout % 8 != 0) return false;
   if (d.operand != MS_F16 && d.operand != MS_BF16) return false;
+  const int xrep = d.x_repeat > 1 ? d.x_repeat : 1;
+  if (d.cin % xrep != 0 || (d.cin / xrep) % 16 != 0) return false;
+  const int xcin = d.cin / xrep;     // k-blocks must not straddle two copies of x
   if (d.kind == MS_CONV) {
     if (d.stride != 1 && d.stride != 0) return false;
     if (d.ksize < 1 || d.ksize > kMaxTaps || d.dilation < 1 || d.pad < 0) return false;
@@ -133,7 +136,7 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     c->MBLK = 1;
     c->RA = 128 + mx - mn;
     const int nth = c->NT / 2;
-    c->KB = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
+    c->KB = xcin % 64 == 0 ? 64 : (xcin % 32 == 0 ? 32 : 16);
     auto pstage = [&](int kb) { return (kb / 8) * c->RA * 16 + c->taps * (kb / 8) * nth * 16; };
     const int pbudget = kSmemBudget - kSmemHeader;
     while (pstage(c->KB) * 3 > pbudget && c->KB > 16) c->KB /= 2;
@@ -165,7 +168,7 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
   }
   c->MBLK = c->Lm > 128 ? 2 : 1;
   c->RA = 128 * c->MBLK + mx - mn;
-  c->KB = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
+  c->KB = xcin % 64 == 0 ? 64 : (xcin % 32 == 0 ? 32 : 16);
   // NT / KB define the packed weight layout, so they must not depend on the input
   // length: size the stages for the largest tile (two M-blocks) regardless of MBLK
   const int ra_max = 256 + mx - mn;
@@ -314,7 +317,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             // one small copy per (clip, channel chunk): all 32 lanes issue them
             for (int i = lane; i < nclips * chunks; i += 32) {
               const int j = i / chunks, c = i - j * chunks;
-              const size_t cbase = static_cast<size_t>(b0 + j) * (p.cin >> 3) + kb * chunks;
+              const size_t cbase = static_cast<size_t>(b0 + j) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
               bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + j * p.fold_stride + a_lo) * 16u,
                        p.x + ((cbase + c) * p.lin + (p.min_off + a_lo)) * 8,
                        static_cast<uint32_t>(frows) * 16u, full_bar(stage));
@@ -348,7 +351,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                                 (static_cast<size_t>(nt_idx) * p.nkb + kb) * p.w_stage_bytes;
           bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
           if (nrows > 0) {
-            const size_t cbase = static_cast<size_t>(b) * (p.cin >> 3) + kb * chunks;
+            const size_t cbase = static_cast<size_t>(b) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
             for (int c = 0; c < chunks; ++c) {
               const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
               bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,
@@ -583,46 +586,58 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 //                                       x[b, ci, lin + e + t - (J-1)] * W[ci, co, r + s*(J-1-t)])
 // Reads the SAME packed 16-bit weights / 16-bit activations as the main GEMM, accumulates in
 // fp32.  Tiny: at most (J-1)*stride*cout outputs per clip.  blockIdx.y = e * stride + r.
-__global__ void convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */,
-                                  int nnt_p /* packed n-tiles */) {
+constexpr int kTailSlices = 8;    // lanes that share one output: each takes every 8th channel chunk
+__global__ void __launch_bounds__(128)
+convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */,
+                  int nnt_p /* packed n-tiles */) {
   const int e = blockIdx.y / p.stride;      // tail row
   const int r = blockIdx.y - e * p.stride;  // phase
   const int b = blockIdx.z;
-  const int co = blockIdx.x * blockDim.x + threadIdx.x;
-  if (co >= p.cout) return;
+  // 16 outputs per block x 8 channel slices (the input-channel loop was 64 dependent L2 round
+  // trips per thread at cin = 512: 40 us for a few thousand outputs)
+  const int slice = threadIdx.x & (kTailSlices - 1);
+  const int co = blockIdx.x * (128 / kTailSlices) + (threadIdx.x >> 3);
   const int orow = p.stride * (p.lin + e) + r - p.pad;
-  if (orow < 0 || orow >= p.Lout) return;
-  const int n = convt_col(r, co, p.stride);   // GEMM column
-  const int nt = n / ntp, nn = n - nt * ntp;
-  const int chunks = p.KB >> 3;
+  const bool live = co < p.cout && orow >= 0 && orow < p.Lout;   // warp-uniform enough: shuffles below
   float acc = 0.f;
-  for (int t = 0; t <= p.taps - 2 - e; ++t) {
-    const int xrow = p.lin + e + t - (p.taps - 1);
-    if (xrow < 0) continue;
-    for (int c8 = 0; c8 < (p.cin >> 3); ++c8) {      // 8 input channels per step (16-byte loads)
-      const int ci = c8 * 8;
-      const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
-      // packed[nt][kb][tap][c][nn][0..7]
-      const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
-      const size_t xi = ((static_cast<size_t>(b) * (p.cin >> 3) + c8) * p.lin + xrow) * 8;
-      const uint4 wq = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
-      const uint4 xq = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
-      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w};
+  if (live) {
+    const int n = convt_col(r, co, p.stride);   // GEMM column
+    const int nt = n / ntp, nn = n - nt * ntp;
+    const int chunks = p.KB >> 3;
+    const int xc8 = p.xcin >> 3;
+    for (int t = 0; t <= p.taps - 2 - e; ++t) {
+      const int xrow = p.lin + e + t - (p.taps - 1);
+      if (xrow < 0) continue;
+      for (int c8 = slice; c8 < (p.cin >> 3); c8 += kTailSlices) {   // 8 input channels per step
+        const int ci = c8 * 8;
+        const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
+        // packed[nt][kb][tap][c][nn][0..7]
+        const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
+        const size_t xi = ((static_cast<size_t>(b) * xc8 + c8 % xc8) * p.lin + xrow) * 8;
+        const uint4 wq = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
+        const uint4 xq = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
+        const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 wf, xf;
-        if (p.operand == MS_BF16) {
-          wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
-          xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
-        } else {
-          wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
-          xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+        for (int j = 0; j < 4; ++j) {
+          float2 wf, xf;
+          if (p.operand == MS_BF16) {
+            wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+            xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
+          } else {
+            wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+            xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+          }
+          acc = fmaf(xf.x, wf.x, acc);
+          acc = fmaf(xf.y, wf.y, acc);
         }
-        acc = fmaf(xf.x, wf.x, acc);
-        acc = fmaf(xf.y, wf.y, acc);
       }
     }
   }
+  // fixed-order combination of the 8 slices (lanes slice = 0..7 of one output are adjacent)
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (!live || slice != 0) return;
   float v = acc * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
   if (p.leaky == 1) v = leaky02(v);
   const size_t idx = ((static_cast<size_t>(b) * (p.cout >> 3) + (co >> 3)) * p.Lout + orow) * 8 + (co & 7);
@@ -688,6 +703,8 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   p.y16 = static_cast<uint16_t*>(y16);
   p.y32 = y32;
   p.B = d.batch; p.cin = d.cin; p.lin = d.lin; p.cout = d.cout;
+  p.xcin = d.cin / (d.x_repeat > 1 ? d.x_repeat : 1);
+  p.xnkb = p.xcin / c.KB;
   p.Lout = c.Lout; p.Lm = c.Lm;
   p.taps = c.taps;
   for (int t = 0; t < kMaxTaps; ++t) p.off[t] = t < c.taps ? c.off[t] : 0;
@@ -706,7 +723,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
 
   if (d.kind == MS_CONVT) {
     // the rows q >= lin first (independent outputs: the last rows of each clip)
-    dim3 tgrid((d.cout + 127) / 128, (c.taps - 1) * d.stride, d.batch);
+    dim3 tgrid((d.cout + 15) / 16, (c.taps - 1) * d.stride, d.batch);
     convt_tail_kernel<<<tgrid, 128, 0, stream>>>(p, c.pair ? c.NT / 2 : c.NT,
                                                  c.pair ? 2 * c.nnt : c.nnt);
     ms_status ts = after_launch("convt_tail_kernel");

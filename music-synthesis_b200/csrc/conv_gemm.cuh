@@ -61,6 +61,7 @@ struct ConvGemmParams {
   uint16_t* y16;        // or null
   float* y32;           // or null
   int B, cin, lin, cout, Lout, Lm;
+  int xcin, xnkb;       // channels of the x tensor (cin / x_repeat) and its k-blocks (xcin / KB)
   int taps;
   int off[kMaxTaps];
   int min_off, RA;

@@ -122,7 +122,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
               ((static_cast<size_t>(nt_idx) * 2 + rank) * p.nkb + kb) * p.w_stage_bytes;
           bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
           if (nrows > 0) {
-            const size_t cbase = static_cast<size_t>(b) * (p.cin >> 3) + kb * chunks;
+            const size_t cbase = static_cast<size_t>(b) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
             for (int c = 0; c < chunks; ++c) {
               const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
               bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,

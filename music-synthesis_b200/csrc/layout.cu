@@ -294,6 +294,35 @@ __global__ void diag_sum_kernel(const float* __restrict__ z, float* __restrict__
   y[gid] = acc;
 }
 
+// Weight of a stride-s conv (padding k/2) as the stride-1 conv over the space-to-depth input
+// (discriminator/multiscale.py:83-88 rewritten, see ms_space_to_depth_blk16):
+//   dir 0: w (Cout, C, k) -> w1 (Cout, s*C, taps), w1[co][i*C + c][t] = w[co][c][(t + jmin)*s + i + k/2]
+//          (0 where that tap does not exist); dir 1: the inverse gather, dw1 -> dw (every (c, kk) has
+//          exactly one image).  taps = jmax - jmin + 1, jmin = -ceil((k/2)/s), jmax = (k/2)/s.
+__global__ void strided_weight_view_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                           int C, int k, int s, int taps, int jmin, int dir,
+                                           size_t total) {
+  const size_t gid = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (gid >= total) return;
+  const int half = k / 2;
+  if (dir == 0) {
+    const int t = static_cast<int>(gid % taps);
+    const int ic = static_cast<int>((gid / taps) % (s * C));
+    const size_t co = gid / (static_cast<size_t>(taps) * s * C);
+    const int i = ic / C, c = ic - i * C;
+    const int kk = (t + jmin) * s + i + half;
+    dst[gid] = (kk >= 0 && kk < k) ? __ldg(src + (co * C + c) * k + kk) : 0.f;
+  } else {
+    const int kk = static_cast<int>(gid % k);
+    const int c = static_cast<int>((gid / k) % C);
+    const size_t co = gid / (static_cast<size_t>(k) * C);
+    const int m = kk - half;
+    const int j = (m >= 0) ? m / s : -((-m + s - 1) / s);
+    const int i = m - j * s;
+    dst[gid] = __ldg(src + (co * s * C + static_cast<size_t>(i) * C + c) * taps + (j - jmin));
+  }
+}
+
 // Noise head of ResidualStackFilterBankGenerator (featuresynth/generator/filterbank.py:76-86):
 //   y[b, t] = add[b, t] + sum_c a[b, c, t] * n[c, t]
 // a: BLK f32 (B, C/8, L, 8) (`to_noise(x)`), n: BLK f32 (1, C/8, L, 8) (the filter-bank analysis
@@ -607,6 +636,21 @@ ms_status ms_diag_sum(const float* z32, float* y, int batch, int channels, int z
                     static_cast<cudaStream_t>(stream)>>>(z32, y, channels / 8, z_len, out_len,
                                                          nphase, skew, total);
   return after_launch("diag_sum_kernel");
+}
+
+ms_status ms_strided_weight_view(const float* src, float* dst, int cout, int channels, int ksize,
+                                 int stride, int backward, void* stream) {
+  if (src == nullptr || dst == nullptr || cout <= 0 || channels <= 0 || ksize <= 0 || stride < 1)
+    return MS_ERR_INVALID;
+  const int half = ksize / 2;
+  const int jmin = -((half + stride - 1) / stride), jmax = half / stride;
+  const int taps = jmax - jmin + 1;
+  const size_t total = backward ? static_cast<size_t>(cout) * channels * ksize
+                                : static_cast<size_t>(cout) * stride * channels * taps;
+  strided_weight_view_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                               static_cast<cudaStream_t>(stream)>>>(
+      src, dst, channels, ksize, stride, taps, jmin, backward ? 1 : 0, total);
+  return after_launch("strided_weight_view_kernel");
 }
 
 ms_status ms_noise_mix_fwd(const float* a32, const float* n32, const float* add, float* y,

@@ -417,6 +417,13 @@ static bool make_wgrad_cfg(int B, int Cm, int Cn, int La, int Lx, int taps, cons
   if (sms <= 0) sms = 148;
   int ks = sms / (c->nnt * c->mblks);
   if (ks < 1) ks = 1;
+  // every split writes a full (taps x 128 x NT) fp32 partial tile and the reduce kernel reads
+  // them all back: with 2 chunks per split (the cfg4 layers: K = B*L of a few thousand rows over
+  // 148 CTAs) that traffic cost 3x the GEMM itself (wgrad_reduce_kernel: 15.7 % of the training
+  // cycle).  At least kMinChunksPerSplit chunks of MMA work per partial tile.
+  constexpr int kMinChunksPerSplit = 8;
+  const int ks_work = (c->total_chunks + kMinChunksPerSplit - 1) / kMinChunksPerSplit;
+  if (ks > ks_work) ks = ks_work;
   if (ks > c->total_chunks) ks = c->total_chunks;
   c->chunks_per_split = (c->total_chunks + ks - 1) / ks;
   c->ksplit = (c->total_chunks + c->chunks_per_split - 1) / c->chunks_per_split;

@@ -74,24 +74,24 @@ class FilterBankChannelGenerator(nn.Module):
         """x16: BLK 16-bit (B, Cin/8, T, 8) features (shared by all bands)."""
         B = x16.shape[0]
         emb = self.main[0][0]
-        ws = self.weight_split and self.operand == MS_F16
+        ws = self.weight_split and self.operand == MS_F16 and not ops.relaxed()
         mult, alpha = (2, 1.0 / ops.W_SPLIT_SCALE) if ws else (1, 1.0)
 
         def run(i, d, h16, w, bias, kind):
-            if ws:
-                return ops.conv_fwd(d, ops.dup_channels(h16), self._cache[i].fwd_wsplit(d, w, kind),
-                                    bias)[0]
+            if ws:       # the K loop wraps over h16 twice (x_repeat): [x, x] * [W_hi, W_lo]
+                return ops.conv_fwd(d, h16, self._cache[i].fwd_wsplit(d, w, kind), bias)[0]
             return ops.conv_fwd(d, h16, self._packed[i].get(d, w), bias)[0]
 
         d = ops.conv_desc(MS_CONV, B, mult * emb.in_channels, emb.out_channels, T, 7, 1, 3,
-                          leaky=True, operand=self.operand, alpha=alpha)
+                          leaky=True, operand=self.operand, alpha=alpha, x_repeat=mult)
         h16 = run(0, d, x16, emb.weight, emb.bias, MS_CONV)
         L = T
         for i in range(1, len(self.main)):
             up = self.main[i]
             s = up.scale_factor
             d = ops.conv_desc(MS_CONVT, B, mult * up.in_channels, up.out_channels, L, 2 * s, 1,
-                              (2 * s - s) // 2, s, leaky=True, operand=self.operand, alpha=alpha)
+                              (2 * s - s) // 2, s, leaky=True, operand=self.operand, alpha=alpha,
+                              x_repeat=mult)
             h16 = run(i, d, h16, up.conv.weight, None, MS_CONVT)
             L *= s
         # F.pad(x, (0, 1)) + transposed_convolve, generator/multiscale.py:90-91

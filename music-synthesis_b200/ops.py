@@ -15,9 +15,9 @@ OPERANDS = {"f16": MS_F16, "fp16": MS_F16, "bf16": MS_BF16}
 
 
 def conv_desc(kind, batch, cin, cout, lin, ksize, dilation=1, pad=0, stride=1, leaky=False,
-              operand=MS_F16, alpha=1.0, crop=0):
+              operand=MS_F16, alpha=1.0, crop=0, x_repeat=1):
     return ConvDesc(kind, batch, cin, cout, lin, ksize, dilation, pad, stride, int(leaky),
-                    operand, alpha, crop)
+                    operand, alpha, crop, x_repeat)
 
 
 def conv_out_len(desc):
@@ -71,6 +71,28 @@ def weight_split(w, operand=MS_F16, scale=1.0, terms=3, kind=MS_CONV):
 #: power-of-two weight scale of the weight-split forward: N(0, 0.02)-sized weights give lo terms
 #: of ~1e-5, inside the fp16 subnormals; x256 moves them to ~2.5e-3 (overflow beyond |w| ~ 250)
 W_SPLIT_SCALE = 256.0
+
+
+_relaxed = [False]
+
+
+class relaxed_forward:
+    """Context of DiscriminatorTrainer's generator call: that fake batch is not returned to the
+    caller, it only feeds the discriminator's loss (asserted to 2e-3), so modules may skip the
+    precision extras of their inference path (the weight-split forward of the filter-bank
+    generators: 2x the MMA work)."""
+
+    def __enter__(self):
+        self.prev = _relaxed[0]
+        _relaxed[0] = True
+
+    def __exit__(self, *exc):
+        _relaxed[0] = self.prev
+        return False
+
+
+def relaxed():
+    return _relaxed[0]
 
 
 def dup_channels(x16, times=2):
@@ -140,20 +162,32 @@ def space_to_depth(x16, stride, length=None):
     return y
 
 
-def strided_conv_weight(w, stride):
-    """(Cout, C, k) weight of a stride-s conv with padding k//2 -> the equivalent stride-1
-    weight (Cout, s*C, taps) over the space-to-depth input, and (taps, pad)."""
-    cout, c, k = w.shape
+def strided_conv_geometry(k, stride):
     half = k // 2
     j_min = -((half + stride - 1) // stride)
-    j_max = half // stride
-    taps = j_max - j_min + 1
-    out = torch.zeros((cout, stride * c, taps), dtype=w.dtype, device=w.device)
-    for kk in range(k):
-        m = kk - half
-        j, i = m // stride, m % stride
-        out[:, i * c:(i + 1) * c, j - j_min] = w[:, :, kk]
-    return out.contiguous(), taps, -j_min
+    return half // stride - j_min + 1, -j_min          # (taps, pad)
+
+
+def strided_conv_weight(w, stride):
+    """(Cout, C, k) weight of a stride-s conv with padding k//2 -> the equivalent stride-1
+    weight (Cout, s*C, taps) over the space-to-depth input, and (taps, pad) -- one kernel launch
+    (ms_strided_weight_view)."""
+    w = w.contiguous()
+    cout, c, k = w.shape
+    taps, pad = strided_conv_geometry(k, stride)
+    out = torch.empty((cout, stride * c, taps), dtype=w.dtype, device=w.device)
+    check(_lib.lib().ms_strided_weight_view(ptr(w), ptr(out), cout, c, k, stride, 0, stream_ptr()),
+          "ms_strided_weight_view")
+    return out, taps, pad
+
+
+def strided_conv_weight_grad(dw1, w_shape, stride):
+    """gradient of strided_conv_weight: dw1 (Cout, s*C, taps) -> dw (Cout, C, k)"""
+    cout, c, k = w_shape
+    dw = torch.empty((cout, c, k), dtype=dw1.dtype, device=dw1.device)
+    check(_lib.lib().ms_strided_weight_view(ptr(dw1.contiguous()), ptr(dw), cout, c, k, stride, 1,
+                                            stream_ptr()), "ms_strided_weight_view")
+    return dw
 
 
 def conv_to_mono(x32, w, bias, ksize, pad, tanh_out):

@@ -244,7 +244,8 @@ class DiscriminatorTrainer(_GraphMixin):
         if self.exact_reference_grads:
             fake = self.generator(features)
         else:
-            with torch.no_grad():
+            from .. import ops
+            with torch.no_grad(), ops.relaxed_forward():
                 fake = self.generator(features)
         if self.exact_reference_grads:
             _, f_score = self.discriminator(fake, features)

@@ -17,3 +17,18 @@ def rnd16(t, operand="f16"):
 def randn(seed, *shape, scale=1.0):
     rs = np.random.RandomState(seed)
     return torch.from_numpy((rs.standard_normal(shape) * scale).astype(np.float32))
+
+
+def strided_weight_view_ref(w, stride):
+    """index map of ms_strided_weight_view (forward): (Cout, C, k) -> (Cout, s*C, taps) with
+    w1[co][i*C + c][j - jmin] = w[co][c][kk], kk - k//2 = s*j + i"""
+    cout, c, k = w.shape
+    half = k // 2
+    j_min = -((half + stride - 1) // stride)
+    taps = half // stride - j_min + 1
+    out = torch.zeros((cout, stride * c, taps), dtype=w.dtype)
+    for kk in range(k):
+        m = kk - half
+        j, i = m // stride, m % stride
+        out[:, i * c:(i + 1) * c, j - j_min] = w[:, :, kk]
+    return out

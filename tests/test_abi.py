@@ -109,17 +109,21 @@ def test_packed_weight_layout_is_length_independent(lib):
 @pytest.mark.parametrize("k,s", [(7, 2), (7, 4), (41, 4), (41, 2), (9, 4)])
 def test_strided_conv_weight_rewrite_is_exact_on_cpu(k, s):
     """host logic behind every strided conv on the tcgen05 path: Conv1d(k, stride s, pad k//2)
-    == stride-1 conv over the space-to-depth input with ops.strided_conv_weight (checked here
-    with CPU torch ops; the GPU tests check the kernels)"""
+    == stride-1 conv over the space-to-depth input with the weight view of
+    ms_strided_weight_view (its index map restated in tests/gpu_util.py and checked here with
+    CPU torch ops; tests/test_gpu_kernels.py checks the kernel against the same restatement)"""
     import torch
     import torch.nn.functional as F
     from music_synthesis_b200 import ops
+    from tests.gpu_util import strided_weight_view_ref
     torch.manual_seed(0)
     B, C, Co, L = 2, 3, 5, 37
     x = torch.randn(B, C, L)
     w = torch.randn(Co, C, k)
     ref = F.conv1d(x, w, stride=s, padding=k // 2)
-    w1, taps, pad = ops.strided_conv_weight(w, s)
+    taps, pad = ops.strided_conv_geometry(k, s)
+    w1 = strided_weight_view_ref(w, s)
+    assert w1.shape == (Co, s * C, taps)
     lx = (L + s - 1) // s
     xp = F.pad(x, (0, lx * s - L))
     xs = xp.reshape(B, C, lx, s).permute(0, 3, 1, 2).reshape(B, s * C, lx)      # Y[i*C + c, u] = X[c, s*u + i]

@@ -211,3 +211,16 @@ def test_conv_many_tiles_per_cta(ops, pairs):
     got = ops.unpack_blk32(y32).cpu()
     per_clip = (got - ref).double().norm(dim=(1, 2)) / ref.double().norm(dim=(1, 2))
     assert per_clip.max().item() < 1e-5, per_clip.tolist()
+
+
+@pytest.mark.parametrize("k,s", [(7, 2), (7, 4), (41, 4), (41, 2), (9, 4)])
+def test_strided_weight_view_kernel_both_directions(k, s):
+    """ms_strided_weight_view: the stride-1 weight over the space-to-depth input and the inverse
+    gather of its gradient, bit-exact against the restated index map"""
+    from music_synthesis_b200 import ops
+    from tests.gpu_util import randn, strided_weight_view_ref
+    w = randn(31, 6, 5, k)
+    w1, taps, pad = ops.strided_conv_weight(w.cuda(), s)
+    ref = strided_weight_view_ref(w, s)
+    assert (taps, pad) == ops.strided_conv_geometry(k, s) and torch.equal(w1.cpu(), ref)
+    assert torch.equal(ops.strided_conv_weight_grad(w1, tuple(w.shape), s).cpu(), w)
