@@ -245,6 +245,21 @@ ms_status ms_resstack_tail_fwd(int batch, int len, const int* dilations /* [3] *
                                const float* tail_w /* (1,32,7) */, const float* tail_b,
                                float* y, void* stream);
 
+/* One generator stage in one kernel: ConvTranspose1d(2C -> C, k 4, stride 2, pad 1) +
+ * LeakyReLU(0.2) + ResidualStack(C) [+ the 32 -> 1 k7 conv + tanh when tail_y != NULL, C = 32].
+ *   replaces generator/full.py:35-37 (C = 64) and 39-44 (C = 32); atoms util/modules.py:350-405.
+ *   params: 14 device pointers in state-dict order (ConvTranspose w (2C,C,4), b, then the
+ *   stack's 12).  x16: BLK 16-bit (B,2C/8,lin,8), the previous stage's operand image;
+ *   y16 / y32: BLK (B,C/8,2*lin,8) or NULL; tail_y: (B,1,2*lin) f32.  Dilations must be odd
+ *   (phase-split tiles), d0+d1+d2+3 <= 16. */
+int ms_upstack_supported(int channels);
+size_t ms_upstack_packed_weight_bytes(int channels);
+ms_status ms_upstack_pack_weights(const float* const* params /* 14 device ptrs */, int channels,
+                                  int operand, void* packed, void* stream);
+ms_status ms_upstack_fwd(int channels, int batch, int lin, const int* dilations /* [3] */,
+                         int operand, const void* x16, const void* packed, void* y16, float* y32,
+                         const float* tail_w, const float* tail_b, float* tail_y, void* stream);
+
 /* ---------------------------------------------------------------------------
  * FFT octave-band split / merge (the fixed multiscale FFT filterbank).
  *   replaces fft_frequency_decompose / fft_resample / fft_frequency_recompose,

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libmsb200.so")
 SOURCES = ["runtime.cu", "conv_gemm.cu", "layout.cu", "generator.cu", "audio2mel.cu",
-           "resstack.cu", "conv_gemm2.cu", "direct_conv.cu", "losses.cu", "fft_bands.cu",
+           "resstack.cu", "upstack.cu", "conv_gemm2.cu", "direct_conv.cu", "losses.cu", "fft_bands.cu",
            "wgrad.cu", "backward.cu", "datafeed.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -74,6 +74,11 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "ms_resstack_tail_fwd": (c_int, [c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ms_upstack_supported": (c_int, [c_int]),
+    "ms_upstack_packed_weight_bytes": (c_size_t, [c_int]),
+    "ms_upstack_pack_weights": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),
+    "ms_upstack_fwd": (c_int, [c_int, c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ms_fft_bands_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ms_fft_frequency_decompose": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p), c_int,
                                            c_void_p, c_size_t, c_void_p]),

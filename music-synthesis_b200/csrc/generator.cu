@@ -24,8 +24,23 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
                        const float* x32, const void* packed, void* y16, float* y32,
                        cudaStream_t stream, const float* mono_w, const float* mono_b,
                        float* mono_out, const void* x16in);
+ms_status upstack_fwd(int channels, int batch, int lin, const int* dil, int operand,
+                      const void* x16, const void* packed, void* y16, float* y32,
+                      const float* mono_w, const float* mono_b, float* mono_out,
+                      cudaStream_t stream);
 
 namespace {
+
+// MSB_FUSE_UP=0: run the stride-2 upsamplers as separate launches in front of the fused stacks
+// (the round-1 schedule; kept for A/B timing).  Default: one launch per stage (upstack.cu).
+bool fuse_upsamplers() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MSB_FUSE_UP");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 // MSB_STAGE1_CHUNK: clips per sub-chunk of the leading low-rate layers (0 = whole pass)
 int stage1_chunk() {
@@ -63,7 +78,8 @@ struct GenLayer {
   size_t w_off, b_off;
   int role;         // 0 first conv, 1 upsampler, 2 atom conv1, 3 atom conv2,
                     // 4 fused ResidualStack (w_param = first of its 12 params), 5 = upsampler
-                    // feeding a fused stack (fp32 output only)
+                    // feeding a fused stack (fp32 output only), 6 = upsampler + ResidualStack
+                    // (+ tail) in one kernel (w_param = first of its 14 params)
   int len_mult;     // lin = len_mult * T (+6 for the first conv)
 };
 
@@ -106,6 +122,17 @@ bool build_plan(int in_channels, int operand, GenPlan* plan) {
     ms_conv_desc u{};
     u.kind = MS_CONVT; u.cin = kUp[s][0]; u.cout = kUp[s][1]; u.ksize = kUp[s][2];
     u.stride = kUp[s][3]; u.pad = kUp[s][4]; u.dilation = 1; u.leaky = 1;
+    if (fuse_upsamplers() && u.ksize == 4 && u.stride == 2 && ms_upstack_supported(u.cout)) {
+      GenLayer L{};
+      L.d = u; L.d.operand = operand;
+      L.role = 6; L.len_mult = mult;    // lin = mult * T
+      L.w_param = param; param += 14; L.b_param = -1;
+      L.w_off = off; off = align_up(off + ms_upstack_packed_weight_bytes(u.cout), 256);
+      L.b_off = 0;
+      plan->layers.push_back(L);
+      mult *= 2;
+      continue;
+    }
     if (!add(u, 1, mult)) return false;
     mult *= kUp[s][3];
     if (ms_resstack_supported(kUp[s][1])) {
@@ -171,6 +198,12 @@ ms_status ms_melgan_pack_weights(const float* const* params, int in_channels, in
       ms_status s4 = ms_resstack_pack_weights(params + L.w_param, L.d.cout, operand,
                                               base + L.w_off, stream);
       if (s4 != MS_OK) return s4;
+      continue;
+    }
+    if (L.role == 6) {
+      ms_status s6 = ms_upstack_pack_weights(params + L.w_param, L.d.cout, operand,
+                                             base + L.w_off, stream);
+      if (s6 != MS_OK) return s6;
       continue;
     }
     ms_status s = ms_conv_pack_weight(&L.d, params[L.w_param], base + L.w_off, stream);
@@ -285,6 +318,20 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
     cur16 = x16[cur];
     for (size_t li = nlead; li < plan.layers.size(); ++li) {
       const GenLayer& L = plan.layers[li];
+      if (L.role == 6) {
+        // upsampler + ResidualStack (+ tail) in one kernel: 16-bit operand in, 16-bit out
+        const bool tail = L.d.cout == 32;
+        void* out16 = (cur16 == x16[1]) ? x16[0] : x16[1];
+        s = upstack_fwd(L.d.cout, nb, L.len_mult * frames, kDil, operand, cur16, wb + L.w_off,
+                        tail ? nullptr : out16, nullptr,
+                        tail ? reinterpret_cast<const float*>(wb + plan.final_w_off) : nullptr,
+                        tail ? reinterpret_cast<const float*>(wb + plan.final_b_off) : nullptr,
+                        tail ? y + static_cast<size_t>(b0) * 256 * T : nullptr, st);
+        if (s != MS_OK) return s;
+        if (tail) fused_tail = true;
+        cur16 = out16;
+        continue;
+      }
       if (L.role == 4) {
         // fused ResidualStack: fp32 stream in, 16-bit operand (+ fp32 for the last stage) out
         if (L.d.cout == 32) {

@@ -1,0 +1,675 @@
+// Fused upsampling stage: ConvTranspose1d(2C -> C, k = 4, stride 2, pad 1) + LeakyReLU(0.2) +
+// ResidualStack(C) [+ the generator's 32 -> 1 k7 conv + tanh] in ONE kernel.
+//   replaces generator/full.py:35-37 (C = 64), 39-44 (C = 32) and
+//   ResidualStack.forward / ResidualAtom.forward, util/modules.py:350-405.
+//
+// The upsampler's fp32 output (the residual stream the stack starts from) never exists in
+// HBM: it is produced by tcgen05 MMAs straight into the stack's accumulator columns in tensor
+// memory, and the stage reads only the previous stage's 16-bit operand image (2 bytes per
+// input element instead of a 4-byte write + 4-byte read per OUTPUT element).
+//
+// Phase-split tile.  A tile covers R = MB*128 output rows t = t0 + 2m + r (t0 even).  Even rows
+// (r = 0, "E") and odd rows (r = 1, "O") live in separate 128-row M-blocks: SMEM operand row
+// r*R/2 + m, TMEM lane m % 128.  Why: the polyphase form of the transposed convolution,
+//     out[2u]     = x[u] W[..,1] + x[u-1] W[..,3]
+//     out[2u + 1] = x[u+1] W[..,0] + x[u] W[..,2],
+// makes each phase a plain GEMM over the INPUT-rate rows u, so with phase-split M-blocks its
+// result lands in exactly the TMEM lanes the stack uses -- no cross-lane shuffle.  The stack's
+// dilations (1, 3, 9 and the inner 1) are all odd, so a tap +-d of an E block reads a shifted
+// window of the O rows and vice versa: still "the same buffer, descriptor start advanced".
+//     E block, m0:  -d -> O[m0 - (d+1)/2]   0 -> E[m0]   +d -> O[m0 + (d-1)/2]
+//     O block, m0:  -d -> E[m0 - (d-1)/2]   0 -> O[m0]   +d -> E[m0 + (d+1)/2]
+//
+// Per tile seven pipelined stages (MMA warp <-> 16 epilogue warps, two parts per tile exactly as
+// in resstack.cu): stage 0 = the transposed conv (input: R/2 + 2 low-rate rows x 2C channels,
+// brought in by bulk async copies into the activation buffer the stack is not using), stages
+// 1..6 = the six k3 convs.  Buffers alternate per tile: tile i's input lands in buf[i & 1]
+// while tile i-1's stage 6 still reads the other one.
+// Rows: the low-rate window holds R/2 rows (q0 = t0/2 - 1 onwards), two short of what the last
+// three output rows need; together with the stack's reach of 16 that costs 4 stored rows per
+// tile (V = R - 2*halo - 4).
+#include <cstdlib>
+#include <type_traits>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+#include "runtime.cuh"
+
+namespace msb {
+
+namespace {
+
+constexpr int kUpHalo = 16;
+constexpr int kUpHeader = 1024;
+constexpr int kUpStages = 7;            // transposed conv + six convs
+constexpr int kUpEntries = 8 + 18;      // weight images per tile (C x C 16-bit each)
+
+struct UpStackParams {
+  const uint16_t* x16;   // BLK 16-bit (B, 2C/8, lin, 8): previous stage's operand image
+  const uint16_t* w;     // [26][C/8][C][8] 16-bit: 8 transposed-conv images, 18 conv taps
+  const float* bias;     // [7][C]: transposed conv, six convs
+  uint16_t* y16;         // BLK 16-bit (B, C/8, L, 8) or null
+  float* y32;            // BLK f32 or null
+  int B, lin, L;         // L = 2 * lin
+  int dil[3];
+  int tiles_per_clip, total_tiles;
+  int halo, V;
+  const float* mono_w;   // fused tail (C == 32): (1, 32, 7) fp32
+  const float* mono_b;
+  float* mono_out;       // (B, 1, L) fp32
+};
+
+template <int C>
+struct UpGeom {
+  static constexpr int MB = 256 / C;          // M-blocks per tile
+  static constexpr int NP = 2;                // pipeline parts per tile
+  static constexpr int HB = MB / NP;          // M-blocks per part
+  static constexpr int HE = HB / 2;           // E (and O) blocks per part
+  static constexpr int MSPLIT = 2;            // M-block split of the epilogue
+  static constexpr int PARTS = 2;             // column split of the epilogue
+  static constexpr int EW = 16;               // epilogue warps = 4 * PARTS * MSPLIT
+  static constexpr int R = MB * 128;          // output rows per tile
+  static constexpr int RH = R / 2;            // rows per phase = low-rate rows staged
+  static constexpr int NCH = C / 8;
+  static constexpr int ACT_BYTES = R * C * 2; // 65536
+  static constexpr int TAP_BYTES = C * C * 2;
+  static constexpr int NSLOT = (96 * 1024 / TAP_BYTES) < 18 ? (96 * 1024 / TAP_BYTES) : 18;
+  static constexpr int MONO_BYTES = 1024;
+  static constexpr int P_BYTES = (C == 32) ? 14 * R * 4 : 0;
+  static constexpr int SMEM = kUpHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES + P_BYTES;
+  static_assert(HB >= 2 && HB % 2 == 0, "a part needs E and O blocks");
+};
+
+template <bool BF>
+__device__ __forceinline__ uint32_t pack2u(float a, float b) {
+  if (BF) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_h2(a, b);
+}
+
+template <int C, bool BF>
+__device__ __forceinline__ void upstack_body(const UpStackParams& p) {
+  constexpr int kOp = BF ? MS_BF16 : MS_F16;
+  using G = UpGeom<C>;
+  constexpr int HB = G::HB, HE = G::HE, R = G::R, RH = G::RH, EW = G::EW, NP = G::NP;
+  constexpr int NSLOT = G::NSLOT, TAPB = G::TAP_BYTES;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  // [0,18) wfull  [18,36) wempty  [36,38) acc_full  [38,40) act_ready  40 in_full  41 in_free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 640);
+  const uint32_t bar_base = smem_u32(bars);
+  const uint32_t sBuf0 = smem_u32(smem + kUpHeader);
+  const uint32_t sW = sBuf0 + 2 * G::ACT_BYTES;
+  float* sMono = reinterpret_cast<float*>(smem + kUpHeader + 2 * G::ACT_BYTES + NSLOT * TAPB);
+  float* sP = sMono + G::MONO_BYTES / 4;
+  const bool mono = (C == 32) && (p.mono_out != nullptr);
+  auto wfull = [&](int s) { return bar_base + 8u * s; };
+  auto wempty = [&](int s) { return bar_base + 8u * (18 + s); };
+  auto acc_full = [&](int m) { return bar_base + 8u * (36 + m); };
+  auto act_ready = [&](int m) { return bar_base + 8u * (38 + m); };
+  const uint32_t in_full = bar_base + 8u * 40;
+  const uint32_t in_free = bar_base + 8u * 41;
+  auto buf = [&](int i) { return sBuf0 + static_cast<uint32_t>(i & 1) * G::ACT_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 18; ++s) {
+      mbar_init(wfull(s), 1);
+      mbar_init(wempty(s), 1);
+    }
+    for (int m = 0; m < NP; ++m) {
+      mbar_init(acc_full(m), 1);
+      mbar_init(act_ready(m), EW);
+    }
+    mbar_init(in_full, 1);
+    mbar_init(in_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  if (mono) {
+    for (int i = threadIdx.x; i < 7 * 32; i += blockDim.x)
+      sMono[i] = p.mono_w[(i & 31) * 7 + (i >> 5)];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tile_first = static_cast<int>(blockIdx.x);
+  const int tile_stride = static_cast<int>(gridDim.x);
+
+  if (warp == 0) {
+    // ================= producer: low-rate input window + weight images =================
+    constexpr int CH2 = 2 * C / 8;    // 16-byte channel chunks of the input
+    uint32_t pos = 0;
+    int it = 0;
+    for (int tile = tile_first; tile < p.total_tiles; tile += tile_stride, ++it) {
+      const int b = tile / p.tiles_per_clip;
+      const int t0 = (tile % p.tiles_per_clip) * p.V - p.halo;     // even
+      const int q0 = (t0 >> 1) - 1;                                // low-rate row of window row 0
+      const int lo = q0 < 0 ? 0 : q0;
+      const int hi = (q0 + RH) > p.lin ? p.lin : (q0 + RH);
+      const int nrows = hi > lo ? hi - lo : 0;
+      const uint32_t dstb = buf(it);
+      // the buffer was last read by stage 5 of this CTA's previous tile
+      mbar_wait(in_free, static_cast<uint32_t>(it & 1) ^ 1u);
+      if (nrows != RH) {
+        // rows outside [0, lin): the transposed conv sees zeros there
+        const int head = lo - q0;
+        const int tail0 = head + nrows;
+        const int nz = head + (RH - tail0);
+        for (int i = lane; i < nz * CH2; i += 32) {
+          const int c = i / nz;
+          int r = i - c * nz;
+          r = r < head ? r : tail0 + (r - head);
+          st_shared_v4(dstb + static_cast<uint32_t>(c * RH + r) * 16u, 0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
+      if (lane == 0)
+        mbar_arrive_expect_tx(in_full, static_cast<uint32_t>(nrows) * 16u * CH2);
+      __syncwarp();
+      if (lane < CH2 && nrows > 0) {
+        const uint16_t* src =
+            p.x16 + ((static_cast<size_t>(b) * CH2 + lane) * p.lin + lo) * 8;
+        bulk_g2s(dstb + static_cast<uint32_t>(lane * RH + (lo - q0)) * 16u, src,
+                 static_cast<uint32_t>(nrows) * 16u, in_full);
+      }
+      __syncwarp();
+      for (int e = 0; e < kUpEntries; ++e, ++pos) {
+        const int slot = pos % NSLOT;
+        const uint32_t par = (pos / NSLOT) & 1u;
+        mbar_wait(wempty(slot), par ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(wfull(slot), TAPB);
+          bulk_g2s(sW + slot * TAPB,
+                   reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(e) * TAPB, TAPB,
+                   wfull(slot));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint32_t idesc = umma_idesc_f16(C, kOp);
+    const uint64_t adesc_up = umma_desc_base_nosw(RH * 16, 128);   // input window [2C/8][RH][8]
+    const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);      // activations [C/8][R][8]
+    const uint64_t bdesc0 = umma_desc_base_nosw(C * 16, 128);
+    uint32_t pos = 0;     // ring position of the current stage's first weight image
+    uint32_t g = 0;       // stages issued so far (parity of the act_ready waits)
+    int it = 0;
+    auto wait_w = [&](uint32_t q) { mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u); };
+    auto commit = [&](uint32_t bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+    for (int tile = tile_first; tile < p.total_tiles; tile += tile_stride, ++it) {
+      const uint32_t inb = buf(it), oth = buf(it + 1);
+      // ---------------- stage 0: transposed conv, phase r = e >> 2 ----------------
+      mbar_wait(in_full, static_cast<uint32_t>(it & 1));
+      for (int part = 0; part < NP; ++part) {
+        mbar_wait(act_ready(part), g & 1u);
+        tc_fence_after();
+        for (int e = 0; e < 8; ++e) {
+          if (part == 0) wait_w(pos + e);
+          const int r = e >> 2, tapsel = (e >> 1) & 1, kh = e & 1;
+          const int shift = (r ? 2 : 1) - tapsel;
+          const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(((pos + e) % NSLOT) * TAPB)) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < HE; ++kk) {
+              const int mb = part * HB + r * HE + kk;
+              const int k = part * HE + kk;
+              const uint64_t ad =
+                  adesc_up +
+                  ((inb + static_cast<uint32_t>((kh * (C / 8) * RH + k * 128 + shift) * 16)) >> 4);
+              const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
+#pragma unroll
+              for (int k16 = 0; k16 < C / 16; ++k16)
+                umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * 2 * RH),
+                            bd + static_cast<uint64_t>(k16 * 2 * C), idesc, 1u);
+            }
+          }
+          __syncwarp();
+          if (part == NP - 1) commit(wempty((pos + e) % NSLOT));
+        }
+        commit(acc_full(part));
+      }
+      pos += 8;
+      ++g;
+      // ---------------- stages 1..6: the six k3 convs ----------------
+      for (int l = 0; l < 6; ++l, pos += 3, ++g) {
+        const int d = (l & 1) ? 1 : p.dil[l >> 1];
+        const uint32_t src = (l & 1) ? inb : oth;
+        // tap t on blocks [kk0, kk1) of both phases of `part`
+        auto issue = [&](int t, int part, int kk0, int kk1) {
+          const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(((pos + t) % NSLOT) * TAPB)) >> 4);
+          // source row of output row m0 of an E / O block (see the header comment)
+          const int offE = t == 1 ? 0 : (t == 0 ? RH - (d + 1) / 2 : RH + (d - 1) / 2);
+          const int offO = t == 1 ? RH : (t == 0 ? -(d - 1) / 2 : (d + 1) / 2);
+          if (elect_one()) {
+            for (int r = 0; r < 2; ++r) {
+              for (int kk = kk0; kk < kk1; ++kk) {
+                const int mb = part * HB + r * HE + kk;
+                const int row = (part * HE + kk) * 128 + (r ? offO : offE);
+                const uint64_t ad = adesc0 + ((src + static_cast<uint32_t>(row * 16)) >> 4);
+                const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
+#pragma unroll
+                for (int k16 = 0; k16 < C / 16; ++k16)
+                  umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * 2 * R),
+                              bd + static_cast<uint64_t>(k16 * 2 * C), idesc, 1u);
+              }
+            }
+          }
+          __syncwarp();
+        };
+        for (int part = 0; part < NP; ++part) {
+          mbar_wait(act_ready(part), g & 1u);
+          tc_fence_after();
+          if (part > 0) {
+            // tap +d of the previous part's last E and O blocks reads into this part
+            issue(2, part - 1, HE - 1, HE);
+            commit(acc_full(part - 1));
+          } else {
+            wait_w(pos + 0);
+          }
+          issue(0, part, 0, HE);
+          if (part == NP - 1) commit(wempty((pos + 0) % NSLOT));
+          if (part == 0) wait_w(pos + 1);
+          issue(1, part, 0, HE);
+          if (part == NP - 1) commit(wempty((pos + 1) % NSLOT));
+          if (part == 0) wait_w(pos + 2);
+          issue(2, part, 0, part == NP - 1 ? HE : HE - 1);
+        }
+        commit(wempty((pos + 2) % NSLOT));
+        commit(acc_full(NP - 1));
+        // stage 5 was the last reader of `oth`: the next tile's input window may land there
+        if (l == 4) commit(in_free);
+      }
+    }
+  } else {
+    // ========================== epilogue warps (16) ==========================
+    const int e = warp - 2;
+    const int q = warp & 3;                   // TMEM lane quarter of this warp
+    const int cpart = (e >> 2) % G::PARTS;    // column slice
+    const int ms = (e >> 2) / G::PARTS;       // M-block slice
+    constexpr int COLS = C / G::PARTS;
+    constexpr int NG = COLS / 16;
+    constexpr int IT = HB / G::MSPLIT;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int chunk0 = cpart * (COLS / 8);
+    const int row0 = q * 32 + lane;
+    const uint32_t tm0 = tmem_base + lane_off + static_cast<uint32_t>(cpart * COLS);
+    uint32_t g = 0;
+    auto arrive_act = [&](int h) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(act_ready(h));
+    };
+    auto store_bias = [&](int s, uint32_t ta) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + s * C + cpart * COLS);
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) {
+        uint32_t bv[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 t4 = __ldg(b4 + gg * 4 + j4);
+          bv[j4 * 4 + 0] = __float_as_uint(t4.x); bv[j4 * 4 + 1] = __float_as_uint(t4.y);
+          bv[j4 * 4 + 2] = __float_as_uint(t4.z); bv[j4 * 4 + 3] = __float_as_uint(t4.w);
+        }
+        tmem_st16p(ta + gg * 16, bv);
+      }
+    };
+    // block j of a part: phase r, SMEM row of this thread, time-order row in the tile
+    auto geom = [&](int h, int u, int& mb, int& srow, int& trow) {
+      const int j = ms + u * G::MSPLIT;
+      const int r = j / HE, kk = j % HE;
+      mb = h * HB + j;
+      const int m = (h * HE + kk) * 128 + row0;
+      srow = r * RH + m;
+      trow = 2 * m + r;
+    };
+    // before the first tile: every accumulator holds the transposed conv's bias
+    for (int h = 0; h < NP; ++h) {
+#pragma unroll
+      for (int u = 0; u < IT; ++u) {
+        int mb, srow, trow;
+        geom(h, u, mb, srow, trow);
+        store_bias(0, tm0 + static_cast<uint32_t>(mb * 2 * C + C));
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      arrive_act(h);
+    }
+    int it = 0;
+    for (int tile = tile_first; tile < p.total_tiles; tile += tile_stride, ++it) {
+      const int b = tile / p.tiles_per_clip;
+      const int t0 = (tile % p.tiles_per_clip) * p.V - p.halo;
+      const bool edge = (t0 < 0) || (t0 + R > p.L);
+      const uint32_t inb = buf(it), oth = buf(it + 1);
+      // KIND 0: transposed conv (stream := leaky(acc)), 1: first conv of an atom,
+      //      2: second conv (stream += leaky(acc)), 3: last conv of the stack
+      auto stage_epi = [&](auto kind_t, const int s) {
+        constexpr int KIND = decltype(kind_t)::value;
+        constexpr bool resid = KIND >= 2;
+        constexpr bool last = KIND == 3;
+        const uint32_t dstbuf = (KIND == 1) ? inb : oth;
+        for (int h = 0; h < NP; ++h) {
+          mbar_wait(acc_full(h), g & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int u = 0; u < IT; ++u) {
+            int mb, srow, trow;
+            geom(h, u, mb, srow, trow);
+            const int t = t0 + trow;
+            const uint32_t tx = tm0 + static_cast<uint32_t>(mb * 2 * C);
+            const uint32_t ta = tx + C;
+            const bool zero_row = edge && (t < 0 || t >= p.L);
+            constexpr int GS = last ? 16 : COLS;
+#pragma unroll
+            for (int c0 = 0; c0 < COLS; c0 += GS) {
+              uint32_t v[GS];
+#pragma unroll
+              for (int gg = 0; gg < GS / 16; ++gg) tmem_ld16p(ta + c0 + gg * 16, &v[gg * 16]);
+              float f[GS];
+              if (resid) {
+                uint32_t xr[GS];
+#pragma unroll
+                for (int gg = 0; gg < GS / 16; ++gg) tmem_ld16p(tx + c0 + gg * 16, &xr[gg * 16]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < GS; ++j)
+                  f[j] = __uint_as_float(xr[j]) + leaky02(__uint_as_float(v[j]));
+              } else {
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < GS; ++j) f[j] = leaky02(__uint_as_float(v[j]));
+              }
+              if (zero_row) {
+#pragma unroll
+                for (int j = 0; j < GS; ++j) f[j] = 0.f;
+              }
+              if (!last) {
+                if (KIND != 1) {
+#pragma unroll
+                  for (int j = 0; j < GS; ++j) v[j] = __float_as_uint(f[j]);
+#pragma unroll
+                  for (int gg = 0; gg < GS / 16; ++gg) tmem_st16p(tx + c0 + gg * 16, &v[gg * 16]);
+                }
+#pragma unroll
+                for (int c = 0; c < GS / 8; ++c) {
+                  const uint32_t dst =
+                      dstbuf + static_cast<uint32_t>(((chunk0 + c0 / 8 + c) * R + srow) * 16);
+                  st_shared_v4(dst, pack2u<BF>(f[c * 8 + 0], f[c * 8 + 1]),
+                               pack2u<BF>(f[c * 8 + 2], f[c * 8 + 3]),
+                               pack2u<BF>(f[c * 8 + 4], f[c * 8 + 5]),
+                               pack2u<BF>(f[c * 8 + 6], f[c * 8 + 7]));
+                }
+              } else if (mono) {
+                // fused tail, step 1: 7 per-tap partial dot products of this thread's channels
+                float pk[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                  for (int j4 = 0; j4 < GS / 4; ++j4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(
+                        sMono + k * 32 + cpart * COLS + c0 + j4 * 4);
+                    a0 = fmaf(f[j4 * 4 + 0], w4.x, a0); a1 = fmaf(f[j4 * 4 + 1], w4.y, a1);
+                    a0 = fmaf(f[j4 * 4 + 2], w4.z, a0); a1 = fmaf(f[j4 * 4 + 3], w4.w, a1);
+                  }
+                  pk[k] = a0 + a1;
+                }
+                float* P = sP + (cpart * 7) * R + trow;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) P[k * R] = pk[k];
+              } else if (t >= 0 && t < p.L && trow >= p.halo && trow < p.halo + p.V) {
+#pragma unroll
+                for (int c = 0; c < GS / 8; ++c) {
+                  const size_t idx =
+                      (static_cast<size_t>(b) * G::NCH + chunk0 + c0 / 8 + c) * p.L + t;
+                  if (p.y16 != nullptr)
+                    *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
+                        make_uint4(pack2u<BF>(f[c * 8 + 0], f[c * 8 + 1]),
+                                   pack2u<BF>(f[c * 8 + 2], f[c * 8 + 3]),
+                                   pack2u<BF>(f[c * 8 + 4], f[c * 8 + 5]),
+                                   pack2u<BF>(f[c * 8 + 6], f[c * 8 + 7]));
+                  if (p.y32 != nullptr) {
+                    const float o8[8] = {f[c * 8 + 0], f[c * 8 + 1], f[c * 8 + 2], f[c * 8 + 3],
+                                         f[c * 8 + 4], f[c * 8 + 5], f[c * 8 + 6], f[c * 8 + 7]};
+                    st_global_v8(p.y32 + idx * 8, o8);
+                  }
+                }
+              }
+            }
+            // the accumulator has been read: seed it with the next stage's bias
+            store_bias(last ? 0 : s + 1, ta);
+          }
+          tmem_st_wait();
+          fence_proxy_async_smem();
+          tc_fence_before();
+          arrive_act(h);
+        }
+        ++g;
+      };
+      using K0 = std::integral_constant<int, 0>;
+      using K1 = std::integral_constant<int, 1>;
+      using K2 = std::integral_constant<int, 2>;
+      using K3 = std::integral_constant<int, 3>;
+      stage_epi(K0{}, 0);
+      stage_epi(K1{}, 1);
+      stage_epi(K2{}, 2);
+      stage_epi(K1{}, 3);
+      stage_epi(K2{}, 4);
+      stage_epi(K1{}, 5);
+      stage_epi(K3{}, 6);
+      if (mono) {
+        // fused tail, step 2: y[t] = tanh(b + sum_k sum_part P[part][k][row + k - 3])
+        named_bar_sync(1, 32 * EW);
+        const float bias0 = __ldg(p.mono_b);
+        const float* P = sP;
+        for (int row = p.halo + static_cast<int>(threadIdx.x) - 64; row < p.halo + p.V;
+             row += 32 * EW) {
+          const int t = t0 + row;
+          if (t < 0 || t >= p.L) continue;
+          float a0 = bias0, a1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            a0 += P[k * R + row + k - 3];
+            a1 += P[(7 + k) * R + row + k - 3];
+          }
+          p.mono_out[static_cast<size_t>(b) * p.L + t] = tanhf(a0 + a1);
+        }
+        // the next writer of P is the next tile's stage 6, six full hand-offs away
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(64 + 32 * UpGeom<C>::EW, 1)
+upstack_kernel(const __grid_constant__ UpStackParams p) {
+  upstack_body<C, false>(p);
+}
+
+template <int C>
+__global__ void __launch_bounds__(64 + 32 * UpGeom<C>::EW, 1)
+upstack_bf16_kernel(const __grid_constant__ UpStackParams p) {
+  upstack_body<C, true>(p);
+}
+
+template <int C>
+ms_status launch_upstack(const UpStackParams& p, int operand, cudaStream_t stream) {
+  using G = UpGeom<C>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(upstack_kernel<C>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(upstack_bf16_kernel<C>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(upstack_kernel)");
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (operand == MS_BF16)
+    upstack_bf16_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+  else
+    upstack_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+  return after_launch("upstack_kernel");
+}
+
+// out[e][chunk][n][j] for the 8 transposed-conv images e = (phase r, tap, K half):
+//   B[n = co][k = ci'] = Wt[kh*C + ci'][co][ktap],  ktap = (r ? 0 : 1) + 2*tap
+// (Wt: ConvTranspose1d weight (2C, C, 4), reference layout)
+__global__ void pack_up_weight_kernel(const float* __restrict__ wt, uint16_t* __restrict__ out,
+                                      int C, int operand) {
+  const int total = 8 * C * C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = i % 8;
+  const int n = (i / 8) % C;
+  const int c = (i / (8 * C)) % (C / 8);
+  const int e = i / (C * C);
+  const int r = e >> 2, tap = (e >> 1) & 1, kh = e & 1;
+  const int ktap = (r ? 0 : 1) + 2 * tap;
+  const int ci = kh * C + c * 8 + j;
+  const float v = wt[(static_cast<size_t>(ci) * C + n) * 4 + ktap];
+  if (operand == MS_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  } else {
+    __half h = __float2half_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+
+// [tap][chunk][C][8] <- w (C, C, 3) fp32 (same image as the fused stack's)
+__global__ void pack_up_tap_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int C,
+                                   int operand) {
+  const int total = 3 * C * C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = i % 8;
+  const int n = (i / 8) % C;
+  const int c = (i / (8 * C)) % (C / 8);
+  const int t = i / (C * C);
+  const float v = w[(static_cast<size_t>(n) * C + c * 8 + j) * 3 + t];
+  if (operand == MS_BF16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  } else {
+    __half h = __float2half_rn(v);
+    out[i] = *reinterpret_cast<uint16_t*>(&h);
+  }
+}
+
+}  // namespace
+
+ms_status upstack_fwd(int channels, int batch, int lin, const int* dil, int operand,
+                      const void* x16, const void* packed, void* y16, float* y32,
+                      const float* mono_w, const float* mono_b, float* mono_out,
+                      cudaStream_t stream) {
+  if (batch <= 0 || lin <= 0 || x16 == nullptr || packed == nullptr ||
+      (y16 == nullptr && y32 == nullptr && mono_out == nullptr))
+    return MS_ERR_INVALID;
+  if (channels != 64 && channels != 32) return MS_ERR_INVALID;
+  if (mono_out != nullptr && (channels != 32 || mono_w == nullptr || mono_b == nullptr))
+    return MS_ERR_INVALID;
+  for (int i = 0; i < 3; ++i)
+    if (dil[i] < 1 || dil[i] > 9 || (dil[i] & 1) == 0) return MS_ERR_INVALID;   // odd only
+  if (dil[0] + dil[1] + dil[2] + 3 > kUpHalo) return MS_ERR_INVALID;
+  UpStackParams p;
+  p.x16 = static_cast<const uint16_t*>(x16);
+  p.w = static_cast<const uint16_t*>(packed);
+  p.bias = reinterpret_cast<const float*>(static_cast<const uint8_t*>(packed) +
+                                          static_cast<size_t>(kUpEntries) * channels * channels * 2);
+  p.y16 = static_cast<uint16_t*>(y16);
+  p.y32 = y32;
+  p.B = batch; p.lin = lin; p.L = 2 * lin;
+  p.dil[0] = dil[0]; p.dil[1] = dil[1]; p.dil[2] = dil[2];
+  p.mono_w = mono_w; p.mono_b = mono_b; p.mono_out = mono_out;
+  // rows lost per tile: the halo on both sides, the 3 rows the low-rate window cannot feed
+  // (rounded to keep V even) and, with the fused k7 tail, its reach of 3 on both sides
+  const int halo = mono_out != nullptr ? kUpHalo + 4 : kUpHalo;
+  const int R = channels == 64 ? UpGeom<64>::R : UpGeom<32>::R;
+  p.halo = halo;
+  p.V = R - 2 * halo - (mono_out != nullptr ? 2 : 4);
+  p.tiles_per_clip = (p.L + p.V - 1) / p.V;
+  const long long tiles = static_cast<long long>(batch) * p.tiles_per_clip;
+  if (tiles > 0x7fffffffLL) return MS_ERR_INVALID;
+  p.total_tiles = static_cast<int>(tiles);
+  return channels == 64 ? launch_upstack<64>(p, operand, stream)
+                        : launch_upstack<32>(p, operand, stream);
+}
+
+}  // namespace msb
+
+using namespace msb;
+
+extern "C" {
+
+int ms_upstack_supported(int channels) { return channels == 64 || channels == 32; }
+
+size_t ms_upstack_packed_weight_bytes(int channels) {
+  if (!ms_upstack_supported(channels)) return 0;
+  return static_cast<size_t>(kUpEntries) * channels * channels * 2 +
+         sizeof(float) * kUpStages * channels;
+}
+
+ms_status ms_upstack_pack_weights(const float* const* params, int channels, int operand,
+                                  void* packed, void* stream) {
+  if (params == nullptr || packed == nullptr || !ms_upstack_supported(channels))
+    return MS_ERR_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  const size_t image = static_cast<size_t>(channels) * channels * 2;
+  float* bias = reinterpret_cast<float*>(base + kUpEntries * image);
+  pack_up_weight_kernel<<<(8 * channels * channels + 255) / 256, 256, 0, st>>>(
+      params[0], reinterpret_cast<uint16_t*>(base), channels, operand);
+  ms_status s = after_launch("pack_up_weight_kernel");
+  if (s != MS_OK) return s;
+  s = check_cuda(cudaMemcpyAsync(bias, params[1], sizeof(float) * channels,
+                                 cudaMemcpyDeviceToDevice, st),
+                 "cudaMemcpyAsync(upstack bias)");
+  if (s != MS_OK) return s;
+  for (int l = 0; l < 6; ++l) {
+    pack_up_tap_kernel<<<(3 * channels * channels + 255) / 256, 256, 0, st>>>(
+        params[2 + 2 * l], reinterpret_cast<uint16_t*>(base + (8 + 3 * l) * image), channels,
+        operand);
+    s = after_launch("pack_up_tap_kernel");
+    if (s != MS_OK) return s;
+    s = check_cuda(cudaMemcpyAsync(bias + (l + 1) * channels, params[3 + 2 * l],
+                                   sizeof(float) * channels, cudaMemcpyDeviceToDevice, st),
+                   "cudaMemcpyAsync(upstack bias)");
+    if (s != MS_OK) return s;
+  }
+  return MS_OK;
+}
+
+ms_status ms_upstack_fwd(int channels, int batch, int lin, const int* dilations, int operand,
+                         const void* x16, const void* packed, void* y16, float* y32,
+                         const float* tail_w, const float* tail_b, float* tail_y, void* stream) {
+  if (dilations == nullptr || !ms_upstack_supported(channels)) return MS_ERR_INVALID;
+  return upstack_fwd(channels, batch, lin, dilations, operand, x16, packed, y16, y32, tail_w,
+                     tail_b, tail_y, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

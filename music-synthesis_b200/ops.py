@@ -306,6 +306,42 @@ def resstack_fwd(x32, blob, dilations, operand=MS_F16, want16=False, want32=True
     return y16, y32
 
 
+def upstack_pack_weights(params, channels, operand=MS_F16):
+    """14 tensors (ConvTranspose1d w, b, then the stack's 12) -> packed blob of the fused stage."""
+    L = _lib.lib()
+    n = L.ms_upstack_packed_weight_bytes(channels)
+    if n == 0 or len(params) != 14:
+        raise _lib.MsbError("fused upsampling stage: unsupported configuration")
+    keep = [p.detach().contiguous() for p in params]
+    for p in keep:
+        _lib.require_cuda(p, "parameter")
+    arr = (ctypes.c_void_p * 14)(*[p.data_ptr() for p in keep])
+    blob = torch.empty(n, dtype=torch.uint8, device=keep[0].device)
+    check(L.ms_upstack_pack_weights(arr, channels, operand, ptr(blob), stream_ptr()),
+          "ms_upstack_pack_weights")
+    return blob
+
+
+def upstack_fwd(x16, blob, dilations, operand=MS_F16, want16=True, want32=False, tail=None):
+    """ConvTranspose1d(2C->C, 4, 2, 1) + LeakyReLU + ResidualStack(C) on a BLK 16-bit tensor
+    (B,2C/8,lin,8).  Returns (y16, y32), or the (B,1,2*lin) waveform when tail=(w, b) (C = 32)."""
+    B, C8in, lin, _ = x16.shape
+    C8 = C8in // 2
+    dil = (ctypes.c_int * 3)(*dilations)
+    if tail is not None:
+        tw, tb = tail
+        y = torch.empty((B, 1, 2 * lin), dtype=torch.float32, device=x16.device)
+        check(_lib.lib().ms_upstack_fwd(C8 * 8, B, lin, dil, operand, ptr(x16), ptr(blob), None,
+                                        None, ptr(tw), ptr(tb), ptr(y), stream_ptr()),
+              "ms_upstack_fwd")
+        return y
+    y16 = torch.empty((B, C8, 2 * lin, 8), dtype=torch.int16, device=x16.device) if want16 else None
+    y32 = torch.empty((B, C8, 2 * lin, 8), dtype=torch.float32, device=x16.device) if want32 else None
+    check(_lib.lib().ms_upstack_fwd(C8 * 8, B, lin, dil, operand, ptr(x16), ptr(blob), ptr(y16),
+                                    ptr(y32), None, None, None, stream_ptr()), "ms_upstack_fwd")
+    return y16, y32
+
+
 class MelGanWeights:
     """Packed parameter blob of a MelGanGenerator (60 state-dict tensors, in order)."""
 
