@@ -45,6 +45,8 @@ constexpr int kUpHalo = 16;
 constexpr int kUpHeader = 1024;
 constexpr int kUpStages = 7;            // transposed conv + six convs
 constexpr int kUpEntries = 8 + 18;      // weight images per tile (C x C 16-bit each)
+constexpr int kUpFills = 3 + 6;         // weight-slot fills per tile (3 images each; one of 2)
+constexpr int kIssuerB = 18;            // warp index of the second MMA issuer
 
 struct UpStackParams {
   const uint16_t* x16;   // BLK 16-bit (B, 2C/8, lin, 8): previous stage's operand image
@@ -59,7 +61,23 @@ struct UpStackParams {
   const float* mono_w;   // fused tail (C == 32): (1, 32, 7) fp32
   const float* mono_b;
   float* mono_out;       // (B, 1, L) fp32
+  long long* dbg;        // MSB_UP_ABLATE builds only: clock trace buffer (256 x int64) or null
+  int ablate;            // MSB_UP_ABLATE builds only (tools/upstack_bench.py): bit 0 no MMAs,
+                         // 1 empty epilogue, 2 no operand stores, 3 no tensor-memory traffic
 };
+
+#ifdef MSB_UP_ABLATE
+#define MSB_ABL(bit) ((p.ablate & (bit)) != 0)
+// clock64 trace of CTA 0's third tile (tools/upstack_trace.py)
+#define MSB_UTRACE(slot)                                                              \
+  do {                                                                                \
+    if (p.dbg != nullptr && blockIdx.x == 0 && it == 2 && (threadIdx.x & 31) == 0)    \
+      p.dbg[(slot)] = clock64();                                                      \
+  } while (0)
+#else
+#define MSB_ABL(bit) false
+#define MSB_UTRACE(slot) do { } while (0)
+#endif
 
 template <int C>
 struct UpGeom {
@@ -75,10 +93,12 @@ struct UpGeom {
   static constexpr int NCH = C / 8;
   static constexpr int ACT_BYTES = R * C * 2; // 65536
   static constexpr int TAP_BYTES = C * C * 2;
-  static constexpr int NSLOT = (96 * 1024 / TAP_BYTES) < 18 ? (96 * 1024 / TAP_BYTES) : 18;
+  static constexpr int SLOT_BYTES = 3 * TAP_BYTES;   // a weight slot = the three taps of a conv
+  static constexpr int NSLOT = 4;                    // 96 KB at C = 64, 24 KB at C = 32
   static constexpr int MONO_BYTES = 1024;
   static constexpr int P_BYTES = (C == 32) ? 14 * R * 4 : 0;
-  static constexpr int SMEM = kUpHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES + P_BYTES;
+  static constexpr int SMEM = kUpHeader + 2 * ACT_BYTES + NSLOT * SLOT_BYTES + MONO_BYTES + P_BYTES;
+  static constexpr int THREADS = 64 + 32 * EW + 32;  // producer, issuer A, epilogue, issuer B
   static_assert(HB >= 2 && HB % 2 == 0, "a part needs E and O blocks");
 };
 
@@ -96,15 +116,16 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
   constexpr int kOp = BF ? MS_BF16 : MS_F16;
   using G = UpGeom<C>;
   constexpr int HB = G::HB, HE = G::HE, R = G::R, RH = G::RH, EW = G::EW, NP = G::NP;
-  constexpr int NSLOT = G::NSLOT, TAPB = G::TAP_BYTES;
+  constexpr int NSLOT = G::NSLOT, TAPB = G::TAP_BYTES, SLOTB = G::SLOT_BYTES;
+  static_assert(NP == 2, "one MMA issuer warp per part");
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  // [0,18) wfull  [18,36) wempty  [36,38) acc_full  [38,40) act_ready  40 in_full  41 in_free
+  // [0,4) wfull  [18,22) wempty  [36,38) acc_full  [38,40) act_ready  40 in_full  41 in_free
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 640);
   const uint32_t bar_base = smem_u32(bars);
   const uint32_t sBuf0 = smem_u32(smem + kUpHeader);
   const uint32_t sW = sBuf0 + 2 * G::ACT_BYTES;
-  float* sMono = reinterpret_cast<float*>(smem + kUpHeader + 2 * G::ACT_BYTES + NSLOT * TAPB);
+  float* sMono = reinterpret_cast<float*>(smem + kUpHeader + 2 * G::ACT_BYTES + NSLOT * SLOTB);
   float* sP = sMono + G::MONO_BYTES / 4;
   const bool mono = (C == 32) && (p.mono_out != nullptr);
   auto wfull = [&](int s) { return bar_base + 8u * s; };
@@ -119,16 +140,16 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 18; ++s) {
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(wfull(s), 1);
-      mbar_init(wempty(s), 1);
+      mbar_init(wempty(s), 2);     // released by both MMA issuers
     }
     for (int m = 0; m < NP; ++m) {
       mbar_init(acc_full(m), 1);
       mbar_init(act_ready(m), EW);
     }
     mbar_init(in_full, 1);
-    mbar_init(in_free, 1);
+    mbar_init(in_free, 2);         // both MMA issuers' stage-5 MMAs
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -147,9 +168,9 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
   const int tile_stride = static_cast<int>(gridDim.x);
 
   if (warp == 0) {
-    // ================= producer: low-rate input window + weight images =================
+    // ================= producer: low-rate input window + weight slots =================
     constexpr int CH2 = 2 * C / 8;    // 16-byte channel chunks of the input
-    uint32_t pos = 0;
+    uint32_t pos = 0;                 // weight slots filled so far
     int it = 0;
     for (int tile = tile_first; tile < p.total_tiles; tile += tile_stride, ++it) {
       const int b = tile / p.tiles_per_clip;
@@ -160,7 +181,9 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
       const int nrows = hi > lo ? hi - lo : 0;
       const uint32_t dstb = buf(it);
       // the buffer was last read by stage 5 of this CTA's previous tile
+      MSB_UTRACE(240);
       mbar_wait(in_free, static_cast<uint32_t>(it & 1) ^ 1u);
+      MSB_UTRACE(241);
       if (nrows != RH) {
         // rows outside [0, lin): the transposed conv sees zeros there
         const int head = lo - q0;
@@ -185,115 +208,146 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
                  static_cast<uint32_t>(nrows) * 16u, in_full);
       }
       __syncwarp();
-      for (int e = 0; e < kUpEntries; ++e, ++pos) {
-        const int slot = pos % NSLOT;
+      // nine slot fills per tile: images 0-2, 3-5, 6-7 (transposed conv), then one conv each
+      for (int f = 0; f < kUpFills; ++f, ++pos) {
+        const int slot = pos & (NSLOT - 1);
         const uint32_t par = (pos / NSLOT) & 1u;
+        const uint32_t bytes = (f == 2 ? 2u : 3u) * TAPB;
+        const int first = f < 3 ? 3 * f : 8 + 3 * (f - 3);         // first image of the fill
         mbar_wait(wempty(slot), par ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(wfull(slot), TAPB);
-          bulk_g2s(sW + slot * TAPB,
-                   reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(e) * TAPB, TAPB,
-                   wfull(slot));
+          mbar_arrive_expect_tx(wfull(slot), bytes);
+          bulk_g2s(sW + slot * SLOTB,
+                   reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(first) * TAPB,
+                   bytes, wfull(slot));
         }
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ================================
+  } else if (warp == 1 || warp == kIssuerB) {
+    // ============================ MMA issuers (two) ============================
+    // One warp per pipeline part: the issue path is a single thread's instruction stream
+    // (descriptor arithmetic + tcgen05.mma), and with N = C <= 64 an MMA retires in 42-48
+    // cycles -- one issuer cannot keep the tensor pipe fed while sharing its scheduler with
+    // four epilogue warps (measured: the lone issuer was busy 100 % of the time, 85 cycles per
+    // MMA).  Each accumulator block is written by exactly one issuer; tcgen05.commit tracks
+    // the issuing thread's own MMAs, so weight slots and the input window are released by
+    // both (barrier count 2).
+    const int part = (warp == 1) ? 0 : 1;
     const uint32_t idesc = umma_idesc_f16(C, kOp);
     const uint64_t adesc_up = umma_desc_base_nosw(RH * 16, 128);   // input window [2C/8][RH][8]
     const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);      // activations [C/8][R][8]
     const uint64_t bdesc0 = umma_desc_base_nosw(C * 16, 128);
-    uint32_t pos = 0;     // ring position of the current stage's first weight image
+    uint32_t pos = 0;     // weight slot of the current stage
     uint32_t g = 0;       // stages issued so far (parity of the act_ready waits)
     int it = 0;
-    auto wait_w = [&](uint32_t q) { mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u); };
-    auto commit = [&](uint32_t bar) {
-      if (elect_one()) umma_commit(bar);
-      __syncwarp();
+    auto wait_w = [&](uint32_t q) { mbar_wait(wfull(q & (NSLOT - 1)), (q / NSLOT) & 1u); };
+    auto slot_addr = [&](uint32_t q) { return (sW + (q & (NSLOT - 1)) * SLOTB) >> 4; };
+    // tap image `img` of weight slot `wq` on block (r, kk) of part `pt`, A rows from `arow`
+    auto mma_block = [&](uint64_t ad, uint32_t wq16, int img, int mb, int kstepA) {
+      const uint64_t bd = bdesc0 + (wq16 + static_cast<uint32_t>(img * (TAPB >> 4)));
+      const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
+#pragma unroll
+      for (int k16 = 0; k16 < C / 16; ++k16)
+        umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * kstepA),
+                    bd + static_cast<uint64_t>(k16 * 2 * C), idesc, 1u);
     };
     for (int tile = tile_first; tile < p.total_tiles; tile += tile_stride, ++it) {
       const uint32_t inb = buf(it), oth = buf(it + 1);
-      // ---------------- stage 0: transposed conv, phase r = e >> 2 ----------------
+      // ---------------- stage 0: transposed conv (image e: phase e >> 2, tap, K half) --------
+      MSB_UTRACE(243 + 2 * part);
       mbar_wait(in_full, static_cast<uint32_t>(it & 1));
-      for (int part = 0; part < NP; ++part) {
-        mbar_wait(act_ready(part), g & 1u);
-        tc_fence_after();
-        for (int e = 0; e < 8; ++e) {
-          if (part == 0) wait_w(pos + e);
-          const int r = e >> 2, tapsel = (e >> 1) & 1, kh = e & 1;
-          const int shift = (r ? 2 : 1) - tapsel;
-          const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(((pos + e) % NSLOT) * TAPB)) >> 4);
-          if (elect_one()) {
+      MSB_UTRACE(244 + 2 * part);
+      MSB_UTRACE(part * 4 + 0);
+      mbar_wait(act_ready(part), g & 1u);
+      wait_w(pos);
+      wait_w(pos + 1);
+      wait_w(pos + 2);
+      tc_fence_after();
+      MSB_UTRACE(part * 4 + 1);
+      if (elect_one()) {
+        if (!MSB_ABL(1)) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int r = e >> 2, tapsel = (e >> 1) & 1, kh = e & 1;
+            const int shift = (r ? 2 : 1) - tapsel;
+            const uint32_t wq16 = slot_addr(pos + e / 3);
 #pragma unroll
             for (int kk = 0; kk < HE; ++kk) {
               const int mb = part * HB + r * HE + kk;
               const int k = part * HE + kk;
               const uint64_t ad =
-                  adesc_up +
-                  ((inb + static_cast<uint32_t>((kh * (C / 8) * RH + k * 128 + shift) * 16)) >> 4);
-              const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
-#pragma unroll
-              for (int k16 = 0; k16 < C / 16; ++k16)
-                umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * 2 * RH),
-                            bd + static_cast<uint64_t>(k16 * 2 * C), idesc, 1u);
+                  adesc_up + ((inb >> 4) + static_cast<uint32_t>(kh * (C / 8) * RH + k * 128 + shift));
+              mma_block(ad, wq16, e % 3, mb, 2 * RH);
             }
           }
-          __syncwarp();
-          if (part == NP - 1) commit(wempty((pos + e) % NSLOT));
         }
-        commit(acc_full(part));
+        umma_commit(wempty(pos & (NSLOT - 1)));
+        umma_commit(wempty((pos + 1) & (NSLOT - 1)));
+        umma_commit(wempty((pos + 2) & (NSLOT - 1)));
+        umma_commit(acc_full(part));
       }
-      pos += 8;
+      __syncwarp();
+      MSB_UTRACE(part * 4 + 2);
+      pos += 3;
       ++g;
       // ---------------- stages 1..6: the six k3 convs ----------------
-      for (int l = 0; l < 6; ++l, pos += 3, ++g) {
+      for (int l = 0; l < 6; ++l, ++pos, ++g) {
         const int d = (l & 1) ? 1 : p.dil[l >> 1];
-        const uint32_t src = (l & 1) ? inb : oth;
-        // tap t on blocks [kk0, kk1) of both phases of `part`
-        auto issue = [&](int t, int part, int kk0, int kk1) {
-          const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(((pos + t) % NSLOT) * TAPB)) >> 4);
-          // source row of output row m0 of an E / O block (see the header comment)
-          const int offE = t == 1 ? 0 : (t == 0 ? RH - (d + 1) / 2 : RH + (d - 1) / 2);
-          const int offO = t == 1 ? RH : (t == 0 ? -(d - 1) / 2 : (d + 1) / 2);
-          if (elect_one()) {
+        const uint32_t src16 = ((l & 1) ? inb : oth) >> 4;
+        // source row (relative to the block's first row) of tap t for E / O blocks
+        const int offE[3] = {RH - (d + 1) / 2, 0, RH + (d - 1) / 2};
+        const int offO[3] = {-(d - 1) / 2, RH, (d + 1) / 2};
+        MSB_UTRACE((l + 1) * 16 + part * 4 + 0);
+        mbar_wait(act_ready(part), g & 1u);
+        wait_w(pos);
+        tc_fence_after();
+        MSB_UTRACE((l + 1) * 16 + part * 4 + 1);
+        const uint32_t wq16 = slot_addr(pos);
+        // taps on blocks [kk0, kk1) of both phases of this warp's part
+        auto issue = [&](int t0_, int t1_, int kk0, int kk1) {
+#pragma unroll
+          for (int t = t0_; t < t1_; ++t) {
+#pragma unroll
             for (int r = 0; r < 2; ++r) {
+#pragma unroll
               for (int kk = kk0; kk < kk1; ++kk) {
                 const int mb = part * HB + r * HE + kk;
-                const int row = (part * HE + kk) * 128 + (r ? offO : offE);
-                const uint64_t ad = adesc0 + ((src + static_cast<uint32_t>(row * 16)) >> 4);
-                const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
-#pragma unroll
-                for (int k16 = 0; k16 < C / 16; ++k16)
-                  umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * 2 * R),
-                              bd + static_cast<uint64_t>(k16 * 2 * C), idesc, 1u);
+                const int row = (part * HE + kk) * 128 + (r ? offO[t] : offE[t]);
+                mma_block(adesc0 + (src16 + static_cast<uint32_t>(row)), wq16, t, mb, 2 * R);
               }
             }
           }
-          __syncwarp();
         };
-        for (int part = 0; part < NP; ++part) {
-          mbar_wait(act_ready(part), g & 1u);
-          tc_fence_after();
-          if (part > 0) {
-            // tap +d of the previous part's last E and O blocks reads into this part
-            issue(2, part - 1, HE - 1, HE);
-            commit(acc_full(part - 1));
-          } else {
-            wait_w(pos + 0);
+        if (part == NP - 1) {
+          if (elect_one()) {
+            if (!MSB_ABL(1)) issue(0, 3, 0, HE);
+            umma_commit(wempty(pos & (NSLOT - 1)));
+            umma_commit(acc_full(part));
+            // stage 5 was the last reader of `oth`: the next tile's input window may land there
+            if (l == 4) umma_commit(in_free);
           }
-          issue(0, part, 0, HE);
-          if (part == NP - 1) commit(wempty((pos + 0) % NSLOT));
-          if (part == 0) wait_w(pos + 1);
-          issue(1, part, 0, HE);
-          if (part == NP - 1) commit(wempty((pos + 1) % NSLOT));
-          if (part == 0) wait_w(pos + 2);
-          issue(2, part, 0, part == NP - 1 ? HE : HE - 1);
+          __syncwarp();
+        } else {
+          // everything except tap +d of the part's last E and O blocks, which reads into the
+          // next part: those two wait for the next part's operand rows
+          if (elect_one() && !MSB_ABL(1)) {
+            issue(0, 2, 0, HE);
+            if (HE > 1) issue(2, 3, 0, HE - 1);
+          }
+          __syncwarp();
+          MSB_UTRACE((l + 1) * 16 + part * 4 + 2);
+          mbar_wait(act_ready(part + 1), g & 1u);
+          tc_fence_after();
+          if (elect_one()) {
+            if (!MSB_ABL(1)) issue(2, 3, HE - 1, HE);
+            umma_commit(wempty(pos & (NSLOT - 1)));
+            umma_commit(acc_full(part));
+            if (l == 4) umma_commit(in_free);
+          }
+          __syncwarp();
         }
-        commit(wempty((pos + 2) % NSLOT));
-        commit(acc_full(NP - 1));
-        // stage 5 was the last reader of `oth`: the next tile's input window may land there
-        if (l == 4) commit(in_free);
+        MSB_UTRACE((l + 1) * 16 + part * 4 + 3);
       }
     }
   } else {
@@ -363,10 +417,13 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
         constexpr bool last = KIND == 3;
         const uint32_t dstbuf = (KIND == 1) ? inb : oth;
         for (int h = 0; h < NP; ++h) {
+          if (warp == 2) MSB_UTRACE(128 + s * 16 + h * 4 + 0);
           mbar_wait(acc_full(h), g & 1u);
           tc_fence_after();
+          if (warp == 2) MSB_UTRACE(128 + s * 16 + h * 4 + 1);
 #pragma unroll
           for (int u = 0; u < IT; ++u) {
+            if (MSB_ABL(2)) continue;
             int mb, srow, trow;
             geom(h, u, mb, srow, trow);
             const int t = t0 + trow;
@@ -377,13 +434,23 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
 #pragma unroll
             for (int c0 = 0; c0 < COLS; c0 += GS) {
               uint32_t v[GS];
+              if (MSB_ABL(8)) {
 #pragma unroll
-              for (int gg = 0; gg < GS / 16; ++gg) tmem_ld16p(ta + c0 + gg * 16, &v[gg * 16]);
+                for (int j = 0; j < GS; ++j) v[j] = static_cast<uint32_t>(t + j);
+              } else {
+#pragma unroll
+                for (int gg = 0; gg < GS / 16; ++gg) tmem_ld16p(ta + c0 + gg * 16, &v[gg * 16]);
+              }
               float f[GS];
               if (resid) {
                 uint32_t xr[GS];
+                if (MSB_ABL(8)) {
 #pragma unroll
-                for (int gg = 0; gg < GS / 16; ++gg) tmem_ld16p(tx + c0 + gg * 16, &xr[gg * 16]);
+                  for (int j = 0; j < GS; ++j) xr[j] = static_cast<uint32_t>(t - j);
+                } else {
+#pragma unroll
+                  for (int gg = 0; gg < GS / 16; ++gg) tmem_ld16p(tx + c0 + gg * 16, &xr[gg * 16]);
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < GS; ++j)
@@ -398,7 +465,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
                 for (int j = 0; j < GS; ++j) f[j] = 0.f;
               }
               if (!last) {
-                if (KIND != 1) {
+                if (KIND != 1 && !MSB_ABL(8)) {
 #pragma unroll
                   for (int j = 0; j < GS; ++j) v[j] = __float_as_uint(f[j]);
 #pragma unroll
@@ -406,6 +473,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
                 }
 #pragma unroll
                 for (int c = 0; c < GS / 8; ++c) {
+                  if (MSB_ABL(4)) continue;
                   const uint32_t dst =
                       dstbuf + static_cast<uint32_t>(((chunk0 + c0 / 8 + c) * R + srow) * 16);
                   st_shared_v4(dst, pack2u<BF>(f[c * 8 + 0], f[c * 8 + 1]),
@@ -451,12 +519,13 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
               }
             }
             // the accumulator has been read: seed it with the next stage's bias
-            store_bias(last ? 0 : s + 1, ta);
+            if (!MSB_ABL(8)) store_bias(last ? 0 : s + 1, ta);
           }
           tmem_st_wait();
           fence_proxy_async_smem();
           tc_fence_before();
           arrive_act(h);
+          if (warp == 2) MSB_UTRACE(128 + s * 16 + h * 4 + 2);
         }
         ++g;
       };
@@ -502,13 +571,13 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(64 + 32 * UpGeom<C>::EW, 1)
+__global__ void __launch_bounds__(UpGeom<C>::THREADS, 1)
 upstack_kernel(const __grid_constant__ UpStackParams p) {
   upstack_body<C, false>(p);
 }
 
 template <int C>
-__global__ void __launch_bounds__(64 + 32 * UpGeom<C>::EW, 1)
+__global__ void __launch_bounds__(UpGeom<C>::THREADS, 1)
 upstack_bf16_kernel(const __grid_constant__ UpStackParams p) {
   upstack_body<C, true>(p);
 }
@@ -530,9 +599,9 @@ ms_status launch_upstack(const UpStackParams& p, int operand, cudaStream_t strea
   if (sms <= 0) return check_cuda(cudaGetLastError(), "sm_count");
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (operand == MS_BF16)
-    upstack_bf16_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+    upstack_bf16_kernel<C><<<grid, G::THREADS, G::SMEM, stream>>>(p);
   else
-    upstack_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+    upstack_kernel<C><<<grid, G::THREADS, G::SMEM, stream>>>(p);
   return after_launch("upstack_kernel");
 }
 
@@ -583,6 +652,8 @@ __global__ void pack_up_tap_kernel(const float* __restrict__ w, uint16_t* __rest
 
 }  // namespace
 
+static thread_local long long* g_up_dbg = nullptr;
+
 ms_status upstack_fwd(int channels, int batch, int lin, const int* dil, int operand,
                       const void* x16, const void* packed, void* y16, float* y32,
                       const float* mono_w, const float* mono_b, float* mono_out,
@@ -606,6 +677,12 @@ ms_status upstack_fwd(int channels, int batch, int lin, const int* dil, int oper
   p.B = batch; p.lin = lin; p.L = 2 * lin;
   p.dil[0] = dil[0]; p.dil[1] = dil[1]; p.dil[2] = dil[2];
   p.mono_w = mono_w; p.mono_b = mono_b; p.mono_out = mono_out;
+  p.ablate = 0;
+  p.dbg = nullptr;
+#ifdef MSB_UP_ABLATE
+  if (const char* e = getenv("MSB_UP_ABLATE")) p.ablate = atoi(e);
+  p.dbg = g_up_dbg;
+#endif
   // rows lost per tile: the halo on both sides, the 3 rows the low-rate window cannot feed
   // (rounded to keep V even) and, with the fused k7 tail, its reach of 3 on both sides
   const int halo = mono_out != nullptr ? kUpHalo + 4 : kUpHalo;
@@ -625,6 +702,9 @@ ms_status upstack_fwd(int channels, int batch, int lin, const int* dil, int oper
 using namespace msb;
 
 extern "C" {
+
+/* debugging aid (not in the public header; effective in MSB_UP_ABLATE builds only) */
+void ms_debug_set_upstack_trace(long long* dev_buf) { msb::g_up_dbg = dev_buf; }
 
 int ms_upstack_supported(int channels) { return channels == 64 || channels == 32; }
 
