@@ -142,14 +142,14 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(wfull(s), 1);
-      mbar_init(wempty(s), 2);     // released by both MMA issuers
+      mbar_init(wempty(s), 1);     // released by epilogue warp 2 (it has seen both acc_full)
     }
     for (int m = 0; m < NP; ++m) {
       mbar_init(acc_full(m), 1);
       mbar_init(act_ready(m), EW);
     }
     mbar_init(in_full, 1);
-    mbar_init(in_free, 2);         // both MMA issuers' stage-5 MMAs
+    mbar_init(in_free, 1);         // epilogue warp 2, once stage 5's MMAs have completed
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -282,9 +282,6 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
             }
           }
         }
-        umma_commit(wempty(pos & (NSLOT - 1)));
-        umma_commit(wempty((pos + 1) & (NSLOT - 1)));
-        umma_commit(wempty((pos + 2) & (NSLOT - 1)));
         umma_commit(acc_full(part));
       }
       __syncwarp();
@@ -304,16 +301,16 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
         tc_fence_after();
         MSB_UTRACE((l + 1) * 16 + part * 4 + 1);
         const uint32_t wq16 = slot_addr(pos);
-        // taps on blocks [kk0, kk1) of both phases of this warp's part
-        auto issue = [&](int t0_, int t1_, int kk0, int kk1) {
+        // taps [t0_, t1_) on blocks [kk0, kk1) of both phases of part pt
+        auto issue_part = [&](int pt, int t0_, int t1_, int kk0, int kk1) {
 #pragma unroll
           for (int t = t0_; t < t1_; ++t) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
 #pragma unroll
               for (int kk = kk0; kk < kk1; ++kk) {
-                const int mb = part * HB + r * HE + kk;
-                const int row = (part * HE + kk) * 128 + (r ? offO[t] : offE[t]);
+                const int mb = pt * HB + r * HE + kk;
+                const int row = (pt * HE + kk) * 128 + (r ? offO[t] : offE[t]);
                 mma_block(adesc0 + (src16 + static_cast<uint32_t>(row)), wq16, t, mb, 2 * R);
               }
             }
@@ -321,29 +318,25 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
         };
         if (part == NP - 1) {
           if (elect_one()) {
-            if (!MSB_ABL(1)) issue(0, 3, 0, HE);
-            umma_commit(wempty(pos & (NSLOT - 1)));
-            umma_commit(acc_full(part));
-            // stage 5 was the last reader of `oth`: the next tile's input window may land there
-            if (l == 4) umma_commit(in_free);
+            if (!MSB_ABL(1)) issue_part(1, 0, 3, 0, HE);
+            umma_commit(acc_full(1));
           }
           __syncwarp();
         } else {
           // everything except tap +d of the part's last E and O blocks, which reads into the
-          // next part: those two wait for the next part's operand rows
+          // next part: those two wait for the next part's operand rows.  (They stay with this
+          // issuer: one thread per accumulator keeps the fp32 summation order fixed.)
           if (elect_one() && !MSB_ABL(1)) {
-            issue(0, 2, 0, HE);
-            if (HE > 1) issue(2, 3, 0, HE - 1);
+            issue_part(0, 0, 2, 0, HE);
+            if (HE > 1) issue_part(0, 2, 3, 0, HE - 1);
           }
           __syncwarp();
           MSB_UTRACE((l + 1) * 16 + part * 4 + 2);
-          mbar_wait(act_ready(part + 1), g & 1u);
+          mbar_wait(act_ready(1), g & 1u);
           tc_fence_after();
           if (elect_one()) {
-            if (!MSB_ABL(1)) issue(2, 3, HE - 1, HE);
-            umma_commit(wempty(pos & (NSLOT - 1)));
-            umma_commit(acc_full(part));
-            if (l == 4) umma_commit(in_free);
+            if (!MSB_ABL(1)) issue_part(0, 2, 3, HE - 1, HE);
+            umma_commit(acc_full(0));
           }
           __syncwarp();
         }
@@ -364,6 +357,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
     const int row0 = q * 32 + lane;
     const uint32_t tm0 = tmem_base + lane_off + static_cast<uint32_t>(cpart * COLS);
     uint32_t g = 0;
+    uint32_t wpos = 0;      // weight slots released so far (warp 2 only)
     auto arrive_act = [&](int h) {
       __syncwarp();
       if (lane == 0) mbar_arrive(act_ready(h));
@@ -421,6 +415,19 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
           mbar_wait(acc_full(h), g & 1u);
           tc_fence_after();
           if (warp == 2) MSB_UTRACE(128 + s * 16 + h * 4 + 1);
+          if (warp == 2 && h == NP - 1) {
+            // every MMA of this stage has completed: its weight slot(s) may be refilled, and
+            // after stage 5 the buffer `oth` may take the next tile's input window
+            if (lane == 0) {
+              mbar_arrive(wempty(wpos & (NSLOT - 1)));
+              if (KIND == 0) {
+                mbar_arrive(wempty((wpos + 1) & (NSLOT - 1)));
+                mbar_arrive(wempty((wpos + 2) & (NSLOT - 1)));
+              }
+              if (s == 5) mbar_arrive(in_free);
+            }
+            wpos += (KIND == 0) ? 3 : 1;
+          }
 #pragma unroll
           for (int u = 0; u < IT; ++u) {
             if (MSB_ABL(2)) continue;
