@@ -40,6 +40,11 @@ def build_library(force=False, verbose=False):
     headers.append(os.path.join(os.path.dirname(CSRC), "..", "include", "msb200.h"))
     nvcc = _nvcc()
     objs, jobs = [], []
+    # a change of flags (MSB_NVCC_EXTRA debug builds) must not leave stale objects behind
+    flags = " ".join(NVCC_FLAGS + _extra_flags())
+    stamp = os.path.join(CSRC, ".build_flags")
+    if not os.path.exists(stamp) or open(stamp).read() != flags:
+        force = True
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = s[:-3] + ".o"
@@ -58,6 +63,8 @@ def build_library(force=False, verbose=False):
         list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs)
+    with open(stamp, "w") as f:
+        f.write(flags)
     return LIB
 
 

@@ -90,7 +90,12 @@ struct StackGeom {
   // registers per row: fits the 96-register budget of 18-warp CTAs only at 16 columns per thread)
   static constexpr bool MERGE_PROLOGUE = (C == 32);
   static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES + P_BYTES;
+  // producer, MMA issuer A, epilogue warps, MMA issuer B (single-CTA kernels only)
+  static constexpr int THREADS = 64 + 32 * EW + 32;
+  static constexpr int THREADS_PAIR = 64 + 32 * EW;
 };
+
+constexpr int kStackIssuerB = 18;   // warp index of the second MMA issuer
 
 __device__ __forceinline__ uint32_t pack2s(float a, float b, int operand) {
   if (operand == MS_BF16) {
@@ -144,7 +149,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < 18; ++s) {
       mbar_init(wfull(s), 1);
-      mbar_init(wempty(s), 1);
+      mbar_init(wempty(s), PAIR ? 1 : 2);   // single-CTA kernels: released by both MMA issuers
       mbar_init(pwfull(s), 1);
     }
     for (int m = 0; m < 8; ++m) {
@@ -192,7 +197,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         __syncwarp();
       }
     }
-  } else if (warp == 1 && PAIR && !leader) {
+  } else if (PAIR && warp == 1 && !leader) {
     // ============ relay (rank 1): "my half of tap landed" -> leader's pwfull ============
     uint32_t pos = 0;
     for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
@@ -202,8 +207,100 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ============================ MMA issuer ==============================
+  } else if (!PAIR && (warp == 1 || warp == kStackIssuerB)) {
+    // ======================== MMA issuers (two, one per part) ========================
+    // The issue path is one thread's instruction stream; a lone issuer sharing its scheduler
+    // with four epilogue warps was busy 100 % of the time at ~85 cycles per MMA (measured on
+    // upstack.cu, tools/upstack_trace.py) while an N <= 128 MMA retires in 42-64 cycles.  Each
+    // accumulator block is written by exactly one issuer (fixed summation order); weight taps
+    // are released by both (wempty count 2).
+    static_assert(PAIR || NP == 2, "one MMA issuer warp per part");
+    const int part = (warp == 1) ? 0 : 1;
+    const uint32_t idesc = umma_idesc_f16(C, kOp);
+    const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);
+    const uint64_t bdesc0 = umma_desc_base_nosw(NB * 16, 128);
+    uint32_t pos = 0;
+    uint32_t nconv = 0;
+    for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
+      for (int l = 0; l < 6; ++l, pos += 3, ++nconv) {
+        const int d = (l & 1) ? 1 : p.dil[l >> 1];
+        const uint32_t src16 = ((l & 1) ? sY : sX) >> 4;
+        const uint32_t ready_par = nconv & 1u;
+        // tap t on M-blocks [mb0, mb1) (call inside the elected region)
+        auto issue = [&](int t, int mb0, int mb1) {
+          const uint32_t slot = (pos + t) % NSLOT;
+          const uint64_t bd = bdesc0 + ((sW + slot * TAPB) >> 4);
+          for (int mb = mb0; mb < mb1; ++mb) {
+            const uint64_t ad = adesc0 + (src16 + static_cast<uint32_t>(mb * 128 + (t - 1) * d));
+            const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
+#pragma unroll
+            for (int k16 = 0; k16 < C / 16; ++k16)
+              umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * 2 * R),
+                          bd + static_cast<uint64_t>(k16 * 2 * NB), idesc, 1u);
+          }
+        };
+        auto wait_tap = [&](int t) {
+          const uint32_t q = pos + t;
+          mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u);
+        };
+        const int m0 = part * HB, m1 = m0 + HB;
+        MSB_TRACE(nconv * 16 + part * 4 + 0);
+        mbar_wait(act_ready(part), ready_par);
+        wait_tap(0);
+        tc_fence_after();
+        MSB_TRACE(nconv * 16 + part * 4 + 1);
+        if (part == NP - 1) {
+          // issuer B: the tile's last part has no successor (its tap +d runs off the tile edge)
+          if (elect_one()) {
+            issue(0, m0, m1);
+            umma_commit(wempty((pos + 0) % NSLOT));
+          }
+          __syncwarp();
+          wait_tap(1);
+          if (elect_one()) {
+            issue(1, m0, m1);
+            umma_commit(wempty((pos + 1) % NSLOT));
+          }
+          __syncwarp();
+          wait_tap(2);
+          if (elect_one()) {
+            issue(2, m0, m1);
+            umma_commit(wempty((pos + 2) % NSLOT));
+            umma_commit(acc_full(part));
+          }
+          __syncwarp();
+        } else {
+          // issuer A: tap +d of the part's last M-block reads into the next part; it waits
+          // for those rows (and stays with this issuer: fixed summation order per accumulator)
+          if (elect_one()) {
+            issue(0, m0, m1);
+            umma_commit(wempty((pos + 0) % NSLOT));
+          }
+          __syncwarp();
+          wait_tap(1);
+          if (elect_one()) {
+            issue(1, m0, m1);
+            umma_commit(wempty((pos + 1) % NSLOT));
+          }
+          __syncwarp();
+          wait_tap(2);
+          if (elect_one()) issue(2, m0, m1 - 1);
+          __syncwarp();
+          MSB_TRACE(nconv * 16 + part * 4 + 2);
+          mbar_wait(act_ready(part + 1), ready_par);
+          tc_fence_after();
+          if (elect_one()) {
+            issue(2, m1 - 1, m1);
+            umma_commit(wempty((pos + 2) % NSLOT));
+            umma_commit(acc_full(part));
+          }
+          __syncwarp();
+        }
+        MSB_TRACE(nconv * 16 + part * 4 + 3);
+      }
+    }
+  } else if (PAIR && warp == 1) {
+    // ====================== MMA issuer (CTA-pair kernel: leader) ======================
     // Warp-uniform control flow; only the tcgen05 instructions are predicated on one
     // elected lane, so descriptors stay in uniform registers.
     {
@@ -583,7 +680,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
+__global__ void __launch_bounds__(StackGeom<C>::THREADS, 1)
 resstack_kernel(const __grid_constant__ StackParams p) {
   resstack_body<C, false, false>(p);
 }
@@ -593,13 +690,13 @@ resstack_kernel(const __grid_constant__ StackParams p) {
 // stages half of every weight tap.  Used for C = 128, where a single CTA's N = 128 MMAs
 // saturate the shared-memory port (A 4 KB + B 4 KB per 64 cycles) and starve the epilogue.
 template <int C>
-__global__ void __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
+__global__ void __launch_bounds__(StackGeom<C>::THREADS, 1)
 resstack_bf16_kernel(const __grid_constant__ StackParams p) {
   resstack_body<C, false, true>(p);
 }
 
 template <int C>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * StackGeom<C>::EW, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(StackGeom<C>::THREADS_PAIR, 1)
 resstack_pair_kernel(const __grid_constant__ StackParams p) {
   resstack_body<C, true, false>(p);
 }
@@ -630,7 +727,7 @@ ms_status launch_stack_pair(const StackParams& p, cudaStream_t stream) {
   if (sms <= 1) return check_cuda(cudaGetLastError(), "sm_count");
   const int pairs = (p.total_tiles + 1) / 2;
   const int clusters = pairs < sms / 2 ? pairs : sms / 2;
-  resstack_pair_kernel<C><<<2 * clusters, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+  resstack_pair_kernel<C><<<2 * clusters, G::THREADS_PAIR, G::SMEM, stream>>>(p);
   return after_launch("resstack_pair_kernel");
 }
 
@@ -655,10 +752,10 @@ ms_status launch_stack(const StackParams& p, cudaStream_t stream) {
       if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(resstack_bf16_kernel)");
       attr_set_bf = true;
     }
-    resstack_bf16_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+    resstack_bf16_kernel<C><<<grid, G::THREADS, G::SMEM, stream>>>(p);
     return after_launch("resstack_bf16_kernel");
   }
-  resstack_kernel<C><<<grid, 64 + 32 * G::EW, G::SMEM, stream>>>(p);
+  resstack_kernel<C><<<grid, G::THREADS, G::SMEM, stream>>>(p);
   return after_launch("resstack_kernel");
 }
 
