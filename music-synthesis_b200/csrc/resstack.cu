@@ -142,6 +142,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
   auto acc_full = [&](int m) { return bar_base + 8u * (36 + m); };
   auto act_ready = [&](int m) { return bar_base + 8u * (44 + m); };
   auto pwfull = [&](int s) { return bar_base + 8u * (52 + s); };
+  const uint32_t a_issued = bar_base + 8u * 70;   // issuer A -> issuer B, once per conv
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -152,6 +153,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
       mbar_init(wempty(s), PAIR ? 1 : 2);   // single-CTA kernels: released by both MMA issuers
       mbar_init(pwfull(s), 1);
     }
+    mbar_init(a_issued, 1);
     for (int m = 0; m < 8; ++m) {
       mbar_init(acc_full(m), 1);
       mbar_init(act_ready(m), (PAIR ? 2 : 1) * EW);   // one arrival per epilogue warp
@@ -250,7 +252,11 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         tc_fence_after();
         MSB_TRACE(nconv * 16 + part * 4 + 1);
         if (part == NP - 1) {
-          // issuer B: the tile's last part has no successor (its tap +d runs off the tile edge)
+          // issuer B: the tile's last part has no successor (its tap +d runs off the tile edge).
+          // It queues behind issuer A's MMAs of this conv: part 0 must COMPLETE first so that
+          // its epilogue overlaps this part's MMAs (interleaved, both parts finish together
+          // and the tensor pipe idles through the whole first epilogue)
+          mbar_wait(a_issued, ready_par);
           if (elect_one()) {
             issue(0, m0, m1);
             umma_commit(wempty((pos + 0) % NSLOT));
@@ -293,6 +299,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
             issue(2, m1 - 1, m1);
             umma_commit(wempty((pos + 2) % NSLOT));
             umma_commit(acc_full(part));
+            mbar_arrive(a_issued);
           }
           __syncwarp();
         }

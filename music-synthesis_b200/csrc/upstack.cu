@@ -134,6 +134,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
   auto act_ready = [&](int m) { return bar_base + 8u * (38 + m); };
   const uint32_t in_full = bar_base + 8u * 40;
   const uint32_t in_free = bar_base + 8u * 41;
+  const uint32_t a_issued = bar_base + 8u * 42;   // issuer A -> issuer B, once per stage
   auto buf = [&](int i) { return sBuf0 + static_cast<uint32_t>(i & 1) * G::ACT_BYTES; };
 
   const int warp = threadIdx.x >> 5;
@@ -149,6 +150,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
       mbar_init(act_ready(m), EW);
     }
     mbar_init(in_full, 1);
+    mbar_init(a_issued, 1);
     mbar_init(in_free, 1);         // epilogue warp 2, once stage 5's MMAs have completed
     fence_mbar_init();
   }
@@ -264,6 +266,10 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
       wait_w(pos + 1);
       wait_w(pos + 2);
       tc_fence_after();
+      // issuer B queues behind issuer A's MMAs of the stage: part 0 has to COMPLETE first so
+      // that its epilogue overlaps part 1's MMAs (interleaved, both parts would finish together
+      // and the tensor pipe would idle through the whole first epilogue)
+      if (part == 1) mbar_wait(a_issued, g & 1u);
       MSB_UTRACE(part * 4 + 1);
       if (elect_one()) {
         if (!MSB_ABL(1)) {
@@ -283,6 +289,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
           }
         }
         umma_commit(acc_full(part));
+        if (part == 0) mbar_arrive(a_issued);
       }
       __syncwarp();
       MSB_UTRACE(part * 4 + 2);
@@ -317,6 +324,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
           }
         };
         if (part == NP - 1) {
+          mbar_wait(a_issued, g & 1u);
           if (elect_one()) {
             if (!MSB_ABL(1)) issue_part(1, 0, 3, 0, HE);
             umma_commit(acc_full(1));
@@ -337,6 +345,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
           if (elect_one()) {
             if (!MSB_ABL(1)) issue_part(0, 2, 3, HE - 1, HE);
             umma_commit(acc_full(0));
+            mbar_arrive(a_issued);
           }
           __syncwarp();
         }

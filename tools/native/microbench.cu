@@ -209,6 +209,60 @@ __global__ void __launch_bounds__(512, 1) tmem_bw_kernel(long long* out, int war
 
 }  // namespace msb
 
+// Tensor-pipe time of 64 back-to-back M=128 MMAs as a function of N and of the A operand's start
+// row (tap shift = descriptor start address + 16*shift bytes: is a core matrix that straddles two
+// 128-byte lines fetched at full rate?).  out[0] = cycles issue -> completion.
+namespace msb {
+__global__ void __launch_bounds__(128, 1) mma_shift_kernel(long long* out, int N, int shift, int lbo_rows) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+  const uint32_t bar1 = smem_u32(bars);
+  const uint32_t sA = smem_u32(smem + 1024);
+  const uint32_t sB = sA + 128 * 1024;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(bar1, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < (128 + 64) * 1024 / 16; i += blockDim.x)
+    st_shared_v4(sA + i * 16, 0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = umma_idesc_f16(N, 0);
+    const uint64_t ad = umma_desc_base_nosw(lbo_rows * 16, 128) + ((sA >> 4) + shift);
+    const uint64_t bd = umma_desc_base_nosw(N * 16, 128) + (sB >> 4);
+    uint32_t par = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      __syncwarp();
+      const long long t0 = clock64();
+      if (elect_one()) {
+#pragma unroll 8
+        for (int k = 0; k < 64; ++k)
+          umma_f16_ss(tmem + (k & 1) * 256, ad + (k & 3) * 2 * lbo_rows, bd + (k & 3) * 2 * N, idesc, 1u);
+        umma_commit(bar1);
+      }
+      __syncwarp();
+      mbar_wait(bar1, par); par ^= 1;
+      const long long t1 = clock64();
+      if (threadIdx.x == 0) out[0] = t1 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+}  // namespace msb
+
+extern "C" int ms_debug_mma_shift(long long* dev_out, int N, int shift, int lbo_rows, void* stream) {
+  const int smem = 1024 + (128 + 64) * 1024;
+  cudaFuncSetAttribute(msb::mma_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  msb::mma_shift_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(dev_out, N, shift, lbo_rows);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 extern "C" int ms_debug_microbench(long long* dev_out, void* stream) {
   const int smem = 1024 + 131072;
   cudaFuncSetAttribute(msb::microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

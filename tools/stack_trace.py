@@ -29,8 +29,8 @@ print("C=%d ; cycles relative to prologue start of tile 0" % C)
 print("prologue tile0: %d -> %d ; tile1: %d -> %d" % (0, d[481] - t0, d[482] - t0, d[483] - t0))
 for n in range(12):
     m = n * 16
-    print("conv %2d MMA: A[wait_act %d->%d] B[wait_act %d->%d] issue_done %d" % (
-        n, d[m] - t0, d[m + 1] - t0, d[m + 4] - t0, d[m + 5] - t0, d[m + 15] - t0))
+    print("conv %2d MMA A[wait %d->%d first %d done %d]  B[wait %d->%d done %d]" % (
+        n, d[m] - t0, d[m + 1] - t0, d[m + 2] - t0, d[m + 3] - t0, d[m + 4] - t0, d[m + 5] - t0, d[m + 7] - t0))
     e = 256 + n * 16
     print("        EPI: A[wait %d->%d done %d] B[wait %d->%d done %d]" % (
         d[e] - t0, d[e + 1] - t0, d[e + 2] - t0, d[e + 4] - t0, d[e + 5] - t0, d[e + 6] - t0))
