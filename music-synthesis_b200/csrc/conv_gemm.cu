@@ -608,27 +608,43 @@ convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */,
     for (int t = 0; t <= p.taps - 2 - e; ++t) {
       const int xrow = p.lin + e + t - (p.taps - 1);
       if (xrow < 0) continue;
-      for (int c8 = slice; c8 < (p.cin >> 3); c8 += kTailSlices) {   // 8 input channels per step
-        const int ci = c8 * 8;
-        const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
-        // packed[nt][kb][tap][c][nn][0..7]
-        const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
-        const size_t xi = ((static_cast<size_t>(b) * xc8 + c8 % xc8) * p.lin + xrow) * 8;
-        const uint4 wq = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
-        const uint4 xq = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
-        const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w}, xx[4] = {xq.x, xq.y, xq.z, xq.w};
+      // this slice's channel chunks in batches of four: all eight loads of a batch are issued
+      // before the first multiply (the loop used to be one dependent L2 round trip per chunk)
+      const int nch = p.cin >> 3;
+      for (int c80 = slice; c80 < nch; c80 += 4 * kTailSlices) {
+        uint4 wq[4], xq[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 wf, xf;
-          if (p.operand == MS_BF16) {
-            wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
-            xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
-          } else {
-            wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
-            xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+        for (int u = 0; u < 4; ++u) {
+          const int c8 = c80 + u * kTailSlices;
+          wq[u] = make_uint4(0u, 0u, 0u, 0u);
+          xq[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (c8 < nch) {
+            const int ci = c8 * 8;
+            const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
+            // packed[nt][kb][tap][c][nn][0..7]
+            const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
+            const size_t xi = ((static_cast<size_t>(b) * xc8 + c8 % xc8) * p.lin + xrow) * 8;
+            wq[u] = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
+            xq[u] = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
           }
-          acc = fmaf(xf.x, wf.x, acc);
-          acc = fmaf(xf.y, wf.y, acc);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t ww[4] = {wq[u].x, wq[u].y, wq[u].z, wq[u].w};
+          const uint32_t xx[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 wf, xf;
+            if (p.operand == MS_BF16) {
+              wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+              xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
+            } else {
+              wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+              xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+            }
+            acc = fmaf(xf.x, wf.x, acc);
+            acc = fmaf(xf.y, wf.y, acc);
+          }
         }
       }
     }

@@ -343,6 +343,24 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_m256(int n, int ab_format)
 // ------------------------------------------------------------------- small math
 __device__ __forceinline__ float leaky02(float v) { return fmaxf(v, 0.2f * v); }
 
+// Packed fp32 pairs (sm_100: FMUL2 / FADD2, one issue slot per two results; same rounding as the
+// scalar forms).  leaky02x2: (max(a, 0.2a), max(b, 0.2b)); add_x2: (a + c, b + d).
+__device__ __forceinline__ void leaky02x2(float a, float b, float& x, float& y) {
+  float t0, t1;
+  asm("{\n\t.reg .b64 ra, rs, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rs, {%4, %4};\n\t"
+      "mul.rn.f32x2 rd, ra, rs;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(t0), "=f"(t1)
+      : "f"(a), "f"(b), "f"(0.2f));
+  x = fmaxf(a, t0);
+  y = fmaxf(b, t1);
+}
+__device__ __forceinline__ void add_x2(float a, float b, float c, float d, float& x, float& y) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(x), "=f"(y)
+      : "f"(a), "f"(b), "f"(c), "f"(d));
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

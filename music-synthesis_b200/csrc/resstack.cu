@@ -569,12 +569,16 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
                 for (int g = 0; g < GS / 16; ++g) tmem_ld16p(tx + c0 + g * 16, &xr[g * 16]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < GS; ++j)
-                  f[j] = __uint_as_float(xr[j]) + leaky02(__uint_as_float(v[j]));
+                for (int j = 0; j < GS; j += 2) {
+                  float l0, l1;
+                  leaky02x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), l0, l1);
+                  add_x2(__uint_as_float(xr[j]), __uint_as_float(xr[j + 1]), l0, l1, f[j], f[j + 1]);
+                }
               } else {
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < GS; ++j) f[j] = leaky02(__uint_as_float(v[j]));
+                for (int j = 0; j < GS; j += 2)
+                  leaky02x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), f[j], f[j + 1]);
               }
               if (zero_row) {
 #pragma unroll
