@@ -53,7 +53,16 @@ struct StackParams {
   const float* mono_b;   // (1)
   float* mono_out;       // (B, 1, L) fp32
   long long* dbg;        // optional clock trace of CTA 0 (null in production)
+  int ablate;            // MSB_STACK_ABLATE builds only (tools/stack_bench.py): bit 0 no MMAs,
+                         // 1 empty epilogue, 2 no operand stores, 3 no tensor-memory traffic in
+                         // the epilogue, 4 no bias pre-load
 };
+
+#ifdef MSB_STACK_ABLATE
+#define MSB_SABL(bit) ((p.ablate & (bit)) != 0)
+#else
+#define MSB_SABL(bit) false
+#endif
 
 #ifdef MSB_STACK_TRACE
 #define MSB_TRACE(slot)                                                     \
@@ -92,7 +101,7 @@ struct StackGeom {
   static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES + P_BYTES;
   // producer, MMA issuer A, epilogue warps, MMA issuer B (single-CTA kernels only)
   static constexpr int THREADS = 64 + 32 * EW + 32;
-  static constexpr int THREADS_PAIR = 64 + 32 * EW;
+  static constexpr int THREADS_PAIR = THREADS;
 };
 
 constexpr int kStackIssuerB = 18;   // warp index of the second MMA issuer
@@ -150,7 +159,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < 18; ++s) {
       mbar_init(wfull(s), 1);
-      mbar_init(wempty(s), PAIR ? 1 : 2);   // single-CTA kernels: released by both MMA issuers
+      mbar_init(wempty(s), 2);              // released by both MMA issuers
       mbar_init(pwfull(s), 1);
     }
     mbar_init(a_issued, 1);
@@ -209,16 +218,25 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         __syncwarp();
       }
     }
-  } else if (!PAIR && (warp == 1 || warp == kStackIssuerB)) {
+  } else if ((warp == 1 || warp == kStackIssuerB) && (!PAIR || leader)) {
     // ======================== MMA issuers (two, one per part) ========================
     // The issue path is one thread's instruction stream; a lone issuer sharing its scheduler
     // with four epilogue warps was busy 100 % of the time at ~85 cycles per MMA (measured on
     // upstack.cu, tools/upstack_trace.py) while an N <= 128 MMA retires in 42-64 cycles.  Each
     // accumulator block is written by exactly one issuer (fixed summation order); weight taps
     // are released by both (wempty count 2).
-    static_assert(PAIR || NP == 2, "one MMA issuer warp per part");
+    // CTA-pair kernel: both issuers live in the leader CTA and issue M = 256 MMAs that cover one
+    // M-block of each CTA's tile; commits are multicast to both CTAs, act_ready collects both
+    // CTAs' epilogue warps (cluster-scope waits), rank 1 relays "my half of the tap landed".
+    static_assert(NP == 2, "one MMA issuer warp per part");
     const int part = (warp == 1) ? 0 : 1;
-    const uint32_t idesc = umma_idesc_f16(C, kOp);
+    const uint32_t idesc = PAIR ? umma_idesc_f16_m256(C, kOp) : umma_idesc_f16(C, kOp);
+    auto commit_to = [&](uint32_t bar) {
+      if (PAIR) umma2_commit_mc(bar); else umma_commit(bar);
+    };
+    auto wait_act = [&](int m, uint32_t par) {
+      if (PAIR) mbar_wait_cluster(act_ready(m), par); else mbar_wait(act_ready(m), par);
+    };
     const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);
     const uint64_t bdesc0 = umma_desc_base_nosw(NB * 16, 128);
     uint32_t pos = 0;
@@ -232,22 +250,27 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         auto issue = [&](int t, int mb0, int mb1) {
           const uint32_t slot = (pos + t) % NSLOT;
           const uint64_t bd = bdesc0 + ((sW + slot * TAPB) >> 4);
+          if (MSB_SABL(1)) return;
           for (int mb = mb0; mb < mb1; ++mb) {
             const uint64_t ad = adesc0 + (src16 + static_cast<uint32_t>(mb * 128 + (t - 1) * d));
             const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
 #pragma unroll
-            for (int k16 = 0; k16 < C / 16; ++k16)
-              umma_f16_ss(dst, ad + static_cast<uint64_t>(k16 * 2 * R),
-                          bd + static_cast<uint64_t>(k16 * 2 * NB), idesc, 1u);
+            for (int k16 = 0; k16 < C / 16; ++k16) {
+              const uint64_t a_k = ad + static_cast<uint64_t>(k16 * 2 * R);
+              const uint64_t b_k = bd + static_cast<uint64_t>(k16 * 2 * NB);
+              if (PAIR) umma2_f16_ss(dst, a_k, b_k, idesc, 1u);
+              else umma_f16_ss(dst, a_k, b_k, idesc, 1u);
+            }
           }
         };
         auto wait_tap = [&](int t) {
           const uint32_t q = pos + t;
           mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u);
+          if (PAIR) mbar_wait_cluster(pwfull(q % NSLOT), (q / NSLOT) & 1u);
         };
         const int m0 = part * HB, m1 = m0 + HB;
         MSB_TRACE(nconv * 16 + part * 4 + 0);
-        mbar_wait(act_ready(part), ready_par);
+        wait_act(part, ready_par);
         wait_tap(0);
         tc_fence_after();
         MSB_TRACE(nconv * 16 + part * 4 + 1);
@@ -259,20 +282,20 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
           mbar_wait(a_issued, ready_par);
           if (elect_one()) {
             issue(0, m0, m1);
-            umma_commit(wempty((pos + 0) % NSLOT));
+            commit_to(wempty((pos + 0) % NSLOT));
           }
           __syncwarp();
           wait_tap(1);
           if (elect_one()) {
             issue(1, m0, m1);
-            umma_commit(wempty((pos + 1) % NSLOT));
+            commit_to(wempty((pos + 1) % NSLOT));
           }
           __syncwarp();
           wait_tap(2);
           if (elect_one()) {
             issue(2, m0, m1);
-            umma_commit(wempty((pos + 2) % NSLOT));
-            umma_commit(acc_full(part));
+            commit_to(wempty((pos + 2) % NSLOT));
+            commit_to(acc_full(part));
           }
           __syncwarp();
         } else {
@@ -280,25 +303,25 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
           // for those rows (and stays with this issuer: fixed summation order per accumulator)
           if (elect_one()) {
             issue(0, m0, m1);
-            umma_commit(wempty((pos + 0) % NSLOT));
+            commit_to(wempty((pos + 0) % NSLOT));
           }
           __syncwarp();
           wait_tap(1);
           if (elect_one()) {
             issue(1, m0, m1);
-            umma_commit(wempty((pos + 1) % NSLOT));
+            commit_to(wempty((pos + 1) % NSLOT));
           }
           __syncwarp();
           wait_tap(2);
           if (elect_one()) issue(2, m0, m1 - 1);
           __syncwarp();
           MSB_TRACE(nconv * 16 + part * 4 + 2);
-          mbar_wait(act_ready(part + 1), ready_par);
+          wait_act(part + 1, ready_par);
           tc_fence_after();
           if (elect_one()) {
             issue(2, m1 - 1, m1);
-            umma_commit(wempty((pos + 2) % NSLOT));
-            umma_commit(acc_full(part));
+            commit_to(wempty((pos + 2) % NSLOT));
+            commit_to(acc_full(part));
             mbar_arrive(a_issued);
           }
           __syncwarp();
@@ -306,85 +329,8 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         MSB_TRACE(nconv * 16 + part * 4 + 3);
       }
     }
-  } else if (PAIR && warp == 1) {
-    // ====================== MMA issuer (CTA-pair kernel: leader) ======================
-    // Warp-uniform control flow; only the tcgen05 instructions are predicated on one
-    // elected lane, so descriptors stay in uniform registers.
-    {
-      const uint32_t idesc = PAIR ? umma_idesc_f16_m256(C, kOp) : umma_idesc_f16(C, kOp);
-      const uint64_t adesc0 = umma_desc_base_nosw(R * 16, 128);
-      const uint64_t bdesc0 = umma_desc_base_nosw(NB * 16, 128);
-      uint32_t pos = 0;      // ring position of the current conv's first tap
-      uint32_t nconv = 0;    // convs issued so far (parity of act_ready waits)
-      for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
-        for (int l = 0; l < 6; ++l, pos += 3, ++nconv) {
-          const int d = (l & 1) ? 1 : p.dil[l >> 1];
-          const uint32_t src = (l & 1) ? sY : sX;
-          const uint32_t ready_par = nconv & 1u;
-          // one elected lane issues tap t for M-blocks [mb0, mb1)
-          auto issue = [&](int t, int mb0, int mb1) {
-            const int slot = (pos + t) % NSLOT;
-            const int shift = (t - 1) * d;
-            const uint64_t bd = bdesc0 + ((sW + static_cast<uint32_t>(slot * TAPB)) >> 4);
-            if (elect_one()) {
-              for (int mb = mb0; mb < mb1; ++mb) {
-                const uint64_t ad =
-                    adesc0 + ((src + static_cast<uint32_t>((mb * 128 + shift) * 16)) >> 4);
-                const uint32_t dst = tmem_base + static_cast<uint32_t>(mb * 2 * C + C);
-#pragma unroll
-                for (int k16 = 0; k16 < C / 16; ++k16) {
-                  const uint64_t a_k = ad + static_cast<uint64_t>(k16 * (2 * R * 16 / 16));
-                  const uint64_t b_k = bd + static_cast<uint64_t>(k16 * (2 * NB * 16 / 16));
-                  // always accumulate: the epilogue pre-loaded the accumulator with the bias
-                  if (PAIR) umma2_f16_ss(dst, a_k, b_k, idesc, 1u);
-                  else umma_f16_ss(dst, a_k, b_k, idesc, 1u);
-                }
-              }
-            }
-            __syncwarp();
-          };
-          auto wait_tap = [&](int t) {
-            const uint32_t q = pos + t;
-            mbar_wait(wfull(q % NSLOT), (q / NSLOT) & 1u);
-            if (PAIR) mbar_wait_cluster(pwfull(q % NSLOT), (q / NSLOT) & 1u);
-          };
-          auto commit = [&](uint32_t bar) {
-            if (elect_one()) {
-              if (PAIR) umma2_commit_mc(bar); else umma_commit(bar);
-            }
-            __syncwarp();
-          };
-          // Part i = M-blocks [i*HB, (i+1)*HB).  As soon as the epilogue has produced part i
-          // (act_ready(i)): tap +d of part i-1's last M-block (it reads into part i) completes
-          // part i-1; then every tap of part i except tap +d of ITS last M-block.
-          for (int part = 0; part < NP; ++part) {
-            MSB_TRACE(nconv * 16 + part * 4 + 0);
-            if (PAIR) mbar_wait_cluster(act_ready(part), ready_par);
-            else mbar_wait(act_ready(part), ready_par);
-            tc_fence_after();
-            MSB_TRACE(nconv * 16 + part * 4 + 1);
-            const int m0 = part * HB, m1 = m0 + HB;
-            if (part > 0) {
-              issue(2, m0 - 1, m0);
-              commit(acc_full(part - 1));
-            } else {
-              wait_tap(0);
-            }
-            issue(0, m0, m1);
-            if (part == NP - 1) commit(wempty((pos + 0) % NSLOT));
-            if (part == 0) wait_tap(1);
-            issue(1, m0, m1);
-            if (part == NP - 1) commit(wempty((pos + 1) % NSLOT));
-            if (part == 0) wait_tap(2);
-            // the tile's very last M-block has no successor: its tap +d runs off the tile edge
-            issue(2, m0, part == NP - 1 ? m1 : m1 - 1);
-          }
-          commit(wempty((pos + 2) % NSLOT));
-          commit(acc_full(NP - 1));
-          MSB_TRACE(nconv * 16 + 15);
-        }
-      }
-    }
+  } else if (warp == 1 || warp == kStackIssuerB) {
+    // (rank 1 of a CTA pair: warp 18 has no role; warp 1 was the relay above)
   } else {
     // ====================== prologue / epilogue warps ======================
     // Thread = one row (TMEM lane) x COLS channels of IT M-blocks per pipeline part.  The
@@ -548,6 +494,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 1);
 #pragma unroll
           for (int u = 0; u < IT; ++u) {
+            if (MSB_SABL(2)) continue;
             const int mb = h * HB + ms + u * G::MSPLIT;
             const int row = mb * 128 + row0;
             const int t = t0 + row;
@@ -560,13 +507,23 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
 #pragma unroll
             for (int c0 = 0; c0 < COLS; c0 += GS) {
               uint32_t v[GS];
+              if (MSB_SABL(8)) {
 #pragma unroll
-              for (int g = 0; g < GS / 16; ++g) tmem_ld16p(ta + c0 + g * 16, &v[g * 16]);
+                for (int j = 0; j < GS; ++j) v[j] = static_cast<uint32_t>(t + j);
+              } else {
+#pragma unroll
+                for (int g = 0; g < GS / 16; ++g) tmem_ld16p(ta + c0 + g * 16, &v[g * 16]);
+              }
               float f[GS];
               if (second) {
                 uint32_t xr[GS];
+                if (MSB_SABL(8)) {
 #pragma unroll
-                for (int g = 0; g < GS / 16; ++g) tmem_ld16p(tx + c0 + g * 16, &xr[g * 16]);
+                  for (int j = 0; j < GS; ++j) xr[j] = static_cast<uint32_t>(t - j);
+                } else {
+#pragma unroll
+                  for (int g = 0; g < GS / 16; ++g) tmem_ld16p(tx + c0 + g * 16, &xr[g * 16]);
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < GS; j += 2) {
@@ -585,7 +542,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
                 for (int j = 0; j < GS; ++j) f[j] = 0.f;
               }
               if (!last) {
-                if (second) {
+                if (second && !MSB_SABL(8)) {
 #pragma unroll
                   for (int j = 0; j < GS; ++j) v[j] = __float_as_uint(f[j]);
 #pragma unroll
@@ -593,6 +550,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
                 }
 #pragma unroll
                 for (int c = 0; c < GS / 8; ++c) {
+                  if (MSB_SABL(4)) continue;
                   const uint32_t dst =
                       dstbuf + so0 + static_cast<uint32_t>(((c0 / 8 + c) * R + mb * 128) * 16);
                   st_shared_v4(dst, pack2s(f[c * 8 + 0], f[c * 8 + 1], kOp),
@@ -637,7 +595,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
               }
             }
             // the accumulator has been read: seed it with the next conv's bias
-            if (!last) store_bias(l + 1, ta);
+            if (!last && !MSB_SABL(8) && !MSB_SABL(16)) store_bias(l + 1, ta);
             // this row is done with the old tile: bring in the next tile's row
             if (last && has_next) store_row(mb, nx[last ? u : 0]);
           }
@@ -799,6 +757,10 @@ ms_status resstack_fwd(int channels, int batch, int len, const int* dil, int ope
   p.operand = operand;
   p.mono_w = mono_w; p.mono_b = mono_b; p.mono_out = mono_out;
   p.dbg = g_stack_dbg;
+  p.ablate = 0;
+#ifdef MSB_STACK_ABLATE
+  if (const char* e = getenv("MSB_STACK_ABLATE")) p.ablate = atoi(e);
+#endif
   int V;
   switch (channels) {
     case 128: V = StackGeom<128>::R - 2 * halo; break;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(512, 1) tmem_bw_kernel(long long* out, int war
 // row (tap shift = descriptor start address + 16*shift bytes: is a core matrix that straddles two
 // 128-byte lines fetched at full rate?).  out[0] = cycles issue -> completion.
 namespace msb {
-__global__ void __launch_bounds__(128, 1) mma_shift_kernel(long long* out, int N, int shift, int lbo_rows) {
+__global__ void __launch_bounds__(128, 1) mma_shift_kernel(long long* out, int N, int shift, int lbo_rows, int nacc, int run) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128, 1) mma_shift_kernel(long long* out, int N
       if (elect_one()) {
 #pragma unroll 8
         for (int k = 0; k < 64; ++k)
-          umma_f16_ss(tmem + (k & 1) * 256, ad + (k & 3) * 2 * lbo_rows, bd + (k & 3) * 2 * N, idesc, 1u);
+          umma_f16_ss(tmem + ((k >> run) & (nacc - 1)) * 256, ad + (k & 3) * 2 * lbo_rows, bd + (k & 3) * 2 * N, idesc, 1u);
         umma_commit(bar1);
       }
       __syncwarp();
@@ -256,10 +256,10 @@ __global__ void __launch_bounds__(128, 1) mma_shift_kernel(long long* out, int N
 }
 }  // namespace msb
 
-extern "C" int ms_debug_mma_shift(long long* dev_out, int N, int shift, int lbo_rows, void* stream) {
+extern "C" int ms_debug_mma_shift(long long* dev_out, int N, int shift, int lbo_rows, int nacc, int run, void* stream) {
   const int smem = 1024 + (128 + 64) * 1024;
   cudaFuncSetAttribute(msb::mma_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  msb::mma_shift_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(dev_out, N, shift, lbo_rows);
+  msb::mma_shift_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(dev_out, N, shift, lbo_rows, nacc, run);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
