@@ -49,7 +49,20 @@ static int pick_nt(int ntot) {
   return 0;
 }
 
+long long* g_conv_dbg = nullptr;   // debugging aid (MSB_CONV_ABLATE builds): see ms_debug_set_conv_trace
+
+// MSB_CONV_WRES=0 disables the weight-resident mode of the pair kernel (A/B timing)
+static bool wres_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MSB_CONV_WRES");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
+  c->wres = 0;
   if (d.batch <= 0 || d.lin <= 0 || d.cin <= 0 || d.cout <= 0) return false;
   if (d.cin % 16 != 0 || d.cout % 8 != 0) return false;
   if (d.operand != MS_F16 && d.operand != MS_BF16) return false;
@@ -158,6 +171,23 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     if (psmem < 120 * 1024) psmem = 120 * 1024;
     c->smem_bytes = psmem;
     c->packed_weight_bytes = static_cast<size_t>(c->nnt) * 2 * c->nkb * c->w_stage_bytes;
+    // Weight-resident mode: when this CTA's half of an n-tile's weights (all k-blocks, all taps)
+    // fits beside three activation stages, it is loaded once per n-tile and the cluster walks
+    // the m-tiles of that n-tile (ConvTranspose 256 -> 128, k16 s8: 128 KB per CTA; the layer
+    // was bound by re-streaming 256 KB of weights per 256 x 256 tile through the SM<->L2 fabric)
+    c->wres = 0;
+    if (!fold && wres_enabled()) {
+      const int slice = c->nkb * c->w_stage_bytes;
+      const int a_stage = (c->a_stage_bytes + 127) / 128 * 128;
+      const int as = slice <= 128 * 1024 ? (pbudget - slice) / a_stage : 0;
+      if (as >= 3) {
+        c->wres = 1;
+        c->stage_bytes = a_stage;
+        c->stages = as > kMaxStages ? kMaxStages : as;
+        c->smem_bytes = kSmemHeader + static_cast<size_t>(slice) +
+                        static_cast<size_t>(c->stages) * c->stage_bytes;
+      }
+    }
     if (!fold) return true;
     // folded tiles run on the single-CTA kernel: the pair layout IS a single-CTA layout with
     // n-tiles of half the width, so the packed image stays the same for every length
@@ -220,7 +250,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int operand) {
   return pack_h2(a, b);
 }
 
-constexpr int kConvEpiWarps = 8;
+// 16 epilogue warps = four column slices per TMEM lane quarter.  With 8 (two per scheduler) the
+// drain of a 128 x 256 accumulator took ~7.6 k cycles against 4.6 k cycles of MMAs per tile: the
+// epilogue is a dependent FFMA/FMNMX chain per element, and two warps cannot fill a scheduler
+// (tools/pair_trace.py; the stack kernels run 16 as well)
+constexpr int kConvEpiWarps = 16;
+constexpr int kConvEpiSlices = kConvEpiWarps / 4;
 constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -251,7 +286,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * kConvEpiWarps);
+      mbar_init(tempty_bar(a), kConvEpiWarps);   // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -422,7 +457,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // 8 warps: lane quarter q = warp % 4 (hardware rule), two warps per quarter take
     // alternate 32-column groups.  TMEM loads are batched (32 columns per wait).
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;   // column slice of this warp
     int acc = 0;
     uint32_t acc_phase = 0;
     const int cout8 = p.cout >> 3;
@@ -462,7 +497,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int mb = 0; mb < p.MBLK; ++mb) {
           const int pm = mt * rows_per_tile + mb * 128 + q * 32 + lane;
           if (pm >= p.Lm) continue;
-          for (int g = 2 * half; g < ngroups; g += 4) {
+          for (int g = 2 * half; g < ngroups; g += 2 * kConvEpiSlices) {
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int cidx = g * 2 + h;
@@ -488,7 +523,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>(acc * acc_cols + mb * p.NT);
         // this warp handles group pairs (2 x 16 columns) g = 2*half, 2*half+4, ...
-        for (int g = 2 * half; g < ngroups; g += 4) {
+        for (int g = 2 * half; g < ngroups; g += 2 * kConvEpiSlices) {
           const bool two = (g + 1) < ngroups;
           // the residual vectors of this group's (up to four) chunks are requested BEFORE the
           // accumulator is read: four independent loads in flight per thread instead of one L2
@@ -509,10 +544,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           tmem_ld16p(taddr + g * 16, &v[0]);
           if (two) tmem_ld16p(taddr + (g + 1) * 16, &v[16]);
           tmem_ld_wait();
-          if (mb == p.MBLK - 1 && g + 4 >= ngroups) {
+          if (mb == p.MBLK - 1 && g + 2 * kConvEpiSlices >= ngroups) {
             // last TMEM read of this tile by this thread: hand the accumulator back
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -564,7 +600,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       // warps with no column group in this tile (tiny NT) still have to arrive
       if (2 * half >= ngroups) {
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
       }
       if (++acc == p.acc_stages) {
         acc = 0;
@@ -726,7 +763,13 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   for (int t = 0; t < kMaxTaps; ++t) p.off[t] = t < c.taps ? c.off[t] : 0;
   p.min_off = c.min_off; p.RA = c.RA;
   p.Ntot = c.Ntot; p.NT = c.NT; p.KB = c.KB; p.nnt = c.nnt; p.nkb = c.nkb;
-  p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages; p.pair = c.pair;
+  p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages; p.pair = c.pair; p.wres = c.wres;
+  p.debug = 0;
+  p.dbg = nullptr;
+#ifdef MSB_CONV_ABLATE
+  if (const char* e = getenv("MSB_CONV_ABLATE")) p.debug = atoi(e);
+  p.dbg = g_conv_dbg;
+#endif
   p.stages = c.stages; p.a_stage_bytes = c.a_stage_bytes; p.w_stage_bytes = c.w_stage_bytes;
   p.stage_bytes = c.stage_bytes; p.tmem_cols = c.tmem_cols;
   p.kind = d.kind; p.stride = d.stride; p.pad = d.pad; p.leaky = d.leaky;
@@ -808,5 +851,9 @@ ms_status ms_conv_fwd(const ms_conv_desc* d, const void* x16, const void* w_pack
   return launch_conv(*d, c, x16, w_packed, bias, res32, y16, y32,
                      static_cast<cudaStream_t>(stream));
 }
+
+/* debugging aid (not in the public header): clock64 trace buffer (512 x int64, device) filled
+ * by cluster 0's leader in subsequent pair-kernel launches (MSB_CONV_ABLATE builds only) */
+void ms_debug_set_conv_trace(long long* dev_buf) { msb::g_conv_dbg = dev_buf; }
 
 }  // extern "C"

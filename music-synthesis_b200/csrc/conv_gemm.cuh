@@ -18,6 +18,8 @@ struct ConvCfg {
   int taps;            // GEMM taps (MS_CONV: ksize; MS_CONVT: ksize / stride)
   int off[kMaxTaps];   // input row of tap t for GEMM row m is m + off[t]
   int pair;            // 1: CTA-pair kernel (cta_group::2, 256-row cluster tile, W split)
+  int wres;            // 1 (pair kernel): the n-tile's weight slice stays resident in shared memory
+                       // and only activations stream through the stage ring
   int MBLK;            // 128-row M-blocks per CTA tile (1 or 2): they share each W stage
   int min_off, RA;     // RA = 128*MBLK + max_off - min_off rows of A staged per tile
   int Ntot;            // GEMM N (MS_CONV: cout; MS_CONVT: stride*cout)
@@ -65,12 +67,15 @@ struct ConvGemmParams {
   int taps;
   int off[kMaxTaps];
   int min_off, RA;
-  int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages, pair;
+  int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages, pair, wres;
   int fold_slots, fold_stride, btiles;
   int stages, a_stage_bytes, w_stage_bytes, stage_bytes, tmem_cols;
   int kind, stride, pad, leaky, operand;
   float alpha;
   int total_tiles;
+  long long* dbg;       // MSB_CONV_ABLATE builds only: clock64 trace buffer (tools/pair_trace.py)
+  int debug;            // MSB_CONV_ABLATE builds only (timing experiments): bit 0 no global stores,
+                        // 1 no MMAs, 2 no residual loads
 };
 
 }  // namespace msb

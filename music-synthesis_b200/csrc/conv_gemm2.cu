@@ -24,7 +24,25 @@
 
 namespace msb {
 
-constexpr int kPairEpiWarps = 8;
+#ifdef MSB_CONV_ABLATE
+#define MSB_CABL(bit) ((p.debug & (bit)) != 0)
+// trace of cluster 0's leader, local tile indices 4..7: slot = role base + (ti - 4) * 16 + k
+#define MSB_CTRACE(base, k)                                                                  \
+  do {                                                                                       \
+    if (p.dbg != nullptr && blockIdx.x == 0 && ti >= 4 && ti < 8 && (threadIdx.x & 31) == 0) \
+      p.dbg[(base) + (ti - 4) * 16 + (k)] = clock64();                                       \
+  } while (0)
+#else
+#define MSB_CABL(bit) false
+#define MSB_CTRACE(base, k) do { } while (0)
+#endif
+
+// 16 epilogue warps = four column slices per TMEM lane quarter.  With 8 (two per scheduler) the
+// drain of a 128 x 256 accumulator took ~7.6 k cycles against 4.6 k cycles of MMAs per tile: the
+// epilogue is a dependent FFMA/FMNMX chain per element, and two warps cannot fill a scheduler
+// (tools/pair_trace.py; the stack kernels run 16 as well)
+constexpr int kPairEpiWarps = 16;
+constexpr int kPairEpiSlices = kPairEpiWarps / 4;
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 
 __device__ __forceinline__ uint32_t pack2p(float a, float b, int operand) {
@@ -50,6 +68,9 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   auto pfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (24 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (26 + a); };
+  // weight-resident mode: this CTA's resident slice landed / (leader) the peer's landed
+  const uint32_t wres_full = bar_base + 8u * 28;
+  const uint32_t wres_pfull = bar_base + 8u * 29;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,8 +87,12 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 2 * 32 * kPairEpiWarps);   // both CTAs' epilogue threads
+      // one arrival per epilogue warp of both CTAs (per-thread arrivals meant 256 remote
+      // mbarrier operations per tile from rank 1, serialised on the leader's barrier)
+      mbar_init(tempty_bar(a), 2 * kPairEpiWarps);
     }
+    mbar_init(wres_full, 1);
+    mbar_init(wres_pfull, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -82,24 +107,68 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
 
   const int chunks = p.KB >> 3;
   const int nth = p.NT >> 1;   // B rows staged by each CTA
+  // Tile walk.  Streaming mode: tile = (b, mt, nt) with nt fastest, clusters interleaved.
+  // Weight-resident mode: nt slowest and each cluster takes a CONTIGUOUS run of tiles, so a
+  // cluster changes its n-tile (reloads its resident weight slice) at most nnt - 1 times.
+  const int per_nt = p.total_tiles / p.nnt;
+  const int run = p.wres ? (p.total_tiles + nclusters - 1) / nclusters : 0;
+  const int tile_begin = p.wres ? cluster_id * run : cluster_id;
+  const int tile_end = p.wres ? min(p.total_tiles, tile_begin + run) : p.total_tiles;
+  const int tile_step = p.wres ? 1 : nclusters;
+  auto decode = [&](int tile, int& nt_idx, int& mt, int& b) {
+    int rest;
+    if (p.wres) {
+      nt_idx = tile / per_nt;
+      rest = tile - nt_idx * per_nt;
+    } else {
+      nt_idx = tile % p.nnt;
+      rest = tile / p.nnt;
+    }
+    mt = rest % p.mtiles;
+    b = rest / p.mtiles;
+  };
+  const uint32_t wslice = p.wres ? static_cast<uint32_t>(p.nkb) * p.w_stage_bytes : 0u;
+  const uint32_t ring_base = data_base + wslice;   // resident weights first, then the stage ring
 
   if (warp == 0) {
     // =============================== producer ===============================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
-      const int nt_idx = tile % p.nnt;
-      const int rest = tile / p.nnt;
-      const int mt = rest % p.mtiles;
-      const int b = rest / p.mtiles;
+    int cur_nt = -1;
+    int ti = -1;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      ++ti;
+      int nt_idx, mt, b;
+      decode(tile, nt_idx, mt, b);
+      if (p.wres && nt_idx != cur_nt) {
+        if (cur_nt >= 0) {
+          // every MMA that reads the old slice has completed once the most recently filled
+          // stage has been released (tcgen05.commit covers all earlier MMAs)
+          const int last = stage == 0 ? p.stages - 1 : stage - 1;
+          const uint32_t last_phase = stage == 0 ? phase ^ 1u : phase;
+          mbar_wait(empty_bar(last), last_phase);
+        }
+        cur_nt = nt_idx;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(wres_full, wslice);
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) +
+                                (static_cast<size_t>(nt_idx) * 2 + rank) * wslice;
+          for (int kb = 0; kb < p.nkb; ++kb)
+            bulk_g2s(data_base + static_cast<uint32_t>(kb) * p.w_stage_bytes,
+                     wsrc + static_cast<size_t>(kb) * p.w_stage_bytes, p.w_stage_bytes, wres_full);
+        }
+        __syncwarp();
+      }
       const int r0 = mt * 256 + static_cast<int>(rank) * 128 + p.min_off;
       const int lo = r0 < 0 ? 0 : r0;
       const int hi = (r0 + p.RA) > p.lin ? p.lin : (r0 + p.RA);
       const int nrows = hi > lo ? hi - lo : 0;
       const bool ragged = (nrows != p.RA);
       for (int kb = 0; kb < p.nkb; ++kb) {
+        if (kb < 4) MSB_CTRACE(0, kb * 3);
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+        if (kb < 4) MSB_CTRACE(0, kb * 3 + 1);
+        const uint32_t sA = ring_base + static_cast<uint32_t>(stage) * p.stage_bytes;
         const uint32_t sW = sA + p.a_stage_bytes;
         if (ragged) {
           const int head = lo - r0;
@@ -116,11 +185,13 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         if (elect_one()) {
           const uint32_t bytes_a = static_cast<uint32_t>(nrows) * 16u * chunks;
-          mbar_arrive_expect_tx(full_bar(stage), bytes_a + p.w_stage_bytes);
-          const uint8_t* wsrc =
-              reinterpret_cast<const uint8_t*>(p.w) +
-              ((static_cast<size_t>(nt_idx) * 2 + rank) * p.nkb + kb) * p.w_stage_bytes;
-          bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
+          mbar_arrive_expect_tx(full_bar(stage), bytes_a + (p.wres ? 0u : p.w_stage_bytes));
+          if (!p.wres) {
+            const uint8_t* wsrc =
+                reinterpret_cast<const uint8_t*>(p.w) +
+                ((static_cast<size_t>(nt_idx) * 2 + rank) * p.nkb + kb) * p.w_stage_bytes;
+            bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
+          }
           if (nrows > 0) {
             const size_t cbase = static_cast<size_t>(b) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
             for (int c = 0; c < chunks; ++c) {
@@ -131,6 +202,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         __syncwarp();
+        if (kb < 4) MSB_CTRACE(0, kb * 3 + 2);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
@@ -150,18 +222,37 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
+      int cur_nt = -1;
+      uint32_t wres_phase = 0;
+      int ti = -1;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        ++ti;
+        if (p.wres) {
+          int nt_idx, mt, b;
+          decode(tile, nt_idx, mt, b);
+          if (nt_idx != cur_nt) {
+            cur_nt = nt_idx;
+            mbar_wait(wres_full, wres_phase);
+            mbar_wait_cluster(wres_pfull, wres_phase);
+            wres_phase ^= 1u;
+          }
+        }
+        MSB_CTRACE(64, 0);
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
+        MSB_CTRACE(64, 1);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.NT);
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (kb < 4) MSB_CTRACE(64, 2 + kb * 3);
           mbar_wait_cluster(pfull_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sA = data_base + static_cast<uint32_t>(stage) * p.stage_bytes;
-          const uint32_t sW = sA + p.a_stage_bytes;
+          if (kb < 4) MSB_CTRACE(64, 3 + kb * 3);
+          const uint32_t sA = ring_base + static_cast<uint32_t>(stage) * p.stage_bytes;
+          const uint32_t sW = p.wres ? data_base + static_cast<uint32_t>(kb) * p.w_stage_bytes
+                                     : sA + p.a_stage_bytes;
           if (elect_one()) {
-            for (int t = 0; t < p.taps; ++t) {
+            for (int t = 0; t < p.taps && !MSB_CABL(2); ++t) {
               uint64_t ad = adesc0 + ((sA >> 4) + static_cast<uint32_t>(p.off[t] - p.min_off));
               uint64_t bd = bdesc0 + ((sW >> 4) + static_cast<uint32_t>(t * chunks * nth));
               for (int k16 = 0; k16 < nk16; ++k16) {
@@ -174,6 +265,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
             if (kb == p.nkb - 1) umma2_commit_mc(tfull_bar(acc));
           }
           __syncwarp();
+          if (kb < 4) MSB_CTRACE(64, 4 + kb * 3);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -186,7 +278,20 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       // ====================== relay (rank 1): stage landed -> leader ======================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
+      int cur_nt = -1;
+      uint32_t wres_phase = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        if (p.wres) {
+          int nt_idx, mt, b;
+          decode(tile, nt_idx, mt, b);
+          if (nt_idx != cur_nt) {
+            cur_nt = nt_idx;
+            mbar_wait(wres_full, wres_phase);
+            wres_phase ^= 1u;
+            if (elect_one()) mbar_arrive_remote(wres_pfull, 0);
+            __syncwarp();
+          }
+        }
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           if (elect_one()) mbar_arrive_remote(pfull_bar(stage), 0);
@@ -201,17 +306,18 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   } else {
     // =============================== epilogue ===============================
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;   // column slice of this warp
     int acc = 0;
     uint32_t acc_phase = 0;
     const int cout8 = p.cout >> 3;
     const int ngroups = p.NT >> 4;
-    for (int tile = cluster_id; tile < p.total_tiles; tile += nclusters) {
-      const int nt_idx = tile % p.nnt;
-      const int rest = tile / p.nnt;
-      const int mt = rest % p.mtiles;
-      const int b = rest / p.mtiles;
+    int ti = -1;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      ++ti;
+      int nt_idx, mt, b;
+      decode(tile, nt_idx, mt, b);
       const int n0 = nt_idx * p.NT;
+      if (warp == 2) MSB_CTRACE(128, 0);
       {
         const int et = threadIdx.x - 64;
         float* tb = s_bias + (acc & 1) * 256;
@@ -237,7 +343,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       if (p.res32 != nullptr && p.kind == MS_CONV && m < p.Lm) {
         // residual rows of this tile into L2 while the MMAs still run: the epilogue is
         // latency-bound on these loads (8 warps, one 32-byte vector per thread per chunk)
-        for (int g = 2 * half; g < ngroups; g += 4) {
+        for (int g = 2 * half; g < ngroups; g += 2 * kPairEpiSlices) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             const int cidx = g * 2 + h;
@@ -247,18 +353,20 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
       }
+      if (warp == 2) MSB_CTRACE(128, 1);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (warp == 2) MSB_CTRACE(128, 2);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                              static_cast<uint32_t>(acc * p.NT);
       bool arrived = false;
-      for (int g = 2 * half; g < ngroups; g += 4) {
+      for (int g = 2 * half; g < ngroups; g += 2 * kPairEpiSlices) {
         const bool two = (g + 1) < ngroups;
         // the residual vectors of this group's (up to four) chunks are requested BEFORE the
         // accumulator is read: four independent loads in flight per thread instead of one L2
         // round trip per chunk (the loads used to sit between the stores of consecutive chunks)
         float r8[4][8];
-        if (p.res32 != nullptr) {
+        if (p.res32 != nullptr && !MSB_CABL(4)) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
             if (h >= 2 && !two) break;
@@ -270,12 +378,20 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         uint32_t v[32];
-        tmem_ld16p(taddr + g * 16, &v[0]);
-        if (two) tmem_ld16p(taddr + (g + 1) * 16, &v[16]);
-        tmem_ld_wait();
-        if (g + 4 >= ngroups) {
+        if (MSB_CABL(8)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = static_cast<uint32_t>(m + j);
+        } else {
+          tmem_ld16p(taddr + g * 16, &v[0]);
+          if (two) tmem_ld16p(taddr + (g + 1) * 16, &v[16]);
+          tmem_ld_wait();
+        }
+        if (g + 2 * kPairEpiSlices >= ngroups) {
           tc_fence_before();
-          if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote_relaxed(tempty_bar(acc), 0);
+          }
           arrived = true;
         }
 #pragma unroll
@@ -286,7 +402,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           const int ch = rc.y;
           const int orow = (p.kind == MS_CONVT) ? p.stride * m + rc.x - p.pad : m;
           const bool valid = (m < p.Lm) && orow >= 0 && orow < p.Lout;
-          if (!valid) continue;
+          if (!valid || MSB_CABL(16)) continue;
           float f[8];
           {
             const float4 b0 = *reinterpret_cast<const float4*>(tbias + cidx * 8);
@@ -313,6 +429,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = leaky02(f[j]);
           }
+          if (MSB_CABL(1)) continue;
           if (p.y32 != nullptr) st_global_v8(p.y32 + idx * 8, f);
           if (p.y16 != nullptr) {
             uint4 o;
@@ -326,8 +443,12 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
       }
       if (!arrived) {
         tc_fence_before();
-        if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote_relaxed(tempty_bar(acc), 0);
+        }
       }
+      if (warp == 2) MSB_CTRACE(128, 3);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }

@@ -289,6 +289,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
       ::"r"(local_bar), "r"(rank)
       : "memory");
 }
+// Same, without release semantics: for hand-offs that publish no memory (an accumulator that
+// has been READ out of tensor memory; tcgen05.wait::ld + fence::before_thread_sync order that).
+// The release form compiles to MEMBAR.ALL.GPU + SYNCS.ARRIVE.RED: it waits for every earlier
+// global store of the thread to reach L2 -- microseconds in a store-heavy epilogue.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t local_bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar), "r"(rank)
+      : "memory");
+}
 // wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
