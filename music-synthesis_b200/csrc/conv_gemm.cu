@@ -51,18 +51,22 @@ static int pick_nt(int ntot) {
 
 long long* g_conv_dbg = nullptr;   // debugging aid (MSB_CONV_ABLATE builds): see ms_debug_set_conv_trace
 
-// MSB_CONV_WRES=0 disables the weight-resident mode of the pair kernel (A/B timing)
+// MSB_CONV_WRES=1 enables the weight-resident mode of the pair kernel.  Off by default: measured
+// on ConvTranspose 256 -> 128 (64 clips) 195.5 vs 199.8 us -- the layer is bound by its output
+// stores, and walking the n-tiles outermost re-reads the input from HBM once per n-tile
+// (262 vs 67 MB, ncu) because 600 MB of output stream through L2 in between.
 static bool wres_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MSB_CONV_WRES");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }
 
 bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
   c->wres = 0;
+  c->out_stage = 0;
   if (d.batch <= 0 || d.lin <= 0 || d.cin <= 0 || d.cout <= 0) return false;
   if (d.cin % 16 != 0 || d.cout % 8 != 0) return false;
   if (d.operand != MS_F16 && d.operand != MS_BF16) return false;
@@ -151,7 +155,13 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     const int nth = c->NT / 2;
     c->KB = xcin % 64 == 0 ? 64 : (xcin % 32 == 0 ? 32 : 16);
     auto pstage = [&](int kb) { return (kb / 8) * c->RA * 16 + c->taps * (kb / 8) * nth * 16; };
-    const int pbudget = kSmemBudget - kSmemHeader;
+    // ConvTranspose with >= 4 phases: a thread's four phases of a channel block are 128
+    // contiguous output bytes, but neighbouring threads are stride*32 bytes apart -- direct
+    // stores touch 32 lines per instruction (measured: the k16 s8 upsamplers drained their fp32
+    // output at ~12 B/clk per SM).  Their epilogue goes through a per-warp staging tile.
+    c->out_stage = (d.kind == MS_CONVT && d.stride % 4 == 0 && c->NT % 32 == 0 && !fold)
+                       ? kPairEpiWarps * kPairStageWarp : 0;
+    const int pbudget = kSmemBudget - kSmemHeader - c->out_stage;
     while (pstage(c->KB) * 3 > pbudget && c->KB > 16) c->KB /= 2;
     if (pstage(c->KB) * 2 > pbudget) return false;
     c->nnt = c->Ntot / c->NT;
@@ -167,7 +177,7 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     int pcols = 32;
     while (pcols < 2 * c->NT) pcols *= 2;
     c->tmem_cols = pcols;
-    size_t psmem = kSmemHeader + static_cast<size_t>(c->stages) * c->stage_bytes;
+    size_t psmem = kSmemHeader + c->out_stage + static_cast<size_t>(c->stages) * c->stage_bytes;
     if (psmem < 120 * 1024) psmem = 120 * 1024;
     c->smem_bytes = psmem;
     c->packed_weight_bytes = static_cast<size_t>(c->nnt) * 2 * c->nkb * c->w_stage_bytes;
@@ -184,7 +194,7 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
         c->wres = 1;
         c->stage_bytes = a_stage;
         c->stages = as > kMaxStages ? kMaxStages : as;
-        c->smem_bytes = kSmemHeader + static_cast<size_t>(slice) +
+        c->smem_bytes = kSmemHeader + c->out_stage + static_cast<size_t>(slice) +
                         static_cast<size_t>(c->stages) * c->stage_bytes;
       }
     }
@@ -192,6 +202,7 @@ bool make_conv_cfg(const ms_conv_desc& d, ConvCfg* c) {
     // folded tiles run on the single-CTA kernel: the pair layout IS a single-CTA layout with
     // n-tiles of half the width, so the packed image stays the same for every length
     c->pair = 0;
+    c->out_stage = 0;
     c->NT = nth;
     c->nnt = 2 * c->nnt;
     return apply_fold();
@@ -254,7 +265,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int operand) {
 // drain of a 128 x 256 accumulator took ~7.6 k cycles against 4.6 k cycles of MMAs per tile: the
 // epilogue is a dependent FFMA/FMNMX chain per element, and two warps cannot fill a scheduler
 // (tools/pair_trace.py; the stack kernels run 16 as well)
-constexpr int kConvEpiWarps = 16;
+constexpr int kConvEpiWarps = 8;
 constexpr int kConvEpiSlices = kConvEpiWarps / 4;
 constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;
 
@@ -763,7 +774,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   for (int t = 0; t < kMaxTaps; ++t) p.off[t] = t < c.taps ? c.off[t] : 0;
   p.min_off = c.min_off; p.RA = c.RA;
   p.Ntot = c.Ntot; p.NT = c.NT; p.KB = c.KB; p.nnt = c.nnt; p.nkb = c.nkb;
-  p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages; p.pair = c.pair; p.wres = c.wres;
+  p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages; p.pair = c.pair; p.wres = c.wres; p.out_stage = c.out_stage;
   p.debug = 0;
   p.dbg = nullptr;
 #ifdef MSB_CONV_ABLATE

@@ -11,6 +11,9 @@ constexpr int kMaxTaps = 32;   // k41 stride-2 convs: 21 taps over space-to-dept
 constexpr int kMaxStages = 8;
 constexpr int kSmemHeader = 3072;          // barriers [0,512) | bias tables [512,2560) | index tables [2560,3072)
 constexpr int kSmemBudget = 227 * 1024;    // max dynamic smem per CTA on sm_100
+constexpr int kPairEpiWarps = 8;
+constexpr int kPairStageRow = 144;         // staged fp32 row: 4 phases x 32 B + 16 B (bank spread)
+constexpr int kPairStageWarp = 32 * kPairStageRow;   // per epilogue warp
 
 // Tile configuration + derived geometry, a pure function of the descriptor so that
 // weight packing and the forward launch always agree.
@@ -18,6 +21,8 @@ struct ConvCfg {
   int taps;            // GEMM taps (MS_CONV: ksize; MS_CONVT: ksize / stride)
   int off[kMaxTaps];   // input row of tap t for GEMM row m is m + off[t]
   int pair;            // 1: CTA-pair kernel (cta_group::2, 256-row cluster tile, W split)
+  int out_stage;       // bytes of epilogue staging (pair kernel, ConvTranspose with stride % 4 == 0:
+                       // outputs go through shared memory so that every store covers whole lines)
   int wres;            // 1 (pair kernel): the n-tile's weight slice stays resident in shared memory
                        // and only activations stream through the stage ring
   int MBLK;            // 128-row M-blocks per CTA tile (1 or 2): they share each W stage
@@ -67,7 +72,7 @@ struct ConvGemmParams {
   int taps;
   int off[kMaxTaps];
   int min_off, RA;
-  int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages, pair, wres;
+  int Ntot, NT, KB, nnt, nkb, mtiles, MBLK, acc_stages, pair, wres, out_stage;
   int fold_slots, fold_stride, btiles;
   int stages, a_stage_bytes, w_stage_bytes, stage_bytes, tmem_cols;
   int kind, stride, pad, leaky, operand;

@@ -37,11 +37,7 @@ namespace msb {
 #define MSB_CTRACE(base, k) do { } while (0)
 #endif
 
-// 16 epilogue warps = four column slices per TMEM lane quarter.  With 8 (two per scheduler) the
-// drain of a 128 x 256 accumulator took ~7.6 k cycles against 4.6 k cycles of MMAs per tile: the
-// epilogue is a dependent FFMA/FMNMX chain per element, and two warps cannot fill a scheduler
-// (tools/pair_trace.py; the stack kernels run 16 as well)
-constexpr int kPairEpiWarps = 16;
+// (16 epilogue warps were tried: no gain -- the drain is bound by the store path, not by issue)
 constexpr int kPairEpiSlices = kPairEpiWarps / 4;
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 
@@ -62,7 +58,9 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
   float* s_bias = reinterpret_cast<float*>(smem + 512);             // [2][256]
   int2* s_tab = reinterpret_cast<int2*>(smem + 512 + 2048);   // [2][32]
   const uint32_t bar_base = smem_u32(bars);
-  const uint32_t data_base = smem_u32(smem + kSmemHeader);
+  // [header][epilogue staging (ConvTranspose)][resident weights (wres)][stage ring]
+  const uint32_t stage_out_base = smem_u32(smem + kSmemHeader);
+  const uint32_t data_base = stage_out_base + static_cast<uint32_t>(p.out_stage);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
   auto pfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
@@ -183,7 +181,10 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           fence_proxy_async_smem();
           __syncwarp();
         }
-        if (elect_one()) {
+        // lane 0 announces the bytes (and streams the weight stage); the activation copies, one
+        // per 16-byte channel chunk, are issued by as many lanes in parallel (one lane issuing
+        // all of them took ~1000 cycles per stage: tools/pair_trace.py)
+        if (lane == 0) {
           const uint32_t bytes_a = static_cast<uint32_t>(nrows) * 16u * chunks;
           mbar_arrive_expect_tx(full_bar(stage), bytes_a + (p.wres ? 0u : p.w_stage_bytes));
           if (!p.wres) {
@@ -192,13 +193,14 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
                 ((static_cast<size_t>(nt_idx) * 2 + rank) * p.nkb + kb) * p.w_stage_bytes;
             bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
           }
-          if (nrows > 0) {
-            const size_t cbase = static_cast<size_t>(b) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
-            for (int c = 0; c < chunks; ++c) {
-              const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
-              bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,
-                       static_cast<uint32_t>(nrows) * 16u, full_bar(stage));
-            }
+        }
+        __syncwarp();
+        if (nrows > 0) {
+          const size_t cbase = static_cast<size_t>(b) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
+          for (int c = lane; c < chunks; c += 32) {
+            const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
+            bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,
+                     static_cast<uint32_t>(nrows) * 16u, full_bar(stage));
           }
         }
         __syncwarp();
@@ -393,6 +395,89 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
             if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote_relaxed(tempty_bar(acc), 0);
           }
           arrived = true;
+        }
+        if (p.out_stage != 0 && two) {
+          // ---- ConvTranspose, staged: the four chunks are phases ph0 .. ph0+3 of one channel
+          //      block = 128 contiguous fp32 output bytes of this thread's input-rate row
+          const int2 rc0 = ttab[g * 2];
+          const int cb = rc0.y >> 3, ph0 = rc0.x;
+          float f[4][8];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int cidx = g * 2 + h;
+            const float4 b0 = *reinterpret_cast<const float4*>(tbias + cidx * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(tbias + cidx * 8 + 4);
+            f[h][0] = fmaf(__uint_as_float(v[h * 8 + 0]), p.alpha, b0.x);
+            f[h][1] = fmaf(__uint_as_float(v[h * 8 + 1]), p.alpha, b0.y);
+            f[h][2] = fmaf(__uint_as_float(v[h * 8 + 2]), p.alpha, b0.z);
+            f[h][3] = fmaf(__uint_as_float(v[h * 8 + 3]), p.alpha, b0.w);
+            f[h][4] = fmaf(__uint_as_float(v[h * 8 + 4]), p.alpha, b1.x);
+            f[h][5] = fmaf(__uint_as_float(v[h * 8 + 5]), p.alpha, b1.y);
+            f[h][6] = fmaf(__uint_as_float(v[h * 8 + 6]), p.alpha, b1.z);
+            f[h][7] = fmaf(__uint_as_float(v[h * 8 + 7]), p.alpha, b1.w);
+            if (p.leaky == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[h][j] = leaky02(f[h][j]);
+            }
+            if (p.res32 != nullptr) {
+              const int orow = p.stride * m + ph0 + h - p.pad;
+              if ((m < p.Lm) && orow >= 0 && orow < p.Lout) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[h][j] += r8[h][j];
+              }
+            }
+            if (p.leaky == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[h][j] = leaky02(f[h][j]);
+            }
+          }
+          if (MSB_CABL(1)) continue;
+          const uint32_t sst = stage_out_base + static_cast<uint32_t>(warp - 2) * kPairStageWarp;
+          const int m0 = m - lane;                       // row of lane 0
+          const size_t plane = (static_cast<size_t>(b) * cout8 + cb) * p.Lout;
+          if (p.y32 != nullptr) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const uint32_t a = sst + static_cast<uint32_t>(lane * kPairStageRow + h * 32);
+              st_shared_v4(a, __float_as_uint(f[h][0]), __float_as_uint(f[h][1]),
+                           __float_as_uint(f[h][2]), __float_as_uint(f[h][3]));
+              st_shared_v4(a + 16, __float_as_uint(f[h][4]), __float_as_uint(f[h][5]),
+                           __float_as_uint(f[h][6]), __float_as_uint(f[h][7]));
+            }
+            __syncwarp();
+            // read back transposed: eight lanes cover one row's 128 bytes, one instruction
+            // writes four whole lines
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + (lane >> 3), p8 = lane & 7;
+              const int orow = p.stride * (m0 + r) + ph0 + (p8 >> 1) - p.pad;
+              if ((m0 + r) < p.Lm && orow >= 0 && orow < p.Lout) {
+                const uint4 qv = ld_shared_v4(sst + static_cast<uint32_t>(r * kPairStageRow + p8 * 16));
+                *reinterpret_cast<uint4*>(p.y32 + (plane + orow) * 8 + (p8 & 1) * 4) = qv;
+              }
+            }
+            __syncwarp();
+          }
+          if (p.y16 != nullptr) {
+            // 16-bit image: 64 bytes per row, rows of 80 bytes in the staging tile
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+              st_shared_v4(sst + static_cast<uint32_t>(lane * 80 + h * 16),
+                           pack2p(f[h][0], f[h][1], p.operand), pack2p(f[h][2], f[h][3], p.operand),
+                           pack2p(f[h][4], f[h][5], p.operand), pack2p(f[h][6], f[h][7], p.operand));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = 8 * i + (lane >> 2), p4 = lane & 3;
+              const int orow = p.stride * (m0 + r) + ph0 + p4 - p.pad;
+              if ((m0 + r) < p.Lm && orow >= 0 && orow < p.Lout) {
+                const uint4 qv = ld_shared_v4(sst + static_cast<uint32_t>(r * 80 + p4 * 16));
+                *reinterpret_cast<uint4*>(p.y16 + (plane + orow) * 8) = qv;
+              }
+            }
+            __syncwarp();
+          }
+          continue;
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
