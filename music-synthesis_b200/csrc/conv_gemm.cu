@@ -635,86 +635,105 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 // Reads the SAME packed 16-bit weights / 16-bit activations as the main GEMM, accumulates in
 // fp32.  Tiny: at most (J-1)*stride*cout outputs per clip.  blockIdx.y = e * stride + r.
 constexpr int kTailSlices = 8;    // lanes that share one output: each takes every 8th channel chunk
+constexpr int kTailClips = 8;     // clips per block: a weight vector is loaded once for all of them
 __global__ void __launch_bounds__(128)
 convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */,
                   int nnt_p /* packed n-tiles */) {
   const int e = blockIdx.y / p.stride;      // tail row
   const int r = blockIdx.y - e * p.stride;  // phase
-  const int b = blockIdx.z;
-  // 16 outputs per block x 8 channel slices (the input-channel loop was 64 dependent L2 round
-  // trips per thread at cin = 512: 40 us for a few thousand outputs)
+  const int b0 = blockIdx.z * kTailClips;
+  // 16 outputs per block x 8 channel slices x 8 clips.  Each output is a dot product over
+  // cin * (taps - 1 - e) elements: the first versions streamed its 16-bit weights once per CLIP
+  // (64 x 2 MB through L2 for the 512 -> 256 upsampler: 37 us for 134 MFLOP); now a thread keeps
+  // a batch of weight vectors in registers and walks the block's clips.
   const int slice = threadIdx.x & (kTailSlices - 1);
   const int co = blockIdx.x * (128 / kTailSlices) + (threadIdx.x >> 3);
   const int orow = p.stride * (p.lin + e) + r - p.pad;
   const bool live = co < p.cout && orow >= 0 && orow < p.Lout;   // warp-uniform enough: shuffles below
-  float acc = 0.f;
+  float acc[kTailClips];
+#pragma unroll
+  for (int cl = 0; cl < kTailClips; ++cl) acc[cl] = 0.f;
   if (live) {
     const int n = convt_col(r, co, p.stride);   // GEMM column
     const int nt = n / ntp, nn = n - nt * ntp;
     const int chunks = p.KB >> 3;
     const int xc8 = p.xcin >> 3;
+    const int nch = p.cin >> 3;
     for (int t = 0; t <= p.taps - 2 - e; ++t) {
       const int xrow = p.lin + e + t - (p.taps - 1);
       if (xrow < 0) continue;
-      // this slice's channel chunks in batches of four: all eight loads of a batch are issued
-      // before the first multiply (the loop used to be one dependent L2 round trip per chunk)
-      const int nch = p.cin >> 3;
       for (int c80 = slice; c80 < nch; c80 += 4 * kTailSlices) {
-        uint4 wq[4], xq[4];
+        uint4 wq[4];
+        size_t xoff[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int c8 = c80 + u * kTailSlices;
           wq[u] = make_uint4(0u, 0u, 0u, 0u);
-          xq[u] = make_uint4(0u, 0u, 0u, 0u);
+          xoff[u] = 0;
           if (c8 < nch) {
             const int ci = c8 * 8;
             const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
             // packed[nt][kb][tap][c][nn][0..7]
             const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
-            const size_t xi = ((static_cast<size_t>(b) * xc8 + c8 % xc8) * p.lin + xrow) * 8;
             wq[u] = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
-            xq[u] = __ldg(reinterpret_cast<const uint4*>(p.x + xi));
+            xoff[u] = (static_cast<size_t>(c8 % xc8) * p.lin + xrow) * 8;
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t ww[4] = {wq[u].x, wq[u].y, wq[u].z, wq[u].w};
-          const uint32_t xx[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+        for (int cl = 0; cl < kTailClips; ++cl) {
+          if (b0 + cl >= p.B) break;
+          const uint16_t* xb = p.x + static_cast<size_t>(b0 + cl) * xc8 * p.lin * 8;
+          uint4 xq[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 wf, xf;
-            if (p.operand == MS_BF16) {
-              wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
-              xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
-            } else {
-              wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
-              xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+          for (int u = 0; u < 4; ++u) {
+            xq[u] = make_uint4(0u, 0u, 0u, 0u);   // (zero weights beyond the last chunk)
+            if (c80 + u * kTailSlices < nch) xq[u] = __ldg(reinterpret_cast<const uint4*>(xb + xoff[u]));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t ww[4] = {wq[u].x, wq[u].y, wq[u].z, wq[u].w};
+            const uint32_t xx[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 wf, xf;
+              if (p.operand == MS_BF16) {
+                wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+                xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
+              } else {
+                wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+                xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+              }
+              acc[cl] = fmaf(xf.x, wf.x, acc[cl]);
+              acc[cl] = fmaf(xf.y, wf.y, acc[cl]);
             }
-            acc = fmaf(xf.x, wf.x, acc);
-            acc = fmaf(xf.y, wf.y, acc);
           }
         }
       }
     }
   }
-  // fixed-order combination of the 8 slices (lanes slice = 0..7 of one output are adjacent)
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (!live || slice != 0) return;
-  float v = acc * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
-  if (p.leaky == 1) v = leaky02(v);
-  const size_t idx = ((static_cast<size_t>(b) * (p.cout >> 3) + (co >> 3)) * p.Lout + orow) * 8 + (co & 7);
-  if (p.res32 != nullptr) v += p.res32[idx];
-  if (p.leaky == 2) v = leaky02(v);
-  if (p.y32 != nullptr) p.y32[idx] = v;
-  if (p.y16 != nullptr) {
-    if (p.operand == MS_BF16) {
-      __nv_bfloat16 h = __float2bfloat16_rn(v);
-      p.y16[idx] = *reinterpret_cast<uint16_t*>(&h);
-    } else {
-      __half h = __float2half_rn(v);
-      p.y16[idx] = *reinterpret_cast<uint16_t*>(&h);
+#pragma unroll
+  for (int cl = 0; cl < kTailClips; ++cl) {
+    // fixed-order combination of the 8 slices (lanes slice = 0..7 of one output are adjacent)
+    float a = acc[cl];
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    const int b = b0 + cl;
+    if (!live || slice != 0 || b >= p.B) continue;
+    float v = a * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
+    if (p.leaky == 1) v = leaky02(v);
+    const size_t idx = ((static_cast<size_t>(b) * (p.cout >> 3) + (co >> 3)) * p.Lout + orow) * 8 + (co & 7);
+    if (p.res32 != nullptr) v += p.res32[idx];
+    if (p.leaky == 2) v = leaky02(v);
+    if (p.y32 != nullptr) p.y32[idx] = v;
+    if (p.y16 != nullptr) {
+      if (p.operand == MS_BF16) {
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        p.y16[idx] = *reinterpret_cast<uint16_t*>(&h);
+      } else {
+        __half h = __float2half_rn(v);
+        p.y16[idx] = *reinterpret_cast<uint16_t*>(&h);
+      }
     }
   }
 }
@@ -793,7 +812,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
 
   if (d.kind == MS_CONVT) {
     // the rows q >= lin first (independent outputs: the last rows of each clip)
-    dim3 tgrid((d.cout + 15) / 16, (c.taps - 1) * d.stride, d.batch);
+    dim3 tgrid((d.cout + 15) / 16, (c.taps - 1) * d.stride, (d.batch + kTailClips - 1) / kTailClips);
     convt_tail_kernel<<<tgrid, 128, 0, stream>>>(p, c.pair ? c.NT / 2 : c.NT,
                                                  c.pair ? 2 * c.nnt : c.nnt);
     ms_status ts = after_launch("convt_tail_kernel");

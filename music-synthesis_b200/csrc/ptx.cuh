@@ -374,6 +374,13 @@ __device__ __forceinline__ void leaky02x2(float a, float b, float& x, float& y) 
   x = fmaxf(a, t0);
   y = fmaxf(b, t1);
 }
+// (c0, c1) = (a0 * b0 + c0, a1 * b1 + c1): one FFMA2
+__device__ __forceinline__ void fma_x2(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%0, %1};\n\tfma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(c0), "+f"(c1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 __device__ __forceinline__ void add_x2(float a, float b, float c, float d, float& x, float& y) {
   asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
       "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"

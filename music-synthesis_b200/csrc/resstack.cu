@@ -568,8 +568,8 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
 #pragma unroll
                   for (int j4 = 0; j4 < GS / 4; ++j4) {
                     const float4 w4 = *reinterpret_cast<const float4*>(sMono + k * 32 + part * COLS + c0 + j4 * 4);
-                    a0 = fmaf(f[j4 * 4 + 0], w4.x, a0); a1 = fmaf(f[j4 * 4 + 1], w4.y, a1);
-                    a0 = fmaf(f[j4 * 4 + 2], w4.z, a0); a1 = fmaf(f[j4 * 4 + 3], w4.w, a1);
+                    fma_x2(f[j4 * 4 + 0], f[j4 * 4 + 1], w4.x, w4.y, a0, a1);
+                    fma_x2(f[j4 * 4 + 2], f[j4 * 4 + 3], w4.z, w4.w, a0, a1);
                   }
                   pk[k] = a0 + a1;
                 }
