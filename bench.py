@@ -488,12 +488,12 @@ def main():
                 "frac": 6 * 2 * 3 * 128 * 128 * clips * 64 * FRAMES / (us_stack * 1e-6) / 1e12 / pk["burst"],
                 "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
                 "us_per_launch": us_stack,
-                # dram__bytes_read+write of this kernel from profiles/r01_ncu_final_summary.tsv
-                # (776.7 MB per 64-clip launch, scaled to this launch's clip count); the
+                # dram__bytes_read+write of this kernel from profiles/r02_ncu_stacks_summary.tsv
+                # (537.5 + 239.9 MB per 64-clip launch, scaled to this launch's clip count); the
                 # algorithmic bytes are 4C in + 2C out per row = 805 MB per 64 clips
-                "traffic": 776.7e6 * clips / 64,
+                "traffic": 777.4e6 * clips / 64,
                 "traffic_source": "ncu constant (dram__bytes_read+write of this kernel at 64 clips, "
-                                  "profiles/r01_ncu_final_summary.tsv), scaled by clip count; not "
+                                  "profiles/r02_ncu_stacks_summary.tsv), scaled by clip count; not "
                                   "measured in this run",
             },
             # the whole step (15 kernels) against the same roofline: algorithmic generator FLOPs
