@@ -399,6 +399,13 @@ ms_status ms_expand_mono_bwd(const float* de32, float* dx, int batch, int len, i
 ms_status ms_depth_to_space_blk32(const float* dys32, float* dx32, int batch, int channels,
                                   int src_rows, int rows_valid, int row_offset, int out_rows,
                                   int len, int stride, void* stream);
+/* ReflectionPad1d on a plain (rows, len) fp32 tensor, y: (rows, len + 2*pad), and its gradient
+ * (gathers in a fixed order: deterministic).
+ *   replaces nn.ReflectionPad1d(7) of NLayerDiscriminator, experiment/realmelgan.py:98-102. */
+ms_status ms_reflect_pad_ncl(const float* x, float* y, int rows, int len, int pad, void* stream);
+ms_status ms_reflect_pad_ncl_bwd(const float* dy, float* dx, int rows, int len, int pad,
+                                 void* stream);
+
 /* gradient of ms_blk_act_pad on the fp32 stream: dx32[t] = act'(x[t]) * (dy32[t+pad] + the rows that
  * reflect onto t); sign16 = BLK 16-bit image of x (LeakyReLU mask) or NULL (no activation).
  * dy32 BLK f32 (B,C/8,len+2*pad,8), dx32 (B,C/8,len,8). */

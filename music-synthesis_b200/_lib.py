@@ -74,6 +74,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "ms_resstack_tail_fwd": (c_int, [c_int, c_int, POINTER(c_int), c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ms_reflect_pad_ncl": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ms_reflect_pad_ncl_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ms_upstack_supported": (c_int, [c_int]),
     "ms_upstack_packed_weight_bytes": (c_size_t, [c_int]),
     "ms_upstack_pack_weights": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p, c_void_p]),

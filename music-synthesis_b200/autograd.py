@@ -323,6 +323,30 @@ class UnpackBlk32(Function):
         return grad_ops.pack_ncl32(dy)
 
 
+class ReflectPadNCL(Function):
+    """nn.ReflectionPad1d on a (B, C, L) fp32 tensor (experiment/realmelgan.py:98-102): gather
+    forward, fixed-order gather backward."""
+
+    @staticmethod
+    def forward(ctx, x, pad):
+        x = x.contiguous()
+        B, C, L = x.shape
+        y = torch.empty((B, C, L + 2 * pad), dtype=torch.float32, device=x.device)
+        check(_lib.lib().ms_reflect_pad_ncl(ptr(x), ptr(y), B * C, L, pad, stream_ptr()),
+                  "ms_reflect_pad_ncl")
+        ctx.cfg = (B, C, L, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, C, L, pad = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty((B, C, L), dtype=torch.float32, device=dy.device)
+        check(_lib.lib().ms_reflect_pad_ncl_bwd(ptr(dy), ptr(dx), B * C, L, pad, stream_ptr()),
+              "ms_reflect_pad_ncl_bwd")
+        return dx, None
+
+
 class DirectConv(Function):
     """grouped / strided fp32 conv1d (+ LeakyReLU), NCL in / out (discriminator/full.py:13-18)."""
 

@@ -508,6 +508,34 @@ ms_status pack_ncl_to_blk16(const float* x, void* y16, int batch, int channels, 
 
 }  // namespace msb
 
+namespace msb {
+
+__global__ void reflect_pad_ncl_kernel(const float* __restrict__ x, float* __restrict__ y, int len,
+                                       int pad, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int lp = len + 2 * pad;
+  const size_t r = i / lp;
+  int t = static_cast<int>(i - r * lp) - pad;
+  t = t < 0 ? -t : (t >= len ? 2 * (len - 1) - t : t);
+  y[i] = __ldg(x + r * len + t);
+}
+
+__global__ void reflect_pad_ncl_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                           int len, int pad, size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const size_t r = i / len;
+  const int t = static_cast<int>(i - r * len);
+  const float* g = dy + r * (len + 2 * pad);
+  float v = __ldg(g + t + pad);
+  if (t >= 1 && t <= pad) v += __ldg(g + pad - t);                              // left mirror
+  if (t >= len - 1 - pad && t <= len - 2) v += __ldg(g + pad + 2 * (len - 1) - t);   // right mirror
+  dx[i] = v;
+}
+
+}  // namespace msb
+
 using namespace msb;
 
 extern "C" {
@@ -685,6 +713,29 @@ ms_status ms_conv_to_mono(const float* x32, const float* w, const float* bias, f
   if (x32 == nullptr || w == nullptr || y == nullptr) return MS_ERR_INVALID;
   return conv_to_mono(x32, w, bias, y, batch, cin, len, ksize, pad, tanh_out,
                       static_cast<cudaStream_t>(stream));
+}
+
+/* ReflectionPad1d on a plain (rows, len) fp32 tensor and its gradient (both gathers: the
+ * backward sums, in a fixed order, the at most three padded positions that read input sample i).
+ *   replaces nn.ReflectionPad1d(7) in front of NLayerDiscriminator's first conv,
+ *   experiment/realmelgan.py:98-102. */
+ms_status ms_reflect_pad_ncl(const float* x, float* y, int rows, int len, int pad, void* stream) {
+  if (x == nullptr || y == nullptr || rows <= 0 || len <= 1 || pad < 0 || pad >= len)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(rows) * (len + 2 * pad);
+  msb::reflect_pad_ncl_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                                static_cast<cudaStream_t>(stream)>>>(x, y, len, pad, total);
+  return msb::after_launch("reflect_pad_ncl_kernel");
+}
+
+ms_status ms_reflect_pad_ncl_bwd(const float* dy, float* dx, int rows, int len, int pad,
+                                 void* stream) {
+  if (dy == nullptr || dx == nullptr || rows <= 0 || len <= 1 || pad < 0 || pad >= len)
+    return MS_ERR_INVALID;
+  const size_t total = static_cast<size_t>(rows) * len;
+  msb::reflect_pad_ncl_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                                    static_cast<cudaStream_t>(stream)>>>(dy, dx, len, pad, total);
+  return msb::after_launch("reflect_pad_ncl_bwd_kernel");
 }
 
 }  // extern "C"

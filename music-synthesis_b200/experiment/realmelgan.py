@@ -290,9 +290,8 @@ class NLayerDiscriminator(nn.Module):
         results = []
         keys = list(self.model.keys())
         conv0 = self.model["layer_0"][1]
-        # ReflectionPad1d(7) on the 1-channel input: torch data movement (and its scatter backward)
-        h = ag.DirectConv.apply(F.pad(x, (7, 7), mode="reflect"), _wn(conv0), conv0.bias, 1, 0, 1,
-                                True)
+        # ReflectionPad1d(7) on the 1-channel input (ms_reflect_pad_ncl + its gather backward)
+        h = ag.DirectConv.apply(ag.ReflectPadNCL.apply(x, 7), _wn(conv0), conv0.bias, 1, 0, 1, True)
         results.append(h)
         for n in range(1, self.n_layers + 1):
             c = self.model["layer_%d" % n][0]

@@ -224,3 +224,22 @@ def test_strided_weight_view_kernel_both_directions(k, s):
     ref = strided_weight_view_ref(w, s)
     assert (taps, pad) == ops.strided_conv_geometry(k, s) and torch.equal(w1.cpu(), ref)
     assert torch.equal(ops.strided_conv_weight_grad(w1, tuple(w.shape), s).cpu(), w)
+
+
+@pytest.mark.parametrize("B,C,L,pad", [(2, 1, 300, 7), (1, 3, 16, 7), (3, 2, 9, 8)])
+def test_reflect_pad_ncl_forward_and_backward(B, C, L, pad):
+    """nn.ReflectionPad1d on a plain NCL tensor (NLayerDiscriminator's first layer,
+    experiment/realmelgan.py:98-102): forward and gradient against torch, bit for bit."""
+    from music_synthesis_b200 import autograd as ag
+    x = randn(90, B, C, L)
+    g = randn(91, B, C, L + 2 * pad)
+    with torch.enable_grad():
+        xr = x.clone().requires_grad_(True)
+        F.pad(xr, (pad, pad), mode="reflect").backward(g)
+        xd = x.cuda().requires_grad_(True)
+        y = ag.ReflectPadNCL.apply(xd, pad)
+        y.backward(g.cuda())
+    assert torch.equal(y.detach().cpu(), F.pad(x, (pad, pad), mode="reflect"))
+    # the three contributions are summed in a fixed order; torch's scatter order may differ in the
+    # last bit where two mirrors meet
+    assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=0, atol=1e-6)
