@@ -277,6 +277,18 @@ ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes
                                      int batch, int desired_size, float* out, void* workspace,
                                      size_t workspace_bytes, void* stream);
 
+/* Gradients of the band split / merge (training with decompose=True / recompose=True,
+ * generator/multiscale.py:166-178, discriminator/multiscale.py:212-252).  The merge is the adjoint
+ * of the split and vice versa up to one bin per band (bin S/2: Nyquist of the S-point transform,
+ * interior of the n-point one), a rank-1 term these calls apply IN PLACE:
+ *   d(split)/dx^T g  = ms_fft_frequency_recompose(g)   then ms_fft_decompose_adjoint_fix(g, .., dx)
+ *   d(merge)/db^T g  = ms_fft_frequency_decompose(g)   then ms_fft_recompose_adjoint_fix(g, .., db)
+ * `dbands` / `sizes` are HOST arrays; rows = batch * channels; reductions in a fixed order. */
+ms_status ms_fft_decompose_adjoint_fix(const float* const* dbands, const int* sizes, int nbands,
+                                       int batch, int n, float* dx, void* stream);
+ms_status ms_fft_recompose_adjoint_fix(const float* dy, int batch, int n, float* const* dbands,
+                                       const int* sizes, int nbands, void* stream);
+
 /* ---------------------------------------------------------------------------
  * GAN loss reductions (forward), deterministic (no atomics).
  *   replaces featuresynth/loss/loss.py:5-79.  out[0] (+)= weight * L(a, b) with

@@ -86,6 +86,10 @@ SIGNATURES = {
                                            c_void_p, c_size_t, c_void_p]),
     "ms_fft_frequency_recompose": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int,
                                            c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ms_fft_decompose_adjoint_fix": (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int,
+                                             c_void_p, c_void_p]),
+    "ms_fft_recompose_adjoint_fix": (c_int, [c_void_p, c_int, c_int, POINTER(c_void_p),
+                                             POINTER(c_int), c_int, c_void_p]),
     "ms_reduce_workspace_bytes": (c_size_t, []),
     "ms_reduce_fwd": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_int,
                               c_void_p, c_void_p]),

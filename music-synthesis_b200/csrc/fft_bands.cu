@@ -402,4 +402,129 @@ ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes
   return after_launch("complex_real_part_kernel");
 }
 
+/* ---- exact adjoints (training with decompose=True / recompose=True) ----
+ * With orthonormal transforms the band merge is the adjoint of the band split and vice versa,
+ * except at ONE bin per band: bin S/2 is the Nyquist bin of the S-point real transform (weight 1
+ * in its adjoint) but an interior bin of the n-point one (weight 1/2 resp. 2).  The difference is a
+ * rank-1 term per band with S < n (derivation and numerical check: DESIGN.md section 5.4):
+ *   split^T(g)[u]   = merge(g)[u]   - sum_S cos(pi S u / n) * (sum_t (-1)^t g_S[t]) / sqrt(n S)
+ *   merge^T(g)_S[t] = split(g)_S[t] + (-1)^t * (sum_u g[u] cos(pi S u / n)) / sqrt(n S)
+ * One block per row; reductions in a fixed order (deterministic). */
+}  // extern "C"
+
+namespace msb {
+namespace {
+
+constexpr int kMaxAdjBands = 12;
+struct AdjBands {
+  float* ptr[kMaxAdjBands];
+  int size[kMaxAdjBands];
+  int nbands;
+};
+
+// sum over the block of v, fixed order; result valid in every thread
+__device__ __forceinline__ float block_sum_fixed(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += sh[w];
+  return t;
+}
+
+__device__ __forceinline__ float cos_band(int u, int S, int n) {
+  // cos(pi * S * u / n), S and n powers of two: reduce u modulo the period 2n/S exactly
+  const int period = 2 * (n / S);
+  return cospif(static_cast<float>(u & (period - 1)) * (static_cast<float>(S) / static_cast<float>(n)));
+}
+
+__global__ void __launch_bounds__(256)
+split_adjoint_fix_kernel(AdjBands bands, float* __restrict__ dx, int n) {
+  __shared__ float sh[8];
+  __shared__ float coef[kMaxAdjBands];
+  const size_t row = blockIdx.x;
+  for (int i = 0; i < bands.nbands; ++i) {
+    const int S = bands.size[i];
+    float a = 0.f;
+    if (S < n) {
+      const float* g = bands.ptr[i] + row * S;
+      for (int t = threadIdx.x; t < S; t += blockDim.x) a += (t & 1) ? -g[t] : g[t];
+    }
+    a = block_sum_fixed(a, sh);
+    if (threadIdx.x == 0)
+      coef[i] = S < n ? a / (sqrtf(static_cast<float>(n)) * sqrtf(static_cast<float>(S))) : 0.f;
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < n; u += blockDim.x) {
+    float c = 0.f;
+    for (int i = 0; i < bands.nbands; ++i)
+      if (bands.size[i] < n) c += coef[i] * cos_band(u, bands.size[i], n);
+    dx[row * n + u] -= c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+merge_adjoint_fix_kernel(AdjBands bands, const float* __restrict__ dy, int n) {
+  __shared__ float sh[8];
+  __shared__ float coef[kMaxAdjBands];
+  const size_t row = blockIdx.x;
+  const float* g = dy + row * n;
+  for (int i = 0; i < bands.nbands; ++i) {
+    const int S = bands.size[i];
+    float a = 0.f;
+    if (S < n)
+      for (int u = threadIdx.x; u < n; u += blockDim.x) a += g[u] * cos_band(u, S, n);
+    a = block_sum_fixed(a, sh);
+    if (threadIdx.x == 0)
+      coef[i] = S < n ? a / (sqrtf(static_cast<float>(n)) * sqrtf(static_cast<float>(S))) : 0.f;
+  }
+  __syncthreads();
+  for (int i = 0; i < bands.nbands; ++i) {
+    const int S = bands.size[i];
+    if (S >= n) continue;
+    float* d = bands.ptr[i] + row * S;
+    const float c = coef[i];
+    for (int t = threadIdx.x; t < S; t += blockDim.x) d[t] += (t & 1) ? -c : c;
+  }
+}
+
+bool fill_adj(AdjBands* a, float* const* ptrs, const int* sizes, int nbands, int n) {
+  if (ptrs == nullptr || sizes == nullptr || nbands <= 0 || nbands > kMaxAdjBands) return false;
+  if (n <= 0 || (n & (n - 1)) != 0) return false;
+  a->nbands = nbands;
+  for (int i = 0; i < nbands; ++i) {
+    if (ptrs[i] == nullptr || sizes[i] <= 1 || (sizes[i] & (sizes[i] - 1)) != 0 || sizes[i] > n)
+      return false;
+    a->ptr[i] = ptrs[i];
+    a->size[i] = sizes[i];
+  }
+  return true;
+}
+
+}  // namespace
+}  // namespace msb
+
+extern "C" {
+
+ms_status ms_fft_decompose_adjoint_fix(const float* const* dbands, const int* sizes, int nbands,
+                                       int batch, int n, float* dx, void* stream) {
+  msb::AdjBands a;
+  if (batch <= 0 || dx == nullptr ||
+      !msb::fill_adj(&a, const_cast<float* const*>(dbands), sizes, nbands, n))
+    return MS_ERR_INVALID;
+  msb::split_adjoint_fix_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dx, n);
+  return msb::after_launch("split_adjoint_fix_kernel");
+}
+
+ms_status ms_fft_recompose_adjoint_fix(const float* dy, int batch, int n, float* const* dbands,
+                                       const int* sizes, int nbands, void* stream) {
+  msb::AdjBands a;
+  if (batch <= 0 || dy == nullptr || !msb::fill_adj(&a, dbands, sizes, nbands, n))
+    return MS_ERR_INVALID;
+  msb::merge_adjoint_fix_kernel<<<batch, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, dy, n);
+  return msb::after_launch("merge_adjoint_fix_kernel");
+}
+
 }  // extern "C"

@@ -220,9 +220,8 @@ class FilterBankMultiScaleDiscriminator(nn.Module):
     def forward(self, x, feat):
         probe = x if isinstance(x, torch.Tensor) else next(iter(x.values()))
         if ag.needs_grad(self, probe):
-            if self.decompose:
-                raise MsbError("training with decompose=True is not on this path (the experiment "
-                               "feeds band dictionaries: experiment/multiscale.py:42-46)")
+            if self.decompose:     # differentiable band split (discriminator/multiscale.py:212-216)
+                x = fft_frequency_decompose(x, self.smallest_band)
             return self._forward_train(x, feat)
         bands = fft_frequency_decompose(x, self.smallest_band) if self.decompose else x
         cond = self.conditioning_channels > 0
@@ -413,9 +412,8 @@ class MultiScaleDiscriminator(nn.Module):
     def forward(self, x, feat):
         probe = x if isinstance(x, torch.Tensor) else next(iter(x.values()))
         if ag.needs_grad(self, probe):
-            if self.decompose:
-                raise MsbError("training with decompose=True (FFT band split in the graph) is not "
-                               "on this path; feed band dictionaries (decompose=False)")
+            if self.decompose:     # differentiable band split (discriminator/multiscale.py:395-397)
+                x = fft_frequency_decompose(x, self.smallest_band)
             return self._forward_train(x, feat)
         bands = fft_frequency_decompose(x, self.smallest_band) if self.decompose else x
         cond = self.conditioning_channels > 0

@@ -291,15 +291,14 @@ class MultiScaleGenerator(nn.Module):
     def _forward_train(self, x):
         if x.requires_grad:
             raise MsbError("gradients w.r.t. the conditioning features are not on this path")
-        if self.recompose:
-            raise MsbError("training with recompose=True (FFT band merge in the graph) is not on "
-                           "this path; the MultiScale experiments train on band dictionaries "
-                           "(experiment/multiscale.py:120-160)")
         x16 = ops.pack_ncl(x, 3, 1)
         e32, e16 = ag.conv_blk(None, x16, self.embedding.weight, self.embedding.bias, self._ce,
                                     MS_CONV, 1, 0, 1, True)
-        return {size: layer.forward_blocked_train(e32, e16)
-                for size, layer in self.channel_generators.items()}
+        results = {size: layer.forward_blocked_train(e32, e16)
+                   for size, layer in self.channel_generators.items()}
+        if self.recompose:      # differentiable band merge (generator/multiscale.py:248-251)
+            return fft_frequency_recompose(results, x.shape[-1] * self.upsample_ratio)
+        return results
 
     def forward(self, x):
         if ag.needs_grad(self, x):
