@@ -485,7 +485,7 @@ def main():
             # dominant kernel (largest single launch of the step), timed alone with CUDA
             # events above; algorithmic FLOPs = 6 convs x 2*3*128^2 per output row.
             "roofline": {
-                "bound": "tensor", "kernel": "resstack_kernel<128> (fused ResidualStack, stage 2)",
+                "bound": "tensor", "kernel": "resstack_pair_kernel<128> (fused ResidualStack, stage 2, CTA pairs)",
                 "achieved": 6 * 2 * 3 * 128 * 128 * clips * 64 * FRAMES / (us_stack * 1e-6) / 1e12,
                 "peak": pk["burst"], "unit": "TFLOP/s",
                 "frac": 6 * 2 * 3 * 128 * 128 * clips * 64 * FRAMES / (us_stack * 1e-6) / 1e12 / pk["burst"],

@@ -214,7 +214,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
     for (int tile = tile_first; pair_has_work(tile); tile += tile_stride) {
       for (int tap = 0; tap < 18; ++tap, ++pos) {
         mbar_wait(wfull(pos % NSLOT), (pos / NSLOT) & 1u);
-        if (elect_one()) mbar_arrive_remote(pwfull(pos % NSLOT), 0);
+        if (elect_one()) mbar_arrive_remote_relaxed(pwfull(pos % NSLOT), 0);
         __syncwarp();
       }
     }
@@ -357,7 +357,10 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
       __syncwarp();
       if (lane == 0) {
         if (!PAIR || leader) mbar_arrive(act_ready(h));
-        else mbar_arrive_remote(act_ready(h), 0);
+        // the rows this arrival publishes live in THIS CTA's shared / tensor memory and were
+        // made visible to the async proxy by fence.proxy.async + tcgen05 fence above; only the
+        // signal crosses CTAs.  (The release.cluster form costs a MEMBAR.ALL.GPU per warp.)
+        else mbar_arrive_remote_relaxed(act_ready(h), 0);
       }
     };
     // accumulator columns [ta, ta + COLS) <- bias of conv l (the MMAs of conv l accumulate)
@@ -670,14 +673,18 @@ resstack_pair_kernel(const __grid_constant__ StackParams p) {
   resstack_body<C, true, false>(p);
 }
 
-// MSB_STACK_PAIR=1 enables the CTA-pair variant (process-wide, read once).  Off by default:
-// measured on B200 at B=256, L=16384 it is 8 % slower (2861 vs 2650 us) -- the cross-CTA
-// hand-offs cost more than the halved B-operand traffic buys.
+// CTA-pair variant for C = 128 (default; MSB_STACK_PAIR=0 selects the single-CTA kernel).  Each CTA
+// stages half of every tap, so the 96 KB ring holds two convs of weights instead of one and the
+// tensor core reads 6 KB instead of 8 KB of operands per MMA -- the single-CTA kernel is bound by
+// the shared-memory port.  Round 1 measured the pair form 8 % slower; the cause was the
+// release.cluster form of the remote act_ready arrivals (a MEMBAR.ALL.GPU per epilogue warp and
+// hand-off, ~1.2 k cycles on the critical path of every conv).  With relaxed remote arrivals and the
+// two-issuer scheme: 579 vs 614 us at 64 clips (tools/stack_bench.py).  fp16 operands only.
 bool stack_pair_enabled(int channels) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MSB_STACK_PAIR");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v == 1 && channels == 128;
 }
@@ -841,7 +848,7 @@ ms_status ms_resstack_pack_weights(const float* const* params, int channels, int
   for (int l = 0; l < 6; ++l) {
     pack_stack_weight_kernel<<<(total + 255) / 256, 256, 0, st>>>(
         params[2 * l], reinterpret_cast<uint16_t*>(base + l * conv_bytes), channels, operand,
-        stack_pair_enabled(channels) ? 1 : 0);
+        (stack_pair_enabled(channels) && operand != MS_BF16) ? 1 : 0);
     ms_status s = after_launch("pack_stack_weight_kernel");
     if (s != MS_OK) return s;
     s = check_cuda(cudaMemcpyAsync(bias + l * channels, params[2 * l + 1],

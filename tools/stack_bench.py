@@ -6,7 +6,7 @@ from music_synthesis_b200 import ops
 from oracle import synth
 
 B = int(os.environ.get("B", "256"))
-print("MSB_STACK_PAIR=%s" % os.environ.get("MSB_STACK_PAIR", "1"))
+print("MSB_STACK_PAIR=%s" % os.environ.get("MSB_STACK_PAIR", "1 (default)"))
 for C, L in ((128, 16384), (64, 32768), (32, 65536)):
     sd = synth.residual_stack_state(1, C)
     params = []
