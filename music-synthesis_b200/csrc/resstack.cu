@@ -97,7 +97,7 @@ struct StackGeom {
   static constexpr int P_BYTES = (C == 32) ? 14 * R * 4 : 0;
   // fold the next tile's prologue into the last conv's epilogue (needs COLS + 2 x 16 live
   // registers per row: fits the 96-register budget of 18-warp CTAs only at 16 columns per thread)
-  static constexpr bool MERGE_PROLOGUE = (C == 32);
+  static constexpr bool MERGE_PROLOGUE = (C == 32);   // C = 64 / 128 (two 16-column groups per row): measured slower (spills + a second exposed load)
   static constexpr int SMEM = kStackHeader + 2 * ACT_BYTES + NSLOT * TAP_BYTES + MONO_BYTES + P_BYTES;
   // producer, MMA issuer A, epilogue warps, MMA issuer B (single-CTA kernels only)
   static constexpr int THREADS = 64 + 32 * EW + 32;
@@ -364,10 +364,11 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
       }
     };
     // accumulator columns [ta, ta + COLS) <- bias of conv l (the MMAs of conv l accumulate)
-    auto store_bias = [&](int l, uint32_t ta) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + l * C + part * COLS);
+    // accumulator columns [ta + c0, ta + c0 + n) <- bias of conv l (n a multiple of 16)
+    auto store_bias_cols = [&](int l, uint32_t ta, int c0, int n) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + l * C + part * COLS + c0);
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
+      for (int g = 0; g < n / 16; ++g) {
         uint32_t bv[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
@@ -375,19 +376,22 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
           bv[j4 * 4 + 0] = __float_as_uint(t4.x); bv[j4 * 4 + 1] = __float_as_uint(t4.y);
           bv[j4 * 4 + 2] = __float_as_uint(t4.z); bv[j4 * 4 + 3] = __float_as_uint(t4.w);
         }
-        tmem_st16p(ta + g * 16, bv);
+        tmem_st16p(ta + c0 + g * 16, bv);
       }
     };
+    auto store_bias = [&](int l, uint32_t ta) { store_bias_cols(l, ta, 0, COLS); };
     // row (M-block mb, this thread's lane) of the tile with origin tt0 in clip tb: this thread's
     // COLS channels as fp32 bit patterns (zeros outside the clip)
-    auto load_row = [&](int tb, int tt0, int mb, uint32_t* v) {
+    // columns [c0, c0 + n) of this thread's COLS (n a multiple of 8) into v[0 .. n)
+    auto load_cols = [&](int tb, int tt0, int mb, int c0, int n, uint32_t* v) {
       const int t = tt0 + mb * 128 + row0;
       const bool inside = (t >= 0) && (t < p.L);
       const size_t cstride = static_cast<size_t>(p.L) * 8;   // elements per channel chunk
-      const size_t off = ((static_cast<size_t>(tb) * G::NCH + chunk0) * p.L + (inside ? t : 0)) * 8;
+      const size_t off =
+          ((static_cast<size_t>(tb) * G::NCH + chunk0 + c0 / 8) * p.L + (inside ? t : 0)) * 8;
       if (p.x16in != nullptr) {
 #pragma unroll
-        for (int c = 0; c < COLS / 8; ++c) {
+        for (int c = 0; c < n / 8; ++c) {
           uint4 q16 = make_uint4(0u, 0u, 0u, 0u);
           if (inside) q16 = __ldg(reinterpret_cast<const uint4*>(p.x16in + off + c * cstride));
           const uint32_t w16[4] = {q16.x, q16.y, q16.z, q16.w};
@@ -402,7 +406,7 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < COLS / 8; ++c) {
+        for (int c = 0; c < n / 8; ++c) {
           float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (inside) ld_global_nc_v8(p.x32 + off + c * cstride, a8);
 #pragma unroll
@@ -411,11 +415,11 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
       }
     };
     // ... -> 16-bit operand in sX, fp32 residual stream in TMEM, conv 0's bias in the accumulator
-    auto store_row = [&](int mb, const uint32_t* v) {
+    auto store_cols = [&](int mb, int c0, int n, const uint32_t* v) {
       const uint32_t tx = tm0 + static_cast<uint32_t>(mb * 2 * C);
 #pragma unroll
-      for (int c = 0; c < COLS / 8; ++c) {
-        const uint32_t dst = sX + so0 + static_cast<uint32_t>((c * R + mb * 128) * 16);
+      for (int c = 0; c < n / 8; ++c) {
+        const uint32_t dst = sX + so0 + static_cast<uint32_t>(((c0 / 8 + c) * R + mb * 128) * 16);
         st_shared_v4(dst,
                      pack2s(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]), kOp),
                      pack2s(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]), kOp),
@@ -423,9 +427,11 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
                      pack2s(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]), kOp));
       }
 #pragma unroll
-      for (int g = 0; g < NG; ++g) tmem_st16p(tx + g * 16, &v[g * 16]);
-      store_bias(0, tx + C);
+      for (int g = 0; g < n / 16; ++g) tmem_st16p(tx + c0 + g * 16, &v[g * 16]);
+      store_bias_cols(0, tx + C, c0, n);
     };
+    auto load_row = [&](int tb, int tt0, int mb, uint32_t* v) { load_cols(tb, tt0, mb, 0, COLS, v); };
+    auto store_row = [&](int mb, const uint32_t* v) { store_cols(mb, 0, COLS, v); };
     auto tile_origin = [&](int tl, int& tb, int& tt0) {
       const bool lv = tl < p.total_tiles;          // false: rank 1's dummy tile of an odd pair
       tb = lv ? tl / p.tiles_per_clip : 0;
@@ -487,10 +493,14 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
         }
         for (int h = 0; h < NP; ++h) {
           if (warp == 2) MSB_TRACE(256 + nconv * 16 + h * 4 + 0);
-          uint32_t nx[last ? IT : 1][last ? COLS : 1];
+          // the next tile's rows travel through registers 16 columns at a time: group 0 is
+          // requested before the wait for this conv's accumulator, group k+1 while group k of the
+          // current tile is being finished (64 live registers per row would not fit)
+          uint32_t nx[last ? IT : 1][last ? 16 : 1];
           if (last && has_next) {
 #pragma unroll
-            for (int u = 0; u < IT; ++u) load_row(nb, nt0, h * HB + ms + u * G::MSPLIT, nx[last ? u : 0]);
+            for (int u = 0; u < IT; ++u)
+              load_cols(nb, nt0, h * HB + ms + u * G::MSPLIT, 0, 16, nx[last ? u : 0]);
           }
           mbar_wait(acc_full(h), nconv & 1u);
           tc_fence_after();
@@ -596,11 +606,14 @@ __device__ __forceinline__ void resstack_body(const StackParams& p) {
                   }
                 }
               }
+              // this row's columns [c0, c0 + 16) are done with the old tile: bring in the next tile's
+              if (last && has_next) {
+                store_cols(mb, c0, 16, nx[last ? u : 0]);
+                if (c0 + 16 < COLS) load_cols(nb, nt0, mb, c0 + 16, 16, nx[last ? u : 0]);
+              }
             }
             // the accumulator has been read: seed it with the next conv's bias
             if (!last && !MSB_SABL(8) && !MSB_SABL(16)) store_bias(l + 1, ta);
-            // this row is done with the old tile: bring in the next tile's row
-            if (last && has_next) store_row(mb, nx[last ? u : 0]);
           }
           if (!last || has_next) {
             tmem_st_wait();
