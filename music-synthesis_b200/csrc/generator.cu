@@ -305,11 +305,17 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
           case 2:
             s = launch_conv(d, c, l16, w, bias, nullptr, ly16, nullptr, st);
             break;
-          default:
-            s = launch_conv(d, c, ly16, w, bias, lx32[lc], lx16[lc ^ 1], lx32[lc ^ 1], st);
+          default: {
+            // the fp32 stream is only written when a later layer reads it (the next atom's skip
+            // connection, or the fp32 final conv): an upsampler next reads the 16-bit image alone
+            const bool feeds_up = li + 1 < plan.layers.size() &&
+                                  (plan.layers[li + 1].role == 1 || plan.layers[li + 1].role >= 5);
+            s = launch_conv(d, c, ly16, w, bias, lx32[lc], lx16[lc ^ 1],
+                            feeds_up ? nullptr : lx32[lc ^ 1], st);
             lc ^= 1;
             l16 = lx16[lc];
             break;
+          }
         }
         if (s != MS_OK) return s;
       }
@@ -383,11 +389,15 @@ ms_status ms_melgan_generator_fwd(const void* packed_weights, int in_channels, i
         case 2:  // y = leaky(conv_dil(x))
           s = launch_conv(d, c, cur16, w, bias, nullptr, y16, nullptr, st);
           break;
-        default:  // x' = x + leaky(conv(y))
-          s = launch_conv(d, c, y16, w, bias, x32[cur], x16[cur ^ 1], x32[cur ^ 1], st);
+        default: {  // x' = x + leaky(conv(y))
+          const bool feeds_up = li + 1 < plan.layers.size() &&
+                                (plan.layers[li + 1].role == 1 || plan.layers[li + 1].role >= 5);
+          s = launch_conv(d, c, y16, w, bias, x32[cur], x16[cur ^ 1],
+                          feeds_up ? nullptr : x32[cur ^ 1], st);
           cur ^= 1;
           cur16 = x16[cur];
           break;
+        }
       }
       if (s != MS_OK) return s;
     }
