@@ -634,93 +634,82 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 //                                       x[b, ci, lin + e + t - (J-1)] * W[ci, co, r + s*(J-1-t)])
 // Reads the SAME packed 16-bit weights / 16-bit activations as the main GEMM, accumulates in
 // fp32.  Tiny: at most (J-1)*stride*cout outputs per clip.  blockIdx.y = e * stride + r.
-constexpr int kTailSlices = 8;    // lanes that share one output: each takes every 8th channel chunk
 constexpr int kTailClips = 8;     // clips per block: a weight vector is loaded once for all of them
+constexpr int kTailMaxSmem = 40 * 1024;
+// One thread = one GEMM column n (consecutive threads read consecutive 16-byte weight vectors:
+// packed[nt][kb][tap][c][nn][0..7]); the block's clips' input rows sit in shared memory and every
+// weight vector is used for all of them.  (Earlier versions streamed each output's weights once
+// per clip through L2: 25-37 us for the 134 MFLOP of the 512 -> 256 upsampler's tail row.)
+// grid: (ceil(Ntot / 128), ceil(B / clips), taps - 1); dynamic smem = clips * rows * cin * 2 bytes.
 __global__ void __launch_bounds__(128)
-convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */,
-                  int nnt_p /* packed n-tiles */) {
-  const int e = blockIdx.y / p.stride;      // tail row
-  const int r = blockIdx.y - e * p.stride;  // phase
-  const int b0 = blockIdx.z * kTailClips;
-  // 16 outputs per block x 8 channel slices x 8 clips.  Each output is a dot product over
-  // cin * (taps - 1 - e) elements: the first versions streamed its 16-bit weights once per CLIP
-  // (64 x 2 MB through L2 for the 512 -> 256 upsampler: 37 us for 134 MFLOP); now a thread keeps
-  // a batch of weight vectors in registers and walks the block's clips.
-  const int slice = threadIdx.x & (kTailSlices - 1);
-  const int co = blockIdx.x * (128 / kTailSlices) + (threadIdx.x >> 3);
+convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */, int clips) {
+  extern __shared__ __align__(16) uint8_t tail_smem[];
+  uint4* sx = reinterpret_cast<uint4*>(tail_smem);      // [clip][tap][chunk]
+  const int e = blockIdx.z;                              // tail row
+  const int b0 = blockIdx.y * clips;
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int ntaps = p.taps - 1 - e;                      // taps that meet real input rows
+  const int nch = p.cin >> 3;
+  const int xc8 = p.xcin >> 3;
+  // stage x[b, :, lin + e + t - (taps-1)] for t < ntaps (zero rows before the clip start)
+  for (int i = threadIdx.x; i < clips * ntaps * nch; i += blockDim.x) {
+    const int c8 = i % nch;
+    const int t = (i / nch) % ntaps;
+    const int cl = i / (nch * ntaps);
+    const int xrow = p.lin + e + t - (p.taps - 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (b0 + cl < p.B && xrow >= 0)
+      v = __ldg(reinterpret_cast<const uint4*>(
+          p.x + ((static_cast<size_t>(b0 + cl) * xc8 + c8 % xc8) * p.lin + xrow) * 8));
+    sx[i] = v;
+  }
+  __syncthreads();
+  if (n >= p.Ntot) return;
+  const int r = convt_col_phase(n, p.stride), co = convt_col_channel(n, p.stride);
   const int orow = p.stride * (p.lin + e) + r - p.pad;
-  const bool live = co < p.cout && orow >= 0 && orow < p.Lout;   // warp-uniform enough: shuffles below
+  if (orow < 0 || orow >= p.Lout) return;
+  const int nt = n / ntp, nn = n - nt * ntp;
+  const int chunks = p.KB >> 3;
   float acc[kTailClips];
 #pragma unroll
   for (int cl = 0; cl < kTailClips; ++cl) acc[cl] = 0.f;
-  if (live) {
-    const int n = convt_col(r, co, p.stride);   // GEMM column
-    const int nt = n / ntp, nn = n - nt * ntp;
-    const int chunks = p.KB >> 3;
-    const int xc8 = p.xcin >> 3;
-    const int nch = p.cin >> 3;
-    for (int t = 0; t <= p.taps - 2 - e; ++t) {
-      const int xrow = p.lin + e + t - (p.taps - 1);
-      if (xrow < 0) continue;
-      for (int c80 = slice; c80 < nch; c80 += 4 * kTailSlices) {
-        uint4 wq[4];
-        size_t xoff[4];
+  for (int t = 0; t < ntaps; ++t) {
+#pragma unroll 4
+    for (int c8 = 0; c8 < nch; ++c8) {
+      const int ci = c8 * 8;
+      const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
+      const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
+      const uint4 wq = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
+      const uint32_t ww[4] = {wq.x, wq.y, wq.z, wq.w};
+      float wf[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c8 = c80 + u * kTailSlices;
-          wq[u] = make_uint4(0u, 0u, 0u, 0u);
-          xoff[u] = 0;
-          if (c8 < nch) {
-            const int ci = c8 * 8;
-            const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
-            // packed[nt][kb][tap][c][nn][0..7]
-            const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
-            wq[u] = __ldg(reinterpret_cast<const uint4*>(p.w + wi));
-            xoff[u] = (static_cast<size_t>(c8 % xc8) * p.lin + xrow) * 8;
-          }
-        }
+      for (int j = 0; j < 4; ++j) {
+        float2 f2;
+        if (p.operand == MS_BF16) f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+        else f2 = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
+        wf[2 * j] = f2.x; wf[2 * j + 1] = f2.y;
+      }
 #pragma unroll
-        for (int cl = 0; cl < kTailClips; ++cl) {
-          if (b0 + cl >= p.B) break;
-          const uint16_t* xb = p.x + static_cast<size_t>(b0 + cl) * xc8 * p.lin * 8;
-          uint4 xq[4];
+      for (int cl = 0; cl < kTailClips; ++cl) {
+        if (cl >= clips) break;
+        const uint4 xq = sx[(cl * ntaps + t) * nch + c8];
+        const uint32_t xx[4] = {xq.x, xq.y, xq.z, xq.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            xq[u] = make_uint4(0u, 0u, 0u, 0u);   // (zero weights beyond the last chunk)
-            if (c80 + u * kTailSlices < nch) xq[u] = __ldg(reinterpret_cast<const uint4*>(xb + xoff[u]));
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t ww[4] = {wq[u].x, wq[u].y, wq[u].z, wq[u].w};
-            const uint32_t xx[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 wf, xf;
-              if (p.operand == MS_BF16) {
-                wf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
-                xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
-              } else {
-                wf = __half22float2(*reinterpret_cast<const __half2*>(&ww[j]));
-                xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
-              }
-              acc[cl] = fmaf(xf.x, wf.x, acc[cl]);
-              acc[cl] = fmaf(xf.y, wf.y, acc[cl]);
-            }
-          }
+        for (int j = 0; j < 4; ++j) {
+          float2 xf;
+          if (p.operand == MS_BF16) xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xx[j]));
+          else xf = __half22float2(*reinterpret_cast<const __half2*>(&xx[j]));
+          acc[cl] = fmaf(xf.x, wf[2 * j], acc[cl]);
+          acc[cl] = fmaf(xf.y, wf[2 * j + 1], acc[cl]);
         }
       }
     }
   }
 #pragma unroll
   for (int cl = 0; cl < kTailClips; ++cl) {
-    // fixed-order combination of the 8 slices (lanes slice = 0..7 of one output are adjacent)
-    float a = acc[cl];
-    a += __shfl_xor_sync(0xffffffffu, a, 1);
-    a += __shfl_xor_sync(0xffffffffu, a, 2);
-    a += __shfl_xor_sync(0xffffffffu, a, 4);
     const int b = b0 + cl;
-    if (!live || slice != 0 || b >= p.B) continue;
-    float v = a * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
+    if (cl >= clips || b >= p.B) break;
+    float v = acc[cl] * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
     if (p.leaky == 1) v = leaky02(v);
     const size_t idx = ((static_cast<size_t>(b) * (p.cout >> 3) + (co >> 3)) * p.Lout + orow) * 8 + (co & 7);
     if (p.res32 != nullptr) v += p.res32[idx];
@@ -812,9 +801,12 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
 
   if (d.kind == MS_CONVT) {
     // the rows q >= lin first (independent outputs: the last rows of each clip)
-    dim3 tgrid((d.cout + 15) / 16, (c.taps - 1) * d.stride, (d.batch + kTailClips - 1) / kTailClips);
-    convt_tail_kernel<<<tgrid, 128, 0, stream>>>(p, c.pair ? c.NT / 2 : c.NT,
-                                                 c.pair ? 2 * c.nnt : c.nnt);
+    int clips = kTailClips;
+    const size_t per_clip = static_cast<size_t>(c.taps - 1) * d.cin * 2;
+    while (clips > 1 && clips * per_clip > static_cast<size_t>(kTailMaxSmem)) clips /= 2;
+    if (clips * per_clip > static_cast<size_t>(kTailMaxSmem)) return MS_ERR_INVALID;
+    dim3 tgrid((c.Ntot + 127) / 128, (d.batch + clips - 1) / clips, c.taps - 1);
+    convt_tail_kernel<<<tgrid, 128, clips * per_clip, stream>>>(p, c.pair ? c.NT / 2 : c.NT, clips);
     ms_status ts = after_launch("convt_tail_kernel");
     if (ts != MS_OK) return ts;
   }
