@@ -206,3 +206,15 @@ def require_cuda(t, name):
             "%s must be a CUDA tensor: this path has no CPU implementation" % name)
     if t.dtype != torch.float32:
         raise MsbError("%s must be float32 (got %s)" % (name, t.dtype))
+    require_current_device(t, name)
+
+
+def require_current_device(t, name="tensor"):
+    """Every C-ABI launch goes to the CURRENT device's current stream (stream_ptr()); a tensor
+    that lives on another GPU would be read by kernels running on the wrong device.  Raise
+    instead (callers select the device with torch.cuda.set_device / torch.cuda.device)."""
+    import torch
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise MsbError("%s is on cuda:%d but the current device is cuda:%d: wrap the call in "
+                       "torch.cuda.device(%s.device)" % (name, t.device.index,
+                                                          torch.cuda.current_device(), name))

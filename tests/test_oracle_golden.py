@@ -11,7 +11,14 @@ import torch
 
 from oracle import restate, synth, bases
 
-torch.set_grad_enabled(False)
+
+
+@pytest.fixture(autouse=True)
+def _no_grad():
+    """the pins run without a tape; scoped to this module's tests (a module-level
+    torch.set_grad_enabled(False) leaked into every test collected after this file)"""
+    with torch.no_grad():
+        yield
 
 
 def _sub(t):
