@@ -335,6 +335,7 @@ def main():
     ap.add_argument("--headline-only", action="store_true",
                     help="skip the strong-scaling / training / cfg1 / cfg2 side measurements")
     ap.add_argument("--e2e-chunk", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--e2e-edge", type=int, default=-1, help=argparse.SUPPRESS)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -416,6 +417,8 @@ def main():
         # the public host-to-host call: pinned features in, pinned waveform out, every step
         # copies its 33.5 MB of inputs H2D and its 67 MB of audio D2H inside the timed region
         ekw = {"chunk_clips": args.e2e_chunk} if args.e2e_chunk > 0 else {}
+        if args.e2e_edge >= 0:
+            ekw["edge_clips"] = args.e2e_edge
         for _ in range(2):
             gen.generate(x_host, out=y_host, **ekw)
         sync_all()
