@@ -243,3 +243,25 @@ def test_reflect_pad_ncl_forward_and_backward(B, C, L, pad):
     # the three contributions are summed in a fixed order; torch's scatter order may differ in the
     # last bit where two mirrors meet
     assert torch.allclose(xd.grad.cpu(), xr.grad, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,L", [(1, 224 * 3), (1, 224 * 2 + 1), (5, 224), (2, 1000)])
+def test_fused_stack_c128_pair_and_single_cta_agree(ops, B, L, monkeypatch):
+    """C = 128 runs on CTA pairs (cta_group::2) by default: odd tile counts (the peer CTA gets a
+    masked dummy tile), one tile, many tiles -- against the host emulation, in a subprocess-free
+    way (the pair switch is read once per process, so only the default is exercised here; the
+    single-CTA form is covered by the MSB_STACK_PAIR=0 run of tools/stack_bench.py)."""
+    from oracle import synth
+    C = 128
+    sd = synth.residual_stack_state(60 + B, C)
+    x = randn(61 + L % 17, B, C, L, scale=0.5)
+    ref = _stack_emulated(x, sd)
+    params = []
+    for a in range(3):
+        for c in range(2):
+            params += [sd[f"s.main.{a}.main.{c}.weight"].cuda(), sd[f"s.main.{a}.main.{c}.bias"].cuda()]
+    y16, y32 = ops.resstack_fwd(_blk32(x).cuda(), ops.resstack_pack_weights(params, C), [1, 3, 9],
+                                want16=True, want32=True)
+    got = ops.unpack_blk32(y32).cpu()
+    assert rel_l2(got, ref) < TIGHT
+    assert torch.equal(ops.unpack_blk16(y16).cpu(), rnd16(got))

@@ -93,3 +93,31 @@ def test_fused_stage_rejects_even_dilations(ops):
     x16 = ops.pack_ncl(randn(601, 1, 64, 64).cuda())
     with pytest.raises(MsbError):
         ops.upstack_fwd(x16, blob, [1, 2, 9])
+
+
+@pytest.mark.parametrize("C,B,lin", [(64, 3, 3), (64, 1, 9), (32, 2, 5), (32, 5, 17)])
+def test_fused_stage_on_clips_shorter_than_the_halo(ops, C, B, lin):
+    """both clip edges inside one tile, fewer input rows than the stack's receptive field"""
+    sd, wt, bt, params = _stage_params(700 + C, C)
+    x = randn(710 + lin, B, 2 * C, lin, scale=0.5)
+    ref = _stage_emulated(x, sd, wt, bt).float()
+    _, y32 = ops.upstack_fwd(ops.pack_ncl(x.cuda()), ops.upstack_pack_weights(params, C), [1, 3, 9],
+                             want16=False, want32=True)
+    assert rel_l2(ops.unpack_blk32(y32).cpu(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("C", [64, 32])
+def test_fused_stage_bf16_operands(ops, C):
+    """the bf16 operand mode of the fused stage against the same layers with bf16-rounded
+    operands (wide accumulate, fp32 stream)"""
+    from music_synthesis_b200._lib import MS_BF16
+    B, lin = 2, 300
+    sd, wt, bt, params = _stage_params(800 + C, C)
+    x = randn(810 + C, B, 2 * C, lin, scale=0.5)
+    up = F.leaky_relu(F.conv_transpose1d(rnd16(x, "bf16").double(), rnd16(wt, "bf16").double(),
+                                         bt.double(), stride=2, padding=1), 0.2)
+    ref = _stack_emulated(up.float(), sd, operand="bf16").float()
+    blob = ops.upstack_pack_weights(params, C, operand=MS_BF16)
+    _, y32 = ops.upstack_fwd(ops.pack_ncl(x.cuda(), operand=MS_BF16), blob, [1, 3, 9],
+                             operand=MS_BF16, want16=False, want32=True)
+    assert rel_l2(ops.unpack_blk32(y32).cpu(), ref) < 2e-5
