@@ -58,8 +58,10 @@ def morlet_bank(samplerate, kernel_size, center_frequencies, scaling_factor=0.05
 
 class FilterBank:
     """kernel_size: any length up to 512 taps.  Internally the bank is zero-padded at the end to
-    kp = the next multiple of 16 taps (a no-op on both operations); banks of more than 128 taps
-    (the 511-tap bank of experiment/filterbank.py:34-45) use 16 synthesis phases, shorter ones 8.
+    kp = the next multiple of 32 taps (a no-op on both operations).  Synthesis runs with 32 phase
+    channels (N = 32 GEMM, kp / 32 taps of dilation 32): with the first version's 8 phases the
+    tensor core saw N = 16 MMAs (half of them zero columns) and 16 taps -- 4x the MMA count for the
+    same arithmetic; the 65 536-sample band of config 5 took 1.74 ms per call.
     torch conventions kept: `convolve` = conv1d(padding = k // 2) -> L + 1 rows for even k, L for
     odd k; `transposed_convolve` = conv_transpose1d(padding = k // 2)."""
 
@@ -79,11 +81,12 @@ class FilterBank:
             raise NotImplementedError("FilterBank: n_bands must be a multiple of 16")
         self.filter_bank = bank.reshape(self.n_bands, 1, kernel_size)
         self.pad = kernel_size // 2                       # torch padding of both operations
-        self.kp = (kernel_size + 15) // 16 * 16           # padded tap count
+        self.kp = (kernel_size + 31) // 32 * 32           # padded tap count
         self.extra = 1 - kernel_size % 2                  # convolve returns L + extra rows
         # synthesis as a conv: nph phase channels, kp / nph taps of dilation nph, padding syn_pad,
         # then y[t] = sum_i z[t + i + 1, i] (ms_diag_sum, skew 1)
-        self.syn_nph = 16 if self.kp > 128 else 8
+        self.syn_nph = 32
+        self.syn_ch = 32                                  # channels of the phase tensor
         self.syn_taps = self.kp // self.syn_nph
         self.syn_pad = kernel_size - self.pad
         self._packed = {}
@@ -130,11 +133,11 @@ class FilterBank:
         return self._padded(device).reshape(n, taps, 16).permute(0, 2, 1).contiguous()
 
     def synthesis_weight(self, device):
-        """(16, n, kp/nph) weight of the synthesis conv (nph phase channels used):
+        """(syn_ch, n, kp/nph) weight of the synthesis conv (nph phase channels used):
         Wg[i, c, j] = flip(bank)[c, nph j + i]"""
         n, nph, taps = self.n_bands, self.syn_nph, self.syn_taps
         wf = self._padded(device, flip=True)
-        w = torch.zeros((16, n, taps), dtype=torch.float32, device=device)
+        w = torch.zeros((self.syn_ch, n, taps), dtype=torch.float32, device=device)
         w[:nph] = wf.reshape(n, taps, nph).permute(2, 0, 1)
         return w.contiguous()
 
@@ -182,12 +185,12 @@ class FilterBank:
             mult, alpha, xrep = 2, 1.0 / ops.W_SPLIT_SCALE, 2    # the K loop wraps over x16 twice
         else:
             mult, alpha = 1, 1.0
-        d = ops.conv_desc(MS_CONV, B, mult * n, 16, Lin, self.syn_taps, self.syn_nph, self.syn_pad,
+        d = ops.conv_desc(MS_CONV, B, mult * n, self.syn_ch, Lin, self.syn_taps, self.syn_nph, self.syn_pad,
                           operand=self.operand, alpha=alpha, x_repeat=xrep)
         _, z32 = ops.conv_fwd(d, x16, self._synth_weights(d, x16.device, wsplit), None,
                               want16=False, want32=True)
         y = torch.empty((B, 1, Lout), dtype=torch.float32, device=x16.device)
-        check(_lib.lib().ms_diag_sum(ptr(z32), ptr(y), B, 16, z32.shape[2], Lout, self.syn_nph, 1,
+        check(_lib.lib().ms_diag_sum(ptr(z32), ptr(y), B, self.syn_ch, z32.shape[2], Lout, self.syn_nph, 1,
                                      stream_ptr()), "ms_diag_sum")
         return y
 

@@ -432,7 +432,7 @@ class BankSynthesis(Function):
     def backward(ctx, dy):
         bank = ctx.bank
         B, _, L, _ = ctx.shape
-        dz32 = grad_ops.diag_sum_bwd(dy, 16, bank.synthesis_rows(L), bank.syn_nph, 1)
+        dz32 = grad_ops.diag_sum_bwd(dy, bank.syn_ch, bank.synthesis_rows(L), bank.syn_nph, 1)
         dz16, _ = grad_ops.act_bwd(dz32, want_bias=False)
         w = bank.synthesis_weight(dy.device)
         cache = bank.__dict__.setdefault("_synth_dgrad_cache", WeightCache())

@@ -390,19 +390,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           fence_proxy_async_smem();
           __syncwarp();
         }
-        if (elect_one()) {
+        // lane 0 announces the bytes and streams the weight stage; the activation copies (one
+        // per 16-byte channel chunk) are issued by as many lanes in parallel -- a single lane
+        // needed ~1000 cycles per stage for eight of them (tools/pair_trace.py)
+        if (lane == 0) {
           const uint32_t bytes_a = static_cast<uint32_t>(nrows) * 16u * chunks;
           mbar_arrive_expect_tx(full_bar(stage), bytes_a + p.w_stage_bytes);
           const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) +
                                 (static_cast<size_t>(nt_idx) * p.nkb + kb) * p.w_stage_bytes;
           bulk_g2s(sW, wsrc, p.w_stage_bytes, full_bar(stage));
-          if (nrows > 0) {
-            const size_t cbase = static_cast<size_t>(b) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
-            for (int c = 0; c < chunks; ++c) {
-              const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
-              bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,
-                       static_cast<uint32_t>(nrows) * 16u, full_bar(stage));
-            }
+        }
+        __syncwarp();
+        if (nrows > 0) {
+          const size_t cbase = static_cast<size_t>(b) * (p.xcin >> 3) + (kb % p.xnkb) * chunks;
+          for (int c = lane; c < chunks; c += 32) {
+            const uint16_t* src = p.x + ((cbase + c) * p.lin + lo) * 8;
+            bulk_g2s(sA + static_cast<uint32_t>(c * p.RA + (lo - r0)) * 16u, src,
+                     static_cast<uint32_t>(nrows) * 16u, full_bar(stage));
           }
         }
         __syncwarp();
