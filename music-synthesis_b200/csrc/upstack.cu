@@ -135,6 +135,9 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
   const uint32_t in_full = bar_base + 8u * 40;
   const uint32_t in_free = bar_base + 8u * 41;
   const uint32_t a_issued = bar_base + 8u * 42;   // issuer A -> issuer B, once per stage
+  // HE == 2 (C = 32): the first E / O blocks of part 1 are done -- all that the deferred taps of
+  // part 0 read; issuer A no longer waits for the whole part
+  const uint32_t act_half = bar_base + 8u * 43;
   auto buf = [&](int i) { return sBuf0 + static_cast<uint32_t>(i & 1) * G::ACT_BYTES; };
 
   const int warp = threadIdx.x >> 5;
@@ -151,6 +154,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
     }
     mbar_init(in_full, 1);
     mbar_init(a_issued, 1);
+    mbar_init(act_half, EW);
     mbar_init(in_free, 1);         // epilogue warp 2, once stage 5's MMAs have completed
     fence_mbar_init();
   }
@@ -340,7 +344,7 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
           }
           __syncwarp();
           MSB_UTRACE((l + 1) * 16 + part * 4 + 2);
-          mbar_wait(act_ready(1), g & 1u);
+          mbar_wait(HE == 2 ? act_half : act_ready(1), g & 1u);
           tc_fence_after();
           if (elect_one()) {
             if (!MSB_ABL(1)) issue_part(0, 2, 3, HE - 1, HE);
@@ -387,7 +391,9 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
     };
     // block j of a part: phase r, SMEM row of this thread, time-order row in the tile
     auto geom = [&](int h, int u, int& mb, int& srow, int& trow) {
-      const int j = ms + u * G::MSPLIT;
+      // HE == 2: ms selects the phase and u the block of that phase, so that after u = 0 the
+      // first E and O blocks of the part are complete (see act_half)
+      const int j = (HE == 2) ? ms * HE + u : ms + u * G::MSPLIT;
       const int r = j / HE, kk = j % HE;
       mb = h * HB + j;
       const int m = (h * HE + kk) * 128 + row0;
@@ -404,6 +410,10 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
       }
       tmem_st_wait();
       tc_fence_before();
+      if (HE == 2 && h == 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(act_half);
+      }
       arrive_act(h);
     }
     int it = 0;
@@ -540,6 +550,14 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
             }
             // the accumulator has been read: seed it with the next stage's bias
             if (!MSB_ABL(8)) store_bias(last ? 0 : s + 1, ta);
+            if (HE == 2 && h == 1 && u == 0) {
+              // (the last stage writes no operand rows, but the barrier's phase must advance)
+              tmem_st_wait();
+              fence_proxy_async_smem();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(act_half);
+            }
           }
           tmem_st_wait();
           fence_proxy_async_smem();
