@@ -477,15 +477,20 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     uint32_t acc_phase = 0;
     const int cout8 = p.cout >> 3;
     const int ngroups = p.NT >> 4;            // 16-column groups per M-block
+    int tab_nt0 = -1, tab_nt1 = -1;     // n-tile whose tables sit in buffer 0 / 1
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt_idx = tile % p.nnt;
       const int rest = tile / p.nnt;
       const int mt = rest % p.mtiles;
       const int b = rest / p.mtiles;
       const int n0 = nt_idx * p.NT;
-      {
-        // tables for this tile (the buffer of this acc stage was last read two tiles ago,
-        // and every epilogue thread passed the barrier below since then)
+      // bias / column tables of this tile's n-tile: rebuilt only when the n-tile of this
+      // accumulator stage changes (for nnt = 1 layers once per CTA; the fill -- a global load
+      // and a barrier of all epilogue warps -- cost 1.1-2.3 k cycles per tile on the epilogue's
+      // critical path, tools/pair_trace.py)
+      if (((acc & 1) ? tab_nt1 : tab_nt0) != nt_idx || (p.debug & 256) != 0) {
+        // every epilogue warp is done with the tiles that read this buffer
+        named_bar_sync(1, 32 * kConvEpiWarps);
         const int et = threadIdx.x - 64;              // 0 .. 255
         float* tb = s_bias + (acc & 1) * 256;
         int2* tt = s_tab + (acc & 1) * 32;
@@ -503,6 +508,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         named_bar_sync(1, 32 * kConvEpiWarps);
+        if (acc & 1) tab_nt1 = nt_idx; else tab_nt0 = nt_idx;
       }
       const float* tbias = s_bias + (acc & 1) * 256;
       const int2* ttab = s_tab + (acc & 1) * 32;
@@ -789,8 +795,17 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
   p.mtiles = c.mtiles; p.MBLK = c.MBLK; p.acc_stages = c.acc_stages; p.pair = c.pair; p.wres = c.wres; p.out_stage = c.out_stage;
   p.debug = 0;
   p.dbg = nullptr;
+  {
+    // MSB_CONV_TABCACHE=0: rebuild the epilogue tables for every tile (A/B timing)
+    static int tabcache = -1;
+    if (tabcache < 0) {
+      const char* e = getenv("MSB_CONV_TABCACHE");
+      tabcache = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (tabcache == 0) p.debug |= 256;
+  }
 #ifdef MSB_CONV_ABLATE
-  if (const char* e = getenv("MSB_CONV_ABLATE")) p.debug = atoi(e);
+  if (const char* e = getenv("MSB_CONV_ABLATE")) p.debug |= atoi(e);
   p.dbg = g_conv_dbg;
 #endif
   p.stages = c.stages; p.a_stage_bytes = c.a_stage_bytes; p.w_stage_bytes = c.w_stage_bytes;

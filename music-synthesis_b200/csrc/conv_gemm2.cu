@@ -314,13 +314,20 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     const int cout8 = p.cout >> 3;
     const int ngroups = p.NT >> 4;
     int ti = -1;
+    int tab_nt0 = -1, tab_nt1 = -1;     // n-tile whose tables sit in buffer 0 / 1
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       ++ti;
       int nt_idx, mt, b;
       decode(tile, nt_idx, mt, b);
       const int n0 = nt_idx * p.NT;
       if (warp == 2) MSB_CTRACE(128, 0);
-      {
+      // bias / column tables of this tile's n-tile: rebuilt only when the n-tile of this
+      // accumulator stage changes (for nnt = 1 layers once per CTA; the fill -- a global load
+      // and a barrier of all epilogue warps -- cost 1.1-2.3 k cycles per tile on the epilogue's
+      // critical path, tools/pair_trace.py)
+      if (((acc & 1) ? tab_nt1 : tab_nt0) != nt_idx || (p.debug & 256) != 0) {
+        // every epilogue warp is done with the tiles that read this buffer
+        named_bar_sync(1, 32 * kPairEpiWarps);
         const int et = threadIdx.x - 64;
         float* tb = s_bias + (acc & 1) * 256;
         int2* tt = s_tab + (acc & 1) * 32;
@@ -338,6 +345,7 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         named_bar_sync(1, 32 * kPairEpiWarps);
+        if (acc & 1) tab_nt1 = nt_idx; else tab_nt0 = nt_idx;
       }
       const float* tbias = s_bias + (acc & 1) * 256;
       const int2* ttab = s_tab + (acc & 1) * 32;
