@@ -803,6 +803,13 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
       tabcache = (e != nullptr && e[0] == '0') ? 0 : 1;
     }
     if (tabcache == 0) p.debug |= 256;
+    // MSB_CONV_FASTEPI=0: plain convs take the generic epilogue (A/B timing)
+    static int fastepi = -1;
+    if (fastepi < 0) {
+      const char* e = getenv("MSB_CONV_FASTEPI");
+      fastepi = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    if (fastepi == 0) p.debug |= 512;
   }
 #ifdef MSB_CONV_ABLATE
   if (const char* e = getenv("MSB_CONV_ABLATE")) p.debug |= atoi(e);

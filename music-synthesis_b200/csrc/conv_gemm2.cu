@@ -315,6 +315,9 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
     const int ngroups = p.NT >> 4;
     int ti = -1;
     int tab_nt0 = -1, tab_nt1 = -1;     // n-tile whose tables sit in buffer 0 / 1
+    // warp-uniform: the specialised epilogue below applies (bias is applied as v + b: alpha = 1)
+    const bool fast = p.kind == MS_CONV && p.leaky == 1 && p.alpha == 1.0f && p.operand == MS_F16 &&
+                      (p.NT & 31) == 0 && (p.debug & 512) == 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
       ++ti;
       int nt_idx, mt, b;
@@ -403,6 +406,40 @@ conv_gemm_pair_kernel(const __grid_constant__ ConvGemmParams p) {
             if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote_relaxed(tempty_bar(acc), 0);
           }
           arrived = true;
+        }
+        if (fast && two) {
+          // ---- plain conv, fp16 operands, alpha = 1, LeakyReLU before the residual (every conv
+          //      of the generator's C = 256 stage and its first conv): no column tables, packed
+          //      fp32 math, one address per chunk.  The generic path below spends ~9 instructions
+          //      per element on run-time flags; this one ~4.
+          if (m < p.Lm && !MSB_CABL(16)) {
+            const size_t row_base = static_cast<size_t>(b) * cout8 * p.Lout + m;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int cidx = g * 2 + h;
+              const float4 b0 = *reinterpret_cast<const float4*>(tbias + cidx * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(tbias + cidx * 8 + 4);
+              float f[8];
+              add_x2(__uint_as_float(v[h * 8 + 0]), __uint_as_float(v[h * 8 + 1]), b0.x, b0.y, f[0], f[1]);
+              add_x2(__uint_as_float(v[h * 8 + 2]), __uint_as_float(v[h * 8 + 3]), b0.z, b0.w, f[2], f[3]);
+              add_x2(__uint_as_float(v[h * 8 + 4]), __uint_as_float(v[h * 8 + 5]), b1.x, b1.y, f[4], f[5]);
+              add_x2(__uint_as_float(v[h * 8 + 6]), __uint_as_float(v[h * 8 + 7]), b1.z, b1.w, f[6], f[7]);
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) leaky02x2(f[j], f[j + 1], f[j], f[j + 1]);
+              if (p.res32 != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) add_x2(f[j], f[j + 1], r8[h][j], r8[h][j + 1], f[j], f[j + 1]);
+              }
+              if (MSB_CABL(1)) continue;
+              const size_t idx = row_base + static_cast<size_t>((n0 >> 3) + cidx) * p.Lout;
+              if (p.y32 != nullptr) st_global_v8(p.y32 + idx * 8, f);
+              if (p.y16 != nullptr)
+                *reinterpret_cast<uint4*>(p.y16 + idx * 8) =
+                    make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]),
+                               pack_h2(f[6], f[7]));
+            }
+          }
+          continue;
         }
         if (p.out_stage != 0 && two) {
           // ---- ConvTranspose, staged: the four chunks are phases ph0 .. ph0+3 of one channel
