@@ -229,7 +229,7 @@ def test_product_511_tap_bank_equals_the_reference_bank(golden):
     from music_synthesis_b200.experiment.wirings import FilterBankExperiment
     g = golden("filterbank_generator_t32")
     fb = FilterBankExperiment.make_filter_bank()
-    assert fb.kernel_size == 511 and fb.kp == 512 and fb.syn_nph == 16 and fb.extra == 0
+    assert fb.kernel_size == 511 and fb.kp == 512 and fb.syn_nph == 32 and fb.syn_taps == 16 and fb.extra == 0
     assert abs(float(fb.filter_bank.double().abs().sum()) - float(g["bank_checksum"])) < 1e-4
     assert np.abs(fb.filter_bank.numpy().reshape(-1)[::97] - g["bank_sub"]).max() < 2e-7
 
