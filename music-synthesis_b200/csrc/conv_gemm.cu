@@ -646,18 +646,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 // fp32.  Tiny: at most (J-1)*stride*cout outputs per clip.  blockIdx.y = e * stride + r.
 constexpr int kTailClips = 8;     // clips per block: a weight vector is loaded once for all of them
 constexpr int kTailMaxSmem = 40 * 1024;
-// One thread = one GEMM column n (consecutive threads read consecutive 16-byte weight vectors:
-// packed[nt][kb][tap][c][nn][0..7]); the block's clips' input rows sit in shared memory and every
-// weight vector is used for all of them.  (Earlier versions streamed each output's weights once
-// per clip through L2: 25-37 us for the 134 MFLOP of the 512 -> 256 upsampler's tail row.)
-// grid: (ceil(Ntot / 128), ceil(B / clips), taps - 1); dynamic smem = clips * rows * cin * 2 bytes.
+// 16 GEMM columns x 8 input-channel slices per block; the block's clips' input rows sit in shared
+// memory and every weight vector (packed[nt][kb][tap][c][nn][0..7]) is used for all of them; the
+// eight slices of a column are combined in a fixed shuffle order.  (Earlier versions streamed each
+// output's weights once per clip through L2: 25-37 us for the 134 MFLOP of the 512 -> 256
+// upsampler's tail row; one column per thread without slices was latency-bound at small batches.)
+// grid: (ceil(Ntot / 16), ceil(B / clips), taps - 1); dynamic smem = clips * rows * cin * 2 bytes.
+constexpr int kTailSlices = 8;
 __global__ void __launch_bounds__(128)
 convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */, int clips) {
   extern __shared__ __align__(16) uint8_t tail_smem[];
   uint4* sx = reinterpret_cast<uint4*>(tail_smem);      // [clip][tap][chunk]
   const int e = blockIdx.z;                              // tail row
   const int b0 = blockIdx.y * clips;
-  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int slice = threadIdx.x & (kTailSlices - 1);
+  const int n = blockIdx.x * (128 / kTailSlices) + (threadIdx.x >> 3);
   const int ntaps = p.taps - 1 - e;                      // taps that meet real input rows
   const int nch = p.cin >> 3;
   const int xc8 = p.xcin >> 3;
@@ -674,18 +677,18 @@ convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */, int clips
     sx[i] = v;
   }
   __syncthreads();
-  if (n >= p.Ntot) return;
-  const int r = convt_col_phase(n, p.stride), co = convt_col_channel(n, p.stride);
+  const int nq = n < p.Ntot ? n : 0;
+  const int r = convt_col_phase(nq, p.stride), co = convt_col_channel(nq, p.stride);
   const int orow = p.stride * (p.lin + e) + r - p.pad;
-  if (orow < 0 || orow >= p.Lout) return;
-  const int nt = n / ntp, nn = n - nt * ntp;
+  const bool live = n < p.Ntot && orow >= 0 && orow < p.Lout;
+  const int nt = nq / ntp, nn = nq - nt * ntp;
   const int chunks = p.KB >> 3;
   float acc[kTailClips];
 #pragma unroll
   for (int cl = 0; cl < kTailClips; ++cl) acc[cl] = 0.f;
-  for (int t = 0; t < ntaps; ++t) {
+  for (int t = 0; live && t < ntaps; ++t) {
 #pragma unroll 4
-    for (int c8 = 0; c8 < nch; ++c8) {
+    for (int c8 = slice; c8 < nch; c8 += kTailSlices) {
       const int ci = c8 * 8;
       const int kb = ci / p.KB, c = (ci % p.KB) >> 3;
       const size_t wi = ((((static_cast<size_t>(nt) * p.nkb + kb) * p.taps + t) * chunks + c) * ntp + nn) * 8;
@@ -718,8 +721,13 @@ convt_tail_kernel(const ConvGemmParams p, int ntp /* packed n-tile */, int clips
 #pragma unroll
   for (int cl = 0; cl < kTailClips; ++cl) {
     const int b = b0 + cl;
-    if (cl >= clips || b >= p.B) break;
-    float v = acc[cl] * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
+    // fixed-order combination of the 8 slices (adjacent lanes)
+    float a = acc[cl];
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    if (!live || slice != 0 || cl >= clips || b >= p.B) continue;
+    float v = a * p.alpha + (p.bias != nullptr ? p.bias[co] : 0.f);
     if (p.leaky == 1) v = leaky02(v);
     const size_t idx = ((static_cast<size_t>(b) * (p.cout >> 3) + (co >> 3)) * p.Lout + orow) * 8 + (co & 7);
     if (p.res32 != nullptr) v += p.res32[idx];
@@ -831,7 +839,7 @@ ms_status launch_conv(const ms_conv_desc& d, const ConvCfg& c, const void* x16,
     const size_t per_clip = static_cast<size_t>(c.taps - 1) * d.cin * 2;
     while (clips > 1 && clips * per_clip > static_cast<size_t>(kTailMaxSmem)) clips /= 2;
     if (clips * per_clip > static_cast<size_t>(kTailMaxSmem)) return MS_ERR_INVALID;
-    dim3 tgrid((c.Ntot + 127) / 128, (d.batch + clips - 1) / clips, c.taps - 1);
+    dim3 tgrid((c.Ntot + 15) / 16, (d.batch + clips - 1) / clips, c.taps - 1);
     convt_tail_kernel<<<tgrid, 128, clips * per_clip, stream>>>(p, c.pair ? c.NT / 2 : c.NT, clips);
     ms_status ts = after_launch("convt_tail_kernel");
     if (ts != MS_OK) return ts;
