@@ -495,10 +495,10 @@ def main():
                 "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
                 "us_per_launch": us_stack,
                 # dram__bytes_read+write of this kernel from profiles/r02_ncu_stacks_summary.tsv
-                # (537.5 + 239.9 MB per 64-clip launch, scaled to this launch's clip count); the
-                # algorithmic bytes are 4C in + 2C out per row = 805 MB per 64 clips
-                "traffic": 777.4e6 * clips / 64,
-                "traffic_source": "ncu constant (dram__bytes_read+write of this kernel at 64 clips, "
+                # (2.155 + 1.045 GB per 256-clip launch of the CTA-pair kernel, scaled to this
+                # launch's clip count); the algorithmic bytes are 4C in + 2C out per row = 3.22 GB
+                "traffic": 3.2007e9 * clips / 256,
+                "traffic_source": "ncu constant (dram__bytes_read+write of this kernel at 256 clips, "
                                   "profiles/r02_ncu_stacks_summary.tsv), scaled by clip count; not "
                                   "measured in this run",
             },
