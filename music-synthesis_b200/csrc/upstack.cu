@@ -447,6 +447,73 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
             }
             wpos += (KIND == 0) ? 3 : 1;
           }
+          if (last && C == 64 && !mono) {
+            // Last stage at C = 64 (output = the next stage's 16-bit image in natural row order):
+            // each thread takes its lane's row of BOTH the E and the O block of this part for a
+            // quarter of the channels, so rows 2m and 2m + 1 leave as 32 contiguous bytes per
+            // channel chunk and a warp writes 1 KB runs.  (One block per thread meant 16-byte
+            // pieces at a 32-byte stride: this epilogue took twice as long as the others.)
+            if (!MSB_ABL(2)) {
+              const int cq = cpart * COLS + ms * 16;             // this thread's 16 channels
+              const int m = h * 128 + row0;                      // HE == 1
+              const int t = t0 + 2 * m;                          // even row; t + 1 is the odd one
+              float f[2][16];
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const uint32_t txr = tmem_base + lane_off + static_cast<uint32_t>((h * HB + r) * 2 * C + cq);
+                uint32_t v[16], xr[16];
+                tmem_ld16p(txr + C, v);
+                tmem_ld16p(txr, xr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float l0, l1;
+                  leaky02x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), l0, l1);
+                  add_x2(__uint_as_float(xr[j]), __uint_as_float(xr[j + 1]), l0, l1, f[r][j], f[r][j + 1]);
+                }
+                // seed the accumulator with the next tile's stage-0 bias
+                if (!MSB_ABL(8)) {
+                  const float4* b4 = reinterpret_cast<const float4*>(p.bias + cq);
+                  uint32_t bv[16];
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 t4 = __ldg(b4 + j4);
+                    bv[j4 * 4 + 0] = __float_as_uint(t4.x); bv[j4 * 4 + 1] = __float_as_uint(t4.y);
+                    bv[j4 * 4 + 2] = __float_as_uint(t4.z); bv[j4 * 4 + 3] = __float_as_uint(t4.w);
+                  }
+                  tmem_st16p(txr + C, bv);
+                }
+              }
+              // rows outside the clip are never stored (t, t + 1 are in or out together: L even)
+              const int trow = 2 * m;
+              if (t >= 0 && t < p.L && trow >= p.halo && trow < p.halo + p.V) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const size_t idx = (static_cast<size_t>(b) * G::NCH + (cq >> 3) + c) * p.L + t;
+                  if (p.y16 != nullptr) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.y16 + idx * 8);
+                    dst[0] = make_uint4(pack2u<BF>(f[0][c * 8 + 0], f[0][c * 8 + 1]),
+                                        pack2u<BF>(f[0][c * 8 + 2], f[0][c * 8 + 3]),
+                                        pack2u<BF>(f[0][c * 8 + 4], f[0][c * 8 + 5]),
+                                        pack2u<BF>(f[0][c * 8 + 6], f[0][c * 8 + 7]));
+                    dst[1] = make_uint4(pack2u<BF>(f[1][c * 8 + 0], f[1][c * 8 + 1]),
+                                        pack2u<BF>(f[1][c * 8 + 2], f[1][c * 8 + 3]),
+                                        pack2u<BF>(f[1][c * 8 + 4], f[1][c * 8 + 5]),
+                                        pack2u<BF>(f[1][c * 8 + 6], f[1][c * 8 + 7]));
+                  }
+                  if (p.y32 != nullptr) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                      const float o8[8] = {f[r][c * 8 + 0], f[r][c * 8 + 1], f[r][c * 8 + 2],
+                                           f[r][c * 8 + 3], f[r][c * 8 + 4], f[r][c * 8 + 5],
+                                           f[r][c * 8 + 6], f[r][c * 8 + 7]};
+                      st_global_v8(p.y32 + (idx + r) * 8, o8);
+                    }
+                  }
+                }
+              }
+            }
+          } else
 #pragma unroll
           for (int u = 0; u < IT; ++u) {
             if (MSB_ABL(2)) continue;
