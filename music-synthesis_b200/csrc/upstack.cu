@@ -447,7 +447,65 @@ __device__ __forceinline__ void upstack_body(const UpStackParams& p) {
             }
             wpos += (KIND == 0) ? 3 : 1;
           }
-          if (last && C == 64 && !mono) {
+          if (last && C == 32 && mono) {
+            // Last stage with the fused k7 tail (C = 32): each thread takes its lane's row of the
+            // E AND the O block (rows 2m, 2m + 1) of one block pair for its 16 channels: the tap
+            // weights are read once for both rows and the per-tap partial sums leave as 8-byte
+            // pairs (one row per thread meant stride-2 shared-memory writes and twice the reads).
+            if (!MSB_ABL(2)) {
+              const int m = (h * HE + ms) * 128 + row0;          // block pair kk = ms
+              const int trow = 2 * m;
+              float f[2][16];
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const int t = t0 + trow + r;
+                const uint32_t txr = tmem_base + lane_off +
+                                     static_cast<uint32_t>((h * HB + r * HE + ms) * 2 * C + cpart * COLS);
+                uint32_t v[16], xr[16];
+                tmem_ld16p(txr + C, v);
+                tmem_ld16p(txr, xr);
+                tmem_ld_wait();
+                const bool zero_row = edge && (t < 0 || t >= p.L);
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                  float l0, l1;
+                  leaky02x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), l0, l1);
+                  add_x2(__uint_as_float(xr[j]), __uint_as_float(xr[j + 1]), l0, l1, f[r][j], f[r][j + 1]);
+                  if (zero_row) { f[r][j] = 0.f; f[r][j + 1] = 0.f; }
+                }
+                if (!MSB_ABL(8)) {
+                  const float4* b4 = reinterpret_cast<const float4*>(p.bias + cpart * COLS);
+                  uint32_t bv[16];
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 t4 = __ldg(b4 + j4);
+                    bv[j4 * 4 + 0] = __float_as_uint(t4.x); bv[j4 * 4 + 1] = __float_as_uint(t4.y);
+                    bv[j4 * 4 + 2] = __float_as_uint(t4.z); bv[j4 * 4 + 3] = __float_as_uint(t4.w);
+                  }
+                  tmem_st16p(txr + C, bv);
+                }
+              }
+              float* P = sP + (cpart * 7) * R + trow;
+#pragma unroll
+              for (int k = 0; k < 7; ++k) {
+                float e0 = 0.f, e1 = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 w4 =
+                      *reinterpret_cast<const float4*>(sMono + k * 32 + cpart * COLS + j4 * 4);
+                  fma_x2(f[0][j4 * 4 + 0], f[0][j4 * 4 + 1], w4.x, w4.y, e0, e1);
+                  fma_x2(f[0][j4 * 4 + 2], f[0][j4 * 4 + 3], w4.z, w4.w, e0, e1);
+                  fma_x2(f[1][j4 * 4 + 0], f[1][j4 * 4 + 1], w4.x, w4.y, o0, o1);
+                  fma_x2(f[1][j4 * 4 + 2], f[1][j4 * 4 + 3], w4.z, w4.w, o0, o1);
+                }
+                *reinterpret_cast<float2*>(P + k * R) = make_float2(e0 + e1, o0 + o1);
+              }
+            }
+            if (h == 1) {      // keep act_half's phase in step (nobody waits on this arrival)
+              __syncwarp();
+              if (lane == 0) mbar_arrive(act_half);
+            }
+          } else if (last && C == 64 && !mono) {
             // Last stage at C = 64 (output = the next stage's 16-bit image in natural row order):
             // each thread takes its lane's row of BOTH the E and the O block of this part for a
             // quarter of the channels, so rows 2m and 2m + 1 leave as 32 contiguous bytes per
