@@ -44,6 +44,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
+        self.period_ms = os.environ.get("MSB_BENCH_SAMPLE_MS", "20")
         self.rows = []
         self.proc = None
 
@@ -51,7 +52,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", self.period_ms],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()

@@ -9,6 +9,9 @@
 // (+ one radix-2 / radix-4 pass for the odd bits of log2 n), real-input load, band cut-out,
 // Hermitian expansion and real-part store folded into the first / last pass of a transform:
 // n = 65536 is 4 passes and no boundary kernels instead of 8 radix-4 passes + 3 copies.
+// Two passes per launch (default; MSB_FFT_FUSE=0: one): the first two passes of a transform and
+// every following pair of radix-16 passes exchange through shared memory inside one kernel, so
+// a half-length transform of 32768 points reads and writes HBM twice instead of four times.
 // Real-input packing: a real sequence of length 2h runs as the h-point complex transform of
 // x[2m] + i x[2m+1]; the band cut-out builds the packed inverse input straight from the packed
 // forward output (MSB_FFT_PACKED=0: full-length complex transforms).
@@ -202,6 +205,72 @@ __global__ void __launch_bounds__(256) fft_pass16_first_kernel(const fftb::PassA
   }
 }
 
+// Two passes per launch (fft_passes.cuh, "two passes in one launch"): 16 groups of G = 16 R1
+// points per CTA, thread (hi, gl) = (tid / 16, tid % 16) works on group gl, so that for every
+// load / store instruction 16 neighbouring lanes touch one contiguous 128-byte run (groups are
+// adjacent in g, and in k1 for the stores when p >= 16).  STAGED (p = 1): a group's outputs are
+// G consecutive elements, the CTA's 16 G outputs one contiguous run -- they go back through the
+// exchange buffer and are stored in order.
+template <int R1, bool STAGED, int LD>
+__global__ void __launch_bounds__(256) fft_pass2x_kernel(const fftb::PassArgs a, const int store) {
+  constexpr int G = 16 * R1;
+  constexpr int GP = fftb::kExPitch * R1 + 1;     // float2 per group: word pitch = 2 mod 4
+  __shared__ float2 ex[16 * GP];
+  const int tid = threadIdx.x, gl = tid & 15, hi = tid >> 4;
+  const size_t group = blockIdx.x * static_cast<size_t>(16) + gl;
+  const bool valid = group < a.total;
+  if (valid) fftb::fused_first_half<R1, LD>(a, group, hi, ex + gl * GP);
+  __syncthreads();
+  const bool act = valid && hi < R1;
+  float re[16], im[16];
+  size_t o = 0;
+  if (act) fftb::fused_second_half<R1>(a, group, hi, ex + gl * GP, re, im, o);
+  if (!STAGED) {
+    if (act) {
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        fftb::store_any(a.y, store, o + static_cast<size_t>(hi + R1 * m) * a.p, re[m], im[m]);
+    }
+    return;
+  }
+  __syncthreads();
+  if (act) {
+#pragma unroll
+    for (int m = 0; m < 16; ++m) ex[gl * GP + hi + R1 * m] = make_float2(re[m], im[m]);
+  }
+  __syncthreads();
+  const size_t first = blockIdx.x * static_cast<size_t>(16);
+  const size_t left = a.total - first;
+  const int count = (left < 16 ? static_cast<int>(left) : 16) * G;
+  for (int i = tid; i < count; i += 256) {
+    const float2 v = ex[(i / G) * GP + (i % G)];
+    fftb::store_any(a.y, store, first * G + i, v.x, v.y);
+  }
+}
+
+// special loaders only occur in the first pass of a transform (p = 1: the staged form)
+static int launch_pass2x(int r1, int load, int store, const fftb::PassArgs& a, cudaStream_t st) {
+  const unsigned grid = static_cast<unsigned>((a.total + 15) / 16);
+  if (a.p > 1 && load != fftb::kLoadComplex) return MS_ERR_INVALID;
+  return fftb::dispatch_fused(r1, load, [&](auto r, auto ld) -> int {
+    constexpr int R1 = decltype(r)::value;
+    if (a.p == 1)
+      fft_pass2x_kernel<R1, true, decltype(ld)::value><<<grid, 256, 0, st>>>(a, store);
+    else
+      fft_pass2x_kernel<R1, false, fftb::kLoadComplex><<<grid, 256, 0, st>>>(a, store);
+    return after_launch("fft_pass2x_kernel");
+  });
+}
+
+// tw[j] = exp(-i pi j / h), 0 <= j <= h (PassArgs::tw)
+__global__ void fft_twiddle_table_kernel(float2* __restrict__ tw, int h) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > h) return;
+  float s, c;
+  sincospif(-static_cast<float>(j) / static_cast<float>(h), &s, &c);
+  tw[j] = make_float2(c, s);
+}
+
 static bool env_flag(const char* name, bool dflt) {
   const char* e = getenv(name);
   if (e == nullptr || e[0] == 0) return dflt;
@@ -212,7 +281,13 @@ static bool env_flag(const char* name, bool dflt) {
 struct PassLauncher {
   cudaStream_t st;
   bool staged;
-  explicit PassLauncher(cudaStream_t s) : st(s), staged(env_flag("MSB_FFT_STAGED", true)) {}
+  bool fuse;         // MSB_FFT_FUSE=0: one pass per launch
+  explicit PassLauncher(cudaStream_t s)
+      : st(s), staged(env_flag("MSB_FFT_STAGED", true)), fuse(env_flag("MSB_FFT_FUSE", true)) {}
+  bool fuses() const { return fuse; }
+  int fused(int r1, int load, int store, const fftb::PassArgs& a) const {
+    return launch_pass2x(r1, load, store, a, st);
+  }
   int operator()(int radix, int load, int store, const fftb::PassArgs& a) const {
     const unsigned grid = static_cast<unsigned>((a.total + 255) / 256);
     if (staged && radix == 16 && a.p == 1 && store == fftb::kStoreComplex &&
@@ -258,6 +333,11 @@ __global__ void accumulate_band_packed_kernel(const float2* __restrict__ zs,
   if (gid < total) fftb::accumulate_one_packed(zs, acc, S, D, lo, scale, first, gid);
 }
 
+inline ms_status twiddle_table(float2* tw, int h, cudaStream_t st) {
+  fft_twiddle_table_kernel<<<(h + 256) / 256, 256, 0, st>>>(tw, h);
+  return after_launch("fft_twiddle_table_kernel");
+}
+
 inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 inline unsigned nblk(size_t total) { return static_cast<unsigned>((total + 255) / 256); }
@@ -272,7 +352,9 @@ extern "C" {
 size_t ms_fft_bands_workspace_bytes(int batch, int n) {
   if (batch <= 0 || n <= 0) return 0;
   // coefficient buffer + two ping-pong transform buffers (complex, full length)
-  return 3 * static_cast<size_t>(batch) * n * sizeof(float2) + 1024;
+  // + the twiddle table of the packed loaders (n / 2 + 1 entries)
+  return 3 * static_cast<size_t>(batch) * n * sizeof(float2) +
+         (static_cast<size_t>(n) / 2 + 1) * sizeof(float2) + 1024;
 }
 
 ms_status ms_fft_frequency_decompose(const float* x, int batch, int n, int min_size,
@@ -295,9 +377,16 @@ ms_status ms_fft_frequency_decompose(const float* x, int batch, int n, int min_s
     // real-input packing (half-length transforms) needs 8-byte aligned rows: float2 accesses
     bool packed = env_flag("MSB_FFT_PACKED", true) && aligned8(x);
     for (int i = 0; i < nbands; ++i) packed = packed && aligned8(bands_out[i]);
-    if (packed)
+    if (packed) {
+      const float2* tw = nullptr;
+      if (env_flag("MSB_FFT_TABLE", true)) {
+        ms_status ts = twiddle_table(w1 + bn, n / 2, st);
+        if (ts != MS_OK) return ts;
+        tw = w1 + bn;
+      }
       return static_cast<ms_status>(fftb::decompose_packed(x, batch, n, min_size, bands_out, coef,
-                                                           w0, w1, PassLauncher(st)));
+                                                           w0, w1, PassLauncher(st), tw, n / 2));
+    }
     return static_cast<ms_status>(
         fftb::decompose(x, batch, n, min_size, bands_out, coef, w0, w1, PassLauncher(st)));
   }
@@ -356,11 +445,17 @@ ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes
     };
     bool packed = env_flag("MSB_FFT_PACKED", true) && aligned8(out);
     for (int i = 0; i < nbands; ++i) packed = packed && aligned8(bands[i]);
+    const float2* tw = nullptr;
+    if (packed && env_flag("MSB_FFT_TABLE", true)) {
+      s = twiddle_table(w1 + bd, D / 2, st);
+      if (s != MS_OK) return s;
+      tw = w1 + bd;
+    }
     if (packed && env_flag("MSB_FFT_MERGE_GATHER", true)) {
       // the bands' packed spectra are kept side by side in the first workspace region and the
       // inverse transform gathers from them while loading: no accumulation passes
       const int rc = fftb::recompose_merged(bands, sizes, nbands, batch, D, out, acc, w0, w1,
-                                            PassLauncher(st));
+                                            PassLauncher(st), tw, D / 2);
       if (rc != -2) return static_cast<ms_status>(rc);
     }
     if (packed) {
@@ -372,7 +467,7 @@ ms_status ms_fft_frequency_recompose(const float* const* bands, const int* sizes
       };
       return static_cast<ms_status>(fftb::recompose_packed(bands, sizes, nbands, batch, D, out,
                                                            acc, w0, w1, PassLauncher(st),
-                                                           accum_pk));
+                                                           accum_pk, tw, D / 2));
     }
     return static_cast<ms_status>(fftb::recompose(bands, sizes, nbands, batch, D, out, acc, w0,
                                                   w1, PassLauncher(st), accum));

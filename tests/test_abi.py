@@ -170,7 +170,7 @@ def test_audio2mel_fft_passes_on_host(tmp_path):
 
 @pytest.mark.parametrize("batch,n,min_size", [(2, 65536, 4096), (2, 8192, 256), (3, 2048, 16),
                                               (1, 32768, 1024), (1, 16, 16), (1, 8, 4)])
-@pytest.mark.parametrize("packed", [2, 1, 0])
+@pytest.mark.parametrize("packed", [3, 2, 1, 0])
 def test_fft_band_passes_on_host(tmp_path, batch, n, min_size, packed):
     """csrc/fft_passes.cuh (radix-2/4/16 Stockham passes with fused boundary loads / stores, the
     pass plan and the decompose / recompose sequences of fft_bands.cu, with real-input packing
@@ -194,8 +194,9 @@ def test_fft_band_passes_on_host(tmp_path, batch, n, min_size, packed):
     x = (np.random.RandomState(n + batch).randn(batch, n) * 0.1).astype(np.float32)
     fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     x.tofile(fin)
-    # packed: 2 = what the library runs (real-input packing, merge gathered by the inverse
-    # transform's loader), 1 = packing with accumulation passes, 0 = full-length transforms
+    # packed: 3 = what the library runs (real-input packing, merge gathered by the inverse
+    # transform's loader, two passes per launch), 2 = the same with one pass per launch,
+    # 1 = packing with accumulation passes, 0 = full-length transforms
     r = subprocess.run([exe, fin, fout, str(batch), str(n), str(min_size), str(packed)],
                        stderr=subprocess.DEVNULL)
     assert r.returncode == 0

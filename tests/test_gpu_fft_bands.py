@@ -63,9 +63,11 @@ def test_multiscale_representation_matches_golden(golden):
     assert RawAudio.from_audio(x, 22050).to_audio().shape == (2, 8192)
 
 
-@pytest.mark.parametrize("knob", ["MSB_FFT_STAGED=0", "MSB_FFT_MERGE_GATHER=0", "MSB_FFT_PACKED=0", "MSB_FFT_LEGACY=1"])
+@pytest.mark.parametrize("knob", ["MSB_FFT_FUSE=0", "MSB_FFT_TABLE=0", "MSB_FFT_STAGED=0", "MSB_FFT_MERGE_GATHER=0", "MSB_FFT_PACKED=0", "MSB_FFT_LEGACY=1"])
 def test_pass_variants_agree(monkeypatch, knob):
-    """The library reads its knobs per call: the first radix-16 pass with direct stores
+    """The library reads its knobs per call: one pass per launch (MSB_FFT_FUSE=0) agrees with the
+    default two passes per launch to rounding; twiddles computed in the loaders (MSB_FFT_TABLE=0)
+    are the same bits as the per-call table; the first radix-16 pass with direct stores
     (MSB_FFT_STAGED=0) is bit-identical to the shared-memory staged one; full-length complex
     transforms (MSB_FFT_PACKED=0) and the first-version radix-4 path (MSB_FFT_LEGACY=1) agree
     with the default real-packed half-length transforms to rounding."""
@@ -78,7 +80,7 @@ def test_pass_variants_agree(monkeypatch, knob):
     b = fft_frequency_decompose(x, 4096)
     rb = fft_frequency_recompose(b, 65536)
     for k in a:
-        if name == "MSB_FFT_STAGED":
+        if name in ("MSB_FFT_STAGED", "MSB_FFT_TABLE"):
             assert torch.equal(a[k], b[k])
         else:
             assert rel_l2(a[k], b[k]) < 3e-6

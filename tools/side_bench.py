@@ -24,7 +24,8 @@ try:
     PEAK_HBM = float(PEAK_HBM.get("hbm_gbps", PEAK_HBM.get("hbm_gbs", 6536.7))) * 1e9
 except Exception:
     PEAK_HBM = 6536.7e9
-KNOBS = ("MSB_A2M_RADIX4", "MSB_FFT_LEGACY", "MSB_FFT_STAGED", "MSB_FFT_PACKED", "MSB_FFT_MERGE_GATHER")
+KNOBS = ("MSB_A2M_RADIX4", "MSB_FFT_LEGACY", "MSB_FFT_STAGED", "MSB_FFT_PACKED", "MSB_FFT_MERGE_GATHER",
+         "MSB_FFT_FUSE", "MSB_FFT_TABLE")
 
 
 def timeit(fn, n=20, warm=3):
@@ -96,6 +97,8 @@ def feed_rows():
 feed_rows()
 # the library reads the knobs per call: default (new kernels), then the A/B settings
 run({})
+run({"MSB_FFT_FUSE": "0"})
+run({"MSB_FFT_TABLE": "0"})
 run({"MSB_FFT_MERGE_GATHER": "0"})
 run({"MSB_FFT_PACKED": "0"})
 run({"MSB_FFT_STAGED": "0"})
