@@ -46,6 +46,11 @@ struct BandTable {        // kLoadMergePk: band b = rows of size[b]/2 float2 at 
   int lo[kMaxBands];
   float scale[kMaxBands];
   long long offset[kMaxBands];
+  // which bands can keep bin k without walking the list: the band whose half-length is the power
+  // of two at or above k (keeps [hb/2, hb]), the next one up when k is a power of two (k is its
+  // lowest kept bin), and the smallest band (keeps [0, hb]).  by_log[L] = band with hb = 2^L or -1.
+  int by_log[32];
+  int smallest;
 };
 enum Store { kStoreComplex = 0, kStoreReal = 1, kStoreConj = 2 };
 
@@ -73,6 +78,17 @@ A2M_HD int ilog2(int v) {
 #else
   int l = 0;
   while ((1 << l) < v) ++l;
+  return l;
+#endif
+}
+
+// smallest L with 2^L >= k, k >= 1
+A2M_HD int ceil_log2(int k) {
+#ifdef __CUDA_ARCH__
+  return 32 - __clz(k - 1);
+#else
+  int l = 0;
+  while ((1 << l) < k) ++l;
   return l;
 #endif
 }
@@ -229,13 +245,27 @@ A2M_HD void load_one(const PassArgs& a, size_t row, int idx, float& re, float& i
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int k = e == 0 ? idx : H - idx;
-      float yr = 0.f, yi = 0.f;
-      for (int b = 0; b < a.bands.count; ++b) {
-        const int hb = a.bands.size[b] >> 1;
-        if (k >= a.bands.lo[b] && k <= hb) {
-          const float2 x = real_bin(a, base + a.bands.offset[b] + row * hb, hb, k);
-          yr += x.x * a.bands.scale[b];
-          yi += x.y * a.bands.scale[b];
+      // primary band: half-length = the power of two at or above k (k lies in its kept upper
+      // half), else the smallest band when k is inside it; un-tangled without a branch (scale 0
+      // and a safe address when no band keeps the bin)
+      const int L = k > 0 ? ceil_log2(k) : 0;
+      const int sm = a.bands.smallest;
+      int p = k > 0 ? a.bands.by_log[L] : -1;
+      if (p < 0 && k <= (a.bands.size[sm] >> 1)) p = sm;
+      const int pb = p < 0 ? sm : p;
+      const int hb = a.bands.size[pb] >> 1;
+      const float sc = p < 0 ? 0.f : a.bands.scale[pb];
+      const float2 x = real_bin(a, base + a.bands.offset[pb] + row * hb, hb, p < 0 ? 0 : k);
+      float yr = x.x * sc, yi = x.y * sc;
+      if (k > 0 && (k & (k - 1)) == 0) {
+        // a power of two is also the lowest kept bin of the next band up (the reference's
+        // double-counted boundary bins): a handful of bins per row
+        const int b2 = a.bands.by_log[L + 1];
+        if (b2 >= 0 && b2 != p && k >= a.bands.lo[b2]) {
+          const int h2 = a.bands.size[b2] >> 1;
+          const float2 x2 = real_bin(a, base + a.bands.offset[b2] + row * h2, h2, k);
+          yr += x2.x * a.bands.scale[b2];
+          yi += x2.y * a.bands.scale[b2];
         }
       }
       y[e] = make_float2(yr, (k == 0 || k == H) ? 0.f : yi);
@@ -639,6 +669,14 @@ int recompose_merged(const float* const* bands, const int* sizes, int nbands, in
   if (total > D) return -2;
   BandTable t;
   t.count = nbands;
+  for (int l = 0; l < 32; ++l) t.by_log[l] = -1;
+  t.smallest = 0;
+  for (int i = 0; i < nbands; ++i) {
+    const int l = ilog2(sizes[i] / 2);
+    if (sizes[i] < 4 || t.by_log[l] >= 0) return -2;     // the lookup needs distinct sizes
+    t.by_log[l] = i;
+    if (sizes[i] < sizes[t.smallest]) t.smallest = i;
+  }
   long long off = 0;
   for (int i = 0; i < nbands; ++i) {
     const int S = sizes[i];

@@ -42,6 +42,18 @@ def test_bands_match_oracle(B, N, min_size):
         assert rel_l2(gxy[k], got[k] + 2 * gy[k]) < 5e-6
 
 
+def test_merge_of_a_sparse_set_of_bands():
+    """fft_frequency_recompose takes any dictionary of bands (audio/transform.py:85-115): sizes
+    with gaps between them, smaller than the output, in any order -- the merge loader's band
+    lookup must keep exactly the bins the reference keeps."""
+    from music_synthesis_b200.audio.transform import fft_frequency_recompose
+    for sizes, N in (((256, 1024, 4096), 8192), ((2048, 64), 2048), ((512,), 4096)):
+        bands = {s: synth.randn(60 + s % 7, 3, 1, s) * 0.1 for s in sizes}
+        want = restate.fft_frequency_recompose(bands, N)
+        got = fft_frequency_recompose({s: v.cuda() for s, v in bands.items()}, N)
+        assert rel_l2(got, want) < 5e-6, (sizes, N)
+
+
 def test_multiscale_representation_matches_golden(golden):
     """`MultiScale.from_audio / to_audio` (audio/representation.py:82-103)
     on the GPU.  The reference's MultiScale run on this input reproduces the fft_bands_n8192
