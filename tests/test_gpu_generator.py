@@ -9,6 +9,7 @@ import torch
 
 from oracle import restate, synth
 from tests.gpu_util import rel_l2
+from music_synthesis_b200._lib import MsbError
 
 pytestmark = pytest.mark.gpu
 
@@ -156,6 +157,41 @@ def test_generate_host_pipeline_matches_forward():
     assert got.shape == ref.shape and torch.equal(got, ref)
     got2 = m.generate(x, chunk_clips=64)          # pageable input, single chunk
     assert torch.equal(got2, ref)
+    got3 = m.generate(x.pin_memory(), chunks=[1, 4, 2])     # explicit chunk sizes
+    assert torch.equal(got3, ref)
+    with pytest.raises(MsbError):
+        m.generate(x, chunks=[3, 3])
+
+
+def test_generate_sees_every_kind_of_weight_change():
+    """generate() checks the packed weights against the Parameter objects of the previous call
+    before its first kernel and walks the module tree only while the GPU works: an in-place
+    update, a load_state_dict and a REPLACED Parameter object must all reach the output."""
+    m = _module(restate.melgan_generator_state(9))
+    x = synth.mel_features(10, 5, 12)
+    xp = x.pin_memory()
+
+    def both():
+        with torch.no_grad():
+            ref = m(x.cuda()).cpu()
+        return ref, m.generate(xp, chunk_clips=2, edge_clips=1)
+
+    ref0, got0 = both()
+    assert torch.equal(got0, ref0)
+    with torch.no_grad():
+        m.main[15].bias.add_(0.25)                                  # in place: version bump
+    got1 = m.generate(xp, chunk_clips=2, edge_clips=1)
+    assert not torch.equal(got1, got0)
+    with torch.no_grad():
+        assert torch.equal(got1, m(x.cuda()).cpu())
+    m.main[15].bias = torch.nn.Parameter(m.main[15].bias.detach() - 0.5)   # new Parameter object
+    got2 = m.generate(xp, chunk_clips=2, edge_clips=1)              # before any forward() call
+    with torch.no_grad():
+        ref2 = m(x.cuda()).cpu()
+    assert torch.equal(got2, ref2) and not torch.equal(got2, got1)
+    m.load_state_dict(restate.melgan_generator_state(11))
+    ref3, got3 = both()
+    assert torch.equal(got3, ref3) and not torch.equal(got3, got2)
 
 
 def test_generator_full_size_config3_properties():
