@@ -32,12 +32,17 @@ struct A2MParams {
 // Shared tail of both kernels: untangle the two real spectra packed in each complex transform
 // (transform j: re plane zr + j * zstride, im plane zi + j * zstride, natural order), take
 // magnitudes, project onto the mel basis, log10(clamp).
+// BINS > 0: compile-time bin count (the index split of the un-tangling loop becomes a multiply)
+template <int BINS = 0>
 __device__ __forceinline__ void a2m_tail(const A2MParams& p, const float* zr, const float* zi,
                                          const int zstride, float* mag, float* tile, const int n,
                                          const int b, const int f0) {
   const int tid = threadIdx.x;
-  const int bins = p.bins;
-  const int magld = bins + 3;
+  const int bins = BINS > 0 ? BINS : p.bins;
+  // magnitudes as mag4[gh][k] = frames 4 gh .. 4 gh + 3 of bin k: the projection reads one
+  // 16-byte vector per bin (quarter-warp wavefronts: the rows' different start bins no longer
+  // collide on banks) instead of four scalars
+  float4* mag4 = reinterpret_cast<float4*>(mag);
   // untangle the two real spectra of each complex transform, take magnitudes
   for (int i = tid; i < 4 * bins; i += kA2MThreads) {
     const int j = i / bins;
@@ -47,8 +52,9 @@ __device__ __forceinline__ void a2m_tail(const A2MParams& p, const float* zr, co
     const float br = zr[j * zstride + kn], bi = zi[j * zstride + kn];
     const float xar = 0.5f * (ar + br), xai = 0.5f * (ai - bi);
     const float xbr = 0.5f * (ai + bi), xbi = -0.5f * (ar - br);
-    mag[(2 * j) * magld + k] = sqrtf(xar * xar + xai * xai);
-    mag[(2 * j + 1) * magld + k] = sqrtf(xbr * xbr + xbi * xbi);
+    // frames 2j, 2j+1 = slots 2 (j & 1), 2 (j & 1) + 1 of group j >> 1
+    reinterpret_cast<float2*>(mag4 + (j >> 1) * bins + k)[j & 1] =
+        make_float2(sqrtf(xar * xar + xai * xai), sqrtf(xbr * xbr + xbi * xbi));
   }
   __syncthreads();
   // mel projection: thread (m, gh) accumulates frames gh*4 .. gh*4+3 of mel row m
@@ -62,14 +68,15 @@ __device__ __forceinline__ void a2m_tail(const A2MParams& p, const float* zr, co
       if (m >= p.n_mels) continue;
       const int2 r = __ldg(p.ranges + m);
       const float* brow = p.basis + static_cast<size_t>(m) * bins;
-      const float* mg = mag + (gh * 4) * magld;
+      const float4* mg = mag4 + gh * bins;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int k = r.x; k < r.y; ++k) {
         const float w = __ldg(brow + k);
-        acc[0] = fmaf(w, mg[k], acc[0]);
-        acc[1] = fmaf(w, mg[magld + k], acc[1]);
-        acc[2] = fmaf(w, mg[2 * magld + k], acc[2]);
-        acc[3] = fmaf(w, mg[3 * magld + k], acc[3]);
+        const float4 v = mg[k];
+        acc[0] = fmaf(w, v.x, acc[0]);
+        acc[1] = fmaf(w, v.y, acc[1]);
+        acc[2] = fmaf(w, v.z, acc[2]);
+        acc[3] = fmaf(w, v.w, acc[3]);
       }
       float* o = p.out + (static_cast<size_t>(b) * p.n_mels + m) * p.F;
 #pragma unroll
@@ -92,13 +99,14 @@ __device__ __forceinline__ void a2m_tail(const A2MParams& p, const float* zr, co
       }
       __syncthreads();
       const int kmax = (bins - k0) < 32 ? (bins - k0) : 32;
-      const float* mg = mag + (gh * 4) * magld + k0;
+      const float4* mg = mag4 + gh * bins + k0;
       for (int kk = 0; kk < kmax; ++kk) {
         const float w = tile[ml * 33 + kk];
-        acc[0] = fmaf(w, mg[kk], acc[0]);
-        acc[1] = fmaf(w, mg[magld + kk], acc[1]);
-        acc[2] = fmaf(w, mg[2 * magld + kk], acc[2]);
-        acc[3] = fmaf(w, mg[3 * magld + kk], acc[3]);
+        const float4 v = mg[kk];
+        acc[0] = fmaf(w, v.x, acc[0]);
+        acc[1] = fmaf(w, v.y, acc[1]);
+        acc[2] = fmaf(w, v.z, acc[2]);
+        acc[3] = fmaf(w, v.w, acc[3]);
       }
       __syncthreads();
     }
@@ -269,11 +277,15 @@ audio2mel_r16_kernel(const A2MParams p) {
     const long long sa = static_cast<long long>(fa) * p.hop + t;
     const long long sb = sa + p.hop;
     const bool oka = fa < p.F, okb = fa + 1 < p.F;
+    // samples left in the clip from each frame's first sample (<= 0: the whole frame is padding)
+    const long long la = oka ? p.N - sa : 0, lb = okb ? p.N - sb : 0;
+    const int lefta = la > 1024 ? 1024 : static_cast<int>(la > 0 ? la : 0);
+    const int leftb = lb > 1024 ? 1024 : static_cast<int>(lb > 0 ? lb : 0);
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const float w = __ldg(p.window + 64 * q + t);
-      const float va = (oka && sa + 64 * q < p.N) ? __ldg(a + sa + 64 * q) : 0.f;
-      const float vb = (okb && sb + 64 * q < p.N) ? __ldg(a + sb + 64 * q) : 0.f;
+      const float va = (64 * q < lefta) ? __ldg(a + sa + 64 * q) : 0.f;
+      const float vb = (64 * q < leftb) ? __ldg(a + sb + 64 * q) : 0.f;
       re[q] = va * w;
       im[q] = vb * w;
     }
@@ -289,7 +301,7 @@ audio2mel_r16_kernel(const A2MParams p) {
     a2m::pass_c_write(t, re, im, sr, si);
   }
   __syncthreads();
-  a2m_tail(p, zr, zi, a2m::kPlane, mag, zr, a2m::kN, b, f0);
+  a2m_tail<a2m::kN / 2 + 1>(p, zr, zi, a2m::kPlane, mag, zr, a2m::kN, b, f0);
 }
 
 }  // namespace msb
