@@ -6,6 +6,8 @@
 // reference), only the data movement happens here: one launch per feature, coalesced reads of
 // the store, coalesced writes of the (B, channels, len) batch.  HBM-bound:
 // 2 * 4 * B * channels * len bytes.
+#include <cstdint>
+
 #include "runtime.cuh"
 
 namespace msb {
@@ -32,6 +34,28 @@ __global__ void __launch_bounds__(256) gather_crops_kernel(const CropArgs a) {
   a.out[(static_cast<size_t>(b) * a.channels + c) * a.len + t] = v;
 }
 
+// len % 4 == 0: four consecutive time steps per thread -- four independent loads in flight (the
+// crop origin is arbitrary, so the reads stay scalar) and one 16-byte store; the index split is
+// done in units of 4 samples.  (One element per thread reached 33 % of the HBM copy rate.)
+__global__ void __launch_bounds__(256) gather_crops4_kernel(const CropArgs a) {
+  const int b = blockIdx.y;
+  const int len4 = a.len >> 2;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= a.channels * len4) return;
+  const int c = i / len4;
+  const int t = (i - c * len4) << 2;
+  const long long origin = __ldg(a.plan + 3 * b);
+  const long long pitch = __ldg(a.plan + 3 * b + 1);
+  const long long valid = __ldg(a.plan + 3 * b + 2);
+  const float* src = a.store + origin + c * pitch + t;
+  float4 v;
+  v.x = t + 0 < valid ? __ldg(src + 0) : 0.f;
+  v.y = t + 1 < valid ? __ldg(src + 1) : 0.f;
+  v.z = t + 2 < valid ? __ldg(src + 2) : 0.f;
+  v.w = t + 3 < valid ? __ldg(src + 3) : 0.f;
+  *reinterpret_cast<float4*>(a.out + (static_cast<size_t>(b) * a.channels + c) * a.len + t) = v;
+}
+
 }  // namespace msb
 
 using namespace msb;
@@ -45,6 +69,11 @@ ms_status ms_gather_crops(const float* store, const long long* plan, float* out,
     return MS_ERR_INVALID;
   CropArgs a;
   a.store = store; a.plan = plan; a.out = out; a.channels = channels; a.len = len;
+  if ((len & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const dim3 grid4((channels * (len >> 2) + 255) / 256, batch);
+    gather_crops4_kernel<<<grid4, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return after_launch("gather_crops4_kernel");
+  }
   const dim3 grid((channels * len + 255) / 256, batch);
   gather_crops_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return after_launch("gather_crops_kernel");

@@ -43,6 +43,13 @@ def test_store_computes_log_mel_on_the_gpu_and_ranks_draw_different_crops():
         a, s = next(stream)
         assert np.array_equal(a.cpu().numpy(), ref[i][0])
         assert np.array_equal(s.cpu().numpy(), ref[i][1])
+    # 9 frames: an odd crop length takes the one-sample-per-thread kernel, its 2304 audio samples
+    # the four-per-thread one
+    odd = {"audio": (2304, 1), "spectrogram": (9, 128)}
+    ref_odd = restate.batch_stream(chunks, full, 5, odd, "spectrogram", 4, 1)
+    a, s = next(batch_stream(store, 5, odd, "spectrogram", seed=4))
+    assert np.array_equal(a.cpu().numpy(), ref_odd[0][0])
+    assert np.array_equal(s.cpu().numpy(), ref_odd[0][1])
     other = next(batch_stream(store, 16, spec, "spectrogram", seed=3, rank=1))
     assert not np.array_equal(other[0].cpu().numpy(), ref[0][0])
     # peak normalisation of `audio()` (feature/feature.py:67)
